@@ -1,0 +1,237 @@
+/*
+ * portcullis_junc.h — C ABI of the B200-native `junc` hot path.
+ *
+ * This is the drop-in boundary for Portcullis' junction-building pass.  The reference has no
+ * plugin / FFI interface for this path; its inner seam is
+ *
+ *     void JunctionBuilder::findJuncs(BamReader&, GenomeMapper&, int32_t seq)
+ *         -> results[seq] (RegionResult)            /root/reference/src/junction_builder.cc:314-357
+ *                                                    /root/reference/src/junction_builder.hpp:72-80
+ *
+ * followed by the merge / sort / index / group statistics of
+ *
+ *     JunctionBuilder::findJunctions()               /root/reference/src/junction_builder.cc:228-291
+ *     JunctionSystem::calcJunctionStats()            /root/reference/lib/src/junction_system.cc:250-320
+ *
+ * The entry points below are what a maintainer of the reference would bind in place of that seam
+ * (see INTEGRATION.md for the C++ stub).  Plain pointers and sizes only; no exceptions cross the
+ * boundary; every call returns 0 on success and a negative PJ_E* code on failure, with a message
+ * available from pj_last_error().
+ *
+ * Threading: a pj_ctx is bound to ONE CUDA device and must be driven by one host thread at a
+ * time.  Create one context per GPU (targets are independent, so shards need no exchange).
+ */
+#ifndef PORTCULLIS_JUNC_H
+#define PORTCULLIS_JUNC_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PJ_ABI_VERSION 1
+
+/* status codes */
+#define PJ_OK            0
+#define PJ_EINVAL       -1   /* bad argument / malformed input                         */
+#define PJ_ECUDA        -2   /* CUDA runtime error (fatal: there is no CPU fallback)   */
+#define PJ_ENOMEM       -3
+#define PJ_ESTATE       -4   /* call sequence violated                                 */
+#define PJ_EDATA        -5   /* input the reference itself aborts on (see Q6/Q12)      */
+#define PJ_EIO          -6
+
+/* Orientation, same order as portcullis::bam::Orientation
+ * (/root/reference/lib/include/portcullis/bam/bam_master.hpp:141-147) */
+enum { PJ_ORIENT_SE = 0, PJ_ORIENT_FR = 1, PJ_ORIENT_RF = 2, PJ_ORIENT_FF = 3, PJ_ORIENT_UNKNOWN = 4 };
+
+/* Strand, same order as portcullis::bam::Strand (bam_master.hpp:50-54) */
+enum { PJ_STRAND_POS = 0, PJ_STRAND_NEG = 1, PJ_STRAND_UNKNOWN = 2 };
+
+/* MAPQ threshold for "uniquely mapped" (/root/reference/lib/include/portcullis/junction.hpp:65) */
+#define PJ_MAP_QUALITY_THRESHOLD 30
+#define PJ_NB_JAD 20
+
+typedef struct pj_ctx pj_ctx;
+
+typedef struct pj_config {
+    int32_t device;        /* CUDA device ordinal                                              */
+    int32_t orientation;   /* PJ_ORIENT_*; only FR/RF/FF enable the portcullis proper-pair rule */
+    int32_t reserved[6];
+} pj_config;
+
+/*
+ * A columnar batch of alignment records, in BAM (coordinate) order.  This replaces the stream of
+ * bam1_t records that BamReader::next() hands to findJuncs (/root/reference/lib/src/bam_reader.cc:134-138,
+ * record layout /root/reference/deps/htslib-1.3/htslib/sam.h:148-181).  Only the fields the path
+ * reads are carried.  Records of several targets may share a batch; tid must be non-decreasing and
+ * pos non-decreasing within a tid across the whole shard.
+ *
+ *   xs        : 0 when the record has no XS tag, otherwise the XS:A character ('+','-','?','.').
+ *   cigar     : raw BAM CIGAR words (len<<4 | op), op index into "MIDNSHP=XB".
+ *   cigar_off : n_records+1 prefix offsets into cigar[] (in words).
+ *   seq4      : BAM 4-bit packed SEQ (high nibble first), each record starting on a byte boundary.
+ *               Records without an N operation may omit their SEQ (seq_off[i+1]==seq_off[i]).
+ *   seq_off   : n_records+1 prefix offsets into seq4[] (in bytes).
+ */
+typedef struct pj_batch {
+    int64_t         n_records;
+    const int32_t*  tid;
+    const int32_t*  pos;
+    const uint16_t* flag;
+    const uint8_t*  mapq;
+    const uint8_t*  xs;
+    const int32_t*  l_qseq;
+    const int32_t*  mtid;
+    const int32_t*  mpos;
+    const uint32_t* cigar_off;
+    const uint32_t* cigar;
+    const uint64_t* seq_off;
+    const uint8_t*  seq4;
+} pj_batch;
+
+/* Per-target scalars: RegionResult minus the junction system
+ * (/root/reference/src/junction_builder.hpp:72-80, filled at junction_builder.cc:352-356). */
+typedef struct pj_target_stats {
+    uint64_t spliced_count;
+    uint64_t unspliced_count;
+    uint64_t sum_query_lengths;
+    int32_t  min_query_length;    /* INT32_MAX when the target has no records */
+    int32_t  max_query_length;
+} pj_target_stats;
+
+/*
+ * One junction row.  The first block is produced on the GPU; the block marked "host finalize" is
+ * filled by pj_junctions_finalize() over the merged, sorted list (A12/A13: it needs every shard).
+ * Field names follow the junctions.tab columns (/root/reference/lib/src/junction.cc:50-115).
+ */
+typedef struct pj_junction {
+    int32_t  tid;
+    int32_t  start;              /* intron start, 0-based inclusive */
+    int32_t  end;                /* intron end,   0-based inclusive */
+    int32_t  left;               /* leftAncStart  */
+    int32_t  right;              /* rightAncEnd   */
+    uint32_t nb_raw_aln;
+    uint32_t nb_dist_aln;
+    uint32_t nb_ms_aln;
+    uint32_t nb_um_aln;
+    uint32_t nb_bpp_aln;
+    uint32_t nb_ppp_aln;
+    uint32_t nb_rel_aln;
+    uint32_t nb_r1_pos;
+    uint32_t nb_r1_neg;
+    uint32_t nb_r2_pos;
+    uint32_t nb_r2_neg;
+    uint32_t nb_xs_pos;          /* XS votes, inputs of the 0.95 read-strand rule */
+    uint32_t nb_xs_neg;
+    uint32_t max_min_anc;
+    uint32_t maxmmes;
+    uint32_t nb_mismatches;      /* uint32 sum, wraps like the reference */
+    uint32_t hamming5p;
+    uint32_t hamming3p;
+    uint32_t nb_up_juncs;
+    uint32_t nb_down_juncs;
+    uint32_t jad[PJ_NB_JAD];
+    uint32_t pad_a;              /* keeps entropy 8-byte aligned; sizeof(pj_junction) == 256 */
+    double   entropy;
+    uint8_t  read_strand;        /* PJ_STRAND_* */
+    uint8_t  ss_strand;
+    uint8_t  consensus_strand;
+    uint8_t  canonical_ss;       /* 'C', 'S' or 'N' */
+    uint8_t  suspicious;
+    char     ss1[2];             /* da1 / da2 as printed in the ss1 / ss2 columns */
+    char     ss2[2];
+    uint8_t  pad0[7];
+    /* ---- host finalize (pj_junctions_finalize) ---- */
+    uint32_t index;
+    uint32_t dist_2_up_junc;
+    uint32_t dist_2_down_junc;
+    uint32_t dist_nearest_junc;
+    uint8_t  uniq_junc;
+    uint8_t  primary_junc;
+    uint8_t  pfp;
+    uint8_t  pad1[5];
+    double   mean_readlen;       /* (uint32) truncation of the mean query length, or 0 when J<=1 */
+    double   rel2raw;
+    double   mean_mismatches;
+} pj_junction;
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+
+int         pj_abi_version(void);
+/* sizeof(pj_junction) as compiled into the library (256): lets bindings verify their mirror of the row layout */
+int         pj_junction_size(void);
+/* message of the last failure in this thread when no context exists (e.g. pj_create failed) */
+const char* pj_global_last_error(void);
+
+int         pj_create(const pj_config* cfg, pj_ctx** out);
+void        pj_destroy(pj_ctx* ctx);
+const char* pj_last_error(const pj_ctx* ctx);
+
+/* ---- genome (replaces GenomeMapper / faidx_fetch_seq, genome_mapper.cc:111-118) ------------ */
+
+/* Declare the target list exactly as the BAM header gives it (bam_reader.cc:103-110). */
+int pj_targets_set(pj_ctx* ctx, int32_t n_targets, const int32_t* target_len);
+
+/*
+ * Upload one target's sequence: `bases` are the bytes faidx would return for the whole sequence
+ * (only isgraph() bytes, any case).  The library upper-cases, packs to 2 bits per base plus an
+ * exception bitmask on the device and keeps it resident in HBM.  `n_bases` may differ from the BAM
+ * header length (the reference clamps fetches to the .fai length).
+ */
+int pj_genome_set_target(pj_ctx* ctx, int32_t tid, const char* bases, int64_t n_bases);
+
+/*
+ * Convenience: load every target straight from FASTA + .fai on disk.  `names` are the BAM header
+ * target names in tid order; raw FASTA bytes are staged through pinned memory and unwrapped +
+ * packed on the device.
+ */
+int pj_genome_load_fasta(pj_ctx* ctx, const char* fasta_path, const char* fai_path,
+                         int32_t n_targets, const char* const* names);
+
+/* ---- alignment shard ----------------------------------------------------------------------- */
+
+/* Start a shard (a set of whole targets owned by this GPU).  Hints size the device arena. */
+int pj_shard_begin(pj_ctx* ctx, int64_t n_records_hint, int64_t n_cigar_hint, int64_t n_seq_bytes_hint);
+
+/*
+ * Double-buffered pinned staging: returns writable columnar buffers of at least the requested
+ * capacities (the pointers in `out` are NON-const views of pinned host memory owned by the
+ * context; n_records is set to 0).  Fill them, set n_records, then pj_batch_submit().
+ * Acquiring blocks only while both staging slots are still in flight.
+ */
+int pj_staging_acquire(pj_ctx* ctx, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out);
+
+/* Enqueue host->device copies of a batch (cudaMemcpyAsync on the context's copy stream) and
+ * append it to the shard.  `b` may be a staging view or any caller-owned host buffers (those are
+ * copied synchronously unless they are pinned). */
+int pj_batch_submit(pj_ctx* ctx, const pj_batch* b);
+
+/* Run the device pipeline over everything submitted since pj_shard_begin. */
+int pj_shard_run(pj_ctx* ctx);
+
+/* Number of junctions found by the last pj_shard_run. */
+int64_t pj_shard_num_junctions(const pj_ctx* ctx);
+
+/* Copy results to caller-allocated arrays: rows[J] in (tid,start,end) order, stats[n_targets]. */
+int pj_shard_fetch(pj_ctx* ctx, pj_junction* rows, int64_t cap_rows, pj_target_stats* stats, int32_t cap_targets);
+
+/* Device time (ms, CUDA events on the compute stream) of the last pj_shard_run, plus the number of
+ * kernel launches it made.  kernel_ms/kernel_names expose the per-kernel breakdown (n entries). */
+int pj_shard_timing(const pj_ctx* ctx, float* total_ms, int32_t* n_launches);
+int pj_shard_kernel_times(const pj_ctx* ctx, int32_t cap, float* kernel_ms, const char** kernel_names, int32_t* n);
+
+/* ---- host finalize (A12/A13) --------------------------------------------------------------- */
+
+/*
+ * rows: all junctions of all shards, concatenated.  Sorts by (tid,start,end), assigns index, and —
+ * only when n_rows > 1, like junction_builder.cc:285 — group / distance / mean_readlen / pfp
+ * statistics.  Always fills rel2raw and mean_mismatches.
+ */
+int pj_junctions_finalize(pj_junction* rows, int64_t n_rows, double mean_query_length);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORTCULLIS_JUNC_H */

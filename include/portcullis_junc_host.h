@@ -1,0 +1,88 @@
+/*
+ * portcullis_junc_host.h — host-side C entry points that sit above the GPU C ABI (portcullis_junc.h):
+ * the `junc` stage driver (the JunctionBuilder equivalent), prep-directory access and the output writers.
+ *
+ * Reference interfaces mirrored here:
+ *   JunctionBuilder(prepDir, output) + setters + process()   /root/reference/src/junction_builder.cc:63-150
+ *   PreparedFiles (prep-dir naming contract)                  /root/reference/src/prepare.hpp:114-140
+ *   JunctionSystem::saveAll                                   /root/reference/lib/src/junction_system.cc:336-383
+ */
+#ifndef PORTCULLIS_JUNC_HOST_H
+#define PORTCULLIS_JUNC_HOST_H
+
+#include "portcullis_junc.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Strandedness, same order as portcullis::bam::Strandedness (bam_master.hpp:99-104) */
+enum { PJ_STRANDED_UNSTRANDED = 0, PJ_STRANDED_FIRSTSTRAND = 1, PJ_STRANDED_SECONDSTRAND = 2, PJ_STRANDED_UNKNOWN = 3 };
+
+typedef struct pjh_options {
+    const char* prep_dir;        /* positional <prep_data_dir>                                   */
+    const char* output_prefix;   /* -o, default "portcullis_junc/portcullis"                      */
+    int32_t threads;             /* -t: host decode threads (>=1)                                 */
+    int32_t n_gpus;              /* --gpus: number of B200s to shard targets over (>=1)           */
+    const int32_t* gpu_ids;      /* optional explicit device ordinals (n_gpus entries) or NULL    */
+    int32_t orientation;         /* PJ_ORIENT_*                                                   */
+    int32_t strandedness;        /* PJ_STRANDED_* (only compared with the detected protocol)      */
+    int32_t use_csi;             /* -c                                                            */
+    int32_t exon_gff;            /* --exon_gff                                                    */
+    int32_t intron_gff;          /* --intron_gff                                                  */
+    const char* source;          /* --source, default "portcullis"                                */
+    int32_t verbose;             /* -v                                                            */
+    int32_t separate;            /* --separate  (not supported on this path: rejected)            */
+    int32_t extra;               /* --extra     (not supported on this path: rejected)            */
+    int32_t quiet;               /* suppress the progress text on stdout                          */
+    const char* version;         /* string for the BED track line; NULL -> "1.2.4"                */
+} pjh_options;
+
+typedef struct pjh_report {
+    int64_t n_junctions;
+    uint64_t n_spliced, n_unspliced;
+    double  mean_query_length;
+    int32_t min_query_length, max_query_length;
+    double  t_open_s;            /* open BAM/BAI/FASTA, plan                                      */
+    double  t_genome_s;          /* FASTA unwrap + upload + pack                                  */
+    double  t_decode_s;          /* BGZF inflate + columnar packing + H2D (overlapped)            */
+    double  t_gpu_ms;            /* max over GPUs of the device pipeline time (CUDA events)       */
+    double  t_finalize_s;        /* host merge + A12/A13                                          */
+    double  t_write_s;           /* tab/bed/gff writers                                           */
+    double  t_total_s;
+    int32_t n_gpus_used;
+    int32_t n_kernel_launches;
+} pjh_report;
+
+void pjh_options_default(pjh_options* o);
+/* Runs the whole `junc` stage. Returns 0 or a PJ_E* code; message in pjh_last_error(). */
+int pjh_junc_run(const pjh_options* opt, pjh_report* report);
+const char* pjh_last_error(void);
+
+/* `portcullis junc ...` command line (argv[0] is the mode word).  Returns the process exit code. */
+int pjh_junc_main(int argc, char** argv);
+
+/* ---- prep directory access (used by tests and the benchmark harness) ---- */
+typedef struct pjh_prep pjh_prep;
+int         pjh_prep_open(const char* prep_dir, int use_csi, pjh_prep** out);
+void        pjh_prep_close(pjh_prep* p);
+int32_t     pjh_prep_n_targets(const pjh_prep* p);
+const char* pjh_prep_target_name(const pjh_prep* p, int32_t tid);
+int32_t     pjh_prep_target_len(const pjh_prep* p, int32_t tid);
+/* records the index reports for a target (mapped + placed unmapped), -1 when unknown */
+int64_t     pjh_prep_target_records(const pjh_prep* p, int32_t tid);
+/* Decode one target (tid >= 0) or every target (tid = -1) with `threads` workers into columnar arrays owned by
+ * `p` (valid until the next decode or close). */
+int         pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out);
+/* Unwrapped FASTA bytes of a target (owned by `p`, valid until the next call for another target or close). */
+int         pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bases);
+
+/* ---- writers (A14) ---- */
+int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,
+                      int32_t n_targets, const char* const* names, const int32_t* lens,
+                      const char* source, const char* version, int32_t exon_gff, int32_t intron_gff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,139 @@
+"""ctypes binding of the B200 junc library (include/portcullis_junc.h, include/portcullis_junc_host.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``make -C portcullis_b200/csrc``.
+There is no Python or CPU fallback: if the library is missing this module raises, and every compute
+entry point fails with PJ_ECUDA when no B200 is visible.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libportcullis_junc.so")
+
+PJ_OK, PJ_EINVAL, PJ_ECUDA, PJ_ENOMEM, PJ_ESTATE, PJ_EDATA, PJ_EIO = 0, -1, -2, -3, -4, -5, -6
+ORIENT = {"SE": 0, "FR": 1, "RF": 2, "FF": 3, "UNKNOWN": 4}
+STRANDEDNESS = {"UNSTRANDED": 0, "FIRSTSTRAND": 1, "SECONDSTRAND": 2, "UNKNOWN": 3}
+NB_JAD = 20
+
+
+class PjError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("[pj %d] %s" % (code, msg))
+        self.code = code
+
+
+class PjConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("orientation", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class PjBatch(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p),
+                ("mapq", C.c_void_p), ("xs", C.c_void_p), ("l_qseq", C.c_void_p), ("mtid", C.c_void_p),
+                ("mpos", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
+                ("seq4", C.c_void_p)]
+
+
+class PjTargetStats(C.Structure):
+    _fields_ = [("spliced_count", C.c_uint64), ("unspliced_count", C.c_uint64), ("sum_query_lengths", C.c_uint64),
+                ("min_query_length", C.c_int32), ("max_query_length", C.c_int32)]
+
+
+# numpy mirror of struct pj_junction (offsets follow the C layout; checked against sizeof in tests)
+JUNCTION_DTYPE = np.dtype([
+    ("tid", "<i4"), ("start", "<i4"), ("end", "<i4"), ("left", "<i4"), ("right", "<i4"),
+    ("nb_raw_aln", "<u4"), ("nb_dist_aln", "<u4"), ("nb_ms_aln", "<u4"), ("nb_um_aln", "<u4"), ("nb_bpp_aln", "<u4"),
+    ("nb_ppp_aln", "<u4"), ("nb_rel_aln", "<u4"), ("nb_r1_pos", "<u4"), ("nb_r1_neg", "<u4"), ("nb_r2_pos", "<u4"),
+    ("nb_r2_neg", "<u4"), ("nb_xs_pos", "<u4"), ("nb_xs_neg", "<u4"), ("max_min_anc", "<u4"), ("maxmmes", "<u4"),
+    ("nb_mismatches", "<u4"), ("hamming5p", "<u4"), ("hamming3p", "<u4"), ("nb_up_juncs", "<u4"), ("nb_down_juncs", "<u4"),
+    ("jad", "<u4", (NB_JAD,)), ("pad_a", "<u4"), ("entropy", "<f8"),
+    ("read_strand", "u1"), ("ss_strand", "u1"), ("consensus_strand", "u1"), ("canonical_ss", "u1"), ("suspicious", "u1"),
+    ("ss1", "S2"), ("ss2", "S2"), ("pad0", "u1", (7,)),
+    ("index", "<u4"), ("dist_2_up_junc", "<u4"), ("dist_2_down_junc", "<u4"), ("dist_nearest_junc", "<u4"),
+    ("uniq_junc", "u1"), ("primary_junc", "u1"), ("pfp", "u1"), ("pad1", "u1", (5,)),
+    ("mean_readlen", "<f8"), ("rel2raw", "<f8"), ("mean_mismatches", "<f8"),
+], align=False)
+
+# fields produced on the GPU (compared bit-exactly against the oracle; entropy within 1e-6 relative)
+DEVICE_INT_FIELDS = ["tid", "start", "end", "left", "right", "nb_raw_aln", "nb_dist_aln", "nb_ms_aln", "nb_um_aln",
+                     "nb_bpp_aln", "nb_ppp_aln", "nb_rel_aln", "nb_r1_pos", "nb_r1_neg", "nb_r2_pos", "nb_r2_neg",
+                     "nb_xs_pos", "nb_xs_neg", "max_min_anc", "maxmmes", "nb_mismatches", "hamming5p", "hamming3p",
+                     "nb_up_juncs", "nb_down_juncs", "jad", "read_strand", "ss_strand", "consensus_strand",
+                     "canonical_ss", "suspicious", "ss1", "ss2"]
+FINALIZE_FIELDS = ["index", "dist_2_up_junc", "dist_2_down_junc", "dist_nearest_junc", "uniq_junc", "primary_junc",
+                   "pfp", "mean_readlen", "rel2raw", "mean_mismatches"]
+
+
+class PjhOptions(C.Structure):
+    _fields_ = [("prep_dir", C.c_char_p), ("output_prefix", C.c_char_p), ("threads", C.c_int32), ("n_gpus", C.c_int32),
+                ("gpu_ids", C.POINTER(C.c_int32)), ("orientation", C.c_int32), ("strandedness", C.c_int32),
+                ("use_csi", C.c_int32), ("exon_gff", C.c_int32), ("intron_gff", C.c_int32), ("source", C.c_char_p),
+                ("verbose", C.c_int32), ("separate", C.c_int32), ("extra", C.c_int32), ("quiet", C.c_int32),
+                ("version", C.c_char_p)]
+
+
+class PjhReport(C.Structure):
+    _fields_ = [("n_junctions", C.c_int64), ("n_spliced", C.c_uint64), ("n_unspliced", C.c_uint64),
+                ("mean_query_length", C.c_double), ("min_query_length", C.c_int32), ("max_query_length", C.c_int32),
+                ("t_open_s", C.c_double), ("t_genome_s", C.c_double), ("t_decode_s", C.c_double), ("t_gpu_ms", C.c_double),
+                ("t_finalize_s", C.c_double), ("t_write_s", C.c_double), ("t_total_s", C.c_double),
+                ("n_gpus_used", C.c_int32), ("n_kernel_launches", C.c_int32)]
+
+
+# every symbol declared in include/*.h, with (restype, argtypes); used by load() and by the export test
+_P = C.c_void_p
+SYMBOLS = {
+    "pj_abi_version": (C.c_int, []),
+    "pj_junction_size": (C.c_int, []),
+    "pj_global_last_error": (C.c_char_p, []),
+    "pj_create": (C.c_int, [C.POINTER(PjConfig), C.POINTER(_P)]),
+    "pj_destroy": (None, [_P]),
+    "pj_last_error": (C.c_char_p, [_P]),
+    "pj_targets_set": (C.c_int, [_P, C.c_int32, _P]),
+    "pj_genome_set_target": (C.c_int, [_P, C.c_int32, _P, C.c_int64]),
+    "pj_genome_load_fasta": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_char_p)]),
+    "pj_shard_begin": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
+    "pj_staging_acquire": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(PjBatch)]),
+    "pj_batch_submit": (C.c_int, [_P, C.POINTER(PjBatch)]),
+    "pj_shard_run": (C.c_int, [_P]),
+    "pj_shard_num_junctions": (C.c_int64, [_P]),
+    "pj_shard_fetch": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32]),
+    "pj_shard_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "pj_shard_kernel_times": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
+    "pj_junctions_finalize": (C.c_int, [_P, C.c_int64, C.c_double]),
+    "pjh_options_default": (None, [C.POINTER(PjhOptions)]),
+    "pjh_junc_run": (C.c_int, [C.POINTER(PjhOptions), C.POINTER(PjhReport)]),
+    "pjh_last_error": (C.c_char_p, []),
+    "pjh_junc_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "pjh_prep_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "pjh_prep_close": (None, [_P]),
+    "pjh_prep_n_targets": (C.c_int32, [_P]),
+    "pjh_prep_target_name": (C.c_char_p, [_P, C.c_int32]),
+    "pjh_prep_target_len": (C.c_int32, [_P, C.c_int32]),
+    "pjh_prep_target_records": (C.c_int64, [_P, C.c_int32]),
+    "pjh_prep_decode": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(PjBatch)]),
+    "pjh_prep_genome": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
+    "pjh_write_outputs": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,
+                                    C.c_int32, C.c_int32]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the in-tree shared library (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                              "`make -C portcullis_b200/csrc` (this package has no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.pj_junction_size() != JUNCTION_DTYPE.itemsize:
+            raise ImportError("pj_junction layout mismatch between the library and portcullis_b200/_lib.py")
+        _lib = lib
+    return _lib

@@ -1,0 +1,306 @@
+// bam_io.cpp — see bam_io.hpp.  BGZF framing: SAM spec §4.1; BAM records: §4.2; BAI: §5.2.
+#include "bam_io.hpp"
+#include <zlib.h>
+#include <cstring>
+#include <algorithm>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+
+namespace pjio {
+
+static inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+MappedFile::~MappedFile() { if (data_ && size_) munmap((void*)data_, size_); }
+
+void MappedFile::open(const std::string& path) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw IoError("cannot open " + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { ::close(fd); throw IoError("cannot stat " + path); }
+    size_ = (uint64_t)st.st_size; path_ = path;
+    if (size_ > 0) {
+        void* p = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (p == MAP_FAILED) { ::close(fd); throw IoError("cannot mmap " + path); }
+        madvise(p, size_, MADV_SEQUENTIAL);
+        data_ = (const uint8_t*)p;
+    }
+    ::close(fd);
+}
+
+BgzfStream::BgzfStream(const MappedFile& f) : f_(f), ubuf_(65536) {
+    z_stream* z = new z_stream; memset(z, 0, sizeof *z);
+    if (inflateInit2(z, -15) != Z_OK) { delete z; throw IoError("inflateInit2 failed"); }
+    z_ = z;
+}
+BgzfStream::~BgzfStream() { z_stream* z = (z_stream*)z_; inflateEnd(z); delete z; }
+
+bool BgzfStream::load_block(uint64_t coff) {
+    have_block_ = false; ulen_ = upos_ = 0; block_coff_ = coff; next_coff_ = coff;
+    if (coff + 18 > f_.size()) return false;
+    const uint8_t* p = f_.data() + coff;
+    if (p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) throw IoError("not a BGZF block in " + f_.path());
+    uint32_t xlen = rd16(p + 10);
+    if (coff + 12 + xlen > f_.size()) throw IoError("truncated BGZF header");
+    uint32_t bsize = 0; bool found = false;
+    for (uint32_t o = 0; o + 4 <= xlen;) {
+        const uint8_t* e = p + 12 + o; uint32_t slen = rd16(e + 2);
+        if (e[0] == 'B' && e[1] == 'C' && slen == 2) { bsize = (uint32_t)rd16(e + 4) + 1; found = true; }
+        o += 4 + slen;
+    }
+    if (!found || coff + bsize > f_.size() || bsize < 12 + xlen + 8) throw IoError("corrupt BGZF block in " + f_.path());
+    uint32_t isize = rd32(p + bsize - 4);
+    if (isize > 65536) throw IoError("BGZF block too large");
+    if (isize) {
+        z_stream* z = (z_stream*)z_;
+        inflateReset(z);
+        z->next_in = (Bytef*)(p + 12 + xlen); z->avail_in = bsize - 12 - xlen - 8;
+        z->next_out = ubuf_.data(); z->avail_out = 65536;
+        int rc = inflate(z, Z_FINISH);
+        if (rc != Z_STREAM_END || z->total_out != isize) throw IoError("BGZF inflate failed in " + f_.path());
+    }
+    ulen_ = isize; upos_ = 0; next_coff_ = coff + bsize; have_block_ = true;
+    return true;
+}
+
+void BgzfStream::seek(uint64_t voff) {
+    uint64_t coff = voff >> 16; uint32_t uoff = (uint32_t)(voff & 0xffff);
+    if (!have_block_ || coff != block_coff_) { if (!load_block(coff)) { ulen_ = upos_ = 0; return; } }
+    upos_ = std::min(uoff, ulen_);
+}
+
+uint64_t BgzfStream::tell() const {
+    if (have_block_ && upos_ >= ulen_) return next_coff_ << 16;   // normalised like htslib after a block is drained
+    return (block_coff_ << 16) | upos_;
+}
+
+size_t BgzfStream::read(void* dst, size_t n) {
+    uint8_t* d = (uint8_t*)dst; size_t got = 0;
+    while (got < n) {
+        if (!have_block_ || upos_ >= ulen_) {
+            uint64_t nc = have_block_ ? next_coff_ : block_coff_;
+            if (!load_block(nc)) break;
+            if (ulen_ == 0) continue;      // empty block (EOF marker or padding): keep going
+        }
+        size_t k = std::min<size_t>(n - got, ulen_ - upos_);
+        memcpy(d + got, ubuf_.data() + upos_, k);
+        got += k; upos_ += (uint32_t)k;
+    }
+    return got;
+}
+
+bool BgzfStream::eof() {
+    while (!have_block_ || upos_ >= ulen_) {
+        uint64_t nc = have_block_ ? next_coff_ : block_coff_;
+        if (!load_block(nc)) return true;
+    }
+    return false;
+}
+
+bool BamHeader::coordinate_sorted() const {
+    size_t e = text.find('\n');
+    std::string first = text.substr(0, e);
+    return first.compare(0, 3, "@HD") == 0 && first.find("SO:coordinate") != std::string::npos;
+}
+
+void ColumnarChunk::clear() {
+    tid.clear(); pos.clear(); l_qseq.clear(); mtid.clear(); mpos.clear(); flag.clear(); mapq.clear(); xs.clear();
+    cigar_off.assign(1, 0); cigar.clear(); seq_off.assign(1, 0); seq4.clear();
+}
+
+void ColumnarChunk::append(const ColumnarChunk& o) {
+    uint32_t cb = (uint32_t)cigar.size(); uint64_t sb = seq4.size();
+    tid.insert(tid.end(), o.tid.begin(), o.tid.end()); pos.insert(pos.end(), o.pos.begin(), o.pos.end());
+    l_qseq.insert(l_qseq.end(), o.l_qseq.begin(), o.l_qseq.end());
+    mtid.insert(mtid.end(), o.mtid.begin(), o.mtid.end()); mpos.insert(mpos.end(), o.mpos.begin(), o.mpos.end());
+    flag.insert(flag.end(), o.flag.begin(), o.flag.end()); mapq.insert(mapq.end(), o.mapq.begin(), o.mapq.end());
+    xs.insert(xs.end(), o.xs.begin(), o.xs.end());
+    for (size_t i = 1; i < o.cigar_off.size(); i++) cigar_off.push_back(cb + o.cigar_off[i]);
+    for (size_t i = 1; i < o.seq_off.size(); i++) seq_off.push_back(sb + o.seq_off[i]);
+    cigar.insert(cigar.end(), o.cigar.begin(), o.cigar.end());
+    seq4.insert(seq4.end(), o.seq4.begin(), o.seq4.end());
+}
+
+void BamFile::open(const std::string& bam_path) {
+    file_.open(bam_path);
+    BgzfStream s(file_);
+    s.seek(0);
+    uint8_t b4[4];
+    if (s.read(b4, 4) != 4 || memcmp(b4, "BAM\1", 4) != 0) throw IoError("not a BAM file: " + bam_path);
+    if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
+    uint32_t l_text = rd32(b4);
+    hdr_.text.resize(l_text);
+    if (l_text && s.read(&hdr_.text[0], l_text) != l_text) throw IoError("truncated BAM header text");
+    while (!hdr_.text.empty() && hdr_.text.back() == '\0') hdr_.text.pop_back();
+    if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
+    uint32_t n_ref = rd32(b4);
+    hdr_.names.resize(n_ref); hdr_.lens.resize(n_ref);
+    for (uint32_t i = 0; i < n_ref; i++) {
+        if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
+        uint32_t l_name = rd32(b4);
+        std::string nm(l_name, '\0');
+        if (l_name && s.read(&nm[0], l_name) != l_name) throw IoError("truncated BAM header");
+        while (!nm.empty() && nm.back() == '\0') nm.pop_back();
+        if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
+        hdr_.names[i] = nm; hdr_.lens[i] = (int32_t)rd32(b4);
+    }
+    hdr_.first_record_voff = s.tell();
+}
+
+bool BamFile::load_bai(const std::string& bai_path) {
+    MappedFile f;
+    try { f.open(bai_path); } catch (const IoError&) { return false; }
+    const uint8_t* p = f.data(); uint64_t n = f.size(), o = 0;
+    auto need = [&](uint64_t k) { if (o + k > n) throw IoError("truncated BAI: " + bai_path); };
+    need(8);
+    if (memcmp(p, "BAI\1", 4) != 0) throw IoError("not a BAI index: " + bai_path);
+    uint32_t n_ref = rd32(p + 4); o = 8;
+    idx_.assign(n_ref, BamTargetIndex());
+    for (uint32_t r = 0; r < n_ref; r++) {
+        BamTargetIndex& t = idx_[r];
+        need(4); uint32_t n_bin = rd32(p + o); o += 4;
+        uint64_t first = 0;
+        for (uint32_t b = 0; b < n_bin; b++) {
+            need(8); uint32_t bin = rd32(p + o); uint32_t n_chunk = rd32(p + o + 4); o += 8;
+            need(16ull * n_chunk);
+            if (bin == 37450) {             // metadata pseudo-bin: (off_beg, off_end), (n_mapped, n_unmapped)
+                if (n_chunk >= 2) { t.n_mapped = rd64(p + o + 16); t.n_unmapped = rd64(p + o + 24); t.has_counts = true; }
+            } else {
+                for (uint32_t c = 0; c < n_chunk; c++) {
+                    uint64_t beg = rd64(p + o + 16ull * c);
+                    if (first == 0 || beg < first) first = beg;
+                }
+            }
+            o += 16ull * n_chunk;
+        }
+        need(4); uint32_t n_intv = rd32(p + o); o += 4;
+        need(8ull * n_intv);
+        t.ioffset.resize(n_intv);
+        for (uint32_t i = 0; i < n_intv; i++) t.ioffset[i] = rd64(p + o + 8ull * i);
+        o += 8ull * n_intv;
+        t.first_voff = first;
+    }
+    return true;
+}
+
+void BamFile::plan_target(int32_t tid, uint64_t chunk_bytes, std::vector<DecodeTask>& out) const {
+    if (tid < 0 || (size_t)tid >= idx_.size()) return;
+    const BamTargetIndex& t = idx_[tid];
+    if (t.first_voff == 0) return;          // no records on this target
+    const int32_t W = 16384;
+    DecodeTask cur{tid, 0, INT32_MAX, t.first_voff, 0};
+    uint64_t cur_c = t.first_voff >> 16;
+    for (size_t w = 1; w < t.ioffset.size(); w++) {
+        uint64_t v = t.ioffset[w];
+        if (v == 0) continue;
+        uint64_t c = v >> 16;
+        if (c >= cur_c + chunk_bytes && (int64_t)w * W < (int64_t)INT32_MAX) {
+            cur.pos_hi = (int32_t)(w * W); cur.approx_bytes = c - cur_c;
+            out.push_back(cur);
+            cur = DecodeTask{tid, (int32_t)(w * W), INT32_MAX, v, 0}; cur_c = c;
+        }
+    }
+    // size of the tail: up to the next target's first record (or EOF)
+    uint64_t end_c = file_.size();
+    for (size_t r = (size_t)tid + 1; r < idx_.size(); r++) if (idx_[r].first_voff) { end_c = idx_[r].first_voff >> 16; break; }
+    cur.approx_bytes = end_c > cur_c ? end_c - cur_c : 1;
+    out.push_back(cur);
+}
+
+DecodeTask BamFile::whole_file_task() const {
+    return DecodeTask{-1, 0, INT32_MAX, hdr_.first_record_voff, file_.size()};
+}
+
+// XS aux lookup: the only tag the junc path reads (lib/src/bam_alignment.cc:226-231).
+// Returns 0 when absent, the character for XS:A, and throws DataError for any other XS type
+// (bam_aux2A yields 0 -> strandFromChar throws, bam_master.hpp:60-72).
+static uint8_t find_xs(const uint8_t* a, const uint8_t* end) {
+    while (a + 3 <= end) {
+        uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+        const uint8_t* v = a + 3;
+        if (t0 == 'X' && t1 == 'S') {
+            if (ty != 'A' || v >= end) throw DataError(std::string("Unknown strand: XS tag is not of type A"));
+            uint8_t c = *v;
+            if (c != '+' && c != '-' && c != '?' && c != '.') throw DataError(std::string("Unknown strand: ") + (char)c);
+            return c;
+        }
+        size_t sz;
+        switch (ty) {
+        case 'A': case 'c': case 'C': sz = 1; break;
+        case 's': case 'S': sz = 2; break;
+        case 'i': case 'I': case 'f': sz = 4; break;
+        case 'd': sz = 8; break;
+        case 'Z': case 'H': { const uint8_t* q = v; while (q < end && *q) q++; sz = (size_t)(q - v) + 1; break; }
+        case 'B': {
+            if (v + 5 > end) return 0;
+            uint8_t st = v[0]; uint32_t cnt = rd32(v + 1);
+            size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+            sz = 5 + es * (size_t)cnt; break;
+        }
+        default: return 0;                 // unknown type: stop scanning like a failed bam_aux_get
+        }
+        a = v + sz;
+    }
+    return 0;
+}
+
+void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
+    BgzfStream s(file_);
+    s.seek(task.voff);
+    std::vector<uint8_t> rec;
+    const int32_t n_ref = (int32_t)hdr_.lens.size();
+    for (;;) {
+        uint8_t b4[4];
+        size_t g = s.read(b4, 4);
+        if (g == 0) break;
+        if (g != 4) throw IoError("truncated BAM record in " + file_.path());
+        uint32_t bs = rd32(b4);
+        if (bs < 32) throw IoError("corrupt BAM record (block_size < 32)");
+        rec.resize(bs);
+        if (s.read(rec.data(), bs) != bs) throw IoError("truncated BAM record in " + file_.path());
+        const uint8_t* p = rec.data();
+        int32_t tid = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
+        uint32_t l_name = p[8]; uint8_t mapq = p[9];
+        uint32_t n_cig = rd16(p + 12); uint16_t flag = rd16(p + 14);
+        int32_t l_seq = (int32_t)rd32(p + 16);
+        int32_t mtid = (int32_t)rd32(p + 20), mpos = (int32_t)rd32(p + 24);
+        if (task.tid >= 0) {
+            if (tid != task.tid) { if (tid > task.tid || tid < 0) break; else continue; }
+            if (pos >= task.pos_hi) break;
+            if (pos < task.pos_lo) continue;
+        }
+        if (tid < 0) { if (task.tid < 0) break; else continue; }   // unplaced reads sort last
+        if (tid >= n_ref) throw IoError("BAM record refers to an unknown target");
+        uint64_t need = 32ull + l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) / 2) + (uint64_t)(l_seq < 0 ? 0 : l_seq);
+        if (l_seq < 0 || need > bs) throw IoError("corrupt BAM record (fields exceed block_size)");
+        const uint8_t* cg = p + 32 + l_name;
+        // record visibility, Q13: pos < target_len and endpos > 0 (hts.c:1951-1953, sam.c:336-342)
+        int64_t rlen = 0; bool spliced = false;
+        for (uint32_t k = 0; k < n_cig; k++) {
+            uint32_t c = rd32(cg + 4 * k); uint32_t op = c & 0xf;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+            if (op == 3) spliced = true;
+        }
+        if (pos >= hdr_.lens[tid]) { if (task.tid >= 0) break; else continue; }
+        int64_t endpos = (!(flag & 0x4) && n_cig > 0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
+        if (endpos <= 0) continue;
+        const uint8_t* sq = cg + 4ull * n_cig;
+        const uint8_t* aux = sq + (l_seq + 1) / 2 + l_seq;
+        out.tid.push_back(tid); out.pos.push_back(pos); out.flag.push_back(flag); out.mapq.push_back(mapq);
+        out.l_qseq.push_back(l_seq); out.mtid.push_back(mtid); out.mpos.push_back(mpos);
+        out.xs.push_back(find_xs(aux, p + bs));
+        size_t c0 = out.cigar.size(); out.cigar.resize(c0 + n_cig);
+        if (n_cig) memcpy(&out.cigar[c0], cg, 4ull * n_cig);
+        out.cigar_off.push_back((uint32_t)out.cigar.size());
+        if (spliced && l_seq > 0) {
+            size_t s0 = out.seq4.size(), nb = (size_t)(l_seq + 1) / 2;
+            out.seq4.resize(s0 + nb); memcpy(&out.seq4[s0], sq, nb);
+        }
+        out.seq_off.push_back((uint64_t)out.seq4.size());
+    }
+}
+
+} // namespace pjio

@@ -1,0 +1,109 @@
+// bam_io.hpp — host-side BGZF / BAM / BAI reading for the junc path.
+//
+// Replaces the reference's BamReader (lib/src/bam_reader.cc:78-146) + htslib iterator
+// (deps/htslib-1.3/hts.c:1923-1963) for ONE purpose: decode alignment records of a prepared,
+// coordinate-sorted BAM into the columnar layout of include/portcullis_junc.h, in parallel.
+// Written from the SAM/BAM specification; zlib is the only dependency.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+namespace pjio {
+
+struct IoError : std::runtime_error { using std::runtime_error::runtime_error; };
+// Input the reference itself aborts on (e.g. a non-'A' XS tag).
+struct DataError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// Read-only memory map of a file (shared by all decode threads).
+class MappedFile {
+public:
+    MappedFile() = default;
+    ~MappedFile();
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+    void open(const std::string& path);
+    const uint8_t* data() const { return data_; }
+    uint64_t size() const { return size_; }
+    const std::string& path() const { return path_; }
+private:
+    const uint8_t* data_ = nullptr; uint64_t size_ = 0; std::string path_;
+};
+
+// Sequential BGZF inflater over a MappedFile, addressed by virtual offsets (coffset<<16 | uoffset).
+class BgzfStream {
+public:
+    explicit BgzfStream(const MappedFile& f);
+    ~BgzfStream();
+    void seek(uint64_t voff);
+    uint64_t tell() const;                 // virtual offset of the next byte
+    size_t read(void* dst, size_t n);      // returns bytes delivered (< n only at EOF)
+    bool eof();
+private:
+    bool load_block(uint64_t coff);
+    const MappedFile& f_;
+    void* z_ = nullptr;                    // z_stream
+    uint64_t block_coff_ = 0, next_coff_ = 0;
+    std::vector<uint8_t> ubuf_; uint32_t ulen_ = 0, upos_ = 0;
+    bool have_block_ = false;
+};
+
+struct BamTargetIndex {
+    uint64_t first_voff = 0;               // virtual offset of the target's first record (0 = no records)
+    uint64_t n_mapped = 0, n_unmapped = 0; // from the metadata pseudo-bin, 0 if absent
+    bool has_counts = false;
+    std::vector<uint64_t> ioffset;         // 16 kb linear index
+};
+
+struct BamHeader {
+    std::string text;
+    std::vector<std::string> names;
+    std::vector<int32_t> lens;
+    uint64_t first_record_voff = 0;
+    bool coordinate_sorted() const;
+};
+
+// One unit of parallel decode: records of `tid` with pos in [pos_lo, pos_hi), reading starts at voff.
+struct DecodeTask {
+    int32_t tid; int32_t pos_lo; int32_t pos_hi; uint64_t voff;
+    uint64_t approx_bytes;                 // compressed-size estimate, for scheduling
+};
+
+// Columnar records (same columns as pj_batch), owned vectors.
+struct ColumnarChunk {
+    std::vector<int32_t> tid, pos, l_qseq, mtid, mpos;
+    std::vector<uint16_t> flag;
+    std::vector<uint8_t> mapq, xs;
+    std::vector<uint32_t> cigar_off{0};    // n+1
+    std::vector<uint32_t> cigar;
+    std::vector<uint64_t> seq_off{0};      // n+1
+    std::vector<uint8_t> seq4;
+    int64_t n() const { return (int64_t)pos.size(); }
+    void clear();
+    void append(const ColumnarChunk& o);
+};
+
+class BamFile {
+public:
+    void open(const std::string& bam_path);                 // maps the file and parses the header
+    bool load_bai(const std::string& bai_path);             // false if the file is missing
+    const BamHeader& header() const { return hdr_; }
+    const std::vector<BamTargetIndex>& index() const { return idx_; }
+    bool has_index() const { return !idx_.empty(); }
+    // Split target `tid` into decode tasks of roughly `chunk_bytes` compressed bytes (needs the BAI).
+    void plan_target(int32_t tid, uint64_t chunk_bytes, std::vector<DecodeTask>& out) const;
+    // Without an index: one task per target found by a sequential scan is impossible, so a single
+    // whole-file task (tid = -1 means "every target") is returned.
+    DecodeTask whole_file_task() const;
+    // Decode one task into `out` (appended).  Applies the reference's record visibility rule (Q13):
+    // tid == target, pos < target_len, endpos > 0; iteration of a target stops at the first pos >= target_len.
+    void decode(const DecodeTask& t, ColumnarChunk& out) const;
+    const MappedFile& file() const { return file_; }
+private:
+    MappedFile file_;
+    BamHeader hdr_;
+    std::vector<BamTargetIndex> idx_;
+};
+
+} // namespace pjio

@@ -1,0 +1,482 @@
+// junc_driver.cpp — the `junc` stage driver: the B200-native counterpart of JunctionBuilder
+// (src/junction_builder.cc:63-150, 228-291, 359-454).  Host work only: validate the prep directory, plan and
+// run the parallel BGZF decode into pinned columnar staging buffers, shard targets over the GPUs (longest
+// processing time first on index record counts; shards are independent, no collective), gather the junction
+// rows, A12/A13 finalize and write the output files.  All junction arithmetic happens in the CUDA library.
+#include "../../include/portcullis_junc_host.h"
+#include "bam_io.hpp"
+#include "fasta_io.hpp"
+#include "junc_host.hpp"
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <climits>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <functional>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <thread>
+#include <sys/ioctl.h>
+#include <unistd.h>
+
+namespace fs = std::filesystem;
+using pjio::BamFile; using pjio::ColumnarChunk; using pjio::DecodeTask; using pjio::FastaFile;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// PreparedFiles naming contract (src/prepare.hpp:114-140)
+struct PrepPaths {
+    std::string dir, bam, bai, csi, fasta, fai;
+    explicit PrepPaths(const std::string& d) : dir(d) {
+        bam = d + "/portcullis.sorted.alignments.bam"; bai = bam + ".bai"; csi = bam + ".csi";
+        fasta = d + "/portcullis.genome.fa"; fai = fasta + ".fai";
+    }
+};
+bool present(const std::string& p) { std::error_code ec; return fs::exists(p, ec) || fs::is_symlink(fs::symlink_status(p, ec)); }
+
+// Decode `tasks` with `threads` workers; chunks reach `sink` strictly in task order.
+int decode_ordered(const BamFile& bam, const std::vector<DecodeTask>& tasks, int threads,
+                   const std::function<int(ColumnarChunk&)>& sink) {
+    const size_t n = tasks.size();
+    if (n == 0) return PJ_OK;
+    threads = std::max(1, std::min<int>(threads, (int)n));
+    std::vector<std::unique_ptr<ColumnarChunk>> done(n);
+    std::mutex mu; std::condition_variable cv;
+    std::atomic<size_t> next{0}; size_t consumed = 0; bool failed = false; std::string fail_msg; int fail_code = PJ_OK;
+    const size_t window = (size_t)threads * 3 + 2;           // bound on decoded-but-unconsumed chunks
+    auto worker = [&]() {
+        for (;;) {
+            size_t k = next.fetch_add(1);
+            if (k >= n) return;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || k < consumed + window; });
+                if (failed) return;
+            }
+            auto ch = std::make_unique<ColumnarChunk>();
+            try { bam.decode(tasks[k], *ch); }
+            catch (const pjio::DataError& e) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_code = PJ_EDATA; fail_msg = e.what(); } cv.notify_all(); return; }
+            catch (const std::exception& e) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_code = PJ_EIO; fail_msg = e.what(); } cv.notify_all(); return; }
+            { std::lock_guard<std::mutex> lk(mu); done[k] = std::move(ch); }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(worker);
+    int rc = PJ_OK;
+    for (size_t k = 0; k < n; k++) {
+        std::unique_ptr<ColumnarChunk> ch;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return failed || done[k]; });
+            if (failed) { rc = fail(fail_code, fail_msg); break; }
+            ch = std::move(done[k]);
+        }
+        rc = sink(*ch);
+        { std::lock_guard<std::mutex> lk(mu); consumed = k + 1; if (rc) { failed = true; } }
+        cv.notify_all();
+        if (rc) break;
+    }
+    { std::lock_guard<std::mutex> lk(mu); if (rc) failed = true; consumed = n; }
+    cv.notify_all();
+    for (auto& t : pool) t.join();
+    return rc;
+}
+
+void chunk_view(const ColumnarChunk& c, pj_batch* b) {
+    b->n_records = c.n(); b->tid = c.tid.data(); b->pos = c.pos.data(); b->flag = c.flag.data(); b->mapq = c.mapq.data(); b->xs = c.xs.data();
+    b->l_qseq = c.l_qseq.data(); b->mtid = c.mtid.data(); b->mpos = c.mpos.data(); b->cigar_off = c.cigar_off.data(); b->cigar = c.cigar.data();
+    b->seq_off = c.seq_off.data(); b->seq4 = c.seq4.data();
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct pjh_prep {
+    PrepPaths paths; BamFile bam; FastaFile fasta; bool indexed = false;
+    ColumnarChunk decoded; std::string genome; int32_t genome_tid = -1;
+    explicit pjh_prep(const std::string& d) : paths(d) {}
+};
+
+extern "C" {
+
+const char* pjh_last_error(void) { return g_err.c_str(); }
+
+void pjh_options_default(pjh_options* o) {
+    memset(o, 0, sizeof *o);
+    o->output_prefix = "portcullis_junc/portcullis"; o->threads = 1; o->n_gpus = 1; o->orientation = PJ_ORIENT_UNKNOWN;
+    o->strandedness = PJ_STRANDED_UNKNOWN; o->source = "portcullis"; o->version = "1.2.4";
+}
+
+int pjh_prep_open(const char* prep_dir, int use_csi, pjh_prep** out) {
+    if (!prep_dir || !out) return fail(PJ_EINVAL, "pjh_prep_open: null argument");
+    *out = nullptr;
+    auto p = std::make_unique<pjh_prep>(prep_dir);
+    // PreparedFiles::valid (src/prepare.cc:57-75)
+    if (!present(p->paths.bam)) return fail(PJ_EIO, "Could not find prepared BAM file at: " + p->paths.bam);
+    if (!present(use_csi ? p->paths.csi : p->paths.bai) || !present(p->paths.fasta) || !present(p->paths.fai))
+        return fail(PJ_EIO, "Prepared data is not complete: " + p->paths.dir);
+    try {
+        p->bam.open(p->paths.bam);
+        p->indexed = !use_csi && p->bam.load_bai(p->paths.bai);   // CSI: decode falls back to one sequential stream
+        p->fasta.open(p->paths.fasta, p->paths.fai);
+    } catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    *out = p.release();
+    return PJ_OK;
+}
+void pjh_prep_close(pjh_prep* p) { delete p; }
+int32_t pjh_prep_n_targets(const pjh_prep* p) { return p ? (int32_t)p->bam.header().names.size() : 0; }
+const char* pjh_prep_target_name(const pjh_prep* p, int32_t t) { return (p && t >= 0 && t < pjh_prep_n_targets(p)) ? p->bam.header().names[t].c_str() : nullptr; }
+int32_t pjh_prep_target_len(const pjh_prep* p, int32_t t) { return (p && t >= 0 && t < pjh_prep_n_targets(p)) ? p->bam.header().lens[t] : -1; }
+int64_t pjh_prep_target_records(const pjh_prep* p, int32_t t) {
+    if (!p || !p->indexed || t < 0 || (size_t)t >= p->bam.index().size() || !p->bam.index()[t].has_counts) return -1;
+    return (int64_t)(p->bam.index()[t].n_mapped + p->bam.index()[t].n_unmapped);
+}
+
+int pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out) {
+    if (!p || !out) return fail(PJ_EINVAL, "pjh_prep_decode: null argument");
+    std::vector<DecodeTask> tasks;
+    const int32_t T = pjh_prep_n_targets(p);
+    if (p->indexed) { for (int32_t t = (tid < 0 ? 0 : tid); t < (tid < 0 ? T : tid + 1); t++) p->bam.plan_target(t, 2u << 20, tasks); }
+    else { DecodeTask w = p->bam.whole_file_task(); if (tid >= 0) { w.tid = tid; } tasks.push_back(w); }
+    p->decoded.clear();
+    int rc = decode_ordered(p->bam, tasks, threads, [&](ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
+    if (rc) return rc;
+    chunk_view(p->decoded, out);
+    return PJ_OK;
+}
+
+int pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bases) {
+    if (!p || !bases || !n_bases || tid < 0 || tid >= pjh_prep_n_targets(p)) return fail(PJ_EINVAL, "pjh_prep_genome: bad argument");
+    if (p->genome_tid != tid) {
+        const pjio::FaiEntry* e = p->fasta.find(p->bam.header().names[tid]);
+        if (!e) return fail(PJ_EDATA, "The sequence \"" + p->bam.header().names[tid] + "\" not found in the genome index");
+        p->fasta.fetch_all(*e, p->genome); p->genome_tid = tid;
+    }
+    *bases = p->genome.data(); *n_bases = (int64_t)p->genome.size();
+    return PJ_OK;
+}
+
+int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows, int32_t n_targets, const char* const* names,
+                      const int32_t* lens, const char* source, const char* version, int32_t exon_gff, int32_t intron_gff) {
+    if (!output_prefix || (n_rows && !rows) || !names || !lens) return fail(PJ_EINVAL, "pjh_write_outputs: null argument");
+    try {
+        std::vector<pjhost::TargetInfo> t((size_t)n_targets);
+        for (int32_t i = 0; i < n_targets; i++) { t[i].name = names[i]; t[i].length = lens[i]; }
+        const std::string pre(output_prefix), src(source ? source : "portcullis"), ver(version ? version : "");
+        fs::path parent = fs::path(pre).parent_path();
+        if (!parent.empty()) { std::error_code ec; fs::create_directories(parent, ec); }
+        pjhost::write_tab(pre + ".junctions.tab", rows, n_rows, t);
+        if (exon_gff) pjhost::write_exon_gff(pre + ".junctions.exon.gff3", rows, n_rows, t, src);
+        if (intron_gff) pjhost::write_intron_gff(pre + ".junctions.intron.gff3", rows, n_rows, t, src);
+        pjhost::write_bed(pre + ".junctions.bed", rows, n_rows, t, src, ver);
+    } catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    return PJ_OK;
+}
+
+int pj_genome_load_fasta(pj_ctx* ctx, const char* fasta_path, const char* fai_path, int32_t n_targets, const char* const* names) {
+    if (!ctx || !fasta_path || !fai_path || !names) return fail(PJ_EINVAL, "pj_genome_load_fasta: null argument");
+    try {
+        FastaFile fa; fa.open(fasta_path, fai_path);
+        std::string seq;
+        for (int32_t t = 0; t < n_targets; t++) {
+            const pjio::FaiEntry* e = fa.find(names[t]);
+            if (!e) continue;                        // like the reference, a missing sequence only matters if a junction needs it
+            fa.fetch_all(*e, seq);
+            int rc = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size());
+            if (rc) return fail(rc, pj_last_error(ctx));
+        }
+    } catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    return PJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// JunctionBuilder::process equivalent
+// ------------------------------------------------------------------------------------------------
+int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
+    if (!o || !o->prep_dir) return fail(PJ_EINVAL, "pjh_junc_run: no prep directory given");
+    pjh_report R; memset(&R, 0, sizeof R);
+    const double t0 = now_s();
+    const bool say = !o->quiet;
+    if (o->separate || o->extra)
+        return fail(PJ_EINVAL, "--separate / --extra are not part of the GPU junc path (they only feed the mm_score, coverage, up_aln and down_aln columns)");
+    const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
+    {   // output directory (junction_builder.cc:65-66, 86-91)
+        fs::path parent = fs::path(prefix).parent_path();
+        std::error_code ec;
+        if (!parent.empty() && !fs::exists(parent, ec) && !fs::create_directories(parent, ec))
+            return fail(PJ_EIO, "Could not create output directory at: " + parent.string());
+    }
+    pjh_prep* prep = nullptr;
+    int rc = pjh_prep_open(o->prep_dir, o->use_csi, &prep);
+    if (rc) return rc;
+    std::unique_ptr<pjh_prep> prep_guard(prep);
+    const pjio::BamHeader& H = prep->bam.header();
+    const int32_t T = (int32_t)H.names.size();
+    if (T == 0) return fail(PJ_EDATA, "BAM header declares no target sequences");
+    int n_gpus = std::max(1, o->n_gpus);
+    if (n_gpus > T) n_gpus = T;
+    int threads = std::max(1, o->threads);
+    static const char* ORI[] = {"SE", "FR", "RF", "FF", "UNKNOWN"};
+    static const char* STR[] = {"UNSTRANDED", "FIRSTSTRAND", "SECONDSTRAND", "UNKNOWN"};
+    if (say) {
+        std::cout << "Settings:\n - BAM Strandedness: " << STR[std::min(std::max(o->strandedness, 0), 3)]
+                  << "\n - BAM Read Orientation: " << ORI[std::min(std::max(o->orientation, 0), 4)]
+                  << "\n - BAM Indexing mode: " << (o->use_csi ? "CSI" : "BAI")
+                  << "\n - Host decode threads: " << threads << "\n - GPUs: " << n_gpus << "\n - Separate BAMs: false\n\n";
+    }
+    // ---- shard targets over GPUs: LPT on index record counts (fallback: compressed bytes) ----
+    std::vector<std::vector<DecodeTask>> ttasks((size_t)T);
+    std::vector<uint64_t> weight((size_t)T, 0);
+    if (prep->indexed) {
+        for (int32_t t = 0; t < T; t++) {
+            prep->bam.plan_target(t, 4u << 20, ttasks[t]);
+            int64_t n = pjh_prep_target_records(prep, t);
+            uint64_t bytes = 0; for (auto& k : ttasks[t]) bytes += k.approx_bytes;
+            weight[t] = n > 0 ? (uint64_t)n : bytes / 64;
+        }
+    } else { n_gpus = 1; }
+    std::vector<std::vector<int32_t>> shard((size_t)n_gpus);
+    {
+        std::vector<int32_t> ord((size_t)T); for (int32_t t = 0; t < T; t++) ord[t] = t;
+        std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
+        std::vector<uint64_t> load((size_t)n_gpus, 0);
+        for (int32_t t : ord) { size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin()); shard[g].push_back(t); load[g] += weight[t] + 1; }
+        for (auto& s : shard) std::sort(s.begin(), s.end());   // BAM order inside a shard
+    }
+    R.t_open_s = now_s() - t0;
+    R.n_gpus_used = n_gpus;
+
+    struct GpuOut { std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0; int rc = PJ_OK; std::string err; };
+    std::vector<GpuOut> outs((size_t)n_gpus);
+    const int threads_per_gpu = std::max(1, threads / n_gpus);
+    auto run_gpu = [&](int g) {
+        GpuOut& out = outs[(size_t)g];
+        auto bail = [&](int code, const std::string& m) { out.rc = code; out.err = m; };
+        pj_config cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
+        pj_ctx* ctx = nullptr;
+        int r = pj_create(&cfg, &ctx);
+        if (r) return bail(r, pj_global_last_error());
+        struct Guard { pj_ctx* c; ~Guard() { pj_destroy(c); } } guard{ctx};
+        if ((r = pj_targets_set(ctx, T, H.lens.data()))) return bail(r, pj_last_error(ctx));
+        // genome: only this shard's targets become resident on this GPU
+        double tg = now_s();
+        {
+            std::string seq;
+            for (int32_t t : shard[(size_t)g]) {
+                if (ttasks[t].empty() && prep->indexed) continue;          // no records -> no junctions -> no genome needed
+                const pjio::FaiEntry* e = prep->fasta.find(H.names[t]);
+                if (!e) continue;
+                try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { return bail(PJ_EIO, ex.what()); }
+                if ((r = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size()))) return bail(r, pj_last_error(ctx));
+            }
+        }
+        out.genome_s = now_s() - tg;
+        // alignments
+        double td = now_s();
+        std::vector<DecodeTask> tasks;
+        uint64_t nrec_hint = 0;
+        if (prep->indexed) for (int32_t t : shard[(size_t)g]) { tasks.insert(tasks.end(), ttasks[t].begin(), ttasks[t].end()); nrec_hint += weight[t]; }
+        else tasks.push_back(prep->bam.whole_file_task());
+        if ((r = pj_shard_begin(ctx, (int64_t)nrec_hint + 1024, (int64_t)nrec_hint * 3 + 1024, (int64_t)nrec_hint * 48 + 1024))) return bail(r, pj_last_error(ctx));
+        r = decode_ordered(prep->bam, tasks, threads_per_gpu, [&](ColumnarChunk& ch) -> int {
+            if (ch.n() == 0) return PJ_OK;
+            pj_batch st;
+            int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
+            if (q) return fail(q, pj_last_error(ctx));
+            const size_t n = (size_t)ch.n();
+            memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
+            memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
+            memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
+            memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
+            memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
+            st.n_records = ch.n();
+            q = pj_batch_submit(ctx, &st);
+            return q ? fail(q, pj_last_error(ctx)) : PJ_OK;
+        });
+        if (r) return bail(r, g_err);
+        out.decode_s = now_s() - td;
+        if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));
+        const int64_t J = pj_shard_num_junctions(ctx);
+        out.rows.resize((size_t)J); out.stats.resize((size_t)T);
+        if ((r = pj_shard_fetch(ctx, out.rows.data(), J, out.stats.data(), T))) return bail(r, pj_last_error(ctx));
+        int32_t nl = 0; pj_shard_timing(ctx, &out.gpu_ms, &nl); out.launches = nl;
+    };
+    if (say) std::cout << "Finding junctions and calculating basic metrics:\n - Sharding " << T << " target sequences over " << n_gpus << " GPU(s)" << std::endl;
+    {
+        std::vector<std::thread> th;
+        for (int g = 1; g < n_gpus; g++) th.emplace_back(run_gpu, g);
+        run_gpu(0);
+        for (auto& t : th) t.join();
+    }
+    for (auto& out : outs) if (out.rc) return fail(out.rc, out.err);
+    // ---- gather (junction_builder.cc:249-283) ----
+    const double tf = now_s();
+    std::vector<pj_junction> rows;
+    std::vector<pj_target_stats> stats((size_t)T);
+    for (int32_t t = 0; t < T; t++) { stats[t] = pj_target_stats{0, 0, 0, INT32_MAX, 0}; }
+    for (int g = 0; g < n_gpus; g++) {
+        rows.insert(rows.end(), outs[g].rows.begin(), outs[g].rows.end());
+        for (int32_t t : shard[(size_t)g]) stats[t] = outs[g].stats[t];
+        if (!prep->indexed) stats = outs[g].stats;
+        R.t_gpu_ms = std::max<double>(R.t_gpu_ms, outs[g].gpu_ms); R.n_kernel_launches += outs[g].launches;
+        R.t_genome_s = std::max(R.t_genome_s, outs[g].genome_s); R.t_decode_s = std::max(R.t_decode_s, outs[g].decode_s);
+    }
+    uint64_t spliced = 0, unspliced = 0, sumq = 0; int32_t minq = INT32_MAX, maxq = 0;
+    if (say) std::cout << " - All shards completed.\n - Combining results.\n\n" << std::left << std::setw(12) << "Sequence" << "\t" << std::right << std::setw(12) << "unspliced"
+                       << "\t" << std::setw(12) << "spliced" << "\t" << std::setw(12) << "total" << std::endl;
+    for (int32_t t = 0; t < T; t++) {
+        spliced += stats[t].spliced_count; unspliced += stats[t].unspliced_count; sumq += stats[t].sum_query_lengths;
+        minq = std::min(minq, stats[t].min_query_length); maxq = std::max(maxq, stats[t].max_query_length);
+        if (say) std::cout << std::left << std::setw(12) << H.names[t] << "\t" << std::right << std::setw(12) << stats[t].unspliced_count << "\t"
+                           << std::setw(12) << stats[t].spliced_count << "\t" << std::setw(12) << stats[t].spliced_count + stats[t].unspliced_count << std::endl;
+    }
+    const uint64_t total = spliced + unspliced;
+    const double mean_q = (double)sumq / (double)total;
+    if ((rc = pj_junctions_finalize(rows.data(), (int64_t)rows.size(), mean_q))) return fail(rc, "finalize failed");
+    R.t_finalize_s = now_s() - tf;
+    if (say) {
+        std::cout << "\nFinal stats:\n - Processed " << total << " alignments.\n - Alignment query length statistics: min: " << minq << "; mean: " << mean_q
+                  << "; max: " << maxq << ";\n - Found " << rows.size() << " junctions from " << spliced << " spliced alignments.\n - Found " << unspliced
+                  << " unspliced alignments.\n\nSaving junctions: " << std::endl;
+    }
+    const double tw = now_s();
+    {
+        std::vector<const char*> names((size_t)T); for (int32_t t = 0; t < T; t++) names[t] = H.names[t].c_str();
+        rc = pjh_write_outputs(prefix.c_str(), rows.data(), (int64_t)rows.size(), T, names.data(), H.lens.data(), o->source ? o->source : "portcullis",
+                               o->version ? o->version : "1.2.4", o->exon_gff, o->intron_gff);
+        if (rc) return rc;
+    }
+    R.t_write_s = now_s() - tw;
+    if (say) {
+        // JunctionSystem::determineStrandedness(true) (junction_system.cc:455-560): report only
+        uint32_t c[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (const auto& j : rows) {
+            if (j.ss_strand == PJ_STRAND_UNKNOWN) continue;
+            uint32_t* k = c[j.ss_strand == PJ_STRAND_POS ? 0 : 1];
+            k[0] += j.nb_r1_pos; k[1] += j.nb_r1_neg; k[2] += j.nb_r2_pos; k[3] += j.nb_r2_neg;
+        }
+        auto ratio = [](uint32_t a, uint32_t b) { return ((double)((int32_t)a - (int32_t)b)) / ((double)(a + b)); };
+        const double posr1 = ratio(c[0][0], c[0][1]), negr1 = ratio(c[1][1], c[1][0]), posr2 = ratio(c[0][2], c[0][3]), negr2 = ratio(c[1][3], c[1][2]);
+        const uint32_t totalr1 = c[0][0] + c[0][1] + c[1][0] + c[1][1], totalr2 = c[0][2] + c[0][3] + c[1][2] + c[1][3];
+        std::cout << "Strand Analysis\n---------------\n\nTotal Alignments:\n - R1:" << totalr1 << "\n - R2:" << totalr2
+                  << "\nAlignment counts when splice site suggests +ve strand:\n - R1+: " << c[0][0] << "\n - R1-: " << c[0][1] << "\n - R2+: " << c[0][2] << "\n - R2-: " << c[0][3]
+                  << "\nAlignment counts when splice site suggests -ve strand:\n - R1+: " << c[1][0] << "\n - R1-: " << c[1][1] << "\n - R2+: " << c[1][2] << "\n - R2-: " << c[1][3]
+                  << "\nCorrelation of read strand to splice site strand (1.0 = complete agreement, -1.0 = complete disagreement):\n - R1+: " << posr1
+                  << "\n - R1-: " << negr1 << "\n - R2+: " << posr2 << "\n - R2-: " << negr2 << "\n" << std::endl;
+        int s = PJ_STRANDED_UNKNOWN; const char* ori = "Unknown";
+        if (totalr1 == 0 && totalr2 == 0) {}
+        else if (totalr2 == 0) { ori = "Single-End (SE)"; if (posr1 > 0.5 && negr1 > 0.5) s = PJ_STRANDED_SECONDSTRAND; else if (posr1 < -0.5 && negr1 < -0.5) s = PJ_STRANDED_FIRSTSTRAND; }
+        else {
+            ori = "Paired-End (FR): Forward Reverse (-> <-)";
+            if (posr1 > 0.5 && negr1 > 0.5 && posr2 < -0.5 && negr2 < -0.5) s = PJ_STRANDED_SECONDSTRAND;
+            else if (posr1 < -0.5 && negr1 < -0.5 && posr2 > 0.5 && negr2 > 0.5) s = PJ_STRANDED_FIRSTSTRAND;
+            else if (posr1 > 0.5 && negr1 > 0.5 && posr2 > 0.5 && negr2 > 0.5) { s = PJ_STRANDED_SECONDSTRAND; ori = "Paired-End (FF): Forward Forward (-> ->)"; }
+            else if (posr1 < -0.5 && negr1 < -0.5 && posr2 < -0.5 && negr2 < -0.5) { s = PJ_STRANDED_FIRSTSTRAND; ori = "Paired-End (FF): Forward Forward (-> ->)"; }
+        }
+        if (std::abs(posr1) <= 0.5 && std::abs(negr1) <= 0.5 && std::abs(posr2) <= 0.5 && std::abs(negr2) <= 0.5) s = PJ_STRANDED_UNSTRANDED;
+        static const char* LONG[] = {"Unstranded - can't determine transcript strand from read strand", "Firststrand - R1 is not on transcript strand",
+                                     "Secondstrand - R1 is on transcript strand", "Unknown strand protocol"};
+        std::cout << "Determined sequence orientation to be: " << ori << "\nDetermined RNAseq strandedness to be: " << LONG[s] << "\n" << std::endl;
+        if (o->strandedness != PJ_STRANDED_UNKNOWN && o->strandedness != s)
+            std::cerr << "Warning!  User input and portcullis disagree about the strandedness of the dataset\n" << std::endl;
+    }
+    R.n_junctions = (int64_t)rows.size(); R.n_spliced = spliced; R.n_unspliced = unspliced; R.mean_query_length = mean_q;
+    R.min_query_length = minq; R.max_query_length = maxq; R.t_total_s = now_s() - t0;
+    if (rep) *rep = R;
+    return PJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// `portcullis junc` command line (JunctionBuilder::main, junction_builder.cc:359-454)
+// ------------------------------------------------------------------------------------------------
+static void junc_usage() {
+    std::cout << "Portcullis Junction Builder Mode Help\n\n"
+                 "Analyses all potential junctions found in the input BAM file.\n"
+                 "Run \"portcullis prep ...\" to generate data suitable for junction finding\n"
+                 "before running \"portcullis junc ...\"\n\n"
+                 "Usage: portcullis junc [options] <prep_data_dir>\n"
+                 "System options:\n"
+                 "  -t [ --threads ] arg (=1)         The number of host threads used to decode the BAM file.\n"
+                 "  --gpus arg (=1)                   The number of GPUs to shard target sequences over.\n"
+                 "  --separate                        Separate spliced from unspliced reads (not available on the GPU path).\n"
+                 "  --orientation arg (=UNKNOWN)      The orientation of the reads that produced the BAM alignments: \"SE\", \"FR\", \"RF\", \"FF\", \"UNKNOWN\".\n"
+                 "  --strandedness arg (=UNKNOWN)     \"unstranded\", \"firststrand\", \"secondstrand\" or \"UNKNOWN\".\n"
+                 "  -c [ --use_csi ]                  Whether to use CSI indexing rather than BAI indexing.\n"
+                 "  -v [ --verbose ]                  Print extra information\n"
+                 "  --help                            Produce help message\n\n"
+                 "Output options:\n"
+                 "  -o [ --output ] arg (=portcullis_junc/portcullis)\n"
+                 "                                    Output prefix for files generated by this program.\n"
+                 "  --exon_gff                        Output exon-based junctions in GFF format.\n"
+                 "  --intron_gff                      Output intron-based junctions in GFF format.\n"
+                 "  --source arg (=portcullis)        The value to enter into the \"source\" field in GFF files.\n" << std::endl;
+}
+
+static bool ieq(const std::string& a, const char* b) {
+    if (a.size() != strlen(b)) return false;
+    for (size_t i = 0; i < a.size(); i++) if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+    return true;
+}
+
+int pjh_junc_main(int argc, char** argv) {
+    pjh_options o; pjh_options_default(&o);
+    std::string prep, output = "portcullis_junc/portcullis", source = "portcullis", orient = "UNKNOWN", strand = "UNKNOWN";
+    bool help = false;
+    auto need = [&](int& i, const std::string& name) -> const char* {
+        if (i + 1 >= argc) { std::cerr << "Error: the required argument for option '--" << name << "' is missing" << std::endl; return nullptr; }
+        return argv[++i];
+    };
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i]; std::string val; bool has_val = false;
+        if (a.rfind("--", 0) == 0) { size_t eq = a.find('='); if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_val = true; } }
+        auto value = [&](const std::string& name) -> const char* { if (has_val) return val.c_str(); return need(i, name); };
+        const char* v = nullptr;
+        if (a == "-t" || a == "--threads") { if (!(v = value("threads"))) return 1; o.threads = atoi(v); }
+        else if (a == "--gpus") { if (!(v = value("gpus"))) return 1; o.n_gpus = atoi(v); }
+        else if (a == "--separate") o.separate = 1;
+        else if (a == "--extra") o.extra = 1;
+        else if (a == "--orientation") { if (!(v = value("orientation"))) return 1; orient = v; }
+        else if (a == "--strandedness") { if (!(v = value("strandedness"))) return 1; strand = v; }
+        else if (a == "-c" || a == "--use_csi") o.use_csi = 1;
+        else if (a == "-v" || a == "--verbose") o.verbose = 1;
+        else if (a == "--help") help = true;
+        else if (a == "-o" || a == "--output") { if (!(v = value("output"))) return 1; output = v; }
+        else if (a == "--exon_gff") o.exon_gff = 1;
+        else if (a == "--intron_gff") o.intron_gff = 1;
+        else if (a == "--source") { if (!(v = value("source"))) return 1; source = v; }
+        else if (a == "-i" || a == "--prep_data_dir") { if (!(v = value("prep_data_dir"))) return 1; prep = v; }
+        else if (!a.empty() && a[0] == '-' && a.size() > 1) { std::cerr << "Error: unrecognised option '" << a << "'" << std::endl; return 1; }
+        else { if (!prep.empty()) { std::cerr << "Error: too many positional options have been specified on the command line" << std::endl; return 1; } prep = a; }
+    }
+    if (help || argc <= 1) { junc_usage(); return 1; }
+    if (ieq(orient, "SE")) o.orientation = PJ_ORIENT_SE; else if (ieq(orient, "FR")) o.orientation = PJ_ORIENT_FR; else if (ieq(orient, "RF")) o.orientation = PJ_ORIENT_RF;
+    else if (ieq(orient, "FF")) o.orientation = PJ_ORIENT_FF; else if (ieq(orient, "UNKNOWN")) o.orientation = PJ_ORIENT_UNKNOWN;
+    else { std::cerr << "Error: Unknown orientation: " << orient << std::endl; return 4; }
+    if (ieq(strand, "UNSTRANDED")) o.strandedness = PJ_STRANDED_UNSTRANDED; else if (ieq(strand, "FIRSTSTRAND")) o.strandedness = PJ_STRANDED_FIRSTSTRAND;
+    else if (ieq(strand, "SECONDSTRAND")) o.strandedness = PJ_STRANDED_SECONDSTRAND; else if (ieq(strand, "UNKNOWN")) o.strandedness = PJ_STRANDED_UNKNOWN;
+    else { std::cerr << "Error: Unknown strandedness: " << strand << std::endl; return 4; }
+    o.prep_dir = prep.c_str(); o.output_prefix = output.c_str(); o.source = source.c_str();
+    std::cout << "Running portcullis in junction builder mode\n------------------------------------------\n" << std::endl;
+    pjh_report rep;
+    const int rc = pjh_junc_run(&o, &rep);
+    if (rc) { std::cerr << "Error: " << pjh_last_error() << std::endl; return rc == PJ_EINVAL ? 1 : 4; }
+    std::cout << std::fixed << std::setprecision(1) << "\nPortcullis junc completed.\nTotal runtime: " << rep.t_total_s << "s"
+              << "  (open " << rep.t_open_s << "s, genome " << rep.t_genome_s << "s, decode+H2D " << rep.t_decode_s << "s, GPU pipeline "
+              << std::setprecision(3) << rep.t_gpu_ms << " ms on " << rep.n_gpus_used << " GPU(s), " << std::setprecision(1) << "finalize " << rep.t_finalize_s << "s, write " << rep.t_write_s << "s)\n" << std::endl;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,816 @@
+// junc_kernels.cu — hand-written sm_100a kernels of the junc hot path.
+//
+// Pipeline over one shard (all alignment columns resident in HBM):
+//   k_scan_reads      per read : N-op count, reference span, per-target scalars (A1)
+//   scan              exclusive prefix of N-op counts -> pair slots
+//   k_emit_pairs      per read : CIGAR walk, one (key, PairA, PairB) record per N op (A2, A3, A6 flags)
+//   radix sort        stable LSD sort of (key, pair index): junction order, BAM order inside a junction
+//   k_seg_heads/scan  junction ids and segment starts
+//   k_reduce1         per pair : warp-shuffle segmented reduce of the integer metrics + entropy run boundaries
+//   k_entropy_*       run-length terms -> fp64 entropy per junction (A5, quirk Q1)
+//   k_match           warp per pair : junction-wide anchor window walk against the packed genome (A10)
+//   k_reduce2         per pair : segmented reduce of mmes / mismatches / minMatch / JAD histogram (A11)
+//   k_finalize        per junction : strands, motif, Hamming distances, JAD suffix sums, row assembly (A4, A8, A9)
+#include "junc_kernels.cuh"
+#include "junc_launch.hpp"
+#include <cstdio>
+
+namespace pjk {
+
+#define FULL 0xffffffffu
+
+// ================================================================================================
+// generic exclusive scan (uint32), three phases; tile = 512 threads x 8 items
+// ================================================================================================
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = warp_incl_scan(v, lane);
+    __syncthreads();                                  // protect wsum reuse across calls
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t s = lane < nw ? wsum[lane] : 0;
+        uint32_t si = warp_incl_scan(s, lane);
+        wsum[lane] = si - s;
+        if (lane == 31) *total = si;                  // lanes >= nw contribute 0, so lane 31 holds the block sum
+    }
+    __syncthreads();
+    return inc - v + wsum[w];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ bsum) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x; if (i < n) s += in[i]; }
+    __shared__ uint32_t tot;
+    block_excl_scan(s, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t* __restrict__ bsum, uint32_t nb, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t tot;
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < nb; b0 += 1024) {
+        uint32_t i = b0 + threadIdx.x;
+        uint32_t v = i < nb ? bsum[i] : 0;
+        uint32_t ex = block_excl_scan(v, &tot);
+        if (i < nb) bsum[i] = ex + carry;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n,
+                                                              const uint32_t* __restrict__ bsum) {
+    // blocked arrangement: thread t owns items [t*ITEMS, t*ITEMS+ITEMS) of the tile
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS]; uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + k; v[k] = i < n ? in[i] : 0; s += v[k]; }
+    __shared__ uint32_t tot;
+    uint32_t ex = block_excl_scan(s, &tot) + bsum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { uint64_t i = base + k; if (i < n) out[i] = ex; ex += v[k]; }
+}
+
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_tmp, uint32_t* total_dev, cudaStream_t st) {
+    const uint32_t nb = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    if (n == 0) { cudaMemsetAsync(total_dev, 0, sizeof(uint32_t), st); return; }
+    k_scan_partials<<<nb, SCAN_THREADS, 0, st>>>(in, n, bsum_tmp);
+    k_scan_bsums<<<1, 1024, 0, st>>>(bsum_tmp, nb, total_dev);
+    k_scan_apply<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, bsum_tmp);
+}
+uint64_t scan_tmp_elems(uint64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+// ================================================================================================
+// small utility kernels
+// ================================================================================================
+__global__ void k_rebase_u32(uint32_t* __restrict__ a, int64_t n, uint32_t add) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] += add;
+}
+__global__ void k_rebase_u64(uint64_t* __restrict__ a, int64_t n, uint64_t add) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] += add;
+}
+__global__ void k_fill_i32(int32_t* __restrict__ a, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = v;
+}
+void launch_fill_i32(int32_t* a, int64_t n, int32_t v, cudaStream_t st) { if (n > 0) k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, v); }
+void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st) { if (n > 0 && add) k_rebase_u32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, add); }
+void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { if (n > 0 && add) k_rebase_u64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, add); }
+
+// ================================================================================================
+// genome packing: raw FASTA bytes (already unwrapped) -> 2-bit plane + exception bitmask
+// one thread packs 64 bases: four 128-bit loads, two g2 words, one gx word
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ raw, int64_t n, uint64_t base_index /* multiple of 64 */,
+                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx,
+                                                      uint64_t* __restrict__ exc_pos, uint8_t* __restrict__ exc_byte,
+                                                      uint32_t* __restrict__ exc_count, uint32_t exc_cap) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b0 = t * 64;
+    if (b0 >= n) return;
+    uint8_t c[64];
+    if (b0 + 64 <= n && ((reinterpret_cast<uintptr_t>(raw + b0) & 15) == 0)) {
+        const uint4* p = reinterpret_cast<const uint4*>(raw + b0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { uint4 v = __ldg(p + k); memcpy(c + 16 * k, &v, 16); }
+    } else {
+#pragma unroll 8
+        for (int k = 0; k < 64; k++) c[k] = (b0 + k < n) ? raw[b0 + k] : (uint8_t)'A';
+    }
+    uint64_t w0 = 0, w1 = 0, x = 0;
+#pragma unroll
+    for (int k = 0; k < 64; k++) {
+        uint8_t ch = c[k];
+        if (ch >= 'a' && ch <= 'z') ch -= 32;                        // boost::to_upper
+        uint32_t code; bool exc = false;
+        switch (ch) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
+                      default: exc = true; code = (ch == 'N') ? 0u : 1u; }
+        if (b0 + k >= n) { exc = false; code = 0; }
+        if (exc) {
+            x |= 1ull << k;
+            if (code == 1u) {
+                uint32_t slot = atomicAdd(exc_count, 1u);
+                if (slot < exc_cap) { exc_pos[slot] = base_index + (uint64_t)(b0 + k); exc_byte[slot] = ch; }
+            }
+        }
+        if (k < 32) w0 |= (uint64_t)code << (2 * k); else w1 |= (uint64_t)code << (2 * (k - 32));
+    }
+    const uint64_t gi = base_index + (uint64_t)b0;
+    g2[gi >> 5] = w0; g2[(gi >> 5) + 1] = w1; gx[gi >> 6] = x;
+}
+
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
+                        uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st) {
+    if (n <= 0) return;
+    const int64_t threads = (n + 63) / 64;
+    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, exc_pos, exc_byte, exc_count, exc_cap);
+}
+
+// ================================================================================================
+// k_scan_reads: per read N-op count, reference span and the per-target scalars of findJuncs
+// (src/junction_builder.cc:333-343, 352-356).  Record visibility = quirk Q13.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_scan_reads(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets,
+                                                     uint32_t* __restrict__ npairs, int32_t* __restrict__ read_end,
+                                                     TargetAcc T, uint32_t* __restrict__ max_nlen) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool valid = i < R.n, vis = false;
+    int32_t tid = -2, lq = 0; uint32_t nN = 0, maxN = 0;
+    if (valid) {
+        tid = R.tid[i];
+        const int32_t pos = R.pos[i];
+        const uint32_t c0 = R.cigar_off[i], c1 = R.cigar_off[i + 1];
+        int64_t rlen = 0;
+        for (uint32_t c = c0; c < c1; c++) {
+            const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
+            if (op_ref(op)) rlen += cig_len(w);
+            if (op == OP_N) { nN++; maxN = max(maxN, (uint32_t)cig_len(w)); }
+        }
+        read_end[i] = (int32_t)(pos + rlen - 1);
+        lq = R.l_qseq[i];
+        if (tid >= 0 && tid < n_targets) {
+            const int64_t endpos = (!(R.flag[i] & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
+            vis = pos < tlen[tid] && endpos > 0;
+        }
+        if (!vis) nN = 0;
+        npairs[i] = nN;
+    }
+    // warp-aggregated per-target accumulation (records of a warp nearly always share the target)
+    const int32_t t0 = __shfl_sync(FULL, tid, 0);
+    const bool uniform = __all_sync(FULL, valid && tid == t0);
+    uint32_t mx = maxN;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+    if (lane == 0 && mx) atomicMax(max_nlen, mx);
+    if (uniform && t0 >= 0 && t0 < n_targets) {
+        const uint32_t sp = __popc(__ballot_sync(FULL, vis && nN > 0));
+        const uint32_t us = __popc(__ballot_sync(FULL, vis && nN == 0));
+        unsigned long long s = vis ? (unsigned long long)(long long)lq : 0ull;
+        int32_t mn = vis ? lq : INT32_MAX, mxq = vis ? lq : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            s += __shfl_xor_sync(FULL, s, o);
+            mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+            mxq = max(mxq, __shfl_xor_sync(FULL, mxq, o));
+        }
+        if (lane == 0 && (sp | us)) {
+            if (sp) atomicAdd(T.spliced + t0, (unsigned long long)sp);
+            if (us) atomicAdd(T.unspliced + t0, (unsigned long long)us);
+            atomicAdd(T.sumq + t0, s); atomicMin(T.minq + t0, mn); atomicMax(T.maxq + t0, mxq);
+        }
+    } else if (vis) {
+        if (nN > 0) atomicAdd(T.spliced + tid, 1ull); else atomicAdd(T.unspliced + tid, 1ull);
+        atomicAdd(T.sumq + tid, (unsigned long long)(long long)lq); atomicMin(T.minq + tid, lq); atomicMax(T.maxq + tid, lq);
+    }
+}
+
+void launch_scan_reads(const Reads& R, const int32_t* tlen, int32_t n_targets, uint32_t* npairs, int32_t* read_end,
+                       const TargetAcc& T, uint32_t* max_nlen, cudaStream_t st) {
+    if (R.n <= 0) return;
+    k_scan_reads<<<(unsigned)((R.n + 255) / 256), 256, 0, st>>>(R, tlen, n_targets, npairs, read_end, T, max_nlen);
+}
+
+// ================================================================================================
+// k_emit_pairs: JunctionSystem::addJunctions (lib/src/junction_system.cc:140-210) with the recursion unrolled
+// into a loop, plus the per-read parts of addJunctionAlignment / calcAlignmentStats (junction.cc:477-502, 755-814).
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_emit_pairs(Reads R, const int32_t* __restrict__ tlen, const uint64_t* __restrict__ toff,
+                                                     int32_t len_bits, int32_t orientation,
+                                                     const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ npairs,
+                                                     const int32_t* __restrict__ read_end,
+                                                     uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
+                                                     uint32_t* __restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n) return;
+    const uint32_t nN = npairs[i];
+    if (nN == 0) return;
+    const int32_t tid = R.tid[i], pos = R.pos[i], refLen = tlen[tid];
+    const uint32_t flag = R.flag[i];
+    const uint32_t* cg = R.cigar + R.cigar_off[i];
+    const int32_t n = (int32_t)(R.cigar_off[i + 1] - R.cigar_off[i]);
+    const uint8_t xs = R.xs[i];
+    uint32_t bits = 0;
+    if (flag & 0x40u) bits |= PB_R1;
+    if (flag & 0x10u) bits |= PB_REV;
+    if (nN > 1) bits |= PB_MS;
+    if (R.mapq[i] >= PJ_MAP_QUALITY_THRESHOLD) bits |= PB_UM;
+    if (flag & 0x2u) bits |= PB_BPP;
+    if (portcullis_proper_pair(flag, tid, R.mtid[i], pos, R.mpos[i], orientation)) bits |= PB_PPP;
+    if (xs == '+') bits |= PB_XSP; else if (xs == '-') bits |= PB_XSN;
+    const int32_t rend_read = read_end[i];
+    const uint64_t tbase = toff[tid];
+    uint32_t slot = pair_off[i], e = 0;
+
+    int32_t lStart = pos, lEndExc = pos;
+    for (int32_t c = 0; c < n; c++) {
+        const uint32_t w = __ldg(cg + c), op = cig_op(w); const int32_t L = cig_len(w);
+        if (op == OP_N) {
+            int32_t rStart = lEndExc + L, rEndExc = rStart;
+            int32_t j = c + 1;
+            while (j < n && rEndExc <= refLen) {
+                const uint32_t w2 = __ldg(cg + j); if (cig_op(w2) == OP_N) break;
+                if (op_ref(cig_op(w2))) rEndExc += cig_len(w2);
+                j++;
+            }
+            if (rStart - 1 >= refLen) rStart = refLen - 1;
+            if (rEndExc - 1 >= refLen) rEndExc = refLen;
+            const int32_t start = lEndExc, end = rStart - 1, rend = rEndExc - 1;
+            if (lStart > start || rend < end) e |= ERR_ANCHOR_ORDER;
+            if (start < 0 || start > refLen - 2 || end < start - 1) e |= ERR_START_RANGE;
+            const uint64_t sz = (uint64_t)(uint32_t)(end - start + 1);
+            if (sz >> len_bits) e |= ERR_KEY_OVERFLOW;
+            // nbUpstreamJunctions / nbDownstreamJunctions contribution of this read (junction.cc:795-812)
+            uint32_t up = 0, down = 0; int32_t p = pos;
+            for (int32_t k = 0; k < n; k++) {
+                const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
+                if (op_ref(o3)) p += cig_len(w3);
+                if (o3 == OP_N) { if (p < start) up++; else if (p > end + 1) down++; }
+            }
+            keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
+            pa[slot] = PairA{(uint32_t)i, lStart, rend, pos};
+            pb[slot] = PairB{rend_read, bits, (up << 16) | (down & 0xffffu), start};
+            slot++;
+            if (j < n) { lStart = rStart; lEndExc = rStart; } else break;
+        } else if (op_ref(op)) lEndExc += L;
+    }
+    if (e) atomicOr(err, e);
+}
+
+void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff, int32_t len_bits, int32_t orientation,
+                       const uint32_t* pair_off, const uint32_t* npairs, const int32_t* read_end,
+                       uint64_t* keys, PairA* pa, PairB* pb, uint32_t* err, cudaStream_t st) {
+    if (R.n <= 0) return;
+    k_emit_pairs<<<(unsigned)((R.n + 255) / 256), 256, 0, st>>>(R, tlen, toff, len_bits, orientation, pair_off, npairs, read_end, keys, pa, pb, err);
+}
+
+// ================================================================================================
+// stable LSD radix sort of (key64, val32), 8-bit digits.
+// Per pass: block digit histograms -> exclusive scan over [digit][block] -> stable scatter.
+// ================================================================================================
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 4096 keys per block
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t nblocks,
+                                                         uint32_t* __restrict__ counts /* [256][nblocks] */) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int k = 0; k < RS_ITEMS; k++) {
+        const uint32_t i = base + k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    counts[(uint32_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in /* null: iota */,
+                                                            uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                            uint32_t n, int shift, uint32_t nblocks, const uint32_t* __restrict__ offs /* scanned counts */) {
+    __shared__ uint32_t wcnt[RS_WARPS][256];
+    __shared__ uint32_t dbase[256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wcnt[0][0])[k] = 0;
+    __syncthreads();
+    // warp w owns keys [base + w*512, base + (w+1)*512), visited in rounds of 32 consecutive keys => stable
+    const uint32_t wbase = blockIdx.x * RS_TILE + w * (RS_ITEMS * 32);
+    uint64_t key[RS_ITEMS]; uint32_t loc[RS_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : ~0ull;
+        const uint32_t d = ok ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;   // 256: padding lanes group together, never counted
+        const uint32_t m = __match_any_sync(FULL, d);
+        uint32_t prev = 0;
+        if (ok) prev = wcnt[w][d];
+        __syncwarp();
+        if (ok && (m & lt) == 0) wcnt[w][d] = prev + __popc(m);
+        __syncwarp();
+        loc[r] = prev + __popc(m & lt);
+    }
+    __syncthreads();
+    {   // exclusive prefix over warps for digit = threadIdx.x, plus the global base of this block's digit run
+        const uint32_t d = threadIdx.x; uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) { uint32_t t = wcnt[ww][d]; wcnt[ww][d] = run; run += t; }
+        dbase[d] = offs[d * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        const uint32_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+            const uint32_t dst = dbase[d] + wcnt[w][d] + loc[r];
+            keys_out[dst] = key[r];
+            vals_out[dst] = vals_in ? vals_in[i] : i;
+        }
+    }
+}
+
+uint32_t rs_num_blocks(uint32_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+
+// Sorts n (key,val) pairs on bits [0, key_bits).  Result ends in (*keys_a, *vals_a) or the alternates; returns 0 if the
+// sorted data is in the `a` buffers and 1 if it is in the `b` buffers.
+int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
+                      uint32_t* counts /* 256*nblocks */, uint32_t* scan_tmp, uint32_t* total_tmp, cudaStream_t st, int* n_launches) {
+    if (n == 0) return 0;
+    const uint32_t nb = rs_num_blocks(n);
+    int cur = 0; bool first = true;
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        const uint64_t* kin = cur ? keys_b : keys_a; const uint32_t* vin = cur ? vals_b : vals_a;
+        uint64_t* kout = cur ? keys_a : keys_b; uint32_t* vout = cur ? vals_a : vals_b;
+        k_rs_hist<<<nb, RS_THREADS, 0, st>>>(kin, n, shift, nb, counts);
+        launch_exclusive_scan(counts, counts, (uint64_t)256 * nb, scan_tmp, total_tmp, st);
+        k_rs_scatter<<<nb, RS_THREADS, 0, st>>>(kin, first ? nullptr : vin, kout, vout, n, shift, nb, counts);
+        if (n_launches) *n_launches += 5;
+        cur ^= 1; first = false;
+    }
+    if (first) {   // key_bits == 0: nothing to sort, but vals must still be the identity
+        k_rs_hist<<<nb, RS_THREADS, 0, st>>>(keys_a, n, 0, nb, counts);
+        launch_exclusive_scan(counts, counts, (uint64_t)256 * nb, scan_tmp, total_tmp, st);
+        k_rs_scatter<<<nb, RS_THREADS, 0, st>>>(keys_a, nullptr, keys_b, vals_b, n, 0, nb, counts);
+        if (n_launches) *n_launches += 5;
+        cur = 1;
+    }
+    return cur;
+}
+
+// ================================================================================================
+// junction segmentation
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_seg_heads(const uint64_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+// head[] holds the exclusive scan on entry to this kernel; jid = excl + is_head - 1
+__global__ void __launch_bounds__(256) k_seg_ids(const uint64_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ excl,
+                                                  uint32_t* __restrict__ jid, uint32_t* __restrict__ seg_start, uint32_t n_junc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool h = (i == 0 || keys[i] != keys[i - 1]);
+    const uint32_t j = excl[i] + (h ? 1u : 0u) - 1u;
+    jid[i] = j;
+    if (h) seg_start[j] = i;
+    if (i == n - 1) seg_start[n_junc] = n;
+}
+void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st) { if (n) k_seg_heads<<<(n + 255) / 256, 256, 0, st>>>(keys, n, head); }
+void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint32_t* jid, uint32_t* seg_start, uint32_t n_junc, cudaStream_t st) {
+    if (n) k_seg_ids<<<(n + 255) / 256, 256, 0, st>>>(keys, n, excl, jid, seg_start, n_junc);
+}
+
+// ================================================================================================
+// warp-shuffle segmented reduction helpers.  Lanes hold nondecreasing junction ids; after the inclusive
+// segmented scan the LAST lane of every run holds the reduction of the run.
+// ================================================================================================
+struct SegCtx { uint32_t same[5]; bool tail; };   // same[s]: lane-2^s exists and is in my segment
+
+__device__ __forceinline__ SegCtx seg_ctx(uint32_t j, int lane) {
+    SegCtx c;
+#pragma unroll
+    for (int s = 0; s < 5; s++) { const uint32_t o = __shfl_up_sync(FULL, j, 1 << s); c.same[s] = (lane >= (1 << s)) && (o == j); }
+    const uint32_t nx = __shfl_down_sync(FULL, j, 1);
+    c.tail = (lane == 31) || (nx != j);
+    return c;
+}
+template <typename T, typename Op>
+__device__ __forceinline__ T seg_reduce(T v, const SegCtx& c, Op op) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) { const T o = __shfl_up_sync(FULL, v, 1 << s); if (c.same[s]) v = op(v, o); }
+    return v;
+}
+struct OpAdd { template <typename T> __device__ T operator()(T a, T b) const { return a + b; } };
+struct OpMin { template <typename T> __device__ T operator()(T a, T b) const { return a < b ? a : b; } };
+struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { return a > b ? a : b; } };
+
+// ================================================================================================
+// k_reduce1: stage-1 reductions per junction (SURVEY §8 "reduction algebra" stage 1)
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_reduce1(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+                                                  const PairA* __restrict__ pa, const PairB* __restrict__ pb, int32_t ppcheck,
+                                                  JuncAcc A, uint32_t* __restrict__ eflag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool ok = i < n;
+    uint32_t j = 0xffffffffu;
+    uint32_t c0 = 0, c1 = 0, c2 = 0;                 // packed 6-bit counters
+    int32_t lmin = INT32_MAX, rmax = INT32_MIN; uint32_t anc = 0, up = 0, down = 0;
+    if (ok) {
+        j = jid[i];
+        const uint32_t idx = vals[i];
+        const PairA a = pa[idx]; const PairB b = pb[idx];
+        const bool has_prev = i > 0 && jid[i - 1] == j;
+        const bool last = (i + 1 == n) || (jid[i + 1] != j);
+        bool dist = true, newpos = false;
+        if (has_prev) {
+            const uint32_t ip = vals[i - 1];
+            const int32_t ppos = pa[ip].pos, pend = pb[ip].read_end;
+            dist = (a.pos != ppos) || (b.read_end != pend);
+            newpos = a.pos != ppos;
+        }
+        eflag[i] = (newpos || last) ? 1u : 0u;       // emission points of the entropy loop (quirk Q1)
+        const uint32_t bits = b.bits;
+        const bool r1 = bits & PB_R1, rev = bits & PB_REV, um = bits & PB_UM, ppp = bits & PB_PPP;
+        const bool rel = um && (!ppcheck || ppp);
+        c0 = (uint32_t)(r1 && !rev) | ((uint32_t)(r1 && rev) << 6) | ((uint32_t)(!r1 && !rev) << 12) | ((uint32_t)(!r1 && rev) << 18) |
+             ((uint32_t)((bits & PB_MS) != 0) << 24);
+        c1 = (uint32_t)um | ((uint32_t)((bits & PB_BPP) != 0) << 6) | ((uint32_t)(ppcheck && ppp) << 12) | ((uint32_t)rel << 18) |
+             ((uint32_t)((bits & PB_XSP) != 0) << 24);
+        c2 = (uint32_t)((bits & PB_XSN) != 0) | ((uint32_t)dist << 6);
+        lmin = a.lstart; rmax = a.rend;
+        // Intron::minAnchorLength (intron.cc:84-86); the intron end comes from the junction table (k_junc_init)
+        anc = (uint32_t)min(b.start - a.lstart, a.rend - A.end[j]);
+        up = b.updown >> 16; down = b.updown & 0xffffu;
+    }
+    const SegCtx sc = seg_ctx(j, lane);
+    c0 = seg_reduce(c0, sc, OpAdd()); c1 = seg_reduce(c1, sc, OpAdd()); c2 = seg_reduce(c2, sc, OpAdd());
+    lmin = seg_reduce(lmin, sc, OpMin()); rmax = seg_reduce(rmax, sc, OpMax());
+    anc = seg_reduce(anc, sc, OpMax()); up = seg_reduce(up, sc, OpMax()); down = seg_reduce(down, sc, OpMax());
+    if (ok && sc.tail) {
+        uint32_t v;
+        if ((v = c0 & 63u)) atomicAdd(A.r1p + j, v);
+        if ((v = (c0 >> 6) & 63u)) atomicAdd(A.r1n + j, v);
+        if ((v = (c0 >> 12) & 63u)) atomicAdd(A.r2p + j, v);
+        if ((v = (c0 >> 18) & 63u)) atomicAdd(A.r2n + j, v);
+        if ((v = (c0 >> 24) & 63u)) atomicAdd(A.ms + j, v);
+        if ((v = c1 & 63u)) atomicAdd(A.um + j, v);
+        if ((v = (c1 >> 6) & 63u)) atomicAdd(A.bpp + j, v);
+        if ((v = (c1 >> 12) & 63u)) atomicAdd(A.ppp + j, v);
+        if ((v = (c1 >> 18) & 63u)) atomicAdd(A.rel + j, v);
+        if ((v = (c1 >> 24) & 63u)) atomicAdd(A.xsp + j, v);
+        if ((v = c2 & 63u)) atomicAdd(A.xsn + j, v);
+        if ((v = (c2 >> 6) & 63u)) atomicAdd(A.dist + j, v);
+        atomicMin(A.left + j, lmin); atomicMax(A.right + j, rmax);
+        atomicMax(A.anc + j, anc); atomicMax(A.up + j, up); atomicMax(A.down + j, down);
+    }
+}
+
+// Decodes the junction coordinates from the key of each segment head and initialises the accumulators.
+__global__ void __launch_bounds__(256) k_junc_init(uint32_t n_junc, const uint32_t* __restrict__ seg_start, const uint64_t* __restrict__ keys,
+                                                    const uint32_t* __restrict__ vals, const PairA* __restrict__ pa, const PairB* __restrict__ pb,
+                                                    const int32_t* __restrict__ read_tid, int32_t len_bits, JuncAcc A) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_junc) return;
+    const uint32_t s = seg_start[j];
+    const uint64_t key = keys[s];
+    const uint32_t idx = vals[s];
+    const int32_t start = pb[idx].start;
+    const int32_t size = (int32_t)(key & ((1ull << len_bits) - 1ull));
+    A.tid[j] = read_tid[pa[idx].rid];
+    A.start[j] = start; A.end[j] = start + size - 1;
+    A.left[j] = INT32_MAX; A.right[j] = INT32_MIN;
+}
+
+void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairA* pa, const PairB* pb,
+                      const int32_t* read_tid, int32_t len_bits, const JuncAcc& A, cudaStream_t st) {
+    if (n_junc) k_junc_init<<<(n_junc + 255) / 256, 256, 0, st>>>(n_junc, seg_start, keys, vals, pa, pb, read_tid, len_bits, A);
+}
+void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, int32_t ppcheck,
+                    const JuncAcc& A, uint32_t* eflag, cudaStream_t st) {
+    if (n) k_reduce1<<<(n + 255) / 256, 256, 0, st>>>(n, vals, jid, pa, pb, ppcheck, A, eflag);
+}
+
+// ================================================================================================
+// entropy (Junction::calcEntropy, junction.cc:718-749).  eflag marks the loop's emission points; their
+// compacted indices give the run-length terms; one thread per junction adds the terms in loop order.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_entropy_compact(uint32_t n, const uint32_t* __restrict__ eflag, const uint32_t* __restrict__ eoff,
+                                                          uint32_t* __restrict__ epos) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && eflag[i]) epos[eoff[i]] = i;
+}
+__global__ void __launch_bounds__(128) k_entropy_sum(uint32_t n_junc, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ eoff,
+                                                      const uint32_t* __restrict__ epos, double* __restrict__ entropy) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_junc) return;
+    const uint32_t s = seg_start[j], e = seg_start[j + 1], n = e - s;
+    double sum = 0.0;
+    if (n > 1) {
+        const uint32_t k0 = eoff[s], k1 = eoff[e - 1];       // the last element of a segment always emits
+        uint32_t prev = s;                                   // terms count elements since the previous emission
+        bool first = true;
+        for (uint32_t k = k0; k <= k1; k++) {
+            const uint32_t i = epos[k];
+            const uint32_t term = first ? (i - s + 1) : (i - prev);
+            first = false; prev = i;
+            const double p = (double)term / (double)n;
+            sum += p * log2(p);
+        }
+    }
+    entropy[j] = fabs(sum);
+}
+void launch_entropy_compact(uint32_t n, const uint32_t* eflag, const uint32_t* eoff, uint32_t* epos, cudaStream_t st) {
+    if (n) k_entropy_compact<<<(n + 255) / 256, 256, 0, st>>>(n, eflag, eoff, epos);
+}
+void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32_t* eoff, const uint32_t* epos, double* entropy, cudaStream_t st) {
+    if (n_junc) k_entropy_sum<<<(n_junc + 127) / 128, 128, 0, st>>>(n_junc, seg_start, eoff, epos, entropy);
+}
+
+// ================================================================================================
+// k_match: AlignmentInfo::calcMatchStats (junction.cc:147-240) = getPaddedQuerySeq / getPaddedGenomeSeq
+// (bam_alignment.cc:341-462) + hammingDistance + getNbMatchesFromEnd/Start, fused into one walk that never
+// materialises the strings.  One warp per (read, junction) pair; the CIGAR walk is warp-uniform, the 32 lanes
+// stride over the columns of each M/=/X block.  Quirks Q3-Q6 are kept.
+// ================================================================================================
+struct SideResult { uint32_t cols, mism; int32_t first_mm, last_mm; };   // string indices of first / last mismatch (-1: none)
+
+__device__ __forceinline__ SideResult walk_side(const Genome& G, uint64_t gbase /* goff[tid] */, int64_t glen,
+                                                const uint32_t* __restrict__ cg, int32_t n_cig, int32_t pos,
+                                                const uint8_t* __restrict__ seq, int32_t qoff, int32_t qsize,
+                                                int32_t wstart, int32_t wend, int lane, uint32_t& err) {
+    SideResult r{0u, 0u, -1, -1};
+    int32_t qPos = 0, rPos = pos;
+    for (int32_t k = 0; k < n_cig; k++) {
+        const uint32_t w = __ldg(cg + k), op = cig_op(w); const int32_t L = cig_len(w);
+        const bool cr = op_ref(op), cq = op_query(op);
+        if (rPos < wstart) { if (cr) rPos += L; if (cq) qPos += L; continue; }          // Q4: op-granular skip
+        if ((rPos > wend && op != OP_I) || (op == OP_N && rPos + L > wend)) break;      // Q5
+        if (cq) {
+            const int32_t len = (rPos + L > wend && op != OP_I) ? wend - rPos + 1 : L;
+            if (len == 0) { err |= ERR_ZERO_LEN; break; }
+            if (qPos + len > qsize) { err |= ERR_QUERY_RANGE; break; }
+            if (op == OP_I) {
+                // query bases against 'X' padding in the genome string: never equal (no 'X' in the BAM alphabet)
+                if (r.first_mm < 0) r.first_mm = (int32_t)r.cols;
+                r.last_mm = (int32_t)r.cols + len - 1;
+                r.mism += (uint32_t)len;
+            } else {
+                if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
+                const int32_t q0 = qoff + qPos;
+                for (int32_t c0 = 0; c0 < len; c0 += 32) {
+                    const int32_t c = c0 + lane;
+                    bool mm = false;
+                    if (c < len) {
+                        const int32_t qi = q0 + c;
+                        const uint32_t nib = (__ldg(seq + (qi >> 1)) >> ((~qi & 1) << 2)) & 0xfu;
+                        mm = !base_matches(G, gbase + (uint64_t)(uint32_t)(rPos + c), nib);
+                    }
+                    const uint32_t b = __ballot_sync(FULL, mm);
+                    if (b) {
+                        if (r.first_mm < 0) r.first_mm = (int32_t)r.cols + c0 + (__ffs(b) - 1);
+                        r.last_mm = (int32_t)r.cols + c0 + (31 - __clz(b));
+                        r.mism += __popc(b);
+                    }
+                }
+            }
+            r.cols += (uint32_t)len;
+        } else if (cr) {                                                                   // D or N inside the window: 'X' vs genome
+            const int32_t len = rPos + L > wend ? wend - rPos + 1 : L;
+            if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
+            if (G.n_exc_x == 0) {
+                if (len > 0) { if (r.first_mm < 0) r.first_mm = (int32_t)r.cols; r.last_mm = (int32_t)r.cols + len - 1; r.mism += (uint32_t)len; }
+            } else {
+                for (int32_t c0 = 0; c0 < len; c0 += 32) {
+                    const int32_t c = c0 + lane;
+                    const bool mm = (c < len) && genome_char(G, gbase + (uint64_t)(uint32_t)(rPos + c)) != (uint8_t)'X';
+                    const uint32_t b = __ballot_sync(FULL, mm);
+                    if (b) {
+                        if (r.first_mm < 0) r.first_mm = (int32_t)r.cols + c0 + (__ffs(b) - 1);
+                        r.last_mm = (int32_t)r.cols + c0 + (31 - __clz(b));
+                        r.mism += __popc(b);
+                    }
+                }
+            }
+            r.cols += (uint32_t)len;
+        }
+        if (cr) rPos += L;
+        if (cq) qPos += L;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+                                                const PairA* __restrict__ pa, const PairB* __restrict__ pb,
+                                                Reads R, Genome G, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const uint32_t j = jid[i];
+    const uint32_t idx = vals[i];
+    const PairA a = pa[idx]; const PairB b = pb[idx];
+    const int32_t start = A.start[j], end = A.end[j], left = A.left[j], right = A.right[j];
+    const int32_t tid = A.tid[j];
+    const int32_t lq = R.l_qseq[a.rid];
+    uint32_t err = 0, mmes, minMatch, nbMism;
+    const int32_t leftEnd = start - 1, rightStart = end + 1;
+    if (lq <= 1) {                                                    // junction.cc:168-185
+        const uint32_t um = (uint32_t)(leftEnd - left + 1), dm = (uint32_t)(right - rightStart + 1);
+        nbMism = 0; minMatch = 0; mmes = min(um, dm);
+    } else {
+        const uint32_t* cg = R.cigar + R.cigar_off[a.rid];
+        const int32_t n_cig = (int32_t)(R.cigar_off[a.rid + 1] - R.cigar_off[a.rid]);
+        const uint64_t so = R.seq_off[a.rid];
+        if ((int64_t)(R.seq_off[a.rid + 1] - so) < (int64_t)((lq + 1) >> 1)) err |= ERR_SEQ_MISSING;
+        // getQuerySeqAfterClipping (bam_alignment.cc:256-264), quirk Q3: only a FIRST / LAST op of type S clips
+        const uint32_t wf = __ldg(cg), wl = __ldg(cg + n_cig - 1);
+        int32_t ds = cig_op(wf) == OP_S ? cig_len(wf) : 0, de = cig_op(wl) == OP_S ? cig_len(wl) : 0;
+        if (ds > lq) ds = lq;
+        int64_t qs = (int64_t)lq - ds - de + 1; if (qs > lq - ds) qs = lq - ds; if (qs < 0) qs = 0;
+        const int64_t glen = G.glen[tid];
+        if (left > b.read_end || leftEnd < a.pos || rightStart > b.read_end || right < a.pos) err |= ERR_NO_PRESENCE;
+        if (glen < 0) err |= ERR_GENOME_RANGE;
+        SideResult L{0, 0, -1, -1}, Rr{0, 0, -1, -1};
+        if (!err) {
+            const uint64_t gbase = G.goff[tid];
+            L = walk_side(G, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, left, leftEnd, lane, err);
+            Rr = walk_side(G, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, rightStart, right, lane, err);
+            if (L.cols == 0 || Rr.cols == 0) err |= ERR_EMPTY_ANCHOR;
+        }
+        const uint32_t upMatches = L.cols - L.mism, downMatches = Rr.cols - Rr.mism;
+        nbMism = L.mism + Rr.mism;
+        const uint32_t us = L.last_mm < 0 ? L.cols : (L.cols - 1u - (uint32_t)L.last_mm);     // getNbMatchesFromEnd
+        const uint32_t dsm = Rr.first_mm < 0 ? Rr.cols : (uint32_t)Rr.first_mm;               // getNbMatchesFromStart
+        minMatch = min(us, dsm);
+        mmes = min(upMatches, downMatches);
+    }
+    if (lane == 0) {
+        pm[i] = make_uint4(mmes, minMatch, nbMism, 0u);
+        if (err) atomicOr(errw, err);
+    }
+}
+void launch_match(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& G,
+                  const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
+    if (!n) return;
+    const uint64_t threads = (uint64_t)n * 32;
+    k_match<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pa, pb, R, G, A, pm, err);
+}
+
+// ================================================================================================
+// k_reduce2: Junction::calcMismatchStats (junction.cc:862-909) as a segmented reduction
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_reduce2(uint32_t n, const uint32_t* __restrict__ jid, const uint4* __restrict__ pm, JuncAcc A) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool ok = i < n;
+    uint32_t j = 0xffffffffu, mmes = 0, mism = 0, firstmm = 0xffffffffu, maxmin = 0, bin = 31;
+    if (ok) {
+        j = jid[i];
+        const uint4 v = pm[i];
+        mmes = v.x; mism = v.z; maxmin = v.y;
+        if (v.y > 0) firstmm = v.y;
+        bin = min(v.y, (uint32_t)PJ_NB_JAD);
+    }
+    const SegCtx sc = seg_ctx(j, lane);
+    mmes = seg_reduce(mmes, sc, OpMax()); mism = seg_reduce(mism, sc, OpAdd());
+    firstmm = seg_reduce(firstmm, sc, OpMin()); maxmin = seg_reduce(maxmin, sc, OpMax());
+    // JAD histogram: one atomic per distinct (junction, bin) in the warp
+    const uint32_t hk = ok ? (j * 32u + bin) : 0xffffffffu;
+    const uint32_t m = __match_any_sync(FULL, hk);
+    if (ok && (m & ((1u << lane) - 1u)) == 0) atomicAdd(A.jadhist + (size_t)j * (PJ_NB_JAD + 1) + bin, (uint32_t)__popc(m));
+    if (ok && sc.tail) {
+        atomicMax(A.maxmmes + j, mmes);
+        if (mism) atomicAdd(A.mism + j, mism);
+        atomicMin(A.firstmm + j, firstmm);
+        atomicMax(A.maxminmatch + j, maxmin);
+    }
+}
+void launch_reduce2(uint32_t n, const uint32_t* jid, const uint4* pm, const JuncAcc& A, cudaStream_t st) {
+    if (n) k_reduce2<<<(n + 255) / 256, 256, 0, st>>>(n, jid, pm, A);
+}
+
+// ================================================================================================
+// k_finalize: per junction strands (junction.cc:531-559), motif (:504-516, 289-326), Hamming (:823-857),
+// suspicious flag (:897-908), JAD suffix sums, and the output row.
+// ================================================================================================
+__global__ void __launch_bounds__(128) k_finalize(uint32_t n_junc, const uint32_t* __restrict__ seg_start, JuncAcc A, Genome G,
+                                                   const double* __restrict__ entropy, pj_junction* __restrict__ rows, uint32_t* __restrict__ errw) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_junc) return;
+    pj_junction o;
+    memset(&o, 0, sizeof o);
+    const int32_t tid = A.tid[j], s = A.start[j], e = A.end[j], left = A.left[j], right = A.right[j];
+    const uint32_t n = seg_start[j + 1] - seg_start[j];
+    o.tid = tid; o.start = s; o.end = e; o.left = left; o.right = right;
+    o.nb_raw_aln = n; o.nb_dist_aln = A.dist[j]; o.nb_ms_aln = A.ms[j]; o.nb_um_aln = A.um[j]; o.nb_bpp_aln = A.bpp[j];
+    o.nb_ppp_aln = A.ppp[j]; o.nb_rel_aln = A.rel[j];
+    o.nb_r1_pos = A.r1p[j]; o.nb_r1_neg = A.r1n[j]; o.nb_r2_pos = A.r2p[j]; o.nb_r2_neg = A.r2n[j];
+    o.nb_xs_pos = A.xsp[j]; o.nb_xs_neg = A.xsn[j];
+    o.max_min_anc = A.anc[j]; o.maxmmes = A.maxmmes[j]; o.nb_mismatches = A.mism[j];
+    o.nb_up_juncs = A.up[j]; o.nb_down_juncs = A.down[j];
+    o.entropy = entropy[j];
+    // determineStrandFromReads: 0.95 rule in fp64 exactly as the reference evaluates it
+    const double tot = (double)n;
+    uint8_t rs = PJ_STRAND_UNKNOWN;
+    if ((double)o.nb_xs_pos / tot >= 0.95) rs = PJ_STRAND_POS; else if ((double)o.nb_xs_neg / tot >= 0.95) rs = PJ_STRAND_NEG;
+    o.read_strand = rs;
+    // JAD_k = #reads with minMatch >= k  (suffix sums of the minMatch histogram)
+    {
+        const uint32_t* h = A.jadhist + (size_t)j * (PJ_NB_JAD + 1);
+        uint32_t run = h[PJ_NB_JAD];
+        for (int k = PJ_NB_JAD - 1; k >= 0; k--) { o.jad[k] = run; run += h[k]; }
+    }
+    {
+        const uint32_t fm = A.firstmm[j] == 0xffffffffu ? 100000000u : A.firstmm[j];
+        o.suspicious = (o.nb_mismatches > 0 && fm < 20 && !(A.maxminmatch[j] > fm)) ? 1 : 0;
+    }
+    uint32_t err = 0;
+    const int64_t glen = G.glen[tid];
+    o.hamming5p = 10; o.hamming3p = 10; o.canonical_ss = 'N'; o.ss_strand = PJ_STRAND_UNKNOWN; o.consensus_strand = rs;
+    if (glen < 0 || s < 0 || (int64_t)s + 9 >= glen || e - 9 < 0 || e >= glen || left < 0 || right >= glen || left >= s || right <= e) {
+        err |= ERR_GENOME_RANGE;                      // the reference throws in processJunctionWindow (junction.cc:573-633)
+    } else {
+        const uint64_t gb = G.goff[tid];
+        const uint8_t d0 = genome_char(G, gb + s), d1 = genome_char(G, gb + s + 1);
+        const uint8_t a0 = genome_char(G, gb + e - 1), a1 = genome_char(G, gb + e);
+        uint8_t css = 'N', ss = PJ_STRAND_UNKNOWN;
+        const uint32_t m = ((uint32_t)d0 << 24) | ((uint32_t)d1 << 16) | ((uint32_t)a0 << 8) | a1;
+        switch (m) {
+        case 0x47544147u: css = 'C'; ss = PJ_STRAND_POS; break;     // GTAG
+        case 0x43544143u: css = 'C'; ss = PJ_STRAND_NEG; break;     // CTAC
+        case 0x41544143u: css = 'S'; ss = PJ_STRAND_POS; break;     // ATAC
+        case 0x47434147u: css = 'S'; ss = PJ_STRAND_POS; break;     // GCAG
+        case 0x47544154u: css = 'S'; ss = PJ_STRAND_NEG; break;     // GTAT
+        case 0x43544743u: css = 'S'; ss = PJ_STRAND_NEG; break;     // CTGC
+        default: break;
+        }
+        o.canonical_ss = css; o.ss_strand = ss;
+        const uint8_t cs = rs == ss ? rs : rs == PJ_STRAND_UNKNOWN ? ss : ss == PJ_STRAND_UNKNOWN ? rs : (uint8_t)PJ_STRAND_UNKNOWN;
+        o.consensus_strand = cs;
+        if (cs == PJ_STRAND_NEG) { o.ss1[0] = revcomp_char(a1); o.ss1[1] = revcomp_char(a0); o.ss2[0] = revcomp_char(d1); o.ss2[1] = revcomp_char(d0); }
+        else { o.ss1[0] = d0; o.ss1[1] = d1; o.ss2[0] = a0; o.ss2[1] = a1; }
+        // Hamming: la = last <=10 bases of the left anchor vs ri = first |la| bases of [e-9,e];
+        //          ra = first <=10 bases of the right anchor vs li = first |ra| bases of [s,s+9]   (quirk Q7)
+        const int32_t lan = min(10, s - left), ran = min(10, right - e);
+        uint32_t hl = 0, hr = 0;
+        for (int32_t k = 0; k < lan; k++) {
+            uint8_t x = genome_char(G, gb + (s - lan + k)), y = genome_char(G, gb + (e - 9 + k));
+            if (cs == PJ_STRAND_NEG) { x = revcomp_char(x); y = revcomp_char(y); }
+            hl += x != y;
+        }
+        for (int32_t k = 0; k < ran; k++) {
+            uint8_t x = genome_char(G, gb + (e + 1 + k)), y = genome_char(G, gb + (s + k));
+            if (cs == PJ_STRAND_NEG) { x = revcomp_char(x); y = revcomp_char(y); }
+            hr += x != y;
+        }
+        if (cs == PJ_STRAND_NEG) { o.hamming5p = hr; o.hamming3p = hl; } else { o.hamming5p = hl; o.hamming3p = hr; }
+    }
+    rows[j] = o;
+    if (err) atomicOr(errw, err);
+}
+void launch_finalize(uint32_t n_junc, const uint32_t* seg_start, const JuncAcc& A, const Genome& G, const double* entropy,
+                     pj_junction* rows, uint32_t* err, cudaStream_t st) {
+    if (n_junc) k_finalize<<<(n_junc + 127) / 128, 128, 0, st>>>(n_junc, seg_start, A, G, entropy, rows, err);
+}
+
+} // namespace pjk

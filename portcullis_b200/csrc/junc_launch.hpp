@@ -1,0 +1,50 @@
+// junc_launch.hpp — host-callable launchers of the kernels in junc_kernels.cu.
+#pragma once
+#include "junc_kernels.cuh"
+
+namespace pjk {
+
+// per-target accumulators of k_scan_reads (RegionResult scalars)
+struct TargetAcc {
+    unsigned long long* spliced; unsigned long long* unspliced; unsigned long long* sumq;
+    int32_t* minq; int32_t* maxq;
+};
+
+// per-junction accumulators, struct of arrays (every field is an integer reduction -> atomics are deterministic)
+struct JuncAcc {
+    int32_t *tid, *start, *end, *left, *right;
+    uint32_t *r1p, *r1n, *r2p, *r2n, *ms, *um, *bpp, *ppp, *rel, *xsp, *xsn, *dist, *anc, *up, *down;
+    uint32_t *maxmmes, *mism, *firstmm, *maxminmatch;
+    uint32_t *jadhist;          // [n_junc][PJ_NB_JAD+1] histogram of min(minMatch, 20)
+};
+
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_tmp, uint32_t* total_dev, cudaStream_t st);
+uint64_t scan_tmp_elems(uint64_t n);
+void launch_fill_i32(int32_t* a, int64_t n, int32_t v, cudaStream_t st);
+void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st);
+void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st);
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
+                        uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st);
+void launch_scan_reads(const Reads& R, const int32_t* tlen, int32_t n_targets, uint32_t* npairs, int32_t* read_end,
+                       const TargetAcc& T, uint32_t* max_nlen, cudaStream_t st);
+void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff, int32_t len_bits, int32_t orientation,
+                       const uint32_t* pair_off, const uint32_t* npairs, const int32_t* read_end,
+                       uint64_t* keys, PairA* pa, PairB* pb, uint32_t* err, cudaStream_t st);
+uint32_t rs_num_blocks(uint32_t n);
+int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
+                      uint32_t* counts, uint32_t* scan_tmp, uint32_t* total_tmp, cudaStream_t st, int* n_launches);
+void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st);
+void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint32_t* jid, uint32_t* seg_start, uint32_t n_junc, cudaStream_t st);
+void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairA* pa, const PairB* pb,
+                      const int32_t* read_tid, int32_t len_bits, const JuncAcc& A, cudaStream_t st);
+void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, int32_t ppcheck,
+                    const JuncAcc& A, uint32_t* eflag, cudaStream_t st);
+void launch_entropy_compact(uint32_t n, const uint32_t* eflag, const uint32_t* eoff, uint32_t* epos, cudaStream_t st);
+void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32_t* eoff, const uint32_t* epos, double* entropy, cudaStream_t st);
+void launch_match(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& G,
+                  const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st);
+void launch_reduce2(uint32_t n, const uint32_t* jid, const uint4* pm, const JuncAcc& A, cudaStream_t st);
+void launch_finalize(uint32_t n_junc, const uint32_t* seg_start, const JuncAcc& A, const Genome& G, const double* entropy,
+                     pj_junction* rows, uint32_t* err, cudaStream_t st);
+
+} // namespace pjk

@@ -1,0 +1,493 @@
+// pj_api.cu — the extern "C" layer of include/portcullis_junc.h: context, genome residency, double-buffered
+// pinned staging, shard arena in HBM and the kernel pipeline driver.  One context = one B200.
+#include "junc_launch.hpp"
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <climits>
+
+using namespace pjk;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct StagingSlot {
+    // pinned host columns
+    int32_t *tid = nullptr, *pos = nullptr, *l_qseq = nullptr, *mtid = nullptr, *mpos = nullptr;
+    uint16_t* flag = nullptr; uint8_t *mapq = nullptr, *xs = nullptr;
+    uint32_t *cigar_off = nullptr, *cigar = nullptr; uint64_t* seq_off = nullptr; uint8_t* seq4 = nullptr;
+    int64_t cap_rec = 0, cap_cig = 0, cap_seq = 0;
+    cudaEvent_t done = nullptr; bool in_flight = false;
+};
+
+struct StageTime { const char* name; cudaEvent_t ev; };
+
+} // namespace
+
+struct pj_ctx {
+    int device = 0; int orientation = PJ_ORIENT_UNKNOWN;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    std::string err;
+    // targets / genome
+    int32_t n_targets = 0;
+    std::vector<int32_t> h_tlen; std::vector<uint64_t> h_toff, h_goff; std::vector<int64_t> h_glen;
+    int32_t* d_tlen = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_goff = nullptr; int64_t* d_glen = nullptr;
+    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint64_t g_total_bases = 0;
+    uint64_t* d_exc_pos = nullptr; uint8_t* d_exc_byte = nullptr; uint32_t* d_exc_count = nullptr; uint32_t exc_cap = 1u << 20;
+    int32_t n_exc = 0, n_exc_x = 0; bool genome_dirty = false;
+    uint8_t* h_graw[2] = {nullptr, nullptr}; uint8_t* d_graw[2] = {nullptr, nullptr}; cudaEvent_t graw_ev[2] = {nullptr, nullptr};
+    static constexpr size_t GRAW_CHUNK = 64u << 20;
+    // shard arena
+    bool shard_open = false;
+    int64_t n_rec = 0; uint64_t n_cig = 0, n_seq = 0;
+    DevBuf<int32_t> tid, pos, l_qseq, mtid, mpos; DevBuf<uint16_t> flag; DevBuf<uint8_t> mapq, xs, seq4;
+    DevBuf<uint32_t> cigar_off, cigar; DevBuf<uint64_t> seq_off;
+    StagingSlot slot[2]; int next_slot = 0;
+    cudaEvent_t copies_done = nullptr;
+    // per-target accumulators + misc device scalars
+    unsigned long long *d_spliced = nullptr, *d_unspliced = nullptr, *d_sumq = nullptr; int32_t *d_minq = nullptr, *d_maxq = nullptr;
+    uint32_t* d_scalars = nullptr;    // [0]=err [1]=max_nlen [2]=P [3]=J [4]=E [5]=scratch total
+    uint32_t* h_scalars = nullptr;    // pinned mirror
+    // results
+    pj_junction* d_rows = nullptr; size_t rows_cap = 0; int64_t n_junc = 0; uint64_t n_pairs = 0;
+    bool have_result = false;
+    // timing
+    std::vector<StageTime> stages; size_t n_stage = 0; float total_ms = 0; int n_launches = 0;
+    std::vector<float> stage_ms; std::vector<const char*> stage_names;
+};
+
+namespace {
+
+int fail(pj_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((c), PJ_ECUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+
+template <typename T> int ensure(pj_ctx* c, DevBuf<T>& b, size_t need, size_t keep, cudaStream_t st) {
+    if (need <= b.cap) return PJ_OK;
+    size_t ncap = std::max(need, b.cap + b.cap / 2 + 1024);
+    T* np = nullptr;
+    CU(c, cudaMalloc(&np, ncap * sizeof(T)));
+    if (b.p && keep) CU(c, cudaMemcpyAsync(np, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (b.p) { CU(c, cudaStreamSynchronize(st)); cudaFree(b.p); }
+    b.p = np; b.cap = ncap;
+    return PJ_OK;
+}
+
+void free_slot(StagingSlot& s) {
+    cudaFreeHost(s.tid); cudaFreeHost(s.pos); cudaFreeHost(s.l_qseq); cudaFreeHost(s.mtid); cudaFreeHost(s.mpos);
+    cudaFreeHost(s.flag); cudaFreeHost(s.mapq); cudaFreeHost(s.xs); cudaFreeHost(s.cigar_off); cudaFreeHost(s.cigar);
+    cudaFreeHost(s.seq_off); cudaFreeHost(s.seq4);
+    s.tid = s.pos = s.l_qseq = s.mtid = s.mpos = nullptr; s.flag = nullptr; s.mapq = s.xs = s.seq4 = nullptr;
+    s.cigar_off = s.cigar = nullptr; s.seq_off = nullptr; s.cap_rec = s.cap_cig = s.cap_seq = 0;
+}
+
+template <typename T> cudaError_t pin(T** p, size_t n) { return cudaMallocHost((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
+
+int alloc_slot(pj_ctx* c, StagingSlot& s, int64_t cr, int64_t cc, int64_t cs) {
+    if (cr <= s.cap_rec && cc <= s.cap_cig && cs <= s.cap_seq && s.tid) return PJ_OK;
+    cr = std::max(cr, s.cap_rec); cc = std::max(cc, s.cap_cig); cs = std::max(cs, s.cap_seq);
+    free_slot(s);
+    CU(c, pin(&s.tid, cr)); CU(c, pin(&s.pos, cr)); CU(c, pin(&s.l_qseq, cr)); CU(c, pin(&s.mtid, cr)); CU(c, pin(&s.mpos, cr));
+    CU(c, pin(&s.flag, cr)); CU(c, pin(&s.mapq, cr)); CU(c, pin(&s.xs, cr));
+    CU(c, pin(&s.cigar_off, cr + 1)); CU(c, pin(&s.cigar, cc)); CU(c, pin(&s.seq_off, cr + 1)); CU(c, pin(&s.seq4, cs));
+    s.cap_rec = cr; s.cap_cig = cc; s.cap_seq = cs;
+    s.cigar_off[0] = 0; s.seq_off[0] = 0;
+    return PJ_OK;
+}
+
+int bit_length(uint64_t v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
+
+void mark(pj_ctx* c, const char* name) {
+    if (c->n_stage >= c->stages.size()) { StageTime s{name, nullptr}; cudaEventCreate(&s.ev); c->stages.push_back(s); }
+    c->stages[c->n_stage].name = name;
+    cudaEventRecord(c->stages[c->n_stage].ev, c->compute_stream);
+    c->n_stage++;
+}
+
+// sort + upload the "other exception byte" table after genome uploads
+int finish_genome(pj_ctx* c) {
+    if (!c->genome_dirty) return PJ_OK;
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    uint32_t cnt = 0;
+    CU(c, cudaMemcpy(&cnt, c->d_exc_count, sizeof cnt, cudaMemcpyDeviceToHost));
+    if (cnt > c->exc_cap)
+        return fail(c, PJ_EDATA, "genome holds %u bytes outside ACGTN after upper-casing (limit %u): not a nucleotide FASTA?", cnt, c->exc_cap);
+    std::vector<uint64_t> pos(cnt); std::vector<uint8_t> byt(cnt);
+    if (cnt) {
+        CU(c, cudaMemcpy(pos.data(), c->d_exc_pos, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(byt.data(), c->d_exc_byte, cnt, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> ord(cnt); for (uint32_t i = 0; i < cnt; i++) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return pos[a] < pos[b]; });
+        std::vector<uint64_t> p2(cnt); std::vector<uint8_t> b2(cnt);
+        for (uint32_t i = 0; i < cnt; i++) { p2[i] = pos[ord[i]]; b2[i] = byt[ord[i]]; }
+        CU(c, cudaMemcpy(c->d_exc_pos, p2.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->d_exc_byte, b2.data(), cnt, cudaMemcpyHostToDevice));
+        c->n_exc_x = (int32_t)std::count(b2.begin(), b2.end(), (uint8_t)'X');
+    } else c->n_exc_x = 0;
+    c->n_exc = (int32_t)cnt;
+    c->genome_dirty = false;
+    return PJ_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+static_assert(sizeof(pj_junction) == 256, "pj_junction layout changed: update the bindings");
+int pj_abi_version(void) { return PJ_ABI_VERSION; }
+int pj_junction_size(void) { return (int)sizeof(pj_junction); }
+const char* pj_global_last_error(void) { return g_last_error.c_str(); }
+const char* pj_last_error(const pj_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int pj_create(const pj_config* cfg, pj_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, PJ_EINVAL, "pj_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, PJ_ECUDA, "pj_create: no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PJ_EINVAL, "pj_create: device %d out of range (0..%d)", cfg->device, ndev - 1);
+    if (cfg->orientation < PJ_ORIENT_SE || cfg->orientation > PJ_ORIENT_UNKNOWN) return fail(nullptr, PJ_EINVAL, "pj_create: bad orientation %d", cfg->orientation);
+    pj_ctx* c = new pj_ctx();
+    c->device = cfg->device; c->orientation = cfg->orientation;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+    CU(c, cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
+    for (int s = 0; s < 2; s++) { CU(c, cudaEventCreateWithFlags(&c->slot[s].done, cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&c->graw_ev[s], cudaEventDisableTiming)); }
+    CU(c, cudaMalloc(&c->d_scalars, 16 * sizeof(uint32_t)));
+    CU(c, cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(uint32_t)));
+    // keep stream-ordered allocations cached between shards
+    cudaMemPool_t pool; CU(c, cudaDeviceGetDefaultMemPool(&pool, c->device));
+    uint64_t thr = UINT64_MAX; CU(c, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return PJ_OK;
+}
+
+void pj_destroy(pj_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
+    c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_();
+    for (int s = 0; s < 2; s++) { free_slot(c->slot[s]); if (c->slot[s].done) cudaEventDestroy(c->slot[s].done); if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
+                                  if (c->h_graw[s]) cudaFreeHost(c->h_graw[s]); if (c->d_graw[s]) cudaFree(c->d_graw[s]); }
+    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx);
+    cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
+    cudaFree(c->d_spliced); cudaFree(c->d_unspliced); cudaFree(c->d_sumq); cudaFree(c->d_minq); cudaFree(c->d_maxq);
+    cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
+    for (auto& s : c->stages) cudaEventDestroy(s.ev);
+    if (c->copies_done) cudaEventDestroy(c->copies_done);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
+    delete c;
+}
+
+int pj_targets_set(pj_ctx* c, int32_t n_targets, const int32_t* target_len) {
+    if (!c || n_targets <= 0 || !target_len) return fail(c, PJ_EINVAL, "pj_targets_set: bad arguments");
+    if (c->n_targets) return fail(c, PJ_ESTATE, "pj_targets_set: targets already set");
+    CU(c, cudaSetDevice(c->device));
+    c->n_targets = n_targets;
+    c->h_tlen.assign(target_len, target_len + n_targets);
+    c->h_toff.assign(n_targets + 1, 0); c->h_goff.assign(n_targets, 0); c->h_glen.assign(n_targets, -1);
+    uint64_t g = 0;
+    for (int32_t t = 0; t < n_targets; t++) {
+        if (target_len[t] < 0) return fail(c, PJ_EINVAL, "pj_targets_set: negative target length");
+        c->h_toff[t + 1] = c->h_toff[t] + (uint64_t)target_len[t];
+        c->h_goff[t] = g; g += ((uint64_t)target_len[t] + 63) / 64 * 64 + 64;
+    }
+    c->g_total_bases = g;
+    CU(c, cudaMalloc(&c->d_tlen, n_targets * sizeof(int32_t))); CU(c, cudaMalloc(&c->d_toff, (n_targets + 1) * sizeof(uint64_t)));
+    CU(c, cudaMalloc(&c->d_goff, n_targets * sizeof(uint64_t))); CU(c, cudaMalloc(&c->d_glen, n_targets * sizeof(int64_t)));
+    CU(c, cudaMemcpy(c->d_tlen, c->h_tlen.data(), n_targets * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_toff, c->h_toff.data(), (n_targets + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_goff, c->h_goff.data(), n_targets * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(c->d_glen, c->h_glen.data(), n_targets * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CU(c, cudaMalloc(&c->d_g2, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMalloc(&c->d_gx, g / 64 * sizeof(uint64_t) + 64));
+    CU(c, cudaMemset(c->d_g2, 0, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMemset(c->d_gx, 0, g / 64 * sizeof(uint64_t) + 64));
+    CU(c, cudaMalloc(&c->d_exc_pos, c->exc_cap * sizeof(uint64_t))); CU(c, cudaMalloc(&c->d_exc_byte, c->exc_cap));
+    CU(c, cudaMalloc(&c->d_exc_count, sizeof(uint32_t))); CU(c, cudaMemset(c->d_exc_count, 0, sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->d_spliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_unspliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_sumq, n_targets * 8));
+    CU(c, cudaMalloc(&c->d_minq, n_targets * 4)); CU(c, cudaMalloc(&c->d_maxq, n_targets * 4));
+    return PJ_OK;
+}
+
+int pj_genome_set_target(pj_ctx* c, int32_t tid, const char* bases, int64_t n_bases) {
+    if (!c || !c->n_targets) return fail(c, PJ_ESTATE, "pj_genome_set_target: call pj_targets_set first");
+    if (tid < 0 || tid >= c->n_targets || n_bases < 0 || (n_bases && !bases)) return fail(c, PJ_EINVAL, "pj_genome_set_target: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    const int64_t n = std::min<int64_t>(n_bases, c->h_tlen[tid]);   // windows never reach past the BAM header length
+    for (int s = 0; s < 2; s++) if (!c->h_graw[s]) { CU(c, cudaMallocHost((void**)&c->h_graw[s], pj_ctx::GRAW_CHUNK)); CU(c, cudaMalloc(&c->d_graw[s], pj_ctx::GRAW_CHUNK)); }
+    int s = 0;
+    for (int64_t o = 0; o < n; o += (int64_t)pj_ctx::GRAW_CHUNK, s ^= 1) {
+        const int64_t k = std::min<int64_t>((int64_t)pj_ctx::GRAW_CHUNK, n - o);
+        CU(c, cudaEventSynchronize(c->graw_ev[s]));                  // slot free again?
+        memcpy(c->h_graw[s], bases + o, (size_t)k);
+        CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->copy_stream));
+        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->copy_stream);
+        CU(c, cudaEventRecord(c->graw_ev[s], c->copy_stream));
+    }
+    c->h_glen[tid] = n_bases < c->h_tlen[tid] ? n_bases : (int64_t)c->h_tlen[tid];
+    CU(c, cudaMemcpyAsync(c->d_glen + tid, &c->h_glen[tid], sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaGetLastError());
+    c->genome_dirty = true;
+    return PJ_OK;
+}
+
+int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int64_t n_seq_bytes_hint) {
+    if (!c || !c->n_targets) return fail(c, PJ_ESTATE, "pj_shard_begin: call pj_targets_set first");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->compute_stream));
+    c->n_rec = 0; c->n_cig = 0; c->n_seq = 0; c->have_result = false; c->n_junc = 0; c->n_pairs = 0;
+    cudaStream_t st = c->copy_stream;
+    const size_t r = (size_t)std::max<int64_t>(n_records_hint, 1024);
+    int rc;
+    if ((rc = ensure(c, c->tid, r, 0, st)) || (rc = ensure(c, c->pos, r, 0, st)) || (rc = ensure(c, c->l_qseq, r, 0, st)) ||
+        (rc = ensure(c, c->mtid, r, 0, st)) || (rc = ensure(c, c->mpos, r, 0, st)) || (rc = ensure(c, c->flag, r, 0, st)) ||
+        (rc = ensure(c, c->mapq, r, 0, st)) || (rc = ensure(c, c->xs, r, 0, st)) || (rc = ensure(c, c->cigar_off, r + 1, 0, st)) ||
+        (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024), 0, st)) ||
+        (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 16, 0, st))) return rc;
+    CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
+    CU(c, cudaMemsetAsync(c->seq_off.p, 0, sizeof(uint64_t), st));
+    c->shard_open = true;
+    return PJ_OK;
+}
+
+int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out) {
+    if (!c || !out || cap_records < 0 || cap_cigar < 0 || cap_seq_bytes < 0) return fail(c, PJ_EINVAL, "pj_staging_acquire: bad arguments");
+    CU(c, cudaSetDevice(c->device));
+    StagingSlot& s = c->slot[c->next_slot];
+    if (s.in_flight) { CU(c, cudaEventSynchronize(s.done)); s.in_flight = false; }
+    int rc = alloc_slot(c, s, std::max<int64_t>(cap_records, 1), std::max<int64_t>(cap_cigar, 1), std::max<int64_t>(cap_seq_bytes, 1));
+    if (rc) return rc;
+    c->next_slot ^= 1;
+    out->n_records = 0; out->tid = s.tid; out->pos = s.pos; out->flag = s.flag; out->mapq = s.mapq; out->xs = s.xs; out->l_qseq = s.l_qseq;
+    out->mtid = s.mtid; out->mpos = s.mpos; out->cigar_off = s.cigar_off; out->cigar = s.cigar; out->seq_off = s.seq_off; out->seq4 = s.seq4;
+    return PJ_OK;
+}
+
+int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
+    if (!c || !b) return fail(c, PJ_EINVAL, "pj_batch_submit: null argument");
+    if (!c->shard_open) return fail(c, PJ_ESTATE, "pj_batch_submit: no open shard");
+    const int64_t n = b->n_records;
+    if (n < 0) return fail(c, PJ_EINVAL, "pj_batch_submit: negative record count");
+    if (n == 0) return PJ_OK;
+    if (!b->tid || !b->pos || !b->flag || !b->mapq || !b->xs || !b->l_qseq || !b->mtid || !b->mpos || !b->cigar_off || !b->seq_off)
+        return fail(c, PJ_EINVAL, "pj_batch_submit: null column");
+    CU(c, cudaSetDevice(c->device));
+    const uint32_t cb = b->cigar_off[0], ce = b->cigar_off[n];
+    const uint64_t sb = b->seq_off[0], se = b->seq_off[n];
+    if (ce < cb || se < sb) return fail(c, PJ_EINVAL, "pj_batch_submit: offsets not monotone");
+    const uint64_t ncig = ce - cb, nseq = se - sb;
+    if ((ncig && !b->cigar) || (nseq && !b->seq4)) return fail(c, PJ_EINVAL, "pj_batch_submit: null cigar/seq column");
+    if (c->n_cig + ncig > 0xfffffff0ull) return fail(c, PJ_EINVAL, "pj_batch_submit: more than 2^32 CIGAR operations in one shard");
+    cudaStream_t st = c->copy_stream;
+    const size_t R = (size_t)c->n_rec, need = R + (size_t)n;
+    int rc;
+    if ((rc = ensure(c, c->tid, need, R, st)) || (rc = ensure(c, c->pos, need, R, st)) || (rc = ensure(c, c->l_qseq, need, R, st)) ||
+        (rc = ensure(c, c->mtid, need, R, st)) || (rc = ensure(c, c->mpos, need, R, st)) || (rc = ensure(c, c->flag, need, R, st)) ||
+        (rc = ensure(c, c->mapq, need, R, st)) || (rc = ensure(c, c->xs, need, R, st)) || (rc = ensure(c, c->cigar_off, need + 1, R + 1, st)) ||
+        (rc = ensure(c, c->seq_off, need + 1, R + 1, st)) || (rc = ensure(c, c->cigar, (size_t)(c->n_cig + ncig), (size_t)c->n_cig, st)) ||
+        (rc = ensure(c, c->seq4, (size_t)(c->n_seq + nseq) + 16, (size_t)c->n_seq, st))) return rc;
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+    CU(c, cudaMemcpyAsync(c->tid.p + R, b->tid, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->pos.p + R, b->pos, n * 4, H2D, st));
+    CU(c, cudaMemcpyAsync(c->l_qseq.p + R, b->l_qseq, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->mtid.p + R, b->mtid, n * 4, H2D, st));
+    CU(c, cudaMemcpyAsync(c->mpos.p + R, b->mpos, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->flag.p + R, b->flag, n * 2, H2D, st));
+    CU(c, cudaMemcpyAsync(c->mapq.p + R, b->mapq, n, H2D, st)); CU(c, cudaMemcpyAsync(c->xs.p + R, b->xs, n, H2D, st));
+    CU(c, cudaMemcpyAsync(c->cigar_off.p + R + 1, b->cigar_off + 1, n * 4, H2D, st));
+    CU(c, cudaMemcpyAsync(c->seq_off.p + R + 1, b->seq_off + 1, n * 8, H2D, st));
+    if (ncig) CU(c, cudaMemcpyAsync(c->cigar.p + c->n_cig, b->cigar + cb, ncig * 4, H2D, st));
+    if (nseq) CU(c, cudaMemcpyAsync(c->seq4.p + c->n_seq, b->seq4 + sb, nseq, H2D, st));
+    launch_rebase_u32(c->cigar_off.p + R + 1, n, (uint32_t)c->n_cig - cb, st);
+    launch_rebase_u64(c->seq_off.p + R + 1, n, c->n_seq - sb, st);
+    CU(c, cudaGetLastError());
+    for (int s = 0; s < 2; s++) if (b->tid == c->slot[s].tid) { CU(c, cudaEventRecord(c->slot[s].done, st)); c->slot[s].in_flight = true; }
+    c->n_rec += n; c->n_cig += ncig; c->n_seq += nseq;
+    return PJ_OK;
+}
+
+int pj_shard_run(pj_ctx* c) {
+    if (!c || !c->shard_open) return fail(c, PJ_ESTATE, "pj_shard_run: no open shard");
+    CU(c, cudaSetDevice(c->device));
+    int rc = finish_genome(c); if (rc) return rc;
+    cudaStream_t st = c->compute_stream;
+    CU(c, cudaEventRecord(c->copies_done, c->copy_stream));
+    CU(c, cudaStreamWaitEvent(st, c->copies_done, 0));
+    c->n_stage = 0; c->n_launches = 0; c->have_result = false;
+    const int64_t R = c->n_rec; const int32_t T = c->n_targets;
+    if (R >= (int64_t)0xfffffff0ll) return fail(c, PJ_EINVAL, "pj_shard_run: more than 2^32 records in one shard");
+    mark(c, "begin");
+    // ---- per-target accumulators ----
+    CU(c, cudaMemsetAsync(c->d_spliced, 0, T * 8, st)); CU(c, cudaMemsetAsync(c->d_unspliced, 0, T * 8, st)); CU(c, cudaMemsetAsync(c->d_sumq, 0, T * 8, st));
+    CU(c, cudaMemsetAsync(c->d_maxq, 0, T * 4, st));
+    launch_fill_i32(c->d_minq, T, INT32_MAX, st); c->n_launches++;
+    CU(c, cudaMemsetAsync(c->d_scalars, 0, 16 * sizeof(uint32_t), st));
+    Reads Rd{R, c->tid.p, c->pos.p, c->flag.p, c->mapq.p, c->xs.p, c->l_qseq.p, c->mtid.p, c->mpos.p, c->cigar_off.p, c->cigar.p, c->seq_off.p, c->seq4.p};
+    TargetAcc TA{c->d_spliced, c->d_unspliced, c->d_sumq, c->d_minq, c->d_maxq};
+    uint32_t* d_err = c->d_scalars + 0; uint32_t* d_maxn = c->d_scalars + 1; uint32_t* d_P = c->d_scalars + 2;
+    uint32_t* d_J = c->d_scalars + 3; uint32_t* d_E = c->d_scalars + 4; uint32_t* d_tmp_total = c->d_scalars + 5;
+
+    uint32_t *npairs = nullptr, *pair_off = nullptr, *scan_tmp = nullptr; int32_t* read_end = nullptr;
+    const size_t Ra = (size_t)std::max<int64_t>(R, 1);
+    CU(c, cudaMallocAsync(&npairs, Ra * 4, st)); CU(c, cudaMallocAsync(&pair_off, (Ra + 1) * 4, st)); CU(c, cudaMallocAsync(&read_end, Ra * 4, st));
+    CU(c, cudaMallocAsync(&scan_tmp, scan_tmp_elems(Ra) * 4, st));
+    launch_scan_reads(Rd, c->d_tlen, T, npairs, read_end, TA, d_maxn, st); c->n_launches++;
+    mark(c, "scan_reads");
+    launch_exclusive_scan(npairs, pair_off, (uint64_t)R, scan_tmp, d_P, st); c->n_launches += 3;
+    mark(c, "pair_offsets");
+    CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    CU(c, cudaGetLastError());
+    const uint32_t P = c->h_scalars[2], maxN = c->h_scalars[1];
+    c->n_pairs = P;
+    // (a uint32 sum of N-op counts can wrap only beyond 2^32 pairs; the CIGAR word limit above excludes that)
+    const int len_bits = std::max(1, bit_length(maxN));
+    const int gbits = std::max(1, bit_length(c->h_toff[T]));
+    const int key_bits = len_bits + gbits;
+    if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
+
+    uint32_t J = 0;
+    if (P > 0) {
+        uint64_t *keys_a = nullptr, *keys_b = nullptr; uint32_t *vals_a = nullptr, *vals_b = nullptr, *counts = nullptr, *scan_tmp2 = nullptr;
+        PairA* pa = nullptr; PairB* pb = nullptr;
+        const uint32_t nb = rs_num_blocks(P);
+        CU(c, cudaMallocAsync(&keys_a, (size_t)P * 8, st)); CU(c, cudaMallocAsync(&keys_b, (size_t)P * 8, st));
+        CU(c, cudaMallocAsync(&vals_a, (size_t)P * 4, st)); CU(c, cudaMallocAsync(&vals_b, (size_t)P * 4, st));
+        CU(c, cudaMallocAsync(&counts, (size_t)256 * nb * 4, st));
+        CU(c, cudaMallocAsync(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, P)) * 4, st));
+        CU(c, cudaMallocAsync(&pa, (size_t)P * sizeof(PairA), st)); CU(c, cudaMallocAsync(&pb, (size_t)P * sizeof(PairB), st));
+        launch_emit_pairs(Rd, c->d_tlen, c->d_toff, len_bits, c->orientation, pair_off, npairs, read_end, keys_a, pa, pb, d_err, st); c->n_launches++;
+        mark(c, "emit_pairs");
+        const int which = launch_radix_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, counts, scan_tmp2, d_tmp_total, st, &c->n_launches);
+        const uint64_t* keys = which ? keys_b : keys_a; const uint32_t* vals = which ? vals_b : vals_a;
+        uint32_t* spare_u32 = which ? vals_a : vals_b;        // free again: reused for the head flags / entropy flags
+        mark(c, "radix_sort");
+        uint32_t *jid = nullptr, *seg_start = nullptr;
+        CU(c, cudaMallocAsync(&jid, (size_t)P * 4, st));
+        launch_seg_heads(keys, P, spare_u32, st); c->n_launches++;
+        launch_exclusive_scan(spare_u32, spare_u32, P, scan_tmp2, d_J, st); c->n_launches += 3;
+        CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        J = c->h_scalars[3];
+        CU(c, cudaMallocAsync(&seg_start, ((size_t)J + 1) * 4, st));
+        launch_seg_ids(keys, P, spare_u32, jid, seg_start, J, st); c->n_launches++;
+        mark(c, "segments");
+        // ---- per-junction accumulators: one zero-filled block of uint32 columns ----
+        const size_t NCOL = 24; uint32_t* acc = nullptr; uint32_t* jadhist = nullptr; double* entropy = nullptr;
+        CU(c, cudaMallocAsync(&acc, NCOL * (size_t)J * 4, st)); CU(c, cudaMemsetAsync(acc, 0, NCOL * (size_t)J * 4, st));
+        CU(c, cudaMallocAsync(&jadhist, (size_t)J * (PJ_NB_JAD + 1) * 4, st)); CU(c, cudaMemsetAsync(jadhist, 0, (size_t)J * (PJ_NB_JAD + 1) * 4, st));
+        CU(c, cudaMallocAsync(&entropy, (size_t)J * 8, st));
+        auto col = [&](size_t k) { return acc + k * (size_t)J; };
+        JuncAcc A{(int32_t*)col(0), (int32_t*)col(1), (int32_t*)col(2), (int32_t*)col(3), (int32_t*)col(4),
+                  col(5), col(6), col(7), col(8), col(9), col(10), col(11), col(12), col(13), col(14), col(15), col(16), col(17), col(18), col(19),
+                  col(20), col(21), col(22), col(23), jadhist};
+        CU(c, cudaMemsetAsync(A.firstmm, 0xff, (size_t)J * 4, st));
+        launch_junc_init(J, seg_start, keys, vals, pa, pb, c->tid.p, len_bits, A, st); c->n_launches++;
+        launch_reduce1(P, vals, jid, pa, pb, (c->orientation == PJ_ORIENT_FR || c->orientation == PJ_ORIENT_RF || c->orientation == PJ_ORIENT_FF) ? 1 : 0,
+                       A, spare_u32, st); c->n_launches++;
+        mark(c, "reduce1");
+        uint64_t* free_keys = which ? keys_a : keys_b;          // the non-result key buffer: 8 bytes per pair, reused below
+        uint32_t* eoff = reinterpret_cast<uint32_t*>(free_keys);
+        uint32_t* epos = eoff + P;
+        launch_exclusive_scan(spare_u32, eoff, P, scan_tmp2, d_E, st); c->n_launches += 3;
+        launch_entropy_compact(P, spare_u32, eoff, epos, st); c->n_launches++;
+        launch_entropy_sum(J, seg_start, eoff, epos, entropy, st); c->n_launches++;
+        mark(c, "entropy");
+        Genome G{c->d_g2, c->d_gx, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x};
+        uint4* pm = nullptr; CU(c, cudaMallocAsync(&pm, (size_t)P * sizeof(uint4), st));
+        launch_match(P, vals, jid, pa, pb, Rd, G, A, pm, d_err, st); c->n_launches++;
+        mark(c, "match");
+        launch_reduce2(P, jid, pm, A, st); c->n_launches++;
+        mark(c, "reduce2");
+        if (c->rows_cap < J) { if (c->d_rows) { CU(c, cudaStreamSynchronize(st)); cudaFree(c->d_rows); } c->rows_cap = (size_t)J + J / 4 + 16; CU(c, cudaMalloc(&c->d_rows, c->rows_cap * sizeof(pj_junction))); }
+        launch_finalize(J, seg_start, A, G, entropy, c->d_rows, d_err, st); c->n_launches++;
+        mark(c, "finalize");
+        CU(c, cudaFreeAsync(keys_a, st)); CU(c, cudaFreeAsync(keys_b, st)); CU(c, cudaFreeAsync(vals_a, st)); CU(c, cudaFreeAsync(vals_b, st));
+        CU(c, cudaFreeAsync(counts, st)); CU(c, cudaFreeAsync(scan_tmp2, st)); CU(c, cudaFreeAsync(pa, st)); CU(c, cudaFreeAsync(pb, st));
+        CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
+        CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st));
+    }
+    CU(c, cudaFreeAsync(npairs, st)); CU(c, cudaFreeAsync(pair_off, st)); CU(c, cudaFreeAsync(read_end, st)); CU(c, cudaFreeAsync(scan_tmp, st));
+    mark(c, "end");
+    CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    CU(c, cudaGetLastError());
+    // timings
+    c->stage_ms.clear(); c->stage_names.clear();
+    for (size_t k = 1; k < c->n_stage; k++) {
+        float ms = 0; cudaEventElapsedTime(&ms, c->stages[k - 1].ev, c->stages[k].ev);
+        c->stage_ms.push_back(ms); c->stage_names.push_back(c->stages[k].name);
+    }
+    cudaEventElapsedTime(&c->total_ms, c->stages[0].ev, c->stages[c->n_stage - 1].ev);
+    const uint32_t err = c->h_scalars[0];
+    if (err) {
+        std::string m = "input rejected (the reference aborts or is undefined on it):";
+        if (err & ERR_ANCHOR_ORDER) m += " intron not enclosed by its anchors;";
+        if (err & ERR_START_RANGE) m += " intron start outside the target (donor site cannot be fetched);";
+        if (err & ERR_KEY_OVERFLOW) m += " internal key overflow;";
+        if (err & ERR_NO_PRESENCE) m += " alignment has no presence in the requested region;";
+        if (err & ERR_QUERY_RANGE) m += " CIGAR consumes more query bases than SEQ holds;";
+        if (err & ERR_EMPTY_ANCHOR) m += " empty anchor window;";
+        if (err & ERR_GENOME_RANGE) m += " junction window leaves the genome sequence (or the target has no sequence loaded);";
+        if (err & ERR_SEQ_MISSING) m += " spliced read without SEQ bytes;";
+        if (err & ERR_ZERO_LEN) m += " zero-length window op;";
+        return fail(c, (err & ERR_KEY_OVERFLOW) ? PJ_EINVAL : PJ_EDATA, "%s", m.c_str());
+    }
+    c->n_junc = J; c->have_result = true;
+    return PJ_OK;
+}
+
+int64_t pj_shard_num_junctions(const pj_ctx* c) { return (c && c->have_result) ? c->n_junc : -1; }
+
+int pj_shard_fetch(pj_ctx* c, pj_junction* rows, int64_t cap_rows, pj_target_stats* stats, int32_t cap_targets) {
+    if (!c || !c->have_result) return fail(c, PJ_ESTATE, "pj_shard_fetch: no result (run pj_shard_run first)");
+    if (cap_rows < c->n_junc || (c->n_junc && !rows)) return fail(c, PJ_EINVAL, "pj_shard_fetch: rows capacity %lld < %lld", (long long)cap_rows, (long long)c->n_junc);
+    CU(c, cudaSetDevice(c->device));
+    if (c->n_junc) CU(c, cudaMemcpyAsync(rows, c->d_rows, (size_t)c->n_junc * sizeof(pj_junction), cudaMemcpyDeviceToHost, c->compute_stream));
+    if (stats) {
+        if (cap_targets < c->n_targets) return fail(c, PJ_EINVAL, "pj_shard_fetch: stats capacity too small");
+        const int32_t T = c->n_targets;
+        std::vector<unsigned long long> a(T), b(T), s(T); std::vector<int32_t> mn(T), mx(T);
+        CU(c, cudaMemcpyAsync(a.data(), c->d_spliced, T * 8, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(c, cudaMemcpyAsync(b.data(), c->d_unspliced, T * 8, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(c, cudaMemcpyAsync(s.data(), c->d_sumq, T * 8, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(c, cudaMemcpyAsync(mn.data(), c->d_minq, T * 4, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(c, cudaMemcpyAsync(mx.data(), c->d_maxq, T * 4, cudaMemcpyDeviceToHost, c->compute_stream));
+        CU(c, cudaStreamSynchronize(c->compute_stream));
+        for (int32_t t = 0; t < T; t++) stats[t] = pj_target_stats{a[t], b[t], s[t], mn[t], mx[t]};
+    }
+    CU(c, cudaStreamSynchronize(c->compute_stream));
+    return PJ_OK;
+}
+
+int pj_shard_timing(const pj_ctx* c, float* total_ms, int32_t* n_launches) {
+    if (!c) return PJ_EINVAL;
+    if (total_ms) *total_ms = c->total_ms;
+    if (n_launches) *n_launches = c->n_launches;
+    return PJ_OK;
+}
+
+int pj_shard_kernel_times(const pj_ctx* c, int32_t cap, float* kernel_ms, const char** kernel_names, int32_t* n) {
+    if (!c || !n) return PJ_EINVAL;
+    const int32_t k = (int32_t)c->stage_ms.size();
+    *n = k;
+    for (int32_t i = 0; i < k && i < cap; i++) { if (kernel_ms) kernel_ms[i] = c->stage_ms[i]; if (kernel_names) kernel_names[i] = c->stage_names[i]; }
+    return PJ_OK;
+}
+
+} // extern "C"

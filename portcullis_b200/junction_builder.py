@@ -1,0 +1,205 @@
+"""Python mirror of the reference's junc-stage interface.
+
+``JunctionBuilder`` follows portcullis::JunctionBuilder (/root/reference/src/junction_builder.cc:63-150):
+constructor ``(prep_dir, output_prefix)``, the same setters, ``process()``.  ``JuncGpu`` is the lower
+seam — the replacement of ``findJuncs`` — driving the C ABI of include/portcullis_junc.h directly with
+columnar host buffers.  Everything computes in the CUDA library; there is no Python fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+from .columnar import batch_struct, from_batch
+
+
+def _check(rc, msg_fn):
+    if rc != 0:
+        m = msg_fn()
+        raise L.PjError(rc, m.decode() if isinstance(m, bytes) else str(m))
+
+
+class PrepDir:
+    """A prepared data directory (PreparedFiles, /root/reference/src/prepare.hpp:74-145)."""
+
+    def __init__(self, prep_dir, use_csi=False):
+        self._lib = L.load()
+        self._p = C.c_void_p()
+        _check(self._lib.pjh_prep_open(os.fsencode(prep_dir), int(use_csi), C.byref(self._p)), self._lib.pjh_last_error)
+        n = self._lib.pjh_prep_n_targets(self._p)
+        self.names = [self._lib.pjh_prep_target_name(self._p, t).decode() for t in range(n)]
+        self.lengths = np.array([self._lib.pjh_prep_target_len(self._p, t) for t in range(n)], dtype=np.int32)
+
+    def target_records(self, tid):
+        return self._lib.pjh_prep_target_records(self._p, tid)
+
+    def decode(self, tid=-1, threads=1):
+        """Decode one target (or all with tid=-1) into owned numpy columns."""
+        b = L.PjBatch()
+        _check(self._lib.pjh_prep_decode(self._p, tid, threads, C.byref(b)), self._lib.pjh_last_error)
+        return from_batch(b)
+
+    def genome(self, tid):
+        s = C.c_char_p()
+        n = C.c_int64()
+        _check(self._lib.pjh_prep_genome(self._p, tid, C.byref(s), C.byref(n)), self._lib.pjh_last_error)
+        return C.string_at(s, n.value)
+
+    def close(self):
+        if self._p:
+            self._lib.pjh_prep_close(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class JuncGpu:
+    """One GPU context of the C ABI (pj_ctx)."""
+
+    def __init__(self, device=0, orientation="UNKNOWN"):
+        self._lib = L.load()
+        cfg = L.PjConfig()
+        cfg.device = device
+        cfg.orientation = L.ORIENT[orientation] if isinstance(orientation, str) else int(orientation)
+        self._ctx = C.c_void_p()
+        _check(self._lib.pj_create(C.byref(cfg), C.byref(self._ctx)), self._lib.pj_global_last_error)
+        self.n_targets = 0
+
+    def _err(self):
+        return self._lib.pj_last_error(self._ctx)
+
+    def set_targets(self, lengths):
+        tl = np.ascontiguousarray(lengths, dtype=np.int32)
+        _check(self._lib.pj_targets_set(self._ctx, len(tl), tl.ctypes.data), self._err)
+        self.n_targets = len(tl)
+
+    def set_genome(self, tid, bases):
+        buf = bytes(bases)
+        _check(self._lib.pj_genome_set_target(self._ctx, tid, C.cast(C.c_char_p(buf), C.c_void_p), len(buf)), self._err)
+
+    def shard_begin(self, n_records=0, n_cigar=0, n_seq=0):
+        _check(self._lib.pj_shard_begin(self._ctx, n_records, n_cigar, n_seq), self._err)
+
+    def submit(self, cols):
+        b, keep = batch_struct(cols)
+        _check(self._lib.pj_batch_submit(self._ctx, C.byref(b)), self._err)
+        del keep
+
+    def submit_pinned(self, cols):
+        """Copy the columns into the context's pinned staging slot, then enqueue the async H2D."""
+        n = len(cols["pos"])
+        st = L.PjBatch()
+        _check(self._lib.pj_staging_acquire(self._ctx, n, len(cols["cigar"]), len(cols["seq4"]), C.byref(st)), self._err)
+        for name, dt in __import__("portcullis_b200.columnar", fromlist=["COLUMNS"]).COLUMNS:
+            a = np.ascontiguousarray(cols[name], dtype=dt)
+            if a.size:
+                C.memmove(getattr(st, name), a.ctypes.data, a.nbytes)
+        st.n_records = n
+        _check(self._lib.pj_batch_submit(self._ctx, C.byref(st)), self._err)
+
+    def run(self):
+        _check(self._lib.pj_shard_run(self._ctx), self._err)
+        return self._lib.pj_shard_num_junctions(self._ctx)
+
+    def fetch(self):
+        n = self._lib.pj_shard_num_junctions(self._ctx)
+        rows = np.zeros(max(n, 0), dtype=L.JUNCTION_DTYPE)
+        stats = (L.PjTargetStats * self.n_targets)()
+        _check(self._lib.pj_shard_fetch(self._ctx, rows.ctypes.data, len(rows), C.addressof(stats), self.n_targets), self._err)
+        st = np.array([(s.spliced_count, s.unspliced_count, s.sum_query_lengths, s.min_query_length, s.max_query_length)
+                       for s in stats], dtype=[("spliced", "u8"), ("unspliced", "u8"), ("sumq", "u8"), ("minq", "i4"), ("maxq", "i4")])
+        return rows, st
+
+    def timing(self):
+        ms = C.c_float()
+        nl = C.c_int32()
+        self._lib.pj_shard_timing(self._ctx, C.byref(ms), C.byref(nl))
+        k = C.c_int32()
+        self._lib.pj_shard_kernel_times(self._ctx, 0, None, None, C.byref(k))
+        tm = (C.c_float * k.value)()
+        nm = (C.c_char_p * k.value)()
+        self._lib.pj_shard_kernel_times(self._ctx, k.value, tm, nm, C.byref(k))
+        return ms.value, nl.value, [(nm[i].decode(), tm[i]) for i in range(k.value)]
+
+    def close(self):
+        if self._ctx:
+            self._lib.pj_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def finalize(rows, mean_query_length):
+    """A12/A13 on the host (pj_junctions_finalize)."""
+    lib = L.load()
+    rows = np.ascontiguousarray(rows)
+    _check(lib.pj_junctions_finalize(rows.ctypes.data, len(rows), float(mean_query_length)), lambda: b"finalize failed")
+    return rows
+
+
+def write_outputs(prefix, rows, names, lengths, source="portcullis", version="1.2.4", exon_gff=False, intron_gff=False):
+    lib = L.load()
+    rows = np.ascontiguousarray(rows)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    tl = np.ascontiguousarray(lengths, dtype=np.int32)
+    _check(lib.pjh_write_outputs(os.fsencode(prefix), rows.ctypes.data, len(rows), len(names), arr, tl.ctypes.data,
+                                 source.encode(), version.encode(), int(exon_gff), int(intron_gff)), lib.pjh_last_error)
+
+
+class JunctionBuilder:
+    """Mirror of portcullis::JunctionBuilder: ``JunctionBuilder(prep_dir, output).process()``."""
+
+    def __init__(self, prep_dir, output="portcullis_junc/portcullis"):
+        self.prep_dir = prep_dir
+        self.output = output
+        self.threads = 1
+        self.gpus = 1
+        self.extra = False
+        self.separate = False
+        self.use_csi = False
+        self.strand_specific = "UNKNOWN"
+        self.orientation = "UNKNOWN"
+        self.source = "portcullis"
+        self.output_exon_gff = False
+        self.output_intron_gff = False
+        self.verbose = False
+        self.quiet = True
+        self.report = None
+
+    # setters named after the reference's (junction_builder.hpp)
+    def setThreads(self, n): self.threads = int(n)
+    def setGpus(self, n): self.gpus = int(n)
+    def setExtra(self, b): self.extra = bool(b)
+    def setSeparate(self, b): self.separate = bool(b)
+    def setSource(self, s): self.source = s
+    def setStrandSpecific(self, s): self.strand_specific = s.upper()
+    def setOrientation(self, s): self.orientation = s.upper()
+    def setUseCsi(self, b): self.use_csi = bool(b)
+    def setOutputExonGFF(self, b): self.output_exon_gff = bool(b)
+    def setOutputIntronGFF(self, b): self.output_intron_gff = bool(b)
+    def setVerbose(self, b): self.verbose = bool(b)
+
+    def process(self):
+        lib = L.load()
+        o = L.PjhOptions()
+        lib.pjh_options_default(C.byref(o))
+        keep = [os.fsencode(self.prep_dir), os.fsencode(self.output), self.source.encode()]
+        o.prep_dir, o.output_prefix, o.source = keep
+        o.threads, o.n_gpus = self.threads, self.gpus
+        o.orientation = L.ORIENT[self.orientation]
+        o.strandedness = L.STRANDEDNESS[self.strand_specific]
+        o.use_csi, o.exon_gff, o.intron_gff = int(self.use_csi), int(self.output_exon_gff), int(self.output_intron_gff)
+        o.verbose, o.separate, o.extra, o.quiet = int(self.verbose), int(self.separate), int(self.extra), int(self.quiet)
+        rep = L.PjhReport()
+        _check(lib.pjh_junc_run(C.byref(o), C.byref(rep)), lib.pjh_last_error)
+        self.report = {f: getattr(rep, f) for f, _ in L.PjhReport._fields_}
+        return self.report
