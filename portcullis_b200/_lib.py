@@ -55,7 +55,7 @@ JUNCTION_DTYPE = np.dtype([
     ("mean_readlen", "<f8"), ("rel2raw", "<f8"), ("mean_mismatches", "<f8"),
 ], align=False)
 
-# fields produced on the GPU (compared bit-exactly against the oracle; entropy within 1e-6 relative)
+# fields produced on the GPU (integer, string and enum columns: bit-exact parity; entropy within 1e-6 relative)
 DEVICE_INT_FIELDS = ["tid", "start", "end", "left", "right", "nb_raw_aln", "nb_dist_aln", "nb_ms_aln", "nb_um_aln",
                      "nb_bpp_aln", "nb_ppp_aln", "nb_rel_aln", "nb_r1_pos", "nb_r1_neg", "nb_r2_pos", "nb_r2_neg",
                      "nb_xs_pos", "nb_xs_neg", "max_min_anc", "maxmmes", "nb_mismatches", "hamming5p", "hamming3p",

@@ -1,0 +1,41 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the product library and the oracle once per session if they are missing."""
+    lib = os.path.join(ROOT, "portcullis_b200", "libportcullis_junc.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "portcullis_b200", "csrc")])
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle_junc.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+
+
+def make_prep(tmpdir, fixture):
+    """Lay out a prep directory (src/prepare.hpp:114-140) over a committed fixture."""
+    src = os.path.join(GOLDEN, fixture)
+    prep = os.path.join(str(tmpdir), "prep_" + fixture)
+    os.makedirs(prep, exist_ok=True)
+    for a, b in (("genome.fa", "portcullis.genome.fa"), ("genome.fa.fai", "portcullis.genome.fa.fai"),
+                 ("reads.bam", "portcullis.sorted.alignments.bam"), ("reads.bam.bai", "portcullis.sorted.alignments.bam.bai")):
+        d = os.path.join(prep, b)
+        if not os.path.lexists(d):
+            os.symlink(os.path.join(src, a), d)
+    return prep
+
+
+FIXTURES = ["kat", "short_pe", "long_se", "indel_rich"]
+ORIENTED = {"kat": "FR", "short_pe": "FR", "indel_rich": "RF"}

@@ -1,0 +1,86 @@
+"""CPU tests of the drop-in boundary: the shared library loads, exports every symbol the headers declare, and
+refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from portcullis_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = set()
+    for h in ("portcullis_junc.h", "portcullis_junc_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(pjh?_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in include/ but not exported" % name
+    assert declared == set(L.SYMBOLS), "python binding table out of sync with the headers: %s" % (declared ^ set(L.SYMBOLS))
+    assert lib.pj_abi_version() == 1
+    assert lib.pj_junction_size() == L.JUNCTION_DTYPE.itemsize == 256
+
+
+def test_product_does_not_reference_the_oracle():
+    """Nothing under portcullis_b200/ may import, link or call oracle/."""
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "portcullis_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".hpp", ".h")) or f == "Makefile":
+                s = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"oracle|oj_run|liboracle", s):
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = L.load()
+    cfg = L.PjConfig()
+    cfg.device, cfg.orientation = 0, L.ORIENT["UNKNOWN"]
+    ctx = C.c_void_p()
+    rc = lib.pj_create(C.byref(cfg), C.byref(ctx))
+    assert rc == L.PJ_ECUDA and not ctx.value
+    assert b"no CPU fallback" in lib.pj_global_last_error()
+    from portcullis_b200 import JunctionBuilder
+    from conftest import make_prep
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        jbd = JunctionBuilder(make_prep(d, "kat"), os.path.join(d, "out", "k"))
+        with pytest.raises(L.PjError) as ei:
+            jbd.process()
+        assert ei.value.code == L.PJ_ECUDA
+
+
+def test_host_finalize_edge_cases():
+    """A13 boundary behaviour (quirk Q8): J=0, J=1 (stats skipped), J=2 same target, cross-target sentinels."""
+    from portcullis_b200 import junction_builder as jb
+    import oracle_binding as ob
+
+    def rows(spec):
+        r = np.zeros(len(spec), dtype=L.JUNCTION_DTYPE)
+        for i, (tid, s, e, raw) in enumerate(spec):
+            r[i]["tid"], r[i]["start"], r[i]["end"], r[i]["nb_raw_aln"], r[i]["nb_rel_aln"] = tid, s, e, raw, raw
+        return r
+    for spec in ([], [(0, 10, 20, 3)], [(0, 10, 20, 3), (0, 30, 40, 5)], [(0, 10, 20, 3), (1, 30, 40, 5)],
+                 [(0, 10, 20, 3), (0, 10, 40, 5), (0, 35, 40, 5), (1, 5, 9, 1), (2, 5, 9, 1), (2, 50, 90, 2)]):
+        a = jb.finalize(rows(spec), 100.5)
+        b = ob.finalize(rows(spec), 100.5)
+        assert a.tobytes() == b.tobytes()
+    two = jb.finalize(rows([(0, 10, 20, 3), (0, 30, 40, 5)]), 100.5)
+    assert list(two["dist_2_down_junc"]) == [0xFFFFFFFF, 10] and list(two["dist_2_up_junc"]) == [10, 0]
+    one = jb.finalize(rows([(0, 10, 20, 3)]), 100.5)
+    assert one["mean_readlen"][0] == 0 and one["uniq_junc"][0] == 0
