@@ -58,7 +58,7 @@ typedef struct pj_ctx pj_ctx;
 typedef struct pj_config {
     int32_t device;        /* CUDA device ordinal                                              */
     int32_t orientation;   /* PJ_ORIENT_*; only FR/RF/FF enable the portcullis proper-pair rule */
-    int32_t reserved[6];
+    int32_t reserved[6];   /* [0]: lanes per (read, junction) pair in the match kernel, 0 = automatic (tuning knob) */
 } pj_config;
 
 /*

@@ -570,16 +570,99 @@ void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32
 // ================================================================================================
 // k_match: AlignmentInfo::calcMatchStats (junction.cc:147-240) = getPaddedQuerySeq / getPaddedGenomeSeq
 // (bam_alignment.cc:341-462) + hammingDistance + getNbMatchesFromEnd/Start, fused into one walk that never
-// materialises the strings.  One warp per (read, junction) pair; the CIGAR walk is warp-uniform, the 32 lanes
-// stride over the columns of each M/=/X block.  Quirks Q3-Q6 are kept.
+// materialises the strings.  Quirks Q3-Q6 are kept.
+//
+// A group of G lanes (G = 1, 2, 4, 8, 16 or 32, chosen from the mean read length of the shard) owns one
+// (read, junction) pair.  The CIGAR walk is uniform inside the group; the columns of every M/=/X block are
+// compared 16 bases per step: 16 BAM nibbles (one unaligned 64-bit window of SEQ) against 16 genome bases
+// expanded from the 2-bit plane to one-hot nibbles, so a mismatch is a non-zero nibble of an XOR.
 // ================================================================================================
-struct SideResult { uint32_t cols, mism; int32_t first_mm, last_mm; };   // string indices of first / last mismatch (-1: none)
+struct SideAcc { uint32_t cols; uint32_t mism; int32_t first_mm; int32_t last_mm; };   // first/last: string indices, INT32_MAX / -1 = none
 
-__device__ __forceinline__ SideResult walk_side(const Genome& G, uint64_t gbase /* goff[tid] */, int64_t glen,
-                                                const uint32_t* __restrict__ cg, int32_t n_cig, int32_t pos,
-                                                const uint8_t* __restrict__ seq, int32_t qoff, int32_t qsize,
-                                                int32_t wstart, int32_t wend, int lane, uint32_t& err) {
-    SideResult r{0u, 0u, -1, -1};
+constexpr uint64_t NIB1 = 0x1111111111111111ull;
+
+// 8 bytes starting at byte address p (any alignment) as a little-endian 64-bit value
+__device__ __forceinline__ uint64_t load_u64_unaligned(const uint8_t* __restrict__ p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(a & 7) * 8;
+    const uint64_t w0 = __ldg(q);
+    if (sh == 0) return w0;
+    const uint64_t w1 = __ldg(q + 1);
+    return (w0 >> sh) | (w1 << (64 - sh));
+}
+// `nbits` (<= 32) bits starting at bit index `bit` of a little-endian array of 64-bit words
+__device__ __forceinline__ uint32_t load_bits32(const uint64_t* __restrict__ w, uint64_t bit) {
+    const uint64_t i = bit >> 6; const uint32_t sh = (uint32_t)(bit & 63);
+    const uint64_t w0 = __ldg(w + i);
+    if (sh <= 32) return (uint32_t)(w0 >> sh);
+    const uint64_t w1 = __ldg(w + i + 1);
+    return (uint32_t)((w0 >> sh) | (w1 << (64 - sh)));
+}
+// 16 two-bit groups of a 32-bit word -> the low two bits of 16 nibbles
+__device__ __forceinline__ uint64_t spread2to4(uint32_t v) {
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    return x;
+}
+// 16 bits -> the lowest bit of 16 nibbles
+__device__ __forceinline__ uint64_t spread1to4(uint32_t v) {
+    uint64_t x = v & 0xFFFFu;
+    x = (x | (x << 24)) & 0x000000FF000000FFull;
+    x = (x | (x << 12)) & 0x000F000F000F000Full;
+    x = (x | (x << 6)) & 0x0303030303030303ull;
+    x = (x | (x << 3)) & NIB1;
+    return x;
+}
+
+// Compare the columns of one M/=/X block: read nibbles q0.. against genome bases gi0.., `len` columns, string offset `sbase`.
+template <int G>
+__device__ __forceinline__ void compare_block(const Genome& Gn, const uint8_t* __restrict__ seq, int32_t q0, uint64_t gi0, int32_t len,
+                                              int32_t sbase, int gl, SideAcc& r) {
+    const int32_t odd = q0 & 1;
+    const int32_t nchunk = (odd + len + 15) >> 4;
+    const uint8_t* sp = seq + (q0 >> 1);
+    for (int32_t k = gl; k < nchunk; k += G) {
+        uint64_t x = load_u64_unaligned(sp + 8 * k);
+        x = ((x & 0x0F0F0F0F0F0F0F0Full) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0Full);   // base t of the chunk at bits [4t, 4t+4)
+        const int32_t c_first = 16 * k - odd;                                          // column of nibble 0 (may be -1)
+        const uint64_t gs = gi0 + (uint64_t)(int64_t)c_first;                          // genome layout has a 64-base lead pad
+        const uint64_t S = spread2to4(load_bits32(Gn.g2, gs * 2));
+        const uint64_t Eb = spread1to4(load_bits32(Gn.gx, gs));
+        const uint64_t L = S & NIB1, H = (S >> 1) & NIB1;
+        uint64_t g4 = (~(L | H) & NIB1) | ((L & ~H) << 1) | ((H & ~L) << 2) | ((L & H) << 3);   // one-hot: A=1 C=2 G=4 T=8
+        g4 |= (Eb << 4) - Eb;                                                          // exception base: 'N' = 15 (sub-code 0)
+        uint64_t d = x ^ g4;
+        d |= d >> 1; d |= d >> 2; d &= NIB1;
+        const int32_t t_lo = c_first < 0 ? -c_first : 0;
+        const int32_t t_hi = min(16, len - c_first);
+        uint64_t V = (t_hi >= 16 ? ~0ull : ((1ull << (4 * t_hi)) - 1ull)) & ~((1ull << (4 * t_lo)) - 1ull);
+        d &= V;
+        uint64_t other = Eb & L & V;                                                   // exception bytes other than 'N': exact side-table compare
+        while (other) {
+            const int t = (__ffsll((long long)other) - 1) >> 2;
+            other &= other - 1;
+            const uint32_t nib = (uint32_t)(x >> (4 * t)) & 0xfu;
+            const bool mm = !base_matches(Gn, gs + (uint64_t)t, nib);
+            d = (d & ~(1ull << (4 * t))) | ((uint64_t)mm << (4 * t));
+        }
+        if (d) {
+            r.mism += __popcll(d);
+            const int32_t f = sbase + c_first + ((__ffsll((long long)d) - 1) >> 2);
+            const int32_t l = sbase + c_first + ((63 - __clzll((long long)d)) >> 2);
+            r.first_mm = min(r.first_mm, f); r.last_mm = max(r.last_mm, l);
+        }
+    }
+}
+
+template <int G>
+__device__ __forceinline__ SideAcc walk_side(const Genome& Gn, uint64_t gbase, int64_t glen, const uint32_t* __restrict__ cg, int32_t n_cig,
+                                             int32_t pos, const uint8_t* __restrict__ seq, int32_t qoff, int32_t qsize,
+                                             int32_t wstart, int32_t wend, int gl, uint32_t& err) {
+    SideAcc r{0u, 0u, INT32_MAX, -1};
     int32_t qPos = 0, rPos = pos;
     for (int32_t k = 0; k < n_cig; k++) {
         const uint32_t w = __ldg(cg + k), op = cig_op(w); const int32_t L = cig_len(w);
@@ -592,43 +675,21 @@ __device__ __forceinline__ SideResult walk_side(const Genome& G, uint64_t gbase 
             if (qPos + len > qsize) { err |= ERR_QUERY_RANGE; break; }
             if (op == OP_I) {
                 // query bases against 'X' padding in the genome string: never equal (no 'X' in the BAM alphabet)
-                if (r.first_mm < 0) r.first_mm = (int32_t)r.cols;
-                r.last_mm = (int32_t)r.cols + len - 1;
-                r.mism += (uint32_t)len;
+                if (gl == 0) { r.first_mm = min(r.first_mm, (int32_t)r.cols); r.last_mm = max(r.last_mm, (int32_t)r.cols + len - 1); r.mism += (uint32_t)len; }
             } else {
                 if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
-                const int32_t q0 = qoff + qPos;
-                for (int32_t c0 = 0; c0 < len; c0 += 32) {
-                    const int32_t c = c0 + lane;
-                    bool mm = false;
-                    if (c < len) {
-                        const int32_t qi = q0 + c;
-                        const uint32_t nib = (__ldg(seq + (qi >> 1)) >> ((~qi & 1) << 2)) & 0xfu;
-                        mm = !base_matches(G, gbase + (uint64_t)(uint32_t)(rPos + c), nib);
-                    }
-                    const uint32_t b = __ballot_sync(FULL, mm);
-                    if (b) {
-                        if (r.first_mm < 0) r.first_mm = (int32_t)r.cols + c0 + (__ffs(b) - 1);
-                        r.last_mm = (int32_t)r.cols + c0 + (31 - __clz(b));
-                        r.mism += __popc(b);
-                    }
-                }
+                compare_block<G>(Gn, seq, qoff + qPos, gbase + (uint64_t)(uint32_t)rPos, len, (int32_t)r.cols, gl, r);
             }
             r.cols += (uint32_t)len;
         } else if (cr) {                                                                   // D or N inside the window: 'X' vs genome
             const int32_t len = rPos + L > wend ? wend - rPos + 1 : L;
             if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
-            if (G.n_exc_x == 0) {
-                if (len > 0) { if (r.first_mm < 0) r.first_mm = (int32_t)r.cols; r.last_mm = (int32_t)r.cols + len - 1; r.mism += (uint32_t)len; }
+            if (Gn.n_exc_x == 0) {
+                if (gl == 0 && len > 0) { r.first_mm = min(r.first_mm, (int32_t)r.cols); r.last_mm = max(r.last_mm, (int32_t)r.cols + len - 1); r.mism += (uint32_t)len; }
             } else {
-                for (int32_t c0 = 0; c0 < len; c0 += 32) {
-                    const int32_t c = c0 + lane;
-                    const bool mm = (c < len) && genome_char(G, gbase + (uint64_t)(uint32_t)(rPos + c)) != (uint8_t)'X';
-                    const uint32_t b = __ballot_sync(FULL, mm);
-                    if (b) {
-                        if (r.first_mm < 0) r.first_mm = (int32_t)r.cols + c0 + (__ffs(b) - 1);
-                        r.last_mm = (int32_t)r.cols + c0 + (31 - __clz(b));
-                        r.mism += __popc(b);
+                for (int32_t c = gl; c < len; c += G) {
+                    if (genome_char(Gn, gbase + (uint64_t)(uint32_t)(rPos + c)) != (uint8_t)'X') {
+                        r.first_mm = min(r.first_mm, (int32_t)r.cols + c); r.last_mm = max(r.last_mm, (int32_t)r.cols + c); r.mism++;
                     }
                 }
             }
@@ -637,15 +698,26 @@ __device__ __forceinline__ SideResult walk_side(const Genome& G, uint64_t gbase 
         if (cr) rPos += L;
         if (cq) qPos += L;
     }
+    if (G > 1) {   // combine the lanes of the group
+        const int lane = threadIdx.x & 31;
+        const uint32_t gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (lane & ~(G - 1)));
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            r.mism += __shfl_xor_sync(gmask, r.mism, o);
+            r.first_mm = min(r.first_mm, __shfl_xor_sync(gmask, r.first_mm, o));
+            r.last_mm = max(r.last_mm, __shfl_xor_sync(gmask, r.last_mm, o));
+        }
+    }
     return r;
 }
 
+template <int G>
 __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairA* __restrict__ pa, const PairB* __restrict__ pb,
-                                                Reads R, Genome G, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= n) return;
+                                                Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
+    const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+    const int gl = threadIdx.x % G;
+    if (i >= n) return;                                              // whole groups leave together
     const uint32_t j = jid[i];
     const uint32_t idx = vals[i];
     const PairA a = pa[idx]; const PairB b = pb[idx];
@@ -658,8 +730,9 @@ __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __res
         const uint32_t um = (uint32_t)(leftEnd - left + 1), dm = (uint32_t)(right - rightStart + 1);
         nbMism = 0; minMatch = 0; mmes = min(um, dm);
     } else {
-        const uint32_t* cg = R.cigar + R.cigar_off[a.rid];
-        const int32_t n_cig = (int32_t)(R.cigar_off[a.rid + 1] - R.cigar_off[a.rid]);
+        const uint32_t c0 = R.cigar_off[a.rid];
+        const uint32_t* cg = R.cigar + c0;
+        const int32_t n_cig = (int32_t)(R.cigar_off[a.rid + 1] - c0);
         const uint64_t so = R.seq_off[a.rid];
         if ((int64_t)(R.seq_off[a.rid + 1] - so) < (int64_t)((lq + 1) >> 1)) err |= ERR_SEQ_MISSING;
         // getQuerySeqAfterClipping (bam_alignment.cc:256-264), quirk Q3: only a FIRST / LAST op of type S clips
@@ -667,33 +740,46 @@ __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __res
         int32_t ds = cig_op(wf) == OP_S ? cig_len(wf) : 0, de = cig_op(wl) == OP_S ? cig_len(wl) : 0;
         if (ds > lq) ds = lq;
         int64_t qs = (int64_t)lq - ds - de + 1; if (qs > lq - ds) qs = lq - ds; if (qs < 0) qs = 0;
-        const int64_t glen = G.glen[tid];
+        const int64_t glen = Gn.glen[tid];
         if (left > b.read_end || leftEnd < a.pos || rightStart > b.read_end || right < a.pos) err |= ERR_NO_PRESENCE;
         if (glen < 0) err |= ERR_GENOME_RANGE;
-        SideResult L{0, 0, -1, -1}, Rr{0, 0, -1, -1};
+        SideAcc L{0, 0, INT32_MAX, -1}, Rr{0, 0, INT32_MAX, -1};
         if (!err) {
-            const uint64_t gbase = G.goff[tid];
-            L = walk_side(G, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, left, leftEnd, lane, err);
-            Rr = walk_side(G, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, rightStart, right, lane, err);
+            const uint64_t gbase = Gn.goff[tid];
+            L = walk_side<G>(Gn, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, left, leftEnd, gl, err);
+            Rr = walk_side<G>(Gn, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, rightStart, right, gl, err);
             if (L.cols == 0 || Rr.cols == 0) err |= ERR_EMPTY_ANCHOR;
         }
         const uint32_t upMatches = L.cols - L.mism, downMatches = Rr.cols - Rr.mism;
         nbMism = L.mism + Rr.mism;
-        const uint32_t us = L.last_mm < 0 ? L.cols : (L.cols - 1u - (uint32_t)L.last_mm);     // getNbMatchesFromEnd
-        const uint32_t dsm = Rr.first_mm < 0 ? Rr.cols : (uint32_t)Rr.first_mm;               // getNbMatchesFromStart
+        const uint32_t us = L.last_mm < 0 ? L.cols : (L.cols - 1u - (uint32_t)L.last_mm);              // getNbMatchesFromEnd
+        const uint32_t dsm = Rr.first_mm == INT32_MAX ? Rr.cols : (uint32_t)Rr.first_mm;                // getNbMatchesFromStart
         minMatch = min(us, dsm);
         mmes = min(upMatches, downMatches);
     }
-    if (lane == 0) {
+    if (gl == 0) {
         pm[i] = make_uint4(mmes, minMatch, nbMism, 0u);
         if (err) atomicOr(errw, err);
     }
 }
-void launch_match(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& G,
+
+template <int G>
+static void launch_match_g(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& Gn,
+                           const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
+    const uint64_t threads = (uint64_t)n * G;
+    k_match<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pa, pb, R, Gn, A, pm, err);
+}
+void launch_match(uint32_t n, int group, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& Gn,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     if (!n) return;
-    const uint64_t threads = (uint64_t)n * 32;
-    k_match<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pa, pb, R, G, A, pm, err);
+    switch (group) {
+    case 1: launch_match_g<1>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    case 2: launch_match_g<2>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    case 4: launch_match_g<4>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    case 8: launch_match_g<8>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    case 16: launch_match_g<16>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    default: launch_match_g<32>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    }
 }
 
 // ================================================================================================

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <climits>
@@ -35,7 +36,7 @@ struct StageTime { const char* name; cudaEvent_t ev; };
 } // namespace
 
 struct pj_ctx {
-    int device = 0; int orientation = PJ_ORIENT_UNKNOWN;
+    int device = 0; int orientation = PJ_ORIENT_UNKNOWN; int match_group = 0;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     std::string err;
     // targets / genome
@@ -165,6 +166,8 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
     if (cfg->orientation < PJ_ORIENT_SE || cfg->orientation > PJ_ORIENT_UNKNOWN) return fail(nullptr, PJ_EINVAL, "pj_create: bad orientation %d", cfg->orientation);
     pj_ctx* c = new pj_ctx();
     c->device = cfg->device; c->orientation = cfg->orientation;
+    c->match_group = cfg->reserved[0];                 // 0 = choose from the data; 1..32 forces the lanes-per-pair of k_match (tuning / tests)
+    if (const char* e = getenv("PJ_MATCH_GROUP")) c->match_group = atoi(e);
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
@@ -205,7 +208,7 @@ int pj_targets_set(pj_ctx* c, int32_t n_targets, const int32_t* target_len) {
     c->n_targets = n_targets;
     c->h_tlen.assign(target_len, target_len + n_targets);
     c->h_toff.assign(n_targets + 1, 0); c->h_goff.assign(n_targets, 0); c->h_glen.assign(n_targets, -1);
-    uint64_t g = 0;
+    uint64_t g = 64;                                   // lead pad: k_match may look one base before a target start
     for (int32_t t = 0; t < n_targets; t++) {
         if (target_len[t] < 0) return fail(c, PJ_EINVAL, "pj_targets_set: negative target length");
         c->h_toff[t + 1] = c->h_toff[t] + (uint64_t)target_len[t];
@@ -410,7 +413,14 @@ int pj_shard_run(pj_ctx* c) {
         mark(c, "entropy");
         Genome G{c->d_g2, c->d_gx, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x};
         uint4* pm = nullptr; CU(c, cudaMallocAsync(&pm, (size_t)P * sizeof(uint4), st));
-        launch_match(P, vals, jid, pa, pb, Rd, G, A, pm, d_err, st); c->n_launches++;
+        {   // lanes per (read, junction) pair: one 16-base word per lane and step; long reads get wider groups
+            int group = c->match_group;
+            if (group <= 0) {
+                const double bases_per_pair = 2.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
+                group = bases_per_pair <= 400 ? 1 : bases_per_pair <= 1200 ? 4 : bases_per_pair <= 4000 ? 8 : 32;
+            }
+            launch_match(P, group, vals, jid, pa, pb, Rd, G, A, pm, d_err, st); c->n_launches++;
+        }
         mark(c, "match");
         launch_reduce2(P, jid, pm, A, st); c->n_launches++;
         mark(c, "reduce2");

@@ -16,8 +16,8 @@ from portcullis_b200 import junction_builder as jb
 pytestmark = pytest.mark.gpu
 
 
-def gpu_run(cols, lengths, genomes, orientation="UNKNOWN", n_batches=1, pinned=False, device=0):
-    g = jb.JuncGpu(device, orientation)
+def gpu_run(cols, lengths, genomes, orientation="UNKNOWN", n_batches=1, pinned=False, device=0, match_group=0):
+    g = jb.JuncGpu(device, orientation, match_group)
     try:
         g.set_targets(lengths)
         for t, s in enumerate(genomes):
@@ -145,3 +145,12 @@ def test_rejected_inputs_fail_loudly():
     # the oracle rejects the same input
     with pytest.raises(ob.OracleError):
         ob.run(cols, ds["lengths"], [b""])
+
+
+@pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])
+def test_match_kernel_group_widths(group):
+    """Every lanes-per-pair instantiation of k_match gives the same answer (short, indel-rich and long reads)."""
+    for seed, kw in ((201, dict(indel_rate=0.5, clip_rate=0.5, retain_rate=0.4, sub_rate=0.04)),
+                     (202, dict(long_reads=True, read_len=(300, 2500), genes_per_target=5, target_len=50000, paired=False, sub_rate=0.03))):
+        ds = synth.make_dataset(seed, **kw)
+        check_against_oracle(synth.to_columns(ds), ds["lengths"], ds["genomes"], match_group=group)
