@@ -117,7 +117,7 @@ void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { 
 // one thread packs 64 bases: four 128-bit loads, two g2 words, one gx word
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ raw, int64_t n, uint64_t base_index /* multiple of 64 */,
-                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx,
+                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx, uint8_t* __restrict__ g4,
                                                       uint64_t* __restrict__ exc_pos, uint8_t* __restrict__ exc_byte,
                                                       uint32_t* __restrict__ exc_count, uint32_t exc_cap) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,10 +133,20 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
         for (int k = 0; k < 64; k++) c[k] = (b0 + k < n) ? raw[b0 + k] : (uint8_t)'A';
     }
     uint64_t w0 = 0, w1 = 0, x = 0;
+    uint32_t n4[8] = {0, 0, 0, 0, 0, 0, 0, 0};                       // 64 nibbles, BAM order: base 2j in the high nibble of byte j
 #pragma unroll
     for (int k = 0; k < 64; k++) {
         uint8_t ch = c[k];
         if (ch >= 'a' && ch <= 'z') ch -= 32;                        // boost::to_upper
+        {
+            uint32_t q;                                                // index into "=ACMGRSVTWYHKDBN" (hts.c:82), 0 if absent
+            switch (ch) { case 'A': q = 1; break; case 'C': q = 2; break; case 'M': q = 3; break; case 'G': q = 4; break; case 'R': q = 5; break;
+                          case 'S': q = 6; break; case 'V': q = 7; break; case 'T': q = 8; break; case 'W': q = 9; break; case 'Y': q = 10; break;
+                          case 'H': q = 11; break; case 'K': q = 12; break; case 'D': q = 13; break; case 'B': q = 14; break; case 'N': q = 15; break;
+                          default: q = 0; }
+            if (b0 + k >= n) q = 0;
+            n4[k >> 3] |= q << (8 * ((k >> 1) & 3) + ((k & 1) ? 0 : 4));
+        }
         uint32_t code; bool exc = false;
         switch (ch) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
                       default: exc = true; code = (ch == 'N') ? 0u : 1u; }
@@ -152,13 +162,15 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
     }
     const uint64_t gi = base_index + (uint64_t)b0;
     g2[gi >> 5] = w0; g2[(gi >> 5) + 1] = w1; gx[gi >> 6] = x;
+    uint4* o4 = reinterpret_cast<uint4*>(g4 + (gi >> 1));             // gi is a multiple of 64 -> 32-byte aligned
+    o4[0] = make_uint4(n4[0], n4[1], n4[2], n4[3]); o4[1] = make_uint4(n4[4], n4[5], n4[6], n4[7]);
 }
 
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint8_t* g4,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st) {
     if (n <= 0) return;
     const int64_t threads = (n + 63) / 64;
-    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, exc_pos, exc_byte, exc_count, exc_cap);
+    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, g4, exc_pos, exc_byte, exc_count, exc_cap);
 }
 
 // ================================================================================================
@@ -167,63 +179,82 @@ void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_scan_reads(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets,
                                                      uint32_t* __restrict__ npairs, int32_t* __restrict__ read_end,
-                                                     TargetAcc T, uint32_t* __restrict__ max_nlen) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                     TargetAcc T, uint32_t* __restrict__ max_nlen, int64_t per_warp) {
+    // Persistent grid: every warp owns a contiguous run of `per_warp` records (a multiple of 32) and keeps the running
+    // per-target scalars of its current target in lane 0's registers, so the same-address atomics that the coordinate
+    // order would otherwise pile onto one target are issued once per warp and target instead of once per 32 records.
     const int lane = threadIdx.x & 31;
-    bool valid = i < R.n, vis = false;
-    int32_t tid = -2, lq = 0; uint32_t nN = 0, maxN = 0;
-    if (valid) {
-        tid = R.tid[i];
-        const int32_t pos = R.pos[i];
-        const uint32_t c0 = R.cigar_off[i], c1 = R.cigar_off[i + 1];
-        int64_t rlen = 0;
-        for (uint32_t c = c0; c < c1; c++) {
-            const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
-            if (op_ref(op)) rlen += cig_len(w);
-            if (op == OP_N) { nN++; maxN = max(maxN, (uint32_t)cig_len(w)); }
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t beg = warp * per_warp, end = min(R.n, beg + per_warp);
+    int32_t cur = -1; unsigned long long a_sp = 0, a_us = 0, a_sum = 0; int32_t a_mn = INT32_MAX, a_mx = 0; uint32_t a_maxn = 0;
+    auto flush = [&]() {
+        if (lane == 0 && cur >= 0 && (a_sp | a_us)) {
+            if (a_sp) atomicAdd(T.spliced + cur, a_sp);
+            if (a_us) atomicAdd(T.unspliced + cur, a_us);
+            atomicAdd(T.sumq + cur, a_sum); atomicMin(T.minq + cur, a_mn); atomicMax(T.maxq + cur, a_mx);
         }
-        read_end[i] = (int32_t)(pos + rlen - 1);
-        lq = R.l_qseq[i];
-        if (tid >= 0 && tid < n_targets) {
-            const int64_t endpos = (!(R.flag[i] & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
-            vis = pos < tlen[tid] && endpos > 0;
+        a_sp = a_us = a_sum = 0; a_mn = INT32_MAX; a_mx = 0;
+    };
+    for (int64_t base = beg; base < end; base += 32) {
+        const int64_t i = base + lane;
+        const bool valid = i < end;
+        bool vis = false; int32_t tid = -2, lq = 0; uint32_t nN = 0, maxN = 0;
+        if (valid) {
+            tid = R.tid[i];
+            const int32_t pos = R.pos[i];
+            const uint32_t c0 = R.cigar_off[i], c1 = R.cigar_off[i + 1];
+            int64_t rlen = 0;
+            for (uint32_t c = c0; c < c1; c++) {
+                const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
+                if (op_ref(op)) rlen += cig_len(w);
+                if (op == OP_N) { nN++; maxN = max(maxN, (uint32_t)cig_len(w)); }
+            }
+            read_end[i] = (int32_t)(pos + rlen - 1);
+            lq = R.l_qseq[i];
+            if (tid >= 0 && tid < n_targets) {
+                const int64_t endpos = (!(R.flag[i] & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
+                vis = pos < tlen[tid] && endpos > 0;
+            }
+            if (!vis) nN = 0;
+            npairs[i] = nN;
         }
-        if (!vis) nN = 0;
-        npairs[i] = nN;
-    }
-    // warp-aggregated per-target accumulation (records of a warp nearly always share the target)
-    const int32_t t0 = __shfl_sync(FULL, tid, 0);
-    const bool uniform = __all_sync(FULL, valid && tid == t0);
-    uint32_t mx = maxN;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-    if (lane == 0 && mx) atomicMax(max_nlen, mx);
-    if (uniform && t0 >= 0 && t0 < n_targets) {
-        const uint32_t sp = __popc(__ballot_sync(FULL, vis && nN > 0));
-        const uint32_t us = __popc(__ballot_sync(FULL, vis && nN == 0));
-        unsigned long long s = vis ? (unsigned long long)(long long)lq : 0ull;
-        int32_t mn = vis ? lq : INT32_MAX, mxq = vis ? lq : 0;
+        for (int o = 16; o; o >>= 1) maxN = max(maxN, __shfl_xor_sync(FULL, maxN, o));
+        a_maxn = max(a_maxn, maxN);
+        // lanes outside the run or invisible contribute nothing; a warp is "uniform" when its visible lanes share one target
+        const uint32_t vmask = __ballot_sync(FULL, vis);
+        if (vmask == 0) continue;
+        const int32_t t0 = __shfl_sync(FULL, tid, __ffs(vmask) - 1);
+        if (__all_sync(FULL, !vis || tid == t0)) {
+            const uint32_t sp = __popc(__ballot_sync(FULL, vis && nN > 0));
+            const uint32_t us = __popc(vmask) - sp;
+            unsigned long long s = vis ? (unsigned long long)(long long)lq : 0ull;
+            int32_t mn = vis ? lq : INT32_MAX, mxq = vis ? lq : 0;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            s += __shfl_xor_sync(FULL, s, o);
-            mn = min(mn, __shfl_xor_sync(FULL, mn, o));
-            mxq = max(mxq, __shfl_xor_sync(FULL, mxq, o));
+            for (int o = 16; o; o >>= 1) {
+                s += __shfl_xor_sync(FULL, s, o);
+                mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+                mxq = max(mxq, __shfl_xor_sync(FULL, mxq, o));
+            }
+            if (t0 != cur) { flush(); cur = t0; }
+            a_sp += sp; a_us += us; a_sum += s; a_mn = min(a_mn, mn); a_mx = max(a_mx, mxq);
+        } else if (vis) {                                  // a target boundary inside the warp: per-lane atomics (rare)
+            if (nN > 0) atomicAdd(T.spliced + tid, 1ull); else atomicAdd(T.unspliced + tid, 1ull);
+            atomicAdd(T.sumq + tid, (unsigned long long)(long long)lq); atomicMin(T.minq + tid, lq); atomicMax(T.maxq + tid, lq);
         }
-        if (lane == 0 && (sp | us)) {
-            if (sp) atomicAdd(T.spliced + t0, (unsigned long long)sp);
-            if (us) atomicAdd(T.unspliced + t0, (unsigned long long)us);
-            atomicAdd(T.sumq + t0, s); atomicMin(T.minq + t0, mn); atomicMax(T.maxq + t0, mxq);
-        }
-    } else if (vis) {
-        if (nN > 0) atomicAdd(T.spliced + tid, 1ull); else atomicAdd(T.unspliced + tid, 1ull);
-        atomicAdd(T.sumq + tid, (unsigned long long)(long long)lq); atomicMin(T.minq + tid, lq); atomicMax(T.maxq + tid, lq);
     }
+    flush();
+    if (lane == 0 && a_maxn) atomicMax(max_nlen, a_maxn);
 }
 
 void launch_scan_reads(const Reads& R, const int32_t* tlen, int32_t n_targets, uint32_t* npairs, int32_t* read_end,
-                       const TargetAcc& T, uint32_t* max_nlen, cudaStream_t st) {
+                       const TargetAcc& T, uint32_t* max_nlen, int n_sm, cudaStream_t st) {
     if (R.n <= 0) return;
-    k_scan_reads<<<(unsigned)((R.n + 255) / 256), 256, 0, st>>>(R, tlen, n_targets, npairs, read_end, T, max_nlen);
+    const int64_t blocks = (int64_t)n_sm * 8, warps = blocks * 8;               // 8 resident CTAs of 256 threads per SM
+    int64_t per_warp = ((R.n + warps - 1) / warps + 31) / 32 * 32;
+    if (per_warp < 32) per_warp = 32;
+    const int64_t used_blocks = ((R.n + per_warp - 1) / per_warp + 7) / 8;
+    k_scan_reads<<<(unsigned)used_blocks, 256, 0, st>>>(R, tlen, n_targets, npairs, read_end, T, max_nlen, per_warp);
 }
 
 // ================================================================================================
@@ -581,78 +612,49 @@ struct SideAcc { uint32_t cols; uint32_t mism; int32_t first_mm; int32_t last_mm
 
 constexpr uint64_t NIB1 = 0x1111111111111111ull;
 
-// 8 bytes starting at byte address p (any alignment) as a little-endian 64-bit value
-__device__ __forceinline__ uint64_t load_u64_unaligned(const uint8_t* __restrict__ p) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+// 16 consecutive nibbles of a BAM-ordered nibble stream (even index = high nibble of its byte), starting at nibble index
+// `nib` of `base`, returned MSB-first: nibble t sits at bits [60-4t, 64-4t).  Two aligned 64-bit loads cover any alignment.
+__device__ __forceinline__ uint64_t bswap64(uint64_t v) {
+    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
+}
+__device__ __forceinline__ uint64_t load_nibbles16(const uint8_t* __restrict__ base, uint64_t nib) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (uintptr_t)(nib >> 1);
     const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
-    const uint32_t sh = (uint32_t)(a & 7) * 8;
-    const uint64_t w0 = __ldg(q);
-    if (sh == 0) return w0;
-    const uint64_t w1 = __ldg(q + 1);
-    return (w0 >> sh) | (w1 << (64 - sh));
-}
-// `nbits` (<= 32) bits starting at bit index `bit` of a little-endian array of 64-bit words
-__device__ __forceinline__ uint32_t load_bits32(const uint64_t* __restrict__ w, uint64_t bit) {
-    const uint64_t i = bit >> 6; const uint32_t sh = (uint32_t)(bit & 63);
-    const uint64_t w0 = __ldg(w + i);
-    if (sh <= 32) return (uint32_t)(w0 >> sh);
-    const uint64_t w1 = __ldg(w + i + 1);
-    return (uint32_t)((w0 >> sh) | (w1 << (64 - sh)));
-}
-// 16 two-bit groups of a 32-bit word -> the low two bits of 16 nibbles
-__device__ __forceinline__ uint64_t spread2to4(uint32_t v) {
-    uint64_t x = v;
-    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
-    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
-    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
-    x = (x | (x << 2)) & 0x3333333333333333ull;
-    return x;
-}
-// 16 bits -> the lowest bit of 16 nibbles
-__device__ __forceinline__ uint64_t spread1to4(uint32_t v) {
-    uint64_t x = v & 0xFFFFu;
-    x = (x | (x << 24)) & 0x000000FF000000FFull;
-    x = (x | (x << 12)) & 0x000F000F000F000Full;
-    x = (x | (x << 6)) & 0x0303030303030303ull;
-    x = (x | (x << 3)) & NIB1;
-    return x;
+    const uint32_t o = (uint32_t)(a & 7) * 8 + (uint32_t)(nib & 1) * 4;       // bit offset into the 128-bit big-endian window
+    const uint64_t B = bswap64(__ldg(q));
+    if (o == 0) return B;
+    const uint64_t C = bswap64(__ldg(q + 1));
+    return (B << o) | (C >> (64 - o));
 }
 
 // Compare the columns of one M/=/X block: read nibbles q0.. against genome bases gi0.., `len` columns, string offset `sbase`.
+// Equal characters <=> equal nibbles, because the g4 plane uses the BAM alphabet; code 0 (rare) is resolved exactly.
 template <int G>
 __device__ __forceinline__ void compare_block(const Genome& Gn, const uint8_t* __restrict__ seq, int32_t q0, uint64_t gi0, int32_t len,
                                               int32_t sbase, int gl, SideAcc& r) {
-    const int32_t odd = q0 & 1;
-    const int32_t nchunk = (odd + len + 15) >> 4;
-    const uint8_t* sp = seq + (q0 >> 1);
+    const int32_t nchunk = (len + 15) >> 4;
     for (int32_t k = gl; k < nchunk; k += G) {
-        uint64_t x = load_u64_unaligned(sp + 8 * k);
-        x = ((x & 0x0F0F0F0F0F0F0F0Full) << 4) | ((x >> 4) & 0x0F0F0F0F0F0F0F0Full);   // base t of the chunk at bits [4t, 4t+4)
-        const int32_t c_first = 16 * k - odd;                                          // column of nibble 0 (may be -1)
-        const uint64_t gs = gi0 + (uint64_t)(int64_t)c_first;                          // genome layout has a 64-base lead pad
-        const uint64_t S = spread2to4(load_bits32(Gn.g2, gs * 2));
-        const uint64_t Eb = spread1to4(load_bits32(Gn.gx, gs));
-        const uint64_t L = S & NIB1, H = (S >> 1) & NIB1;
-        uint64_t g4 = (~(L | H) & NIB1) | ((L & ~H) << 1) | ((H & ~L) << 2) | ((L & H) << 3);   // one-hot: A=1 C=2 G=4 T=8
-        g4 |= (Eb << 4) - Eb;                                                          // exception base: 'N' = 15 (sub-code 0)
-        uint64_t d = x ^ g4;
-        d |= d >> 1; d |= d >> 2; d &= NIB1;
-        const int32_t t_lo = c_first < 0 ? -c_first : 0;
-        const int32_t t_hi = min(16, len - c_first);
-        uint64_t V = (t_hi >= 16 ? ~0ull : ((1ull << (4 * t_hi)) - 1ull)) & ~((1ull << (4 * t_lo)) - 1ull);
-        d &= V;
-        uint64_t other = Eb & L & V;                                                   // exception bytes other than 'N': exact side-table compare
-        while (other) {
-            const int t = (__ffsll((long long)other) - 1) >> 2;
-            other &= other - 1;
-            const uint32_t nib = (uint32_t)(x >> (4 * t)) & 0xfu;
-            const bool mm = !base_matches(Gn, gs + (uint64_t)t, nib);
-            d = (d & ~(1ull << (4 * t))) | ((uint64_t)mm << (4 * t));
+        const uint64_t x = load_nibbles16(seq, (uint64_t)(uint32_t)(q0 + 16 * k));
+        const uint64_t g = load_nibbles16(Gn.g4, gi0 + (uint64_t)(16 * k));
+        const int32_t nv = min(16, len - 16 * k);
+        const uint64_t V = nv >= 16 ? ~0ull : ~(~0ull >> (4 * nv));                   // the first nv nibbles
+        uint64_t d = (x ^ g) & V;
+        if (Gn.n_zero_code) {                                                         // genome bytes outside the BAM alphabet (or '=')
+            uint64_t z = ~(g | (g >> 1) | (g >> 2) | (g >> 3)) & NIB1 & V;
+            while (z) {
+                const int t = (63 - (__ffsll((long long)z) - 1)) >> 2;
+                z &= z - 1;
+                const uint32_t nibq = (uint32_t)(x >> (60 - 4 * t)) & 0xfu;
+                const bool mm = (uint8_t)("=ACMGRSVTWYHKDBN"[nibq]) != genome_exc_lookup(Gn, gi0 + (uint64_t)(16 * k + t));
+                d = (d & ~(0xfull << (60 - 4 * t))) | ((mm ? 0xfull : 0ull) << (60 - 4 * t));
+            }
         }
         if (d) {
-            r.mism += __popcll(d);
-            const int32_t f = sbase + c_first + ((__ffsll((long long)d) - 1) >> 2);
-            const int32_t l = sbase + c_first + ((63 - __clzll((long long)d)) >> 2);
+            uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;
+            r.mism += __popcll(m);
+            const int32_t f = sbase + 16 * k + (__clzll((long long)d) >> 2);
+            const int32_t l = sbase + 16 * k + 15 - ((__ffsll((long long)d) - 1) >> 2);
             r.first_mm = min(r.first_mm, f); r.last_mm = max(r.last_mm, l);
         }
     }

@@ -32,6 +32,9 @@ enum : uint32_t {
 };
 
 // ---- packed genome resident in HBM ----
+// Two views of the same upper-cased sequence are kept resident:
+//   * 2-bit plane + exception bitmask (g2/gx): splice-site motif and Hamming windows (k_finalize), 128-bit friendly;
+//   * 4-bit plane (g4) in the BAM SEQ alphabet: lets the per-read anchor comparison be a 64-bit XOR of 16 bases.
 // g2 : 2 bits per base (A=0,C=1,G=2,T=3), 32 bases per 64-bit word, little-endian within the word.
 // gx : 1 bit per base, set when the upper-cased byte is not A/C/G/T; 64 bases per 64-bit word.
 //      For an exception base the 2-bit field holds a sub-code: 0 = 'N', 1 = any other byte, whose exact value lives
@@ -40,12 +43,15 @@ enum : uint32_t {
 struct Genome {
     const uint64_t* g2;
     const uint64_t* gx;
+    const uint8_t*  g4;         // 4 bits per base in the BAM SEQ alphabet and nibble order (even base = high nibble): the plane the
+                                // mismatch walk XORs against SEQ.  Code 0 = '=' or a byte outside "=ACMGRSVTWYHKDBN" (exact byte in the side table)
     const uint64_t* goff;       // [n_targets] first base index of each target (multiple of 64)
     const int64_t*  glen;       // [n_targets] sequence length from the FASTA (-1 when the target was not loaded)
     const uint64_t* exc_pos;    // sorted global base indices of "other" exception bytes
     const uint8_t*  exc_byte;
     int32_t n_exc;
     int32_t n_exc_x;            // how many of them are 'X'
+    int32_t n_zero_code;        // how many bases have g4 code 0 (needs the side table to compare exactly)
 };
 
 __device__ __forceinline__ uint8_t genome_exc_lookup(const Genome& g, uint64_t gi) {

@@ -23,10 +23,10 @@ uint64_t scan_tmp_elems(uint64_t n);
 void launch_fill_i32(int32_t* a, int64_t n, int32_t v, cudaStream_t st);
 void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st);
 void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st);
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint8_t* g4,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st);
 void launch_scan_reads(const Reads& R, const int32_t* tlen, int32_t n_targets, uint32_t* npairs, int32_t* read_end,
-                       const TargetAcc& T, uint32_t* max_nlen, cudaStream_t st);
+                       const TargetAcc& T, uint32_t* max_nlen, int n_sm, cudaStream_t st);
 void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff, int32_t len_bits, int32_t orientation,
                        const uint32_t* pair_off, const uint32_t* npairs, const int32_t* read_end,
                        uint64_t* keys, PairA* pa, PairB* pb, uint32_t* err, cudaStream_t st);

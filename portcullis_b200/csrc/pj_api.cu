@@ -36,16 +36,16 @@ struct StageTime { const char* name; cudaEvent_t ev; };
 } // namespace
 
 struct pj_ctx {
-    int device = 0; int orientation = PJ_ORIENT_UNKNOWN; int match_group = 0;
+    int device = 0; int orientation = PJ_ORIENT_UNKNOWN; int match_group = 0; int n_sm = 148;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     std::string err;
     // targets / genome
     int32_t n_targets = 0;
     std::vector<int32_t> h_tlen; std::vector<uint64_t> h_toff, h_goff; std::vector<int64_t> h_glen;
     int32_t* d_tlen = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_goff = nullptr; int64_t* d_glen = nullptr;
-    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint64_t g_total_bases = 0;
+    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint8_t* d_g4 = nullptr; uint64_t g_total_bases = 0;
     uint64_t* d_exc_pos = nullptr; uint8_t* d_exc_byte = nullptr; uint32_t* d_exc_count = nullptr; uint32_t exc_cap = 1u << 20;
-    int32_t n_exc = 0, n_exc_x = 0; bool genome_dirty = false;
+    int32_t n_exc = 0, n_exc_x = 0, n_zero_code = 0; bool genome_dirty = false;
     uint8_t* h_graw[2] = {nullptr, nullptr}; uint8_t* d_graw[2] = {nullptr, nullptr}; cudaEvent_t graw_ev[2] = {nullptr, nullptr};
     static constexpr size_t GRAW_CHUNK = 64u << 20;
     // shard arena
@@ -139,7 +139,8 @@ int finish_genome(pj_ctx* c) {
         CU(c, cudaMemcpy(c->d_exc_pos, p2.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CU(c, cudaMemcpy(c->d_exc_byte, b2.data(), cnt, cudaMemcpyHostToDevice));
         c->n_exc_x = (int32_t)std::count(b2.begin(), b2.end(), (uint8_t)'X');
-    } else c->n_exc_x = 0;
+        c->n_zero_code = (int32_t)std::count_if(b2.begin(), b2.end(), [](uint8_t b) { return b == '=' || !strchr("ACMGRSVTWYHKDBN", (int)b); });
+    } else { c->n_exc_x = 0; c->n_zero_code = 0; }
     c->n_exc = (int32_t)cnt;
     c->genome_dirty = false;
     return PJ_OK;
@@ -169,6 +170,7 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
     c->match_group = cfg->reserved[0];                 // 0 = choose from the data; 1..32 forces the lanes-per-pair of k_match (tuning / tests)
     if (const char* e = getenv("PJ_MATCH_GROUP")) c->match_group = atoi(e);
     CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
     CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
     CU(c, cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
@@ -190,7 +192,7 @@ void pj_destroy(pj_ctx* c) {
     c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_();
     for (int s = 0; s < 2; s++) { free_slot(c->slot[s]); if (c->slot[s].done) cudaEventDestroy(c->slot[s].done); if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
                                   if (c->h_graw[s]) cudaFreeHost(c->h_graw[s]); if (c->d_graw[s]) cudaFree(c->d_graw[s]); }
-    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx);
+    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx); cudaFree(c->d_g4);
     cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
     cudaFree(c->d_spliced); cudaFree(c->d_unspliced); cudaFree(c->d_sumq); cudaFree(c->d_minq); cudaFree(c->d_maxq);
     cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
@@ -223,6 +225,7 @@ int pj_targets_set(pj_ctx* c, int32_t n_targets, const int32_t* target_len) {
     CU(c, cudaMemcpy(c->d_glen, c->h_glen.data(), n_targets * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(c, cudaMalloc(&c->d_g2, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMalloc(&c->d_gx, g / 64 * sizeof(uint64_t) + 64));
     CU(c, cudaMemset(c->d_g2, 0, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMemset(c->d_gx, 0, g / 64 * sizeof(uint64_t) + 64));
+    CU(c, cudaMalloc(&c->d_g4, g / 2 + 64)); CU(c, cudaMemset(c->d_g4, 0, g / 2 + 64));
     CU(c, cudaMalloc(&c->d_exc_pos, c->exc_cap * sizeof(uint64_t))); CU(c, cudaMalloc(&c->d_exc_byte, c->exc_cap));
     CU(c, cudaMalloc(&c->d_exc_count, sizeof(uint32_t))); CU(c, cudaMemset(c->d_exc_count, 0, sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->d_spliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_unspliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_sumq, n_targets * 8));
@@ -242,7 +245,7 @@ int pj_genome_set_target(pj_ctx* c, int32_t tid, const char* bases, int64_t n_ba
         CU(c, cudaEventSynchronize(c->graw_ev[s]));                  // slot free again?
         memcpy(c->h_graw[s], bases + o, (size_t)k);
         CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->copy_stream));
-        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->copy_stream);
+        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_g4, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->copy_stream);
         CU(c, cudaEventRecord(c->graw_ev[s], c->copy_stream));
     }
     c->h_glen[tid] = n_bases < c->h_tlen[tid] ? n_bases : (int64_t)c->h_tlen[tid];
@@ -349,7 +352,7 @@ int pj_shard_run(pj_ctx* c) {
     const size_t Ra = (size_t)std::max<int64_t>(R, 1);
     CU(c, cudaMallocAsync(&npairs, Ra * 4, st)); CU(c, cudaMallocAsync(&pair_off, (Ra + 1) * 4, st)); CU(c, cudaMallocAsync(&read_end, Ra * 4, st));
     CU(c, cudaMallocAsync(&scan_tmp, scan_tmp_elems(Ra) * 4, st));
-    launch_scan_reads(Rd, c->d_tlen, T, npairs, read_end, TA, d_maxn, st); c->n_launches++;
+    launch_scan_reads(Rd, c->d_tlen, T, npairs, read_end, TA, d_maxn, c->n_sm, st); c->n_launches++;
     mark(c, "scan_reads");
     launch_exclusive_scan(npairs, pair_off, (uint64_t)R, scan_tmp, d_P, st); c->n_launches += 3;
     mark(c, "pair_offsets");
@@ -411,7 +414,7 @@ int pj_shard_run(pj_ctx* c) {
         launch_entropy_compact(P, spare_u32, eoff, epos, st); c->n_launches++;
         launch_entropy_sum(J, seg_start, eoff, epos, entropy, st); c->n_launches++;
         mark(c, "entropy");
-        Genome G{c->d_g2, c->d_gx, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x};
+        Genome G{c->d_g2, c->d_gx, c->d_g4, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->n_zero_code};
         uint4* pm = nullptr; CU(c, cudaMallocAsync(&pm, (size_t)P * sizeof(uint4), st));
         {   // lanes per (read, junction) pair: one 16-base word per lane and step; long reads get wider groups
             int group = c->match_group;
