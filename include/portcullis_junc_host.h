@@ -77,6 +77,11 @@ int         pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch*
 /* Unwrapped FASTA bytes of a target (owned by `p`, valid until the next call for another target or close). */
 int         pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bases);
 
+/* Shard plan: gpu_of_target[tid] in [0, n_gpus) — whole targets, longest processing time first on the index's record
+ * counts (compressed bytes when the index has no counts).  Deterministic, so every rank of a multi-process launch
+ * computes the same plan. */
+int         pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_target);
+
 /* ---- writers (A14) ---- */
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,
                       int32_t n_targets, const char* const* names, const int32_t* lens,

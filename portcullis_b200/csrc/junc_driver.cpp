@@ -144,6 +144,26 @@ int64_t pjh_prep_target_records(const pjh_prep* p, int32_t t) {
     return (int64_t)(p->bam.index()[t].n_mapped + p->bam.index()[t].n_unmapped);
 }
 
+static uint64_t target_weight(const pjh_prep* p, int32_t t) {
+    const int64_t n = pjh_prep_target_records(p, t);
+    if (n > 0) return (uint64_t)n;
+    std::vector<DecodeTask> tasks; p->bam.plan_target(t, 4u << 20, tasks);
+    uint64_t bytes = 0; for (auto& k : tasks) bytes += k.approx_bytes;
+    return bytes / 64;
+}
+
+int pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_target) {
+    if (!p || n_gpus < 1 || !gpu_of_target) return fail(PJ_EINVAL, "pjh_plan_shards: bad argument");
+    const int32_t T = pjh_prep_n_targets(p);
+    std::vector<uint64_t> weight((size_t)T, 0);
+    if (p->indexed) for (int32_t t = 0; t < T; t++) weight[t] = target_weight(p, t);
+    std::vector<int32_t> ord((size_t)T); for (int32_t t = 0; t < T; t++) ord[t] = t;
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
+    std::vector<uint64_t> load((size_t)n_gpus, 0);
+    for (int32_t t : ord) { const size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin()); gpu_of_target[t] = (int32_t)g; load[g] += weight[t] + 1; }
+    return PJ_OK;
+}
+
 int pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out) {
     if (!p || !out) return fail(PJ_EINVAL, "pjh_prep_decode: null argument");
     std::vector<DecodeTask> tasks;
@@ -239,21 +259,13 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     // ---- shard targets over GPUs: LPT on index record counts (fallback: compressed bytes) ----
     std::vector<std::vector<DecodeTask>> ttasks((size_t)T);
     std::vector<uint64_t> weight((size_t)T, 0);
-    if (prep->indexed) {
-        for (int32_t t = 0; t < T; t++) {
-            prep->bam.plan_target(t, 4u << 20, ttasks[t]);
-            int64_t n = pjh_prep_target_records(prep, t);
-            uint64_t bytes = 0; for (auto& k : ttasks[t]) bytes += k.approx_bytes;
-            weight[t] = n > 0 ? (uint64_t)n : bytes / 64;
-        }
-    } else { n_gpus = 1; }
+    if (prep->indexed) for (int32_t t = 0; t < T; t++) { prep->bam.plan_target(t, 4u << 20, ttasks[t]); weight[t] = target_weight(prep, t); }
+    else n_gpus = 1;
     std::vector<std::vector<int32_t>> shard((size_t)n_gpus);
     {
-        std::vector<int32_t> ord((size_t)T); for (int32_t t = 0; t < T; t++) ord[t] = t;
-        std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return weight[a] > weight[b]; });
-        std::vector<uint64_t> load((size_t)n_gpus, 0);
-        for (int32_t t : ord) { size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin()); shard[g].push_back(t); load[g] += weight[t] + 1; }
-        for (auto& s : shard) std::sort(s.begin(), s.end());   // BAM order inside a shard
+        std::vector<int32_t> owner((size_t)T, 0);
+        if ((rc = pjh_plan_shards(prep, n_gpus, owner.data()))) return rc;
+        for (int32_t t = 0; t < T; t++) shard[(size_t)owner[t]].push_back(t);     // ascending tid = BAM order inside a shard
     }
     R.t_open_s = now_s() - t0;
     R.n_gpus_used = n_gpus;

@@ -34,6 +34,12 @@ class PrepDir:
     def target_records(self, tid):
         return self._lib.pjh_prep_target_records(self._p, tid)
 
+    def plan_shards(self, n_gpus):
+        """gpu_of_target[tid] for an n_gpus launch (LPT on index record counts); identical on every rank."""
+        owner = np.zeros(len(self.names), dtype=np.int32)
+        _check(self._lib.pjh_plan_shards(self._p, n_gpus, owner.ctypes.data), self._lib.pjh_last_error)
+        return owner
+
     def decode(self, tid=-1, threads=1):
         """Decode one target (or all with tid=-1) into owned numpy columns."""
         b = L.PjBatch()
