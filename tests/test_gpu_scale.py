@@ -32,10 +32,14 @@ def synth(tmpdir, preset, scale, seed=0):
 
 
 @pytest.mark.parametrize("preset,scale,orient,gpus", [("c2", 0.05, None, 1), ("c2", 0.03, "FR", 1), ("c3", 0.004, None, 1),
-                                                      ("c4", 0.05, None, 1), ("c5", 0.03, None, 1)])
+                                                      ("c4", 0.05, None, 1), ("c5", 0.03, None, 1),
+                                                      ("c2", 0.05, None, 2), ("c3", 0.004, "RF", 4)])
 def test_presets_reproduce_reference_files(tmp_path, preset, scale, orient, gpus):
+    import torch
     if not os.path.exists(ob.REF_BIN):
         pytest.skip("oracle/_ref/portcullis_ref not built")
+    if torch.cuda.device_count() < gpus:
+        pytest.skip("needs %d GPUs" % gpus)
     prep, meta = synth(tmp_path, preset, scale)
     ref_prefix = os.path.join(str(tmp_path), "ref", "r")
     refrun.run_reference(prep, ref_prefix, threads=min(8, meta["n_targets"]), orientation=orient)
@@ -72,14 +76,11 @@ def test_full_c2_properties(tmp_path):
     assert int(st["spliced"].sum()) == meta["n_spliced"]
     assert int(st["spliced"].sum() + st["unspliced"].sum()) == meta["n_records"]
     assert int(st["sumq"].sum()) == int(cols["l_qseq"].astype(np.int64).sum())
-    key = rows["tid"].astype(np.int64) << 40 | rows["start"].astype(np.int64) << 8
     assert np.all(np.diff(rows["tid"]) >= 0)
     order = np.lexsort((rows["end"], rows["start"], rows["tid"]))
     assert np.array_equal(order, np.arange(len(rows))), "rows not sorted by (tid,start,end)"
     assert len(np.unique(np.stack([rows["tid"], rows["start"], rows["end"]], 1), axis=0)) == len(rows)
     # per-junction identities
-    for a, b, c in (("nb_r1_pos", "nb_r1_neg", None),):
-        pass
     tot = rows["nb_r1_pos"].astype(np.int64) + rows["nb_r1_neg"] + rows["nb_r2_pos"] + rows["nb_r2_neg"]
     assert np.array_equal(tot, rows["nb_raw_aln"].astype(np.int64))
     assert np.all(rows["nb_dist_aln"] <= rows["nb_raw_aln"]) and np.all(rows["nb_dist_aln"] >= 1)
@@ -87,5 +88,6 @@ def test_full_c2_properties(tmp_path):
     assert np.all(rows["jad"][:, 0] <= rows["nb_raw_aln"]) and np.all(np.diff(rows["jad"].astype(np.int64), axis=1) <= 0)
     assert np.all(rows["left"] < rows["start"]) and np.all(rows["right"] > rows["end"])
     assert np.all((rows["entropy"] >= 0) & (rows["entropy"] <= np.log2(np.maximum(rows["nb_raw_aln"], 1)) + 1e-9))
-    canon = (rows["canonical_ss"] == ord("C")).mean()
-    assert canon > 0.9, canon                                                      # planted GT..AG / CT..AC
+    w = rows["nb_raw_aln"].astype(np.float64)
+    canon = float((w * (rows["canonical_ss"] == ord("C"))).sum() / w.sum())
+    assert canon > 0.9, canon                                                      # planted GT..AG / CT..AC carry most reads
