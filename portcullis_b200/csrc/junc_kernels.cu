@@ -608,7 +608,6 @@ void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32
 // compared 16 bases per step: 16 BAM nibbles (one unaligned 64-bit window of SEQ) against 16 genome bases
 // expanded from the 2-bit plane to one-hot nibbles, so a mismatch is a non-zero nibble of an XOR.
 // ================================================================================================
-struct SideAcc { uint32_t cols; uint32_t mism; int32_t first_mm; int32_t last_mm; };   // first/last: string indices, INT32_MAX / -1 = none
 
 constexpr uint64_t NIB1 = 0x1111111111111111ull;
 
@@ -628,17 +627,47 @@ __device__ __forceinline__ uint64_t load_nibbles16(const uint8_t* __restrict__ b
     return (B << o) | (C >> (64 - o));
 }
 
-// Compare the columns of one M/=/X block: read nibbles q0.. against genome bases gi0.., `len` columns, string offset `sbase`.
-// Equal characters <=> equal nibbles, because the g4 plane uses the BAM alphabet; code 0 (rare) is resolved exactly.
+// ---- per-lane queue of compare blocks (shared memory, one column per thread: conflict-free) ----
+// Lanes of a warp reach their M/=/X blocks in different CIGAR iterations; comparing inside the walk would make the
+// warp pay the longest block in EVERY iteration.  Instead the walk only queues (SEQ nibble index, genome index, length,
+// string offset, side) and drain() then runs ONE flat loop over 16-base chunks in which every lane is busy.
+constexpr int MQ = 4;              // queued blocks per lane before a drain
+struct MatchQueue {
+    uint64_t qn[MQ][256];          // index of the block's first read nibble in the shard's SEQ stream
+    uint64_t gi[MQ][256];          // global genome base index of its first column
+    int32_t  len[MQ][256];
+    int32_t  sb[MQ][256];          // (string offset of column 0) << 1 | side
+};
+
+struct PairStats { uint32_t mism_l, mism_r; int32_t last_left; int32_t first_right; };
+
+// Flat loop over the 16-base chunks of all queued blocks.  Chunks are aligned to the genome's 16-base words (one aligned
+// 64-bit load); SEQ is extracted unaligned.  The left anchor tracks its LAST mismatch, the right anchor its FIRST: that is
+// all getNbMatchesFromEnd / getNbMatchesFromStart need.  Equal characters <=> equal nibbles because g4 uses the BAM
+// alphabet; code 0 (bytes outside it) is resolved exactly through the side table.
 template <int G>
-__device__ __forceinline__ void compare_block(const Genome& Gn, const uint8_t* __restrict__ seq, int32_t q0, uint64_t gi0, int32_t len,
-                                              int32_t sbase, int gl, SideAcc& r) {
-    const int32_t nchunk = (len + 15) >> 4;
-    for (int32_t k = gl; k < nchunk; k += G) {
-        const uint64_t x = load_nibbles16(seq, (uint64_t)(uint32_t)(q0 + 16 * k));
-        const uint64_t g = load_nibbles16(Gn.g4, gi0 + (uint64_t)(16 * k));
-        const int32_t nv = min(16, len - 16 * k);
-        const uint64_t V = nv >= 16 ? ~0ull : ~(~0ull >> (4 * nv));                   // the first nv nibbles
+__device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome& Gn, const uint8_t* __restrict__ seq4, int gl, PairStats& r) {
+    const int col = threadIdx.x;
+    int bi = -1; int32_t k = 0, nchunk = 0, a0 = 0, len = 0, sbase = 0, side = 0;
+    uint64_t qn = 0, gi0 = 0; const uint64_t* gw = nullptr;
+    for (;;) {
+        if (k >= nchunk) {                                                            // next block of this lane
+            if (++bi >= nq) break;
+            gi0 = Q.gi[bi][col]; len = Q.len[bi][col];
+            const int32_t sbv = Q.sb[bi][col]; sbase = sbv >> 1; side = sbv & 1;
+            a0 = (int32_t)(gi0 & 15);
+            nchunk = (a0 + len + 15) >> 4;
+            gw = reinterpret_cast<const uint64_t*>(Gn.g4) + ((gi0 - a0) >> 4);
+            qn = Q.qn[bi][col] - (uint64_t)a0;                                        // SEQ stream has a 16-byte lead pad
+            k = gl;
+            if (k >= nchunk) continue;
+        }
+        const uint64_t g = bswap64(__ldg(gw + k));
+        const uint64_t x = load_nibbles16(seq4, qn + (uint64_t)(16 * k));
+        const int32_t c0 = 16 * k - a0;                                               // column of nibble 0 of this chunk
+        const int32_t t_hi = min(16, len - c0);
+        uint64_t V = t_hi >= 16 ? ~0ull : ~(~0ull >> (4 * t_hi));
+        if (c0 < 0) V &= ~0ull >> (4 * -c0);
         uint64_t d = (x ^ g) & V;
         if (Gn.n_zero_code) {                                                         // genome bytes outside the BAM alphabet (or '=')
             uint64_t z = ~(g | (g >> 1) | (g >> 2) | (g >> 3)) & NIB1 & V;
@@ -646,68 +675,90 @@ __device__ __forceinline__ void compare_block(const Genome& Gn, const uint8_t* _
                 const int t = (63 - (__ffsll((long long)z) - 1)) >> 2;
                 z &= z - 1;
                 const uint32_t nibq = (uint32_t)(x >> (60 - 4 * t)) & 0xfu;
-                const bool mm = (uint8_t)("=ACMGRSVTWYHKDBN"[nibq]) != genome_exc_lookup(Gn, gi0 + (uint64_t)(16 * k + t));
+                const bool mm = (uint8_t)("=ACMGRSVTWYHKDBN"[nibq]) != genome_exc_lookup(Gn, gi0 + (uint64_t)(int64_t)(c0 + t));
                 d = (d & ~(0xfull << (60 - 4 * t))) | ((mm ? 0xfull : 0ull) << (60 - 4 * t));
             }
         }
         if (d) {
             uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;
-            r.mism += __popcll(m);
-            const int32_t f = sbase + 16 * k + (__clzll((long long)d) >> 2);
-            const int32_t l = sbase + 16 * k + 15 - ((__ffsll((long long)d) - 1) >> 2);
-            r.first_mm = min(r.first_mm, f); r.last_mm = max(r.last_mm, l);
+            const uint32_t cnt = (uint32_t)__popcll(m);
+            if (side == 0) { r.mism_l += cnt; r.last_left = max(r.last_left, sbase + c0 + 15 - ((__ffsll((long long)d) - 1) >> 2)); }
+            else           { r.mism_r += cnt; r.first_right = min(r.first_right, sbase + c0 + (__clzll((long long)d) >> 2)); }
         }
+        k += G;
     }
 }
 
+// One pass over the CIGAR serves both anchor windows: the left walk of the reference stops at the first op it rejects,
+// and every op the right walk accepts starts at or after rightStart > leftEnd, so the two walks touch disjoint ops while
+// rPos / qPos accumulate identically (bam_alignment.cc:349-399).
 template <int G>
-__device__ __forceinline__ SideAcc walk_side(const Genome& Gn, uint64_t gbase, int64_t glen, const uint32_t* __restrict__ cg, int32_t n_cig,
-                                             int32_t pos, const uint8_t* __restrict__ seq, int32_t qoff, int32_t qsize,
-                                             int32_t wstart, int32_t wend, int gl, uint32_t& err) {
-    SideAcc r{0u, 0u, INT32_MAX, -1};
+__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, uint64_t gbase, int64_t glen, const uint32_t* __restrict__ cg, int32_t n_cig,
+                                               int32_t pos, const uint8_t* __restrict__ seq4, uint64_t seq_nib0, int32_t qsize,
+                                               int32_t left, int32_t leftEnd, int32_t rightStart, int32_t right, int gl, uint32_t& err,
+                                               uint32_t& cols_l, uint32_t& cols_r) {
+    PairStats r{0u, 0u, -1, INT32_MAX};
+    const int col = threadIdx.x;
     int32_t qPos = 0, rPos = pos;
+    int side = 0; int32_t wstart = left, wend = leftEnd;
+    uint32_t cols = 0; int nq = 0;
+    cols_l = 0; cols_r = 0;
     for (int32_t k = 0; k < n_cig; k++) {
         const uint32_t w = __ldg(cg + k), op = cig_op(w); const int32_t L = cig_len(w);
         const bool cr = op_ref(op), cq = op_query(op);
+        if (side == 0 && rPos >= wstart && ((rPos > wend && op != OP_I) || (op == OP_N && rPos + L > wend))) {   // left walk ends here
+            side = 1; wstart = rightStart; wend = right; cols_l = cols; cols = 0;
+        }
         if (rPos < wstart) { if (cr) rPos += L; if (cq) qPos += L; continue; }          // Q4: op-granular skip
-        if ((rPos > wend && op != OP_I) || (op == OP_N && rPos + L > wend)) break;      // Q5
+        if ((rPos > wend && op != OP_I) || (op == OP_N && rPos + L > wend)) break;      // Q5 (only reachable with side == 1)
         if (cq) {
             const int32_t len = (rPos + L > wend && op != OP_I) ? wend - rPos + 1 : L;
             if (len == 0) { err |= ERR_ZERO_LEN; break; }
             if (qPos + len > qsize) { err |= ERR_QUERY_RANGE; break; }
             if (op == OP_I) {
                 // query bases against 'X' padding in the genome string: never equal (no 'X' in the BAM alphabet)
-                if (gl == 0) { r.first_mm = min(r.first_mm, (int32_t)r.cols); r.last_mm = max(r.last_mm, (int32_t)r.cols + len - 1); r.mism += (uint32_t)len; }
+                if (gl == 0) {
+                    if (side == 0) { r.mism_l += (uint32_t)len; r.last_left = max(r.last_left, (int32_t)cols + len - 1); }
+                    else           { r.mism_r += (uint32_t)len; r.first_right = min(r.first_right, (int32_t)cols); }
+                }
             } else {
                 if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
-                compare_block<G>(Gn, seq, qoff + qPos, gbase + (uint64_t)(uint32_t)rPos, len, (int32_t)r.cols, gl, r);
+                Q.qn[nq][col] = seq_nib0 + (uint64_t)qPos; Q.gi[nq][col] = gbase + (uint64_t)(uint32_t)rPos;
+                Q.len[nq][col] = len; Q.sb[nq][col] = (int32_t)(cols << 1) | side;
+                if (++nq == MQ) { drain<G>(Q, nq, Gn, seq4, gl, r); nq = 0; }
             }
-            r.cols += (uint32_t)len;
+            cols += (uint32_t)len;
         } else if (cr) {                                                                   // D or N inside the window: 'X' vs genome
             const int32_t len = rPos + L > wend ? wend - rPos + 1 : L;
             if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
             if (Gn.n_exc_x == 0) {
-                if (gl == 0 && len > 0) { r.first_mm = min(r.first_mm, (int32_t)r.cols); r.last_mm = max(r.last_mm, (int32_t)r.cols + len - 1); r.mism += (uint32_t)len; }
+                if (gl == 0 && len > 0) {
+                    if (side == 0) { r.mism_l += (uint32_t)len; r.last_left = max(r.last_left, (int32_t)cols + len - 1); }
+                    else           { r.mism_r += (uint32_t)len; r.first_right = min(r.first_right, (int32_t)cols); }
+                }
             } else {
                 for (int32_t c = gl; c < len; c += G) {
                     if (genome_char(Gn, gbase + (uint64_t)(uint32_t)(rPos + c)) != (uint8_t)'X') {
-                        r.first_mm = min(r.first_mm, (int32_t)r.cols + c); r.last_mm = max(r.last_mm, (int32_t)r.cols + c); r.mism++;
+                        if (side == 0) { r.mism_l++; r.last_left = max(r.last_left, (int32_t)cols + c); }
+                        else           { r.mism_r++; r.first_right = min(r.first_right, (int32_t)cols + c); }
                     }
                 }
             }
-            r.cols += (uint32_t)len;
+            cols += (uint32_t)len;
         }
         if (cr) rPos += L;
         if (cq) qPos += L;
     }
+    drain<G>(Q, nq, Gn, seq4, gl, r);
+    if (side == 0) cols_l = cols; else cols_r = cols;
     if (G > 1) {   // combine the lanes of the group
         const int lane = threadIdx.x & 31;
         const uint32_t gmask = (G == 32) ? FULL : (((1u << G) - 1u) << (lane & ~(G - 1)));
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
-            r.mism += __shfl_xor_sync(gmask, r.mism, o);
-            r.first_mm = min(r.first_mm, __shfl_xor_sync(gmask, r.first_mm, o));
-            r.last_mm = max(r.last_mm, __shfl_xor_sync(gmask, r.last_mm, o));
+            r.mism_l += __shfl_xor_sync(gmask, r.mism_l, o); r.mism_r += __shfl_xor_sync(gmask, r.mism_r, o);
+            r.last_left = max(r.last_left, __shfl_xor_sync(gmask, r.last_left, o));
+            r.first_right = min(r.first_right, __shfl_xor_sync(gmask, r.first_right, o));
         }
     }
     return r;
@@ -717,13 +768,14 @@ template <int G>
 __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairA* __restrict__ pa, const PairB* __restrict__ pb,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
+    __shared__ MatchQueue Q;
     const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
     const int gl = threadIdx.x % G;
-    if (i >= n) return;                                              // whole groups leave together
+    if (i >= n) return;                                              // whole groups leave together; no block-wide barrier is used
     const uint32_t j = jid[i];
     const uint32_t idx = vals[i];
     const PairA a = pa[idx]; const PairB b = pb[idx];
-    const int32_t start = A.start[j], end = A.end[j], left = A.left[j], right = A.right[j];
+    const int32_t start = b.start, end = A.end[j], left = A.left[j], right = A.right[j];
     const int32_t tid = A.tid[j];
     const int32_t lq = R.l_qseq[a.rid];
     uint32_t err = 0, mmes, minMatch, nbMism;
@@ -745,17 +797,15 @@ __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __res
         const int64_t glen = Gn.glen[tid];
         if (left > b.read_end || leftEnd < a.pos || rightStart > b.read_end || right < a.pos) err |= ERR_NO_PRESENCE;
         if (glen < 0) err |= ERR_GENOME_RANGE;
-        SideAcc L{0, 0, INT32_MAX, -1}, Rr{0, 0, INT32_MAX, -1};
+        PairStats S{0u, 0u, -1, INT32_MAX}; uint32_t cols_l = 0, cols_r = 0;
         if (!err) {
-            const uint64_t gbase = Gn.goff[tid];
-            L = walk_side<G>(Gn, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, left, leftEnd, gl, err);
-            Rr = walk_side<G>(Gn, gbase, glen, cg, n_cig, a.pos, R.seq4 + so, ds, (int32_t)qs, rightStart, right, gl, err);
-            if (L.cols == 0 || Rr.cols == 0) err |= ERR_EMPTY_ANCHOR;
+            S = walk_pair<G>(Q, Gn, Gn.goff[tid], glen, cg, n_cig, a.pos, R.seq4, so * 2 + (uint64_t)ds, (int32_t)qs, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
+            if (cols_l == 0 || cols_r == 0) err |= ERR_EMPTY_ANCHOR;
         }
-        const uint32_t upMatches = L.cols - L.mism, downMatches = Rr.cols - Rr.mism;
-        nbMism = L.mism + Rr.mism;
-        const uint32_t us = L.last_mm < 0 ? L.cols : (L.cols - 1u - (uint32_t)L.last_mm);              // getNbMatchesFromEnd
-        const uint32_t dsm = Rr.first_mm == INT32_MAX ? Rr.cols : (uint32_t)Rr.first_mm;                // getNbMatchesFromStart
+        const uint32_t upMatches = cols_l - S.mism_l, downMatches = cols_r - S.mism_r;
+        nbMism = S.mism_l + S.mism_r;
+        const uint32_t us = S.last_left < 0 ? cols_l : (cols_l - 1u - (uint32_t)S.last_left);            // getNbMatchesFromEnd
+        const uint32_t dsm = S.first_right == INT32_MAX ? cols_r : (uint32_t)S.first_right;               // getNbMatchesFromStart
         minMatch = min(us, dsm);
         mmes = min(upMatches, downMatches);
     }

@@ -259,7 +259,7 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     if (!c || !c->n_targets) return fail(c, PJ_ESTATE, "pj_shard_begin: call pj_targets_set first");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->compute_stream));
-    c->n_rec = 0; c->n_cig = 0; c->n_seq = 0; c->have_result = false; c->n_junc = 0; c->n_pairs = 0;
+    c->n_rec = 0; c->n_cig = 0; c->n_seq = 16; c->have_result = false;   // SEQ stream: 16-byte lead pad (k_match may look back up to 15 nibbles) c->n_junc = 0; c->n_pairs = 0;
     cudaStream_t st = c->copy_stream;
     const size_t r = (size_t)std::max<int64_t>(n_records_hint, 1024);
     int rc;
@@ -267,9 +267,9 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
         (rc = ensure(c, c->mtid, r, 0, st)) || (rc = ensure(c, c->mpos, r, 0, st)) || (rc = ensure(c, c->flag, r, 0, st)) ||
         (rc = ensure(c, c->mapq, r, 0, st)) || (rc = ensure(c, c->xs, r, 0, st)) || (rc = ensure(c, c->cigar_off, r + 1, 0, st)) ||
         (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024), 0, st)) ||
-        (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 16, 0, st))) return rc;
+        (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 48, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
-    CU(c, cudaMemsetAsync(c->seq_off.p, 0, sizeof(uint64_t), st));
+    { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
     c->shard_open = true;
     return PJ_OK;
 }
