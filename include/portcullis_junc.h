@@ -18,8 +18,12 @@
  * boundary; every call returns 0 on success and a negative PJ_E* code on failure, with a message
  * available from pj_last_error().
  *
- * Threading: a pj_ctx is bound to ONE CUDA device and must be driven by one host thread at a
- * time.  Create one context per GPU (targets are independent, so shards need no exchange).
+ * Threading: a pj_ctx is bound to ONE CUDA device.  Create one context per GPU (targets are independent,
+ * so shards need no exchange).  Calls on one context must be serialised by the caller, with two exceptions
+ * that exist for the decode pipeline: pj_staging_acquire / pj_batch_submit are internally locked (decode
+ * workers may acquire and fill staging buffers concurrently while one thread submits them in BAM order), and
+ * pj_genome_set_target / pj_genome_load_fasta use their own stream and may run on a second host thread
+ * while batches are being staged and submitted.  pj_shard_run must not overlap any other call.
  */
 #ifndef PORTCULLIS_JUNC_H
 #define PORTCULLIS_JUNC_H
@@ -58,7 +62,9 @@ typedef struct pj_ctx pj_ctx;
 typedef struct pj_config {
     int32_t device;        /* CUDA device ordinal                                              */
     int32_t orientation;   /* PJ_ORIENT_*; only FR/RF/FF enable the portcullis proper-pair rule */
-    int32_t reserved[6];   /* [0]: lanes per (read, junction) pair in the match kernel, 0 = automatic (tuning knob) */
+    int32_t reserved[6];   /* tuning knobs, 0 = default. [0]: lanes per (read, junction) pair in the match kernel;
+                              [1]: 1 = multi-kernel radix sort instead of the one-sweep sort;
+                              [2]: number of pinned staging buffers pj_staging_acquire may create (default 4) */
 } pj_config;
 
 /*
@@ -196,10 +202,10 @@ int pj_genome_load_fasta(pj_ctx* ctx, const char* fasta_path, const char* fai_pa
 int pj_shard_begin(pj_ctx* ctx, int64_t n_records_hint, int64_t n_cigar_hint, int64_t n_seq_bytes_hint);
 
 /*
- * Double-buffered pinned staging: returns writable columnar buffers of at least the requested
- * capacities (the pointers in `out` are NON-const views of pinned host memory owned by the
- * context; n_records is set to 0).  Fill them, set n_records, then pj_batch_submit().
- * Acquiring blocks only while both staging slots are still in flight.
+ * Pinned staging pool: returns writable columnar buffers of at least the requested capacities (the pointers in
+ * `out` are NON-const views of pinned host memory owned by the context; n_records is set to 0).  Fill them, set
+ * n_records, then pj_batch_submit().  A buffer returns to the pool when its host-to-device copies have completed;
+ * acquiring blocks only while every buffer of the pool is in flight.
  */
 int pj_staging_acquire(pj_ctx* ctx, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out);
 

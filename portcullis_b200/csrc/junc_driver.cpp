@@ -45,16 +45,16 @@ struct PrepPaths {
 };
 bool present(const std::string& p) { std::error_code ec; return fs::exists(p, ec) || fs::is_symlink(fs::symlink_status(p, ec)); }
 
-// Decode `tasks` with `threads` workers; chunks reach `sink` strictly in task order.
-int decode_ordered(const BamFile& bam, const std::vector<DecodeTask>& tasks, int threads,
-                   const std::function<int(ColumnarChunk&)>& sink) {
-    const size_t n = tasks.size();
+// Ordered parallel pipeline: `produce(k)` runs on a pool of `threads` workers (out of order), `consume(k, payload)` runs
+// on the calling thread strictly in task order.  At most `window` tasks are produced-but-not-consumed at any time.
+template <typename Payload>
+int ordered_pipeline(size_t n, int threads, size_t window, const std::function<int(size_t, Payload&)>& produce,
+                     const std::function<int(size_t, Payload&)>& consume) {
     if (n == 0) return PJ_OK;
     threads = std::max(1, std::min<int>(threads, (int)n));
-    std::vector<std::unique_ptr<ColumnarChunk>> done(n);
+    std::vector<std::unique_ptr<Payload>> done(n);
     std::mutex mu; std::condition_variable cv;
     std::atomic<size_t> next{0}; size_t consumed = 0; bool failed = false; std::string fail_msg; int fail_code = PJ_OK;
-    const size_t window = (size_t)threads * 3 + 2;           // bound on decoded-but-unconsumed chunks
     auto worker = [&]() {
         for (;;) {
             size_t k = next.fetch_add(1);
@@ -64,27 +64,33 @@ int decode_ordered(const BamFile& bam, const std::vector<DecodeTask>& tasks, int
                 cv.wait(lk, [&] { return failed || k < consumed + window; });
                 if (failed) return;
             }
-            auto ch = std::make_unique<ColumnarChunk>();
-            try { bam.decode(tasks[k], *ch); }
-            catch (const pjio::DataError& e) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_code = PJ_EDATA; fail_msg = e.what(); } cv.notify_all(); return; }
-            catch (const std::exception& e) { std::lock_guard<std::mutex> lk(mu); if (!failed) { failed = true; fail_code = PJ_EIO; fail_msg = e.what(); } cv.notify_all(); return; }
-            { std::lock_guard<std::mutex> lk(mu); done[k] = std::move(ch); }
+            auto p = std::make_unique<Payload>();
+            int rc = PJ_OK; std::string msg;
+            try { rc = produce(k, *p); if (rc) msg = g_err; }
+            catch (const pjio::DataError& e) { rc = PJ_EDATA; msg = e.what(); }
+            catch (const std::exception& e) { rc = PJ_EIO; msg = e.what(); }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (rc) { if (!failed) { failed = true; fail_code = rc; fail_msg = msg; } }
+                else done[k] = std::move(p);
+            }
             cv.notify_all();
+            if (rc) return;
         }
     };
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++) pool.emplace_back(worker);
     int rc = PJ_OK;
     for (size_t k = 0; k < n; k++) {
-        std::unique_ptr<ColumnarChunk> ch;
+        std::unique_ptr<Payload> p;
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return failed || done[k]; });
             if (failed) { rc = fail(fail_code, fail_msg); break; }
-            ch = std::move(done[k]);
+            p = std::move(done[k]);
         }
-        rc = sink(*ch);
-        { std::lock_guard<std::mutex> lk(mu); consumed = k + 1; if (rc) { failed = true; } }
+        rc = consume(k, *p);
+        { std::lock_guard<std::mutex> lk(mu); consumed = k + 1; if (rc) failed = true; }
         cv.notify_all();
         if (rc) break;
     }
@@ -171,7 +177,9 @@ int pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out) {
     if (p->indexed) { for (int32_t t = (tid < 0 ? 0 : tid); t < (tid < 0 ? T : tid + 1); t++) p->bam.plan_target(t, 2u << 20, tasks); }
     else { DecodeTask w = p->bam.whole_file_task(); if (tid >= 0) { w.tid = tid; } tasks.push_back(w); }
     p->decoded.clear();
-    int rc = decode_ordered(p->bam, tasks, threads, [&](ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
+    int rc = ordered_pipeline<ColumnarChunk>(tasks.size(), threads, (size_t)threads * 3 + 2,
+        [&](size_t k, ColumnarChunk& c) { p->bam.decode(tasks[k], c); return PJ_OK; },
+        [&](size_t, ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
     if (rc) return rc;
     chunk_view(p->decoded, out);
     return PJ_OK;
@@ -273,53 +281,69 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     struct GpuOut { std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0; int rc = PJ_OK; std::string err; };
     std::vector<GpuOut> outs((size_t)n_gpus);
     const int threads_per_gpu = std::max(1, threads / n_gpus);
+    const size_t window_per_gpu = (size_t)threads_per_gpu + 2;          // staged-but-unsubmitted batches; staging slots = window + 2
     auto run_gpu = [&](int g) {
         GpuOut& out = outs[(size_t)g];
         auto bail = [&](int code, const std::string& m) { out.rc = code; out.err = m; };
         pj_config cfg; memset(&cfg, 0, sizeof cfg);
         cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
+        cfg.reserved[2] = (int32_t)window_per_gpu + 2;                     // pinned staging buffers
         pj_ctx* ctx = nullptr;
         int r = pj_create(&cfg, &ctx);
         if (r) return bail(r, pj_global_last_error());
         struct Guard { pj_ctx* c; ~Guard() { pj_destroy(c); } } guard{ctx};
         if ((r = pj_targets_set(ctx, T, H.lens.data()))) return bail(r, pj_last_error(ctx));
-        // genome: only this shard's targets become resident on this GPU
+        // genome: only this shard's targets become resident on this GPU.  The upload runs on its own host thread and CUDA
+        // stream, concurrently with the alignment decode below (pj_genome_* may overlap pj_staging_* / pj_batch_submit).
         double tg = now_s();
-        {
+        int genome_rc = PJ_OK; std::string genome_err;
+        std::thread genome_thread([&]() {
             std::string seq;
             for (int32_t t : shard[(size_t)g]) {
                 if (ttasks[t].empty() && prep->indexed) continue;          // no records -> no junctions -> no genome needed
                 const pjio::FaiEntry* e = prep->fasta.find(H.names[t]);
                 if (!e) continue;
-                try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { return bail(PJ_EIO, ex.what()); }
-                if ((r = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size()))) return bail(r, pj_last_error(ctx));
+                try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { genome_rc = PJ_EIO; genome_err = ex.what(); return; }
+                int q = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size());
+                if (q) { genome_rc = q; genome_err = pj_last_error(ctx); return; }
             }
-        }
-        out.genome_s = now_s() - tg;
-        // alignments
+            out.genome_s = now_s() - tg;
+        });
+        struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } join_guard{genome_thread};
+        // alignments: workers inflate + parse a task, then copy its columns into a pinned staging buffer; this thread
+        // submits the staged batches in BAM order (cudaMemcpyAsync on the copy stream)
         double td = now_s();
         std::vector<DecodeTask> tasks;
         uint64_t nrec_hint = 0;
         if (prep->indexed) for (int32_t t : shard[(size_t)g]) { tasks.insert(tasks.end(), ttasks[t].begin(), ttasks[t].end()); nrec_hint += weight[t]; }
         else tasks.push_back(prep->bam.whole_file_task());
-        if ((r = pj_shard_begin(ctx, (int64_t)nrec_hint + 1024, (int64_t)nrec_hint * 3 + 1024, (int64_t)nrec_hint * 48 + 1024))) return bail(r, pj_last_error(ctx));
-        r = decode_ordered(prep->bam, tasks, threads_per_gpu, [&](ColumnarChunk& ch) -> int {
-            if (ch.n() == 0) return PJ_OK;
-            pj_batch st;
-            int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
-            if (q) return fail(q, pj_last_error(ctx));
-            const size_t n = (size_t)ch.n();
-            memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
-            memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
-            memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
-            memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
-            memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
-            st.n_records = ch.n();
-            q = pj_batch_submit(ctx, &st);
-            return q ? fail(q, pj_last_error(ctx)) : PJ_OK;
-        });
+        if ((r = pj_shard_begin(ctx, (int64_t)nrec_hint + 1024, (int64_t)nrec_hint * 4 + 1024, (int64_t)nrec_hint * 56 + 1024))) return bail(r, pj_last_error(ctx));
+        r = ordered_pipeline<pj_batch>(tasks.size(), threads_per_gpu, window_per_gpu,
+            [&](size_t k, pj_batch& st) -> int {
+                ColumnarChunk ch;
+                prep->bam.decode(tasks[k], ch);
+                st.n_records = 0;
+                if (ch.n() == 0) return PJ_OK;
+                int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
+                if (q) return fail(q, pj_last_error(ctx));
+                const size_t n = (size_t)ch.n();
+                memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
+                memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
+                memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
+                memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
+                memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
+                st.n_records = ch.n();
+                return PJ_OK;
+            },
+            [&](size_t, pj_batch& st) -> int {
+                if (st.n_records == 0) return PJ_OK;
+                int q = pj_batch_submit(ctx, &st);
+                return q ? fail(q, pj_last_error(ctx)) : PJ_OK;
+            });
         if (r) return bail(r, g_err);
         out.decode_s = now_s() - td;
+        genome_thread.join();
+        if (genome_rc) return bail(genome_rc, genome_err);
         if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));
         const int64_t J = pj_shard_num_junctions(ctx);
         out.rows.resize((size_t)J); out.stats.resize((size_t)T);

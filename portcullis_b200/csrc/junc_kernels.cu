@@ -14,6 +14,7 @@
 #include "junc_kernels.cuh"
 #include "junc_launch.hpp"
 #include <cstdio>
+#include <algorithm>
 
 namespace pjk {
 
@@ -425,6 +426,148 @@ int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
         if (n_launches) *n_launches += 5;
         cur = 1;
     }
+    return cur;
+}
+
+// ================================================================================================
+// One-sweep radix sort: stable LSD, up to 10-bit digits, ONE kernel per digit.
+// A single upfront kernel builds the global digit histograms of every pass (the multiset of keys does not change between
+// passes).  Each pass then ranks a tile of 8192 keys in shared memory (warp-synchronous match_any ranking, stable) and
+// obtains the tile's base offsets with a decoupled look-back over per-tile status words, so keys are read once and
+// written once per pass and no separate histogram / scan launches are needed.  Tiles take their index from an atomic
+// ticket, which guarantees that every tile a block waits on has already started.
+// ================================================================================================
+constexpr int OS_THREADS = 512;
+constexpr int OS_ITEMS = 16;
+constexpr int OS_TILE = OS_THREADS * OS_ITEMS;       // 8192 keys per tile
+constexpr int OS_WARPS = OS_THREADS / 32;
+constexpr int OS_MAX_BITS = 10;
+constexpr int OS_MAX_BINS = 1 << OS_MAX_BITS;
+constexpr int OS_MAX_PASSES = 7;
+constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+
+struct OsPlan { int npass; int shift[OS_MAX_PASSES]; int bits[OS_MAX_PASSES]; };
+
+__global__ void __launch_bounds__(512) k_os_hist(const uint64_t* __restrict__ keys, uint32_t n, OsPlan plan, uint32_t* __restrict__ ghist /* [npass][1024] */) {
+    extern __shared__ uint32_t sh[];                 // [npass][1024]
+    for (int k = threadIdx.x; k < plan.npass * OS_MAX_BINS; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i];
+#pragma unroll 4
+        for (int p = 0; p < plan.npass; p++) atomicAdd(&sh[p * OS_MAX_BINS + ((uint32_t)(key >> plan.shift[p]) & ((1u << plan.bits[p]) - 1u))], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < plan.npass * OS_MAX_BINS; k += blockDim.x) { const uint32_t v = sh[k]; if (v) atomicAdd(&ghist[k], v); }
+}
+
+// exclusive scan of each pass's histogram in place (one block per pass, 1024 threads)
+__global__ void __launch_bounds__(1024) k_os_scan_hist(uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t tot;
+    uint32_t* h = ghist + (size_t)blockIdx.x * OS_MAX_BINS;
+    const uint32_t v = h[threadIdx.x];
+    const uint32_t ex = block_excl_scan(v, &tot);
+    h[threadIdx.x] = ex;
+}
+
+__global__ void __launch_bounds__(OS_THREADS, 2) k_os_pass(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in /* null: iota */,
+                                                         uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                         int shift, int bits, const uint32_t* __restrict__ gbase /* [1024] exclusive digit offsets */,
+                                                         uint32_t* __restrict__ status /* [ntiles][1024] */, uint32_t* __restrict__ ticket) {
+    __shared__ uint16_t wcnt[OS_WARPS][OS_MAX_BINS];
+    __shared__ uint32_t dbase[OS_MAX_BINS];
+    __shared__ uint32_t s_tile;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t nbins = 1u << bits, dmask = nbins - 1u;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int k = threadIdx.x; k < OS_WARPS * OS_MAX_BINS / 2; k += OS_THREADS) reinterpret_cast<uint32_t*>(&wcnt[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    // warp w owns keys [tile*8192 + w*512, +512), visited in rounds of 32 consecutive keys => stable
+    const uint32_t wbase = tile * OS_TILE + w * (OS_ITEMS * 32);
+    uint32_t dl[OS_ITEMS];                           // digit << 16 | rank of the key among equal digits of its warp
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; r++) {
+        const uint32_t i = wbase + r * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t d = ok ? ((uint32_t)(keys_in[i] >> shift) & dmask) : 0xffffu;   // padding lanes group together, never counted
+        const uint32_t m = __match_any_sync(FULL, d);
+        uint32_t prev = 0;
+        if (ok) prev = wcnt[w][d];
+        __syncwarp();
+        if (ok && (m & lt) == 0) wcnt[w][d] = (uint16_t)(prev + __popc(m));
+        __syncwarp();
+        dl[r] = (d << 16) | (prev + __popc(m & lt));
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over the warps, tile total, publish + look back
+    for (uint32_t d = threadIdx.x; d < nbins; d += OS_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int ww = 0; ww < OS_WARPS; ww++) { const uint32_t t = wcnt[ww][d]; wcnt[ww][d] = (uint16_t)run; run += t; }
+        volatile uint32_t* st = status + (size_t)tile * OS_MAX_BINS + d;
+        if (tile == 0) { *st = run | OS_FLAG_PREFIX; dbase[d] = gbase[d]; }
+        else {
+            *st = run | OS_FLAG_AGG;
+            __threadfence();
+            uint32_t excl = 0;
+            for (int32_t t = (int32_t)tile - 1; t >= 0; t--) {
+                volatile const uint32_t* sp = status + (size_t)t * OS_MAX_BINS + d;
+                uint32_t v;
+                do { v = *sp; } while ((v >> 30) == 0u);
+                excl += v & OS_VALUE_MASK;
+                if ((v >> 30) == 2u) break;
+            }
+            *st = ((excl + run) & OS_VALUE_MASK) | OS_FLAG_PREFIX;
+            dbase[d] = gbase[d] + excl;
+        }
+    }
+    __syncthreads();
+    // the tile (64 KB of keys) was just read: the second read below is served by L2, and not holding 16 keys in
+    // registers across the ranking doubles the resident warps
+#pragma unroll
+    for (int r = 0; r < OS_ITEMS; r++) {
+        const uint32_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = dl[r] >> 16;
+            const uint32_t dst = dbase[d] + wcnt[w][d] + (dl[r] & 0xffffu);
+            keys_out[dst] = keys_in[i];
+            vals_out[dst] = vals_in ? vals_in[i] : i;
+        }
+    }
+}
+
+uint32_t os_num_tiles(uint32_t n) { return (n + OS_TILE - 1) / OS_TILE; }
+// scratch: [npass][1024] histograms + [npass] tickets + [npass][ntiles][1024] status words
+size_t os_scratch_words(uint32_t n, int key_bits) {
+    const int npass = key_bits <= 0 ? 1 : (key_bits + OS_MAX_BITS - 1) / OS_MAX_BITS;
+    return (size_t)npass * OS_MAX_BINS + 64 + (size_t)npass * os_num_tiles(n) * OS_MAX_BINS;
+}
+
+// Sorts n (key,val) pairs on bits [0, key_bits), n < 2^30.  Returns 0 if the sorted data ends in the `a` buffers, 1 for `b`.
+int launch_onesweep_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
+                         uint32_t* scratch, int n_sm, cudaStream_t st, int* n_launches) {
+    if (n == 0) return 0;
+    OsPlan plan;
+    plan.npass = key_bits <= 0 ? 1 : (key_bits + OS_MAX_BITS - 1) / OS_MAX_BITS;
+    const int per = key_bits <= 0 ? 1 : (key_bits + plan.npass - 1) / plan.npass;
+    for (int p = 0, sh = 0; p < plan.npass; p++, sh += per) { plan.shift[p] = sh; plan.bits[p] = std::max(1, std::min(per, key_bits - sh)); }
+    const uint32_t ntiles = os_num_tiles(n);
+    uint32_t* ghist = scratch; uint32_t* tickets = scratch + (size_t)plan.npass * OS_MAX_BINS; uint32_t* status = tickets + 64;
+    cudaMemsetAsync(scratch, 0, os_scratch_words(n, key_bits) * sizeof(uint32_t), st);
+    const int hist_blocks = (int)std::min<uint64_t>((uint64_t)n_sm * 4, ((uint64_t)n + 511) / 512);
+    k_os_hist<<<hist_blocks, 512, (size_t)plan.npass * OS_MAX_BINS * sizeof(uint32_t), st>>>(keys_a, n, plan, ghist);
+    k_os_scan_hist<<<plan.npass, 1024, 0, st>>>(ghist);
+    int cur = 0;
+    for (int p = 0; p < plan.npass; p++) {
+        const uint64_t* kin = cur ? keys_b : keys_a; const uint32_t* vin = cur ? vals_b : vals_a;
+        uint64_t* kout = cur ? keys_a : keys_b; uint32_t* vout = cur ? vals_a : vals_b;
+        k_os_pass<<<ntiles, OS_THREADS, 0, st>>>(kin, p == 0 ? nullptr : vin, kout, vout, n, plan.shift[p], plan.bits[p],
+                                                 ghist + (size_t)p * OS_MAX_BINS, status + (size_t)p * ntiles * OS_MAX_BINS, tickets + p);
+        cur ^= 1;
+    }
+    if (n_launches) *n_launches += 2 + plan.npass;
     return cur;
 }
 

@@ -33,6 +33,9 @@ void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff
 uint32_t rs_num_blocks(uint32_t n);
 int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
                       uint32_t* counts, uint32_t* scan_tmp, uint32_t* total_tmp, cudaStream_t st, int* n_launches);
+size_t os_scratch_words(uint32_t n, int key_bits);
+int launch_onesweep_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
+                         uint32_t* scratch, int n_sm, cudaStream_t st, int* n_launches);
 void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st);
 void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint32_t* jid, uint32_t* seg_start, uint32_t n_junc, cudaStream_t st);
 void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairA* pa, const PairB* pb,

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include <climits>
+#include <mutex>
 
 using namespace pjk;
 
@@ -23,12 +24,15 @@ template <typename T> struct DevBuf {
 };
 
 struct StagingSlot {
-    // pinned host columns
+    // one pinned host block carved into the columns of a pj_batch
+    uint8_t* block = nullptr; size_t block_bytes = 0;
     int32_t *tid = nullptr, *pos = nullptr, *l_qseq = nullptr, *mtid = nullptr, *mpos = nullptr;
     uint16_t* flag = nullptr; uint8_t *mapq = nullptr, *xs = nullptr;
     uint32_t *cigar_off = nullptr, *cigar = nullptr; uint64_t* seq_off = nullptr; uint8_t* seq4 = nullptr;
     int64_t cap_rec = 0, cap_cig = 0, cap_seq = 0;
-    cudaEvent_t done = nullptr; bool in_flight = false;
+    cudaEvent_t done = nullptr;
+    int state = 0;                         // 0 free, 1 handed out (being filled / waiting for submit), 2 copy in flight
+    uint64_t seq_no = 0;                   // submit order, to find the oldest in-flight slot
 };
 
 struct StageTime { const char* name; cudaEvent_t ev; };
@@ -36,7 +40,7 @@ struct StageTime { const char* name; cudaEvent_t ev; };
 } // namespace
 
 struct pj_ctx {
-    int device = 0; int orientation = PJ_ORIENT_UNKNOWN; int match_group = 0; int n_sm = 148;
+    int device = 0; int orientation = PJ_ORIENT_UNKNOWN; int match_group = 0; int n_sm = 148; int legacy_sort = 0;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     std::string err;
     // targets / genome
@@ -53,7 +57,9 @@ struct pj_ctx {
     int64_t n_rec = 0; uint64_t n_cig = 0, n_seq = 0;
     DevBuf<int32_t> tid, pos, l_qseq, mtid, mpos; DevBuf<uint16_t> flag; DevBuf<uint8_t> mapq, xs, seq4;
     DevBuf<uint32_t> cigar_off, cigar; DevBuf<uint64_t> seq_off;
-    StagingSlot slot[2]; int next_slot = 0;
+    std::vector<StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
+    std::mutex staging_mu;              // pj_staging_acquire / pj_batch_submit may be called from several host threads
+    cudaStream_t genome_stream = nullptr;
     cudaEvent_t copies_done = nullptr;
     // per-target accumulators + misc device scalars
     unsigned long long *d_spliced = nullptr, *d_unspliced = nullptr, *d_sumq = nullptr; int32_t *d_minq = nullptr, *d_maxq = nullptr;
@@ -90,22 +96,27 @@ template <typename T> int ensure(pj_ctx* c, DevBuf<T>& b, size_t need, size_t ke
 }
 
 void free_slot(StagingSlot& s) {
-    cudaFreeHost(s.tid); cudaFreeHost(s.pos); cudaFreeHost(s.l_qseq); cudaFreeHost(s.mtid); cudaFreeHost(s.mpos);
-    cudaFreeHost(s.flag); cudaFreeHost(s.mapq); cudaFreeHost(s.xs); cudaFreeHost(s.cigar_off); cudaFreeHost(s.cigar);
-    cudaFreeHost(s.seq_off); cudaFreeHost(s.seq4);
+    if (s.block) cudaFreeHost(s.block);
+    s.block = nullptr; s.block_bytes = 0;
     s.tid = s.pos = s.l_qseq = s.mtid = s.mpos = nullptr; s.flag = nullptr; s.mapq = s.xs = s.seq4 = nullptr;
     s.cigar_off = s.cigar = nullptr; s.seq_off = nullptr; s.cap_rec = s.cap_cig = s.cap_seq = 0;
 }
 
-template <typename T> cudaError_t pin(T** p, size_t n) { return cudaMallocHost((void**)p, std::max<size_t>(n, 1) * sizeof(T)); }
-
 int alloc_slot(pj_ctx* c, StagingSlot& s, int64_t cr, int64_t cc, int64_t cs) {
-    if (cr <= s.cap_rec && cc <= s.cap_cig && cs <= s.cap_seq && s.tid) return PJ_OK;
-    cr = std::max(cr, s.cap_rec); cc = std::max(cc, s.cap_cig); cs = std::max(cs, s.cap_seq);
+    if (cr <= s.cap_rec && cc <= s.cap_cig && cs <= s.cap_seq && s.block) return PJ_OK;
+    cr = std::max(cr + cr / 8, s.cap_rec); cc = std::max(cc + cc / 8, s.cap_cig); cs = std::max(cs + cs / 8, s.cap_seq);
     free_slot(s);
-    CU(c, pin(&s.tid, cr)); CU(c, pin(&s.pos, cr)); CU(c, pin(&s.l_qseq, cr)); CU(c, pin(&s.mtid, cr)); CU(c, pin(&s.mpos, cr));
-    CU(c, pin(&s.flag, cr)); CU(c, pin(&s.mapq, cr)); CU(c, pin(&s.xs, cr));
-    CU(c, pin(&s.cigar_off, cr + 1)); CU(c, pin(&s.cigar, cc)); CU(c, pin(&s.seq_off, cr + 1)); CU(c, pin(&s.seq4, cs));
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t r = (size_t)cr;
+    const size_t sz[12] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r),
+                           up((r + 1) * 4), up((size_t)cc * 4), up((r + 1) * 8), up((size_t)cs + 16)};
+    size_t total = 0; for (size_t v : sz) total += v;
+    CU(c, cudaMallocHost((void**)&s.block, total));
+    s.block_bytes = total;
+    uint8_t* p = s.block; size_t k = 0;
+    s.tid = (int32_t*)p; p += sz[k++]; s.pos = (int32_t*)p; p += sz[k++]; s.l_qseq = (int32_t*)p; p += sz[k++]; s.mtid = (int32_t*)p; p += sz[k++];
+    s.mpos = (int32_t*)p; p += sz[k++]; s.flag = (uint16_t*)p; p += sz[k++]; s.mapq = p; p += sz[k++]; s.xs = p; p += sz[k++];
+    s.cigar_off = (uint32_t*)p; p += sz[k++]; s.cigar = (uint32_t*)p; p += sz[k++]; s.seq_off = (uint64_t*)p; p += sz[k++]; s.seq4 = p;
     s.cap_rec = cr; s.cap_cig = cc; s.cap_seq = cs;
     s.cigar_off[0] = 0; s.seq_off[0] = 0;
     return PJ_OK;
@@ -123,7 +134,7 @@ void mark(pj_ctx* c, const char* name) {
 // sort + upload the "other exception byte" table after genome uploads
 int finish_genome(pj_ctx* c) {
     if (!c->genome_dirty) return PJ_OK;
-    CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, cudaStreamSynchronize(c->genome_stream));
     uint32_t cnt = 0;
     CU(c, cudaMemcpy(&cnt, c->d_exc_count, sizeof cnt, cudaMemcpyDeviceToHost));
     if (cnt > c->exc_cap)
@@ -169,12 +180,16 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
     c->device = cfg->device; c->orientation = cfg->orientation;
     c->match_group = cfg->reserved[0];                 // 0 = choose from the data; 1..32 forces the lanes-per-pair of k_match (tuning / tests)
     if (const char* e = getenv("PJ_MATCH_GROUP")) c->match_group = atoi(e);
+    c->legacy_sort = cfg->reserved[1];                 // 1 = multi-kernel histogram/scan/scatter sort (kept for > 2^30 pairs and as a cross-check)
+    if (const char* e = getenv("PJ_LEGACY_SORT")) c->legacy_sort = atoi(e);
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
     CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
     CU(c, cudaEventCreateWithFlags(&c->copies_done, cudaEventDisableTiming));
-    for (int s = 0; s < 2; s++) { CU(c, cudaEventCreateWithFlags(&c->slot[s].done, cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&c->graw_ev[s], cudaEventDisableTiming)); }
+    CU(c, cudaStreamCreateWithFlags(&c->genome_stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; s++) CU(c, cudaEventCreateWithFlags(&c->graw_ev[s], cudaEventDisableTiming));
+    c->max_slots = cfg->reserved[2] > 0 ? std::max(2, cfg->reserved[2]) : 4;
     CU(c, cudaMalloc(&c->d_scalars, 16 * sizeof(uint32_t)));
     CU(c, cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(uint32_t)));
     // keep stream-ordered allocations cached between shards
@@ -190,7 +205,9 @@ void pj_destroy(pj_ctx* c) {
     cudaDeviceSynchronize();
     c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
     c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_();
-    for (int s = 0; s < 2; s++) { free_slot(c->slot[s]); if (c->slot[s].done) cudaEventDestroy(c->slot[s].done); if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
+    for (StagingSlot* sl : c->slots) { free_slot(*sl); if (sl->done) cudaEventDestroy(sl->done); delete sl; }
+    if (c->genome_stream) cudaStreamDestroy(c->genome_stream);
+    for (int s = 0; s < 2; s++) { if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
                                   if (c->h_graw[s]) cudaFreeHost(c->h_graw[s]); if (c->d_graw[s]) cudaFree(c->d_graw[s]); }
     cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx); cudaFree(c->d_g4);
     cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
@@ -244,12 +261,12 @@ int pj_genome_set_target(pj_ctx* c, int32_t tid, const char* bases, int64_t n_ba
         const int64_t k = std::min<int64_t>((int64_t)pj_ctx::GRAW_CHUNK, n - o);
         CU(c, cudaEventSynchronize(c->graw_ev[s]));                  // slot free again?
         memcpy(c->h_graw[s], bases + o, (size_t)k);
-        CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->copy_stream));
-        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_g4, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->copy_stream);
-        CU(c, cudaEventRecord(c->graw_ev[s], c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->genome_stream));
+        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_g4, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->genome_stream);
+        CU(c, cudaEventRecord(c->graw_ev[s], c->genome_stream));
     }
     c->h_glen[tid] = n_bases < c->h_tlen[tid] ? n_bases : (int64_t)c->h_tlen[tid];
-    CU(c, cudaMemcpyAsync(c->d_glen + tid, &c->h_glen[tid], sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaMemcpyAsync(c->d_glen + tid, &c->h_glen[tid], sizeof(int64_t), cudaMemcpyHostToDevice, c->genome_stream));
     CU(c, cudaGetLastError());
     c->genome_dirty = true;
     return PJ_OK;
@@ -277,11 +294,31 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
 int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out) {
     if (!c || !out || cap_records < 0 || cap_cigar < 0 || cap_seq_bytes < 0) return fail(c, PJ_EINVAL, "pj_staging_acquire: bad arguments");
     CU(c, cudaSetDevice(c->device));
-    StagingSlot& s = c->slot[c->next_slot];
-    if (s.in_flight) { CU(c, cudaEventSynchronize(s.done)); s.in_flight = false; }
-    int rc = alloc_slot(c, s, std::max<int64_t>(cap_records, 1), std::max<int64_t>(cap_cigar, 1), std::max<int64_t>(cap_seq_bytes, 1));
+    std::lock_guard<std::mutex> lk(c->staging_mu);
+    StagingSlot* pick = nullptr;
+    for (;;) {
+        StagingSlot* oldest = nullptr;
+        for (StagingSlot* sl : c->slots) {
+            if (sl->state == 2 && cudaEventQuery(sl->done) == cudaSuccess) sl->state = 0;
+            if (sl->state == 0 && (!pick || sl->cap_seq > pick->cap_seq)) pick = sl;      // prefer the roomiest free slot
+            if (sl->state == 2 && (!oldest || sl->seq_no < oldest->seq_no)) oldest = sl;
+        }
+        if (pick) break;
+        if ((int)c->slots.size() < c->max_slots) {
+            pick = new StagingSlot();
+            cudaError_t e = cudaEventCreateWithFlags(&pick->done, cudaEventDisableTiming);
+            if (e != cudaSuccess) { delete pick; return fail(c, PJ_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(e)); }
+            c->slots.push_back(pick);
+            break;
+        }
+        if (!oldest) return fail(c, PJ_ESTATE, "pj_staging_acquire: all %d staging buffers are handed out and none was submitted", c->max_slots);
+        CU(c, cudaEventSynchronize(oldest->done));
+        oldest->state = 0;
+    }
+    int rc = alloc_slot(c, *pick, std::max<int64_t>(cap_records, 1), std::max<int64_t>(cap_cigar, 1), std::max<int64_t>(cap_seq_bytes, 1));
     if (rc) return rc;
-    c->next_slot ^= 1;
+    pick->state = 1;
+    StagingSlot& s = *pick;
     out->n_records = 0; out->tid = s.tid; out->pos = s.pos; out->flag = s.flag; out->mapq = s.mapq; out->xs = s.xs; out->l_qseq = s.l_qseq;
     out->mtid = s.mtid; out->mpos = s.mpos; out->cigar_off = s.cigar_off; out->cigar = s.cigar; out->seq_off = s.seq_off; out->seq4 = s.seq4;
     return PJ_OK;
@@ -322,7 +359,10 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
     launch_rebase_u32(c->cigar_off.p + R + 1, n, (uint32_t)c->n_cig - cb, st);
     launch_rebase_u64(c->seq_off.p + R + 1, n, c->n_seq - sb, st);
     CU(c, cudaGetLastError());
-    for (int s = 0; s < 2; s++) if (b->tid == c->slot[s].tid) { CU(c, cudaEventRecord(c->slot[s].done, st)); c->slot[s].in_flight = true; }
+    {
+        std::lock_guard<std::mutex> lk(c->staging_mu);
+        for (StagingSlot* sl : c->slots) if (b->tid == sl->tid) { CU(c, cudaEventRecord(sl->done, st)); sl->state = 2; sl->seq_no = ++c->submit_seq; }
+    }
     c->n_rec += n; c->n_cig += ncig; c->n_seq += nseq;
     return PJ_OK;
 }
@@ -379,7 +419,15 @@ int pj_shard_run(pj_ctx* c) {
         CU(c, cudaMallocAsync(&pa, (size_t)P * sizeof(PairA), st)); CU(c, cudaMallocAsync(&pb, (size_t)P * sizeof(PairB), st));
         launch_emit_pairs(Rd, c->d_tlen, c->d_toff, len_bits, c->orientation, pair_off, npairs, read_end, keys_a, pa, pb, d_err, st); c->n_launches++;
         mark(c, "emit_pairs");
-        const int which = launch_radix_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, counts, scan_tmp2, d_tmp_total, st, &c->n_launches);
+        int which;
+        if (P < (1u << 30) && !c->legacy_sort) {
+            uint32_t* os_scratch = nullptr;
+            CU(c, cudaMallocAsync(&os_scratch, os_scratch_words(P, key_bits) * sizeof(uint32_t), st));
+            which = launch_onesweep_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, os_scratch, c->n_sm, st, &c->n_launches);
+            CU(c, cudaFreeAsync(os_scratch, st));
+        } else {
+            which = launch_radix_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, counts, scan_tmp2, d_tmp_total, st, &c->n_launches);
+        }
         const uint64_t* keys = which ? keys_b : keys_a; const uint32_t* vals = which ? vals_b : vals_a;
         uint32_t* spare_u32 = which ? vals_a : vals_b;        // free again: reused for the head flags / entropy flags
         mark(c, "radix_sort");

@@ -67,11 +67,12 @@ class PrepDir:
 class JuncGpu:
     """One GPU context of the C ABI (pj_ctx)."""
 
-    def __init__(self, device=0, orientation="UNKNOWN", match_group=0):
+    def __init__(self, device=0, orientation="UNKNOWN", match_group=0, legacy_sort=0):
         self._lib = L.load()
         cfg = L.PjConfig()
         cfg.device = device
         cfg.reserved[0] = match_group        # lanes per (read, junction) pair in k_match; 0 = chosen from the data
+        cfg.reserved[1] = legacy_sort        # 1 = multi-kernel radix sort instead of the one-sweep sort
         cfg.orientation = L.ORIENT[orientation] if isinstance(orientation, str) else int(orientation)
         self._ctx = C.c_void_p()
         _check(self._lib.pj_create(C.byref(cfg), C.byref(self._ctx)), self._lib.pj_global_last_error)

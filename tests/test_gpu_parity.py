@@ -16,8 +16,8 @@ from portcullis_b200 import junction_builder as jb
 pytestmark = pytest.mark.gpu
 
 
-def gpu_run(cols, lengths, genomes, orientation="UNKNOWN", n_batches=1, pinned=False, device=0, match_group=0):
-    g = jb.JuncGpu(device, orientation, match_group)
+def gpu_run(cols, lengths, genomes, orientation="UNKNOWN", n_batches=1, pinned=False, device=0, match_group=0, legacy_sort=0):
+    g = jb.JuncGpu(device, orientation, match_group, legacy_sort)
     try:
         g.set_targets(lengths)
         for t, s in enumerate(genomes):
@@ -154,3 +154,13 @@ def test_match_kernel_group_widths(group):
                      (202, dict(long_reads=True, read_len=(300, 2500), genes_per_target=5, target_len=50000, paired=False, sub_rate=0.03))):
         ds = synth.make_dataset(seed, **kw)
         check_against_oracle(synth.to_columns(ds), ds["lengths"], ds["genomes"], match_group=group)
+
+
+def test_both_sort_implementations_agree():
+    """The one-sweep sort (default) and the multi-kernel histogram/scan/scatter sort give identical rows."""
+    ds = synth.make_dataset(301, n_targets=3, target_len=30000, genes_per_target=10, hot=30000)
+    cols = synth.to_columns(ds)
+    a, _, _ = gpu_run(cols, ds["lengths"], ds["genomes"])
+    b, _, _ = gpu_run(cols, ds["lengths"], ds["genomes"], legacy_sort=1)
+    assert a.tobytes() == b.tobytes()
+    check_against_oracle(cols, ds["lengths"], ds["genomes"], legacy_sort=1)
