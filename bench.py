@@ -94,10 +94,12 @@ def algorithmic_bytes(cols, n_pairs, n_junc):
     n_rec = len(cols["pos"])
     n_cig = len(cols["cigar"])
     seq_bytes = len(cols["seq4"])                    # 4-bit SEQ of spliced records only
+    # CIGAR words of spliced records (the only ones the per-pair kernels touch)
+    has_seq = np.diff(cols["seq_off"].astype(np.int64)) > 0
+    n_cig_spliced = int(np.diff(cols["cigar_off"].astype(np.int64))[has_seq].sum())
     fixed = 32 * n_rec + 4 * n_cig + seq_bytes
     pair = 48 * n_pairs                               # 8-B key + 16-B payload, written once and read once
-    # anchor bases ~ read bases of spliced records (short reads): 2-bit genome window
-    genome = seq_bytes // 2
+    genome = seq_bytes // 2                           # SURVEY: 2-bit genome window of the anchor bases
     rows = 326 * n_junc
     total = fixed + pair + genome + rows
     per_stage = {
@@ -109,7 +111,9 @@ def algorithmic_bytes(cols, n_pairs, n_junc):
         "segments": (8 + 4 + 4) * n_pairs,
         "reduce1": (4 + 4 + 32) * n_pairs + 4 * n_pairs,
         "entropy": 12 * n_pairs + 8 * n_junc,
-        "match": (4 + 4 + 32 + 16) * n_pairs + 4 * n_cig + seq_bytes + genome * 3 // 2,
+        # k_match: vals + jid + PairA/B + result per pair; CIGAR and SEQ of the read; the same number of genome bases
+        # from the 4-bit plane (SEQ and genome windows have equal length)
+        "match": (4 + 4 + 32 + 16) * n_pairs + 4 * n_cig_spliced + seq_bytes + seq_bytes,
         "reduce2": (4 + 16) * n_pairs,
         "finalize": (256 + 100 + 84) * n_junc,
     }
