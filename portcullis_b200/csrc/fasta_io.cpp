@@ -28,20 +28,24 @@ const FaiEntry* FastaFile::find(const std::string& name) const {
     return it == by_name_.end() ? nullptr : &entries_[it->second];
 }
 
+// true when every byte of [p, p+n) is printable non-space (isgraph in the C locale); written so that it vectorises
+static inline bool all_graph(const uint8_t* p, size_t n) {
+    unsigned bad = 0;
+    for (size_t k = 0; k < n; k++) bad |= (unsigned)((uint8_t)(p[k] - 33u) > 93u);
+    return bad == 0;
+}
+
 void FastaFile::fetch_all(const FaiEntry& e, std::string& out) const {
     out.clear(); out.resize((size_t)e.len);
     const uint8_t* p = file_.data(); uint64_t n = file_.size(), o = e.offset; size_t l = 0;
-    // Fast path: copy line_blen bytes per line, then verify they are all printable; fall back to the
-    // byte loop of faidx.c:470-472 when a line is irregular.
+    const size_t blen = (size_t)(e.line_blen > 0 ? e.line_blen : 1);
+    const uint64_t term = (uint64_t)(e.line_len > e.line_blen ? e.line_len - e.line_blen : 0);
+    // Fast path: whole lines of line_blen printable bytes followed by the terminator; anything irregular falls back to
+    // the byte loop of faidx.c:470-472 (keep isgraph bytes, stop after e.len of them).
     while (l < (size_t)e.len && o < n) {
-        size_t want = std::min<size_t>((size_t)e.len - l, (size_t)(e.line_blen > 0 ? e.line_blen : 1));
-        size_t avail = (size_t)std::min<uint64_t>(want, n - o);
-        bool clean = true;
-        for (size_t k = 0; k < avail; k++) if (!isgraph(p[o + k])) { clean = false; break; }
-        if (clean && avail == want) {
+        const size_t want = std::min<size_t>((size_t)e.len - l, blen);
+        if (o + want + term <= n && all_graph(p + o, want) && (want < blen || (term > 0 && !isgraph(p[o + want])))) {
             memcpy(&out[l], p + o, want); l += want; o += want;
-            // skip the line terminator(s)
-            uint64_t term = (uint64_t)(e.line_len - e.line_blen);
             for (uint64_t k = 0; k < term && o < n && !isgraph(p[o]); k++) o++;
         } else {
             while (l < (size_t)e.len && o < n) { uint8_t c = p[o++]; if (isgraph(c)) out[l++] = (char)c; if (c == '\n') break; }

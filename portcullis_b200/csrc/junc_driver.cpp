@@ -205,10 +205,16 @@ int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_
         const std::string pre(output_prefix), src(source ? source : "portcullis"), ver(version ? version : "");
         fs::path parent = fs::path(pre).parent_path();
         if (!parent.empty()) { std::error_code ec; fs::create_directories(parent, ec); }
-        pjhost::write_tab(pre + ".junctions.tab", rows, n_rows, t);
-        if (exon_gff) pjhost::write_exon_gff(pre + ".junctions.exon.gff3", rows, n_rows, t, src);
-        if (intron_gff) pjhost::write_intron_gff(pre + ".junctions.intron.gff3", rows, n_rows, t, src);
-        pjhost::write_bed(pre + ".junctions.bed", rows, n_rows, t, src, ver);
+        // the files are independent: write them concurrently (each writer also formats its rows on a few threads)
+        std::string werr; std::mutex wmu;
+        auto guarded = [&](const std::function<void()>& f) { try { f(); } catch (const std::exception& e) { std::lock_guard<std::mutex> lk(wmu); werr = e.what(); } };
+        std::vector<std::thread> wt;
+        wt.emplace_back([&]() { guarded([&]() { pjhost::write_bed(pre + ".junctions.bed", rows, n_rows, t, src, ver); }); });
+        if (exon_gff) wt.emplace_back([&]() { guarded([&]() { pjhost::write_exon_gff(pre + ".junctions.exon.gff3", rows, n_rows, t, src); }); });
+        if (intron_gff) wt.emplace_back([&]() { guarded([&]() { pjhost::write_intron_gff(pre + ".junctions.intron.gff3", rows, n_rows, t, src); }); });
+        guarded([&]() { pjhost::write_tab(pre + ".junctions.tab", rows, n_rows, t); });
+        for (auto& x : wt) x.join();
+        if (!werr.empty()) return fail(PJ_EIO, werr);
     } catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
     return PJ_OK;
 }

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
+#include <vector>
 
 // ------------------------------------------------------------------------------------------------
 // A12/A13.  Reference: JunctionBuilder::findJunctions tail (src/junction_builder.cc:270-290),
@@ -90,8 +92,10 @@ public:
         if (!f_) throw std::runtime_error("cannot open " + path + " for writing");
         buf_.reserve(1 << 22);
     }
+    Out() : f_(nullptr) {}                                   // in-memory: rows formatted by a worker thread
     ~Out() { if (f_) { flush(); fclose(f_); } }
-    void s(const char* p, size_t n) { buf_.append(p, n); if (buf_.size() > (1u << 22) - 4096) flush(); }
+    const std::string& str() const { return buf_; }
+    void s(const char* p, size_t n) { buf_.append(p, n); if (f_ && buf_.size() > (1u << 22) - 4096) flush(); }
     void s(const char* p) { s(p, strlen(p)); }
     void s(const std::string& v) { s(v.data(), v.size()); }
     void c(char ch) { buf_.push_back(ch); }
@@ -99,10 +103,22 @@ public:
     void i(int64_t v) { if (v < 0) { c('-'); u((uint64_t)(-(v + 1)) + 1); } else u((uint64_t)v); }
     void g(double v, int prec = 6) { char t[48]; int k = snprintf(t, sizeof t, "%.*g", prec, v); s(t, (size_t)k); }
     void f3(double v) { char t[48]; int k = snprintf(t, sizeof t, "%.3f", v); s(t, (size_t)k); }
-    void flush() { if (!buf_.empty()) { fwrite(buf_.data(), 1, buf_.size(), f_); buf_.clear(); } }
+    void flush() { if (f_ && !buf_.empty()) { fwrite(buf_.data(), 1, buf_.size(), f_); buf_.clear(); } }
 private:
     FILE* f_; std::string buf_;
 };
+
+// Formats rows [0, n) with `fmt(out, r)` on a few threads and appends the pieces to `o` in row order.
+template <typename F>
+void format_rows_parallel(Out& o, int64_t n, F fmt) {
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, (int64_t)std::thread::hardware_concurrency()), n / 1024));
+    if (nt <= 1) { for (int64_t r = 0; r < n; r++) fmt(o, r); return; }
+    std::vector<Out> parts((size_t)nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&, t]() { const int64_t a = n * t / nt, b = n * (t + 1) / nt; for (int64_t r = a; r < b; r++) fmt(parts[(size_t)t], r); });
+    for (auto& x : th) x.join();
+    for (auto& p : parts) o.s(p.str());
+}
 
 inline char strand_char(uint8_t s) { return s == PJ_STRAND_POS ? '+' : s == PJ_STRAND_NEG ? '-' : '?'; }
 inline const char* strand_name(uint8_t s) { return s == PJ_STRAND_POS ? "POSITIVE" : s == PJ_STRAND_NEG ? "NEGATIVE" : "UNKNOWN"; }
@@ -132,9 +148,10 @@ std::string tab_header() {
 void write_tab(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets) {
     Out o(path);
     o.s(tab_header()); o.c('\n');
-    for (int64_t r = 0; r < n; r++) {
+    for (int64_t r = 0; r < n; r++) target_of(targets, rows[r].tid);          // validate before going parallel
+    format_rows_parallel(o, n, [&](Out& o, int64_t r) {
         const pj_junction& j = rows[r];
-        const TargetInfo& t = target_of(targets, j.tid);
+        const TargetInfo& t = targets[(size_t)j.tid];
         o.u(j.index); o.c('\t'); o.i(j.tid); o.c('\t'); o.s(t.name); o.c('\t'); o.i(t.length); o.c('\t');
         o.i(j.start); o.c('\t'); o.i(j.end); o.c('\t'); o.u((uint32_t)(j.end - j.start + 1)); o.c('\t');
         o.i(j.left); o.c('\t'); o.i(j.right); o.c('\t');
@@ -159,7 +176,7 @@ void write_tab(const std::string& path, const pj_junction* rows, int64_t n, cons
         o.s("0\t0\t0\t0\t1");                                          // mm_score, coverage, up_aln, down_aln, nb_samples
         for (int k = 0; k < PJ_NB_JAD; k++) { o.c('\t'); o.u(j.jad[k]); }
         o.c('\n');
-    }
+    });
     o.c('\n');        // `strm << js << endl` leaves one blank line at EOF (junction_system.cc:356)
 }
 
@@ -167,9 +184,10 @@ void write_bed(const std::string& path, const pj_junction* rows, int64_t n, cons
                const std::string& source, const std::string& version) {
     Out o(path);
     o.s("track name=\"junctions\" description=\"Portcullis V"); o.s(version.empty() ? std::string("X.X.X") : version); o.s(" junctions\"\n");
-    for (int64_t r = 0; r < n; r++) {
+    for (int64_t r = 0; r < n; r++) target_of(targets, rows[r].tid);
+    format_rows_parallel(o, n, [&](Out& o, int64_t r) {
         const pj_junction& j = rows[r];
-        const TargetInfo& t = target_of(targets, j.tid);
+        const TargetInfo& t = targets[(size_t)j.tid];
         o.s(t.name); o.c('\t'); o.i(j.left); o.c('\t'); o.i((int64_t)j.right + 1); o.c('\t');
         o.s(source); o.c('_'); o.u(j.index); o.c('\t');
         o.f3((double)j.nb_raw_aln); o.c('\t');                       // the ?: makes the score a double under std::fixed, precision 3
@@ -178,15 +196,16 @@ void write_bed(const std::string& path, const pj_junction* rows, int64_t n, cons
         o.s("255,0,0\t2\t");
         o.i(j.start - j.left); o.c(','); o.i(j.right - j.end); o.c('\t');
         o.s("0,"); o.i(j.end - j.left + 1); o.c('\n');
-    }
+    });
 }
 
 void write_exon_gff(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
                     const std::string& source) {
     Out o(path);
-    for (int64_t r = 0; r < n; r++) {
+    for (int64_t r = 0; r < n; r++) target_of(targets, rows[r].tid);
+    format_rows_parallel(o, n, [&](Out& o, int64_t r) {
         const pj_junction& j = rows[r];
-        const TargetInfo& t = target_of(targets, j.tid);
+        const TargetInfo& t = targets[(size_t)j.tid];
         const char strand = strand_char(j.consensus_strand);          // '?' when unknown
         auto lead = [&](const char* type, int64_t b, int64_t e) {
             o.s(t.name); o.c('\t'); o.s(source); o.c('\t'); o.s(type); o.c('\t'); o.i(b); o.c('\t'); o.i(e);
@@ -209,19 +228,20 @@ void write_exon_gff(const std::string& path, const pj_junction* rows, int64_t n,
         o.s("ID=junc_"); o.u(j.index); o.s("_left;Parent=junc_"); o.u(j.index); o.c('\n');
         lead("match_part", (int64_t)j.end + 2, (int64_t)j.right + 1);
         o.s("ID=junc_"); o.u(j.index); o.s("_right;Parent=junc_"); o.u(j.index); o.c('\n');
-    }
+    });
 }
 
 void write_intron_gff(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
                       const std::string& source) {
     Out o(path);
-    for (int64_t r = 0; r < n; r++) {
+    for (int64_t r = 0; r < n; r++) target_of(targets, rows[r].tid);
+    format_rows_parallel(o, n, [&](Out& o, int64_t r) {
         const pj_junction& j = rows[r];
-        const TargetInfo& t = target_of(targets, j.tid);
+        const TargetInfo& t = targets[(size_t)j.tid];
         o.s(t.name); o.c('\t'); o.s(source); o.s("\tintron\t"); o.i((int64_t)j.start + 1); o.c('\t'); o.i((int64_t)j.end + 1); o.c('\t');
         o.u(j.nb_raw_aln); o.c('\t'); o.c(strand_char(j.consensus_strand)); o.s("\t.\tmult="); o.u(j.nb_raw_aln);
         o.s(";grp=junc_"); o.u(j.index); o.s(";src=E\n");
-    }
+    });
 }
 
 } // namespace pjhost

@@ -300,19 +300,23 @@ __global__ void __launch_bounds__(256) k_emit_pairs(Reads R, const int32_t* __re
                 if (op_ref(cig_op(w2))) rEndExc += cig_len(w2);
                 j++;
             }
-            if (rStart - 1 >= refLen) rStart = refLen - 1;
-            if (rEndExc - 1 >= refLen) rEndExc = refLen;
+            bool clamped = false;
+            if (rStart - 1 >= refLen) { rStart = refLen - 1; clamped = true; }
+            if (rEndExc - 1 >= refLen) { rEndExc = refLen; clamped = true; }
             const int32_t start = lEndExc, end = rStart - 1, rend = rEndExc - 1;
             if (lStart > start || rend < end) e |= ERR_ANCHOR_ORDER;
             if (start < 0 || start > refLen - 2 || end < start - 1) e |= ERR_START_RANGE;
             const uint64_t sz = (uint64_t)(uint32_t)(end - start + 1);
             if (sz >> len_bits) e |= ERR_KEY_OVERFLOW;
             // nbUpstreamJunctions / nbDownstreamJunctions contribution of this read (junction.cc:795-812)
-            uint32_t up = 0, down = 0; int32_t p = pos;
-            for (int32_t k = 0; k < n; k++) {
-                const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
-                if (op_ref(o3)) p += cig_len(w3);
-                if (o3 == OP_N) { if (p < start) up++; else if (p > end + 1) down++; }
+            uint32_t up = 0, down = 0;
+            if (nN > 1 || clamped) {                       // a lone, unclamped N op ends exactly at end + 1: neither up nor down
+                int32_t p = pos;
+                for (int32_t k = 0; k < n; k++) {
+                    const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
+                    if (op_ref(o3)) p += cig_len(w3);
+                    if (o3 == OP_N) { if (p < start) up++; else if (p > end + 1) down++; }
+                }
             }
             keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
             pa[slot] = PairA{(uint32_t)i, lStart, rend, pos};
@@ -714,31 +718,34 @@ __global__ void __launch_bounds__(256) k_entropy_compact(uint32_t n, const uint3
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && eflag[i]) epos[eoff[i]] = i;
 }
-__global__ void __launch_bounds__(128) k_entropy_sum(uint32_t n_junc, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ eoff,
+// One warp per junction: lane l evaluates emission points l, l+32, ... and the warp adds the terms with a fixed shuffle
+// tree (deterministic; the order differs from the reference's loop only by fp64 rounding, far inside the 1e-6 bound).
+__global__ void __launch_bounds__(256) k_entropy_sum(uint32_t n_junc, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ eoff,
                                                       const uint32_t* __restrict__ epos, double* __restrict__ entropy) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (j >= n_junc) return;
     const uint32_t s = seg_start[j], e = seg_start[j + 1], n = e - s;
     double sum = 0.0;
     if (n > 1) {
         const uint32_t k0 = eoff[s], k1 = eoff[e - 1];       // the last element of a segment always emits
-        uint32_t prev = s;                                   // terms count elements since the previous emission
-        bool first = true;
-        for (uint32_t k = k0; k <= k1; k++) {
+        const double inv = 1.0 / (double)n;
+        for (uint32_t k = k0 + lane; k <= k1; k += 32) {
             const uint32_t i = epos[k];
-            const uint32_t term = first ? (i - s + 1) : (i - prev);
-            first = false; prev = i;
-            const double p = (double)term / (double)n;
+            const uint32_t term = (k == k0) ? (i - s + 1) : (i - epos[k - 1]);   // elements since the previous emission (quirk Q1)
+            const double p = (double)term * inv;
             sum += p * log2(p);
         }
     }
-    entropy[j] = fabs(sum);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    if (lane == 0) entropy[j] = fabs(sum);
 }
 void launch_entropy_compact(uint32_t n, const uint32_t* eflag, const uint32_t* eoff, uint32_t* epos, cudaStream_t st) {
     if (n) k_entropy_compact<<<(n + 255) / 256, 256, 0, st>>>(n, eflag, eoff, epos);
 }
 void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32_t* eoff, const uint32_t* epos, double* entropy, cudaStream_t st) {
-    if (n_junc) k_entropy_sum<<<(n_junc + 127) / 128, 128, 0, st>>>(n_junc, seg_start, eoff, epos, entropy);
+    if (n_junc) k_entropy_sum<<<(unsigned)(((uint64_t)n_junc * 32 + 255) / 256), 256, 0, st>>>(n_junc, seg_start, eoff, epos, entropy);
 }
 
 // ================================================================================================
