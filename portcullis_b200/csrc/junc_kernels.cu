@@ -729,11 +729,10 @@ __global__ void __launch_bounds__(256) k_entropy_sum(uint32_t n_junc, const uint
     double sum = 0.0;
     if (n > 1) {
         const uint32_t k0 = eoff[s], k1 = eoff[e - 1];       // the last element of a segment always emits
-        const double inv = 1.0 / (double)n;
         for (uint32_t k = k0 + lane; k <= k1; k += 32) {
             const uint32_t i = epos[k];
             const uint32_t term = (k == k0) ? (i - s + 1) : (i - epos[k - 1]);   // elements since the previous emission (quirk Q1)
-            const double p = (double)term * inv;
+            const double p = (double)term / (double)n;          // a true division: term == n must give exactly 1.0 (entropy 0)
             sum += p * log2(p);
         }
     }
