@@ -82,6 +82,10 @@ int         pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_
  * computes the same plan. */
 int         pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_target);
 
+/* Checks the built-in fast DEFLATE decoder (BGZF blocks) against zlib on n_cases synthetic streams; returns the number of
+ * mismatches (0 = pass).  BGZF blocks the fast decoder rejects are decoded by zlib, so it can only be an accelerator. */
+int         pjh_inflate_selftest(int32_t n_cases);
+
 /* ---- writers (A14) ---- */
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,
                       int32_t n_targets, const char* const* names, const int32_t* lens,

@@ -114,6 +114,7 @@ SYMBOLS = {
     "pjh_prep_target_records": (C.c_int64, [_P, C.c_int32]),
     "pjh_prep_decode": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(PjBatch)]),
     "pjh_prep_genome": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
+    "pjh_inflate_selftest": (C.c_int, [C.c_int32]),
     "pjh_plan_shards": (C.c_int, [_P, C.c_int32, _P]),
     "pjh_write_outputs": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,
                                     C.c_int32, C.c_int32]),

@@ -1,6 +1,7 @@
 // bam_io.cpp — see bam_io.hpp.  BGZF framing: SAM spec §4.1; BAM records: §4.2; BAI: §5.2.
 #include "bam_io.hpp"
 #include <zlib.h>
+#include "inflate_fast.hpp"
 #include <cstring>
 #include <algorithm>
 #include <fcntl.h>
@@ -31,12 +32,12 @@ void MappedFile::open(const std::string& path) {
     ::close(fd);
 }
 
-BgzfStream::BgzfStream(const MappedFile& f) : f_(f), ubuf_(65536) {
+BgzfStream::BgzfStream(const MappedFile& f) : f_(f), ubuf_(65536 + 64), fast_(new pjinflate::Inflater()) {
     z_stream* z = new z_stream; memset(z, 0, sizeof *z);
     if (inflateInit2(z, -15) != Z_OK) { delete z; throw IoError("inflateInit2 failed"); }
     z_ = z;
 }
-BgzfStream::~BgzfStream() { z_stream* z = (z_stream*)z_; inflateEnd(z); delete z; }
+BgzfStream::~BgzfStream() { z_stream* z = (z_stream*)z_; inflateEnd(z); delete z; delete (pjinflate::Inflater*)fast_; }
 
 bool BgzfStream::load_block(uint64_t coff) {
     have_block_ = false; ulen_ = upos_ = 0; block_coff_ = coff; next_coff_ = coff;
@@ -54,7 +55,10 @@ bool BgzfStream::load_block(uint64_t coff) {
     if (!found || coff + bsize > f_.size() || bsize < 12 + xlen + 8) throw IoError("corrupt BGZF block in " + f_.path());
     uint32_t isize = rd32(p + bsize - 4);
     if (isize > 65536) throw IoError("BGZF block too large");
-    if (isize) {
+    // fast path: our own DEFLATE decoder (inflate_fast.hpp); anything it does not accept is decoded again by zlib
+    const bool fast_ok = isize && coff + bsize + 16 <= f_.size() &&
+                         ((pjinflate::Inflater*)fast_)->run(p + 12 + xlen, bsize - 12 - xlen - 8, ubuf_.data(), isize);
+    if (isize && !fast_ok) {
         z_stream* z = (z_stream*)z_;
         inflateReset(z);
         z->next_in = (Bytef*)(p + 12 + xlen); z->avail_in = bsize - 12 - xlen - 8;
@@ -304,3 +308,35 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
 }
 
 } // namespace pjio
+
+// Self-test of the fast inflater against zlib on synthetic streams (several data shapes, levels and strategies).
+// Returns the number of mismatches; exported through pjh_inflate_selftest for the CPU test-suite.
+int pjio::inflate_selftest(int n_cases) {
+    pjinflate::Inflater inf;
+    uint64_t rs = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return (uint32_t)(rs >> 16); };
+    int bad = 0;
+    static const int levels[] = {0, 1, 6, 9};
+    static const int strats[] = {Z_DEFAULT_STRATEGY, Z_FIXED, Z_HUFFMAN_ONLY, Z_RLE, Z_FILTERED};
+    for (int t = 0; t < n_cases; t++) {
+        const size_t n = 1 + rnd() % 65000; std::vector<uint8_t> d(n); const int mode = t % 5;
+        for (size_t i = 0; i < n; i++) {
+            if (mode == 0) d[i] = (uint8_t)rnd();
+            else if (mode == 1) d[i] = (uint8_t)"ACGT"[rnd() & 3];
+            else if (mode == 2) d[i] = (i % 97 < 50) ? 0xff : (uint8_t)(rnd() & 15);
+            else if (mode == 3) d[i] = (i > 200 && rnd() % 3) ? d[i - 1 - (rnd() % 200)] : (uint8_t)(rnd() & 63);
+            else d[i] = 0;
+        }
+        z_stream z; memset(&z, 0, sizeof z);
+        if (deflateInit2(&z, levels[t % 4], Z_DEFLATED, -15, 8, strats[(t / 4) % 5]) != Z_OK) return -1;
+        std::vector<uint8_t> c(n * 2 + 1024);
+        z.next_in = d.data(); z.avail_in = (uInt)n; z.next_out = c.data(); z.avail_out = (uInt)c.size();
+        deflate(&z, Z_FINISH); const size_t cn = z.total_out; deflateEnd(&z);
+        std::vector<uint8_t> o(n + 64);
+        if (!inf.run(c.data(), cn, o.data(), n) || memcmp(o.data(), d.data(), n) != 0) bad++;
+        // corrupted and truncated input must never read or write out of bounds (the result itself is irrelevant: the caller
+        // falls back to zlib whenever run() returns false, and BGZF carries its own size trailer)
+        if (cn > 8) { c[cn / 2] ^= 0x55; std::vector<uint8_t> o2(n + 64); (void)inf.run(c.data(), cn, o2.data(), n); (void)inf.run(c.data(), cn / 2, o2.data(), n); }
+    }
+    return bad;
+}

@@ -43,9 +43,10 @@ public:
 private:
     bool load_block(uint64_t coff);
     const MappedFile& f_;
-    void* z_ = nullptr;                    // z_stream
+    void* z_ = nullptr;                    // z_stream (fallback decoder)
     uint64_t block_coff_ = 0, next_coff_ = 0;
     std::vector<uint8_t> ubuf_; uint32_t ulen_ = 0, upos_ = 0;
+    void* fast_ = nullptr;                 // pjinflate::Inflater (inflate_fast.hpp)
     bool have_block_ = false;
 };
 
@@ -105,5 +106,7 @@ private:
     BamHeader hdr_;
     std::vector<BamTargetIndex> idx_;
 };
+
+int inflate_selftest(int n_cases);
 
 } // namespace pjio

@@ -158,6 +158,8 @@ static uint64_t target_weight(const pjh_prep* p, int32_t t) {
     return bytes / 64;
 }
 
+int pjh_inflate_selftest(int32_t n_cases) { return pjio::inflate_selftest(n_cases); }
+
 int pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_target) {
     if (!p || n_gpus < 1 || !gpu_of_target) return fail(PJ_EINVAL, "pjh_plan_shards: bad argument");
     const int32_t T = pjh_prep_n_targets(p);

@@ -84,3 +84,9 @@ def test_host_finalize_edge_cases():
     assert list(two["dist_2_down_junc"]) == [0xFFFFFFFF, 10] and list(two["dist_2_up_junc"]) == [10, 0]
     one = jb.finalize(rows([(0, 10, 20, 3)]), 100.5)
     assert one["mean_readlen"][0] == 0 and one["uniq_junc"][0] == 0
+
+
+def test_fast_inflate_matches_zlib():
+    """The built-in DEFLATE decoder used for BGZF blocks agrees with zlib on 300 synthetic streams (random, DNA-like,
+    run-heavy, LZ-heavy, all-zero data; stored / fixed / dynamic blocks; several strategies)."""
+    assert L.load().pjh_inflate_selftest(300) == 0
