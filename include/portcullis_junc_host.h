@@ -52,6 +52,9 @@ typedef struct pjh_report {
     double  t_total_s;
     int32_t n_gpus_used;
     int32_t n_kernel_launches;
+    double  t_init_s;            /* CUDA context + pj_create + pj_targets_set (max over GPUs)     */
+    double  t_run_s;             /* wall time of pj_shard_run + pj_shard_fetch (max over GPUs)    */
+    double  t_teardown_s;        /* pj_destroy                                                    */
 } pjh_report;
 
 void pjh_options_default(pjh_options* o);

@@ -78,7 +78,8 @@ class PjhReport(C.Structure):
                 ("mean_query_length", C.c_double), ("min_query_length", C.c_int32), ("max_query_length", C.c_int32),
                 ("t_open_s", C.c_double), ("t_genome_s", C.c_double), ("t_decode_s", C.c_double), ("t_gpu_ms", C.c_double),
                 ("t_finalize_s", C.c_double), ("t_write_s", C.c_double), ("t_total_s", C.c_double),
-                ("n_gpus_used", C.c_int32), ("n_kernel_launches", C.c_int32)]
+                ("n_gpus_used", C.c_int32), ("n_kernel_launches", C.c_int32),
+                ("t_init_s", C.c_double), ("t_run_s", C.c_double), ("t_teardown_s", C.c_double)]
 
 
 # every symbol declared in include/*.h, with (restype, argtypes); used by load() and by the export test

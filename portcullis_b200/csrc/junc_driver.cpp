@@ -286,7 +286,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     R.t_open_s = now_s() - t0;
     R.n_gpus_used = n_gpus;
 
-    struct GpuOut { std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0; int rc = PJ_OK; std::string err; };
+    struct GpuOut { std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int rc = PJ_OK; std::string err; };
     std::vector<GpuOut> outs((size_t)n_gpus);
     const int threads_per_gpu = std::max(1, threads / n_gpus);
     const size_t window_per_gpu = (size_t)threads_per_gpu + 2;          // staged-but-unsubmitted batches; staging slots = window + 2
@@ -297,10 +297,12 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
         cfg.reserved[2] = (int32_t)window_per_gpu + 2;                     // pinned staging buffers
         pj_ctx* ctx = nullptr;
+        const double ti = now_s();
         int r = pj_create(&cfg, &ctx);
         if (r) return bail(r, pj_global_last_error());
-        struct Guard { pj_ctx* c; ~Guard() { pj_destroy(c); } } guard{ctx};
+        struct Guard { pj_ctx* c; double* t; ~Guard() { const double a = now_s(); pj_destroy(c); *t = now_s() - a; } } guard{ctx, &out.teardown_s};
         if ((r = pj_targets_set(ctx, T, H.lens.data()))) return bail(r, pj_last_error(ctx));
+        out.init_s = now_s() - ti;
         // genome: only this shard's targets become resident on this GPU.  The upload runs on its own host thread and CUDA
         // stream, concurrently with the alignment decode below (pj_genome_* may overlap pj_staging_* / pj_batch_submit).
         double tg = now_s();
@@ -352,10 +354,12 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         out.decode_s = now_s() - td;
         genome_thread.join();
         if (genome_rc) return bail(genome_rc, genome_err);
+        const double tr = now_s();
         if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));
         const int64_t J = pj_shard_num_junctions(ctx);
         out.rows.resize((size_t)J); out.stats.resize((size_t)T);
         if ((r = pj_shard_fetch(ctx, out.rows.data(), J, out.stats.data(), T))) return bail(r, pj_last_error(ctx));
+        out.run_s = now_s() - tr;
         int32_t nl = 0; pj_shard_timing(ctx, &out.gpu_ms, &nl); out.launches = nl;
     };
     if (say) std::cout << "Finding junctions and calculating basic metrics:\n - Sharding " << T << " target sequences over " << n_gpus << " GPU(s)" << std::endl;
@@ -377,6 +381,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         if (!prep->indexed) stats = outs[g].stats;
         R.t_gpu_ms = std::max<double>(R.t_gpu_ms, outs[g].gpu_ms); R.n_kernel_launches += outs[g].launches;
         R.t_genome_s = std::max(R.t_genome_s, outs[g].genome_s); R.t_decode_s = std::max(R.t_decode_s, outs[g].decode_s);
+        R.t_init_s = std::max(R.t_init_s, outs[g].init_s); R.t_run_s = std::max(R.t_run_s, outs[g].run_s); R.t_teardown_s = std::max(R.t_teardown_s, outs[g].teardown_s);
     }
     uint64_t spliced = 0, unspliced = 0, sumq = 0; int32_t minq = INT32_MAX, maxq = 0;
     if (say) std::cout << " - All shards completed.\n - Combining results.\n\n" << std::left << std::setw(12) << "Sequence" << "\t" << std::right << std::setw(12) << "unspliced"
@@ -518,7 +523,8 @@ int pjh_junc_main(int argc, char** argv) {
     const int rc = pjh_junc_run(&o, &rep);
     if (rc) { std::cerr << "Error: " << pjh_last_error() << std::endl; return rc == PJ_EINVAL ? 1 : 4; }
     std::cout << std::fixed << std::setprecision(1) << "\nPortcullis junc completed.\nTotal runtime: " << rep.t_total_s << "s"
-              << "  (open " << rep.t_open_s << "s, genome " << rep.t_genome_s << "s, decode+H2D " << rep.t_decode_s << "s, GPU pipeline "
+              << "  (open " << rep.t_open_s << "s, GPU init " << rep.t_init_s << "s, genome " << rep.t_genome_s << "s [overlapped], decode+H2D " << rep.t_decode_s << "s, run+fetch "
+              << rep.t_run_s << "s, teardown " << rep.t_teardown_s << "s, GPU pipeline "
               << std::setprecision(3) << rep.t_gpu_ms << " ms on " << rep.n_gpus_used << " GPU(s), " << std::setprecision(1) << "finalize " << rep.t_finalize_s << "s, write " << rep.t_write_s << "s)\n" << std::endl;
     return 0;
 }

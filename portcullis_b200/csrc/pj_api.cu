@@ -11,6 +11,7 @@
 #include <vector>
 #include <climits>
 #include <mutex>
+#include <thread>
 
 using namespace pjk;
 
@@ -58,6 +59,7 @@ struct pj_ctx {
     DevBuf<int32_t> tid, pos, l_qseq, mtid, mpos; DevBuf<uint16_t> flag; DevBuf<uint8_t> mapq, xs, seq4;
     DevBuf<uint32_t> cigar_off, cigar; DevBuf<uint64_t> seq_off;
     std::vector<StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
+    std::thread prewarm_thread;         // grows the stream-ordered memory pool while the caller is still decoding
     std::mutex staging_mu;              // pj_staging_acquire / pj_batch_submit may be called from several host threads
     cudaStream_t genome_stream = nullptr;
     cudaEvent_t copies_done = nullptr;
@@ -201,6 +203,7 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
 
 void pj_destroy(pj_ctx* c) {
     if (!c) return;
+    if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
@@ -287,6 +290,22 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
         (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 48, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
+    // Pre-grow the stream-ordered pool that pj_shard_run allocates its temporaries from (about 12 B per record and 80 B
+    // per read-junction pair): a cold pool costs hundreds of milliseconds for a multi-GB shard, and this way the growth
+    // overlaps the caller's decode instead of sitting in front of the first kernel.
+    if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
+    {
+        const size_t est = (size_t)std::max<int64_t>(n_records_hint, 0) * (12 + 80) + (64u << 20);
+        const int dev = c->device; cudaStream_t ps = c->genome_stream;
+        if (n_records_hint > (1 << 20)) c->prewarm_thread = std::thread([est, dev, ps]() {
+            cudaSetDevice(dev);
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || est > free_b / 2) return;
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, est, ps) == cudaSuccess) { cudaFreeAsync(p, ps); cudaStreamSynchronize(ps); }
+            else cudaGetLastError();
+        });
+    }
     c->shard_open = true;
     return PJ_OK;
 }
@@ -370,6 +389,7 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
 int pj_shard_run(pj_ctx* c) {
     if (!c || !c->shard_open) return fail(c, PJ_ESTATE, "pj_shard_run: no open shard");
     CU(c, cudaSetDevice(c->device));
+    if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     int rc = finish_genome(c); if (rc) return rc;
     cudaStream_t st = c->compute_stream;
     CU(c, cudaEventRecord(c->copies_done, c->copy_stream));
