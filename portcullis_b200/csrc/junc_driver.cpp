@@ -289,25 +289,36 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     struct GpuOut { std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int rc = PJ_OK; std::string err; };
     std::vector<GpuOut> outs((size_t)n_gpus);
     const int threads_per_gpu = std::max(1, threads / n_gpus);
-    const size_t window_per_gpu = (size_t)threads_per_gpu + 2;          // staged-but-unsubmitted batches; staging slots = window + 2
+    const size_t window_per_gpu = (size_t)threads_per_gpu * 3 + 2;      // decoded-but-unsubmitted batches (pageable while CUDA starts, pinned after)
     auto run_gpu = [&](int g) {
         GpuOut& out = outs[(size_t)g];
         auto bail = [&](int code, const std::string& m) { out.rc = code; out.err = m; };
-        pj_config cfg; memset(&cfg, 0, sizeof cfg);
-        cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
-        cfg.reserved[2] = (int32_t)window_per_gpu + 2;                     // pinned staging buffers
+        // ---- decode plan for this shard ----
+        std::vector<DecodeTask> tasks;
+        uint64_t nrec_hint = 0;
+        if (prep->indexed) for (int32_t t : shard[(size_t)g]) { tasks.insert(tasks.end(), ttasks[t].begin(), ttasks[t].end()); nrec_hint += weight[t]; }
+        else tasks.push_back(prep->bam.whole_file_task());
+        // ---- GPU side on its own host thread: CUDA context + library context + genome upload.  CUDA start-up takes about a
+        // second on a B200, so BGZF decode starts right away and only the staging copies wait for the context. ----
         pj_ctx* ctx = nullptr;
-        const double ti = now_s();
-        int r = pj_create(&cfg, &ctx);
-        if (r) return bail(r, pj_global_last_error());
-        struct Guard { pj_ctx* c; double* t; ~Guard() { const double a = now_s(); pj_destroy(c); *t = now_s() - a; } } guard{ctx, &out.teardown_s};
-        if ((r = pj_targets_set(ctx, T, H.lens.data()))) return bail(r, pj_last_error(ctx));
-        out.init_s = now_s() - ti;
-        // genome: only this shard's targets become resident on this GPU.  The upload runs on its own host thread and CUDA
-        // stream, concurrently with the alignment decode below (pj_genome_* may overlap pj_staging_* / pj_batch_submit).
-        double tg = now_s();
+        std::mutex gm; std::condition_variable gcv; bool ready = false; int gpu_rc = PJ_OK; std::string gpu_err;
         int genome_rc = PJ_OK; std::string genome_err;
-        std::thread genome_thread([&]() {
+        const double ti = now_s();
+        std::thread gpu_thread([&]() {
+            pj_config cfg; memset(&cfg, 0, sizeof cfg);
+            cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
+            cfg.reserved[2] = (int32_t)window_per_gpu + 4;                 // pinned staging buffers
+            int r = pj_create(&cfg, &ctx);
+            std::string em;
+            if (r) em = pj_global_last_error();
+            if (!r && (r = pj_targets_set(ctx, T, H.lens.data()))) em = pj_last_error(ctx);
+            if (!r && (r = pj_shard_begin(ctx, (int64_t)nrec_hint + 1024, (int64_t)nrec_hint * 4 + 1024, (int64_t)nrec_hint * 56 + 1024))) em = pj_last_error(ctx);
+            out.init_s = now_s() - ti;
+            { std::lock_guard<std::mutex> lk(gm); ready = true; gpu_rc = r; gpu_err = em; }
+            gcv.notify_all();
+            if (r) return;
+            // genome: only this shard's targets become resident on this GPU (own CUDA stream; overlaps the batch submission)
+            const double tg = now_s();
             std::string seq;
             for (int32_t t : shard[(size_t)g]) {
                 if (ttasks[t].empty() && prep->indexed) continue;          // no records -> no junctions -> no genome needed
@@ -319,40 +330,51 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             }
             out.genome_s = now_s() - tg;
         });
-        struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } join_guard{genome_thread};
-        // alignments: workers inflate + parse a task, then copy its columns into a pinned staging buffer; this thread
-        // submits the staged batches in BAM order (cudaMemcpyAsync on the copy stream)
-        double td = now_s();
-        std::vector<DecodeTask> tasks;
-        uint64_t nrec_hint = 0;
-        if (prep->indexed) for (int32_t t : shard[(size_t)g]) { tasks.insert(tasks.end(), ttasks[t].begin(), ttasks[t].end()); nrec_hint += weight[t]; }
-        else tasks.push_back(prep->bam.whole_file_task());
-        if ((r = pj_shard_begin(ctx, (int64_t)nrec_hint + 1024, (int64_t)nrec_hint * 4 + 1024, (int64_t)nrec_hint * 56 + 1024))) return bail(r, pj_last_error(ctx));
-        r = ordered_pipeline<pj_batch>(tasks.size(), threads_per_gpu, window_per_gpu,
-            [&](size_t k, pj_batch& st) -> int {
-                ColumnarChunk ch;
-                prep->bam.decode(tasks[k], ch);
-                st.n_records = 0;
-                if (ch.n() == 0) return PJ_OK;
-                int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
-                if (q) return fail(q, pj_last_error(ctx));
-                const size_t n = (size_t)ch.n();
-                memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
-                memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
-                memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
-                memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
-                memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
-                st.n_records = ch.n();
-                return PJ_OK;
+        struct Cleanup {
+            std::thread& t; pj_ctx*& c; double* td;
+            ~Cleanup() { if (t.joinable()) t.join(); if (c) { const double a = now_s(); pj_destroy(c); *td = now_s() - a; } }
+        } cleanup{gpu_thread, ctx, &out.teardown_s};
+        auto is_ready = [&]() { std::lock_guard<std::mutex> lk(gm); return ready; };
+        auto wait_ready = [&]() -> int { std::unique_lock<std::mutex> lk(gm); gcv.wait(lk, [&] { return ready; }); return gpu_rc; };
+        // copy one decoded chunk into a pinned staging buffer of the context
+        auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
+            int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
+            if (q) return fail(q, pj_last_error(ctx));
+            const size_t n = (size_t)ch.n();
+            memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
+            memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
+            memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
+            memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
+            memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
+            st.n_records = ch.n();
+            return PJ_OK;
+        };
+        // alignments: workers inflate + parse a task and (once the context exists) copy its columns into pinned staging;
+        // this thread submits the batches in BAM order (cudaMemcpyAsync on the copy stream)
+        struct Payload { pj_batch st; std::unique_ptr<ColumnarChunk> chunk; };
+        const double td = now_s();
+        int r = ordered_pipeline<Payload>(tasks.size(), threads_per_gpu, window_per_gpu,
+            [&](size_t k, Payload& p) -> int {
+                auto ch = std::make_unique<ColumnarChunk>();
+                prep->bam.decode(tasks[k], *ch);
+                memset(&p.st, 0, sizeof p.st);
+                if (ch->n() == 0) return PJ_OK;
+                if (!is_ready()) { p.chunk = std::move(ch); return PJ_OK; }   // context still starting: keep the chunk in pageable memory
+                if (gpu_rc) return fail(gpu_rc, gpu_err);
+                return stage(*ch, p.st);
             },
-            [&](size_t, pj_batch& st) -> int {
-                if (st.n_records == 0) return PJ_OK;
-                int q = pj_batch_submit(ctx, &st);
+            [&](size_t, Payload& p) -> int {
+                if (!p.chunk && p.st.n_records == 0) return PJ_OK;
+                int q = wait_ready();
+                if (q) return fail(q, gpu_err);
+                if (p.chunk) { if ((q = stage(*p.chunk, p.st))) return q; p.chunk.reset(); }
+                q = pj_batch_submit(ctx, &p.st);
                 return q ? fail(q, pj_last_error(ctx)) : PJ_OK;
             });
-        if (r) return bail(r, g_err);
+        if (r) { wait_ready(); return bail(r, g_err); }
         out.decode_s = now_s() - td;
-        genome_thread.join();
+        if ((r = wait_ready())) return bail(r, gpu_err);
+        gpu_thread.join();
         if (genome_rc) return bail(genome_rc, genome_err);
         const double tr = now_s();
         if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));

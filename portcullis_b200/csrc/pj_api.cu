@@ -12,6 +12,7 @@
 #include <climits>
 #include <mutex>
 #include <thread>
+#include <chrono>
 
 using namespace pjk;
 
@@ -203,23 +204,37 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
 
 void pj_destroy(pj_ctx* c) {
     if (!c) return;
+    const bool trace = getenv("PJ_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    auto lap = [&](const char* what) { if (trace) { const double t = now(); fprintf(stderr, "[pj_destroy] %-22s %.3f s\n", what, t - t0); t0 = t; } };
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    lap("sync");
     c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
     c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_();
+    lap("arena");
     for (StagingSlot* sl : c->slots) { free_slot(*sl); if (sl->done) cudaEventDestroy(sl->done); delete sl; }
+    lap("pinned staging");
     if (c->genome_stream) cudaStreamDestroy(c->genome_stream);
     for (int s = 0; s < 2; s++) { if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
                                   if (c->h_graw[s]) cudaFreeHost(c->h_graw[s]); if (c->d_graw[s]) cudaFree(c->d_graw[s]); }
+    lap("genome staging");
     cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx); cudaFree(c->d_g4);
     cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
     cudaFree(c->d_spliced); cudaFree(c->d_unspliced); cudaFree(c->d_sumq); cudaFree(c->d_minq); cudaFree(c->d_maxq);
     cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
+    lap("genome + misc");
     for (auto& s : c->stages) cudaEventDestroy(s.ev);
     if (c->copies_done) cudaEventDestroy(c->copies_done);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
+    {   // give the stream-ordered pool back (it was told to keep everything while the context lived)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+    lap("streams + pool");
     delete c;
 }
 
