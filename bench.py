@@ -104,6 +104,8 @@ def algorithmic_bytes(cols, n_pairs, n_junc):
     total = fixed + pair + genome + rows
     per_stage = {
         # what each kernel must at least move (inputs read once, outputs written once)
+        # fused front end: every record column once, every CIGAR word once, one (key, PairA, PairB) per pair written
+        "scan_emit": (4 + 4 + 2 + 1 + 1 + 4 + 4 + 4 + 4) * n_rec + 4 * n_cig + (8 + 32) * n_pairs,
         "scan_reads": (4 + 4 + 2 + 4 + 4) * n_rec + 4 * n_cig + 8 * n_rec,
         "pair_offsets": 8 * n_rec,
         "emit_pairs": (4 + 4 + 2 + 1 + 1 + 4 + 4 + 4 + 4 + 4) * n_rec + 4 * n_cig + (8 + 32) * n_pairs,

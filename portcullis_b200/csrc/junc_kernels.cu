@@ -336,6 +336,206 @@ void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff
 }
 
 // ================================================================================================
+// k_scan_emit: k_scan_reads + the prefix scan of the N-op counts + k_emit_pairs in ONE pass over the records.
+// A tile of 1024 records is scanned (N-op counts, reference spans, per-target scalars), its pair slots come from a
+// block scan plus a decoupled look-back over per-tile status words (tiles take their index from an atomic ticket),
+// and the pair records are written straight away while the tile's CIGAR words are still in L1.  The record columns are
+// read once and the npairs / pair_off / read_end arrays disappear.  The width of the size field of the key comes from
+// the longest N op of the shard, which pj_batch_submit tracks while the batches are copied in (k_prescan_cigar).
+// ================================================================================================
+constexpr int SE_THREADS = 256;
+constexpr int SE_ITEMS = 4;
+constexpr int SE_TILE = SE_THREADS * SE_ITEMS;
+constexpr unsigned long long SE_PREFIX = 1ull << 63, SE_AGG = 1ull << 62, SE_MASK = (1ull << 62) - 1ull;
+
+__global__ void __launch_bounds__(256) k_prescan_cigar(const uint32_t* __restrict__ cigar, uint64_t n, uint32_t* __restrict__ max_nlen,
+                                                        unsigned long long* __restrict__ n_nops) {
+    uint32_t m = 0, k = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(cigar + i);
+        if (cig_op(w) == OP_N) { m = max(m, (uint32_t)cig_len(w)); k++; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { m = max(m, __shfl_xor_sync(FULL, m, o)); k += __shfl_xor_sync(FULL, k, o); }
+    if ((threadIdx.x & 31) == 0 && k) { atomicMax(max_nlen, m); atomicAdd(n_nops, (unsigned long long)k); }
+}
+// Longest N op and number of N ops of a batch's CIGAR words (upper bound of its read-junction pairs), accumulated per shard.
+void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen, unsigned long long* n_nops, int n_sm, cudaStream_t st) {
+    if (!n) return;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)n_sm * 8, (n + 255) / 256);
+    k_prescan_cigar<<<blocks, 256, 0, st>>>(cigar, n, max_nlen, n_nops);
+}
+
+__global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
+                                                           const uint32_t* __restrict__ max_nlen, int32_t orientation, TargetAcc T,
+                                                           uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
+                                                           unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket,
+                                                           uint32_t* __restrict__ total_pairs, uint32_t pair_cap, uint32_t* __restrict__ err) {
+    __shared__ uint32_t s_tile, s_tot;
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned long long b_sp[4], b_us[4], b_sum[4];
+    __shared__ int32_t b_mn[4], b_mx[4];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    if (threadIdx.x < 4) { b_sp[threadIdx.x] = 0; b_us[threadIdx.x] = 0; b_sum[threadIdx.x] = 0; b_mn[threadIdx.x] = INT32_MAX; b_mx[threadIdx.x] = 0; }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * SE_TILE;
+    const int32_t tid_first = R.tid[min(base, R.n - 1)];
+    const int32_t len_bits = max(1, 32 - __clz((int)__ldg(max_nlen)));
+    // ---- phase A: scan the tile's records ----
+    uint32_t cnt[SE_ITEMS]; int32_t rend[SE_ITEMS];
+#pragma unroll
+    for (int r = 0; r < SE_ITEMS; r++) {
+        const int64_t i = base + r * SE_THREADS + threadIdx.x;
+        bool vis = false; int32_t tid = -2, lq = 0; uint32_t nN = 0; rend[r] = 0;
+        if (i < R.n) {
+            tid = R.tid[i];
+            const int32_t pos = R.pos[i];
+            const uint32_t c0 = R.cigar_off[i], c1 = R.cigar_off[i + 1];
+            int64_t rlen = 0;
+            for (uint32_t c = c0; c < c1; c++) {
+                const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
+                if (op_ref(op)) rlen += cig_len(w);
+                nN += (op == OP_N);
+            }
+            rend[r] = (int32_t)(pos + rlen - 1);
+            lq = R.l_qseq[i];
+            if (tid >= 0 && tid < n_targets) {
+                const int64_t endpos = (!(R.flag[i] & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
+                vis = pos < tlen[tid] && endpos > 0;
+            }
+            if (!vis) nN = 0;
+        }
+        cnt[r] = nN;
+        // per-target scalars: warp partials into the block's shared slots (slot = tid - first tid of the tile)
+        const uint32_t vmask = __ballot_sync(FULL, vis);
+        if (vmask) {
+            const int32_t t0 = __shfl_sync(FULL, tid, __ffs(vmask) - 1);
+            if (__all_sync(FULL, !vis || tid == t0)) {
+                const uint32_t sp = __popc(__ballot_sync(FULL, vis && nN > 0)), us = __popc(vmask) - sp;
+                unsigned long long sm = vis ? (unsigned long long)(long long)lq : 0ull;
+                int32_t mn = vis ? lq : INT32_MAX, mx = vis ? lq : 0;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) { sm += __shfl_xor_sync(FULL, sm, o); mn = min(mn, __shfl_xor_sync(FULL, mn, o)); mx = max(mx, __shfl_xor_sync(FULL, mx, o)); }
+                if (lane == 0) {
+                    const int32_t slot = t0 - tid_first;
+                    if (slot >= 0 && slot < 4) { atomicAdd(&b_sp[slot], (unsigned long long)sp); atomicAdd(&b_us[slot], (unsigned long long)us); atomicAdd(&b_sum[slot], sm); atomicMin(&b_mn[slot], mn); atomicMax(&b_mx[slot], mx); }
+                    else { atomicAdd(T.spliced + t0, (unsigned long long)sp); atomicAdd(T.unspliced + t0, (unsigned long long)us); atomicAdd(T.sumq + t0, sm); atomicMin(T.minq + t0, mn); atomicMax(T.maxq + t0, mx); }
+                }
+            } else if (vis) {
+                if (nN > 0) atomicAdd(T.spliced + tid, 1ull); else atomicAdd(T.unspliced + tid, 1ull);
+                atomicAdd(T.sumq + tid, (unsigned long long)(long long)lq); atomicMin(T.minq + tid, lq); atomicMax(T.maxq + tid, lq);
+            }
+        }
+    }
+    // ---- pair slots: block scan in record order + look-back ----
+    uint32_t off[SE_ITEMS]; uint32_t carry = 0;
+#pragma unroll
+    for (int r = 0; r < SE_ITEMS; r++) { const uint32_t ex = block_excl_scan(cnt[r], &s_tot); off[r] = carry + ex; carry += s_tot; }
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status + tile;
+        unsigned long long excl = 0;
+        if (tile == 0) *st = (unsigned long long)carry | SE_PREFIX;
+        else {
+            *st = (unsigned long long)carry | SE_AGG;
+            __threadfence();
+            for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
+                volatile const unsigned long long* sp = status + t;
+                unsigned long long v;
+                do { v = *sp; } while ((v >> 62) == 0ull);
+                excl += v & SE_MASK;
+                if (v & SE_PREFIX) break;
+            }
+            *st = ((excl + carry) & SE_MASK) | SE_PREFIX;
+        }
+        s_base = excl;
+        if (base + SE_TILE >= R.n) *total_pairs = (uint32_t)min(excl + carry, 0xffffffffull);   // the last tile knows the total
+    }
+    if (threadIdx.x < 4) {   // flush the block's per-target partials
+        const int32_t t = tid_first + (int32_t)threadIdx.x;
+        if (t >= 0 && t < n_targets && (b_sp[threadIdx.x] | b_us[threadIdx.x])) {
+            atomicAdd(T.spliced + t, b_sp[threadIdx.x]); atomicAdd(T.unspliced + t, b_us[threadIdx.x]); atomicAdd(T.sumq + t, b_sum[threadIdx.x]);
+            atomicMin(T.minq + t, b_mn[threadIdx.x]); atomicMax(T.maxq + t, b_mx[threadIdx.x]);
+        }
+    }
+    __syncthreads();
+    const unsigned long long tile_base = s_base;
+    // ---- phase B: JunctionSystem::addJunctions (junction_system.cc:140-210, recursion unrolled) for the spliced records ----
+    uint32_t e = 0;
+#pragma unroll
+    for (int r = 0; r < SE_ITEMS; r++) {
+        const uint32_t nN = cnt[r];
+        if (nN == 0) continue;
+        const int64_t i = base + r * SE_THREADS + threadIdx.x;
+        const unsigned long long slot0 = tile_base + off[r];
+        if (slot0 + nN > (unsigned long long)pair_cap) { e |= ERR_KEY_OVERFLOW; continue; }
+        uint32_t slot = (uint32_t)slot0;
+        const int32_t tid = R.tid[i], pos = R.pos[i], refLen = tlen[tid];
+        const uint32_t flag = R.flag[i];
+        const uint32_t* cg = R.cigar + R.cigar_off[i];
+        const int32_t n = (int32_t)(R.cigar_off[i + 1] - R.cigar_off[i]);
+        const uint8_t xs = R.xs[i];
+        uint32_t bits = 0;
+        if (flag & 0x40u) bits |= PB_R1;
+        if (flag & 0x10u) bits |= PB_REV;
+        if (nN > 1) bits |= PB_MS;
+        if (R.mapq[i] >= PJ_MAP_QUALITY_THRESHOLD) bits |= PB_UM;
+        if (flag & 0x2u) bits |= PB_BPP;
+        if (portcullis_proper_pair(flag, tid, R.mtid[i], pos, R.mpos[i], orientation)) bits |= PB_PPP;
+        if (xs == '+') bits |= PB_XSP; else if (xs == '-') bits |= PB_XSN;
+        const uint64_t tbase = toff[tid];
+        int32_t lStart = pos, lEndExc = pos;
+        for (int32_t c = 0; c < n; c++) {
+            const uint32_t w = __ldg(cg + c), op = cig_op(w); const int32_t L = cig_len(w);
+            if (op == OP_N) {
+                int32_t rStart = lEndExc + L, rEndExc = rStart;
+                int32_t j = c + 1;
+                while (j < n && rEndExc <= refLen) {
+                    const uint32_t w2 = __ldg(cg + j); if (cig_op(w2) == OP_N) break;
+                    if (op_ref(cig_op(w2))) rEndExc += cig_len(w2);
+                    j++;
+                }
+                bool clamped = false;
+                if (rStart - 1 >= refLen) { rStart = refLen - 1; clamped = true; }
+                if (rEndExc - 1 >= refLen) { rEndExc = refLen; clamped = true; }
+                const int32_t start = lEndExc, end = rStart - 1, rendj = rEndExc - 1;
+                if (lStart > start || rendj < end) e |= ERR_ANCHOR_ORDER;
+                if (start < 0 || start > refLen - 2 || end < start - 1) e |= ERR_START_RANGE;
+                const uint64_t sz = (uint64_t)(uint32_t)(end - start + 1);
+                if (sz >> len_bits) e |= ERR_KEY_OVERFLOW;
+                uint32_t up = 0, down = 0;
+                if (nN > 1 || clamped) {                       // a lone, unclamped N op ends exactly at end + 1: neither up nor down
+                    int32_t p = pos;
+                    for (int32_t k = 0; k < n; k++) {
+                        const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
+                        if (op_ref(o3)) p += cig_len(w3);
+                        if (o3 == OP_N) { if (p < start) up++; else if (p > end + 1) down++; }
+                    }
+                }
+                keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
+                pa[slot] = PairA{(uint32_t)i, lStart, rendj, pos};
+                pb[slot] = PairB{rend[r], bits, (up << 16) | (down & 0xffffu), start};
+                slot++;
+                if (j < n) { lStart = rStart; lEndExc = rStart; } else break;
+            } else if (op_ref(op)) lEndExc += L;
+        }
+    }
+    if (e) atomicOr(err, e);
+}
+
+uint32_t se_num_tiles(int64_t n) { return (uint32_t)((n + SE_TILE - 1) / SE_TILE); }
+void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
+                      const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, unsigned long long* status, uint32_t* ticket,
+                      uint32_t* total_pairs, uint32_t pair_cap, uint32_t* err, cudaStream_t st) {
+    if (R.n <= 0) return;
+    const uint32_t nt = se_num_tiles(R.n);
+    cudaMemsetAsync(status, 0, (size_t)nt * sizeof(unsigned long long), st);
+    cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
+    k_scan_emit<<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err);
+}
+
+// ================================================================================================
 // stable LSD radix sort of (key64, val32), 8-bit digits.
 // Per pass: block digit histograms -> exclusive scan over [digit][block] -> stable scatter.
 // ================================================================================================

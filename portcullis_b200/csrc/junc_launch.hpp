@@ -30,6 +30,11 @@ void launch_scan_reads(const Reads& R, const int32_t* tlen, int32_t n_targets, u
 void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff, int32_t len_bits, int32_t orientation,
                        const uint32_t* pair_off, const uint32_t* npairs, const int32_t* read_end,
                        uint64_t* keys, PairA* pa, PairB* pb, uint32_t* err, cudaStream_t st);
+void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen, unsigned long long* n_nops, int n_sm, cudaStream_t st);
+uint32_t se_num_tiles(int64_t n);
+void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
+                      const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, unsigned long long* status, uint32_t* ticket,
+                      uint32_t* total_pairs, uint32_t pair_cap, uint32_t* err, cudaStream_t st);
 uint32_t rs_num_blocks(uint32_t n);
 int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
                       uint32_t* counts, uint32_t* scan_tmp, uint32_t* total_tmp, cudaStream_t st, int* n_launches);

@@ -66,7 +66,8 @@ struct pj_ctx {
     cudaEvent_t copies_done = nullptr;
     // per-target accumulators + misc device scalars
     unsigned long long *d_spliced = nullptr, *d_unspliced = nullptr, *d_sumq = nullptr; int32_t *d_minq = nullptr, *d_maxq = nullptr;
-    uint32_t* d_scalars = nullptr;    // [0]=err [1]=max_nlen [2]=P [3]=J [4]=E [5]=scratch total
+    uint32_t* d_scalars = nullptr;    // [0]=err [1]=max_nlen [2]=P [3]=J [4]=E [5]=scratch total [6]=tile ticket
+    unsigned long long* d_shard_acc = nullptr;   // [0] (low 32 bits) longest N op, [1] number of N ops of the shard: filled while batches are copied in
     uint32_t* h_scalars = nullptr;    // pinned mirror
     // results
     pj_junction* d_rows = nullptr; size_t rows_cap = 0; int64_t n_junc = 0; uint64_t n_pairs = 0;
@@ -194,6 +195,7 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
     for (int s = 0; s < 2; s++) CU(c, cudaEventCreateWithFlags(&c->graw_ev[s], cudaEventDisableTiming));
     c->max_slots = cfg->reserved[2] > 0 ? std::max(2, cfg->reserved[2]) : 4;
     CU(c, cudaMalloc(&c->d_scalars, 16 * sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->d_shard_acc, 2 * sizeof(unsigned long long)));
     CU(c, cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(uint32_t)));
     // keep stream-ordered allocations cached between shards
     cudaMemPool_t pool; CU(c, cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -224,7 +226,7 @@ void pj_destroy(pj_ctx* c) {
     cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx); cudaFree(c->d_g4);
     cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
     cudaFree(c->d_spliced); cudaFree(c->d_unspliced); cudaFree(c->d_sumq); cudaFree(c->d_minq); cudaFree(c->d_maxq);
-    cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
+    cudaFree(c->d_scalars); cudaFree(c->d_shard_acc); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
     lap("genome + misc");
     for (auto& s : c->stages) cudaEventDestroy(s.ev);
     if (c->copies_done) cudaEventDestroy(c->copies_done);
@@ -304,6 +306,7 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
         (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024), 0, st)) ||
         (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 48, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
+    CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 2 * sizeof(unsigned long long), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
     // Pre-grow the stream-ordered pool that pj_shard_run allocates its temporaries from (about 12 B per record and 80 B
     // per read-junction pair): a cold pool costs hundreds of milliseconds for a multi-GB shard, and this way the growth
@@ -388,7 +391,10 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
     CU(c, cudaMemcpyAsync(c->mapq.p + R, b->mapq, n, H2D, st)); CU(c, cudaMemcpyAsync(c->xs.p + R, b->xs, n, H2D, st));
     CU(c, cudaMemcpyAsync(c->cigar_off.p + R + 1, b->cigar_off + 1, n * 4, H2D, st));
     CU(c, cudaMemcpyAsync(c->seq_off.p + R + 1, b->seq_off + 1, n * 8, H2D, st));
-    if (ncig) CU(c, cudaMemcpyAsync(c->cigar.p + c->n_cig, b->cigar + cb, ncig * 4, H2D, st));
+    if (ncig) {
+        CU(c, cudaMemcpyAsync(c->cigar.p + c->n_cig, b->cigar + cb, ncig * 4, H2D, st));
+        launch_prescan_cigar(c->cigar.p + c->n_cig, ncig, reinterpret_cast<uint32_t*>(c->d_shard_acc), c->d_shard_acc + 1, c->n_sm, st);
+    }
     if (nseq) CU(c, cudaMemcpyAsync(c->seq4.p + c->n_seq, b->seq4 + sb, nseq, H2D, st));
     launch_rebase_u32(c->cigar_off.p + R + 1, n, (uint32_t)c->n_cig - cb, st);
     launch_rebase_u64(c->seq_off.p + R + 1, n, c->n_seq - sb, st);
@@ -424,36 +430,63 @@ int pj_shard_run(pj_ctx* c) {
     uint32_t* d_J = c->d_scalars + 3; uint32_t* d_E = c->d_scalars + 4; uint32_t* d_tmp_total = c->d_scalars + 5;
 
     uint32_t *npairs = nullptr, *pair_off = nullptr, *scan_tmp = nullptr; int32_t* read_end = nullptr;
-    const size_t Ra = (size_t)std::max<int64_t>(R, 1);
-    CU(c, cudaMallocAsync(&npairs, Ra * 4, st)); CU(c, cudaMallocAsync(&pair_off, (Ra + 1) * 4, st)); CU(c, cudaMallocAsync(&read_end, Ra * 4, st));
-    CU(c, cudaMallocAsync(&scan_tmp, scan_tmp_elems(Ra) * 4, st));
-    launch_scan_reads(Rd, c->d_tlen, T, npairs, read_end, TA, d_maxn, c->n_sm, st); c->n_launches++;
-    mark(c, "scan_reads");
-    launch_exclusive_scan(npairs, pair_off, (uint64_t)R, scan_tmp, d_P, st); c->n_launches += 3;
-    mark(c, "pair_offsets");
-    CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU(c, cudaStreamSynchronize(st));
-    CU(c, cudaGetLastError());
-    const uint32_t P = c->h_scalars[2], maxN = c->h_scalars[1];
-    c->n_pairs = P;
-    // (a uint32 sum of N-op counts can wrap only beyond 2^32 pairs; the CIGAR word limit above excludes that)
-    const int len_bits = std::max(1, bit_length(maxN));
+    uint64_t *keys_a = nullptr, *keys_b = nullptr; uint32_t *vals_a = nullptr, *vals_b = nullptr, *counts = nullptr, *scan_tmp2 = nullptr;
+    PairA* pa = nullptr; PairB* pb = nullptr; unsigned long long* se_status = nullptr;
+    uint32_t P = 0; int len_bits = 1, key_bits = 2;
     const int gbits = std::max(1, bit_length(c->h_toff[T]));
-    const int key_bits = len_bits + gbits;
-    if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
+    const size_t Ra = (size_t)std::max<int64_t>(R, 1);
+    auto alloc_pairs = [&](uint32_t cap) -> int {
+        const size_t n = std::max<size_t>(cap, 1);
+        const uint32_t nb = rs_num_blocks((uint32_t)n);
+        CU(c, cudaMallocAsync(&keys_a, n * 8, st)); CU(c, cudaMallocAsync(&keys_b, n * 8, st));
+        CU(c, cudaMallocAsync(&vals_a, n * 4, st)); CU(c, cudaMallocAsync(&vals_b, n * 4, st));
+        CU(c, cudaMallocAsync(&counts, (size_t)256 * nb * 4, st));
+        CU(c, cudaMallocAsync(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, n)) * 4, st));
+        CU(c, cudaMallocAsync(&pa, n * sizeof(PairA), st)); CU(c, cudaMallocAsync(&pb, n * sizeof(PairB), st));
+        return PJ_OK;
+    };
+    if (!c->legacy_sort) {
+        // fused front end: the longest N op and the number of N ops were accumulated while the batches were copied in
+        unsigned long long acc[2] = {0, 0};
+        CU(c, cudaStreamSynchronize(c->copy_stream));
+        CU(c, cudaMemcpy(acc, c->d_shard_acc, sizeof acc, cudaMemcpyDeviceToHost));
+        const uint32_t maxN = (uint32_t)(acc[0] & 0xffffffffull);
+        if (acc[1] >= 0xfffffff0ull) return fail(c, PJ_EINVAL, "pj_shard_run: more than 2^32 read-junction pairs in one shard");
+        len_bits = std::max(1, bit_length(maxN)); key_bits = len_bits + gbits;
+        if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
+        if ((rc = alloc_pairs((uint32_t)acc[1]))) return rc;
+        CU(c, cudaMallocAsync(&se_status, (size_t)std::max<uint32_t>(se_num_tiles(R), 1) * sizeof(unsigned long long), st));
+        launch_scan_emit(Rd, c->d_tlen, T, c->d_toff, reinterpret_cast<const uint32_t*>(c->d_shard_acc), c->orientation, TA, keys_a, pa, pb,
+                         se_status, c->d_scalars + 6, d_P, (uint32_t)acc[1], d_err, st); c->n_launches++;
+        mark(c, "scan_emit");
+        CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        CU(c, cudaGetLastError());
+        P = c->h_scalars[2];
+    } else {
+        CU(c, cudaMallocAsync(&npairs, Ra * 4, st)); CU(c, cudaMallocAsync(&pair_off, (Ra + 1) * 4, st)); CU(c, cudaMallocAsync(&read_end, Ra * 4, st));
+        CU(c, cudaMallocAsync(&scan_tmp, scan_tmp_elems(Ra) * 4, st));
+        launch_scan_reads(Rd, c->d_tlen, T, npairs, read_end, TA, d_maxn, c->n_sm, st); c->n_launches++;
+        mark(c, "scan_reads");
+        launch_exclusive_scan(npairs, pair_off, (uint64_t)R, scan_tmp, d_P, st); c->n_launches += 3;
+        mark(c, "pair_offsets");
+        CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        CU(c, cudaGetLastError());
+        P = c->h_scalars[2];
+        // (a uint32 sum of N-op counts can wrap only beyond 2^32 pairs; the CIGAR word limit above excludes that)
+        len_bits = std::max(1, bit_length(c->h_scalars[1])); key_bits = len_bits + gbits;
+        if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
+        if (P > 0) {
+            if ((rc = alloc_pairs(P))) return rc;
+            launch_emit_pairs(Rd, c->d_tlen, c->d_toff, len_bits, c->orientation, pair_off, npairs, read_end, keys_a, pa, pb, d_err, st); c->n_launches++;
+            mark(c, "emit_pairs");
+        }
+    }
+    c->n_pairs = P;
 
     uint32_t J = 0;
     if (P > 0) {
-        uint64_t *keys_a = nullptr, *keys_b = nullptr; uint32_t *vals_a = nullptr, *vals_b = nullptr, *counts = nullptr, *scan_tmp2 = nullptr;
-        PairA* pa = nullptr; PairB* pb = nullptr;
-        const uint32_t nb = rs_num_blocks(P);
-        CU(c, cudaMallocAsync(&keys_a, (size_t)P * 8, st)); CU(c, cudaMallocAsync(&keys_b, (size_t)P * 8, st));
-        CU(c, cudaMallocAsync(&vals_a, (size_t)P * 4, st)); CU(c, cudaMallocAsync(&vals_b, (size_t)P * 4, st));
-        CU(c, cudaMallocAsync(&counts, (size_t)256 * nb * 4, st));
-        CU(c, cudaMallocAsync(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, P)) * 4, st));
-        CU(c, cudaMallocAsync(&pa, (size_t)P * sizeof(PairA), st)); CU(c, cudaMallocAsync(&pb, (size_t)P * sizeof(PairB), st));
-        launch_emit_pairs(Rd, c->d_tlen, c->d_toff, len_bits, c->orientation, pair_off, npairs, read_end, keys_a, pa, pb, d_err, st); c->n_launches++;
-        mark(c, "emit_pairs");
         int which;
         if (P < (1u << 30) && !c->legacy_sort) {
             uint32_t* os_scratch = nullptr;
@@ -513,12 +546,12 @@ int pj_shard_run(pj_ctx* c) {
         if (c->rows_cap < J) { if (c->d_rows) { CU(c, cudaStreamSynchronize(st)); cudaFree(c->d_rows); } c->rows_cap = (size_t)J + J / 4 + 16; CU(c, cudaMalloc(&c->d_rows, c->rows_cap * sizeof(pj_junction))); }
         launch_finalize(J, seg_start, A, G, entropy, c->d_rows, d_err, st); c->n_launches++;
         mark(c, "finalize");
-        CU(c, cudaFreeAsync(keys_a, st)); CU(c, cudaFreeAsync(keys_b, st)); CU(c, cudaFreeAsync(vals_a, st)); CU(c, cudaFreeAsync(vals_b, st));
-        CU(c, cudaFreeAsync(counts, st)); CU(c, cudaFreeAsync(scan_tmp2, st)); CU(c, cudaFreeAsync(pa, st)); CU(c, cudaFreeAsync(pb, st));
         CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
         CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st));
     }
-    CU(c, cudaFreeAsync(npairs, st)); CU(c, cudaFreeAsync(pair_off, st)); CU(c, cudaFreeAsync(read_end, st)); CU(c, cudaFreeAsync(scan_tmp, st));
+    for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pa, (void*)pb, (void*)se_status,
+                    (void*)npairs, (void*)pair_off, (void*)read_end, (void*)scan_tmp})
+        if (p) CU(c, cudaFreeAsync(p, st));
     mark(c, "end");
     CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));

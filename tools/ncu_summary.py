@@ -11,7 +11,7 @@ import re
 import subprocess
 import sys
 
-STAGE_OF = {"k_os_pass": "radix_sort_one_pass", "k_os_hist": "radix_sort_hist", "k_scan_reads": "scan_reads", "k_emit_pairs": "emit_pairs", "k_rs_hist": "radix_sort", "k_rs_scatter": "radix_sort",
+STAGE_OF = {"k_scan_emit": "scan_emit", "k_os_pass": "radix_sort_one_pass", "k_os_hist": "radix_sort_hist", "k_scan_reads": "scan_reads", "k_emit_pairs": "emit_pairs", "k_rs_hist": "radix_sort", "k_rs_scatter": "radix_sort",
             "k_reduce1": "reduce1", "k_match": "match", "k_reduce2": "reduce2", "k_finalize": "finalize", "k_entropy_sum": "entropy",
             "k_entropy_compact": "entropy", "k_seg_heads": "segments", "k_seg_ids": "segments", "k_junc_init": "reduce1"}
 
