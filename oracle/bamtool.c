@@ -3,6 +3,7 @@
  * reference binary (oracle/_ref/portcullis_ref) can read, and to cross-check our own BAM/BAI writer.
  *   bamtool sam2bam in.sam out.bam     (input must already be coordinate sorted)
  *   bamtool index in.bam
+ *   bamtool index_csi in.bam           (writes in.bam.csi)
  *   bamtool view in.bam                (SAM text to stdout)
  */
 #include <stdio.h>
@@ -30,6 +31,9 @@ int main(int argc, char** argv) {
     }
     if (argc >= 3 && strcmp(argv[1], "index") == 0) {
         return sam_index_build(argv[2], 0) == 0 ? 0 : 3;
+    }
+    if (argc >= 3 && strcmp(argv[1], "index_csi") == 0) {
+        return sam_index_build(argv[2], 14) == 0 ? 0 : 3;          /* min_shift 14 -> .csi */
     }
     if (argc >= 3 && strcmp(argv[1], "view") == 0) {
         samFile* in = sam_open(argv[2], "r");

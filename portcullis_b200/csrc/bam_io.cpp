@@ -3,6 +3,7 @@
 #include <zlib.h>
 #include "inflate_fast.hpp"
 #include <cstring>
+#include <climits>
 #include <algorithm>
 #include <fcntl.h>
 #include <unistd.h>
@@ -190,18 +191,65 @@ bool BamFile::load_bai(const std::string& bai_path) {
     return true;
 }
 
+bool BamFile::load_csi(const std::string& csi_path) {
+    MappedFile f;
+    try { f.open(csi_path); } catch (const IoError&) { return false; }
+    std::vector<uint8_t> buf;
+    {   // the whole index is one BGZF stream
+        BgzfStream s(f); s.seek(0);
+        uint8_t tmp[65536]; size_t g;
+        while ((g = s.read(tmp, sizeof tmp)) > 0) buf.insert(buf.end(), tmp, tmp + g);
+    }
+    const uint8_t* p = buf.data(); uint64_t n = buf.size(), o = 0;
+    auto need = [&](uint64_t k) { if (o + k > n) throw IoError("truncated CSI: " + csi_path); };
+    need(16);
+    if (memcmp(p, "CSI\1", 4) != 0) throw IoError("not a CSI index: " + csi_path);
+    const int32_t min_shift = (int32_t)rd32(p + 4), depth = (int32_t)rd32(p + 8); const uint32_t l_aux = rd32(p + 12);
+    if (min_shift < 1 || min_shift > 30 || depth < 1 || depth > 10) throw IoError("unsupported CSI geometry: " + csi_path);
+    o = 16; need(l_aux + 4ull); o += l_aux;
+    const uint32_t n_ref = rd32(p + o); o += 4;
+    auto first_bin = [](int lvl) { return (uint64_t)(((1ull << (3 * lvl)) - 1) / 7); };
+    const uint64_t meta_bin = first_bin(depth + 1) + 1;
+    idx_.assign(n_ref, BamTargetIndex());
+    for (uint32_t r = 0; r < n_ref; r++) {
+        BamTargetIndex& t = idx_[r];
+        t.window_shift = min_shift;
+        need(4); const uint32_t n_bin = rd32(p + o); o += 4;
+        uint64_t first = 0;
+        for (uint32_t b = 0; b < n_bin; b++) {
+            need(16); const uint64_t bin = rd32(p + o); const uint64_t loff = rd64(p + o + 4); const uint32_t n_chunk = rd32(p + o + 12); o += 16;
+            need(16ull * n_chunk);
+            if (bin == meta_bin) {
+                if (n_chunk >= 2) { t.n_mapped = rd64(p + o + 16); t.n_unmapped = rd64(p + o + 24); t.has_counts = true; }
+            } else {
+                for (uint32_t c = 0; c < n_chunk; c++) { const uint64_t beg = rd64(p + o + 16ull * c); if (first == 0 || beg < first) first = beg; }
+                // loffset = linear-index value of the bin's first finest-level window (htslib update_loff)
+                int lvl = depth; while (lvl > 0 && bin < first_bin(lvl)) lvl--;
+                const uint64_t w = (bin - first_bin(lvl)) << (3 * (depth - lvl));
+                if (loff && w < (1ull << 28)) {
+                    if (t.ioffset.size() <= w) t.ioffset.resize((size_t)w + 1, 0);
+                    if (t.ioffset[w] == 0 || loff < t.ioffset[w]) t.ioffset[w] = loff;
+                }
+            }
+            o += 16ull * n_chunk;
+        }
+        t.first_voff = first;
+    }
+    return true;
+}
+
 void BamFile::plan_target(int32_t tid, uint64_t chunk_bytes, std::vector<DecodeTask>& out) const {
     if (tid < 0 || (size_t)tid >= idx_.size()) return;
     const BamTargetIndex& t = idx_[tid];
     if (t.first_voff == 0) return;          // no records on this target
-    const int32_t W = 16384;
+    const int64_t W = 1ll << t.window_shift;
     DecodeTask cur{tid, 0, INT32_MAX, t.first_voff, 0};
     uint64_t cur_c = t.first_voff >> 16;
     for (size_t w = 1; w < t.ioffset.size(); w++) {
         uint64_t v = t.ioffset[w];
         if (v == 0) continue;
         uint64_t c = v >> 16;
-        if (c >= cur_c + chunk_bytes && (int64_t)w * W < (int64_t)INT32_MAX) {
+        if (c >= cur_c + chunk_bytes && v > cur.voff && (int64_t)w * W < (int64_t)INT32_MAX) {
             cur.pos_hi = (int32_t)(w * W); cur.approx_bytes = c - cur_c;
             out.push_back(cur);
             cur = DecodeTask{tid, (int32_t)(w * W), INT32_MAX, v, 0}; cur_c = c;

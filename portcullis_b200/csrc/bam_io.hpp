@@ -54,7 +54,8 @@ struct BamTargetIndex {
     uint64_t first_voff = 0;               // virtual offset of the target's first record (0 = no records)
     uint64_t n_mapped = 0, n_unmapped = 0; // from the metadata pseudo-bin, 0 if absent
     bool has_counts = false;
-    std::vector<uint64_t> ioffset;         // 16 kb linear index
+    std::vector<uint64_t> ioffset;         // linear index: smallest virtual offset of records overlapping each window (0 = none)
+    int window_shift = 14;                 // window = 1 << window_shift bases (16 kb for BAI; CSI min_shift)
 };
 
 struct BamHeader {
@@ -89,6 +90,7 @@ class BamFile {
 public:
     void open(const std::string& bam_path);                 // maps the file and parses the header
     bool load_bai(const std::string& bai_path);             // false if the file is missing
+    bool load_csi(const std::string& csi_path);             // CSI (SAM spec, CSIv1): same planning data rebuilt from the per-bin loffset fields
     const BamHeader& header() const { return hdr_; }
     const std::vector<BamTargetIndex>& index() const { return idx_; }
     bool has_index() const { return !idx_.empty(); }

@@ -135,7 +135,7 @@ int pjh_prep_open(const char* prep_dir, int use_csi, pjh_prep** out) {
         return fail(PJ_EIO, "Prepared data is not complete: " + p->paths.dir);
     try {
         p->bam.open(p->paths.bam);
-        p->indexed = !use_csi && p->bam.load_bai(p->paths.bai);   // CSI: decode falls back to one sequential stream
+        p->indexed = use_csi ? p->bam.load_csi(p->paths.csi) : p->bam.load_bai(p->paths.bai);
         p->fasta.open(p->paths.fasta, p->paths.fai);
     } catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
     *out = p.release();

@@ -14,6 +14,7 @@
 #include "junc_kernels.cuh"
 #include "junc_launch.hpp"
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 
 namespace pjk {
@@ -344,8 +345,6 @@ void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff
 // the longest N op of the shard, which pj_batch_submit tracks while the batches are copied in (k_prescan_cigar).
 // ================================================================================================
 constexpr int SE_THREADS = 256;
-constexpr int SE_ITEMS = 4;
-constexpr int SE_TILE = SE_THREADS * SE_ITEMS;
 constexpr unsigned long long SE_PREFIX = 1ull << 63, SE_AGG = 1ull << 62, SE_MASK = (1ull << 62) - 1ull;
 
 __global__ void __launch_bounds__(256) k_prescan_cigar(const uint32_t* __restrict__ cigar, uint64_t n, uint32_t* __restrict__ max_nlen,
@@ -366,6 +365,7 @@ void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen,
     k_prescan_cigar<<<blocks, 256, 0, st>>>(cigar, n, max_nlen, n_nops);
 }
 
+template <int SE_ITEMS>
 __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
                                                            const uint32_t* __restrict__ max_nlen, int32_t orientation, TargetAcc T,
                                                            uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     if (threadIdx.x < 4) { b_sp[threadIdx.x] = 0; b_us[threadIdx.x] = 0; b_sum[threadIdx.x] = 0; b_mn[threadIdx.x] = INT32_MAX; b_mx[threadIdx.x] = 0; }
     __syncthreads();
+    constexpr int SE_TILE = SE_THREADS * SE_ITEMS;
     const uint32_t tile = s_tile;
     const int64_t base = (int64_t)tile * SE_TILE;
     const int32_t tid_first = R.tid[min(base, R.n - 1)];
@@ -524,7 +525,8 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
     if (e) atomicOr(err, e);
 }
 
-uint32_t se_num_tiles(int64_t n) { return (uint32_t)((n + SE_TILE - 1) / SE_TILE); }
+static int se_items() { static int v = [] { const char* e = getenv("PJ_SE_ITEMS"); int k = e ? atoi(e) : 2; return (k == 1 || k == 2 || k == 4) ? k : 2; }(); return v; }
+uint32_t se_num_tiles(int64_t n) { const int64_t tile = (int64_t)SE_THREADS * se_items(); return (uint32_t)((n + tile - 1) / tile); }
 void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
                       const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, unsigned long long* status, uint32_t* ticket,
                       uint32_t* total_pairs, uint32_t pair_cap, uint32_t* err, cudaStream_t st) {
@@ -532,7 +534,11 @@ void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, co
     const uint32_t nt = se_num_tiles(R.n);
     cudaMemsetAsync(status, 0, (size_t)nt * sizeof(unsigned long long), st);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
-    k_scan_emit<<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err);
+    switch (se_items()) {
+    case 1: k_scan_emit<1><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err); break;
+    case 4: k_scan_emit<4><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err); break;
+    default: k_scan_emit<2><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err); break;
+    }
 }
 
 // ================================================================================================
