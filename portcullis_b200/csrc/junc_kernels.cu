@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
     if (e) atomicOr(err, e);
 }
 
-static int se_items() { static int v = [] { const char* e = getenv("PJ_SE_ITEMS"); int k = e ? atoi(e) : 2; return (k == 1 || k == 2 || k == 4) ? k : 2; }(); return v; }
+static int se_items() { static int v = [] { const char* e = getenv("PJ_SE_ITEMS"); int k = e ? atoi(e) : 4; return (k == 1 || k == 2 || k == 4) ? k : 4; }(); return v; }
 uint32_t se_num_tiles(int64_t n) { const int64_t tile = (int64_t)SE_THREADS * se_items(); return (uint32_t)((n + tile - 1) / tile); }
 void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
                       const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, unsigned long long* status, uint32_t* ticket,
@@ -802,6 +802,82 @@ __global__ void __launch_bounds__(256) k_seg_ids(const uint64_t* __restrict__ ke
 void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st) { if (n) k_seg_heads<<<(n + 255) / 256, 256, 0, st>>>(keys, n, head); }
 void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint32_t* jid, uint32_t* seg_start, uint32_t n_junc, cudaStream_t st) {
     if (n) k_seg_ids<<<(n + 255) / 256, 256, 0, st>>>(keys, n, excl, jid, seg_start, n_junc);
+}
+
+// ================================================================================================
+// single-pass flag scan (decoupled look-back, ticketed tiles of 2048 items): the exclusive prefix of a 0/1 flag per
+// item is consumed right where it is produced, so segmentation and the entropy compaction are one kernel each instead of
+// flag kernel + three scan kernels + consumer kernel.
+// ================================================================================================
+constexpr int FS_THREADS = 512;
+constexpr int FS_ITEMS = 4;
+constexpr int FS_TILE = FS_THREADS * FS_ITEMS;
+
+template <typename F>
+__global__ void __launch_bounds__(FS_THREADS) k_flag_scan(uint32_t n, F f, unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket,
+                                                          uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_tile, s_tot, s_base;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t i0 = tile * FS_TILE + threadIdx.x * FS_ITEMS;          // blocked: thread t owns 4 consecutive items
+    uint32_t fl[FS_ITEMS]; uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < FS_ITEMS; k++) { fl[k] = (i0 + k < n) ? f.flag(i0 + k) : 0u; sum += fl[k]; }
+    uint32_t ex = block_excl_scan(sum, &s_tot);
+    if (threadIdx.x == 0) {
+        const uint32_t tot = s_tot;
+        volatile unsigned long long* st = status + tile;
+        unsigned long long excl = 0;
+        if (tile == 0) *st = (unsigned long long)tot | SE_PREFIX;
+        else {
+            *st = (unsigned long long)tot | SE_AGG;
+            __threadfence();
+            for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
+                volatile const unsigned long long* sp = status + t;
+                unsigned long long v;
+                do { v = *sp; } while ((v >> 62) == 0ull);
+                excl += v & SE_MASK;
+                if (v & SE_PREFIX) break;
+            }
+            *st = ((excl + tot) & SE_MASK) | SE_PREFIX;
+        }
+        s_base = (uint32_t)excl;
+        if ((uint64_t)(tile + 1) * FS_TILE >= n) { *total_out = (uint32_t)(excl + tot); f.finish(n, (uint32_t)(excl + tot)); }
+    }
+    __syncthreads();
+    ex += s_base;
+#pragma unroll
+    for (int k = 0; k < FS_ITEMS; k++) { if (i0 + k < n) f.emit(i0 + k, ex, fl[k]); ex += fl[k]; }
+}
+
+// junction segmentation: flag = first pair of a junction; jid = number of heads up to and including the pair, minus one
+struct SegmentOp {
+    const uint64_t* keys; uint32_t* jid; uint32_t* seg_start;
+    __device__ uint32_t flag(uint32_t i) const { return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u; }
+    __device__ void emit(uint32_t i, uint32_t excl, uint32_t fl) const { const uint32_t j = excl + fl - 1u; jid[i] = j; if (fl) seg_start[j] = i; }
+    __device__ void finish(uint32_t n, uint32_t total) const { seg_start[total] = n; }
+};
+// entropy: flag = emission point of the loop in Junction::calcEntropy; epos = compacted emission indices
+struct EntropyIndexOp {
+    const uint32_t* eflag; uint32_t* eoff; uint32_t* epos;
+    __device__ uint32_t flag(uint32_t i) const { return eflag[i]; }
+    __device__ void emit(uint32_t i, uint32_t excl, uint32_t fl) const { eoff[i] = excl; if (fl) epos[excl] = i; }
+    __device__ void finish(uint32_t, uint32_t) const {}
+};
+uint32_t fs_num_tiles(uint32_t n) { return (n + FS_TILE - 1) / FS_TILE; }
+// scratch: ntiles status words (8 B each) followed by one 4-byte ticket; zeroed here
+void launch_segment(const uint64_t* keys, uint32_t n, uint32_t* jid, uint32_t* seg_start /* n+1 */, uint32_t* n_junc_dev, unsigned long long* scratch, cudaStream_t st) {
+    if (!n) return;
+    const uint32_t nt = fs_num_tiles(n);
+    cudaMemsetAsync(scratch, 0, ((size_t)nt + 1) * 8, st);
+    k_flag_scan<<<nt, FS_THREADS, 0, st>>>(n, SegmentOp{keys, jid, seg_start}, scratch, reinterpret_cast<uint32_t*>(scratch + nt), n_junc_dev);
+}
+void launch_entropy_index(uint32_t n, const uint32_t* eflag, uint32_t* eoff, uint32_t* epos, uint32_t* total_dev, unsigned long long* scratch, cudaStream_t st) {
+    if (!n) return;
+    const uint32_t nt = fs_num_tiles(n);
+    cudaMemsetAsync(scratch, 0, ((size_t)nt + 1) * 8, st);
+    k_flag_scan<<<nt, FS_THREADS, 0, st>>>(n, EntropyIndexOp{eflag, eoff, epos}, scratch, reinterpret_cast<uint32_t*>(scratch + nt), total_dev);
 }
 
 // ================================================================================================

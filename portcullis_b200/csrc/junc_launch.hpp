@@ -41,6 +41,9 @@ int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
 size_t os_scratch_words(uint32_t n, int key_bits);
 int launch_onesweep_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
                          uint32_t* scratch, int n_sm, cudaStream_t st, int* n_launches);
+uint32_t fs_num_tiles(uint32_t n);
+void launch_segment(const uint64_t* keys, uint32_t n, uint32_t* jid, uint32_t* seg_start, uint32_t* n_junc_dev, unsigned long long* scratch, cudaStream_t st);
+void launch_entropy_index(uint32_t n, const uint32_t* eflag, uint32_t* eoff, uint32_t* epos, uint32_t* total_dev, unsigned long long* scratch, cudaStream_t st);
 void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st);
 void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint32_t* jid, uint32_t* seg_start, uint32_t n_junc, cudaStream_t st);
 void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairA* pa, const PairB* pb,

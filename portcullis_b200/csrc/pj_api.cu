@@ -499,15 +499,24 @@ int pj_shard_run(pj_ctx* c) {
         const uint64_t* keys = which ? keys_b : keys_a; const uint32_t* vals = which ? vals_b : vals_a;
         uint32_t* spare_u32 = which ? vals_a : vals_b;        // free again: reused for the head flags / entropy flags
         mark(c, "radix_sort");
-        uint32_t *jid = nullptr, *seg_start = nullptr;
+        uint32_t *jid = nullptr, *seg_start = nullptr; unsigned long long* fs_scratch = nullptr;
         CU(c, cudaMallocAsync(&jid, (size_t)P * 4, st));
-        launch_seg_heads(keys, P, spare_u32, st); c->n_launches++;
-        launch_exclusive_scan(spare_u32, spare_u32, P, scan_tmp2, d_J, st); c->n_launches += 3;
-        CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CU(c, cudaStreamSynchronize(st));
-        J = c->h_scalars[3];
-        CU(c, cudaMallocAsync(&seg_start, ((size_t)J + 1) * 4, st));
-        launch_seg_ids(keys, P, spare_u32, jid, seg_start, J, st); c->n_launches++;
+        CU(c, cudaMallocAsync(&fs_scratch, ((size_t)fs_num_tiles(P) + 1) * 8, st));
+        if (!c->legacy_sort) {
+            CU(c, cudaMallocAsync(&seg_start, ((size_t)P + 1) * 4, st));        // J <= P is only known after the pass
+            launch_segment(keys, P, jid, seg_start, d_J, fs_scratch, st); c->n_launches++;
+            CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+            J = c->h_scalars[3];
+        } else {
+            launch_seg_heads(keys, P, spare_u32, st); c->n_launches++;
+            launch_exclusive_scan(spare_u32, spare_u32, P, scan_tmp2, d_J, st); c->n_launches += 3;
+            CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(c, cudaStreamSynchronize(st));
+            J = c->h_scalars[3];
+            CU(c, cudaMallocAsync(&seg_start, ((size_t)J + 1) * 4, st));
+            launch_seg_ids(keys, P, spare_u32, jid, seg_start, J, st); c->n_launches++;
+        }
         mark(c, "segments");
         // ---- per-junction accumulators: one zero-filled block of uint32 columns ----
         const size_t NCOL = 24; uint32_t* acc = nullptr; uint32_t* jadhist = nullptr; double* entropy = nullptr;
@@ -526,8 +535,11 @@ int pj_shard_run(pj_ctx* c) {
         uint64_t* free_keys = which ? keys_a : keys_b;          // the non-result key buffer: 8 bytes per pair, reused below
         uint32_t* eoff = reinterpret_cast<uint32_t*>(free_keys);
         uint32_t* epos = eoff + P;
-        launch_exclusive_scan(spare_u32, eoff, P, scan_tmp2, d_E, st); c->n_launches += 3;
-        launch_entropy_compact(P, spare_u32, eoff, epos, st); c->n_launches++;
+        if (!c->legacy_sort) { launch_entropy_index(P, spare_u32, eoff, epos, d_E, fs_scratch, st); c->n_launches++; }
+        else {
+            launch_exclusive_scan(spare_u32, eoff, P, scan_tmp2, d_E, st); c->n_launches += 3;
+            launch_entropy_compact(P, spare_u32, eoff, epos, st); c->n_launches++;
+        }
         launch_entropy_sum(J, seg_start, eoff, epos, entropy, st); c->n_launches++;
         mark(c, "entropy");
         Genome G{c->d_g2, c->d_gx, c->d_g4, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->n_zero_code};
@@ -546,7 +558,7 @@ int pj_shard_run(pj_ctx* c) {
         if (c->rows_cap < J) { if (c->d_rows) { CU(c, cudaStreamSynchronize(st)); cudaFree(c->d_rows); } c->rows_cap = (size_t)J + J / 4 + 16; CU(c, cudaMalloc(&c->d_rows, c->rows_cap * sizeof(pj_junction))); }
         launch_finalize(J, seg_start, A, G, entropy, c->d_rows, d_err, st); c->n_launches++;
         mark(c, "finalize");
-        CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
+        CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(fs_scratch, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
         CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st));
     }
     for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pa, (void*)pb, (void*)se_status,
