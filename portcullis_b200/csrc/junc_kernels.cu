@@ -907,7 +907,7 @@ struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { r
 // ================================================================================================
 // k_reduce1: stage-1 reductions per junction (SURVEY §8 "reduction algebra" stage 1)
 // ================================================================================================
-__global__ void __launch_bounds__(256) k_reduce1(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+__global__ void __launch_bounds__(512) k_reduce1(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                   const PairA* __restrict__ pa, const PairB* __restrict__ pb, int32_t ppcheck,
                                                   JuncAcc A, uint32_t* __restrict__ eflag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -947,6 +947,48 @@ __global__ void __launch_bounds__(256) k_reduce1(uint32_t n, const uint32_t* __r
     c0 = seg_reduce(c0, sc, OpAdd()); c1 = seg_reduce(c1, sc, OpAdd()); c2 = seg_reduce(c2, sc, OpAdd());
     lmin = seg_reduce(lmin, sc, OpMin()); rmax = seg_reduce(rmax, sc, OpMax());
     anc = seg_reduce(anc, sc, OpMax()); up = seg_reduce(up, sc, OpMax()); down = seg_reduce(down, sc, OpMax());
+    // A block whose pairs all belong to ONE junction (deep junctions span thousands of blocks) first combines its warps in
+    // shared memory, so the junction's counters see one atomic per block and field instead of one per warp.
+    __shared__ uint32_t part[32][17];
+    __shared__ uint32_t s_j0;
+    if (threadIdx.x == 0) s_j0 = j;
+    __syncthreads();
+    const bool uniform = __syncthreads_and(!ok || j == s_j0) != 0;
+    if (uniform) {
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const uint32_t okm = __ballot_sync(FULL, ok);
+        if (okm ? (ok && sc.tail) : lane == 31) {      // exactly one writer per warp (an all-invalid warp publishes neutral values)
+            uint32_t* p = part[w];
+            p[0] = c0 & 63u; p[1] = (c0 >> 6) & 63u; p[2] = (c0 >> 12) & 63u; p[3] = (c0 >> 18) & 63u; p[4] = (c0 >> 24) & 63u;
+            p[5] = c1 & 63u; p[6] = (c1 >> 6) & 63u; p[7] = (c1 >> 12) & 63u; p[8] = (c1 >> 18) & 63u; p[9] = (c1 >> 24) & 63u;
+            p[10] = c2 & 63u; p[11] = (c2 >> 6) & 63u;
+            p[12] = (uint32_t)lmin; p[13] = (uint32_t)rmax; p[14] = anc; p[15] = up; p[16] = down;
+        }
+        __syncthreads();
+        if (w == 0) {
+            const bool has = lane < nw;
+            uint32_t v[17];
+#pragma unroll
+            for (int f = 0; f < 17; f++) v[f] = has ? part[lane][f] : (f == 12 ? (uint32_t)INT32_MAX : f == 13 ? (uint32_t)INT32_MIN : 0u);
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+#pragma unroll
+                for (int f = 0; f < 12; f++) v[f] += __shfl_xor_sync(FULL, v[f], o);
+                v[12] = (uint32_t)min((int32_t)v[12], (int32_t)__shfl_xor_sync(FULL, v[12], o));
+                v[13] = (uint32_t)max((int32_t)v[13], (int32_t)__shfl_xor_sync(FULL, v[13], o));
+                v[14] = max(v[14], __shfl_xor_sync(FULL, v[14], o)); v[15] = max(v[15], __shfl_xor_sync(FULL, v[15], o)); v[16] = max(v[16], __shfl_xor_sync(FULL, v[16], o));
+            }
+            const uint32_t jj = s_j0;
+            if (lane == 0 && jj != 0xffffffffu) {
+                uint32_t* const sums[12] = {A.r1p, A.r1n, A.r2p, A.r2n, A.ms, A.um, A.bpp, A.ppp, A.rel, A.xsp, A.xsn, A.dist};
+#pragma unroll
+                for (int f = 0; f < 12; f++) if (v[f]) atomicAdd(sums[f] + jj, v[f]);
+                atomicMin(A.left + jj, (int32_t)v[12]); atomicMax(A.right + jj, (int32_t)v[13]);
+                atomicMax(A.anc + jj, v[14]); atomicMax(A.up + jj, v[15]); atomicMax(A.down + jj, v[16]);
+            }
+        }
+        return;
+    }
     if (ok && sc.tail) {
         uint32_t v;
         if ((v = c0 & 63u)) atomicAdd(A.r1p + j, v);
@@ -988,7 +1030,7 @@ void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t
 }
 void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, int32_t ppcheck,
                     const JuncAcc& A, uint32_t* eflag, cudaStream_t st) {
-    if (n) k_reduce1<<<(n + 255) / 256, 256, 0, st>>>(n, vals, jid, pa, pb, ppcheck, A, eflag);
+    if (n) k_reduce1<<<(n + 511) / 512, 512, 0, st>>>(n, vals, jid, pa, pb, ppcheck, A, eflag);
 }
 
 // ================================================================================================
@@ -1268,7 +1310,7 @@ void launch_match(uint32_t n, int group, const uint32_t* vals, const uint32_t* j
 // ================================================================================================
 // k_reduce2: Junction::calcMismatchStats (junction.cc:862-909) as a segmented reduction
 // ================================================================================================
-__global__ void __launch_bounds__(256) k_reduce2(uint32_t n, const uint32_t* __restrict__ jid, const uint4* __restrict__ pm, JuncAcc A) {
+__global__ void __launch_bounds__(512) k_reduce2(uint32_t n, const uint32_t* __restrict__ jid, const uint4* __restrict__ pm, JuncAcc A) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool ok = i < n;
@@ -1283,6 +1325,35 @@ __global__ void __launch_bounds__(256) k_reduce2(uint32_t n, const uint32_t* __r
     const SegCtx sc = seg_ctx(j, lane);
     mmes = seg_reduce(mmes, sc, OpMax()); mism = seg_reduce(mism, sc, OpAdd());
     firstmm = seg_reduce(firstmm, sc, OpMin()); maxmin = seg_reduce(maxmin, sc, OpMax());
+    // single-junction blocks (deep junctions) combine in shared memory first: one atomic per block and field / histogram bin
+    __shared__ uint32_t part[32][4];
+    __shared__ uint32_t hist[PJ_NB_JAD + 1];
+    __shared__ uint32_t s_j0;
+    if (threadIdx.x == 0) s_j0 = j;
+    if (threadIdx.x <= PJ_NB_JAD) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const bool uniform = __syncthreads_and(!ok || j == s_j0) != 0;
+    if (uniform) {
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if (ok) atomicAdd(&hist[bin], 1u);
+        const uint32_t okm = __ballot_sync(FULL, ok);
+        if (okm ? (ok && sc.tail) : lane == 31) { part[w][0] = mmes; part[w][1] = mism; part[w][2] = firstmm; part[w][3] = maxmin; }
+        __syncthreads();
+        const uint32_t jj = s_j0;
+        if (jj == 0xffffffffu) return;
+        if (threadIdx.x <= PJ_NB_JAD && hist[threadIdx.x]) atomicAdd(A.jadhist + (size_t)jj * (PJ_NB_JAD + 1) + threadIdx.x, hist[threadIdx.x]);
+        if (w == 1) {
+            const bool has = lane < nw;
+            uint32_t a = has ? part[lane][0] : 0u, b = has ? part[lane][1] : 0u, c = has ? part[lane][2] : 0xffffffffu, d = has ? part[lane][3] : 0u;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                a = max(a, __shfl_xor_sync(FULL, a, o)); b += __shfl_xor_sync(FULL, b, o);
+                c = min(c, __shfl_xor_sync(FULL, c, o)); d = max(d, __shfl_xor_sync(FULL, d, o));
+            }
+            if (lane == 0) { atomicMax(A.maxmmes + jj, a); if (b) atomicAdd(A.mism + jj, b); atomicMin(A.firstmm + jj, c); atomicMax(A.maxminmatch + jj, d); }
+        }
+        return;
+    }
     // JAD histogram: one atomic per distinct (junction, bin) in the warp
     const uint32_t hk = ok ? (j * 32u + bin) : 0xffffffffu;
     const uint32_t m = __match_any_sync(FULL, hk);
@@ -1295,7 +1366,7 @@ __global__ void __launch_bounds__(256) k_reduce2(uint32_t n, const uint32_t* __r
     }
 }
 void launch_reduce2(uint32_t n, const uint32_t* jid, const uint4* pm, const JuncAcc& A, cudaStream_t st) {
-    if (n) k_reduce2<<<(n + 255) / 256, 256, 0, st>>>(n, jid, pm, A);
+    if (n) k_reduce2<<<(n + 511) / 512, 512, 0, st>>>(n, jid, pm, A);
 }
 
 // ================================================================================================
