@@ -1,11 +1,11 @@
 // junc_kernels.cu — hand-written sm_100a kernels of the junc hot path.
 //
 // Pipeline over one shard (all alignment columns resident in HBM):
-//   k_scan_reads      per read : N-op count, reference span, per-target scalars (A1)
-//   scan              exclusive prefix of N-op counts -> pair slots
-//   k_emit_pairs      per read : CIGAR walk, one (key, PairA, PairB) record per N op (A2, A3, A6 flags)
-//   radix sort        stable LSD sort of (key, pair index): junction order, BAM order inside a junction
-//   k_seg_heads/scan  junction ids and segment starts
+//   k_prescan_cigar   at submit : longest N op and N-op count of the shard (key width, pair capacity)
+//   k_scan_emit       per read : N-op count, reference span, per-target scalars (A1); pair slots by look-back scan;
+//                     CIGAR walk, one (key, PairA..PairD) record per N op (A2, A3, A6 flags)
+//   k_os_*            one-sweep stable LSD radix sort of (key, pair index): junction order, BAM order inside a junction
+//   k_flag_scan       junction ids and segment starts (single pass)
 //   k_reduce1         per pair : warp-shuffle segmented reduce of the integer metrics + entropy run boundaries
 //   k_entropy_*       run-length terms -> fp64 entropy per junction (A5, quirk Q1)
 //   k_match           warp per pair : junction-wide anchor window walk against the packed genome (A10)
@@ -176,167 +176,6 @@ void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint
 }
 
 // ================================================================================================
-// k_scan_reads: per read N-op count, reference span and the per-target scalars of findJuncs
-// (src/junction_builder.cc:333-343, 352-356).  Record visibility = quirk Q13.
-// ================================================================================================
-__global__ void __launch_bounds__(256) k_scan_reads(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets,
-                                                     uint32_t* __restrict__ npairs, int32_t* __restrict__ read_end,
-                                                     TargetAcc T, uint32_t* __restrict__ max_nlen, int64_t per_warp) {
-    // Persistent grid: every warp owns a contiguous run of `per_warp` records (a multiple of 32) and keeps the running
-    // per-target scalars of its current target in lane 0's registers, so the same-address atomics that the coordinate
-    // order would otherwise pile onto one target are issued once per warp and target instead of once per 32 records.
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t beg = warp * per_warp, end = min(R.n, beg + per_warp);
-    int32_t cur = -1; unsigned long long a_sp = 0, a_us = 0, a_sum = 0; int32_t a_mn = INT32_MAX, a_mx = 0; uint32_t a_maxn = 0;
-    auto flush = [&]() {
-        if (lane == 0 && cur >= 0 && (a_sp | a_us)) {
-            if (a_sp) atomicAdd(T.spliced + cur, a_sp);
-            if (a_us) atomicAdd(T.unspliced + cur, a_us);
-            atomicAdd(T.sumq + cur, a_sum); atomicMin(T.minq + cur, a_mn); atomicMax(T.maxq + cur, a_mx);
-        }
-        a_sp = a_us = a_sum = 0; a_mn = INT32_MAX; a_mx = 0;
-    };
-    for (int64_t base = beg; base < end; base += 32) {
-        const int64_t i = base + lane;
-        const bool valid = i < end;
-        bool vis = false; int32_t tid = -2, lq = 0; uint32_t nN = 0, maxN = 0;
-        if (valid) {
-            tid = R.tid[i];
-            const int32_t pos = R.pos[i];
-            const uint32_t c0 = R.cigar_off[i], c1 = R.cigar_off[i + 1];
-            int64_t rlen = 0;
-            for (uint32_t c = c0; c < c1; c++) {
-                const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
-                if (op_ref(op)) rlen += cig_len(w);
-                if (op == OP_N) { nN++; maxN = max(maxN, (uint32_t)cig_len(w)); }
-            }
-            read_end[i] = (int32_t)(pos + rlen - 1);
-            lq = R.l_qseq[i];
-            if (tid >= 0 && tid < n_targets) {
-                const int64_t endpos = (!(R.flag[i] & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
-                vis = pos < tlen[tid] && endpos > 0;
-            }
-            if (!vis) nN = 0;
-            npairs[i] = nN;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) maxN = max(maxN, __shfl_xor_sync(FULL, maxN, o));
-        a_maxn = max(a_maxn, maxN);
-        // lanes outside the run or invisible contribute nothing; a warp is "uniform" when its visible lanes share one target
-        const uint32_t vmask = __ballot_sync(FULL, vis);
-        if (vmask == 0) continue;
-        const int32_t t0 = __shfl_sync(FULL, tid, __ffs(vmask) - 1);
-        if (__all_sync(FULL, !vis || tid == t0)) {
-            const uint32_t sp = __popc(__ballot_sync(FULL, vis && nN > 0));
-            const uint32_t us = __popc(vmask) - sp;
-            unsigned long long s = vis ? (unsigned long long)(long long)lq : 0ull;
-            int32_t mn = vis ? lq : INT32_MAX, mxq = vis ? lq : 0;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                s += __shfl_xor_sync(FULL, s, o);
-                mn = min(mn, __shfl_xor_sync(FULL, mn, o));
-                mxq = max(mxq, __shfl_xor_sync(FULL, mxq, o));
-            }
-            if (t0 != cur) { flush(); cur = t0; }
-            a_sp += sp; a_us += us; a_sum += s; a_mn = min(a_mn, mn); a_mx = max(a_mx, mxq);
-        } else if (vis) {                                  // a target boundary inside the warp: per-lane atomics (rare)
-            if (nN > 0) atomicAdd(T.spliced + tid, 1ull); else atomicAdd(T.unspliced + tid, 1ull);
-            atomicAdd(T.sumq + tid, (unsigned long long)(long long)lq); atomicMin(T.minq + tid, lq); atomicMax(T.maxq + tid, lq);
-        }
-    }
-    flush();
-    if (lane == 0 && a_maxn) atomicMax(max_nlen, a_maxn);
-}
-
-void launch_scan_reads(const Reads& R, const int32_t* tlen, int32_t n_targets, uint32_t* npairs, int32_t* read_end,
-                       const TargetAcc& T, uint32_t* max_nlen, int n_sm, cudaStream_t st) {
-    if (R.n <= 0) return;
-    const int64_t blocks = (int64_t)n_sm * 8, warps = blocks * 8;               // 8 resident CTAs of 256 threads per SM
-    int64_t per_warp = ((R.n + warps - 1) / warps + 31) / 32 * 32;
-    if (per_warp < 32) per_warp = 32;
-    const int64_t used_blocks = ((R.n + per_warp - 1) / per_warp + 7) / 8;
-    k_scan_reads<<<(unsigned)used_blocks, 256, 0, st>>>(R, tlen, n_targets, npairs, read_end, T, max_nlen, per_warp);
-}
-
-// ================================================================================================
-// k_emit_pairs: JunctionSystem::addJunctions (lib/src/junction_system.cc:140-210) with the recursion unrolled
-// into a loop, plus the per-read parts of addJunctionAlignment / calcAlignmentStats (junction.cc:477-502, 755-814).
-// ================================================================================================
-__global__ void __launch_bounds__(256) k_emit_pairs(Reads R, const int32_t* __restrict__ tlen, const uint64_t* __restrict__ toff,
-                                                     int32_t len_bits, int32_t orientation,
-                                                     const uint32_t* __restrict__ pair_off, const uint32_t* __restrict__ npairs,
-                                                     const int32_t* __restrict__ read_end,
-                                                     uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
-                                                     uint32_t* __restrict__ err) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R.n) return;
-    const uint32_t nN = npairs[i];
-    if (nN == 0) return;
-    const int32_t tid = R.tid[i], pos = R.pos[i], refLen = tlen[tid];
-    const uint32_t flag = R.flag[i];
-    const uint32_t* cg = R.cigar + R.cigar_off[i];
-    const int32_t n = (int32_t)(R.cigar_off[i + 1] - R.cigar_off[i]);
-    const uint8_t xs = R.xs[i];
-    uint32_t bits = 0;
-    if (flag & 0x40u) bits |= PB_R1;
-    if (flag & 0x10u) bits |= PB_REV;
-    if (nN > 1) bits |= PB_MS;
-    if (R.mapq[i] >= PJ_MAP_QUALITY_THRESHOLD) bits |= PB_UM;
-    if (flag & 0x2u) bits |= PB_BPP;
-    if (portcullis_proper_pair(flag, tid, R.mtid[i], pos, R.mpos[i], orientation)) bits |= PB_PPP;
-    if (xs == '+') bits |= PB_XSP; else if (xs == '-') bits |= PB_XSN;
-    const int32_t rend_read = read_end[i];
-    const uint64_t tbase = toff[tid];
-    uint32_t slot = pair_off[i], e = 0;
-
-    int32_t lStart = pos, lEndExc = pos;
-    for (int32_t c = 0; c < n; c++) {
-        const uint32_t w = __ldg(cg + c), op = cig_op(w); const int32_t L = cig_len(w);
-        if (op == OP_N) {
-            int32_t rStart = lEndExc + L, rEndExc = rStart;
-            int32_t j = c + 1;
-            while (j < n && rEndExc <= refLen) {
-                const uint32_t w2 = __ldg(cg + j); if (cig_op(w2) == OP_N) break;
-                if (op_ref(cig_op(w2))) rEndExc += cig_len(w2);
-                j++;
-            }
-            bool clamped = false;
-            if (rStart - 1 >= refLen) { rStart = refLen - 1; clamped = true; }
-            if (rEndExc - 1 >= refLen) { rEndExc = refLen; clamped = true; }
-            const int32_t start = lEndExc, end = rStart - 1, rend = rEndExc - 1;
-            if (lStart > start || rend < end) e |= ERR_ANCHOR_ORDER;
-            if (start < 0 || start > refLen - 2 || end < start - 1) e |= ERR_START_RANGE;
-            const uint64_t sz = (uint64_t)(uint32_t)(end - start + 1);
-            if (sz >> len_bits) e |= ERR_KEY_OVERFLOW;
-            // nbUpstreamJunctions / nbDownstreamJunctions contribution of this read (junction.cc:795-812)
-            uint32_t up = 0, down = 0;
-            if (nN > 1 || clamped) {                       // a lone, unclamped N op ends exactly at end + 1: neither up nor down
-                int32_t p = pos;
-                for (int32_t k = 0; k < n; k++) {
-                    const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
-                    if (op_ref(o3)) p += cig_len(w3);
-                    if (o3 == OP_N) { if (p < start) up++; else if (p > end + 1) down++; }
-                }
-            }
-            keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
-            pa[slot] = PairA{(uint32_t)i, lStart, rend, pos};
-            pb[slot] = PairB{rend_read, bits, (up << 16) | (down & 0xffffu), start};
-            slot++;
-            if (j < n) { lStart = rStart; lEndExc = rStart; } else break;
-        } else if (op_ref(op)) lEndExc += L;
-    }
-    if (e) atomicOr(err, e);
-}
-
-void launch_emit_pairs(const Reads& R, const int32_t* tlen, const uint64_t* toff, int32_t len_bits, int32_t orientation,
-                       const uint32_t* pair_off, const uint32_t* npairs, const int32_t* read_end,
-                       uint64_t* keys, PairA* pa, PairB* pb, uint32_t* err, cudaStream_t st) {
-    if (R.n <= 0) return;
-    k_emit_pairs<<<(unsigned)((R.n + 255) / 256), 256, 0, st>>>(R, tlen, toff, len_bits, orientation, pair_off, npairs, read_end, keys, pa, pb, err);
-}
-
-// ================================================================================================
 // k_scan_emit: k_scan_reads + the prefix scan of the N-op counts + k_emit_pairs in ONE pass over the records.
 // A tile of 1024 records is scanned (N-op counts, reference spans, per-target scalars), its pair slots come from a
 // block scan plus a decoupled look-back over per-tile status words (tiles take their index from an atomic ticket),
@@ -369,6 +208,7 @@ template <int SE_ITEMS>
 __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
                                                            const uint32_t* __restrict__ max_nlen, int32_t orientation, TargetAcc T,
                                                            uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
+                                                           PairC* __restrict__ pc, PairD* __restrict__ pd,
                                                            unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket,
                                                            uint32_t* __restrict__ total_pairs, uint32_t pair_cap, uint32_t* __restrict__ err) {
     __shared__ uint32_t s_tile, s_tot;
@@ -385,11 +225,11 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
     const int32_t tid_first = R.tid[min(base, R.n - 1)];
     const int32_t len_bits = max(1, 32 - __clz((int)__ldg(max_nlen)));
     // ---- phase A: scan the tile's records ----
-    uint32_t cnt[SE_ITEMS]; int32_t rend[SE_ITEMS];
+    uint32_t cnt[SE_ITEMS]; int32_t rend[SE_ITEMS]; bool zeron[SE_ITEMS];
 #pragma unroll
     for (int r = 0; r < SE_ITEMS; r++) {
         const int64_t i = base + r * SE_THREADS + threadIdx.x;
-        bool vis = false; int32_t tid = -2, lq = 0; uint32_t nN = 0; rend[r] = 0;
+        bool vis = false; int32_t tid = -2, lq = 0; uint32_t nN = 0; rend[r] = 0; zeron[r] = false;
         if (i < R.n) {
             tid = R.tid[i];
             const int32_t pos = R.pos[i];
@@ -398,7 +238,7 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
             for (uint32_t c = c0; c < c1; c++) {
                 const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
                 if (op_ref(op)) rlen += cig_len(w);
-                nN += (op == OP_N);
+                if (op == OP_N) { nN++; if (cig_len(w) == 0) zeron[r] = true; }
             }
             rend[r] = (int32_t)(pos + rlen - 1);
             lq = R.l_qseq[i];
@@ -486,7 +326,18 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
         if (portcullis_proper_pair(flag, tid, R.mtid[i], pos, R.mpos[i], orientation)) bits |= PB_PPP;
         if (xs == '+') bits |= PB_XSP; else if (xs == '-') bits |= PB_XSN;
         const uint64_t tbase = toff[tid];
+        // getQuerySeqAfterClipping (bam_alignment.cc:256-264), quirk Q3: only a FIRST / LAST op of type S clips
+        const int32_t lq = R.l_qseq[i];
+        const uint32_t wf = __ldg(cg), wl = __ldg(cg + n - 1);
+        int32_t ds = cig_op(wf) == OP_S ? cig_len(wf) : 0; const int32_t de = cig_op(wl) == OP_S ? cig_len(wl) : 0;
+        if (ds > lq) ds = lq;
+        int64_t qs = (int64_t)lq - ds - de + 1; if (qs > lq - ds) qs = lq - ds; if (qs < 0) qs = 0;
+        const uint64_t so = R.seq_off[i];
+        if (lq > 1 && (int64_t)(R.seq_off[i + 1] - so) < (int64_t)((lq + 1) >> 1)) e |= ERR_SEQ_MISSING;
+        const uint32_t cig0 = R.cigar_off[i];
         int32_t lStart = pos, lEndExc = pos;
+        int32_t p = pos, qpos = 0;            // plain reference / query position at the start of op c (calcAlignmentStats / getPadded* walks)
+        uint32_t kN = 0, a_eq = 0;            // N ops seen so far; how many of them end exactly at p
         for (int32_t c = 0; c < n; c++) {
             const uint32_t w = __ldg(cg + c), op = cig_op(w); const int32_t L = cig_len(w);
             if (op == OP_N) {
@@ -505,21 +356,30 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
                 if (start < 0 || start > refLen - 2 || end < start - 1) e |= ERR_START_RANGE;
                 const uint64_t sz = (uint64_t)(uint32_t)(end - start + 1);
                 if (sz >> len_bits) e |= ERR_KEY_OVERFLOW;
-                uint32_t up = 0, down = 0;
-                if (nN > 1 || clamped) {                       // a lone, unclamped N op ends exactly at end + 1: neither up nor down
-                    int32_t p = pos;
+                // nbUpstreamJunctions / nbDownstreamJunctions contribution of this read (junction.cc:795-812): N ops whose end lies
+                // before the intron start / beyond its end + 1.  Ends are non-decreasing along the read, so with positive-length
+                // N ops and no clamping the counts follow from the op's rank; degenerate CIGARs take the literal loop.
+                uint32_t up, down;
+                if (zeron[r] || clamped || start != p) {
+                    up = 0; down = 0; int32_t pp = pos;
                     for (int32_t k = 0; k < n; k++) {
                         const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
-                        if (op_ref(o3)) p += cig_len(w3);
-                        if (o3 == OP_N) { if (p < start) up++; else if (p > end + 1) down++; }
+                        if (op_ref(o3)) pp += cig_len(w3);
+                        if (o3 == OP_N) { if (pp < start) up++; else if (pp > end + 1) down++; }
                     }
-                }
+                } else { up = kN - a_eq; down = nN - 1u - kN; }
                 keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
                 pa[slot] = PairA{(uint32_t)i, lStart, rendj, pos};
                 pb[slot] = PairB{rend[r], bits, (up << 16) | (down & 0xffffu), start};
+                pc[slot] = PairC{so * 2 + (uint64_t)ds, cig0 + (uint32_t)c, qpos};
+                pd[slot] = PairD{(int32_t)qs, lq, (uint32_t)c | ((uint32_t)(n - 1 - c) << 16), 0u};
                 slot++;
+                kN++; p += L; a_eq = L > 0 ? 1u : a_eq + 1u;
                 if (j < n) { lStart = rStart; lEndExc = rStart; } else break;
-            } else if (op_ref(op)) lEndExc += L;
+            } else {
+                if (op_ref(op)) { lEndExc += L; if (L > 0) { p += L; a_eq = 0; } }
+                if (op_query(op)) qpos += L;
+            }
         }
     }
     if (e) atomicOr(err, e);
@@ -528,16 +388,16 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
 static int se_items() { static int v = [] { const char* e = getenv("PJ_SE_ITEMS"); int k = e ? atoi(e) : 4; return (k == 1 || k == 2 || k == 4) ? k : 4; }(); return v; }
 uint32_t se_num_tiles(int64_t n) { const int64_t tile = (int64_t)SE_THREADS * se_items(); return (uint32_t)((n + tile - 1) / tile); }
 void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
-                      const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, unsigned long long* status, uint32_t* ticket,
+                      const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, PairC* pc, PairD* pd, unsigned long long* status, uint32_t* ticket,
                       uint32_t* total_pairs, uint32_t pair_cap, uint32_t* err, cudaStream_t st) {
     if (R.n <= 0) return;
     const uint32_t nt = se_num_tiles(R.n);
     cudaMemsetAsync(status, 0, (size_t)nt * sizeof(unsigned long long), st);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     switch (se_items()) {
-    case 1: k_scan_emit<1><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err); break;
-    case 4: k_scan_emit<4><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err); break;
-    default: k_scan_emit<2><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, status, ticket, total_pairs, pair_cap, err); break;
+    case 1: k_scan_emit<1><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, pc, pd, status, ticket, total_pairs, pair_cap, err); break;
+    case 4: k_scan_emit<4><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, pc, pd, status, ticket, total_pairs, pair_cap, err); break;
+    default: k_scan_emit<2><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, pc, pd, status, ticket, total_pairs, pair_cap, err); break;
     }
 }
 
@@ -1166,13 +1026,27 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome&
 // and every op the right walk accepts starts at or after rightStart > leftEnd, so the two walks touch disjoint ops while
 // rPos / qPos accumulate identically (bam_alignment.cc:349-399).
 template <int G>
-__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, uint64_t gbase, int64_t glen, const uint32_t* __restrict__ cg, int32_t n_cig,
-                                               int32_t pos, const uint8_t* __restrict__ seq4, uint64_t seq_nib0, int32_t qsize,
+__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, uint64_t gbase, int64_t glen,
+                                               const uint32_t* __restrict__ cgn /* this junction's N op */, int32_t ops_before, int32_t ops_after,
+                                               int32_t start, int32_t qpos_n, const uint8_t* __restrict__ seq4, uint64_t seq_nib0, int32_t qsize,
                                                int32_t left, int32_t leftEnd, int32_t rightStart, int32_t right, int gl, uint32_t& err,
                                                uint32_t& cols_l, uint32_t& cols_r) {
     PairStats r{0u, 0u, -1, INT32_MAX};
     const int col = threadIdx.x;
-    int32_t qPos = 0, rPos = pos;
+    // The reference walks the CIGAR from its first op and skips, op by op, everything that starts before the window
+    // (bam_alignment.cc:353-357).  Reference positions never decrease along the CIGAR, so the first op it does NOT skip is found
+    // by stepping BACK from this junction's N op while the op still starts at or after `left`; the forward walk below then
+    // starts there with the same rPos / qPos the reference would have.  A long read is no longer re-walked for each of its introns.
+    int32_t rPos = start, qPos = qpos_n, back = 0;
+    while (back < ops_before) {
+        const uint32_t w = __ldg(cgn - (back + 1)), op = cig_op(w); const int32_t L = cig_len(w);
+        const int32_t rs = rPos - (op_ref(op) ? L : 0);
+        if (rs < left) break;
+        rPos = rs; if (op_query(op)) qPos -= L;
+        back++;
+    }
+    const uint32_t* cg = cgn - back;
+    const int32_t n_cig = back + 1 + ops_after;
     int side = 0; int32_t wstart = left, wend = leftEnd;
     uint32_t cols = 0; int nq = 0;
     cols_l = 0; cols_r = 0;
@@ -1240,6 +1114,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, 
 template <int G>
 __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairA* __restrict__ pa, const PairB* __restrict__ pb,
+                                                const PairC* __restrict__ pc, const PairD* __restrict__ pd,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
     __shared__ MatchQueue Q;
     const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
@@ -1247,32 +1122,23 @@ __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __res
     if (i >= n) return;                                              // whole groups leave together; no block-wide barrier is used
     const uint32_t j = jid[i];
     const uint32_t idx = vals[i];
-    const PairA a = pa[idx]; const PairB b = pb[idx];
+    const PairA a = pa[idx]; const PairB b = pb[idx]; const PairC c = pc[idx]; const PairD d = pd[idx];
     const int32_t start = b.start, end = A.end[j], left = A.left[j], right = A.right[j];
     const int32_t tid = A.tid[j];
-    const int32_t lq = R.l_qseq[a.rid];
+    const int32_t lq = d.lq;
     uint32_t err = 0, mmes, minMatch, nbMism;
     const int32_t leftEnd = start - 1, rightStart = end + 1;
     if (lq <= 1) {                                                    // junction.cc:168-185
         const uint32_t um = (uint32_t)(leftEnd - left + 1), dm = (uint32_t)(right - rightStart + 1);
         nbMism = 0; minMatch = 0; mmes = min(um, dm);
     } else {
-        const uint32_t c0 = R.cigar_off[a.rid];
-        const uint32_t* cg = R.cigar + c0;
-        const int32_t n_cig = (int32_t)(R.cigar_off[a.rid + 1] - c0);
-        const uint64_t so = R.seq_off[a.rid];
-        if ((int64_t)(R.seq_off[a.rid + 1] - so) < (int64_t)((lq + 1) >> 1)) err |= ERR_SEQ_MISSING;
-        // getQuerySeqAfterClipping (bam_alignment.cc:256-264), quirk Q3: only a FIRST / LAST op of type S clips
-        const uint32_t wf = __ldg(cg), wl = __ldg(cg + n_cig - 1);
-        int32_t ds = cig_op(wf) == OP_S ? cig_len(wf) : 0, de = cig_op(wl) == OP_S ? cig_len(wl) : 0;
-        if (ds > lq) ds = lq;
-        int64_t qs = (int64_t)lq - ds - de + 1; if (qs > lq - ds) qs = lq - ds; if (qs < 0) qs = 0;
         const int64_t glen = Gn.glen[tid];
         if (left > b.read_end || leftEnd < a.pos || rightStart > b.read_end || right < a.pos) err |= ERR_NO_PRESENCE;
         if (glen < 0) err |= ERR_GENOME_RANGE;
         PairStats S{0u, 0u, -1, INT32_MAX}; uint32_t cols_l = 0, cols_r = 0;
         if (!err) {
-            S = walk_pair<G>(Q, Gn, Gn.goff[tid], glen, cg, n_cig, a.pos, R.seq4, so * 2 + (uint64_t)ds, (int32_t)qs, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
+            S = walk_pair<G>(Q, Gn, Gn.goff[tid], glen, R.cigar + c.cig_abs, (int32_t)(d.nops & 0xffffu), (int32_t)(d.nops >> 16), start, c.qpos_n,
+                             R.seq4, c.seq_nib0, d.qsize, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
             if (cols_l == 0 || cols_r == 0) err |= ERR_EMPTY_ANCHOR;
         }
         const uint32_t upMatches = cols_l - S.mism_l, downMatches = cols_r - S.mism_r;
@@ -1289,21 +1155,21 @@ __global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __res
 }
 
 template <int G>
-static void launch_match_g(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& Gn,
+static void launch_match_g(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const PairC* pc, const PairD* pd, const Reads& R, const Genome& Gn,
                            const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     const uint64_t threads = (uint64_t)n * G;
-    k_match<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pa, pb, R, Gn, A, pm, err);
+    k_match<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err);
 }
-void launch_match(uint32_t n, int group, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const Reads& R, const Genome& Gn,
+void launch_match(uint32_t n, int group, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const PairC* pc, const PairD* pd, const Reads& R, const Genome& Gn,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     if (!n) return;
     switch (group) {
-    case 1: launch_match_g<1>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
-    case 2: launch_match_g<2>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
-    case 4: launch_match_g<4>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
-    case 8: launch_match_g<8>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
-    case 16: launch_match_g<16>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
-    default: launch_match_g<32>(n, vals, jid, pa, pb, R, Gn, A, pm, err, st); break;
+    case 1: launch_match_g<1>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
+    case 2: launch_match_g<2>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
+    case 4: launch_match_g<4>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
+    case 8: launch_match_g<8>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
+    case 16: launch_match_g<16>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
+    default: launch_match_g<32>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
     }
 }
 

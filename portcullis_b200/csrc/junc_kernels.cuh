@@ -114,6 +114,11 @@ struct Reads {
 // Two 16-byte halves so that each is one 128-bit load.
 struct __align__(16) PairA { uint32_t rid; int32_t lstart; int32_t rend; int32_t pos; };
 struct __align__(16) PairB { int32_t read_end; uint32_t bits; uint32_t updown; int32_t start; };
+// Junction-local view of the read for the anchor comparison (k_match): lets it start at the N op instead of re-walking the
+// whole CIGAR (long reads have dozens of ops and a pair per N op) and spares it the per-read column gathers.
+struct __align__(16) PairC { uint64_t seq_nib0; uint32_t cig_abs; int32_t qpos_n; };   // first nibble of the clipped query in the SEQ stream;
+                                                                                       // index of this N op in the CIGAR stream; query offset at it
+struct __align__(16) PairD { int32_t qsize; int32_t lq; uint32_t nops; uint32_t pad; }; // clipped query length (Q3); l_qseq; ops before | ops after << 16
 enum : uint32_t { PB_R1 = 1u << 0, PB_REV = 1u << 1, PB_MS = 1u << 2, PB_UM = 1u << 3, PB_BPP = 1u << 4, PB_PPP = 1u << 5,
                   PB_XSP = 1u << 6, PB_XSN = 1u << 7 };
 

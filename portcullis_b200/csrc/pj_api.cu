@@ -426,15 +426,13 @@ int pj_shard_run(pj_ctx* c) {
     CU(c, cudaMemsetAsync(c->d_scalars, 0, 16 * sizeof(uint32_t), st));
     Reads Rd{R, c->tid.p, c->pos.p, c->flag.p, c->mapq.p, c->xs.p, c->l_qseq.p, c->mtid.p, c->mpos.p, c->cigar_off.p, c->cigar.p, c->seq_off.p, c->seq4.p};
     TargetAcc TA{c->d_spliced, c->d_unspliced, c->d_sumq, c->d_minq, c->d_maxq};
-    uint32_t* d_err = c->d_scalars + 0; uint32_t* d_maxn = c->d_scalars + 1; uint32_t* d_P = c->d_scalars + 2;
+    uint32_t* d_err = c->d_scalars + 0; uint32_t* d_P = c->d_scalars + 2;
     uint32_t* d_J = c->d_scalars + 3; uint32_t* d_E = c->d_scalars + 4; uint32_t* d_tmp_total = c->d_scalars + 5;
 
-    uint32_t *npairs = nullptr, *pair_off = nullptr, *scan_tmp = nullptr; int32_t* read_end = nullptr;
     uint64_t *keys_a = nullptr, *keys_b = nullptr; uint32_t *vals_a = nullptr, *vals_b = nullptr, *counts = nullptr, *scan_tmp2 = nullptr;
-    PairA* pa = nullptr; PairB* pb = nullptr; unsigned long long* se_status = nullptr;
+    PairA* pa = nullptr; PairB* pb = nullptr; PairC* pc = nullptr; PairD* pd = nullptr; unsigned long long* se_status = nullptr;
     uint32_t P = 0; int len_bits = 1, key_bits = 2;
     const int gbits = std::max(1, bit_length(c->h_toff[T]));
-    const size_t Ra = (size_t)std::max<int64_t>(R, 1);
     auto alloc_pairs = [&](uint32_t cap) -> int {
         const size_t n = std::max<size_t>(cap, 1);
         const uint32_t nb = rs_num_blocks((uint32_t)n);
@@ -443,10 +441,11 @@ int pj_shard_run(pj_ctx* c) {
         CU(c, cudaMallocAsync(&counts, (size_t)256 * nb * 4, st));
         CU(c, cudaMallocAsync(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, n)) * 4, st));
         CU(c, cudaMallocAsync(&pa, n * sizeof(PairA), st)); CU(c, cudaMallocAsync(&pb, n * sizeof(PairB), st));
+        CU(c, cudaMallocAsync(&pc, n * sizeof(PairC), st)); CU(c, cudaMallocAsync(&pd, n * sizeof(PairD), st));
         return PJ_OK;
     };
-    if (!c->legacy_sort) {
-        // fused front end: the longest N op and the number of N ops were accumulated while the batches were copied in
+    {
+        // front end: the longest N op and the number of N ops were accumulated while the batches were copied in
         unsigned long long acc[2] = {0, 0};
         CU(c, cudaStreamSynchronize(c->copy_stream));
         CU(c, cudaMemcpy(acc, c->d_shard_acc, sizeof acc, cudaMemcpyDeviceToHost));
@@ -456,32 +455,13 @@ int pj_shard_run(pj_ctx* c) {
         if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
         if ((rc = alloc_pairs((uint32_t)acc[1]))) return rc;
         CU(c, cudaMallocAsync(&se_status, (size_t)std::max<uint32_t>(se_num_tiles(R), 1) * sizeof(unsigned long long), st));
-        launch_scan_emit(Rd, c->d_tlen, T, c->d_toff, reinterpret_cast<const uint32_t*>(c->d_shard_acc), c->orientation, TA, keys_a, pa, pb,
+        launch_scan_emit(Rd, c->d_tlen, T, c->d_toff, reinterpret_cast<const uint32_t*>(c->d_shard_acc), c->orientation, TA, keys_a, pa, pb, pc, pd,
                          se_status, c->d_scalars + 6, d_P, (uint32_t)acc[1], d_err, st); c->n_launches++;
         mark(c, "scan_emit");
         CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(c, cudaStreamSynchronize(st));
         CU(c, cudaGetLastError());
         P = c->h_scalars[2];
-    } else {
-        CU(c, cudaMallocAsync(&npairs, Ra * 4, st)); CU(c, cudaMallocAsync(&pair_off, (Ra + 1) * 4, st)); CU(c, cudaMallocAsync(&read_end, Ra * 4, st));
-        CU(c, cudaMallocAsync(&scan_tmp, scan_tmp_elems(Ra) * 4, st));
-        launch_scan_reads(Rd, c->d_tlen, T, npairs, read_end, TA, d_maxn, c->n_sm, st); c->n_launches++;
-        mark(c, "scan_reads");
-        launch_exclusive_scan(npairs, pair_off, (uint64_t)R, scan_tmp, d_P, st); c->n_launches += 3;
-        mark(c, "pair_offsets");
-        CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CU(c, cudaStreamSynchronize(st));
-        CU(c, cudaGetLastError());
-        P = c->h_scalars[2];
-        // (a uint32 sum of N-op counts can wrap only beyond 2^32 pairs; the CIGAR word limit above excludes that)
-        len_bits = std::max(1, bit_length(c->h_scalars[1])); key_bits = len_bits + gbits;
-        if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
-        if (P > 0) {
-            if ((rc = alloc_pairs(P))) return rc;
-            launch_emit_pairs(Rd, c->d_tlen, c->d_toff, len_bits, c->orientation, pair_off, npairs, read_end, keys_a, pa, pb, d_err, st); c->n_launches++;
-            mark(c, "emit_pairs");
-        }
     }
     c->n_pairs = P;
 
@@ -550,7 +530,7 @@ int pj_shard_run(pj_ctx* c) {
                 const double bases_per_pair = 2.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
                 group = bases_per_pair <= 400 ? 1 : bases_per_pair <= 1200 ? 4 : bases_per_pair <= 4000 ? 8 : 32;
             }
-            launch_match(P, group, vals, jid, pa, pb, Rd, G, A, pm, d_err, st); c->n_launches++;
+            launch_match(P, group, vals, jid, pa, pb, pc, pd, Rd, G, A, pm, d_err, st); c->n_launches++;
         }
         mark(c, "match");
         launch_reduce2(P, jid, pm, A, st); c->n_launches++;
@@ -561,8 +541,7 @@ int pj_shard_run(pj_ctx* c) {
         CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(fs_scratch, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
         CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st));
     }
-    for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pa, (void*)pb, (void*)se_status,
-                    (void*)npairs, (void*)pair_off, (void*)read_end, (void*)scan_tmp})
+    for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pa, (void*)pb, (void*)pc, (void*)pd, (void*)se_status})
         if (p) CU(c, cudaFreeAsync(p, st));
     mark(c, "end");
     CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
