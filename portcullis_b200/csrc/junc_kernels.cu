@@ -224,8 +224,10 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
     const int64_t base = (int64_t)tile * SE_TILE;
     const int32_t tid_first = R.tid[min(base, R.n - 1)];
     const int32_t len_bits = max(1, 32 - __clz((int)__ldg(max_nlen)));
-    // ---- phase A: scan the tile's records ----
+    // ---- phase A: scan the tile's records.  Loads and CIGAR walks of the thread's records come first (independent, so
+    // their latencies overlap); the warp collectives for the per-target scalars follow in a second loop. ----
     uint32_t cnt[SE_ITEMS]; int32_t rend[SE_ITEMS]; bool zeron[SE_ITEMS];
+    int32_t tids[SE_ITEMS], lqs[SE_ITEMS]; bool viss[SE_ITEMS];
 #pragma unroll
     for (int r = 0; r < SE_ITEMS; r++) {
         const int64_t i = base + r * SE_THREADS + threadIdx.x;
@@ -234,6 +236,8 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
             tid = R.tid[i];
             const int32_t pos = R.pos[i];
             const uint32_t c0 = R.cigar_off[i], c1 = R.cigar_off[i + 1];
+            const uint32_t flag = R.flag[i];
+            lq = R.l_qseq[i];
             int64_t rlen = 0;
             for (uint32_t c = c0; c < c1; c++) {
                 const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
@@ -241,14 +245,17 @@ __global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t
                 if (op == OP_N) { nN++; if (cig_len(w) == 0) zeron[r] = true; }
             }
             rend[r] = (int32_t)(pos + rlen - 1);
-            lq = R.l_qseq[i];
             if (tid >= 0 && tid < n_targets) {
-                const int64_t endpos = (!(R.flag[i] & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
+                const int64_t endpos = (!(flag & 0x4) && c1 > c0) ? (int64_t)pos + rlen : (int64_t)pos + 1;
                 vis = pos < tlen[tid] && endpos > 0;
             }
             if (!vis) nN = 0;
         }
-        cnt[r] = nN;
+        cnt[r] = nN; tids[r] = tid; lqs[r] = lq; viss[r] = vis;
+    }
+#pragma unroll
+    for (int r = 0; r < SE_ITEMS; r++) {
+        const bool vis = viss[r]; const int32_t tid = tids[r], lq = lqs[r]; const uint32_t nN = cnt[r];
         // per-target scalars: warp partials into the block's shared slots (slot = tid - first tid of the tile)
         const uint32_t vmask = __ballot_sync(FULL, vis);
         if (vmask) {
