@@ -205,7 +205,7 @@ void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen,
 }
 
 template <int SE_ITEMS>
-__global__ void __launch_bounds__(SE_THREADS) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
+__global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
                                                            const uint32_t* __restrict__ max_nlen, int32_t orientation, TargetAcc T,
                                                            uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
                                                            PairC* __restrict__ pc, PairD* __restrict__ pd,
@@ -1119,7 +1119,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, 
 }
 
 template <int G>
-__global__ void __launch_bounds__(256) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+__global__ void __launch_bounds__(256, 5) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairA* __restrict__ pa, const PairB* __restrict__ pb,
                                                 const PairC* __restrict__ pc, const PairD* __restrict__ pd,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
