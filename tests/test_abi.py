@@ -90,3 +90,29 @@ def test_fast_inflate_matches_zlib():
     """The built-in DEFLATE decoder used for BGZF blocks agrees with zlib on 300 synthetic streams (random, DNA-like,
     run-heavy, LZ-heavy, all-zero data; stored / fixed / dynamic blocks; several strategies)."""
     assert L.load().pjh_inflate_selftest(300) == 0
+
+
+def test_headers_are_plain_c_and_link(tmp_path):
+    """include/*.h compile as C99 and a C program can link the library and call it (no C++ or torch types in the ABI)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('''
+#include "portcullis_junc.h"
+#include "portcullis_junc_host.h"
+#include <stdio.h>
+int main(void) {
+    pj_config cfg = {0}; pj_ctx* ctx = 0; pjh_options o; pj_junction row;
+    pjh_options_default(&o);
+    cfg.device = 0; cfg.orientation = PJ_ORIENT_UNKNOWN;
+    int rc = pj_create(&cfg, &ctx);          /* no GPU here: must fail loudly, not fall back */
+    printf("%d %d %d %s\\n", pj_abi_version(), pj_junction_size(), (int)sizeof row, rc == PJ_OK ? "gpu" : pj_global_last_error());
+    if (ctx) pj_destroy(ctx);
+    return (pj_junction_size() == (int)sizeof row && o.threads == 1) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "portcullis_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lportcullis_junc", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()
+    assert out[0] == "1" and out[1] == "256" and out[2] == "256"
