@@ -65,6 +65,9 @@ typedef struct pj_config {
     int32_t reserved[6];   /* tuning knobs, 0 = default. [0]: lanes per (read, junction) pair in the match kernel;
                               [1]: 1 = multi-kernel radix sort instead of the one-sweep sort;
                               [2]: number of pinned staging buffers pj_staging_acquire may create (default 4) */
+    int32_t extra_metrics; /* 1 = also keep what the hidden `--extra` metrics need (pj_extra_* below); batches must
+                              then carry name_code */
+    int32_t pad;
 } pj_config;
 
 /*
@@ -80,6 +83,9 @@ typedef struct pj_config {
  *   seq4      : BAM 4-bit packed SEQ (high nibble first), each record starting on a byte boundary.
  *               Records without an N operation may omit their SEQ (seq_off[i+1]==seq_off[i]).
  *   seq_off   : n_records+1 prefix offsets into seq4[] (in bytes).
+ *   name_code : optional (NULL unless pj_config.extra_metrics): a 64-bit code of BamAlignment::deriveName()
+ *               (bam_alignment.cc:233-242: QNAME plus "_R1"/"_R2"/"_R?" for paired reads).  Only equality of codes
+ *               matters — it plays the role of std::hash<string> in junction.hpp:158 / junction_builder.cc:182-185.
  */
 typedef struct pj_batch {
     int64_t         n_records;
@@ -95,6 +101,7 @@ typedef struct pj_batch {
     const uint32_t* cigar;
     const uint64_t* seq_off;
     const uint8_t*  seq4;
+    const uint64_t* name_code;
 } pj_batch;
 
 /* Per-target scalars: RegionResult minus the junction system
@@ -227,6 +234,65 @@ int pj_shard_fetch(pj_ctx* ctx, pj_junction* rows, int64_t cap_rows, pj_target_s
  * kernel launches it made.  kernel_ms/kernel_names expose the per-kernel breakdown (n entries). */
 int pj_shard_timing(const pj_ctx* ctx, float* total_ms, int32_t* n_launches);
 int pj_shard_kernel_times(const pj_ctx* ctx, int32_t cap, float* kernel_ms, const char** kernel_names, int32_t* n);
+
+/* ---- `--extra` metrics (JunctionBuilder::calcExtraMetrics, junction_builder.cc:293-312) ---- */
+
+/*
+ * The four junctions.tab columns plain `junc` leaves 0.  The reference computes them from the separated BAMs
+ * (spliced / unspliced); here the same record classes are taken from the columnar batches already in HBM:
+ *   spliced   = any N op in the CIGAR (BamAlignment::isSplicedRead, bam_alignment.cc:294-301)
+ *   unspliced = not spliced and mapped (junction_builder.cc:188-191)
+ * Integer columns are produced on the GPU; the two doubles are filled by pj_extra_finalize() on the host.
+ */
+typedef struct pj_junction_extra {
+    uint32_t up_aln;             /* nbUpstreamFlankingAlignments   (Junction::processJunctionVicinity, junction.cc:651-677) */
+    uint32_t down_aln;           /* nbDownstreamFlankingAlignments                                                       */
+    uint32_t mm_n;               /* N of calcMultipleMappingScore (junction.cc:914-921): alignments of the junction        */
+    uint32_t mm_m;               /* M: sum over them of the number of spliced alignments with the same name (uint16 map
+                                    values, uint32 sum — both wrap like the reference)                                     */
+    uint32_t cov_sum[4];         /* read counts of Junction::calcCoverage (junction.cc:935-951), in its call order:
+                                    [start-20,start-11], [start-10,start], [end+10,end+20], [end,end+9]                  */
+    double   mm_score;           /* (double)N / (double)M                                                                  */
+    double   coverage;
+} pj_junction_extra;
+
+/* 64-bit codes of the shard's spliced records (device -> host), so that a multi-GPU caller can give every context the
+ * names of the whole file: the reference's map is built over the whole BAM (junction_builder.cc:179-186). */
+int64_t pj_extra_num_spliced_names(const pj_ctx* ctx);
+int pj_extra_export_names(pj_ctx* ctx, uint64_t* codes, int64_t cap);
+/* Add spliced-read name codes that live on OTHER contexts (host -> device). */
+int pj_extra_import_names(pj_ctx* ctx, const uint64_t* codes, int64_t n);
+
+/*
+ * After pj_shard_run: up_aln / down_aln / mm_n / mm_m for the shard's junctions, in pj_shard_fetch order
+ * (cov_sum, mm_score and coverage are left 0).  max_query_length is the maximum over ALL targets of the file
+ * (JunctionSystem::setQueryLengthStats, junction_builder.cc:270): it sizes the region the reference queries.
+ */
+int pj_extra_run(pj_ctx* ctx, int32_t max_query_length, pj_junction_extra* out, int64_t cap_rows);
+
+/*
+ * Unspliced pileup of one target held by this context (DepthParser, depth_parser.cc:112-167): *covered = 1 when the
+ * pileup reports at least one position, *max_depth = the deepest column (reads, D included).  htslib stops accepting
+ * reads that start at a position already holding 8000 of them (sam.c:1906); this library does not model that, so a
+ * caller should warn when max_depth >= 8000.
+ */
+int pj_extra_target_pileup(pj_ctx* ctx, int32_t tid, int32_t* covered, uint32_t* max_depth);
+
+/*
+ * cov_sum[4] of n junction coordinates against the depth vector of target depth_tid (which must belong to this
+ * context's shard).  The reference pairs each depth vector with the junctions of the NEXT covered target
+ * (depth_parser.hpp:94-96 returns the index of the target the parser has just moved on to; quirk Q14) — the caller
+ * chooses depth_tid accordingly, see pj_extra_coverage_source().
+ */
+int pj_extra_coverage(pj_ctx* ctx, int32_t depth_tid, int64_t n, const int32_t* intron_start, const int32_t* intron_end,
+                      uint32_t* cov_sum4);
+
+/* Q14 as a function: covered[t] per target -> depth_src[t] = target whose depth vector the reference applies to the
+ * junctions of t (-1: coverage stays 0). */
+void pj_extra_coverage_source(int32_t n_targets, const uint8_t* covered, int32_t* depth_src);
+
+/* mm_score and coverage from the integer columns, with the reference's operation order. */
+void pj_extra_finalize(pj_junction_extra* x, int64_t n);
 
 /* ---- host finalize (A12/A13) --------------------------------------------------------------- */
 

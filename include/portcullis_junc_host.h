@@ -32,8 +32,8 @@ typedef struct pjh_options {
     int32_t intron_gff;          /* --intron_gff                                                  */
     const char* source;          /* --source, default "portcullis"                                */
     int32_t verbose;             /* -v                                                            */
-    int32_t separate;            /* --separate  (not supported on this path: rejected)            */
-    int32_t extra;               /* --extra     (not supported on this path: rejected)            */
+    int32_t separate;            /* --separate  (writing the three BAM files is not on this path: rejected) */
+    int32_t extra;               /* --extra: mm_score, coverage, up_aln, down_aln from the records in HBM   */
     int32_t quiet;               /* suppress the progress text on stdout                          */
     const char* version;         /* string for the BED track line; NULL -> "1.2.4"                */
 } pjh_options;
@@ -55,6 +55,7 @@ typedef struct pjh_report {
     double  t_init_s;            /* CUDA context + pj_create + pj_targets_set (max over GPUs)     */
     double  t_run_s;             /* wall time of pj_shard_run + pj_shard_fetch (max over GPUs)    */
     double  t_teardown_s;        /* pj_destroy                                                    */
+    double  t_extra_s;           /* --extra: name exchange + pj_extra_run + coverage (0 otherwise) */
 } pjh_report;
 
 void pjh_options_default(pjh_options* o);
@@ -77,6 +78,8 @@ int64_t     pjh_prep_target_records(const pjh_prep* p, int32_t tid);
 /* Decode one target (tid >= 0) or every target (tid = -1) with `threads` workers into columnar arrays owned by
  * `p` (valid until the next decode or close). */
 int         pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out);
+/* on != 0: later pjh_prep_decode calls also fill pj_batch.name_code (needed by the `--extra` metrics) */
+void        pjh_prep_want_names(pjh_prep* p, int32_t on);
 /* Unwrapped FASTA bytes of a target (owned by `p`, valid until the next call for another target or close). */
 int         pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bases);
 
@@ -93,6 +96,11 @@ int         pjh_inflate_selftest(int32_t n_cases);
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,
                       int32_t n_targets, const char* const* names, const int32_t* lens,
                       const char* source, const char* version, int32_t exon_gff, int32_t intron_gff);
+
+/* Same, with the `--extra` columns (mm_score, coverage, up_aln, down_aln) taken from extra[n_rows] (NULL: printed as 0). */
+int pjh_write_outputs_extra(const char* output_prefix, const pj_junction* rows, const pj_junction_extra* extra, int64_t n_rows,
+                            int32_t n_targets, const char* const* names, const int32_t* lens,
+                            const char* source, const char* version, int32_t exon_gff, int32_t intron_gff);
 
 #ifdef __cplusplus
 }

@@ -251,7 +251,7 @@ static int add_junctions(JuncSet* S, const pj_batch* b, int64_t r, int32_t refLe
             if (rEndExc - 1 >= refLength) rEndExc = refLength;
             int32_t is = lEndExc, ie = rStart - 1;
             if (set_grow(S)) return PJ_ENOMEM;
-            int64_t* slot; int64_t idx = set_find(S, tid, is, ie, &slot);
+            int64_t* slot = NULL; int64_t idx = set_find(S, tid, is, ie, &slot);
             if (idx < 0) {
                 /* Junction ctor (junction.cc:328-387): maxMinAnchor = minAnchorLength(lStart, rEndExc-1) which throws
                  * when the anchors do not enclose the intron (intron.cc:68-85) */
@@ -507,17 +507,10 @@ static int cmp_rows(const void* a, const void* b) {            /* IntronComparat
     return 0;
 }
 
-int oj_run(const pj_batch* b, int32_t n_targets, const int32_t* target_len,
-           const char* genome_cat, const int64_t* genome_off, int32_t orientation,
-           pj_junction** rows_out, int64_t* n_rows_out, pj_target_stats* stats) {
-    JuncSet S; memset(&S, 0, sizeof S);
+/* findJuncs (junction_builder.cc:314-357).  Record visibility (Q13, htslib hts.c:1951-1953): tid==target,
+ * pos < target_len, endpos > 0.  The flush at :324-331 only bounds memory; results equal a batch pass. */
+static int build_junction_set(const pj_batch* b, int32_t n_targets, const int32_t* target_len, JuncSet* S, pj_target_stats* stats) {
     int rc = 0;
-    for (int32_t t = 0; t < n_targets; t++) {
-        memset(&stats[t], 0, sizeof stats[t]);
-        stats[t].min_query_length = INT32_MAX;
-    }
-    /* findJuncs (junction_builder.cc:314-357).  Record visibility (Q13, htslib hts.c:1951-1953): tid==target,
-     * pos < target_len, endpos > 0.  The flush at :324-331 only bounds memory; results equal a batch pass. */
     for (int64_t r = 0; r < b->n_records && !rc; r++) {
         int32_t tid = b->tid[r];
         if (tid < 0 || tid >= n_targets) continue;
@@ -528,16 +521,30 @@ int oj_run(const pj_batch* b, int32_t n_targets, const int32_t* target_len,
         int64_t endpos = (!(b->flag[r] & 0x4) && n > 0) ? (int64_t)pos + rlen : (int64_t)pos + 1;   /* sam.c:336-342 bam_endpos */
         if (!(pos < target_len[tid] && endpos > 0)) continue;
         int32_t len = b->l_qseq[r];
-        pj_target_stats* st = &stats[tid];
-        if (len < st->min_query_length) st->min_query_length = len;
-        if (len > st->max_query_length) st->max_query_length = len;
-        st->sum_query_lengths += (uint64_t)(int64_t)len;
+        if (stats) {
+            pj_target_stats* st = &stats[tid];
+            if (len < st->min_query_length) st->min_query_length = len;
+            if (len > st->max_query_length) st->max_query_length = len;
+            st->sum_query_lengths += (uint64_t)(int64_t)len;
+        }
         int nbN = 0;
         for (int32_t c = 0; c < n; c++) if (op_type(cg[c]) == OP_N) nbN++;
         int found = 0;
-        rc = add_junctions(&S, b, r, target_len[tid], nbN, 0, pos, &found);
-        if (found) st->spliced_count++; else st->unspliced_count++;
+        rc = add_junctions(S, b, r, target_len[tid], nbN, 0, pos, &found);
+        if (stats) { if (found) stats[tid].spliced_count++; else stats[tid].unspliced_count++; }
     }
+    return rc;
+}
+
+int oj_run(const pj_batch* b, int32_t n_targets, const int32_t* target_len,
+           const char* genome_cat, const int64_t* genome_off, int32_t orientation,
+           pj_junction** rows_out, int64_t* n_rows_out, pj_target_stats* stats) {
+    JuncSet S; memset(&S, 0, sizeof S);
+    for (int32_t t = 0; t < n_targets; t++) {
+        memset(&stats[t], 0, sizeof stats[t]);
+        stats[t].min_query_length = INT32_MAX;
+    }
+    int rc = build_junction_set(b, n_targets, target_len, &S, stats);
     pj_junction* rows = NULL;
     if (!rc) {
         rows = (pj_junction*)calloc((size_t)(S.n ? S.n : 1), sizeof(pj_junction));
@@ -611,4 +618,242 @@ int oj_finalize(pj_junction* rows, int64_t n, double meanQueryLength) {
         }
     }
     return 0;
+}
+
+
+/* ================================================================================================================
+ * `--extra` metrics: JunctionBuilder::separateBams + calcExtraMetrics restated on the
+ * columnar batch (junction_builder.cc:152-226, 293-312).  The batch plays the role of the whole sorted BAM.
+ * ================================================================================================================ */
+
+static int is_spliced(const uint32_t* cg, int32_t n) {                /* bam_alignment.cc:294-301 */
+    for (int32_t i = 0; i < n; i++) if (op_type(cg[i]) == OP_N) return 1;
+    return 0;
+}
+
+/* SplicedAlignmentMap = unordered_map<size_t, uint16_t> (junction.hpp:38) */
+typedef struct { uint64_t* key; uint16_t* val; uint8_t* used; uint64_t cap; } NameMap;
+static uint64_t mix64(uint64_t h) { h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33; return h; }
+static uint16_t* namemap_slot(NameMap* m, uint64_t k) {
+    uint64_t i = mix64(k) & (m->cap - 1);
+    while (m->used[i] && m->key[i] != k) i = (i + 1) & (m->cap - 1);
+    if (!m->used[i]) { m->used[i] = 1; m->key[i] = k; m->val[i] = 0; }
+    return &m->val[i];
+}
+
+typedef struct { int64_t* v; int64_t n, cap; } Heap;                  /* min-heap of end positions */
+static int heap_push(Heap* h, int64_t x) {
+    if (h->n == h->cap) { int64_t nc = h->cap ? h->cap * 2 : 1024; int64_t* nv = (int64_t*)realloc(h->v, (size_t)nc * 8); if (!nv) return -1; h->v = nv; h->cap = nc; }
+    int64_t i = h->n++;
+    while (i > 0 && h->v[(i - 1) / 2] > x) { h->v[i] = h->v[(i - 1) / 2]; i = (i - 1) / 2; }
+    h->v[i] = x;
+    return 0;
+}
+static void heap_pop(Heap* h) {
+    int64_t x = h->v[--h->n], i = 0;
+    for (;;) {
+        int64_t c = 2 * i + 1;
+        if (c >= h->n) break;
+        if (c + 1 < h->n && h->v[c + 1] < h->v[c]) c++;
+        if (h->v[c] >= x) break;
+        h->v[i] = h->v[c]; i = c;
+    }
+    if (h->n) h->v[i] = x;
+}
+
+#ifndef PLP_MAXCNT
+#define PLP_MAXCNT 8000                                               /* bam_plp_init, sam.c:1651 */
+#endif
+
+/* DepthParser::loadNextBatch over one target of the unspliced BAM (depth_parser.cc:112-167): bam_plp_auto /
+ * bam_plp_push / resolve_cigar2 of htslib-1.3 sam.c:1515-1590, 1838-1936.  u[]: the target's unspliced mapped
+ * records in file order.  depth[] has target_len entries and is indexed with the reference's +1 shift
+ * (`rpos = pos + 1`, depth_parser.cc:155).  Returns 1 when the pileup reports at least one column. */
+static int pileup_target(const pj_batch* b, const int64_t* u, int64_t nu, uint32_t* depth, int64_t size, int64_t* n_capped, Heap* live) {
+    int covered = 0;
+    live->n = 0;
+    int64_t last_pos = -1;
+    for (int64_t k = 0; k < nu; k++) {
+        int64_t r = u[k];
+        const uint32_t* cg = b->cigar + b->cigar_off[r];
+        int32_t n = (int32_t)(b->cigar_off[r + 1] - b->cigar_off[r]);
+        int64_t P = b->pos[r];
+        int64_t end = n > 0 ? P + aligned_length(cg, n) : P + 1;      /* bam_endpos; FUNMAP is clear here */
+        int first_here = (P != last_pos);
+        last_pos = P;
+        /* bam_plp_next frees nodes with end <= every column it has visited; before a second read at P is pushed
+         * the iterator stands on P, having visited up to P-1 */
+        while (live->n && live->v[0] <= P - 1) heap_pop(live);
+        /* mempool count = live nodes + the spare tail + the dummy node (bam_plp_init, sam.c:1619-1620) */
+        if (!first_here && 2 + live->n > PLP_MAXCNT) { (*n_capped)++; continue; }      /* sam.c:1906-1910 */
+        int64_t iter_pos = first_here ? P - 1 : P;
+        if (end > iter_pos) { if (heap_push(live, end)) return -1; }                   /* sam.c:1930-1933 */
+        if (end <= P) continue;                                                        /* never piled up */
+        covered = 1;
+        int64_t x = P;
+        for (int32_t c = 0; c < n; c++) {
+            int t = op_type(cg[c]); int64_t L = op_len(cg[c]);
+            if (t == OP_M || t == OP_EQ || t == OP_X) {
+                for (int64_t q = x; q < x + L; q++) if (q + 1 >= 0 && q + 1 < size) depth[q + 1]++;
+                x += L;
+            }
+            else if (t == OP_D || t == OP_N) x += L;                   /* is_del / is_refskip: not counted (:121-124) */
+        }
+    }
+    return covered;
+}
+
+/* Junction::calcCoverage(a, b, levels) (junction.cc:923-933) */
+static double coverage_window(int32_t a, int32_t b, const uint32_t* lev, int64_t size, uint32_t* sum) {
+    double multiplier = 1.0 / (b - a);
+    uint32_t readCount = 0;
+    for (int32_t i = a; i <= b; i++) if (i >= 0 && i < size) readCount += lev[i];
+    *sum = readCount;
+    return multiplier * (double)readCount;
+}
+
+static int64_t lower_row(const pj_junction* rows, int64_t n, int32_t tid) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t m = (lo + hi) / 2; if (rows[m].tid < tid) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+int oj_extra(const pj_batch* b, int32_t n_targets, const int32_t* target_len, const pj_junction* rows, int64_t n_rows,
+             int32_t max_query_length, pj_junction_extra* out, int64_t* n_capped_reads) {
+    int rc = 0;
+    memset(out, 0, (size_t)n_rows * sizeof *out);
+    *n_capped_reads = 0;
+    if (!b->name_code && b->n_records) FAIL(PJ_EINVAL, "oj_extra needs name_code");
+
+    /* ---- separateBams (junction_builder.cc:176-198): name map over every spliced record of the file ---- */
+    NameMap nm; memset(&nm, 0, sizeof nm);
+    nm.cap = 1024; while (nm.cap < (uint64_t)b->n_records * 2 + 2) nm.cap <<= 1;
+    nm.key = (uint64_t*)malloc(nm.cap * 8); nm.val = (uint16_t*)malloc(nm.cap * 2); nm.used = (uint8_t*)calloc(nm.cap, 1);
+    int64_t* uns = (int64_t*)malloc((size_t)(b->n_records + 1) * 8);            /* unspliced mapped, file order */
+    int64_t* uoff = (int64_t*)calloc((size_t)n_targets + 1, 8);
+    JuncSet S; memset(&S, 0, sizeof S);
+    int64_t* pmax = NULL; uint32_t* depth = NULL; Heap live; memset(&live, 0, sizeof live);
+    if (!nm.key || !nm.val || !nm.used || !uns || !uoff) { snprintf(g_err, sizeof g_err, "oom"); rc = PJ_ENOMEM; goto done; }
+    int64_t nuns = 0;
+    {
+        int32_t cur = 0;
+        for (int64_t r = 0; r < b->n_records; r++) {
+            const uint32_t* cg = b->cigar + b->cigar_off[r];
+            int32_t n = (int32_t)(b->cigar_off[r + 1] - b->cigar_off[r]);
+            if (is_spliced(cg, n)) { (*namemap_slot(&nm, b->name_code[r]))++; continue; }
+            if (b->flag[r] & 0x4) continue;                                        /* unmapped.bam */
+            int32_t tid = b->tid[r];
+            if (tid < 0 || tid >= n_targets) continue;                            /* no region query can reach it */
+            if (tid < cur) { snprintf(g_err, sizeof g_err, "batch not sorted by tid"); rc = PJ_EINVAL; goto done; }
+            if (n == 0) { snprintf(g_err, sizeof g_err, "mapped record %lld has no CIGAR (htslib pileup asserts, sam.c:1537)", (long long)r); rc = PJ_EDATA; goto done; }
+            while (cur < tid) uoff[++cur] = nuns;
+            uns[nuns++] = r;
+        }
+        while (cur < n_targets) uoff[++cur] = nuns;
+    }
+
+    /* ---- calcMultipleMappingScore (junction.cc:914-921) ---- */
+    rc = build_junction_set(b, n_targets, target_len, &S, NULL);
+    if (rc) goto done;
+    for (int64_t k = 0; k < S.n; k++) {
+        const Junc* q = &S.j[k];
+        pj_junction key; key.tid = q->tid; key.start = q->start; key.end = q->end;
+        const pj_junction* hit = (const pj_junction*)bsearch(&key, rows, (size_t)n_rows, sizeof *rows, cmp_rows);
+        if (!hit) { snprintf(g_err, sizeof g_err, "rows do not belong to this batch"); rc = PJ_EINVAL; goto done; }
+        pj_junction_extra* x = &out[hit - rows];
+        uint32_t M = 0;
+        for (int64_t i = 0; i < q->n; i++) M += *namemap_slot(&nm, b->name_code[q->reads[i]]);
+        x->mm_n = (uint32_t)q->n; x->mm_m = M;
+        x->mm_score = (double)(size_t)q->n / (double)M;
+    }
+
+    /* ---- findFlankingAlignments -> processJunctionVicinity (junction_system.cc:212-229, junction.cc:651-677) ---- */
+    pmax = (int64_t*)malloc((size_t)(nuns + 1) * 8);
+    if (!pmax) { snprintf(g_err, sizeof g_err, "oom"); rc = PJ_ENOMEM; goto done; }
+    for (int32_t t = 0; t < n_targets; t++) {
+        int64_t m = INT64_MIN;
+        for (int64_t k = uoff[t]; k < uoff[t + 1]; k++) {
+            int64_t r = uns[k];
+            int64_t e = (int64_t)b->pos[r] + aligned_length(b->cigar + b->cigar_off[r], (int32_t)(b->cigar_off[r + 1] - b->cigar_off[r]));
+            if (e > m) m = e;
+            pmax[k] = m;
+        }
+    }
+    for (int64_t j = 0; j < n_rows; j++) {
+        const pj_junction* q = &rows[j];
+        if (q->tid < 0 || q->tid >= n_targets) continue;
+        int32_t refLength = target_len[q->tid];
+        int32_t regionStart = q->left - max_query_length - 1;
+        regionStart = regionStart < 0 ? 0 : regionStart;
+        int32_t regionEnd = q->right + max_query_length + 1;
+        regionEnd = regionEnd >= refLength ? refLength - 1 : regionEnd;
+        uint32_t nl = 0, nr = 0;
+        if (regionEnd > regionStart) {                                             /* hts_itr_query: end < beg -> no iterator; reg2bins: beg >= end -> none */
+            int64_t lo = uoff[q->tid], hi = uoff[q->tid + 1];
+            int64_t a = lo, z = hi;                                                /* first record whose running max end exceeds regionStart */
+            while (a < z) { int64_t m = (a + z) / 2; if (pmax[m] > regionStart) z = m; else a = m + 1; }
+            for (int64_t k = a; k < hi; k++) {
+                int64_t r = uns[k];
+                int32_t pos = b->pos[r];
+                if (pos >= regionEnd) break;                                       /* hts_itr_next: beg >= iter->end -> finished */
+                int32_t alen = aligned_length(b->cigar + b->cigar_off[r], (int32_t)(b->cigar_off[r + 1] - b->cigar_off[r]));
+                int64_t endpos = (int64_t)pos + alen;                              /* bam_endpos (mapped, n_cigar > 0) */
+                if (!(endpos > regionStart)) continue;
+                int32_t getEnd = pos + alen - 1;                                   /* bam_alignment.hpp:221-223 */
+                if (q->start > pos && q->left <= getEnd) nl++;
+                if (q->right >= pos && q->end < pos) nr++;
+            }
+        }
+        out[j].up_aln = nl; out[j].down_aln = nr;
+    }
+
+    /* ---- calcCoverage (junction_system.cc:231-243) with DepthParser's batch/target pairing (Q14) ---- */
+    {
+        int32_t prev_cov = -1;           /* previous covered target, whose batch has been built but is applied to the next one */
+        int32_t maxlen = 0;
+        for (int32_t t = 0; t < n_targets; t++) if (target_len[t] > maxlen) maxlen = target_len[t];
+        depth = (uint32_t*)malloc(((size_t)maxlen + 1) * 4);
+        uint32_t* depth_prev = (uint32_t*)malloc(((size_t)maxlen + 1) * 4);
+        if (!depth || !depth_prev) { free(depth_prev); snprintf(g_err, sizeof g_err, "oom"); rc = PJ_ENOMEM; goto done; }
+        int32_t last_cov = -1;
+        for (int32_t t = 0; t < n_targets; t++) {
+            if (uoff[t + 1] == uoff[t]) continue;
+            memset(depth, 0, ((size_t)target_len[t] + 1) * 4);
+            int c = pileup_target(b, uns + uoff[t], uoff[t + 1] - uoff[t], depth, target_len[t], n_capped_reads, &live);
+            if (c < 0) { free(depth_prev); snprintf(g_err, sizeof g_err, "oom"); rc = PJ_ENOMEM; goto done; }
+            if (!c) continue;
+            /* the batch of prev_cov is handed to the junctions of t (getCurrentRefIndex() == last.ref == t) */
+            if (prev_cov >= 0) {
+                for (int64_t j = lower_row(rows, n_rows, t); j < n_rows && rows[j].tid == t; j++) {
+                    const int32_t R = 10;                                          /* junction.cc:936 */
+                    int32_t ds = rows[j].start - 2 * R, dm = rows[j].start - R, de = rows[j].start;
+                    int32_t as = rows[j].end, am = rows[j].end + R, ae = rows[j].end + 2 * R;
+                    uint32_t* cs = out[j].cov_sum;
+                    double donor = coverage_window(ds, dm - 1, depth_prev, target_len[prev_cov], &cs[0]) - coverage_window(dm, de, depth_prev, target_len[prev_cov], &cs[1]);
+                    double acceptor = coverage_window(am, ae, depth_prev, target_len[prev_cov], &cs[2]) - coverage_window(as, am - 1, depth_prev, target_len[prev_cov], &cs[3]);
+                    out[j].coverage = donor + acceptor;
+                }
+            }
+            uint32_t* sw = depth_prev; depth_prev = depth; depth = sw;
+            prev_cov = t; last_cov = t;
+        }
+        if (last_cov >= 0) {             /* final batch: res == 0, last.ref still names the target the batch belongs to */
+            int32_t t = last_cov;
+            for (int64_t j = lower_row(rows, n_rows, t); j < n_rows && rows[j].tid == t; j++) {
+                const int32_t R = 10;
+                int32_t ds = rows[j].start - 2 * R, dm = rows[j].start - R, de = rows[j].start;
+                int32_t as = rows[j].end, am = rows[j].end + R, ae = rows[j].end + 2 * R;
+                uint32_t* cs = out[j].cov_sum;
+                double donor = coverage_window(ds, dm - 1, depth_prev, target_len[t], &cs[0]) - coverage_window(dm, de, depth_prev, target_len[t], &cs[1]);
+                double acceptor = coverage_window(am, ae, depth_prev, target_len[t], &cs[2]) - coverage_window(as, am - 1, depth_prev, target_len[t], &cs[3]);
+                out[j].coverage = donor + acceptor;
+            }
+        }
+        free(depth_prev);
+    }
+done:
+    for (int64_t k = 0; k < S.n; k++) free(S.j[k].reads);
+    free(S.j); free(S.table);
+    free(nm.key); free(nm.val); free(nm.used); free(uns); free(uoff); free(pmax); free(depth); free(live.v);
+    return rc;
 }

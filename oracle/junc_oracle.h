@@ -36,6 +36,12 @@ const char* oj_last_error(void);
 /* A12/A13 restated: sort, index, groups, neighbour distances, mean_readlen, pfp, rel2raw, mean_mismatches. */
 int oj_finalize(pj_junction* rows, int64_t n_rows, double mean_query_length);
 
+/* `--extra` metrics (junction_builder.cc:152-226, 293-312) restated over the same batch (which must
+ * carry name_code and hold the whole file in BAM order).  rows: the finalized rows of oj_run for that batch.
+ * *n_capped_reads = reads htslib's pileup dropped at its 8000-read cap (sam.c:1906), which this restatement models. */
+int oj_extra(const pj_batch* b, int32_t n_targets, const int32_t* target_len, const pj_junction* rows, int64_t n_rows,
+             int32_t max_query_length, pj_junction_extra* out, int64_t* n_capped_reads);
+
 /* ---- unit-level entry points used to replay the reference's own known-answer tests ---- */
 
 /* BamAlignment::getPaddedQuerySeq (bam_alignment.cc:341-403), include_soft_clips=false.

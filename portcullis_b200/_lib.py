@@ -25,14 +25,15 @@ class PjError(RuntimeError):
 
 
 class PjConfig(C.Structure):
-    _fields_ = [("device", C.c_int32), ("orientation", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("device", C.c_int32), ("orientation", C.c_int32), ("reserved", C.c_int32 * 6),
+                ("extra_metrics", C.c_int32), ("pad", C.c_int32)]
 
 
 class PjBatch(C.Structure):
     _fields_ = [("n_records", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p),
                 ("mapq", C.c_void_p), ("xs", C.c_void_p), ("l_qseq", C.c_void_p), ("mtid", C.c_void_p),
                 ("mpos", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
-                ("seq4", C.c_void_p)]
+                ("seq4", C.c_void_p), ("name_code", C.c_void_p)]
 
 
 class PjTargetStats(C.Structure):
@@ -54,6 +55,10 @@ JUNCTION_DTYPE = np.dtype([
     ("uniq_junc", "u1"), ("primary_junc", "u1"), ("pfp", "u1"), ("pad1", "u1", (5,)),
     ("mean_readlen", "<f8"), ("rel2raw", "<f8"), ("mean_mismatches", "<f8"),
 ], align=False)
+
+# numpy mirror of struct pj_junction_extra (48 bytes)
+EXTRA_DTYPE = np.dtype([("up_aln", "<u4"), ("down_aln", "<u4"), ("mm_n", "<u4"), ("mm_m", "<u4"), ("cov_sum", "<u4", (4,)),
+                        ("mm_score", "<f8"), ("coverage", "<f8")], align=False)
 
 # fields produced on the GPU (integer, string and enum columns: bit-exact parity; entropy within 1e-6 relative)
 DEVICE_INT_FIELDS = ["tid", "start", "end", "left", "right", "nb_raw_aln", "nb_dist_aln", "nb_ms_aln", "nb_um_aln",
@@ -79,7 +84,8 @@ class PjhReport(C.Structure):
                 ("t_open_s", C.c_double), ("t_genome_s", C.c_double), ("t_decode_s", C.c_double), ("t_gpu_ms", C.c_double),
                 ("t_finalize_s", C.c_double), ("t_write_s", C.c_double), ("t_total_s", C.c_double),
                 ("n_gpus_used", C.c_int32), ("n_kernel_launches", C.c_int32),
-                ("t_init_s", C.c_double), ("t_run_s", C.c_double), ("t_teardown_s", C.c_double)]
+                ("t_init_s", C.c_double), ("t_run_s", C.c_double), ("t_teardown_s", C.c_double),
+                ("t_extra_s", C.c_double)]
 
 
 # every symbol declared in include/*.h, with (restype, argtypes); used by load() and by the export test
@@ -103,6 +109,14 @@ SYMBOLS = {
     "pj_shard_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pj_shard_kernel_times": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "pj_junctions_finalize": (C.c_int, [_P, C.c_int64, C.c_double]),
+    "pj_extra_num_spliced_names": (C.c_int64, [_P]),
+    "pj_extra_export_names": (C.c_int, [_P, _P, C.c_int64]),
+    "pj_extra_import_names": (C.c_int, [_P, _P, C.c_int64]),
+    "pj_extra_run": (C.c_int, [_P, C.c_int32, _P, C.c_int64]),
+    "pj_extra_target_pileup": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
+    "pj_extra_coverage": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "pj_extra_coverage_source": (None, [C.c_int32, _P, _P]),
+    "pj_extra_finalize": (None, [_P, C.c_int64]),
     "pjh_options_default": (None, [C.POINTER(PjhOptions)]),
     "pjh_junc_run": (C.c_int, [C.POINTER(PjhOptions), C.POINTER(PjhReport)]),
     "pjh_last_error": (C.c_char_p, []),
@@ -114,9 +128,12 @@ SYMBOLS = {
     "pjh_prep_target_len": (C.c_int32, [_P, C.c_int32]),
     "pjh_prep_target_records": (C.c_int64, [_P, C.c_int32]),
     "pjh_prep_decode": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(PjBatch)]),
+    "pjh_prep_want_names": (None, [_P, C.c_int32]),
     "pjh_prep_genome": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
     "pjh_inflate_selftest": (C.c_int, [C.c_int32]),
     "pjh_plan_shards": (C.c_int, [_P, C.c_int32, _P]),
+    "pjh_write_outputs_extra": (C.c_int, [C.c_char_p, _P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,
+                                          C.c_int32, C.c_int32]),
     "pjh_write_outputs": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,
                                     C.c_int32, C.c_int32]),
 }

@@ -23,6 +23,12 @@ def batch_struct(cols):
         a = np.ascontiguousarray(cols[name], dtype=dt)
         keep.append(a)
         setattr(b, name, a.ctypes.data if a.size else None)
+    if cols.get("name_code") is not None:        # optional column: only the `--extra` metrics read it
+        a = np.ascontiguousarray(cols["name_code"], dtype=np.uint64)
+        if len(a) != n:
+            raise ValueError("name_code must have n_records entries")
+        keep.append(a)
+        b.name_code = a.ctypes.data if a.size else None
     if len(cols["cigar_off"]) != n + 1 or len(cols["seq_off"]) != n + 1:
         raise ValueError("cigar_off / seq_off must have n_records + 1 entries")
     return b, keep
@@ -48,6 +54,8 @@ def from_batch(b):
         out["seq_off"] = np.zeros(1, np.uint64)
     out["cigar"] = arr(b.cigar, int(out["cigar_off"][-1]), np.uint32)
     out["seq4"] = arr(b.seq4, int(out["seq_off"][-1]), np.uint8)
+    if b.name_code:
+        out["name_code"] = arr(b.name_code, n, np.uint64)
     return out
 
 
@@ -71,15 +79,35 @@ def encode_seq(seq):
     return bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(codes), 2))
 
 
+_M64 = (1 << 64) - 1
+
+
+def name_code(qname, flag):
+    """64-bit code of BamAlignment::deriveName() (bam_alignment.cc:233-242); same function as pjio::name_code."""
+    s = qname.encode() if isinstance(qname, str) else bytes(qname)
+    if flag & 0x1:
+        s += b"_R1" if flag & 0x40 else b"_R2" if flag & 0x80 else b"_R?"
+    h = 0xCBF29CE484222325
+    for c in s:
+        h = ((h ^ c) * 0x100000001B3) & _M64
+    h ^= h >> 33; h = (h * 0xFF51AFD7ED558CCD) & _M64
+    h ^= h >> 33; h = (h * 0xC4CEB9FE1A85EC53) & _M64
+    h ^= h >> 33
+    return h
+
+
 def from_records(records):
     """records: iterable of dicts(tid,pos,flag,mapq,xs,cigar(str),seq(str or None),mtid,mpos) in BAM order."""
     cols = {k: [] for k, _ in COLUMNS}
+    names = []
     cols["cigar_off"].append(0)
     cols["seq_off"].append(0)
     seq_bytes = bytearray()
     for r in records:
         cols["tid"].append(r["tid"]); cols["pos"].append(r["pos"]); cols["flag"].append(r.get("flag", 0))
         cols["mapq"].append(r.get("mapq", 60))
+        if "name" in r:
+            names.append(name_code(r["name"], r.get("flag", 0)))
         xs = r.get("xs", 0)
         cols["xs"].append(ord(xs) if isinstance(xs, str) else xs)
         seq = r.get("seq")
@@ -92,4 +120,8 @@ def from_records(records):
         cols["seq_off"].append(len(seq_bytes))
     out = {k: np.array(cols[k], dtype=dt) for k, dt in COLUMNS if k != "seq4"}
     out["seq4"] = np.frombuffer(bytes(seq_bytes), dtype=np.uint8).copy()
+    if names:
+        if len(names) != len(out["pos"]):
+            raise ValueError("either every record has a name or none has")
+        out["name_code"] = np.array(names, dtype=np.uint64)
     return out

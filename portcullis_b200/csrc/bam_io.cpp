@@ -113,7 +113,16 @@ bool BamHeader::coordinate_sorted() const {
 
 void ColumnarChunk::clear() {
     tid.clear(); pos.clear(); l_qseq.clear(); mtid.clear(); mpos.clear(); flag.clear(); mapq.clear(); xs.clear();
-    cigar_off.assign(1, 0); cigar.clear(); seq_off.assign(1, 0); seq4.clear();
+    cigar_off.assign(1, 0); cigar.clear(); seq_off.assign(1, 0); seq4.clear(); name_code.clear();
+}
+
+uint64_t name_code(const char* qname, size_t len, uint16_t flag) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    auto eat = [&](const char* s, size_t n) { for (size_t i = 0; i < n; i++) { h ^= (uint8_t)s[i]; h *= 0x100000001B3ull; } };
+    eat(qname, len);
+    if (flag & 0x1) eat((flag & 0x40) ? "_R1" : (flag & 0x80) ? "_R2" : "_R?", 3);
+    h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33;
+    return h;
 }
 
 void ColumnarChunk::append(const ColumnarChunk& o) {
@@ -127,6 +136,7 @@ void ColumnarChunk::append(const ColumnarChunk& o) {
     for (size_t i = 1; i < o.seq_off.size(); i++) seq_off.push_back(sb + o.seq_off[i]);
     cigar.insert(cigar.end(), o.cigar.begin(), o.cigar.end());
     seq4.insert(seq4.end(), o.seq4.begin(), o.seq4.end());
+    name_code.insert(name_code.end(), o.name_code.begin(), o.name_code.end());
 }
 
 void BamFile::open(const std::string& bam_path) {
@@ -344,6 +354,11 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
         out.tid.push_back(tid); out.pos.push_back(pos); out.flag.push_back(flag); out.mapq.push_back(mapq);
         out.l_qseq.push_back(l_seq); out.mtid.push_back(mtid); out.mpos.push_back(mpos);
         out.xs.push_back(find_xs(aux, p + bs));
+        if (out.with_names) {
+            size_t ln = l_name; const char* qn = (const char*)p + 32;
+            while (ln && qn[ln - 1] == 0) ln--;                 // l_read_name counts the NUL (and htslib >= 1.5 pads with more)
+            out.name_code.push_back(name_code(qn, strnlen(qn, ln), flag));
+        }
         size_t c0 = out.cigar.size(); out.cigar.resize(c0 + n_cig);
         if (n_cig) memcpy(&out.cigar[c0], cg, 4ull * n_cig);
         out.cigar_off.push_back((uint32_t)out.cigar.size());

@@ -81,6 +81,8 @@ struct ColumnarChunk {
     std::vector<uint32_t> cigar;
     std::vector<uint64_t> seq_off{0};      // n+1
     std::vector<uint8_t> seq4;
+    bool with_names = false;               // set before decode(): also fill name_code (the `--extra` metrics need it)
+    std::vector<uint64_t> name_code;
     int64_t n() const { return (int64_t)pos.size(); }
     void clear();
     void append(const ColumnarChunk& o);
@@ -108,6 +110,10 @@ private:
     BamHeader hdr_;
     std::vector<BamTargetIndex> idx_;
 };
+
+// 64-bit code of BamAlignment::deriveName() (bam_alignment.cc:233-242): QNAME, plus "_R1"/"_R2"/"_R?" when the read is
+// paired.  Stands in for std::hash<string> (junction.hpp:158): only equality matters.  FNV-1a then a 64-bit finaliser.
+uint64_t name_code(const char* qname, size_t len, uint16_t flag);
 
 int inflate_selftest(int n_cases);
 

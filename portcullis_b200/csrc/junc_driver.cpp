@@ -104,6 +104,7 @@ void chunk_view(const ColumnarChunk& c, pj_batch* b) {
     b->n_records = c.n(); b->tid = c.tid.data(); b->pos = c.pos.data(); b->flag = c.flag.data(); b->mapq = c.mapq.data(); b->xs = c.xs.data();
     b->l_qseq = c.l_qseq.data(); b->mtid = c.mtid.data(); b->mpos = c.mpos.data(); b->cigar_off = c.cigar_off.data(); b->cigar = c.cigar.data();
     b->seq_off = c.seq_off.data(); b->seq4 = c.seq4.data();
+    b->name_code = (c.with_names && (int64_t)c.name_code.size() == c.n()) ? c.name_code.data() : nullptr;
 }
 
 } // namespace
@@ -112,6 +113,7 @@ void chunk_view(const ColumnarChunk& c, pj_batch* b) {
 struct pjh_prep {
     PrepPaths paths; BamFile bam; FastaFile fasta; bool indexed = false;
     ColumnarChunk decoded; std::string genome; int32_t genome_tid = -1;
+    bool want_names = false;
     explicit pjh_prep(const std::string& d) : paths(d) {}
 };
 
@@ -178,14 +180,16 @@ int pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out) {
     const int32_t T = pjh_prep_n_targets(p);
     if (p->indexed) { for (int32_t t = (tid < 0 ? 0 : tid); t < (tid < 0 ? T : tid + 1); t++) p->bam.plan_target(t, 2u << 20, tasks); }
     else { DecodeTask w = p->bam.whole_file_task(); if (tid >= 0) { w.tid = tid; } tasks.push_back(w); }
-    p->decoded.clear();
+    p->decoded.clear(); p->decoded.with_names = p->want_names;
     int rc = ordered_pipeline<ColumnarChunk>(tasks.size(), threads, (size_t)threads * 3 + 2,
-        [&](size_t k, ColumnarChunk& c) { p->bam.decode(tasks[k], c); return PJ_OK; },
+        [&](size_t k, ColumnarChunk& c) { c.with_names = p->want_names; p->bam.decode(tasks[k], c); return PJ_OK; },
         [&](size_t, ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
     if (rc) return rc;
     chunk_view(p->decoded, out);
     return PJ_OK;
 }
+
+void pjh_prep_want_names(pjh_prep* p, int32_t on) { if (p) p->want_names = on != 0; }
 
 int pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bases) {
     if (!p || !bases || !n_bases || tid < 0 || tid >= pjh_prep_n_targets(p)) return fail(PJ_EINVAL, "pjh_prep_genome: bad argument");
@@ -200,6 +204,11 @@ int pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bas
 
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows, int32_t n_targets, const char* const* names,
                       const int32_t* lens, const char* source, const char* version, int32_t exon_gff, int32_t intron_gff) {
+    return pjh_write_outputs_extra(output_prefix, rows, nullptr, n_rows, n_targets, names, lens, source, version, exon_gff, intron_gff);
+}
+
+int pjh_write_outputs_extra(const char* output_prefix, const pj_junction* rows, const pj_junction_extra* extra, int64_t n_rows, int32_t n_targets,
+                            const char* const* names, const int32_t* lens, const char* source, const char* version, int32_t exon_gff, int32_t intron_gff) {
     if (!output_prefix || (n_rows && !rows) || !names || !lens) return fail(PJ_EINVAL, "pjh_write_outputs: null argument");
     try {
         std::vector<pjhost::TargetInfo> t((size_t)n_targets);
@@ -214,7 +223,7 @@ int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_
         wt.emplace_back([&]() { guarded([&]() { pjhost::write_bed(pre + ".junctions.bed", rows, n_rows, t, src, ver); }); });
         if (exon_gff) wt.emplace_back([&]() { guarded([&]() { pjhost::write_exon_gff(pre + ".junctions.exon.gff3", rows, n_rows, t, src); }); });
         if (intron_gff) wt.emplace_back([&]() { guarded([&]() { pjhost::write_intron_gff(pre + ".junctions.intron.gff3", rows, n_rows, t, src); }); });
-        guarded([&]() { pjhost::write_tab(pre + ".junctions.tab", rows, n_rows, t); });
+        guarded([&]() { pjhost::write_tab(pre + ".junctions.tab", rows, n_rows, t, extra); });
         for (auto& x : wt) x.join();
         if (!werr.empty()) return fail(PJ_EIO, werr);
     } catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
@@ -245,8 +254,9 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     pjh_report R; memset(&R, 0, sizeof R);
     const double t0 = now_s();
     const bool say = !o->quiet;
-    if (o->separate || o->extra)
-        return fail(PJ_EINVAL, "--separate / --extra are not part of the GPU junc path (they only feed the mm_score, coverage, up_aln and down_aln columns)");
+    if (o->separate)
+        return fail(PJ_EINVAL, "--separate (writing spliced / unspliced / unmapped BAM files) is not part of the GPU junc path; --extra does not need it here");
+    const bool extra = o->extra != 0;      // junction_builder.cc:113-117 turns --separate on for --extra; the metrics come from the records in HBM instead
     const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
     {   // output directory (junction_builder.cc:65-66, 86-91)
         fs::path parent = fs::path(prefix).parent_path();
@@ -286,7 +296,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     R.t_open_s = now_s() - t0;
     R.n_gpus_used = n_gpus;
 
-    struct GpuOut { std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int rc = PJ_OK; std::string err; };
+    struct GpuOut { pj_ctx* ctx = nullptr; std::vector<pj_junction_extra> extra; std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int rc = PJ_OK; std::string err; };
     std::vector<GpuOut> outs((size_t)n_gpus);
     const int threads_per_gpu = std::max(1, threads / n_gpus);
     const size_t window_per_gpu = (size_t)threads_per_gpu * 3 + 2;      // decoded-but-unsubmitted batches (pageable while CUDA starts, pinned after)
@@ -308,6 +318,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             pj_config cfg; memset(&cfg, 0, sizeof cfg);
             cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
             cfg.reserved[2] = (int32_t)window_per_gpu + 4;                 // pinned staging buffers
+            cfg.extra_metrics = extra ? 1 : 0;
             int r = pj_create(&cfg, &ctx);
             std::string em;
             if (r) em = pj_global_last_error();
@@ -346,6 +357,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
             memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
             memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
+            if (extra) memcpy((void*)st.name_code, ch.name_code.data(), n * 8);
             st.n_records = ch.n();
             return PJ_OK;
         };
@@ -356,6 +368,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         int r = ordered_pipeline<Payload>(tasks.size(), threads_per_gpu, window_per_gpu,
             [&](size_t k, Payload& p) -> int {
                 auto ch = std::make_unique<ColumnarChunk>();
+                ch->with_names = extra;
                 prep->bam.decode(tasks[k], *ch);
                 memset(&p.st, 0, sizeof p.st);
                 if (ch->n() == 0) return PJ_OK;
@@ -383,6 +396,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         if ((r = pj_shard_fetch(ctx, out.rows.data(), J, out.stats.data(), T))) return bail(r, pj_last_error(ctx));
         out.run_s = now_s() - tr;
         int32_t nl = 0; pj_shard_timing(ctx, &out.gpu_ms, &nl); out.launches = nl;
+        if (extra) { out.ctx = ctx; ctx = nullptr; }                       // the extra metrics need every shard's context: destroyed after that phase
     };
     if (say) std::cout << "Finding junctions and calculating basic metrics:\n - Sharding " << T << " target sequences over " << n_gpus << " GPU(s)" << std::endl;
     {
@@ -391,14 +405,72 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         run_gpu(0);
         for (auto& t : th) t.join();
     }
+    struct CtxGuard { std::vector<GpuOut>& o; ~CtxGuard() { for (auto& x : o) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; } } } ctx_guard{outs};
     for (auto& out : outs) if (out.rc) return fail(out.rc, out.err);
+    if (extra) {
+        // ---- calcExtraMetrics (junction_builder.cc:293-312) over the records resident on the GPUs ----
+        const double tx = now_s();
+        if (say) std::cout << "Calculating extra junction metrics:" << std::endl;
+        int32_t maxq_all = 0;
+        for (int g = 0; g < n_gpus; g++) for (int32_t t : shard[(size_t)g]) maxq_all = std::max(maxq_all, outs[g].stats[t].max_query_length);
+        if (!prep->indexed) for (auto& st : outs[0].stats) maxq_all = std::max(maxq_all, st.max_query_length);
+        // spliced read names of the whole file on every GPU (the reference's map spans the BAM, junction_builder.cc:179-186)
+        if (n_gpus > 1) {
+            std::vector<std::vector<uint64_t>> names((size_t)n_gpus);
+            for (int g = 0; g < n_gpus; g++) {
+                names[g].resize((size_t)std::max<int64_t>(pj_extra_num_spliced_names(outs[g].ctx), 0));
+                if ((rc = pj_extra_export_names(outs[g].ctx, names[g].data(), (int64_t)names[g].size()))) return fail(rc, pj_last_error(outs[g].ctx));
+            }
+            for (int g = 0; g < n_gpus; g++) for (int h = 0; h < n_gpus; h++)
+                if (h != g && (rc = pj_extra_import_names(outs[g].ctx, names[h].data(), (int64_t)names[h].size()))) return fail(rc, pj_last_error(outs[g].ctx));
+        }
+        {
+            std::vector<std::thread> th; std::vector<int> xr((size_t)n_gpus, PJ_OK);
+            auto one = [&](int g) { outs[g].extra.resize(outs[g].rows.size()); xr[g] = pj_extra_run(outs[g].ctx, maxq_all, outs[g].extra.data(), (int64_t)outs[g].extra.size()); };
+            for (int g = 1; g < n_gpus; g++) th.emplace_back(one, g);
+            one(0);
+            for (auto& t : th) t.join();
+            for (int g = 0; g < n_gpus; g++) if (xr[g]) return fail(xr[g], pj_last_error(outs[g].ctx));
+        }
+        // coverage: depth vector of the previous covered target (Q14), wherever that target lives
+        std::vector<int32_t> owner((size_t)T, 0);
+        for (int g = 0; g < n_gpus; g++) for (int32_t t : shard[(size_t)g]) owner[t] = g;
+        std::vector<uint8_t> covered((size_t)T, 0); std::vector<int32_t> src((size_t)T, -1);
+        for (int32_t t = 0; t < T; t++) {
+            int32_t cv = 0; uint32_t live = 0;
+            if ((rc = pj_extra_target_pileup(outs[owner[t]].ctx, t, &cv, &live))) return fail(rc, pj_last_error(outs[owner[t]].ctx));
+            covered[t] = (uint8_t)cv;
+            if (live >= 8000)
+                std::cerr << "Warning: " << live << " unspliced alignments pile up on " << H.names[t] << "; htslib's pileup (used by the reference) stops accepting reads at 8000 per "
+                             "position, this implementation does not: the coverage column can differ from the reference around that locus\n";
+        }
+        pj_extra_coverage_source(T, covered.data(), src.data());
+        for (int g = 0; g < n_gpus; g++) {
+            auto& rws = outs[g].rows;
+            for (size_t a = 0; a < rws.size();) {
+                size_t b = a; while (b < rws.size() && rws[b].tid == rws[a].tid) b++;
+                const int32_t t = rws[a].tid, d = src[t];
+                if (d >= 0) {
+                    std::vector<int32_t> st(b - a), en(b - a); std::vector<uint32_t> sums((b - a) * 4);
+                    for (size_t k = a; k < b; k++) { st[k - a] = rws[k].start; en[k - a] = rws[k].end; }
+                    pj_ctx* dc = outs[owner[d]].ctx;
+                    if ((rc = pj_extra_coverage(dc, d, (int64_t)(b - a), st.data(), en.data(), sums.data()))) return fail(rc, pj_last_error(dc));
+                    for (size_t k = a; k < b; k++) memcpy(outs[g].extra[k].cov_sum, &sums[(k - a) * 4], 16);
+                }
+                a = b;
+            }
+        }
+        for (auto& x : outs) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; }
+        R.t_extra_s = now_s() - tx;
+    }
     // ---- gather (junction_builder.cc:249-283) ----
     const double tf = now_s();
-    std::vector<pj_junction> rows;
+    std::vector<pj_junction> rows; std::vector<pj_junction_extra> xrows;
     std::vector<pj_target_stats> stats((size_t)T);
     for (int32_t t = 0; t < T; t++) { stats[t] = pj_target_stats{0, 0, 0, INT32_MAX, 0}; }
     for (int g = 0; g < n_gpus; g++) {
         rows.insert(rows.end(), outs[g].rows.begin(), outs[g].rows.end());
+        xrows.insert(xrows.end(), outs[g].extra.begin(), outs[g].extra.end());
         for (int32_t t : shard[(size_t)g]) stats[t] = outs[g].stats[t];
         if (!prep->indexed) stats = outs[g].stats;
         R.t_gpu_ms = std::max<double>(R.t_gpu_ms, outs[g].gpu_ms); R.n_kernel_launches += outs[g].launches;
@@ -416,6 +488,16 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     }
     const uint64_t total = spliced + unspliced;
     const double mean_q = (double)sumq / (double)total;
+    if (extra) {     // bring rows and their extra columns into the final (tid, start, end) order together
+        std::vector<size_t> ord(rows.size()); for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+            const pj_junction &x = rows[a], &y = rows[b];
+            return x.tid != y.tid ? x.tid < y.tid : x.start != y.start ? x.start < y.start : x.end < y.end; });
+        std::vector<pj_junction> r2(rows.size()); std::vector<pj_junction_extra> x2(rows.size());
+        for (size_t i = 0; i < ord.size(); i++) { r2[i] = rows[ord[i]]; x2[i] = xrows[ord[i]]; }
+        rows.swap(r2); xrows.swap(x2);
+        pj_extra_finalize(xrows.data(), (int64_t)xrows.size());
+    }
     if ((rc = pj_junctions_finalize(rows.data(), (int64_t)rows.size(), mean_q))) return fail(rc, "finalize failed");
     R.t_finalize_s = now_s() - tf;
     if (say) {
@@ -426,8 +508,8 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     const double tw = now_s();
     {
         std::vector<const char*> names((size_t)T); for (int32_t t = 0; t < T; t++) names[t] = H.names[t].c_str();
-        rc = pjh_write_outputs(prefix.c_str(), rows.data(), (int64_t)rows.size(), T, names.data(), H.lens.data(), o->source ? o->source : "portcullis",
-                               o->version ? o->version : "1.2.4", o->exon_gff, o->intron_gff);
+        rc = pjh_write_outputs_extra(prefix.c_str(), rows.data(), extra ? xrows.data() : nullptr, (int64_t)rows.size(), T, names.data(), H.lens.data(),
+                                     o->source ? o->source : "portcullis", o->version ? o->version : "1.2.4", o->exon_gff, o->intron_gff);
         if (rc) return rc;
     }
     R.t_write_s = now_s() - tw;
@@ -483,6 +565,8 @@ static void junc_usage() {
                  "  -t [ --threads ] arg (=1)         The number of host threads used to decode the BAM file.\n"
                  "  --gpus arg (=1)                   The number of GPUs to shard target sequences over.\n"
                  "  --separate                        Separate spliced from unspliced reads (not available on the GPU path).\n"
+                 "  --extra                           Calculate the additional metrics mm_score, coverage, up_aln and down_aln (from the\n"
+                 "                                    records on the GPU; no separated BAM files are written).\n"
                  "  --orientation arg (=UNKNOWN)      The orientation of the reads that produced the BAM alignments: \"SE\", \"FR\", \"RF\", \"FF\", \"UNKNOWN\".\n"
                  "  --strandedness arg (=UNKNOWN)     \"unstranded\", \"firststrand\", \"secondstrand\" or \"UNKNOWN\".\n"
                  "  -c [ --use_csi ]                  Whether to use CSI indexing rather than BAI indexing.\n"

@@ -9,6 +9,36 @@
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
+// `--extra` metrics, host part.
+// Q14: DepthParser::loadNextBatch fills `depths` for target c_k but leaves last.ref on the NEXT covered target c_k+1
+// (depth_parser.cc:159-163), and JunctionSystem::calcCoverage asks getCurrentRefIndex() (depth_parser.hpp:94-96) which
+// junctions to update (junction_system.cc:231-243).  So the junctions of c_k+1 are scored against the depth of c_k; only
+// after the final batch (res == 0) does last.ref still name the batch's own target, which overwrites the last one.
+// ------------------------------------------------------------------------------------------------
+extern "C" void pj_extra_coverage_source(int32_t n_targets, const uint8_t* covered, int32_t* depth_src) {
+    int32_t prev = -1, last = -1;
+    for (int32_t t = 0; t < n_targets; t++) {
+        depth_src[t] = -1;
+        if (!covered[t]) continue;
+        depth_src[t] = prev;            // -1 for the first covered target: its junctions are never visited ...
+        prev = t; last = t;
+    }
+    if (last >= 0) depth_src[last] = last;   // ... unless it is also the last one
+}
+
+// Junction::calcMultipleMappingScore (junction.cc:914-921) and calcCoverage (:935-951): same operands, same order.
+extern "C" void pj_extra_finalize(pj_junction_extra* x, int64_t n) {
+    for (int64_t i = 0; i < n; i++) {
+        pj_junction_extra& e = x[i];
+        e.mm_score = (double)(size_t)e.mm_n / (double)e.mm_m;
+        const double m10 = 1.0 / (double)(10 - 1), m11 = 1.0 / (double)10;          // multiplier = 1.0 / (b - a) for the 10- and 11-base windows
+        const double donor = m10 * (double)e.cov_sum[0] - m11 * (double)e.cov_sum[1];
+        const double acceptor = m11 * (double)e.cov_sum[2] - m10 * (double)e.cov_sum[3];
+        e.coverage = donor + acceptor;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A12/A13.  Reference: JunctionBuilder::findJunctions tail (src/junction_builder.cc:270-290),
 // JunctionSystem::sort/index (lib/src/junction_system.cc:322-330), calcJunctionStats (:250-320),
 // createJunctionGroup (:55-70).  Expressed here as passes over the sorted row array.
@@ -145,7 +175,7 @@ std::string tab_header() {
     return h;
 }
 
-void write_tab(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets) {
+void write_tab(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets, const pj_junction_extra* extra) {
     Out o(path);
     o.s(tab_header()); o.c('\n');
     for (int64_t r = 0; r < n; r++) target_of(targets, rows[r].tid);          // validate before going parallel
@@ -173,7 +203,8 @@ void write_tab(const std::string& path, const pj_junction* rows, int64_t n, cons
         o.u(j.uniq_junc); o.c('\t'); o.u(j.primary_junc); o.c('\t');
         o.u(j.nb_up_juncs); o.c('\t'); o.u(j.nb_down_juncs); o.c('\t');
         o.u(j.dist_2_up_junc); o.c('\t'); o.u(j.dist_2_down_junc); o.c('\t'); o.u(j.dist_nearest_junc); o.c('\t');
-        o.s("0\t0\t0\t0\t1");                                          // mm_score, coverage, up_aln, down_aln, nb_samples
+        if (!extra) o.s("0\t0\t0\t0\t1");                              // mm_score, coverage, up_aln, down_aln, nb_samples
+        else { const pj_junction_extra& x = extra[r]; o.g(x.mm_score); o.c('\t'); o.g(x.coverage); o.c('\t'); o.u(x.up_aln); o.c('\t'); o.u(x.down_aln); o.s("\t1"); }
         for (int k = 0; k < PJ_NB_JAD; k++) { o.c('\t'); o.u(j.jad[k]); }
         o.c('\n');
     });

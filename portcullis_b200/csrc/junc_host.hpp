@@ -12,7 +12,8 @@ struct TargetInfo { std::string name; int32_t length; };
 
 // JunctionSystem::saveAll (lib/src/junction_system.cc:336-383): <prefix>.junctions.tab, .bed and optional GFFs.
 // `version` is the string of the BED track line (JunctionSystem::version; "X.X.X" when empty).
-void write_tab(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets);
+// extra: the `--extra` columns (mm_score, coverage, up_aln, down_aln) per row, or nullptr to print them as 0 like plain `junc`
+void write_tab(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets, const pj_junction_extra* extra = nullptr);
 void write_bed(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
                const std::string& source, const std::string& version);
 void write_exon_gff(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,

@@ -1,7 +1,6 @@
 // pj_api.cu — the extern "C" layer of include/portcullis_junc.h: context, genome residency, double-buffered
 // pinned staging, shard arena in HBM and the kernel pipeline driver.  One context = one B200.
-#include "junc_launch.hpp"
-#include <cuda_runtime.h>
+#include "pj_ctx.hpp"
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -16,68 +15,9 @@
 
 using namespace pjk;
 
-namespace {
+namespace pjapi {
 
 thread_local std::string g_last_error;
-
-template <typename T> struct DevBuf {
-    T* p = nullptr; size_t cap = 0;
-    void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct StagingSlot {
-    // one pinned host block carved into the columns of a pj_batch
-    uint8_t* block = nullptr; size_t block_bytes = 0;
-    int32_t *tid = nullptr, *pos = nullptr, *l_qseq = nullptr, *mtid = nullptr, *mpos = nullptr;
-    uint16_t* flag = nullptr; uint8_t *mapq = nullptr, *xs = nullptr;
-    uint32_t *cigar_off = nullptr, *cigar = nullptr; uint64_t* seq_off = nullptr; uint8_t* seq4 = nullptr;
-    int64_t cap_rec = 0, cap_cig = 0, cap_seq = 0;
-    cudaEvent_t done = nullptr;
-    int state = 0;                         // 0 free, 1 handed out (being filled / waiting for submit), 2 copy in flight
-    uint64_t seq_no = 0;                   // submit order, to find the oldest in-flight slot
-};
-
-struct StageTime { const char* name; cudaEvent_t ev; };
-
-} // namespace
-
-struct pj_ctx {
-    int device = 0; int orientation = PJ_ORIENT_UNKNOWN; int match_group = 0; int n_sm = 148; int legacy_sort = 0;
-    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
-    std::string err;
-    // targets / genome
-    int32_t n_targets = 0;
-    std::vector<int32_t> h_tlen; std::vector<uint64_t> h_toff, h_goff; std::vector<int64_t> h_glen;
-    int32_t* d_tlen = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_goff = nullptr; int64_t* d_glen = nullptr;
-    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint8_t* d_g4 = nullptr; uint64_t g_total_bases = 0;
-    uint64_t* d_exc_pos = nullptr; uint8_t* d_exc_byte = nullptr; uint32_t* d_exc_count = nullptr; uint32_t exc_cap = 1u << 20;
-    int32_t n_exc = 0, n_exc_x = 0, n_zero_code = 0; bool genome_dirty = false;
-    uint8_t* h_graw[2] = {nullptr, nullptr}; uint8_t* d_graw[2] = {nullptr, nullptr}; cudaEvent_t graw_ev[2] = {nullptr, nullptr};
-    static constexpr size_t GRAW_CHUNK = 64u << 20;
-    // shard arena
-    bool shard_open = false;
-    int64_t n_rec = 0; uint64_t n_cig = 0, n_seq = 0;
-    DevBuf<int32_t> tid, pos, l_qseq, mtid, mpos; DevBuf<uint16_t> flag; DevBuf<uint8_t> mapq, xs, seq4;
-    DevBuf<uint32_t> cigar_off, cigar; DevBuf<uint64_t> seq_off;
-    std::vector<StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
-    std::thread prewarm_thread;         // grows the stream-ordered memory pool while the caller is still decoding
-    std::mutex staging_mu;              // pj_staging_acquire / pj_batch_submit may be called from several host threads
-    cudaStream_t genome_stream = nullptr;
-    cudaEvent_t copies_done = nullptr;
-    // per-target accumulators + misc device scalars
-    unsigned long long *d_spliced = nullptr, *d_unspliced = nullptr, *d_sumq = nullptr; int32_t *d_minq = nullptr, *d_maxq = nullptr;
-    uint32_t* d_scalars = nullptr;    // [0]=err [1]=max_nlen [2]=P [3]=J [4]=E [5]=scratch total [6]=tile ticket
-    unsigned long long* d_shard_acc = nullptr;   // [0] (low 32 bits) longest N op, [1] number of N ops of the shard: filled while batches are copied in
-    uint32_t* h_scalars = nullptr;    // pinned mirror
-    // results
-    pj_junction* d_rows = nullptr; size_t rows_cap = 0; int64_t n_junc = 0; uint64_t n_pairs = 0;
-    bool have_result = false;
-    // timing
-    std::vector<StageTime> stages; size_t n_stage = 0; float total_ms = 0; int n_launches = 0;
-    std::vector<float> stage_ms; std::vector<const char*> stage_names;
-};
-
-namespace {
 
 int fail(pj_ctx* c, int code, const char* fmt, ...) {
     char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
@@ -86,24 +26,17 @@ int fail(pj_ctx* c, int code, const char* fmt, ...) {
     return code;
 }
 
-#define CU(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((c), PJ_ECUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
+} // namespace pjapi
 
-template <typename T> int ensure(pj_ctx* c, DevBuf<T>& b, size_t need, size_t keep, cudaStream_t st) {
-    if (need <= b.cap) return PJ_OK;
-    size_t ncap = std::max(need, b.cap + b.cap / 2 + 1024);
-    T* np = nullptr;
-    CU(c, cudaMalloc(&np, ncap * sizeof(T)));
-    if (b.p && keep) CU(c, cudaMemcpyAsync(np, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    if (b.p) { CU(c, cudaStreamSynchronize(st)); cudaFree(b.p); }
-    b.p = np; b.cap = ncap;
-    return PJ_OK;
-}
+using namespace pjapi;
+
+namespace {
 
 void free_slot(StagingSlot& s) {
     if (s.block) cudaFreeHost(s.block);
     s.block = nullptr; s.block_bytes = 0;
     s.tid = s.pos = s.l_qseq = s.mtid = s.mpos = nullptr; s.flag = nullptr; s.mapq = s.xs = s.seq4 = nullptr;
-    s.cigar_off = s.cigar = nullptr; s.seq_off = nullptr; s.cap_rec = s.cap_cig = s.cap_seq = 0;
+    s.cigar_off = s.cigar = nullptr; s.seq_off = nullptr; s.name_code = nullptr; s.cap_rec = s.cap_cig = s.cap_seq = 0;
 }
 
 int alloc_slot(pj_ctx* c, StagingSlot& s, int64_t cr, int64_t cc, int64_t cs) {
@@ -112,15 +45,16 @@ int alloc_slot(pj_ctx* c, StagingSlot& s, int64_t cr, int64_t cc, int64_t cs) {
     free_slot(s);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t r = (size_t)cr;
-    const size_t sz[12] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r),
-                           up((r + 1) * 4), up((size_t)cc * 4), up((r + 1) * 8), up((size_t)cs + 16)};
+    const size_t sz[13] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r),
+                           up((r + 1) * 4), up((size_t)cc * 4), up((r + 1) * 8), up((size_t)cs + 16), c->extra ? up(r * 8) : 0};
     size_t total = 0; for (size_t v : sz) total += v;
     CU(c, cudaMallocHost((void**)&s.block, total));
     s.block_bytes = total;
     uint8_t* p = s.block; size_t k = 0;
     s.tid = (int32_t*)p; p += sz[k++]; s.pos = (int32_t*)p; p += sz[k++]; s.l_qseq = (int32_t*)p; p += sz[k++]; s.mtid = (int32_t*)p; p += sz[k++];
     s.mpos = (int32_t*)p; p += sz[k++]; s.flag = (uint16_t*)p; p += sz[k++]; s.mapq = p; p += sz[k++]; s.xs = p; p += sz[k++];
-    s.cigar_off = (uint32_t*)p; p += sz[k++]; s.cigar = (uint32_t*)p; p += sz[k++]; s.seq_off = (uint64_t*)p; p += sz[k++]; s.seq4 = p;
+    s.cigar_off = (uint32_t*)p; p += sz[k++]; s.cigar = (uint32_t*)p; p += sz[k++]; s.seq_off = (uint64_t*)p; p += sz[k++]; s.seq4 = p; p += sz[k++];
+    s.name_code = c->extra ? (uint64_t*)p : nullptr;
     s.cap_rec = cr; s.cap_cig = cc; s.cap_seq = cs;
     s.cigar_off[0] = 0; s.seq_off[0] = 0;
     return PJ_OK;
@@ -194,6 +128,7 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
     CU(c, cudaStreamCreateWithFlags(&c->genome_stream, cudaStreamNonBlocking));
     for (int s = 0; s < 2; s++) CU(c, cudaEventCreateWithFlags(&c->graw_ev[s], cudaEventDisableTiming));
     c->max_slots = cfg->reserved[2] > 0 ? std::max(2, cfg->reserved[2]) : 4;
+    c->extra = cfg->extra_metrics != 0;
     CU(c, cudaMalloc(&c->d_scalars, 16 * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->d_shard_acc, 2 * sizeof(unsigned long long)));
     CU(c, cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(uint32_t)));
@@ -215,7 +150,8 @@ void pj_destroy(pj_ctx* c) {
     cudaDeviceSynchronize();
     lap("sync");
     c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
-    c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_();
+    c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_(); c->name_code.free_();
+    extra_reset(c);
     lap("arena");
     for (StagingSlot* sl : c->slots) { free_slot(*sl); if (sl->done) cudaEventDestroy(sl->done); delete sl; }
     lap("pinned staging");
@@ -296,6 +232,7 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     if (!c || !c->n_targets) return fail(c, PJ_ESTATE, "pj_shard_begin: call pj_targets_set first");
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->compute_stream));
+    extra_reset(c);
     c->n_rec = 0; c->n_cig = 0; c->n_seq = 16; c->have_result = false;   // SEQ stream: 16-byte lead pad (k_match may look back up to 15 nibbles) c->n_junc = 0; c->n_pairs = 0;
     cudaStream_t st = c->copy_stream;
     const size_t r = (size_t)std::max<int64_t>(n_records_hint, 1024);
@@ -305,6 +242,7 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
         (rc = ensure(c, c->mapq, r, 0, st)) || (rc = ensure(c, c->xs, r, 0, st)) || (rc = ensure(c, c->cigar_off, r + 1, 0, st)) ||
         (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024), 0, st)) ||
         (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 48, 0, st))) return rc;
+    if (c->extra && (rc = ensure(c, c->name_code, r, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 2 * sizeof(unsigned long long), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
@@ -358,6 +296,7 @@ int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_
     StagingSlot& s = *pick;
     out->n_records = 0; out->tid = s.tid; out->pos = s.pos; out->flag = s.flag; out->mapq = s.mapq; out->xs = s.xs; out->l_qseq = s.l_qseq;
     out->mtid = s.mtid; out->mpos = s.mpos; out->cigar_off = s.cigar_off; out->cigar = s.cigar; out->seq_off = s.seq_off; out->seq4 = s.seq4;
+    out->name_code = s.name_code;
     return PJ_OK;
 }
 
@@ -369,6 +308,7 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
     if (n == 0) return PJ_OK;
     if (!b->tid || !b->pos || !b->flag || !b->mapq || !b->xs || !b->l_qseq || !b->mtid || !b->mpos || !b->cigar_off || !b->seq_off)
         return fail(c, PJ_EINVAL, "pj_batch_submit: null column");
+    if (c->extra && !b->name_code) return fail(c, PJ_EINVAL, "pj_batch_submit: the context computes the extra metrics, so batches must carry name_code");
     CU(c, cudaSetDevice(c->device));
     const uint32_t cb = b->cigar_off[0], ce = b->cigar_off[n];
     const uint64_t sb = b->seq_off[0], se = b->seq_off[n];
@@ -384,11 +324,13 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
         (rc = ensure(c, c->mapq, need, R, st)) || (rc = ensure(c, c->xs, need, R, st)) || (rc = ensure(c, c->cigar_off, need + 1, R + 1, st)) ||
         (rc = ensure(c, c->seq_off, need + 1, R + 1, st)) || (rc = ensure(c, c->cigar, (size_t)(c->n_cig + ncig), (size_t)c->n_cig, st)) ||
         (rc = ensure(c, c->seq4, (size_t)(c->n_seq + nseq) + 16, (size_t)c->n_seq, st))) return rc;
+    if (c->extra && (rc = ensure(c, c->name_code, need, R, st))) return rc;
     const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
     CU(c, cudaMemcpyAsync(c->tid.p + R, b->tid, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->pos.p + R, b->pos, n * 4, H2D, st));
     CU(c, cudaMemcpyAsync(c->l_qseq.p + R, b->l_qseq, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->mtid.p + R, b->mtid, n * 4, H2D, st));
     CU(c, cudaMemcpyAsync(c->mpos.p + R, b->mpos, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->flag.p + R, b->flag, n * 2, H2D, st));
     CU(c, cudaMemcpyAsync(c->mapq.p + R, b->mapq, n, H2D, st)); CU(c, cudaMemcpyAsync(c->xs.p + R, b->xs, n, H2D, st));
+    if (c->extra) CU(c, cudaMemcpyAsync(c->name_code.p + R, b->name_code, n * 8, H2D, st));
     CU(c, cudaMemcpyAsync(c->cigar_off.p + R + 1, b->cigar_off + 1, n * 4, H2D, st));
     CU(c, cudaMemcpyAsync(c->seq_off.p + R + 1, b->seq_off + 1, n * 8, H2D, st));
     if (ncig) {
@@ -538,11 +480,13 @@ int pj_shard_run(pj_ctx* c) {
         if (c->rows_cap < J) { if (c->d_rows) { CU(c, cudaStreamSynchronize(st)); cudaFree(c->d_rows); } c->rows_cap = (size_t)J + J / 4 + 16; CU(c, cudaMalloc(&c->d_rows, c->rows_cap * sizeof(pj_junction))); }
         launch_finalize(J, seg_start, A, G, entropy, c->d_rows, d_err, st); c->n_launches++;
         mark(c, "finalize");
+        if (c->extra && (rc = extra_keep_pairs(c, P, vals, jid, pa, st))) return rc;
         CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(fs_scratch, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
         CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st));
     }
     for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pa, (void*)pb, (void*)pc, (void*)pd, (void*)se_status})
         if (p) CU(c, cudaFreeAsync(p, st));
+    if (c->extra && (rc = extra_classify(c, st))) return rc;
     mark(c, "end");
     CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));

@@ -1,0 +1,400 @@
+// pj_extra.cu — the hidden `--extra` metrics of `junc` on the columnar records already in HBM.
+//
+// Reference: JunctionBuilder::separateBams + calcExtraMetrics (/root/reference/src/junction_builder.cc:152-226, 293-312)
+//   mm_score          Junction::calcMultipleMappingScore   lib/src/junction.cc:914-921   (name map: junction_builder.cc:179-186)
+//   up_aln / down_aln Junction::processJunctionVicinity     lib/src/junction.cc:651-677   (region query on unspliced.bam)
+//   coverage          Junction::calcCoverage                lib/src/junction.cc:923-951   (DepthParser, lib/src/depth_parser.cc:112-167)
+//
+// The reference re-reads two BAM files it has just written; here the same record classes are views of the shard arena:
+//   spliced   = any N op (bam_alignment.cc:294-301); unspliced = not spliced and mapped (junction_builder.cc:188-191).
+// Kernels (all HBM-bound integer work, grids sized from the data):
+//   k_x_classify    one thread per record: class, reference span, spliced name codes compacted with warp-aggregated atomics
+//   k_x_scatter     unspliced records compacted in BAM order (offsets from the library's exclusive scan)
+//   k_x_names_add   open-addressing table name code -> number of spliced alignments (atomicCAS + atomicAdd)
+//   k_x_mm          one thread per (read, junction) pair: table lookup, integer atomics into mm_n / mm_m
+//   k_x_flank       one warp per junction: binary searches into the unspliced start positions, lanes stride the window
+//   k_x_live/k_x_depth  +1/-1 difference arrays per target, turned into depth vectors by the exclusive scan
+//   k_x_max         per-target maximum of the live-read vector (htslib's 8000-read cap binds iff it reaches 8000)
+//   k_x_coverage    one thread per (junction, window): the four read-count sums of Junction::calcCoverage
+#include "pj_ctx.hpp"
+#include <climits>
+#include <cstring>
+
+using namespace pjk;
+using namespace pjapi;
+
+namespace {
+
+constexpr uint64_t X_EMPTY = ~0ull;
+constexpr uint32_t XERR_NOCIGAR = 1u;      // mapped unspliced record without CIGAR: htslib's pileup asserts (sam.c:1537)
+constexpr uint32_t XERR_UNSORTED = 2u;     // unspliced records not in (tid, pos) order
+
+__device__ __forceinline__ uint64_t x_mix(uint64_t h) { h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull; h ^= h >> 33; return h; }
+__device__ __forceinline__ uint64_t x_key(uint64_t code) { return code == X_EMPTY ? X_EMPTY - 1 : code; }
+
+__global__ void __launch_bounds__(256) k_x_classify(int64_t n, const uint32_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar,
+                                                     const uint16_t* __restrict__ flag, const int32_t* __restrict__ tid, const uint64_t* __restrict__ name_code,
+                                                     int32_t n_targets, uint32_t* __restrict__ uflag, int32_t* __restrict__ alen_out,
+                                                     uint64_t* __restrict__ names_out, unsigned long long* __restrict__ n_spliced, uint32_t* __restrict__ err) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool spliced = false; bool uns = false; int32_t alen = 0;
+    if (r < n) {
+        const uint32_t c0 = cigar_off[r], c1 = cigar_off[r + 1];
+        for (uint32_t k = c0; k < c1; k++) {
+            const uint32_t w = __ldg(cigar + k); const uint32_t op = w & 15u;
+            if (op == 3u) spliced = true;
+            if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) alen += (int32_t)(w >> 4);      // bam_alignment.cc:78-88
+        }
+        const int32_t t = tid[r];
+        uns = !spliced && !(flag[r] & 0x4u) && t >= 0 && t < n_targets;
+        if (uns && c1 == c0) { atomicOr(err, XERR_NOCIGAR); uns = false; }
+        uflag[r] = uns ? 1u : 0u;
+        alen_out[r] = alen;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, spliced);
+    if (spliced) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(n_spliced, (unsigned long long)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        names_out[base + __popc(m & ((1u << lane) - 1u))] = name_code[r];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_x_scatter(int64_t n, const uint32_t* __restrict__ uflag, const uint32_t* __restrict__ uoff,
+                                                    const int32_t* __restrict__ tid, const int32_t* __restrict__ pos, const int32_t* __restrict__ alen,
+                                                    int32_t* __restrict__ u_tid, int32_t* __restrict__ u_pos, int32_t* __restrict__ u_alen, uint32_t* __restrict__ u_rid,
+                                                    int32_t* __restrict__ maxspan, uint8_t* __restrict__ covered) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !uflag[r]) return;
+    const uint32_t i = uoff[r];
+    const int32_t t = tid[r], a = alen[r];
+    u_tid[i] = t; u_pos[i] = pos[r]; u_alen[i] = a; u_rid[i] = (uint32_t)r;
+    if (a > maxspan[t]) atomicMax(maxspan + t, a);      // racy pre-check only skips atomics that cannot raise the maximum
+    if (a > 0) covered[t] = 1;
+}
+
+// u_toff[t] = first unspliced index of target t (T + 1 entries); also checks the (tid, pos) order the searches rely on
+__global__ void __launch_bounds__(256) k_x_toff(uint32_t U, const int32_t* __restrict__ u_tid, const int32_t* __restrict__ u_pos, int32_t T,
+                                                 uint32_t* __restrict__ u_toff, uint32_t* __restrict__ err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > U) return;
+    const int32_t prev = i == 0 ? -1 : u_tid[i - 1];
+    const int32_t cur = i == U ? T : u_tid[i];
+    if (cur < prev || (i > 0 && i < U && cur == prev && u_pos[i] < u_pos[i - 1])) { atomicOr(err, XERR_UNSORTED); return; }
+    for (int32_t t = prev + 1; t <= cur; t++) u_toff[t] = i;
+}
+
+__global__ void __launch_bounds__(256) k_x_names_add(int64_t n, const uint64_t* __restrict__ codes, uint64_t* __restrict__ keys, uint32_t* __restrict__ counts, uint64_t mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = x_key(codes[i]);
+    uint64_t s = x_mix(k) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + s), (unsigned long long)X_EMPTY, (unsigned long long)k);
+        if (old == X_EMPTY || old == k) { atomicAdd(counts + s, 1u); return; }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_x_mm(uint32_t P, const uint32_t* __restrict__ pair_rid, const uint32_t* __restrict__ pair_jid, const uint64_t* __restrict__ name_code,
+                                               const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t mask, pj_junction_extra* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const uint64_t k = x_key(name_code[pair_rid[i]]);
+    uint64_t s = x_mix(k) & mask;
+    uint32_t cnt = 0;
+    for (;;) {
+        const uint64_t cur = keys[s];
+        if (cur == k) { cnt = counts[s] & 0xffffu; break; }       // map values are uint16_t (junction.hpp:38)
+        if (cur == X_EMPTY) break;                                 // operator[] on a missing name inserts 0
+        s = (s + 1) & mask;
+    }
+    pj_junction_extra* o = out + pair_jid[i];
+    atomicAdd(&o->mm_n, 1u);
+    atomicAdd(&o->mm_m, cnt);                                      // uint32 sum, wraps like `uint32_t M` (junction.cc:916)
+}
+
+__device__ __forceinline__ uint32_t x_lower(const int32_t* __restrict__ a, uint32_t lo, uint32_t hi, int64_t v) {     // first index with a[i] >= v
+    while (lo < hi) { const uint32_t m = lo + ((hi - lo) >> 1); if ((int64_t)a[m] < v) lo = m + 1; else hi = m; }
+    return lo;
+}
+
+// Junction::processJunctionVicinity (junction.cc:651-677): one warp per junction.  The region query is htslib's
+// iterator (hts.c:1944-1960): records of the target with pos < regionEnd and bam_endpos > regionStart.
+__global__ void __launch_bounds__(256) k_x_flank(uint32_t J, const pj_junction* __restrict__ rows, const int32_t* __restrict__ tlen, const uint32_t* __restrict__ u_toff,
+                                                  const int32_t* __restrict__ u_pos, const int32_t* __restrict__ u_alen, const int32_t* __restrict__ maxspan,
+                                                  int32_t max_query_length, pj_junction_extra* __restrict__ out) {
+    const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; const int lane = threadIdx.x & 31;
+    if (j >= J) return;
+    const pj_junction* q = rows + j;
+    const int32_t t = q->tid, start = q->start, end = q->end, left = q->left, right = q->right;
+    const int32_t refLength = tlen[t];
+    int32_t regionStart = left - max_query_length - 1; regionStart = regionStart < 0 ? 0 : regionStart;
+    int32_t regionEnd = right + max_query_length + 1; regionEnd = regionEnd >= refLength ? refLength - 1 : regionEnd;
+    uint32_t nl = 0, nr = 0;
+    if (regionEnd > regionStart) {
+        const uint32_t lo = u_toff[t], hi = u_toff[t + 1];
+        const uint32_t stop = x_lower(u_pos, lo, hi, regionEnd);                       // pos >= regionEnd ends the iteration
+        // left flank: pos < intron start and getEnd() >= leftAncStart; no read further left than the longest span can reach it
+        uint32_t a = x_lower(u_pos, lo, stop, (int64_t)left - (int64_t)maxspan[t]);
+        uint32_t z = x_lower(u_pos, a, stop, start);
+        for (uint32_t i = a + lane; i < z; i += 32) {
+            const int32_t pos = u_pos[i], al = u_alen[i];
+            const int64_t endpos = (int64_t)pos + al;                                  // bam_endpos: mapped, n_cigar > 0
+            const int32_t getEnd = pos + al - 1;                                       // bam_alignment.hpp:221-223
+            if (endpos > regionStart && start > pos && left <= getEnd) nl++;
+        }
+        // right flank: intron end < pos <= rightAncEnd
+        a = x_lower(u_pos, lo, stop, (int64_t)end + 1);
+        z = x_lower(u_pos, a, stop, (int64_t)right + 1);
+        for (uint32_t i = a + lane; i < z; i += 32) {
+            const int32_t pos = u_pos[i];
+            const int64_t endpos = (int64_t)pos + u_alen[i];
+            if (endpos > regionStart && right >= pos && end < pos) nr++;
+        }
+    }
+    nl = __reduce_add_sync(0xffffffffu, nl); nr = __reduce_add_sync(0xffffffffu, nr);
+    if (lane == 0) { out[j].up_aln = nl; out[j].down_aln = nr; }
+}
+
+// live-read vector: +1 at pos, -1 after the last base a node stays allocated for (bam_plp_next frees a node once the
+// iterator has passed its end, so a read is "live" on [pos, endpos] inclusive)
+__global__ void __launch_bounds__(256) k_x_live(uint32_t U, const int32_t* __restrict__ u_tid, const int32_t* __restrict__ u_pos, const int32_t* __restrict__ u_alen,
+                                                 const int32_t* __restrict__ tlen, const uint64_t* __restrict__ doff, uint32_t* __restrict__ diff) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U) return;
+    const int32_t t = u_tid[i]; const int64_t L = tlen[t]; const int64_t p = u_pos[i];
+    if (p < 0 || p >= L) return;
+    uint32_t* d = diff + doff[t];
+    atomicAdd(d + p, 1u);
+    int64_t e = p + (int64_t)u_alen[i] + 1; if (e > L) e = L;
+    atomicAdd(d + e, 0xffffffffu);
+}
+
+// depth vector of DepthParser (depth_parser.cc:121-156): reads count on M/=/X columns only (is_del / is_refskip are
+// subtracted), stored with the reference's `rpos = pos + 1` shift — the exclusive scan supplies the shift
+__global__ void __launch_bounds__(256) k_x_depth(uint32_t U, const int32_t* __restrict__ u_tid, const int32_t* __restrict__ u_pos, const uint32_t* __restrict__ u_rid,
+                                                  const uint32_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar,
+                                                  const int32_t* __restrict__ tlen, const uint64_t* __restrict__ doff, uint32_t* __restrict__ diff) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U) return;
+    const int32_t t = u_tid[i]; const int64_t L = tlen[t];
+    uint32_t* d = diff + doff[t];
+    const uint32_t r = u_rid[i];
+    int64_t x = u_pos[i];
+    for (uint32_t k = cigar_off[r]; k < cigar_off[r + 1]; k++) {
+        const uint32_t w = __ldg(cigar + k); const uint32_t op = w & 15u; const int64_t n = w >> 4;
+        if (op == 0u || op == 7u || op == 8u) {
+            int64_t a = x < 0 ? 0 : x, b = x + n; if (b > L) b = L;
+            if (a < b) { atomicAdd(d + a, 1u); atomicAdd(d + b, 0xffffffffu); }
+            x += n;
+        } else if (op == 2u || op == 3u) x += n;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_x_max(const uint32_t* __restrict__ v, uint64_t n, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, v[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// Junction::calcCoverage(a, b, levels) (junction.cc:923-933) for the four windows of :935-951
+__global__ void __launch_bounds__(256) k_x_coverage(int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ end, const uint32_t* __restrict__ depth,
+                                                     int64_t size, uint32_t* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * 4) return;
+    const int64_t j = g >> 2; const int w = (int)(g & 3);
+    const int32_t R = 10;
+    const int32_t s = start[j], e = end[j];
+    int32_t a, b;
+    if (w == 0) { a = s - 2 * R; b = s - R - 1; } else if (w == 1) { a = s - R; b = s; }
+    else if (w == 2) { a = e + R; b = e + 2 * R; } else { a = e; b = e + R - 1; }
+    uint32_t sum = 0;
+    for (int64_t i = a; i <= b; i++) if (i >= 0 && i < size) sum += depth[i];
+    out[g] = sum;
+}
+
+__global__ void __launch_bounds__(256) k_x_keep(uint32_t P, const uint32_t* __restrict__ vals, const PairA* __restrict__ pa, uint32_t* __restrict__ rid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) rid[i] = pa[vals[i]].rid;
+}
+
+inline uint32_t blocks_for(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
+
+} // namespace
+
+namespace pjapi {
+
+void extra_reset(pj_ctx* c) {
+    cudaFree(c->x_pair_rid); cudaFree(c->x_pair_jid); cudaFree(c->x_names); cudaFree(c->x_uflag); cudaFree(c->x_alen); cudaFree(c->x_depth);
+    c->x_pair_rid = c->x_pair_jid = nullptr; c->x_names = nullptr; c->x_uflag = nullptr; c->x_alen = nullptr; c->x_depth = nullptr;
+    c->x_n_spliced = -1; c->x_imported.clear(); c->x_doff.clear(); c->x_covered.clear(); c->x_maxlive.clear(); c->x_ready = false;
+}
+
+// end of pj_shard_run: remember, for every (read, junction) pair in sorted order, its record and its junction
+int extra_keep_pairs(pj_ctx* c, uint32_t P, const uint32_t* vals, const uint32_t* jid, const PairA* pa, cudaStream_t st) {
+    CU(c, cudaMalloc(&c->x_pair_rid, (size_t)std::max<uint32_t>(P, 1) * 4)); CU(c, cudaMalloc(&c->x_pair_jid, (size_t)std::max<uint32_t>(P, 1) * 4));
+    if (P) {
+        k_x_keep<<<blocks_for(P, 256), 256, 0, st>>>(P, vals, pa, c->x_pair_rid); c->n_launches++;
+        CU(c, cudaMemcpyAsync(c->x_pair_jid, jid, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return PJ_OK;
+}
+
+// end of pj_shard_run: classify the shard's records (spliced / unspliced + mapped / neither) and compact the name codes
+// of the spliced ones, so that pj_extra_export_names can hand them to the other contexts before pj_extra_run
+int extra_classify(pj_ctx* c, cudaStream_t st) {
+    const int64_t R = c->n_rec;
+    unsigned long long* d_n = nullptr;
+    CU(c, cudaMalloc(&c->x_names, (size_t)std::max<int64_t>(R, 1) * 8));
+    CU(c, cudaMalloc(&c->x_uflag, (size_t)std::max<int64_t>(R, 1) * 4)); CU(c, cudaMalloc(&c->x_alen, (size_t)std::max<int64_t>(R, 1) * 4));
+    uint32_t* uflag = c->x_uflag; int32_t* alen = c->x_alen;
+    CU(c, cudaMallocAsync(&d_n, 8, st)); CU(c, cudaMemsetAsync(d_n, 0, 8, st));
+    CU(c, cudaMemsetAsync(c->d_scalars + 8, 0, 4 * sizeof(uint32_t), st));
+    if (R) k_x_classify<<<blocks_for((uint64_t)R, 256), 256, 0, st>>>(R, c->cigar_off.p, c->cigar.p, c->flag.p, c->tid.p, c->name_code.p, c->n_targets,
+                                                                       uflag, alen, c->x_names, d_n, c->d_scalars + 8);
+    c->n_launches++;
+    unsigned long long n = 0;
+    CU(c, cudaMemcpyAsync(&n, d_n, 8, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
+    CU(c, cudaFreeAsync(d_n, st));
+    c->x_n_spliced = (int64_t)n;
+    return PJ_OK;
+}
+
+} // namespace pjapi
+
+extern "C" {
+
+static_assert(sizeof(pj_junction_extra) == 48, "pj_junction_extra layout changed: update the bindings");
+
+int64_t pj_extra_num_spliced_names(const pj_ctx* c) { return (c && c->extra && c->have_result) ? c->x_n_spliced : -1; }
+
+int pj_extra_export_names(pj_ctx* c, uint64_t* codes, int64_t cap) {
+    if (!c || !c->extra || !c->have_result || c->x_n_spliced < 0) return fail(c, PJ_ESTATE, "pj_extra_export_names: needs a context created with extra_metrics and a finished pj_shard_run");
+    if (cap < c->x_n_spliced || (c->x_n_spliced && !codes)) return fail(c, PJ_EINVAL, "pj_extra_export_names: capacity %lld < %lld", (long long)cap, (long long)c->x_n_spliced);
+    CU(c, cudaSetDevice(c->device));
+    if (c->x_n_spliced) CU(c, cudaMemcpy(codes, c->x_names, (size_t)c->x_n_spliced * 8, cudaMemcpyDeviceToHost));
+    return PJ_OK;
+}
+
+int pj_extra_import_names(pj_ctx* c, const uint64_t* codes, int64_t n) {
+    if (!c || !c->extra || !c->have_result) return fail(c, PJ_ESTATE, "pj_extra_import_names: needs a context created with extra_metrics and a finished pj_shard_run");
+    if (n < 0 || (n && !codes)) return fail(c, PJ_EINVAL, "pj_extra_import_names: bad arguments");
+    c->x_imported.insert(c->x_imported.end(), codes, codes + n);
+    return PJ_OK;
+}
+
+int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, int64_t cap_rows) {
+    if (!c || !c->extra || !c->have_result) return fail(c, PJ_ESTATE, "pj_extra_run: needs a context created with extra_metrics and a finished pj_shard_run");
+    if (cap_rows < c->n_junc || (c->n_junc && !out)) return fail(c, PJ_EINVAL, "pj_extra_run: rows capacity %lld < %lld", (long long)cap_rows, (long long)c->n_junc);
+    if (c->x_ready) return fail(c, PJ_ESTATE, "pj_extra_run: already run for this shard");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->compute_stream;
+    const int64_t R = c->n_rec; const int32_t T = c->n_targets; const uint32_t J = (uint32_t)c->n_junc; const uint32_t P = (uint32_t)c->n_pairs;
+    if (c->x_n_spliced < 0 || !c->x_uflag) return fail(c, PJ_ESTATE, "pj_extra_run: internal state");
+    uint32_t* uflag = c->x_uflag; int32_t* alen = c->x_alen;
+    uint32_t err = 0;
+    CU(c, cudaMemcpy(&err, c->d_scalars + 8, 4, cudaMemcpyDeviceToHost));
+    if (err & XERR_NOCIGAR) return fail(c, PJ_EDATA, "input rejected (the reference aborts on it): mapped unspliced record without CIGAR (htslib pileup, sam.c:1537)");
+
+    // ---- unspliced records, compacted in BAM order ----
+    uint32_t* uoff = nullptr; uint32_t* scan_tmp = nullptr;
+    CU(c, cudaMallocAsync(&uoff, (size_t)std::max<int64_t>(R, 1) * 4, st));
+    CU(c, cudaMallocAsync(&scan_tmp, scan_tmp_elems((uint64_t)std::max<int64_t>(R, 1)) * 4, st));
+    launch_exclusive_scan(uflag, uoff, (uint64_t)R, scan_tmp, c->d_scalars + 9, st);
+    uint32_t U = 0;
+    CU(c, cudaMemcpyAsync(&U, c->d_scalars + 9, 4, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+    int32_t *u_tid = nullptr, *u_pos = nullptr, *u_alen = nullptr, *maxspan = nullptr; uint32_t *u_rid = nullptr, *u_toff = nullptr; uint8_t* covered = nullptr;
+    const size_t Un = std::max<uint32_t>(U, 1);
+    CU(c, cudaMallocAsync(&u_tid, Un * 4, st)); CU(c, cudaMallocAsync(&u_pos, Un * 4, st)); CU(c, cudaMallocAsync(&u_alen, Un * 4, st)); CU(c, cudaMallocAsync(&u_rid, Un * 4, st));
+    CU(c, cudaMallocAsync(&maxspan, (size_t)T * 4, st)); CU(c, cudaMemsetAsync(maxspan, 0, (size_t)T * 4, st));
+    CU(c, cudaMallocAsync(&covered, (size_t)T, st)); CU(c, cudaMemsetAsync(covered, 0, (size_t)T, st));
+    CU(c, cudaMallocAsync(&u_toff, ((size_t)T + 1) * 4, st)); CU(c, cudaMemsetAsync(u_toff, 0, ((size_t)T + 1) * 4, st));
+    if (R) k_x_scatter<<<blocks_for((uint64_t)R, 256), 256, 0, st>>>(R, uflag, uoff, c->tid.p, c->pos.p, alen, u_tid, u_pos, u_alen, u_rid, maxspan, covered);
+    k_x_toff<<<blocks_for((uint64_t)U + 1, 256), 256, 0, st>>>(U, u_tid, u_pos, T, u_toff, c->d_scalars + 8);
+    CU(c, cudaFreeAsync(uoff, st));
+
+    // ---- multiple-mapping score: name table over the spliced records of the whole file ----
+    pj_junction_extra* d_out = nullptr;
+    CU(c, cudaMallocAsync(&d_out, (size_t)std::max<uint32_t>(J, 1) * sizeof(pj_junction_extra), st));
+    CU(c, cudaMemsetAsync(d_out, 0, (size_t)std::max<uint32_t>(J, 1) * sizeof(pj_junction_extra), st));
+    {
+        const uint64_t n_names = (uint64_t)c->x_n_spliced + c->x_imported.size();
+        uint64_t cap = 1024; while (cap < 2 * n_names + 2) cap <<= 1;
+        uint64_t* keys = nullptr; uint32_t* counts = nullptr; uint64_t* d_imp = nullptr;
+        CU(c, cudaMallocAsync(&keys, cap * 8, st)); CU(c, cudaMemsetAsync(keys, 0xff, cap * 8, st));
+        CU(c, cudaMallocAsync(&counts, cap * 4, st)); CU(c, cudaMemsetAsync(counts, 0, cap * 4, st));
+        if (c->x_n_spliced) k_x_names_add<<<blocks_for((uint64_t)c->x_n_spliced, 256), 256, 0, st>>>(c->x_n_spliced, c->x_names, keys, counts, cap - 1);
+        if (!c->x_imported.empty()) {
+            CU(c, cudaMallocAsync(&d_imp, c->x_imported.size() * 8, st));
+            CU(c, cudaMemcpyAsync(d_imp, c->x_imported.data(), c->x_imported.size() * 8, cudaMemcpyHostToDevice, st));
+            k_x_names_add<<<blocks_for(c->x_imported.size(), 256), 256, 0, st>>>((int64_t)c->x_imported.size(), d_imp, keys, counts, cap - 1);
+        }
+        if (P) k_x_mm<<<blocks_for(P, 256), 256, 0, st>>>(P, c->x_pair_rid, c->x_pair_jid, c->name_code.p, keys, counts, cap - 1, d_out);
+        CU(c, cudaFreeAsync(keys, st)); CU(c, cudaFreeAsync(counts, st)); if (d_imp) { CU(c, cudaStreamSynchronize(st)); CU(c, cudaFreeAsync(d_imp, st)); }
+    }
+
+    // ---- flanking alignments ----
+    if (J) k_x_flank<<<blocks_for((uint64_t)J * 32, 256), 256, 0, st>>>(J, c->d_rows, c->d_tlen, u_toff, u_pos, u_alen, maxspan, max_query_length, d_out);
+    if (J) CU(c, cudaMemcpyAsync(out, d_out, (size_t)J * sizeof(pj_junction_extra), cudaMemcpyDeviceToHost, st));
+
+    // ---- unspliced pileup: live-read maximum (htslib cap check), then the depth vectors kept for pj_extra_coverage ----
+    c->x_doff.assign((size_t)T + 1, 0);
+    for (int32_t t = 0; t < T; t++) c->x_doff[t + 1] = c->x_doff[t] + (uint64_t)c->h_tlen[t] + 1;
+    const uint64_t D = c->x_doff[T];
+    uint64_t* d_doff = nullptr; uint32_t* d_max = nullptr; uint32_t* dscan_tmp = nullptr;
+    CU(c, cudaMalloc(&c->x_depth, D * 4));
+    CU(c, cudaMallocAsync(&d_doff, ((size_t)T + 1) * 8, st)); CU(c, cudaMemcpyAsync(d_doff, c->x_doff.data(), ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMallocAsync(&d_max, (size_t)T * 4, st)); CU(c, cudaMemsetAsync(d_max, 0, (size_t)T * 4, st));
+    CU(c, cudaMallocAsync(&dscan_tmp, scan_tmp_elems(D) * 4, st));
+    CU(c, cudaMemsetAsync(c->x_depth, 0, D * 4, st));
+    if (U) k_x_live<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_alen, c->d_tlen, d_doff, c->x_depth);
+    launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
+    for (int32_t t = 0; t < T; t++) {
+        const uint64_t n = (uint64_t)c->h_tlen[t] + 1;
+        if (U && n > 1) k_x_max<<<std::min<uint32_t>(blocks_for(n, 256 * 8), 148 * 8), 256, 0, st>>>(c->x_depth + c->x_doff[t], n, d_max + t);
+    }
+    CU(c, cudaMemsetAsync(c->x_depth, 0, D * 4, st));
+    if (U) k_x_depth<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_rid, c->cigar_off.p, c->cigar.p, c->d_tlen, d_doff, c->x_depth);
+    launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
+    c->x_covered.assign((size_t)T, 0); c->x_maxlive.assign((size_t)T, 0);
+    CU(c, cudaMemcpyAsync(c->x_covered.data(), covered, (size_t)T, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(c->x_maxlive.data(), d_max, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(&err, c->d_scalars + 8, 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
+    for (void* p : {(void*)u_tid, (void*)u_pos, (void*)u_alen, (void*)u_rid, (void*)maxspan, (void*)covered, (void*)u_toff, (void*)scan_tmp, (void*)d_out,
+                    (void*)d_doff, (void*)d_max, (void*)dscan_tmp}) CU(c, cudaFreeAsync(p, st));
+    if (err & XERR_UNSORTED) return fail(c, PJ_EINVAL, "pj_extra_run: records are not in (tid, pos) order");
+    cudaFree(c->x_uflag); cudaFree(c->x_alen); c->x_uflag = nullptr; c->x_alen = nullptr;
+    c->x_ready = true;
+    return PJ_OK;
+}
+
+int pj_extra_target_pileup(pj_ctx* c, int32_t tid, int32_t* covered, uint32_t* max_depth) {
+    if (!c || !c->x_ready) return fail(c, PJ_ESTATE, "pj_extra_target_pileup: call pj_extra_run first");
+    if (tid < 0 || tid >= c->n_targets) return fail(c, PJ_EINVAL, "pj_extra_target_pileup: bad target");
+    if (covered) *covered = c->x_covered[tid];
+    if (max_depth) *max_depth = c->x_maxlive[tid];
+    return PJ_OK;
+}
+
+int pj_extra_coverage(pj_ctx* c, int32_t depth_tid, int64_t n, const int32_t* intron_start, const int32_t* intron_end, uint32_t* cov_sum4) {
+    if (!c || !c->x_ready) return fail(c, PJ_ESTATE, "pj_extra_coverage: call pj_extra_run first");
+    if (depth_tid < 0 || depth_tid >= c->n_targets || n < 0 || (n && (!intron_start || !intron_end || !cov_sum4))) return fail(c, PJ_EINVAL, "pj_extra_coverage: bad arguments");
+    if (n == 0) return PJ_OK;
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->compute_stream;
+    int32_t *ds = nullptr, *de = nullptr; uint32_t* dout = nullptr;
+    CU(c, cudaMallocAsync(&ds, (size_t)n * 4, st)); CU(c, cudaMallocAsync(&de, (size_t)n * 4, st)); CU(c, cudaMallocAsync(&dout, (size_t)n * 16, st));
+    CU(c, cudaMemcpyAsync(ds, intron_start, (size_t)n * 4, cudaMemcpyHostToDevice, st)); CU(c, cudaMemcpyAsync(de, intron_end, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_x_coverage<<<blocks_for((uint64_t)n * 4, 256), 256, 0, st>>>(n, ds, de, c->x_depth + c->x_doff[depth_tid], (int64_t)c->h_tlen[depth_tid], dout);
+    CU(c, cudaMemcpyAsync(cov_sum4, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
+    CU(c, cudaFreeAsync(ds, st)); CU(c, cudaFreeAsync(de, st)); CU(c, cudaFreeAsync(dout, st));
+    return PJ_OK;
+}
+
+} // extern "C"

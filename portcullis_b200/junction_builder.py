@@ -40,9 +40,10 @@ class PrepDir:
         _check(self._lib.pjh_plan_shards(self._p, n_gpus, owner.ctypes.data), self._lib.pjh_last_error)
         return owner
 
-    def decode(self, tid=-1, threads=1):
-        """Decode one target (or all with tid=-1) into owned numpy columns."""
+    def decode(self, tid=-1, threads=1, names=False):
+        """Decode one target (or all with tid=-1) into owned numpy columns; names=True adds the name_code column."""
         b = L.PjBatch()
+        self._lib.pjh_prep_want_names(self._p, 1 if names else 0)
         _check(self._lib.pjh_prep_decode(self._p, tid, threads, C.byref(b)), self._lib.pjh_last_error)
         return from_batch(b)
 
@@ -67,10 +68,11 @@ class PrepDir:
 class JuncGpu:
     """One GPU context of the C ABI (pj_ctx)."""
 
-    def __init__(self, device=0, orientation="UNKNOWN", match_group=0, legacy_sort=0):
+    def __init__(self, device=0, orientation="UNKNOWN", match_group=0, legacy_sort=0, extra=False):
         self._lib = L.load()
         cfg = L.PjConfig()
         cfg.device = device
+        cfg.extra_metrics = 1 if extra else 0    # keep what the `--extra` metrics need; batches must carry name_code
         cfg.reserved[0] = match_group        # lanes per (read, junction) pair in k_match; 0 = chosen from the data
         cfg.reserved[1] = legacy_sort        # 1 = multi-kernel radix sort instead of the one-sweep sort
         cfg.orientation = L.ORIENT[orientation] if isinstance(orientation, str) else int(orientation)
@@ -107,6 +109,9 @@ class JuncGpu:
             a = np.ascontiguousarray(cols[name], dtype=dt)
             if a.size:
                 C.memmove(getattr(st, name), a.ctypes.data, a.nbytes)
+        if st.name_code and cols.get("name_code") is not None and n:
+            a = np.ascontiguousarray(cols["name_code"], dtype=np.uint64)
+            C.memmove(st.name_code, a.ctypes.data, a.nbytes)
         st.n_records = n
         _check(self._lib.pj_batch_submit(self._ctx, C.byref(st)), self._err)
 
@@ -122,6 +127,56 @@ class JuncGpu:
         st = np.array([(s.spliced_count, s.unspliced_count, s.sum_query_lengths, s.min_query_length, s.max_query_length)
                        for s in stats], dtype=[("spliced", "u8"), ("unspliced", "u8"), ("sumq", "u8"), ("minq", "i4"), ("maxq", "i4")])
         return rows, st
+
+    # ---- `--extra` metrics (contexts created with extra=True, after run()) ----
+    def export_names(self):
+        n = self._lib.pj_extra_num_spliced_names(self._ctx)
+        codes = np.zeros(max(n, 0), dtype=np.uint64)
+        _check(self._lib.pj_extra_export_names(self._ctx, codes.ctypes.data, len(codes)), self._err)
+        return codes
+
+    def import_names(self, codes):
+        codes = np.ascontiguousarray(codes, dtype=np.uint64)
+        _check(self._lib.pj_extra_import_names(self._ctx, codes.ctypes.data, len(codes)), self._err)
+
+    def extra_run(self, max_query_length):
+        """up_aln / down_aln / mm_n / mm_m of the shard's junctions (pj_shard_fetch order)."""
+        n = self._lib.pj_shard_num_junctions(self._ctx)
+        out = np.zeros(max(n, 0), dtype=L.EXTRA_DTYPE)
+        _check(self._lib.pj_extra_run(self._ctx, int(max_query_length), out.ctypes.data, len(out)), self._err)
+        return out
+
+    def target_pileup(self, tid):
+        cov = C.c_int32()
+        mx = C.c_uint32()
+        _check(self._lib.pj_extra_target_pileup(self._ctx, tid, C.byref(cov), C.byref(mx)), self._err)
+        return bool(cov.value), mx.value
+
+    def coverage(self, depth_tid, starts, ends):
+        s = np.ascontiguousarray(starts, dtype=np.int32)
+        e = np.ascontiguousarray(ends, dtype=np.int32)
+        out = np.zeros((len(s), 4), dtype=np.uint32)
+        _check(self._lib.pj_extra_coverage(self._ctx, int(depth_tid), len(s), s.ctypes.data, e.ctypes.data, out.ctypes.data), self._err)
+        return out
+
+    def extra(self, rows, max_query_length):
+        """All four `--extra` columns for a single-context run: rows as returned by fetch().  Returns
+        (EXTRA_DTYPE array in the order of rows, {tid: live-read maximum} of targets where htslib's pileup cap binds)."""
+        x = self.extra_run(max_query_length)
+        covered = np.zeros(self.n_targets, dtype=np.uint8)
+        over = {}
+        for t in range(self.n_targets):
+            c, mx = self.target_pileup(t)
+            covered[t] = c
+            if mx >= 8000:
+                over[t] = mx
+        src = coverage_source(covered)
+        for t in np.unique(rows["tid"]):
+            if src[t] < 0:
+                continue
+            sel = np.nonzero(rows["tid"] == t)[0]
+            x["cov_sum"][sel] = self.coverage(src[t], rows["start"][sel], rows["end"][sel])
+        return extra_finalize(x), over
 
     def timing(self):
         ms = C.c_float()
@@ -154,9 +209,37 @@ def finalize(rows, mean_query_length):
     return rows
 
 
-def write_outputs(prefix, rows, names, lengths, source="portcullis", version="1.2.4", exon_gff=False, intron_gff=False):
+def coverage_source(covered):
+    """Q14: which target's depth vector the reference applies to the junctions of each target (-1: none)."""
+    lib = L.load()
+    cov = np.ascontiguousarray(covered, dtype=np.uint8)
+    src = np.zeros(len(cov), dtype=np.int32)
+    lib.pj_extra_coverage_source(len(cov), cov.ctypes.data, src.ctypes.data)
+    return src
+
+
+def extra_finalize(x):
+    lib = L.load()
+    x = np.ascontiguousarray(x)
+    lib.pj_extra_finalize(x.ctypes.data, len(x))
+    return x
+
+
+def write_outputs(prefix, rows, names, lengths, source="portcullis", version="1.2.4", exon_gff=False, intron_gff=False,
+                  extra=None):
+    """tab / bed / gff writers; extra: EXTRA_DTYPE array aligned with rows (the `--extra` columns) or None."""
     lib = L.load()
     rows = np.ascontiguousarray(rows)
+    if extra is not None:
+        extra = np.ascontiguousarray(extra, dtype=L.EXTRA_DTYPE)
+        if len(extra) != len(rows):
+            raise ValueError("extra must have one entry per row")
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        tl = np.ascontiguousarray(lengths, dtype=np.int32)
+        _check(lib.pjh_write_outputs_extra(os.fsencode(prefix), rows.ctypes.data, extra.ctypes.data, len(rows), len(names), arr,
+                                           tl.ctypes.data, source.encode(), version.encode(), int(exon_gff), int(intron_gff)),
+               lib.pjh_last_error)
+        return
     arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
     tl = np.ascontiguousarray(lengths, dtype=np.int32)
     _check(lib.pjh_write_outputs(os.fsencode(prefix), rows.ctypes.data, len(rows), len(names), arr, tl.ctypes.data,
@@ -171,6 +254,7 @@ class JunctionBuilder:
         self.output = output
         self.threads = 1
         self.gpus = 1
+        self.gpu_ids = None          # optional explicit device ordinals (len == gpus); default 0..gpus-1
         self.extra = False
         self.separate = False
         self.use_csi = False
@@ -203,6 +287,12 @@ class JunctionBuilder:
         keep = [os.fsencode(self.prep_dir), os.fsencode(self.output), self.source.encode()]
         o.prep_dir, o.output_prefix, o.source = keep
         o.threads, o.n_gpus = self.threads, self.gpus
+        if self.gpu_ids is not None:
+            if len(self.gpu_ids) != self.gpus:
+                raise ValueError("gpu_ids must name one device per GPU")
+            ids = (C.c_int32 * self.gpus)(*self.gpu_ids)
+            keep.append(ids)
+            o.gpu_ids = ids
         o.orientation = L.ORIENT[self.orientation]
         o.strandedness = L.STRANDEDNESS[self.strand_specific]
         o.use_csi, o.exon_gff, o.intron_gff = int(self.use_csi), int(self.output_exon_gff), int(self.output_intron_gff)

@@ -26,7 +26,7 @@ def assert_rows_equal(got, exp, what="rows", finalize_fields=False):
         raise AssertionError("%s: entropy differs at junction %d: got %r expected %r" % (what, i, got["entropy"][i], exp["entropy"][i]))
 
 
-FP_COLS = {27, 32, 33}            # 0-based: rel2raw, entropy, mean_mismatches
+FP_COLS = {27, 32, 33, 50, 51}    # 0-based: rel2raw, entropy, mean_mismatches; mm_score and coverage (`--extra`)
 
 
 def assert_tab_equal(path_got, path_exp):
@@ -63,3 +63,26 @@ def assert_exon_gff_equal(path_got, path_exp):
         assert pat.sub(r"\1#", a) == pat.sub(r"\1#", b), "line %d differs outside entropy fields" % ln
         for (_, x), (_, y) in zip(va, vb):
             assert abs(float(x) - float(y)) <= FP_TOL * max(abs(float(y)), 1e-300), "line %d: %s vs %s" % (ln, x, y)
+
+
+EXTRA_INT_FIELDS = ["up_aln", "down_aln", "mm_n", "mm_m", "cov_sum"]
+
+
+def assert_extra_equal(got, exp, rows, what="extra"):
+    """pj_junction_extra arrays: integer fields bit-exact, the two doubles bit-equal too (same operands, same order)."""
+    assert len(got) == len(exp)
+    for f in EXTRA_INT_FIELDS + ["mm_score", "coverage"]:
+        a, b = got[f], exp[f]
+        ok = (a == b) | ((a != a) & (b != b)) if a.dtype.kind == "f" else a == b
+        if ok.ndim > 1:
+            ok = ok.all(axis=1)
+        if not ok.all():
+            i = int(np.flatnonzero(~ok)[0])
+            raise AssertionError("%s: field %s differs at junction %d (tid %d, %d-%d): got %r expected %r; %d of %d rows differ"
+                                 % (what, f, i, rows["tid"][i], rows["start"][i], rows["end"][i], a[i], b[i], int((~ok).sum()), len(ok)))
+
+
+def extra_tab_columns(x):
+    """The four junctions.tab columns (mm_score, coverage, up_aln, down_aln) as the writer prints them (ostream << double
+    = %.6g, junction.cc:105-108)."""
+    return [["%.6g" % r["mm_score"], "%.6g" % r["coverage"], str(int(r["up_aln"])), str(int(r["down_aln"]))] for r in x]

@@ -38,4 +38,5 @@ def make_prep(tmpdir, fixture):
 
 
 FIXTURES = ["kat", "short_pe", "long_se", "indel_rich"]
+EXTRA_FIXTURES = FIXTURES + ["extra_mm"]      # every fixture also holds ref_extra.junctions.tab (`junc --extra`)
 ORIENTED = {"kat": "FR", "short_pe": "FR", "indel_rich": "RF"}

@@ -5,7 +5,8 @@
     python tests/golden/make_golden.py
 
 Each fixture directory holds the inputs (genome.fa[.fai], reads.bam[.bai]) and the reference's outputs
-(ref.junctions.tab/.bed/.exon.gff3/.intron.gff3, plus ref_FR.* for --orientation FR where listed).
+(ref.junctions.tab/.bed/.exon.gff3/.intron.gff3, plus ref_FR.* for --orientation FR where listed, and
+ref_extra.junctions.tab from `junc --extra`).
 """
 import os
 import shutil
@@ -35,6 +36,9 @@ def finish(work, out, orientations):
         refrun.run_reference(prep, os.path.join(work, tag), orientation=o)
         for e in ("tab", "bed", "exon.gff3", "intron.gff3"):
             shutil.copy(os.path.join(work, "%s.junctions.%s" % (tag, e)), os.path.join(out, "%s.junctions.%s" % (tag, e)))
+    # the hidden --extra metrics (mm_score, coverage, up_aln, down_aln): only the tab differs
+    refrun.run_reference(prep, os.path.join(work, "ref_extra"), extra=True, exon_gff=False, intron_gff=False)
+    shutil.copy(os.path.join(work, "ref_extra.junctions.tab"), os.path.join(out, "ref_extra.junctions.tab"))
 
 
 def main():

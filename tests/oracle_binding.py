@@ -37,6 +37,8 @@ def load():
         o.oj_last_error.restype = C.c_char_p
         o.oj_finalize.restype = C.c_int
         o.oj_finalize.argtypes = [P, C.c_int64, C.c_double]
+        o.oj_extra.restype = C.c_int
+        o.oj_extra.argtypes = [C.POINTER(L.PjBatch), C.c_int32, P, P, C.c_int64, C.c_int32, P, C.POINTER(C.c_int64)]
         o.oj_padded_query.restype = C.c_int
         o.oj_padded_query.argtypes = [C.c_int32, P, C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p,
                                       C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -97,3 +99,20 @@ def finalize(rows, mean_query_length):
     if rc:
         raise OracleError(rc, o.oj_last_error().decode())
     return rows
+
+
+def extra(cols, target_len, rows, max_query_length):
+    """`--extra` metrics of the finalized oracle rows; returns (EXTRA_DTYPE array, reads dropped by htslib's pileup cap)."""
+    from portcullis_b200.columnar import batch_struct
+    o = load()
+    b, keep = batch_struct(cols)
+    tl = np.ascontiguousarray(target_len, dtype=np.int32)
+    rows = np.ascontiguousarray(rows)
+    out = np.zeros(len(rows), dtype=L.EXTRA_DTYPE)
+    capped = C.c_int64()
+    rc = o.oj_extra(C.byref(b), len(tl), tl.ctypes.data, rows.ctypes.data, len(rows), int(max_query_length),
+                    out.ctypes.data, C.byref(capped))
+    if rc:
+        raise OracleError(rc, o.oj_last_error().decode())
+    del keep
+    return out, capped.value

@@ -61,8 +61,15 @@ def link_prep_dir(workdir, fa, bam):
     return prep
 
 
-def run_reference(prep, out_prefix, threads=1, orientation=None, exon_gff=True, intron_gff=True):
+SAMTOOLS_SHIM = os.path.join(ob.ORACLE_DIR, "samtools_shim")
+
+
+def run_reference(prep, out_prefix, threads=1, orientation=None, exon_gff=True, intron_gff=True, extra=False, separate=False):
     cmd = [ob.REF_BIN, "junc", "-t", str(threads), "-o", out_prefix]
+    if extra:
+        cmd.append("--extra")
+    if separate:
+        cmd.append("--separate")
     if exon_gff:
         cmd.append("--exon_gff")
     if intron_gff:
@@ -70,7 +77,8 @@ def run_reference(prep, out_prefix, threads=1, orientation=None, exon_gff=True, 
     if orientation:
         cmd += ["--orientation", orientation]
     cmd.append(prep)
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    env = dict(os.environ, PATH=SAMTOOLS_SHIM + os.pathsep + os.environ.get("PATH", ""))   # `samtools index` for --separate/--extra
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
     if p.returncode != 0:
         raise RuntimeError("reference junc failed (%d): %s\n%s" % (p.returncode, p.stderr[-2000:], p.stdout[-500:]))
     return p.stdout

@@ -144,8 +144,15 @@ def _read_from_gene(rng, gseq_upper, gene, read_len, sub_rate, indel_rate, clip_
 
 def make_dataset(seed, n_targets=2, target_len=20000, genes_per_target=12, reads_per_gene=(5, 120), read_len=(60, 150),
                  long_reads=False, sub_rate=0.01, indel_rate=0.15, clip_rate=0.1, retain_rate=0.15, unspliced_frac=0.2,
-                 paired=True, secondary_frac=0.05, lowq_frac=0.15, xs_frac=0.8, hot=None):
-    """Returns dict(names, lengths, genomes (list[bytes], original case), records (sorted list of dicts))."""
+                 paired=True, secondary_frac=0.05, lowq_frac=0.15, xs_frac=0.8, hot=None,
+                 multimap_frac=0.0, unspliced_indel=0.0, deep=(), no_background=()):
+    """Returns dict(names, lengths, genomes (list[bytes], original case), records (sorted list of dicts)).
+
+    Options for the `--extra` metrics (all off by default, so the seeds of older data sets keep their records):
+    multimap_frac: fraction of alignments that get a second alignment with the SAME read name (a multi-mapping read);
+    unspliced_indel: fraction of background reads with a deletion / insertion / soft clips; deep: (tid, pos, count, len)
+    piles of identical unspliced reads (htslib's 8000-read pileup cap); no_background: targets without any unspliced
+    read."""
     rng = np.random.default_rng(seed)
     genomes = make_genome(rng, n_targets, target_len)
     names = ["chr%s" % (t + 1) for t in range(n_targets)]
@@ -167,6 +174,8 @@ def make_dataset(seed, n_targets=2, target_len=20000, genes_per_target=12, reads
                     continue
                 pos, cigar, seq = r
                 spliced = "N" in cigar
+                if not spliced and t in no_background:
+                    continue
                 rev = rng.random() < 0.5
                 flag = 0
                 mtid, mpos = -1, -1
@@ -187,15 +196,37 @@ def make_dataset(seed, n_targets=2, target_len=20000, genes_per_target=12, reads
                 xs = 0
                 if spliced and rng.random() < xs_frac:
                     xs = gene[0] if rng.random() < 0.93 else ("+" if gene[0] == "-" else "-")
-                records.append(dict(name="r%06d" % rid, tid=t, pos=pos, flag=flag, mapq=mapq, cigar=cigar, seq=seq, xs=xs,
+                name = "r%06d" % rid
+                if multimap_frac and records and rng.random() < multimap_frac:
+                    other = records[int(rng.integers(0, len(records)))]
+                    if (other["flag"] & 0xC1) == (flag & 0xC1):      # same deriveName() suffix
+                        name = other["name"]; flag |= 0x100
+                records.append(dict(name=name, tid=t, pos=pos, flag=flag, mapq=mapq, cigar=cigar, seq=seq, xs=xs,
                                     mtid=mtid, mpos=mpos))
                 rid += 1
         # unspliced background + a placed unmapped read
-        nb = int(unspliced_frac * sum(1 for r in records if r["tid"] == t))
+        nb = 0 if t in no_background else int(unspliced_frac * sum(1 for r in records if r["tid"] == t))
         for _ in range(nb):
             rl = int(rng.integers(30, 120)); pos = int(rng.integers(0, target_len - rl))
-            records.append(dict(name="u%06d" % rid, tid=t, pos=pos, flag=0, mapq=60, cigar="%dM" % rl, seq=gu[pos:pos + rl].replace("X", "N"), xs=0, mtid=-1, mpos=-1))
+            cigar, seq, fl = "%dM" % rl, gu[pos:pos + rl].replace("X", "N"), 0
+            if unspliced_indel and rl >= 40 and rng.random() < unspliced_indel:
+                a = int(rng.integers(5, rl - 20)); d = int(rng.integers(1, 12)); kind = int(rng.integers(0, 3))
+                if kind == 0 and pos + rl + d < target_len:      # deletion: the read spans rl + d reference bases
+                    cigar = "%dM%dD%dM" % (a, d, rl - a); seq = (gu[pos:pos + a] + gu[pos + a + d:pos + rl + d]).replace("X", "N")
+                elif kind == 1:                                   # insertion
+                    cigar = "%dM%dI%dM" % (a, d, rl - a); seq = (gu[pos:pos + a] + "A" * d + gu[pos + a:pos + rl]).replace("X", "N")
+                else:                                             # soft clips on both sides
+                    cigar = "%dS%dM%dS" % (d, rl, d); seq = "C" * d + seq + "G" * d
+                fl = int(rng.choice([0, 0x10, 0x100, 0x400, 0x200]))
+            records.append(dict(name="u%06d" % rid, tid=t, pos=pos, flag=fl, mapq=60, cigar=cigar, seq=seq, xs=0, mtid=-1, mpos=-1))
             rid += 1
+        for (dt, dpos, dcount, dlen) in deep:
+            if dt != t:
+                continue
+            for _ in range(dcount):
+                records.append(dict(name="d%06d" % rid, tid=t, pos=dpos, flag=0, mapq=60, cigar="%dM" % dlen,
+                                    seq=gu[dpos:dpos + dlen].replace("X", "N"), xs=0, mtid=-1, mpos=-1))
+                rid += 1
         records.append(dict(name="x%06d" % rid, tid=t, pos=int(rng.integers(0, target_len - 50)), flag=4, mapq=0, cigar="", seq="ACGTACGTAC", xs=0, mtid=-1, mpos=-1))
         rid += 1
     records.sort(key=lambda r: (r["tid"], r["pos"]))
@@ -235,6 +266,10 @@ GOLDEN_SPECS = {
     "short_pe": (11, dict(n_targets=2, target_len=12000, genes_per_target=8, reads_per_gene=(5, 60)), [None, "FR"]),
     "long_se": (12, dict(n_targets=2, target_len=40000, genes_per_target=5, reads_per_gene=(5, 40), long_reads=True,
                          read_len=(400, 2500), paired=False), [None]),
+    # `--extra` metrics: multi-mapping read names, background reads with indels / clips / secondary / duplicate flags,
+    # and a target (the second of four) without unspliced reads so that DepthParser's batch pairing (Q14) skips it
+    "extra_mm": (14, dict(n_targets=4, target_len=9000, genes_per_target=6, reads_per_gene=(5, 60), multimap_frac=0.2,
+                          unspliced_indel=0.5, unspliced_frac=1.5, no_background=(1,)), [None]),
     "indel_rich": (13, dict(n_targets=3, target_len=10000, genes_per_target=6, reads_per_gene=(5, 50), indel_rate=0.5,
                             clip_rate=0.5, retain_rate=0.4, sub_rate=0.03), [None, "RF"]),
 }

@@ -44,6 +44,8 @@ def slice_cols(cols, a, b):
     out["seq_off"] = (so[a:b + 1] - so[a]).astype(np.uint64)
     out["cigar"] = cols["cigar"][int(co[a]):int(co[b])]
     out["seq4"] = cols["seq4"][int(so[a]):int(so[b])]
+    if cols.get("name_code") is not None:
+        out["name_code"] = cols["name_code"][a:b]
     return out
 
 

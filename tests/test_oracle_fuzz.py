@@ -23,15 +23,16 @@ def test_oracle_equals_reference_on_fuzzed_cigars(tmp_path, seed):
     ds = make_case(1000 + seed, want_records=True)
     wd = str(tmp_path)
     prep = refrun.make_prep_dir(ds, wd)
-    refrun.run_reference(prep, os.path.join(wd, "ref", "k"), orientation=None if orient == "UNKNOWN" else orient)
+    refrun.run_reference(prep, os.path.join(wd, "ref", "k"), orientation=None if orient == "UNKNOWN" else orient, extra=True)
     p = jb.PrepDir(prep)
-    cols = p.decode(-1, 2)
+    cols = p.decode(-1, 2, names=True)
     direct = synth.to_columns(ds)
     for k in direct:
         assert np.array_equal(direct[k], cols[k]), k
     rows, st = ob.run(cols, p.lengths, [p.genome(t) for t in range(len(p.names))], L.ORIENT[orient])
     total = float(st["spliced"].sum() + st["unspliced"].sum())
     fin = jb.finalize(rows.copy(), float(st["sumq"].sum()) / total)
-    jb.write_outputs(os.path.join(wd, "mine", "k"), fin, p.names, p.lengths, exon_gff=True, intron_gff=True)
+    x, _ = ob.extra(cols, p.lengths, fin, int(st["maxq"].max()))     # the reference ran with --extra: all 75 columns are compared
+    jb.write_outputs(os.path.join(wd, "mine", "k"), fin, p.names, p.lengths, exon_gff=True, intron_gff=True, extra=x)
     for ext in ("tab", "bed", "exon.gff3", "intron.gff3"):
         assert filecmp.cmp(os.path.join(wd, "mine", "k.junctions." + ext), os.path.join(wd, "ref", "k.junctions." + ext), shallow=False), ext
