@@ -272,9 +272,10 @@ int pj_extra_run(pj_ctx* ctx, int32_t max_query_length, pj_junction_extra* out, 
 
 /*
  * Unspliced pileup of one target held by this context (DepthParser, depth_parser.cc:112-167): *covered = 1 when the
- * pileup reports at least one position, *max_depth = the deepest column (reads, D included).  htslib stops accepting
- * reads that start at a position already holding 8000 of them (sam.c:1906); this library does not model that, so a
- * caller should warn when max_depth >= 8000.
+ * pileup reports at least one position, *max_depth = the largest number of reads alive on one position (reads with
+ * pos <= p <= endpos, before any are dropped).  htslib stops accepting reads that start on a position whose node pool
+ * already holds 8000 (sam.c:1622, 1906); where max_depth reaches 8000 pj_extra_run replays that rule on the device, so the
+ * depth vectors equal the reference's there too.  Informational.
  */
 int pj_extra_target_pileup(pj_ctx* ctx, int32_t tid, int32_t* covered, uint32_t* max_depth);
 

@@ -440,9 +440,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             int32_t cv = 0; uint32_t live = 0;
             if ((rc = pj_extra_target_pileup(outs[owner[t]].ctx, t, &cv, &live))) return fail(rc, pj_last_error(outs[owner[t]].ctx));
             covered[t] = (uint8_t)cv;
-            if (live >= 8000)
-                std::cerr << "Warning: " << live << " unspliced alignments pile up on " << H.names[t] << "; htslib's pileup (used by the reference) stops accepting reads at 8000 per "
-                             "position, this implementation does not: the coverage column can differ from the reference around that locus\n";
+            if (live >= 8000 && o->verbose) std::cerr << " - " << H.names[t] << ": up to " << live << " unspliced alignments on one position; htslib's 8000-read pileup cap is replayed there\n";
         }
         pj_extra_coverage_source(T, covered.data(), src.data());
         for (int g = 0; g < n_gpus; g++) {

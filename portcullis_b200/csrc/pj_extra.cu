@@ -175,10 +175,11 @@ __global__ void __launch_bounds__(256) k_x_live(uint32_t U, const int32_t* __res
 // depth vector of DepthParser (depth_parser.cc:121-156): reads count on M/=/X columns only (is_del / is_refskip are
 // subtracted), stored with the reference's `rpos = pos + 1` shift — the exclusive scan supplies the shift
 __global__ void __launch_bounds__(256) k_x_depth(uint32_t U, const int32_t* __restrict__ u_tid, const int32_t* __restrict__ u_pos, const uint32_t* __restrict__ u_rid,
-                                                  const uint32_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar,
+                                                  const uint32_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar, const uint8_t* __restrict__ accepted,
                                                   const int32_t* __restrict__ tlen, const uint64_t* __restrict__ doff, uint32_t* __restrict__ diff) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= U) return;
+    if (accepted && !accepted[i]) return;               // dropped by the pileup's read cap (k_x_cap)
     const int32_t t = u_tid[i]; const int64_t L = tlen[t];
     uint32_t* d = diff + doff[t];
     const uint32_t r = u_rid[i];
@@ -190,6 +191,113 @@ __global__ void __launch_bounds__(256) k_x_depth(uint32_t U, const int32_t* __re
             if (a < b) { atomicAdd(d + a, 1u); atomicAdd(d + b, 0xffffffffu); }
             x += n;
         } else if (op == 2u || op == 3u) x += n;
+    }
+}
+
+constexpr int32_t PLP_MAXCNT = 8000;       // bam_plp_init (htslib-1.3 sam.c:1622)
+
+// hot[i] = 1 when read i starts on a column whose live-read count (reads with pos <= p <= endpos, cap ignored) reaches the
+// cap: only there can bam_plp_push drop reads (sam.c:1906).  `live` is the exclusive scan of k_x_live: L(p) = live[p + 1].
+__global__ void __launch_bounds__(256) k_x_hot(uint32_t U, const int32_t* __restrict__ u_tid, const int32_t* __restrict__ u_pos, const int32_t* __restrict__ tlen,
+                                                const uint64_t* __restrict__ doff, const uint32_t* __restrict__ live, uint32_t* __restrict__ hot) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U) return;
+    const int32_t t = u_tid[i]; const int64_t p = u_pos[i];
+    hot[i] = (p >= 0 && p < tlen[t] && live[doff[t] + p + 1] >= (uint32_t)PLP_MAXCNT) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_x_compact(uint32_t U, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ off, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < U && flag[i]) out[off[i]] = i;
+}
+
+// htslib's pileup buffer cap, replayed (bam_plp_push / bam_plp_next, sam.c:1838-1936).  A read that starts on the column
+// the iterator stands on is dropped when the node pool already holds more than 8000 nodes: pool = live reads + the spare
+// tail + the dummy node (sam.c:1619-1620).  With `live` = accepted reads whose end is >= P when the first read of column
+// P has just been pushed, the k-th read of the column (k >= 1) is kept iff 2 + live + k <= 8000, the first one always.
+// The process is sequential along a target, but it can only drop reads on "hot" columns (k_x_hot), and its state equals
+// the uncapped one again once every read that started on a hot column has ended.  One warp per target walks those
+// regions column by column: `endcnt` (the target's slice of the zeroed depth buffer, used as scratch and left zeroed)
+// counts accepted reads per end position, lanes share the per-column work.
+__global__ void __launch_bounds__(32) k_x_cap(int32_t T, const uint32_t* __restrict__ u_toff, const int32_t* __restrict__ u_pos, const int32_t* __restrict__ u_alen,
+                                               const int32_t* __restrict__ maxspan_t, const int32_t* __restrict__ tlen, const uint64_t* __restrict__ doff,
+                                               const uint32_t* __restrict__ H, uint32_t nH, uint32_t* __restrict__ scratch, uint8_t* __restrict__ accepted) {
+    const int32_t t = blockIdx.x; const int lane = threadIdx.x;
+    if (t >= T) return;
+    const uint32_t lo = u_toff[t], hi = u_toff[t + 1];
+    uint32_t hlo = 0, hhi = nH;
+    { uint32_t a = 0, z = nH; while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (H[m] < lo) a = m + 1; else z = m; } hlo = a; }
+    { uint32_t a = hlo, z = nH; while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (H[m] < hi) a = m + 1; else z = m; } hhi = a; }
+    if (hlo == hhi) return;
+    uint32_t* endcnt = scratch + doff[t];
+    const int64_t L = tlen[t]; const int64_t span = maxspan_t[t];
+    uint32_t h = hlo;
+    while (h < hhi) {
+        const uint32_t start = H[h];
+        const int64_t P0 = u_pos[start];
+        // state at the start of the region: every earlier read is accepted (no hot column within reach)
+        int64_t live = 0, maxE = P0;
+        {
+            const uint32_t a0 = x_lower(u_pos, lo, start, P0 - span);
+            uint32_t c = 0; int64_t me = P0;
+            for (uint32_t j = a0 + lane; j < start; j += 32) {
+                const int64_t E = (int64_t)u_pos[j] + u_alen[j];
+                if (E >= P0) { c++; atomicAdd(endcnt + (E < L ? E : L), 1u); if (E > me) me = E; }
+            }
+            live = __reduce_add_sync(0xffffffffu, c);
+            maxE = __reduce_max_sync(0xffffffffu, (unsigned)(me > 0x7fffffff ? 0x7fffffff : me));
+        }
+        __syncwarp();
+        uint32_t i = start; int64_t prevP = P0, lastHot = P0;
+        while (i < hi) {
+            const int64_t P = u_pos[i];
+            if (P > lastHot + span) break;
+            if (P > prevP) {                                   // nodes whose end has been passed are freed (end <= P - 1)
+                uint32_t s = 0;
+                for (int64_t e = prevP + lane; e < P; e += 32) if (e <= L) s += __ldcg(endcnt + e);       // L2 read: the counts are built with atomics
+                live -= __reduce_add_sync(0xffffffffu, s);
+            }
+            uint32_t n = 0;                                    // reads on this column
+            for (;;) {
+                const uint32_t j = i + n + lane;
+                const unsigned same = __ballot_sync(0xffffffffu, j < hi && u_pos[j] == P);
+                if (same == 0xffffffffu) { n += 32; continue; }
+                n += __ffs(~same) - 1; break;
+            }
+            const bool is_hot = h < hhi && H[h] == i;
+            uint32_t keep = n;
+            if (is_hot) { const int64_t room = (int64_t)(PLP_MAXCNT - 1) - live; keep = (uint32_t)(room < 1 ? 1 : room > (int64_t)n ? (int64_t)n : room); h += n; }
+            bool zero_len = false;
+            if (is_hot) { for (uint32_t k = lane; k < n; k += 32) zero_len |= u_alen[i + k] == 0; zero_len = __any_sync(0xffffffffu, zero_len); }
+            if (is_hot && zero_len) {                          // a read without reference span gets no node unless it opens the column: replay one by one
+                if (lane == 0) {
+                    int64_t lv = live;
+                    for (uint32_t k = 0; k < n; k++) {
+                        const int64_t E = P + u_alen[i + k];
+                        const bool ok = k == 0 || 2 + lv <= PLP_MAXCNT;
+                        accepted[i + k] = ok ? 1 : 0;
+                        if (ok && (k == 0 ? E >= P : E > P)) { atomicAdd(endcnt + (E < L ? E : L), 1u); lv++; if (E > maxE) maxE = E; }
+                    }
+                    live = lv;
+                }
+                live = __shfl_sync(0xffffffffu, live, 0); maxE = __shfl_sync(0xffffffffu, maxE, 0);
+            } else {
+                uint32_t c = 0; int64_t me = maxE;
+                for (uint32_t k = lane; k < n; k += 32) {
+                    if (k >= keep) { accepted[i + k] = 0; continue; }
+                    const int64_t E = P + u_alen[i + k];
+                    if (k == 0 ? E >= P : E > P) { c++; atomicAdd(endcnt + (E < L ? E : L), 1u); if (E > me) me = E; }
+                }
+                live += __reduce_add_sync(0xffffffffu, c);
+                maxE = __reduce_max_sync(0xffffffffu, (unsigned)(me > 0x7fffffff ? 0x7fffffff : me));
+            }
+            __syncwarp();
+            i += n; prevP = P; if (is_hot) lastHot = P;
+        }
+        // leave the scratch zeroed for the next region and for the depth pass
+        { const int64_t a = P0 < 0 ? 0 : P0, z = maxE < L ? maxE : L; for (int64_t e = a + lane; e <= z; e += 32) endcnt[e] = 0; }
+        __syncwarp();
+        while (h < hhi && H[h] < i) h++;
     }
 }
 
@@ -357,12 +465,28 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
         const uint64_t n = (uint64_t)c->h_tlen[t] + 1;
         if (U && n > 1) k_x_max<<<std::min<uint32_t>(blocks_for(n, 256 * 8), 148 * 8), 256, 0, st>>>(c->x_depth + c->x_doff[t], n, d_max + t);
     }
-    CU(c, cudaMemsetAsync(c->x_depth, 0, D * 4, st));
-    if (U) k_x_depth<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_rid, c->cigar_off.p, c->cigar.p, c->d_tlen, d_doff, c->x_depth);
-    launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
     c->x_covered.assign((size_t)T, 0); c->x_maxlive.assign((size_t)T, 0);
     CU(c, cudaMemcpyAsync(c->x_covered.data(), covered, (size_t)T, cudaMemcpyDeviceToHost, st));
     CU(c, cudaMemcpyAsync(c->x_maxlive.data(), d_max, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    bool capped = false; for (int32_t t = 0; t < T; t++) capped |= c->x_maxlive[t] >= (uint32_t)PLP_MAXCNT;
+    uint32_t *hot = nullptr, *hoff = nullptr, *H = nullptr; uint8_t* accepted = nullptr;
+    uint32_t nH = 0;
+    if (capped && U) {      // some column holds >= 8000 live reads: replay htslib's read cap there
+        CU(c, cudaMallocAsync(&hot, (size_t)U * 4, st)); CU(c, cudaMallocAsync(&hoff, (size_t)U * 4, st));
+        k_x_hot<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, c->d_tlen, d_doff, c->x_depth, hot);
+        launch_exclusive_scan(hot, hoff, U, dscan_tmp, c->d_scalars + 11, st);
+        CU(c, cudaMemcpyAsync(&nH, c->d_scalars + 11, 4, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+    }
+    CU(c, cudaMemsetAsync(c->x_depth, 0, D * 4, st));
+    if (nH) {
+        CU(c, cudaMallocAsync(&H, (size_t)nH * 4, st)); CU(c, cudaMallocAsync(&accepted, (size_t)U, st)); CU(c, cudaMemsetAsync(accepted, 1, (size_t)U, st));
+        k_x_compact<<<blocks_for(U, 256), 256, 0, st>>>(U, hot, hoff, H);
+        k_x_cap<<<(uint32_t)T, 32, 0, st>>>(T, u_toff, u_pos, u_alen, maxspan, c->d_tlen, d_doff, H, nH, c->x_depth, accepted);
+    }
+    if (U) k_x_depth<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_rid, c->cigar_off.p, c->cigar.p, accepted, c->d_tlen, d_doff, c->x_depth);
+    launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
+    for (void* p : {(void*)hot, (void*)hoff, (void*)H, (void*)accepted}) if (p) CU(c, cudaFreeAsync(p, st));
     CU(c, cudaMemcpyAsync(&err, c->d_scalars + 8, 4, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
     for (void* p : {(void*)u_tid, (void*)u_pos, (void*)u_alen, (void*)u_rid, (void*)maxspan, (void*)covered, (void*)u_toff, (void*)scan_tmp, (void*)d_out,

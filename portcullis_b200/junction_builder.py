@@ -161,7 +161,7 @@ class JuncGpu:
 
     def extra(self, rows, max_query_length):
         """All four `--extra` columns for a single-context run: rows as returned by fetch().  Returns
-        (EXTRA_DTYPE array in the order of rows, {tid: live-read maximum} of targets where htslib's pileup cap binds)."""
+        (EXTRA_DTYPE array in the order of rows, {tid: live-read maximum} of the targets where htslib's pileup read cap was replayed)."""
         x = self.extra_run(max_query_length)
         covered = np.zeros(self.n_targets, dtype=np.uint8)
         over = {}

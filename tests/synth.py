@@ -273,3 +273,28 @@ GOLDEN_SPECS = {
     "indel_rich": (13, dict(n_targets=3, target_len=10000, genes_per_target=6, reads_per_gene=(5, 50), indel_rate=0.5,
                             clip_rate=0.5, retain_rate=0.4, sub_rate=0.03), [None, "RF"]),
 }
+
+
+def deep_dataset(seed=21):
+    """Piles of > 8000 identical unspliced reads (htslib's pileup read cap, sam.c:1622/1906) next to crafted junctions whose
+    coverage windows touch them, plus reads without reference span ("20S") inside a capped column."""
+    import re
+    ds = make_dataset(seed, n_targets=2, target_len=6000, genes_per_target=4, reads_per_gene=(5, 40), multimap_frac=0.1,
+                      unspliced_indel=0.3, deep=((0, 1500, 4000, 80), (0, 1520, 5000, 90), (0, 1520, 300, 30), (0, 1530, 4000, 60),
+                                                 (0, 1531, 20, 10), (0, 4000, 9000, 40), (1, 2500, 8100, 50), (1, 2500, 10, 70)))
+
+    def add(t, pos, cigar):
+        g = ds["genomes"][t].decode().upper()
+        seq, x = "", pos
+        for n, op in re.findall(r"(\d+)([MNS])", cigar):
+            if op in "MS":
+                seq += g[x:x + int(n)]
+            if op != "S":
+                x += int(n)
+        ds["records"].append(dict(name="m%d_%d_%s_%d" % (t, pos, cigar, len(ds["records"])), tid=t, pos=pos, flag=0, mapq=60, cigar=cigar,
+                                  seq=seq.replace("X", "N"), xs=0, mtid=-1, mpos=-1))
+    add(0, 1300, "50M145N60M"); add(1, 2545, "15M100N50M"); add(1, 2300, "50M149N40M"); add(0, 3900, "60M95N30M")
+    for _ in range(3):
+        add(0, 1520, "20S"); add(1, 2500, "12S")
+    ds["records"].sort(key=lambda r: (r["tid"], r["pos"]))
+    return ds

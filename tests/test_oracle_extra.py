@@ -78,23 +78,8 @@ def test_extra_finalize_arithmetic():
 def test_oracle_pileup_cap_matches_reference_live(tmp_path):
     """Piles of > 8000 identical unspliced reads next to crafted junctions: htslib drops reads at its cap, the
     restatement drops the same ones (coverage is sensitive to a single read here)."""
-    import re
     import refrun
-    ds = synth.make_dataset(21, n_targets=2, target_len=6000, genes_per_target=4, reads_per_gene=(5, 40), multimap_frac=0.1,
-                            unspliced_indel=0.3, deep=((0, 1500, 4000, 80), (0, 1520, 5000, 90), (0, 1520, 300, 30), (0, 1530, 4000, 60),
-                                                       (0, 1531, 20, 10), (1, 2500, 8100, 50), (1, 2500, 10, 70)))
-
-    def add(t, pos, cigar):
-        g = ds["genomes"][t].decode().upper()
-        seq, x = "", pos
-        for n, op in re.findall(r"(\d+)([MN])", cigar):
-            if op == "M":
-                seq += g[x:x + int(n)]
-            x += int(n)
-        ds["records"].append(dict(name="m%d_%d" % (t, pos), tid=t, pos=pos, flag=0, mapq=60, cigar=cigar, seq=seq.replace("X", "N"),
-                                  xs=0, mtid=-1, mpos=-1))
-    add(0, 1300, "50M145N60M"); add(1, 2545, "15M100N50M"); add(1, 2300, "50M149N40M")
-    ds["records"].sort(key=lambda r: (r["tid"], r["pos"]))
+    ds = synth.deep_dataset()
     prep = refrun.make_prep_dir(ds, str(tmp_path / "deep"))
     refrun.run_reference(prep, str(tmp_path / "ref"), extra=True, exon_gff=False, intron_gff=False)
     _, _, rows, _, x, capped = oracle_all(prep)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--orientation", default=None)
     ap.add_argument("--workdir", default="/tmp/pj_scale")
     ap.add_argument("--skip-reference", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="run both sides with --extra (mm_score, coverage, up_aln, down_aln)")
     a = ap.parse_args()
     from compare import assert_exon_gff_equal, assert_tab_equal
     d = os.path.join(a.workdir, "%s_%g" % (a.preset, a.scale))
@@ -39,6 +40,11 @@ def main():
     out = {"preset": a.preset, "scale": a.scale, "records": meta["n_records"], "spliced": meta["n_spliced"], "pairs": meta["n_pairs"],
            "generate_s": round(t_gen, 1), "gpus": a.gpus, "host_threads": a.threads}
     extra = ["--orientation", a.orientation] if a.orientation else []
+    if a.extra:
+        extra.append("--extra")
+        out["extra"] = True
+    # the reference shells out to `samtools index` for --extra: oracle/samtools_shim answers with htslib-1.3's indexer
+    ref_env = dict(os.environ, PATH=os.path.join(ROOT, "oracle", "samtools_shim") + os.pathsep + os.environ.get("PATH", ""))
     cmd = [os.path.join(ROOT, "portcullis_b200", "bin", "portcullis"), "junc", "-t", str(a.threads), "--gpus", str(a.gpus), "--exon_gff", "--intron_gff",
            "-o", d + "/ours/p"] + extra + [d + "/prep"]
     t0 = time.time()
@@ -47,13 +53,15 @@ def main():
     if p.returncode != 0:
         out["ours_error"] = p.stderr[-400:]
         print(json.dumps(out)); return 1
+    if a.extra:
+        out["ours_warnings"] = [l for l in p.stderr.split("\n") if l.startswith("Warning")][:3]
     out["ours_runtime_line"] = [l.strip() for l in p.stdout.split("\n") if "Total runtime" in l][-1]
     out["ours_spliced_per_s"] = round(meta["n_spliced"] / out["ours_s"])
     if not a.skip_reference:
         nt = min(a.threads, meta["n_targets"])
         cmd = [os.path.join(ROOT, "oracle", "_ref", "portcullis_ref"), "junc", "-t", str(nt), "--exon_gff", "--intron_gff", "-o", d + "/ref/p"] + extra + [d + "/prep"]
         t0 = time.time()
-        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=ref_env)
         out["reference_s"] = round(time.time() - t0, 2)
         out["reference_threads"] = nt
         if p.returncode != 0:
