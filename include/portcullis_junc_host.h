@@ -32,7 +32,7 @@ typedef struct pjh_options {
     int32_t intron_gff;          /* --intron_gff                                                  */
     const char* source;          /* --source, default "portcullis"                                */
     int32_t verbose;             /* -v                                                            */
-    int32_t separate;            /* --separate  (writing the three BAM files is not on this path: rejected) */
+    int32_t separate;            /* --separate: also write <prefix>.spliced/.unspliced/.unmapped.bam (+ indices) */
     int32_t extra;               /* --extra: mm_score, coverage, up_aln, down_aln from the records in HBM   */
     int32_t quiet;               /* suppress the progress text on stdout                          */
     const char* version;         /* string for the BED track line; NULL -> "1.2.4"                */
@@ -56,6 +56,7 @@ typedef struct pjh_report {
     double  t_run_s;             /* wall time of pj_shard_run + pj_shard_fetch (max over GPUs)    */
     double  t_teardown_s;        /* pj_destroy                                                    */
     double  t_extra_s;           /* --extra: name exchange + pj_extra_run + coverage (0 otherwise) */
+    double  t_separate_s;        /* --separate: splitting + indexing the BAM on the host (0 otherwise) */
 } pjh_report;
 
 void pjh_options_default(pjh_options* o);
@@ -91,6 +92,12 @@ int         pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_t
 /* Checks the built-in fast DEFLATE decoder (BGZF blocks) against zlib on n_cases synthetic streams; returns the number of
  * mismatches (0 = pass).  BGZF blocks the fast decoder rejects are decoded by zlib, so it can only be an accelerator. */
 int         pjh_inflate_selftest(int32_t n_cases);
+
+/* ---- `--separate` (JunctionBuilder::separateBams, src/junction_builder.cc:152-226) ----
+ * Splits the prepared BAM into <output_prefix>.spliced.bam (any N op), .unspliced.bam (mapped, no N) and .unmapped.bam and
+ * indexes the first two (BAI, or CSI with use_csi).  Host only: pjh_junc_run calls it first when options.separate is set.
+ * counts[3] = records written to spliced / unspliced / unmapped. */
+int pjh_separate_bams(const char* prep_dir, const char* output_prefix, int32_t use_csi, int32_t threads, uint64_t* counts);
 
 /* ---- writers (A14) ---- */
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,

@@ -85,7 +85,7 @@ class PjhReport(C.Structure):
                 ("t_finalize_s", C.c_double), ("t_write_s", C.c_double), ("t_total_s", C.c_double),
                 ("n_gpus_used", C.c_int32), ("n_kernel_launches", C.c_int32),
                 ("t_init_s", C.c_double), ("t_run_s", C.c_double), ("t_teardown_s", C.c_double),
-                ("t_extra_s", C.c_double)]
+                ("t_extra_s", C.c_double), ("t_separate_s", C.c_double)]
 
 
 # every symbol declared in include/*.h, with (restype, argtypes); used by load() and by the export test
@@ -132,6 +132,7 @@ SYMBOLS = {
     "pjh_prep_genome": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
     "pjh_inflate_selftest": (C.c_int, [C.c_int32]),
     "pjh_plan_shards": (C.c_int, [_P, C.c_int32, _P]),
+    "pjh_separate_bams": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _P]),
     "pjh_write_outputs_extra": (C.c_int, [C.c_char_p, _P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,
                                           C.c_int32, C.c_int32]),
     "pjh_write_outputs": (C.c_int, [C.c_char_p, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,

@@ -215,7 +215,7 @@ bool BamFile::load_csi(const std::string& csi_path) {
     need(16);
     if (memcmp(p, "CSI\1", 4) != 0) throw IoError("not a CSI index: " + csi_path);
     const int32_t min_shift = (int32_t)rd32(p + 4), depth = (int32_t)rd32(p + 8); const uint32_t l_aux = rd32(p + 12);
-    if (min_shift < 1 || min_shift > 30 || depth < 1 || depth > 10) throw IoError("unsupported CSI geometry: " + csi_path);
+    if (min_shift < 1 || min_shift > 30 || depth < 0 || depth > 10) throw IoError("unsupported CSI geometry: " + csi_path);   // depth 0: htslib writes it for targets shorter than one window
     o = 16; need(l_aux + 4ull); o += l_aux;
     const uint32_t n_ref = rd32(p + o); o += 4;
     auto first_bin = [](int lvl) { return (uint64_t)(((1ull << (3 * lvl)) - 1) / 7); };

@@ -115,6 +115,13 @@ private:
 // paired.  Stands in for std::hash<string> (junction.hpp:158): only equality matters.  FNV-1a then a 64-bit finaliser.
 uint64_t name_code(const char* qname, size_t len, uint16_t flag);
 
+// `junc --separate` (JunctionBuilder::separateBams, src/junction_builder.cc:152-226): every record of the BAM goes to one of
+// three files — spliced (any N op), unspliced (mapped, no N), unmapped — laid out block for block like htslib's BamWriter
+// output; the first two get a BAI (or CSI) index.  Inflate and deflate run on `threads` host threads.  bam_separate.cpp.
+struct SeparateCounts { uint64_t spliced = 0, unspliced = 0, unmapped = 0; };
+void separate_bams(const BamFile& bam, const std::string& spliced_path, const std::string& unspliced_path, const std::string& unmapped_path,
+                   bool use_csi, int threads, SeparateCounts& counts);
+
 int inflate_selftest(int n_cases);
 
 } // namespace pjio

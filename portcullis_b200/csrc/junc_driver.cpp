@@ -202,6 +202,22 @@ int pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_t* n_bas
     return PJ_OK;
 }
 
+int pjh_separate_bams(const char* prep_dir, const char* output_prefix, int32_t use_csi, int32_t threads, uint64_t* counts) {
+    if (!prep_dir || !output_prefix) return fail(PJ_EINVAL, "pjh_separate_bams: null argument");
+    pjh_prep* prep = nullptr;
+    int rc = pjh_prep_open(prep_dir, use_csi, &prep);
+    if (rc) return rc;
+    std::unique_ptr<pjh_prep> guard(prep);
+    const std::string pre(output_prefix);
+    fs::path parent = fs::path(pre).parent_path();
+    if (!parent.empty()) { std::error_code ec; fs::create_directories(parent, ec); }
+    pjio::SeparateCounts sc;
+    try { pjio::separate_bams(prep->bam, pre + ".spliced.bam", pre + ".unspliced.bam", pre + ".unmapped.bam", use_csi != 0, std::max(1, threads), sc); }
+    catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    if (counts) { counts[0] = sc.spliced; counts[1] = sc.unspliced; counts[2] = sc.unmapped; }
+    return PJ_OK;
+}
+
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows, int32_t n_targets, const char* const* names,
                       const int32_t* lens, const char* source, const char* version, int32_t exon_gff, int32_t intron_gff) {
     return pjh_write_outputs_extra(output_prefix, rows, nullptr, n_rows, n_targets, names, lens, source, version, exon_gff, intron_gff);
@@ -254,9 +270,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     pjh_report R; memset(&R, 0, sizeof R);
     const double t0 = now_s();
     const bool say = !o->quiet;
-    if (o->separate)
-        return fail(PJ_EINVAL, "--separate (writing spliced / unspliced / unmapped BAM files) is not part of the GPU junc path; --extra does not need it here");
-    const bool extra = o->extra != 0;      // junction_builder.cc:113-117 turns --separate on for --extra; the metrics come from the records in HBM instead
+    const bool extra = o->extra != 0;      // junction_builder.cc:113-117 turns --separate on for --extra; here the metrics come from the records in HBM instead
     const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
     {   // output directory (junction_builder.cc:65-66, 86-91)
         fs::path parent = fs::path(prefix).parent_path();
@@ -280,7 +294,21 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         std::cout << "Settings:\n - BAM Strandedness: " << STR[std::min(std::max(o->strandedness, 0), 3)]
                   << "\n - BAM Read Orientation: " << ORI[std::min(std::max(o->orientation, 0), 4)]
                   << "\n - BAM Indexing mode: " << (o->use_csi ? "CSI" : "BAI")
-                  << "\n - Host decode threads: " << threads << "\n - GPUs: " << n_gpus << "\n - Separate BAMs: false\n\n";
+                  << "\n - Host decode threads: " << threads << "\n - GPUs: " << n_gpus << "\n - Separate BAMs: " << (o->separate ? "true" : "false") << "\n\n";
+    }
+    if (o->separate) {
+        // JunctionBuilder::separateBams (junction_builder.cc:152-226): host I/O only, before the junction pass like the reference
+        const double ts = now_s();
+        pjio::SeparateCounts sc;
+        const std::string un = prefix + ".unspliced.bam", sp = prefix + ".spliced.bam", um = prefix + ".unmapped.bam";
+        if (say) std::cout << "Splitting BAM:\n - Saving unspliced alignments to: \"" << un << "\"\n - Saving spliced alignments to: \"" << sp
+                           << "\"\n - Saving unmapped reads to: \"" << um << "\"\n - Processing BAM ..." << std::flush;
+        try { pjio::separate_bams(prep->bam, sp, un, um, o->use_csi != 0, threads, sc); }
+        catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+        R.t_separate_s = now_s() - ts;
+        if (say) std::cout << " done.\n - Found " << sc.spliced << " spliced alignments.\n - Found " << sc.unspliced << " unspliced alignments.\n - Found "
+                           << sc.unmapped << " unmapped reads.\n - Indexed the unspliced and spliced alignments (" << (o->use_csi ? "CSI" : "BAI") << ").\n = Wall time taken: "
+                           << std::fixed << std::setprecision(1) << R.t_separate_s << "s\n" << std::defaultfloat << std::setprecision(6) << std::endl;
     }
     // ---- shard targets over GPUs: LPT on index record counts (fallback: compressed bytes) ----
     std::vector<std::vector<DecodeTask>> ttasks((size_t)T);
@@ -562,7 +590,7 @@ static void junc_usage() {
                  "System options:\n"
                  "  -t [ --threads ] arg (=1)         The number of host threads used to decode the BAM file.\n"
                  "  --gpus arg (=1)                   The number of GPUs to shard target sequences over.\n"
-                 "  --separate                        Separate spliced from unspliced reads (not available on the GPU path).\n"
+                 "  --separate                        Separate spliced from unspliced reads.\n"
                  "  --extra                           Calculate the additional metrics mm_score, coverage, up_aln and down_aln (from the\n"
                  "                                    records on the GPU; no separated BAM files are written).\n"
                  "  --orientation arg (=UNKNOWN)      The orientation of the reads that produced the BAM alignments: \"SE\", \"FR\", \"RF\", \"FF\", \"UNKNOWN\".\n"

@@ -209,6 +209,16 @@ def finalize(rows, mean_query_length):
     return rows
 
 
+def separate_bams(prep_dir, output_prefix, use_csi=False, threads=1):
+    """`junc --separate` on its own (host only): writes <prefix>.spliced/.unspliced/.unmapped.bam and the two indices.
+    Returns (n_spliced, n_unspliced, n_unmapped)."""
+    lib = L.load()
+    counts = np.zeros(3, dtype=np.uint64)
+    _check(lib.pjh_separate_bams(os.fsencode(prep_dir), os.fsencode(output_prefix), int(use_csi), int(threads), counts.ctypes.data),
+           lib.pjh_last_error)
+    return tuple(int(x) for x in counts)
+
+
 def coverage_source(covered):
     """Q14: which target's depth vector the reference applies to the junctions of each target (-1: none)."""
     lib = L.load()

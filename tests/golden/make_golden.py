@@ -6,7 +6,8 @@
 
 Each fixture directory holds the inputs (genome.fa[.fai], reads.bam[.bai]) and the reference's outputs
 (ref.junctions.tab/.bed/.exon.gff3/.intron.gff3, plus ref_FR.* for --orientation FR where listed, and
-ref_extra.junctions.tab from `junc --extra`).
+ref_extra.junctions.tab from `junc --extra`, and ref_separate.md5: file / inflated-stream md5 of the spliced, unspliced
+and unmapped BAMs that run wrote).
 """
 import os
 import shutil
@@ -39,6 +40,13 @@ def finish(work, out, orientations):
     # the hidden --extra metrics (mm_score, coverage, up_aln, down_aln): only the tab differs
     refrun.run_reference(prep, os.path.join(work, "ref_extra"), extra=True, exon_gff=False, intron_gff=False)
     shutil.copy(os.path.join(work, "ref_extra.junctions.tab"), os.path.join(out, "ref_extra.junctions.tab"))
+    # --extra implies --separate: keep the md5 of the three BAM files (whole file, and the inflated record stream)
+    import gzip
+    import hashlib
+    with open(os.path.join(out, "ref_separate.md5"), "w") as f:
+        for kind in ("spliced", "unspliced", "unmapped"):
+            raw = open(os.path.join(work, "ref_extra.%s.bam" % kind), "rb").read()
+            f.write("%s\t%s\t%s\n" % (kind, hashlib.md5(raw).hexdigest(), hashlib.md5(gzip.decompress(raw)).hexdigest()))
 
 
 def main():
