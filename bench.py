@@ -261,10 +261,55 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args, cores)
         if world == 1 and not args.no_bam:
             line["e2e_bam"] = e2e_bam(prep, cores, n_spliced)
+        if world == 1 and args.extra:
+            g.close()
+            line["extra_metrics"] = extra_leg(p, local, genomes, cores, max(2, min(args.steps, 5)))
         print(json.dumps(line))
     g.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_leg(p, device, genomes, cores, steps):
+    """The `--extra` metrics on the bench workload: device time of pj_extra_run (CUDA events inside the
+    library) and of the whole junc + extra step, inputs resident in pinned host memory."""
+    import numpy as np
+    from portcullis_b200 import junction_builder as jb
+    cols = p.decode(-1, cores, names=True)
+    n = len(cols["pos"])
+    g = jb.JuncGpu(device, "UNKNOWN", extra=True)
+    g.set_targets(p.lengths)
+    for t, s in enumerate(genomes):
+        g.set_genome(t, s)
+    acc, stage_acc, junc_ms, cov_s = 0.0, {}, 0.0, 0.0
+    for it in range(steps + 1):
+        g.shard_begin(n, len(cols["cigar"]), len(cols["seq4"]))
+        g.submit(cols)
+        g.run()
+        rows, st = g.fetch()
+        x = g.extra_run(int(st["maxq"].max()))
+        t0 = time.perf_counter()
+        covered = np.array([g.target_pileup(t)[0] for t in range(len(p.lengths))], dtype=np.uint8)
+        src = jb.coverage_source(covered)
+        for t in np.unique(rows["tid"]):
+            if src[t] >= 0:
+                sel = np.nonzero(rows["tid"] == t)[0]
+                x["cov_sum"][sel] = g.coverage(src[t], rows["start"][sel], rows["end"][sel])
+        dt = time.perf_counter() - t0
+        if it == 0:
+            continue                                   # warm-up
+        ms, nl, stages = g.extra_timing()
+        acc += ms
+        cov_s += dt
+        junc_ms += g.timing()[0]
+        for name, v in stages:
+            stage_acc[name] = stage_acc.get(name, 0.0) + v
+    g.close()
+    x = jb.extra_finalize(x)
+    return {"pj_extra_run_device_ms": round(acc / steps, 3), "launches": nl, "stage_ms": {k: round(v / steps, 4) for k, v in stage_acc.items()},
+            "coverage_queries_wall_ms": round(cov_s / steps * 1e3, 3), "junc_pipeline_device_ms_in_extra_mode": round(junc_ms / steps, 3),
+            "junctions": int(len(rows)), "unspliced_flank_total": int(x["up_aln"].astype(np.int64).sum() + x["down_aln"].astype(np.int64).sum()),
+            "steps": steps}
 
 
 def e2e_bam(prep, cores, n_spliced):
@@ -361,6 +406,7 @@ def main():
     ap.add_argument("--cpu-sample-frac", type=float, default=0.2, help="fraction of the workload the CPU reference is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bam", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time the `--extra` metrics phase (pj_extra_run + coverage) on the same workload; adds an extra_metrics object")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

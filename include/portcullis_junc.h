@@ -270,6 +270,11 @@ int pj_extra_import_names(pj_ctx* ctx, const uint64_t* codes, int64_t n);
  */
 int pj_extra_run(pj_ctx* ctx, int32_t max_query_length, pj_junction_extra* out, int64_t cap_rows);
 
+/* Device time (CUDA events) and kernel launches of the last pj_extra_run, and its per-stage breakdown (x_unspliced,
+ * x_mm_score, x_flank, x_live, [x_cap,] x_depth) — same conventions as pj_shard_timing / pj_shard_kernel_times. */
+int pj_extra_timing(const pj_ctx* ctx, float* total_ms, int32_t* n_launches);
+int pj_extra_kernel_times(const pj_ctx* ctx, int32_t cap, float* kernel_ms, const char** kernel_names, int32_t* n);
+
 /*
  * Unspliced pileup of one target held by this context (DepthParser, depth_parser.cc:112-167): *covered = 1 when the
  * pileup reports at least one position, *max_depth = the largest number of reads alive on one position (reads with

@@ -113,6 +113,8 @@ SYMBOLS = {
     "pj_extra_export_names": (C.c_int, [_P, _P, C.c_int64]),
     "pj_extra_import_names": (C.c_int, [_P, _P, C.c_int64]),
     "pj_extra_run": (C.c_int, [_P, C.c_int32, _P, C.c_int64]),
+    "pj_extra_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "pj_extra_kernel_times": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "pj_extra_target_pileup": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
     "pj_extra_coverage": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "pj_extra_coverage_source": (None, [C.c_int32, _P, _P]),

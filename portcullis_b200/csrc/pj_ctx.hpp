@@ -75,6 +75,7 @@ struct pj_ctx {
     std::vector<uint64_t> x_imported;                                   // spliced names of other contexts (pj_extra_import_names)
     uint32_t* x_depth = nullptr; std::vector<uint64_t> x_doff;          // unspliced pileup per target: x_doff[t] .. + tlen + 1 slots
     std::vector<uint8_t> x_covered; std::vector<uint32_t> x_maxlive; bool x_ready = false;
+    std::vector<float> x_stage_ms; std::vector<const char*> x_stage_names; float x_total_ms = 0; int x_launches = 0;
     // timing
     std::vector<pjapi::StageTime> stages; size_t n_stage = 0; float total_ms = 0; int n_launches = 0;
     std::vector<float> stage_ms; std::vector<const char*> stage_names;

@@ -301,11 +301,14 @@ __global__ void __launch_bounds__(32) k_x_cap(int32_t T, const uint32_t* __restr
     }
 }
 
-__global__ void __launch_bounds__(256) k_x_max(const uint32_t* __restrict__ v, uint64_t n, uint32_t* __restrict__ out) {
+// out[t] = max of target t's slice of v; blockIdx.y walks the targets [t0, t0 + gridDim.y)
+__global__ void __launch_bounds__(256) k_x_max(const uint32_t* __restrict__ v, const uint64_t* __restrict__ doff, int32_t t0, uint32_t* __restrict__ out) {
+    const int32_t t = t0 + (int32_t)blockIdx.y;
+    const uint32_t* p = v + doff[t]; const uint64_t n = doff[t + 1] - doff[t];
     uint32_t m = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, v[i]);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, p[i]);
     m = __reduce_max_sync(0xffffffffu, m);
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out + t, m);
 }
 
 // Junction::calcCoverage(a, b, levels) (junction.cc:923-933) for the four windows of :935-951
@@ -329,21 +332,38 @@ __global__ void __launch_bounds__(256) k_x_keep(uint32_t P, const uint32_t* __re
     if (i < P) rid[i] = pa[vals[i]].rid;
 }
 
+// CUDA-event stage marks of pj_extra_run (same idea as the marks of pj_shard_run)
+struct XMarks {
+    cudaStream_t st; std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    explicit XMarks(cudaStream_t s) : st(s) {}
+    void mark(const char* name) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.emplace_back(name, e); }
+    void collect(pj_ctx* c) {
+        c->x_stage_ms.clear(); c->x_stage_names.clear();
+        for (size_t k = 1; k < ev.size(); k++) { float ms = 0; cudaEventElapsedTime(&ms, ev[k - 1].second, ev[k].second); c->x_stage_ms.push_back(ms); c->x_stage_names.push_back(ev[k].first); }
+        c->x_total_ms = 0; if (ev.size() > 1) cudaEventElapsedTime(&c->x_total_ms, ev.front().second, ev.back().second);
+    }
+    ~XMarks() { for (auto& e : ev) cudaEventDestroy(e.second); }
+};
+
 inline uint32_t blocks_for(uint64_t n, uint32_t per) { return (uint32_t)((n + per - 1) / per); }
 
 } // namespace
 
 namespace pjapi {
 
+// All of this state comes from the stream-ordered pool (the pool keeps the memory between shards, so a steady-state
+// step pays no allocation) and is returned on the compute stream.
 void extra_reset(pj_ctx* c) {
-    cudaFree(c->x_pair_rid); cudaFree(c->x_pair_jid); cudaFree(c->x_names); cudaFree(c->x_uflag); cudaFree(c->x_alen); cudaFree(c->x_depth);
+    if (!c->compute_stream) return;
+    for (void* p : {(void*)c->x_pair_rid, (void*)c->x_pair_jid, (void*)c->x_names, (void*)c->x_uflag, (void*)c->x_alen, (void*)c->x_depth})
+        if (p) cudaFreeAsync(p, c->compute_stream);
     c->x_pair_rid = c->x_pair_jid = nullptr; c->x_names = nullptr; c->x_uflag = nullptr; c->x_alen = nullptr; c->x_depth = nullptr;
     c->x_n_spliced = -1; c->x_imported.clear(); c->x_doff.clear(); c->x_covered.clear(); c->x_maxlive.clear(); c->x_ready = false;
 }
 
 // end of pj_shard_run: remember, for every (read, junction) pair in sorted order, its record and its junction
 int extra_keep_pairs(pj_ctx* c, uint32_t P, const uint32_t* vals, const uint32_t* jid, const PairA* pa, cudaStream_t st) {
-    CU(c, cudaMalloc(&c->x_pair_rid, (size_t)std::max<uint32_t>(P, 1) * 4)); CU(c, cudaMalloc(&c->x_pair_jid, (size_t)std::max<uint32_t>(P, 1) * 4));
+    CU(c, cudaMallocAsync(&c->x_pair_rid, (size_t)std::max<uint32_t>(P, 1) * 4, st)); CU(c, cudaMallocAsync(&c->x_pair_jid, (size_t)std::max<uint32_t>(P, 1) * 4, st));
     if (P) {
         k_x_keep<<<blocks_for(P, 256), 256, 0, st>>>(P, vals, pa, c->x_pair_rid); c->n_launches++;
         CU(c, cudaMemcpyAsync(c->x_pair_jid, jid, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
@@ -356,8 +376,8 @@ int extra_keep_pairs(pj_ctx* c, uint32_t P, const uint32_t* vals, const uint32_t
 int extra_classify(pj_ctx* c, cudaStream_t st) {
     const int64_t R = c->n_rec;
     unsigned long long* d_n = nullptr;
-    CU(c, cudaMalloc(&c->x_names, (size_t)std::max<int64_t>(R, 1) * 8));
-    CU(c, cudaMalloc(&c->x_uflag, (size_t)std::max<int64_t>(R, 1) * 4)); CU(c, cudaMalloc(&c->x_alen, (size_t)std::max<int64_t>(R, 1) * 4));
+    CU(c, cudaMallocAsync(&c->x_names, (size_t)std::max<int64_t>(R, 1) * 8, st));
+    CU(c, cudaMallocAsync(&c->x_uflag, (size_t)std::max<int64_t>(R, 1) * 4, st)); CU(c, cudaMallocAsync(&c->x_alen, (size_t)std::max<int64_t>(R, 1) * 4, st));
     uint32_t* uflag = c->x_uflag; int32_t* alen = c->x_alen;
     CU(c, cudaMallocAsync(&d_n, 8, st)); CU(c, cudaMemsetAsync(d_n, 0, 8, st));
     CU(c, cudaMemsetAsync(c->d_scalars + 8, 0, 4 * sizeof(uint32_t), st));
@@ -408,6 +428,7 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
     CU(c, cudaMemcpy(&err, c->d_scalars + 8, 4, cudaMemcpyDeviceToHost));
     if (err & XERR_NOCIGAR) return fail(c, PJ_EDATA, "input rejected (the reference aborts on it): mapped unspliced record without CIGAR (htslib pileup, sam.c:1537)");
 
+    XMarks marks(st); marks.mark("begin"); int launches = 0;
     // ---- unspliced records, compacted in BAM order ----
     uint32_t* uoff = nullptr; uint32_t* scan_tmp = nullptr;
     CU(c, cudaMallocAsync(&uoff, (size_t)std::max<int64_t>(R, 1) * 4, st));
@@ -424,6 +445,7 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
     if (R) k_x_scatter<<<blocks_for((uint64_t)R, 256), 256, 0, st>>>(R, uflag, uoff, c->tid.p, c->pos.p, alen, u_tid, u_pos, u_alen, u_rid, maxspan, covered);
     k_x_toff<<<blocks_for((uint64_t)U + 1, 256), 256, 0, st>>>(U, u_tid, u_pos, T, u_toff, c->d_scalars + 8);
     CU(c, cudaFreeAsync(uoff, st));
+    launches += 5; marks.mark("x_unspliced");
 
     // ---- multiple-mapping score: name table over the spliced records of the whole file ----
     pj_junction_extra* d_out = nullptr;
@@ -445,26 +467,30 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
         CU(c, cudaFreeAsync(keys, st)); CU(c, cudaFreeAsync(counts, st)); if (d_imp) { CU(c, cudaStreamSynchronize(st)); CU(c, cudaFreeAsync(d_imp, st)); }
     }
 
+    launches += 3; marks.mark("x_mm_score");
     // ---- flanking alignments ----
     if (J) k_x_flank<<<blocks_for((uint64_t)J * 32, 256), 256, 0, st>>>(J, c->d_rows, c->d_tlen, u_toff, u_pos, u_alen, maxspan, max_query_length, d_out);
     if (J) CU(c, cudaMemcpyAsync(out, d_out, (size_t)J * sizeof(pj_junction_extra), cudaMemcpyDeviceToHost, st));
 
+    launches += 1; marks.mark("x_flank");
     // ---- unspliced pileup: live-read maximum (htslib cap check), then the depth vectors kept for pj_extra_coverage ----
     c->x_doff.assign((size_t)T + 1, 0);
     for (int32_t t = 0; t < T; t++) c->x_doff[t + 1] = c->x_doff[t] + (uint64_t)c->h_tlen[t] + 1;
     const uint64_t D = c->x_doff[T];
     uint64_t* d_doff = nullptr; uint32_t* d_max = nullptr; uint32_t* dscan_tmp = nullptr;
-    CU(c, cudaMalloc(&c->x_depth, D * 4));
+    CU(c, cudaMallocAsync(&c->x_depth, D * 4, st));
     CU(c, cudaMallocAsync(&d_doff, ((size_t)T + 1) * 8, st)); CU(c, cudaMemcpyAsync(d_doff, c->x_doff.data(), ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(c, cudaMallocAsync(&d_max, (size_t)T * 4, st)); CU(c, cudaMemsetAsync(d_max, 0, (size_t)T * 4, st));
     CU(c, cudaMallocAsync(&dscan_tmp, scan_tmp_elems(D) * 4, st));
     CU(c, cudaMemsetAsync(c->x_depth, 0, D * 4, st));
     if (U) k_x_live<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_alen, c->d_tlen, d_doff, c->x_depth);
     launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
-    for (int32_t t = 0; t < T; t++) {
-        const uint64_t n = (uint64_t)c->h_tlen[t] + 1;
-        if (U && n > 1) k_x_max<<<std::min<uint32_t>(blocks_for(n, 256 * 8), 148 * 8), 256, 0, st>>>(c->x_depth + c->x_doff[t], n, d_max + t);
+    if (U) {
+        int32_t longest = 1; for (int32_t t = 0; t < T; t++) longest = std::max(longest, c->h_tlen[t]);
+        const uint32_t gx = std::max<uint32_t>(1, std::min<uint32_t>(blocks_for((uint64_t)longest + 1, 256 * 8), (uint32_t)(148 * 8 / std::min<int32_t>(T, 148) + 1)));
+        for (int32_t t0 = 0; t0 < T; t0 += 65535) k_x_max<<<dim3(gx, (uint32_t)std::min<int32_t>(65535, T - t0)), 256, 0, st>>>(c->x_depth, d_doff, t0, d_max);
     }
+    launches += 5 + (T - 1) / 65535; marks.mark("x_live");
     c->x_covered.assign((size_t)T, 0); c->x_maxlive.assign((size_t)T, 0);
     CU(c, cudaMemcpyAsync(c->x_covered.data(), covered, (size_t)T, cudaMemcpyDeviceToHost, st));
     CU(c, cudaMemcpyAsync(c->x_maxlive.data(), d_max, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
@@ -484,16 +510,33 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
         k_x_compact<<<blocks_for(U, 256), 256, 0, st>>>(U, hot, hoff, H);
         k_x_cap<<<(uint32_t)T, 32, 0, st>>>(T, u_toff, u_pos, u_alen, maxspan, c->d_tlen, d_doff, H, nH, c->x_depth, accepted);
     }
+    if (nH) { launches += 6; marks.mark("x_cap"); }
     if (U) k_x_depth<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_rid, c->cigar_off.p, c->cigar.p, accepted, c->d_tlen, d_doff, c->x_depth);
     launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
+    launches += 4; marks.mark("x_depth");
     for (void* p : {(void*)hot, (void*)hoff, (void*)H, (void*)accepted}) if (p) CU(c, cudaFreeAsync(p, st));
     CU(c, cudaMemcpyAsync(&err, c->d_scalars + 8, 4, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
     for (void* p : {(void*)u_tid, (void*)u_pos, (void*)u_alen, (void*)u_rid, (void*)maxspan, (void*)covered, (void*)u_toff, (void*)scan_tmp, (void*)d_out,
                     (void*)d_doff, (void*)d_max, (void*)dscan_tmp}) CU(c, cudaFreeAsync(p, st));
+    marks.collect(c); c->x_launches = launches;
     if (err & XERR_UNSORTED) return fail(c, PJ_EINVAL, "pj_extra_run: records are not in (tid, pos) order");
-    cudaFree(c->x_uflag); cudaFree(c->x_alen); c->x_uflag = nullptr; c->x_alen = nullptr;
+    cudaFreeAsync(c->x_uflag, st); cudaFreeAsync(c->x_alen, st); c->x_uflag = nullptr; c->x_alen = nullptr;
     c->x_ready = true;
+    return PJ_OK;
+}
+
+int pj_extra_timing(const pj_ctx* c, float* total_ms, int32_t* n_launches) {
+    if (!c || !c->x_ready) return PJ_ESTATE;
+    if (total_ms) *total_ms = c->x_total_ms;
+    if (n_launches) *n_launches = c->x_launches;
+    return PJ_OK;
+}
+
+int pj_extra_kernel_times(const pj_ctx* c, int32_t cap, float* kernel_ms, const char** kernel_names, int32_t* n) {
+    if (!c || !n) return PJ_EINVAL;
+    *n = (int32_t)c->x_stage_ms.size();
+    for (int32_t k = 0; k < cap && k < *n; k++) { if (kernel_ms) kernel_ms[k] = c->x_stage_ms[k]; if (kernel_names) kernel_names[k] = c->x_stage_names[k]; }
     return PJ_OK;
 }
 

@@ -146,6 +146,18 @@ class JuncGpu:
         _check(self._lib.pj_extra_run(self._ctx, int(max_query_length), out.ctypes.data, len(out)), self._err)
         return out
 
+    def extra_timing(self):
+        """(device ms, kernel launches, [(stage, ms)]) of the last extra_run()."""
+        ms = C.c_float()
+        nl = C.c_int32()
+        _check(self._lib.pj_extra_timing(self._ctx, C.byref(ms), C.byref(nl)), self._err)
+        k = C.c_int32()
+        self._lib.pj_extra_kernel_times(self._ctx, 0, None, None, C.byref(k))
+        tm = (C.c_float * k.value)()
+        nm = (C.c_char_p * k.value)()
+        self._lib.pj_extra_kernel_times(self._ctx, k.value, tm, nm, C.byref(k))
+        return ms.value, nl.value, [(nm[i].decode(), tm[i]) for i in range(k.value)]
+
     def target_pileup(self, tid):
         cov = C.c_int32()
         mx = C.c_uint32()
