@@ -110,9 +110,16 @@ __global__ void __launch_bounds__(256) k_x_mm(uint32_t P, const uint32_t* __rest
         if (cur == X_EMPTY) break;                                 // operator[] on a missing name inserts 0
         s = (s + 1) & mask;
     }
-    pj_junction_extra* o = out + pair_jid[i];
-    atomicAdd(&o->mm_n, 1u);
-    atomicAdd(&o->mm_m, cnt);                                      // uint32 sum, wraps like `uint32_t M` (junction.cc:916)
+    // pairs are sorted by junction: lanes of one junction combine first, so a junction with 100 000 alignments costs
+    // thousands of atomics on its row, not hundreds of thousands
+    const uint32_t j = pair_jid[i];
+    const unsigned peers = __match_any_sync(__activemask(), j);
+    const uint32_t total = __reduce_add_sync(peers, cnt);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        pj_junction_extra* o = out + j;
+        atomicAdd(&o->mm_n, (uint32_t)__popc(peers));
+        atomicAdd(&o->mm_m, total);                                // uint32 sum, wraps like `uint32_t M` (junction.cc:916)
+    }
 }
 
 __device__ __forceinline__ uint32_t x_lower(const int32_t* __restrict__ a, uint32_t lo, uint32_t hi, int64_t v) {     // first index with a[i] >= v
@@ -301,12 +308,25 @@ __global__ void __launch_bounds__(32) k_x_cap(int32_t T, const uint32_t* __restr
     }
 }
 
-// out[t] = max of target t's slice of v; blockIdx.y walks the targets [t0, t0 + gridDim.y)
+// out[t] = max of target t's slice of v; blockIdx.y walks the targets [t0, t0 + gridDim.y).  16-byte loads once the slice
+// is aligned (slices start at arbitrary word offsets), several of them in flight per thread.
 __global__ void __launch_bounds__(256) k_x_max(const uint32_t* __restrict__ v, const uint64_t* __restrict__ doff, int32_t t0, uint32_t* __restrict__ out) {
     const int32_t t = t0 + (int32_t)blockIdx.y;
     const uint32_t* p = v + doff[t]; const uint64_t n = doff[t + 1] - doff[t];
+    uint64_t head = (4 - (((uint64_t)(uintptr_t)p >> 2) & 3)) & 3; if (head > n) head = n;
+    const uint64_t nv = (n - head) >> 2;
+    const uint4* q = reinterpret_cast<const uint4*>(p + head);
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t m = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, p[i]);
+    uint64_t i = tid;
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+        const uint4 a = q[i], b = q[i + stride], c = q[i + 2 * stride], d = q[i + 3 * stride];
+        m = max(m, max(max(max(a.x, a.y), max(a.z, a.w)), max(max(b.x, b.y), max(b.z, b.w))));
+        m = max(m, max(max(max(c.x, c.y), max(c.z, c.w)), max(max(d.x, d.y), max(d.z, d.w))));
+    }
+    for (; i < nv; i += stride) { const uint4 a = q[i]; m = max(m, max(max(a.x, a.y), max(a.z, a.w))); }
+    if (tid < head) m = max(m, p[tid]);
+    for (uint64_t k = head + (nv << 2) + tid; k < n; k += stride) m = max(m, p[k]);
     m = __reduce_max_sync(0xffffffffu, m);
     if ((threadIdx.x & 31) == 0 && m) atomicMax(out + t, m);
 }
