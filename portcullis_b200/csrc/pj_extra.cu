@@ -501,7 +501,7 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
     CU(c, cudaMallocAsync(&c->x_depth, D * 4, st));
     CU(c, cudaMallocAsync(&d_doff, ((size_t)T + 1) * 8, st)); CU(c, cudaMemcpyAsync(d_doff, c->x_doff.data(), ((size_t)T + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(c, cudaMallocAsync(&d_max, (size_t)T * 4, st)); CU(c, cudaMemsetAsync(d_max, 0, (size_t)T * 4, st));
-    CU(c, cudaMallocAsync(&dscan_tmp, scan_tmp_elems(D) * 4, st));
+    CU(c, cudaMallocAsync(&dscan_tmp, scan_tmp_elems(std::max<uint64_t>(D, U)) * 4, st));      // also scans the U hot-read flags
     CU(c, cudaMemsetAsync(c->x_depth, 0, D * 4, st));
     if (U) k_x_live<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_alen, c->d_tlen, d_doff, c->x_depth);
     launch_exclusive_scan(c->x_depth, c->x_depth, D, dscan_tmp, c->d_scalars + 10, st);
