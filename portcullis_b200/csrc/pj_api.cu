@@ -246,6 +246,7 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 2 * sizeof(unsigned long long), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
+    CU(c, cudaMemsetAsync(c->seq4.p, 0, 16, st));                       // the lead pad is read (and masked out) by k_match: keep it defined
     // Pre-grow the stream-ordered pool that pj_shard_run allocates its temporaries from (about 12 B per record and 80 B
     // per read-junction pair): a cold pool costs hundreds of milliseconds for a multi-GB shard, and this way the growth
     // overlaps the caller's decode instead of sitting in front of the first kernel.
@@ -355,6 +356,7 @@ int pj_shard_run(pj_ctx* c) {
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     int rc = finish_genome(c); if (rc) return rc;
     cudaStream_t st = c->compute_stream;
+    CU(c, cudaMemsetAsync(c->seq4.p + c->n_seq, 0, 16, c->copy_stream));  // tail slack of the SEQ stream: read in 8-byte words, masked out
     CU(c, cudaEventRecord(c->copies_done, c->copy_stream));
     CU(c, cudaStreamWaitEvent(st, c->copies_done, 0));
     c->n_stage = 0; c->n_launches = 0; c->have_result = false;
