@@ -119,7 +119,7 @@ void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { 
 // one thread packs 64 bases: four 128-bit loads, two g2 words, one gx word
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ raw, int64_t n, uint64_t base_index /* multiple of 64 */,
-                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx, uint8_t* __restrict__ g4,
+                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx, uint64_t* __restrict__ g4,
                                                       uint64_t* __restrict__ exc_pos, uint8_t* __restrict__ exc_byte,
                                                       uint32_t* __restrict__ exc_count, uint32_t exc_cap) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
         for (int k = 0; k < 64; k++) c[k] = (b0 + k < n) ? raw[b0 + k] : (uint8_t)'A';
     }
     uint64_t w0 = 0, w1 = 0, x = 0;
-    uint32_t n4[8] = {0, 0, 0, 0, 0, 0, 0, 0};                       // 64 nibbles, BAM order: base 2j in the high nibble of byte j
+    uint64_t n8[4] = {0, 0, 0, 0};                                    // 4 words of 16 bases, base 16w + k in bits 63-4k .. 60-4k
 #pragma unroll
     for (int k = 0; k < 64; k++) {
         uint8_t ch = c[k];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
                           case 'H': q = 11; break; case 'K': q = 12; break; case 'D': q = 13; break; case 'B': q = 14; break; case 'N': q = 15; break;
                           default: q = 0; }
             if (b0 + k >= n) q = 0;
-            n4[k >> 3] |= q << (8 * ((k >> 1) & 3) + ((k & 1) ? 0 : 4));
+            n8[k >> 4] |= (uint64_t)q << (60 - 4 * (k & 15));
         }
         uint32_t code; bool exc = false;
         switch (ch) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
@@ -164,11 +164,11 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
     }
     const uint64_t gi = base_index + (uint64_t)b0;
     g2[gi >> 5] = w0; g2[(gi >> 5) + 1] = w1; gx[gi >> 6] = x;
-    uint4* o4 = reinterpret_cast<uint4*>(g4 + (gi >> 1));             // gi is a multiple of 64 -> 32-byte aligned
-    o4[0] = make_uint4(n4[0], n4[1], n4[2], n4[3]); o4[1] = make_uint4(n4[4], n4[5], n4[6], n4[7]);
+    ulonglong2* o4 = reinterpret_cast<ulonglong2*>(g4 + (gi >> 4));   // gi is a multiple of 64 -> 32-byte aligned
+    o4[0] = make_ulonglong2(n8[0], n8[1]); o4[1] = make_ulonglong2(n8[2], n8[3]);
 }
 
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint8_t* g4,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint64_t* g4,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st) {
     if (n <= 0) return;
     const int64_t threads = (n + 63) / 64;
@@ -949,6 +949,9 @@ void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32
 // expanded from the 2-bit plane to one-hot nibbles, so a mismatch is a non-zero nibble of an XOR.
 // ================================================================================================
 
+#ifndef PJ_MATCH_CTAS
+#define PJ_MATCH_CTAS 5          // resident CTAs per SM the register budget of k_match is set for (measured: 4 and 6 are slower on B200)
+#endif
 constexpr uint64_t NIB1 = 0x1111111111111111ull;
 
 // 16 consecutive nibbles of a BAM-ordered nibble stream (even index = high nibble of its byte), starting at nibble index
@@ -957,16 +960,6 @@ __device__ __forceinline__ uint64_t bswap64(uint64_t v) {
     const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
     return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
 }
-__device__ __forceinline__ uint64_t load_nibbles16(const uint8_t* __restrict__ base, uint64_t nib) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(base) + (uintptr_t)(nib >> 1);
-    const uint64_t* q = reinterpret_cast<const uint64_t*>(a & ~(uintptr_t)7);
-    const uint32_t o = (uint32_t)(a & 7) * 8 + (uint32_t)(nib & 1) * 4;       // bit offset into the 128-bit big-endian window
-    const uint64_t B = bswap64(__ldg(q));
-    if (o == 0) return B;
-    const uint64_t C = bswap64(__ldg(q + 1));
-    return (B << o) | (C >> (64 - o));
-}
-
 // ---- per-lane queue of compare blocks (shared memory, one column per thread: conflict-free) ----
 // Lanes of a warp reach their M/=/X blocks in different CIGAR iterations; comparing inside the walk would make the
 // warp pay the longest block in EVERY iteration.  Instead the walk only queues (SEQ nibble index, genome index, length,
@@ -985,30 +978,52 @@ struct PairStats { uint32_t mism_l, mism_r; int32_t last_left; int32_t first_rig
 // 64-bit load); SEQ is extracted unaligned.  The left anchor tracks its LAST mismatch, the right anchor its FIRST: that is
 // all getNbMatchesFromEnd / getNbMatchesFromStart need.  Equal characters <=> equal nibbles because g4 uses the BAM
 // alphabet; code 0 (bytes outside it) is resolved exactly through the side table.
+struct MatchMasks { uint64_t first[16]; uint64_t last[17]; };     // column masks of a block's first / last chunk (shared memory: conflict-free 8-byte lookups)
+__device__ __forceinline__ void init_match_masks(MatchMasks& M) {
+    if (threadIdx.x < 16) M.first[threadIdx.x] = ~0ull >> (4 * threadIdx.x);                                   // a0 columns before the block
+    else if (threadIdx.x < 33) { const int t = threadIdx.x - 16; M.last[t] = t >= 16 ? ~0ull : ~(~0ull >> (4 * t)); }   // t valid columns
+}
+
 template <int G>
-__device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome& Gn, const uint8_t* __restrict__ seq4, int gl, PairStats& r) {
+__device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, int nq, const Genome& Gn, const uint8_t* __restrict__ seq4, int gl, PairStats& r) {
     const int col = threadIdx.x;
-    int bi = -1; int32_t k = 0, nchunk = 0, a0 = 0, len = 0, sbase = 0, side = 0;
-    uint64_t qn = 0, gi0 = 0; const uint64_t* gw = nullptr;
+    int bi = -1; int32_t k = 0, nchunk = 0, a0 = 0, sbase = 0, side = 0;
+    uint32_t o = 0; int32_t tl = 0;
+    uint64_t gi0 = 0; uint32_t Bh = 0, Bl = 0;                                        // big-endian halves of SEQ word k (G == 1: carried)
+    const uint64_t* gw = nullptr; const uint2* qw = nullptr;
     for (;;) {
         if (k >= nchunk) {                                                            // next block of this lane
             if (++bi >= nq) break;
-            gi0 = Q.gi[bi][col]; len = Q.len[bi][col];
+            gi0 = Q.gi[bi][col];
+            const int32_t len = Q.len[bi][col];
             const int32_t sbv = Q.sb[bi][col]; sbase = sbv >> 1; side = sbv & 1;
-            a0 = (int32_t)(gi0 & 15);
+            a0 = (int32_t)(gi0 & 15);                                                 // chunks are aligned to the genome words
             nchunk = (a0 + len + 15) >> 4;
-            gw = reinterpret_cast<const uint64_t*>(Gn.g4) + ((gi0 - a0) >> 4);
-            qn = Q.qn[bi][col] - (uint64_t)a0;                                        // SEQ stream has a 16-byte lead pad
+            gw = Gn.g4 + ((gi0 - a0) >> 4);
+            // the SEQ nibbles of chunk k are the 64 bits at bit offset o of the big-endian words qw[k], qw[k + 1]: the offset
+            // is the same for every chunk of the block (the stream has a 16-byte lead pad and 16 bytes of tail slack)
+            const uint64_t qn0 = Q.qn[bi][col] - (uint64_t)a0;
+            const uintptr_t ad = reinterpret_cast<uintptr_t>(seq4) + (uintptr_t)(qn0 >> 1);
+            qw = reinterpret_cast<const uint2*>(ad & ~(uintptr_t)7);
+            o = (uint32_t)(ad & 7) * 8 + (uint32_t)(qn0 & 1) * 4;
+            tl = a0 + len;                                                            // end column of the block in chunk coordinates
             k = gl;
             if (k >= nchunk) continue;
+            if (G == 1) { const uint2 v = __ldg(qw); Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123); }
         }
-        const uint64_t g = bswap64(__ldg(gw + k));
-        const uint64_t x = load_nibbles16(seq4, qn + (uint64_t)(16 * k));
-        const int32_t c0 = 16 * k - a0;                                               // column of nibble 0 of this chunk
-        const int32_t t_hi = min(16, len - c0);
-        uint64_t V = t_hi >= 16 ? ~0ull : ~(~0ull >> (4 * t_hi));
-        if (c0 < 0) V &= ~0ull >> (4 * -c0);
+        if (G != 1) { const uint2 v = __ldg(qw + k); Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123); }
+        const uint2 cv = __ldg(qw + k + 1);                                           // consecutive chunks share a SEQ word: one load per chunk when G == 1
+        const uint32_t Ch = __byte_perm(cv.x, 0, 0x0123), Cl = __byte_perm(cv.y, 0, 0x0123);
+        // 64 bits at bit offset o of Bh:Bl:Ch:Cl, as two 32-bit funnel shifts
+        const bool up = (o & 32u) != 0; const uint32_t sh = o & 31u;
+        const uint32_t w0 = up ? Bl : Bh, w1 = up ? Ch : Bl, w2 = up ? Cl : Ch;
+        const uint64_t x = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | (uint64_t)__funnelshift_l(w2, w1, sh);
+        if (G == 1) { Bh = Ch; Bl = Cl; }
+        const uint64_t g = __ldg(gw + k);
+        const int32_t tk = tl - 16 * k;                                               // valid columns from this chunk's start (>= 16: all)
+        const uint64_t V = M.first[k == 0 ? a0 : 0] & M.last[tk < 16 ? tk : 16];
         uint64_t d = (x ^ g) & V;
+        const int32_t c0 = 16 * k - a0;                                               // column of nibble 0 of this chunk
         if (Gn.n_zero_code) {                                                         // genome bytes outside the BAM alphabet (or '=')
             uint64_t z = ~(g | (g >> 1) | (g >> 2) | (g >> 3)) & NIB1 & V;
             while (z) {
@@ -1022,6 +1037,7 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome&
         if (d) {
             uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;
             const uint32_t cnt = (uint32_t)__popcll(m);
+            // max / min, not assignment: insertions and deletions update the same fields during the walk, before this drain
             if (side == 0) { r.mism_l += cnt; r.last_left = max(r.last_left, sbase + c0 + 15 - ((__ffsll((long long)d) - 1) >> 2)); }
             else           { r.mism_r += cnt; r.first_right = min(r.first_right, sbase + c0 + (__clzll((long long)d) >> 2)); }
         }
@@ -1033,7 +1049,7 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome&
 // and every op the right walk accepts starts at or after rightStart > leftEnd, so the two walks touch disjoint ops while
 // rPos / qPos accumulate identically (bam_alignment.cc:349-399).
 template <int G>
-__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, uint64_t gbase, int64_t glen,
+__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& M, const Genome& Gn, uint64_t gbase, int64_t glen,
                                                const uint32_t* __restrict__ cgn /* this junction's N op */, int32_t ops_before, int32_t ops_after,
                                                int32_t start, int32_t qpos_n, const uint8_t* __restrict__ seq4, uint64_t seq_nib0, int32_t qsize,
                                                int32_t left, int32_t leftEnd, int32_t rightStart, int32_t right, int gl, uint32_t& err,
@@ -1079,7 +1095,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, 
                 if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
                 Q.qn[nq][col] = seq_nib0 + (uint64_t)qPos; Q.gi[nq][col] = gbase + (uint64_t)(uint32_t)rPos;
                 Q.len[nq][col] = len; Q.sb[nq][col] = (int32_t)(cols << 1) | side;
-                if (++nq == MQ) { drain<G>(Q, nq, Gn, seq4, gl, r); nq = 0; }
+                if (++nq == MQ) { drain<G>(Q, M, nq, Gn, seq4, gl, r); nq = 0; }
             }
             cols += (uint32_t)len;
         } else if (cr) {                                                                   // D or N inside the window: 'X' vs genome
@@ -1103,7 +1119,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, 
         if (cr) rPos += L;
         if (cq) qPos += L;
     }
-    drain<G>(Q, nq, Gn, seq4, gl, r);
+    drain<G>(Q, M, nq, Gn, seq4, gl, r);
     if (side == 0) cols_l = cols; else cols_r = cols;
     if (G > 1) {   // combine the lanes of the group
         const int lane = threadIdx.x & 31;
@@ -1119,14 +1135,17 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, 
 }
 
 template <int G>
-__global__ void __launch_bounds__(256, 5) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+__global__ void __launch_bounds__(256, PJ_MATCH_CTAS) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairA* __restrict__ pa, const PairB* __restrict__ pb,
                                                 const PairC* __restrict__ pc, const PairD* __restrict__ pd,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
     __shared__ MatchQueue Q;
+    __shared__ MatchMasks M;
+    init_match_masks(M);
+    __syncthreads();                                                 // the only block-wide barrier: before any thread leaves
     const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
     const int gl = threadIdx.x % G;
-    if (i >= n) return;                                              // whole groups leave together; no block-wide barrier is used
+    if (i >= n) return;                                              // whole groups leave together
     const uint32_t j = jid[i];
     const uint32_t idx = vals[i];
     const PairA a = pa[idx]; const PairB b = pb[idx]; const PairC c = pc[idx]; const PairD d = pd[idx];
@@ -1144,7 +1163,7 @@ __global__ void __launch_bounds__(256, 5) k_match(uint32_t n, const uint32_t* __
         if (glen < 0) err |= ERR_GENOME_RANGE;
         PairStats S{0u, 0u, -1, INT32_MAX}; uint32_t cols_l = 0, cols_r = 0;
         if (!err) {
-            S = walk_pair<G>(Q, Gn, Gn.goff[tid], glen, R.cigar + c.cig_abs, (int32_t)(d.nops & 0xffffu), (int32_t)(d.nops >> 16), start, c.qpos_n,
+            S = walk_pair<G>(Q, M, Gn, Gn.goff[tid], glen, R.cigar + c.cig_abs, (int32_t)(d.nops & 0xffffu), (int32_t)(d.nops >> 16), start, c.qpos_n,
                              R.seq4, c.seq_nib0, d.qsize, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
             if (cols_l == 0 || cols_r == 0) err |= ERR_EMPTY_ANCHOR;
         }

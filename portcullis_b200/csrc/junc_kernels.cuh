@@ -43,7 +43,8 @@ enum : uint32_t {
 struct Genome {
     const uint64_t* g2;
     const uint64_t* gx;
-    const uint8_t*  g4;         // 4 bits per base in the BAM SEQ alphabet and nibble order (even base = high nibble): the plane the
+    const uint64_t* g4;         // 4 bits per base in the BAM SEQ alphabet, 16 bases per word, base 16w + k in bits 63-4k..60-4k (the order a
+                                // byte-swapped BAM SEQ word has, so only the read side needs the swap): the plane the
                                 // mismatch walk XORs against SEQ.  Code 0 = '=' or a byte outside "=ACMGRSVTWYHKDBN" (exact byte in the side table)
     const uint64_t* goff;       // [n_targets] first base index of each target (multiple of 64)
     const int64_t*  glen;       // [n_targets] sequence length from the FASTA (-1 when the target was not loaded)
