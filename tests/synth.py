@@ -245,6 +245,10 @@ def to_sam(ds):
     for r in ds["records"]:
         mt = "*" if r["mtid"] < 0 else ("=" if r["mtid"] == r["tid"] else ds["names"][r["mtid"]])
         xs = ("\tXS:A:%s" % r["xs"]) if r["xs"] else ""
+        if r.get("tags_before"):          # other aux fields in front of XS (aligner output order): the decoder must step over every type
+            xs = "\t" + r["tags_before"] + xs
+        if r.get("tags_after"):
+            xs = xs + "\t" + r["tags_after"]
         out.append("%s\t%d\t%s\t%d\t%d\t%s\t%s\t%d\t0\t%s\t*%s" % (
             r["name"], r["flag"], ds["names"][r["tid"]], r["pos"] + 1, r["mapq"], r["cigar"] or "*", mt, r["mpos"] + 1 if r["mpos"] >= 0 else 0,
             r["seq"], xs))
