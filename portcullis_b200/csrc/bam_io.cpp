@@ -315,15 +315,22 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
     std::vector<uint8_t> rec;
     const int32_t n_ref = (int32_t)hdr_.lens.size();
     for (;;) {
-        uint8_t b4[4];
-        size_t g = s.read(b4, 4);
-        if (g == 0) break;
-        if (g != 4) throw IoError("truncated BAM record in " + file_.path());
-        uint32_t bs = rd32(b4);
+        uint32_t bs;
+        if (const uint8_t* h = s.take(4)) bs = rd32(h);
+        else {
+            uint8_t b4[4];
+            size_t g = s.read(b4, 4);
+            if (g == 0) break;
+            if (g != 4) throw IoError("truncated BAM record in " + file_.path());
+            bs = rd32(b4);
+        }
         if (bs < 32) throw IoError("corrupt BAM record (block_size < 32)");
-        rec.resize(bs);
-        if (s.read(rec.data(), bs) != bs) throw IoError("truncated BAM record in " + file_.path());
-        const uint8_t* p = rec.data();
+        const uint8_t* p = s.take(bs);                      // most records lie inside one BGZF block: parse them in place
+        if (!p) {
+            rec.resize(bs);
+            if (s.read(rec.data(), bs) != bs) throw IoError("truncated BAM record in " + file_.path());
+            p = rec.data();
+        }
         int32_t tid = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
         uint32_t l_name = p[8]; uint8_t mapq = p[9];
         uint32_t n_cig = rd16(p + 12); uint16_t flag = rd16(p + 14);

@@ -39,6 +39,8 @@ public:
     void seek(uint64_t voff);
     uint64_t tell() const;                 // virtual offset of the next byte
     size_t read(void* dst, size_t n);      // returns bytes delivered (< n only at EOF)
+    // n bytes straight out of the current block when it holds them all (no copy; valid until the next call), else nullptr
+    const uint8_t* take(size_t n) { if (have_block_ && (size_t)(ulen_ - upos_) >= n) { const uint8_t* p = ubuf_.data() + upos_; upos_ += (uint32_t)n; return p; } return nullptr; }
     bool eof();
 private:
     bool load_block(uint64_t coff);

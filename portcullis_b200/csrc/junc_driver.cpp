@@ -327,7 +327,8 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     struct GpuOut { pj_ctx* ctx = nullptr; std::vector<pj_junction_extra> extra; std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int rc = PJ_OK; std::string err; };
     std::vector<GpuOut> outs((size_t)n_gpus);
     const int threads_per_gpu = std::max(1, threads / n_gpus);
-    const size_t window_per_gpu = (size_t)threads_per_gpu * 3 + 2;      // decoded-but-unsubmitted batches (pageable while CUDA starts, pinned after)
+    // decoded-but-unsubmitted chunks (pageable): enough for the decode to keep going while a CUDA context is still starting
+    const size_t window_per_gpu = std::max<size_t>((size_t)threads_per_gpu * 4 + 2, 192);
     auto run_gpu = [&](int g) {
         GpuOut& out = outs[(size_t)g];
         auto bail = [&](int code, const std::string& m) { out.rc = code; out.err = m; };
@@ -345,7 +346,7 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
         std::thread gpu_thread([&]() {
             pj_config cfg; memset(&cfg, 0, sizeof cfg);
             cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
-            cfg.reserved[2] = (int32_t)window_per_gpu + 4;                 // pinned staging buffers
+            cfg.reserved[2] = 4;                                           // pinned staging buffers (filled by one thread, drained by the copy engine)
             cfg.extra_metrics = extra ? 1 : 0;
             int r = pj_create(&cfg, &ctx);
             std::string em;
@@ -373,7 +374,6 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             std::thread& t; pj_ctx*& c; double* td;
             ~Cleanup() { if (t.joinable()) t.join(); if (c) { const double a = now_s(); pj_destroy(c); *td = now_s() - a; } }
         } cleanup{gpu_thread, ctx, &out.teardown_s};
-        auto is_ready = [&]() { std::lock_guard<std::mutex> lk(gm); return ready; };
         auto wait_ready = [&]() -> int { std::unique_lock<std::mutex> lk(gm); gcv.wait(lk, [&] { return ready; }); return gpu_rc; };
         // copy one decoded chunk into a pinned staging buffer of the context
         auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
@@ -389,28 +389,37 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             st.n_records = ch.n();
             return PJ_OK;
         };
-        // alignments: workers inflate + parse a task and (once the context exists) copy its columns into pinned staging;
-        // this thread submits the batches in BAM order (cudaMemcpyAsync on the copy stream)
-        struct Payload { pj_batch st; std::unique_ptr<ColumnarChunk> chunk; };
+        // alignments: workers inflate + parse a task into a pooled pageable chunk (recycled, so its vectors keep their capacity and
+        // their faulted-in pages); this thread takes the chunks in BAM order, copies each into one of a few pinned staging buffers
+        // and enqueues the host-to-device copies.  Growing a large pinned pool costs far more (cudaMallocHost, about 0.6 ms per MB,
+        // serialised) than this one extra memcpy, and the decode can run ahead of a context that is still starting.
+        struct ChunkPool {
+            std::mutex mu; std::vector<std::unique_ptr<ColumnarChunk>> free_list;
+            std::unique_ptr<ColumnarChunk> get() {
+                { std::lock_guard<std::mutex> lk(mu); if (!free_list.empty()) { auto c = std::move(free_list.back()); free_list.pop_back(); return c; } }
+                return std::make_unique<ColumnarChunk>();
+            }
+            void put(std::unique_ptr<ColumnarChunk> c) { c->clear(); std::lock_guard<std::mutex> lk(mu); free_list.push_back(std::move(c)); }
+        } pool;
+        struct Payload { std::unique_ptr<ColumnarChunk> chunk; };
         const double td = now_s();
         int r = ordered_pipeline<Payload>(tasks.size(), threads_per_gpu, window_per_gpu,
             [&](size_t k, Payload& p) -> int {
-                auto ch = std::make_unique<ColumnarChunk>();
-                ch->with_names = extra;
-                prep->bam.decode(tasks[k], *ch);
-                memset(&p.st, 0, sizeof p.st);
-                if (ch->n() == 0) return PJ_OK;
-                if (!is_ready()) { p.chunk = std::move(ch); return PJ_OK; }   // context still starting: keep the chunk in pageable memory
-                if (gpu_rc) return fail(gpu_rc, gpu_err);
-                return stage(*ch, p.st);
+                p.chunk = pool.get();
+                p.chunk->with_names = extra;
+                prep->bam.decode(tasks[k], *p.chunk);
+                return PJ_OK;
             },
             [&](size_t, Payload& p) -> int {
-                if (!p.chunk && p.st.n_records == 0) return PJ_OK;
-                int q = wait_ready();
-                if (q) return fail(q, gpu_err);
-                if (p.chunk) { if ((q = stage(*p.chunk, p.st))) return q; p.chunk.reset(); }
-                q = pj_batch_submit(ctx, &p.st);
-                return q ? fail(q, pj_last_error(ctx)) : PJ_OK;
+                int q = PJ_OK;
+                if (p.chunk->n() > 0) {
+                    if ((q = wait_ready())) return fail(q, gpu_err);
+                    pj_batch st; memset(&st, 0, sizeof st);
+                    if ((q = stage(*p.chunk, st))) return q;
+                    if ((q = pj_batch_submit(ctx, &st))) q = fail(q, pj_last_error(ctx));
+                }
+                pool.put(std::move(p.chunk));
+                return q;
             });
         if (r) { wait_ready(); return bail(r, g_err); }
         out.decode_s = now_s() - td;

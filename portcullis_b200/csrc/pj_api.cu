@@ -48,7 +48,11 @@ int alloc_slot(pj_ctx* c, StagingSlot& s, int64_t cr, int64_t cc, int64_t cs) {
     const size_t sz[13] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r),
                            up((r + 1) * 4), up((size_t)cc * 4), up((r + 1) * 8), up((size_t)cs + 16), c->extra ? up(r * 8) : 0};
     size_t total = 0; for (size_t v : sz) total += v;
-    CU(c, cudaMallocHost((void**)&s.block, total));
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        CU(c, cudaMallocHost((void**)&s.block, total));
+        c->t_pinned_alloc_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); c->pinned_alloc_bytes += total; c->n_pinned_allocs++;
+    }
     s.block_bytes = total;
     uint8_t* p = s.block; size_t k = 0;
     s.tid = (int32_t*)p; p += sz[k++]; s.pos = (int32_t*)p; p += sz[k++]; s.l_qseq = (int32_t*)p; p += sz[k++]; s.mtid = (int32_t*)p; p += sz[k++];
@@ -146,6 +150,7 @@ void pj_destroy(pj_ctx* c) {
     double t0 = now();
     auto lap = [&](const char* what) { if (trace) { const double t = now(); fprintf(stderr, "[pj_destroy] %-22s %.3f s\n", what, t - t0); t0 = t; } };
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
+    if (trace) fprintf(stderr, "[pj_destroy] pinned staging: %d allocations, %.1f MB, %.3f s inside cudaMallocHost\n", c->n_pinned_allocs, c->pinned_alloc_bytes / 1e6, c->t_pinned_alloc_s);
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     lap("sync");

@@ -55,6 +55,7 @@ struct pj_ctx {
     pjapi::DevBuf<uint32_t> cigar_off, cigar; pjapi::DevBuf<uint64_t> seq_off;
     std::vector<pjapi::StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
     std::thread prewarm_thread;         // grows the stream-ordered memory pool while the caller is still decoding
+    double t_pinned_alloc_s = 0; size_t pinned_alloc_bytes = 0; int n_pinned_allocs = 0;   // PJ_TRACE: cost of growing the staging pool
     std::mutex staging_mu;              // pj_staging_acquire / pj_batch_submit may be called from several host threads
     cudaStream_t genome_stream = nullptr;
     cudaEvent_t copies_done = nullptr;
