@@ -956,6 +956,7 @@ constexpr uint64_t NIB1 = 0x1111111111111111ull;
 
 // 16 consecutive nibbles of a BAM-ordered nibble stream (even index = high nibble of its byte), starting at nibble index
 // `nib` of `base`, returned MSB-first: nibble t sits at bits [60-4t, 64-4t).  Two aligned 64-bit loads cover any alignment.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) {
     const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
     return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
@@ -1149,8 +1150,21 @@ __global__ void __launch_bounds__(256, PJ_MATCH_CTAS) k_match(uint32_t n, const 
     const uint32_t j = jid[i];
     const uint32_t idx = vals[i];
     const PairA a = pa[idx]; const PairB b = pb[idx]; const PairC c = pc[idx]; const PairD d = pd[idx];
+    // The walk below is a chain of dependent loads (CIGAR ops -> SEQ words / genome words).  The lines it will need are
+    // known already: ask for them now so that they arrive while the CIGAR is being walked.
+    if (G == 1) {
+        const uint8_t* sp = R.seq4 + (c.seq_nib0 >> 1);
+        prefetch_l1(R.cigar + c.cig_abs);
+        prefetch_l1(sp);
+        if (d.qsize > 200) prefetch_l1(sp + 100);
+    }
     const int32_t start = b.start, end = A.end[j], left = A.left[j], right = A.right[j];
     const int32_t tid = A.tid[j];
+    if (G == 1) {   // genome words under the two anchors of this read (16 bases per 8-byte word)
+        const uint64_t gb = Gn.goff[tid];
+        prefetch_l1(Gn.g4 + ((gb + (uint64_t)(uint32_t)max(left, a.pos)) >> 4));
+        prefetch_l1(Gn.g4 + ((gb + (uint64_t)(uint32_t)(end + 1)) >> 4));
+    }
     const int32_t lq = d.lq;
     uint32_t err = 0, mmes, minMatch, nbMism;
     const int32_t leftEnd = start - 1, rightStart = end + 1;
