@@ -661,6 +661,12 @@ int pjh_junc_main(int argc, char** argv) {
     o.prep_dir = prep.c_str(); o.output_prefix = output.c_str(); o.source = source.c_str();
     std::cout << "Running portcullis in junction builder mode\n------------------------------------------\n" << std::endl;
     pjh_report rep;
+    // CUDA start-up initialises every visible device (seconds on an 8-GPU box).  The command-line tool only ever uses
+    // devices 0..gpus-1, so unless the user chose the devices already, hide the rest before the first CUDA call.
+    if (!getenv("CUDA_VISIBLE_DEVICES") && o.n_gpus >= 1) {
+        std::string vis; for (int g = 0; g < o.n_gpus; g++) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 0);
+    }
     const int rc = pjh_junc_run(&o, &rep);
     if (rc) { std::cerr << "Error: " << pjh_last_error() << std::endl; return rc == PJ_EINVAL ? 1 : 4; }
     std::cout << std::fixed << std::setprecision(1) << "\nPortcullis junc completed.\nTotal runtime: " << rep.t_total_s << "s"
