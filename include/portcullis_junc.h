@@ -300,6 +300,15 @@ void pj_extra_coverage_source(int32_t n_targets, const uint8_t* covered, int32_t
 /* mm_score and coverage from the integer columns, with the reference's operation order. */
 void pj_extra_finalize(pj_junction_extra* x, int64_t n);
 
+/* ---- coordinate sort for `prep` (replaces `samtools sort`, src/prepare.cc:202-236) ---------------- */
+
+/*
+ * order[k] = index of the record that comes k-th in samtools' coordinate order: key = tid << 32 | (pos + 1) << 1 |
+ * reverse-strand flag (bam_sort.c bam1_lt), unplaced reads (tid = -1) last, equal keys in input order (stable).  One-sweep
+ * LSD radix sort of 64-bit keys on the given device; n < 2^30.  No context needed.
+ */
+int pj_coordinate_order(int32_t device, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag, uint32_t* order);
+
 /* ---- host finalize (A12/A13) --------------------------------------------------------------- */
 
 /*

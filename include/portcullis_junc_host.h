@@ -99,6 +99,32 @@ int         pjh_inflate_selftest(int32_t n_cases);
  * counts[3] = records written to spliced / unspliced / unmapped. */
 int pjh_separate_bams(const char* prep_dir, const char* output_prefix, int32_t use_csi, int32_t threads, uint64_t* counts);
 
+/* ---- `prep` without samtools (Prepare::prepare, src/prepare.cc:262-344) ----
+ * Lays out <output_dir>/portcullis.genome.fa[.fai] and portcullis.sorted.alignments.bam[.bai|.csi].  A single BAM whose header
+ * says SO:coordinate is symlinked (or copied); anything else — an unsorted BAM, several BAMs, or --force — is sorted / merged
+ * in process: records in host memory, coordinate order from pj_coordinate_order on `device`. */
+typedef struct pjh_prep_options {
+    const char* genome_file;
+    const char* const* bam_files; int32_t n_bam_files;
+    const char* output_dir;      /* -o, default "portcullis_prep"                                  */
+    int32_t force;               /* --force: clean the directory first, always re-sort             */
+    int32_t copy;                /* --copy: copy instead of symlink                                 */
+    int32_t use_csi;             /* -c                                                              */
+    int32_t threads;             /* -t: host threads for BGZF inflate / deflate                     */
+    int32_t verbose, quiet;
+    int32_t device;              /* GPU used for the coordinate order                               */
+} pjh_prep_options;
+typedef struct pjh_prep_report {
+    int64_t n_records;           /* records written by the in-process sort (0: input was linked)    */
+    int32_t sorted_in_process;
+    double  t_sort_s, t_sort_gpu_s, t_total_s;
+} pjh_prep_report;
+void pjh_prep_options_default(pjh_prep_options* o);
+int  pjh_prep_run(const pjh_prep_options* opt, pjh_prep_report* report);
+const char* pjh_prep_last_error(void);
+/* `portcullis prep ...` command line (argv[0] is the mode word).  Returns the process exit code. */
+int  pjh_prep_main(int argc, char** argv);
+
 /* ---- writers (A14) ---- */
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,
                       int32_t n_targets, const char* const* names, const int32_t* lens,

@@ -88,6 +88,17 @@ class PjhReport(C.Structure):
                 ("t_extra_s", C.c_double), ("t_separate_s", C.c_double)]
 
 
+class PjhPrepOptions(C.Structure):
+    _fields_ = [("genome_file", C.c_char_p), ("bam_files", C.POINTER(C.c_char_p)), ("n_bam_files", C.c_int32), ("output_dir", C.c_char_p),
+                ("force", C.c_int32), ("copy", C.c_int32), ("use_csi", C.c_int32), ("threads", C.c_int32), ("verbose", C.c_int32),
+                ("quiet", C.c_int32), ("device", C.c_int32)]
+
+
+class PjhPrepReport(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("sorted_in_process", C.c_int32), ("t_sort_s", C.c_double), ("t_sort_gpu_s", C.c_double),
+                ("t_total_s", C.c_double)]
+
+
 # every symbol declared in include/*.h, with (restype, argtypes); used by load() and by the export test
 _P = C.c_void_p
 SYMBOLS = {
@@ -109,6 +120,11 @@ SYMBOLS = {
     "pj_shard_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pj_shard_kernel_times": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "pj_junctions_finalize": (C.c_int, [_P, C.c_int64, C.c_double]),
+    "pj_coordinate_order": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P]),
+    "pjh_prep_options_default": (None, [C.POINTER(PjhPrepOptions)]),
+    "pjh_prep_run": (C.c_int, [C.POINTER(PjhPrepOptions), C.POINTER(PjhPrepReport)]),
+    "pjh_prep_last_error": (C.c_char_p, []),
+    "pjh_prep_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "pj_extra_num_spliced_names": (C.c_int64, [_P]),
     "pj_extra_export_names": (C.c_int, [_P, _P, C.c_int64]),
     "pj_extra_import_names": (C.c_int, [_P, _P, C.c_int64]),

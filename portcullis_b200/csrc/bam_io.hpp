@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <functional>
 
 namespace pjio {
 
@@ -120,6 +121,10 @@ uint64_t name_code(const char* qname, size_t len, uint16_t flag);
 // `junc --separate` (JunctionBuilder::separateBams, src/junction_builder.cc:152-226): every record of the BAM goes to one of
 // three files — spliced (any N op), unspliced (mapped, no N), unmapped — laid out block for block like htslib's BamWriter
 // output; the first two get a BAI (or CSI) index.  Inflate and deflate run on `threads` host threads.  bam_separate.cpp.
+// Every record of a BAM in file order: fn(pointer to the block_size field, 4 + block_size).  Blocks are inflated in groups on
+// `threads` threads; after_group() runs after each group (writers drain their finished blocks there).  bam_separate.cpp.
+void scan_records(const BamFile& bam, int threads, const std::function<void(const uint8_t*, size_t)>& fn, const std::function<void()>& after_group);
+
 struct SeparateCounts { uint64_t spliced = 0, unspliced = 0, unmapped = 0; };
 void separate_bams(const BamFile& bam, const std::string& spliced_path, const std::string& unspliced_path, const std::string& unmapped_path,
                    bool use_csi, int threads, SeparateCounts& counts);

@@ -110,6 +110,21 @@ __global__ void k_rebase_u64(uint64_t* __restrict__ a, int64_t n, uint64_t add) 
 __global__ void k_fill_i32(int32_t* __restrict__ a, int64_t n, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) a[i] = v;
 }
+// samtools' coordinate order (bam_sort.c bam1_lt, samtools 1.x): key = tid << 32 | (pos + 1) << 1 | reverse-strand; unplaced
+// reads (tid = -1) compare as the largest target.  Used by `prep` (csrc/prep_driver.cpp); the LSD radix sort is stable, so
+// records with equal keys keep their input order, like samtools' merge sort.
+__global__ void __launch_bounds__(256) k_coord_keys(int64_t n, const int32_t* __restrict__ tid, const int32_t* __restrict__ pos, const uint16_t* __restrict__ flag,
+                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lo = ((uint32_t)(pos[i] + 1) << 1) | ((flag[i] & 0x10u) ? 1u : 0u);
+    keys[i] = ((uint64_t)(uint32_t)tid[i] << 32) | lo;
+    vals[i] = (uint32_t)i;
+}
+void launch_coord_keys(int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag, uint64_t* keys, uint32_t* vals, cudaStream_t st) {
+    if (n > 0) k_coord_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, tid, pos, flag, keys, vals);
+}
+
 void launch_fill_i32(int32_t* a, int64_t n, int32_t v, cudaStream_t st) { if (n > 0) k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, v); }
 void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st) { if (n > 0 && add) k_rebase_u32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, add); }
 void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { if (n > 0 && add) k_rebase_u64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, add); }

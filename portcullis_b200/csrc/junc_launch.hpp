@@ -20,6 +20,7 @@ struct JuncAcc {
 
 void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* bsum_tmp, uint32_t* total_dev, cudaStream_t st);
 uint64_t scan_tmp_elems(uint64_t n);
+void launch_coord_keys(int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag, uint64_t* keys, uint32_t* vals, cudaStream_t st);
 void launch_fill_i32(int32_t* a, int64_t n, int32_t v, cudaStream_t st);
 void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st);
 void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st);

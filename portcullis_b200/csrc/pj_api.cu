@@ -181,6 +181,40 @@ void pj_destroy(pj_ctx* c) {
     delete c;
 }
 
+// Coordinate order of n records on a GPU (no context needed): order[k] = index of the record that comes k-th.
+int pj_coordinate_order(int32_t device, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag, uint32_t* order) {
+    if (n < 0 || (n && (!tid || !pos || !flag || !order))) return fail(nullptr, PJ_EINVAL, "pj_coordinate_order: bad arguments");
+    if (n >= (1ll << 30)) return fail(nullptr, PJ_EINVAL, "pj_coordinate_order: more than 2^30 records");
+    if (n == 0) return PJ_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, PJ_ECUDA, "pj_coordinate_order: no CUDA device available; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, PJ_EINVAL, "pj_coordinate_order: device %d out of range", device);
+    pj_ctx* c = nullptr;
+    CU(c, cudaSetDevice(device));
+    int n_sm = 148; CU(c, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t st; CU(c, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int32_t *d_tid = nullptr, *d_pos = nullptr; uint16_t* d_flag = nullptr; uint64_t *ka = nullptr, *kb = nullptr; uint32_t *va = nullptr, *vb = nullptr, *scratch = nullptr;
+    const size_t N = (size_t)n;
+    int rc = PJ_OK;
+    auto run = [&]() -> int {
+        CU(c, cudaMalloc(&d_tid, N * 4)); CU(c, cudaMalloc(&d_pos, N * 4)); CU(c, cudaMalloc(&d_flag, N * 2));
+        CU(c, cudaMalloc(&ka, N * 8)); CU(c, cudaMalloc(&kb, N * 8)); CU(c, cudaMalloc(&va, N * 4)); CU(c, cudaMalloc(&vb, N * 4));
+        CU(c, cudaMalloc(&scratch, os_scratch_words((uint32_t)n, 64) * sizeof(uint32_t)));
+        CU(c, cudaMemcpyAsync(d_tid, tid, N * 4, cudaMemcpyHostToDevice, st)); CU(c, cudaMemcpyAsync(d_pos, pos, N * 4, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemcpyAsync(d_flag, flag, N * 2, cudaMemcpyHostToDevice, st));
+        launch_coord_keys(n, d_tid, d_pos, d_flag, ka, va, st);
+        int launches = 0;
+        const int which = launch_onesweep_sort(ka, va, kb, vb, (uint32_t)n, 64, scratch, n_sm, st, &launches);
+        CU(c, cudaMemcpyAsync(order, which ? vb : va, N * 4, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
+        return PJ_OK;
+    };
+    rc = run();
+    for (void* p : {(void*)d_tid, (void*)d_pos, (void*)d_flag, (void*)ka, (void*)kb, (void*)va, (void*)vb, (void*)scratch}) cudaFree(p);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
 int pj_targets_set(pj_ctx* c, int32_t n_targets, const int32_t* target_len) {
     if (!c || n_targets <= 0 || !target_len) return fail(c, PJ_EINVAL, "pj_targets_set: bad arguments");
     if (c->n_targets) return fail(c, PJ_ESTATE, "pj_targets_set: targets already set");

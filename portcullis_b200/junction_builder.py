@@ -221,6 +221,51 @@ def finalize(rows, mean_query_length):
     return rows
 
 
+def coordinate_order(tid, pos, flag, device=0):
+    """samtools' coordinate order of records, computed on the GPU (pj_coordinate_order): order[k] = index of the k-th record."""
+    lib = L.load()
+    t = np.ascontiguousarray(tid, dtype=np.int32); p = np.ascontiguousarray(pos, dtype=np.int32); f = np.ascontiguousarray(flag, dtype=np.uint16)
+    order = np.zeros(len(t), dtype=np.uint32)
+    _check(lib.pj_coordinate_order(int(device), len(t), t.ctypes.data, p.ctypes.data, f.ctypes.data, order.ctypes.data), lib.pj_global_last_error)
+    return order
+
+
+class Prepare:
+    """Mirror of portcullis::Prepare (src/prepare.hpp:148-216): ``Prepare(output_dir).prepare(bam_files, genome_file)``."""
+
+    def __init__(self, output_dir="portcullis_prep"):
+        self.output_dir = output_dir
+        self.force = False
+        self.use_links = True
+        self.use_csi = False
+        self.threads = 1
+        self.verbose = False
+        self.device = 0
+        self.report = None
+
+    def setForce(self, b): self.force = bool(b)
+    def setUseLinks(self, b): self.use_links = bool(b)
+    def setUseCsi(self, b): self.use_csi = bool(b)
+    def setThreads(self, n): self.threads = int(n)
+    def setVerbose(self, b): self.verbose = bool(b)
+
+    def prepare(self, bam_files, genome_file):
+        lib = L.load()
+        o = L.PjhPrepOptions()
+        lib.pjh_prep_options_default(C.byref(o))
+        bams = [os.fsencode(b) for b in bam_files]
+        arr = (C.c_char_p * len(bams))(*bams)
+        keep = [os.fsencode(genome_file), os.fsencode(self.output_dir), arr]
+        o.genome_file, o.output_dir = keep[0], keep[1]
+        o.bam_files, o.n_bam_files = arr, len(bams)
+        o.force, o.copy, o.use_csi, o.threads = int(self.force), int(not self.use_links), int(self.use_csi), self.threads
+        o.verbose, o.quiet, o.device = int(self.verbose), 1, self.device
+        rep = L.PjhPrepReport()
+        _check(lib.pjh_prep_run(C.byref(o), C.byref(rep)), lib.pjh_prep_last_error)
+        self.report = {f: getattr(rep, f) for f, _ in L.PjhPrepReport._fields_}
+        return self.report
+
+
 def separate_bams(prep_dir, output_prefix, use_csi=False, threads=1):
     """`junc --separate` on its own (host only): writes <prefix>.spliced/.unspliced/.unmapped.bam and the two indices.
     Returns (n_spliced, n_unspliced, n_unmapped)."""
