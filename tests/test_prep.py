@@ -63,10 +63,7 @@ def write_inputs(ds, workdir, shuffle_seed=None, parts=1):
         with open(sam, "w") as f:
             f.write(text)
         bam = os.path.join(workdir, "in%d.bam" % k)
-        subprocess.check_call([ob.BAMTOOL, "sam2bam", sam, bam], stderr=subprocess.DEVNULL)
-        for ext in (".bai",):
-            if os.path.exists(bam + ext):
-                os.remove(bam + ext)      # sam2bam indexes; prep must cope without
+        subprocess.check_call([ob.BAMTOOL, "sam2bam", sam, bam, "noindex"], stderr=subprocess.DEVNULL)      # prep must cope without an index
         bams.append(bam)
     return fa, bams
 
