@@ -208,6 +208,10 @@ int pjh_prep_run(const pjh_prep_options* o, pjh_prep_report* rep) {
             if (rc) return pfail(rc, pj_global_last_error());
             R.t_sort_gpu_s = now_s() - tg;
             hdr.text = with_sorted_hd(hdr.text);
+            // an index linked / copied from the input describes the input's block offsets, not the file written here (the
+            // reference keeps it, prepare.cc:238-244, and ends up with a stale index): drop it, the writer makes a new one —
+            // and must not write THROUGH a symlink into the user's own index file
+            { std::error_code ec; fs::remove(index, ec); }
             pjio::BamOut out(sorted.string(), true, hdr, csi);
             for (int64_t k = 0; k < n; k++) {
                 const uint32_t i = order[(size_t)k];

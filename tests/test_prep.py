@@ -174,3 +174,24 @@ def test_prep_sort_and_merge_match_reference(tmp_path, parts, csi):
         b.process()
         outs.append(open(str(tmp_path / ("j_" + d) / "p.junctions.tab"), "rb").read())
     assert outs[0] == outs[1] and len(outs[0]) > 1000
+
+
+@pytest.mark.gpu
+def test_force_resort_does_not_touch_the_input_index(tmp_path):
+    """--force re-sorts an already sorted BAM (prepare.cc:211).  The input's .bai describes the INPUT's block offsets: the
+    prep directory must get its own index file, and nothing may be written through the symlink into the user's index."""
+    if not os.path.exists(ob.BAMTOOL):
+        pytest.skip("oracle/_ref not built")
+    ds = synth.make_dataset(57, n_targets=2, target_len=20000, genes_per_target=8, reads_per_gene=(20, 100))
+    fa, bams = write_inputs(ds, str(tmp_path / "in"))
+    subprocess.check_call([ob.BAMTOOL, "index", bams[0]])
+    before = open(bams[0] + ".bai", "rb").read()
+    p = jb.Prepare(str(tmp_path / "o")); p.setForce(True); p.setThreads(2)
+    rep = p.prepare(bams, fa)
+    assert rep["sorted_in_process"] == 1
+    assert open(bams[0] + ".bai", "rb").read() == before
+    idx = str(tmp_path / "o" / "portcullis.sorted.alignments.bam.bai")
+    assert os.path.exists(idx) and not os.path.islink(idx)
+    a = jb.PrepDir(str(tmp_path / "o")).decode(-1, 2)
+    b = synth.to_columns(ds)
+    assert len(a["pos"]) == len(b["pos"]) and np.array_equal(np.sort(a["pos"]), np.sort(b["pos"]))
