@@ -309,6 +309,19 @@ void pj_extra_finalize(pj_junction_extra* x, int64_t n);
  */
 int pj_coordinate_order(int32_t device, int64_t n, const int32_t* tid, const int32_t* pos, const uint16_t* flag, uint32_t* order);
 
+/* ---- junction-set membership for `bamfilt` (BamFilter, src/bam_filter.cc:75-245) ------------------- */
+
+typedef struct pj_jset pj_jset;
+/* A junction set resident on `device`: n introns sorted by (tid, start, end), coordinates as in junctions.tab columns
+ * refid / start / end (JunctionSystem::load + Intron key, junction_system.cc:424-444). */
+int  pj_jset_create(int32_t device, int64_t n, const int32_t* tid, const int32_t* start, const int32_t* end, pj_jset** out);
+void pj_jset_destroy(pj_jset* s);
+/* keep[i] = 1 when record i has no N op, or at least one of its N ops is in the set (containsJunctionInSystem,
+ * bam_filter.cc:75-99 — the condition all three clip modes reduce to, see csrc/pj_bamfilt.cu); n_nops[i] (optional) = its
+ * number of N ops, saturated at 255.  cigar_off has n_records + 1 entries starting at 0. */
+int  pj_jset_filter(pj_jset* s, int64_t n_records, const int32_t* tid, const int32_t* pos, const uint32_t* cigar_off,
+                    const uint32_t* cigar, uint8_t* keep, uint8_t* n_nops);
+
 /* ---- host finalize (A12/A13) --------------------------------------------------------------- */
 
 /*

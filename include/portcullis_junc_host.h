@@ -125,6 +125,23 @@ const char* pjh_prep_last_error(void);
 /* `portcullis prep ...` command line (argv[0] is the mode word).  Returns the process exit code. */
 int  pjh_prep_main(int argc, char** argv);
 
+/* ---- `bamfilt` (BamFilter::filter, src/bam_filter.cc:152-245) ----
+ * Keeps every unspliced alignment and every spliced alignment with at least one junction in junction_file (a junctions.tab);
+ * writes output_bam (+ .bai / .csi) and, with save_msrs, <output>.mod.bam / .unmod.bam.  The decision runs on `device`
+ * (pj_jset_filter); the files are laid out like htslib's writer lays them out. */
+enum { PJ_CLIP_HARD = 0, PJ_CLIP_SOFT = 1, PJ_CLIP_COMPLETE = 2 };
+typedef struct pjh_bamfilt_options {
+    const char* junction_file; const char* bam_file;
+    const char* output_bam;      /* -o, default "filtered.bam"                                      */
+    int32_t clip_mode;           /* PJ_CLIP_*: changes the Modified count only, like the reference  */
+    int32_t save_msrs, use_csi, threads, verbose, quiet, device;
+} pjh_bamfilt_options;
+typedef struct pjh_bamfilt_report { int64_t n_junctions; uint64_t n_in, n_out, n_modified; double t_device_s, t_total_s; } pjh_bamfilt_report;
+void pjh_bamfilt_options_default(pjh_bamfilt_options* o);
+int  pjh_bamfilt_run(const pjh_bamfilt_options* opt, pjh_bamfilt_report* report);
+const char* pjh_bamfilt_last_error(void);
+int  pjh_bamfilt_main(int argc, char** argv);
+
 /* ---- writers (A14) ---- */
 int pjh_write_outputs(const char* output_prefix, const pj_junction* rows, int64_t n_rows,
                       int32_t n_targets, const char* const* names, const int32_t* lens,

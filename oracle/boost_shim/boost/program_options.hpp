@@ -1,6 +1,7 @@
 // Test-infrastructure only: small stand-in for <boost/program_options.hpp>, just enough for the
 // reference's `prep` and `junc` command lines (oracle build, see oracle/README.md).
 #pragma once
+#include <boost/lexical_cast.hpp>   // real Boost.Program_options pulls it in; src/bam_filter.cc relies on that
 #include <string>
 #include <vector>
 #include <map>

@@ -99,6 +99,19 @@ class PjhPrepReport(C.Structure):
                 ("t_total_s", C.c_double)]
 
 
+class PjhBamfiltOptions(C.Structure):
+    _fields_ = [("junction_file", C.c_char_p), ("bam_file", C.c_char_p), ("output_bam", C.c_char_p), ("clip_mode", C.c_int32),
+                ("save_msrs", C.c_int32), ("use_csi", C.c_int32), ("threads", C.c_int32), ("verbose", C.c_int32), ("quiet", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class PjhBamfiltReport(C.Structure):
+    _fields_ = [("n_junctions", C.c_int64), ("n_in", C.c_uint64), ("n_out", C.c_uint64), ("n_modified", C.c_uint64),
+                ("t_device_s", C.c_double), ("t_total_s", C.c_double)]
+
+
+CLIP_MODE = {"HARD": 0, "SOFT": 1, "COMPLETE": 2}
+
 # every symbol declared in include/*.h, with (restype, argtypes); used by load() and by the export test
 _P = C.c_void_p
 SYMBOLS = {
@@ -120,6 +133,13 @@ SYMBOLS = {
     "pj_shard_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "pj_shard_kernel_times": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "pj_junctions_finalize": (C.c_int, [_P, C.c_int64, C.c_double]),
+    "pj_jset_create": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, C.POINTER(_P)]),
+    "pj_jset_destroy": (None, [_P]),
+    "pj_jset_filter": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "pjh_bamfilt_options_default": (None, [C.POINTER(PjhBamfiltOptions)]),
+    "pjh_bamfilt_run": (C.c_int, [C.POINTER(PjhBamfiltOptions), C.POINTER(PjhBamfiltReport)]),
+    "pjh_bamfilt_last_error": (C.c_char_p, []),
+    "pjh_bamfilt_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "pj_coordinate_order": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "pjh_prep_options_default": (None, [C.POINTER(PjhPrepOptions)]),
     "pjh_prep_run": (C.c_int, [C.POINTER(PjhPrepOptions), C.POINTER(PjhPrepReport)]),

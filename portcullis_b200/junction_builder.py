@@ -266,6 +266,68 @@ class Prepare:
         return self.report
 
 
+class BamFilter:
+    """Mirror of portcullis::BamFilter (src/bam_filter.hpp): ``BamFilter(junction_file, bam_file, output_bam).filter()``."""
+
+    def __init__(self, junction_file, bam_file, output_bam="filtered.bam"):
+        self.junction_file, self.bam_file, self.output_bam = junction_file, bam_file, output_bam
+        self.clip_mode = "HARD"
+        self.save_msrs = False
+        self.use_csi = False
+        self.threads = 1
+        self.device = 0
+        self.report = None
+
+    def setClipMode(self, m): self.clip_mode = m.upper()
+    def setSaveMSRs(self, b): self.save_msrs = bool(b)
+    def setUseCsi(self, b): self.use_csi = bool(b)
+    def setThreads(self, n): self.threads = int(n)
+
+    def filter(self):
+        lib = L.load()
+        o = L.PjhBamfiltOptions()
+        lib.pjh_bamfilt_options_default(C.byref(o))
+        keep = [os.fsencode(self.junction_file), os.fsencode(self.bam_file), os.fsencode(self.output_bam)]
+        o.junction_file, o.bam_file, o.output_bam = keep
+        o.clip_mode, o.save_msrs, o.use_csi = L.CLIP_MODE[self.clip_mode], int(self.save_msrs), int(self.use_csi)
+        o.threads, o.quiet, o.device = self.threads, 1, self.device
+        rep = L.PjhBamfiltReport()
+        _check(lib.pjh_bamfilt_run(C.byref(o), C.byref(rep)), lib.pjh_bamfilt_last_error)
+        self.report = {f: getattr(rep, f) for f, _ in L.PjhBamfiltReport._fields_}
+        return self.report
+
+
+class JunctionSet:
+    """A junction set on the GPU (pj_jset): ``keep, n_nops = JunctionSet(tid, start, end).filter(cols)``."""
+
+    def __init__(self, tid, start, end, device=0):
+        self._lib = L.load()
+        order = np.lexsort((end, start, tid))
+        t, s, e = (np.ascontiguousarray(np.asarray(a)[order], dtype=np.int32) for a in (tid, start, end))
+        self._s = C.c_void_p()
+        _check(self._lib.pj_jset_create(int(device), len(t), t.ctypes.data, s.ctypes.data, e.ctypes.data, C.byref(self._s)), self._lib.pj_global_last_error)
+
+    def filter(self, cols):
+        n = len(cols["pos"])
+        t = np.ascontiguousarray(cols["tid"], dtype=np.int32); p = np.ascontiguousarray(cols["pos"], dtype=np.int32)
+        co = np.ascontiguousarray(cols["cigar_off"], dtype=np.uint32); cg = np.ascontiguousarray(cols["cigar"], dtype=np.uint32)
+        keep = np.zeros(n, dtype=np.uint8); nn = np.zeros(n, dtype=np.uint8)
+        _check(self._lib.pj_jset_filter(self._s, n, t.ctypes.data, p.ctypes.data, co.ctypes.data, cg.ctypes.data if cg.size else None,
+                                        keep.ctypes.data, nn.ctypes.data), self._lib.pj_global_last_error)
+        return keep, nn
+
+    def close(self):
+        if self._s:
+            self._lib.pj_jset_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def separate_bams(prep_dir, output_prefix, use_csi=False, threads=1):
     """`junc --separate` on its own (host only): writes <prefix>.spliced/.unspliced/.unmapped.bam and the two indices.
     Returns (n_spliced, n_unspliced, n_unmapped)."""
