@@ -302,3 +302,23 @@ def deep_dataset(seed=21):
         add(0, 1520, "20S"); add(1, 2500, "12S")
     ds["records"].sort(key=lambda r: (r["tid"], r["pos"]))
     return ds
+
+
+def chr4_fasta(path, length=18585056, seed=12345):
+    """Config 1a of SURVEY.md §8(d) / Appendix B: the genome of the reference's bundled clipped3.bam (artha_chr4.fa) is not shipped,
+    so the survey pinned a synthetic one — numpy.random.default_rng(12345).integers(0, 4, L) -> ACGT, header >Chr4, 60 columns.
+    Writes the FASTA and its .fai (one sequence, so the index is a single line)."""
+    rng = np.random.default_rng(seed)
+    g = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, length)]
+    full = (length // 60) * 60
+    body = np.empty((full // 60, 61), dtype=np.uint8)
+    body[:, :60] = g[:full].reshape(-1, 60)
+    body[:, 60] = 10
+    with open(path, "wb") as f:
+        f.write(b">Chr4\n")
+        f.write(body.tobytes())
+        if length > full:
+            f.write(g[full:].tobytes() + b"\n")
+    with open(path + ".fai", "w") as f:
+        f.write("Chr4\t%d\t6\t60\t61\n" % length)
+    return path
