@@ -145,7 +145,7 @@ def _read_from_gene(rng, gseq_upper, gene, read_len, sub_rate, indel_rate, clip_
 def make_dataset(seed, n_targets=2, target_len=20000, genes_per_target=12, reads_per_gene=(5, 120), read_len=(60, 150),
                  long_reads=False, sub_rate=0.01, indel_rate=0.15, clip_rate=0.1, retain_rate=0.15, unspliced_frac=0.2,
                  paired=True, secondary_frac=0.05, lowq_frac=0.15, xs_frac=0.8, hot=None,
-                 multimap_frac=0.0, unspliced_indel=0.0, deep=(), no_background=()):
+                 multimap_frac=0.0, unspliced_indel=0.0, deep=(), no_background=(), base_genomes=None):
     """Returns dict(names, lengths, genomes (list[bytes], original case), records (sorted list of dicts)).
 
     Options for the `--extra` metrics (all off by default, so the seeds of older data sets keep their records):
@@ -155,13 +155,18 @@ def make_dataset(seed, n_targets=2, target_len=20000, genes_per_target=12, reads
     read."""
     rng = np.random.default_rng(seed)
     genomes = make_genome(rng, n_targets, target_len)
+    if base_genomes is not None:          # real sequences (e.g. soft-masked, with n runs): genes are planted into a copy
+        genomes = [np.frombuffer(bytes(b), dtype=np.uint8).copy() for b in base_genomes]
+        n_targets = len(genomes)
     names = ["chr%s" % (t + 1) for t in range(n_targets)]
     records = []
     rid = 0
     for t in range(n_targets):
         g = genomes[t]
         genes = plant_genes(rng, g, genes_per_target, max_exons=(20 if long_reads else 8))
-        decorate_genome(rng, g)
+        if base_genomes is None:
+            decorate_genome(rng, g)
+        target_len = len(g)
         gu = bytes(np.where((g >= 97) & (g <= 122), g - 32, g).astype(np.uint8)).decode()
         for gi, gene in enumerate(genes):
             nr = int(rng.integers(reads_per_gene[0], reads_per_gene[1]))
@@ -230,7 +235,7 @@ def make_dataset(seed, n_targets=2, target_len=20000, genes_per_target=12, reads
         records.append(dict(name="x%06d" % rid, tid=t, pos=int(rng.integers(0, target_len - 50)), flag=4, mapq=0, cigar="", seq="ACGTACGTAC", xs=0, mtid=-1, mpos=-1))
         rid += 1
     records.sort(key=lambda r: (r["tid"], r["pos"]))
-    return dict(names=names, lengths=np.array([target_len] * n_targets, dtype=np.int32),
+    return dict(names=names, lengths=np.array([len(g) for g in genomes], dtype=np.int32),
                 genomes=[bytes(g) for g in genomes], records=records)
 
 
