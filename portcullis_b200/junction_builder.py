@@ -119,9 +119,16 @@ class JuncGpu:
         _check(self._lib.pj_shard_run(self._ctx), self._err)
         return self._lib.pj_shard_num_junctions(self._ctx)
 
-    def fetch(self):
+    def fetch(self, out=None):
+        """Rows + per-target stats of the last run.  out: optional preallocated JUNCTION_DTYPE array (e.g. a view of pinned
+        host memory) with room for the rows; a slice of it is returned instead of a fresh pageable array."""
         n = self._lib.pj_shard_num_junctions(self._ctx)
-        rows = np.zeros(max(n, 0), dtype=L.JUNCTION_DTYPE)
+        if out is not None:
+            if out.dtype != L.JUNCTION_DTYPE or len(out) < n or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("fetch(out=...): need a contiguous JUNCTION_DTYPE array with at least %d rows" % n)
+            rows = out[:max(n, 0)]
+        else:
+            rows = np.zeros(max(n, 0), dtype=L.JUNCTION_DTYPE)
         stats = (L.PjTargetStats * self.n_targets)()
         _check(self._lib.pj_shard_fetch(self._ctx, rows.ctypes.data, len(rows), C.addressof(stats), self.n_targets), self._err)
         st = np.array([(s.spliced_count, s.unspliced_count, s.sum_query_lengths, s.min_query_length, s.max_query_length)
