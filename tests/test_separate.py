@@ -105,3 +105,45 @@ def test_separate_live_against_reference(tmp_path, csi):
             q = [subprocess.run([ob.BAMTOOL, "query", bam, ix] + regions, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
                  for ix in (bam + ext, "%s.%s.bam%s" % (ref, kind, ext))]
             assert q[0] == q[1] and sum(int(l.split(b"\t")[1]) for l in q[0].splitlines()) > 1000
+
+
+@pytest.mark.skipif(not os.path.exists(ob.BAMTOOL), reason="oracle/_ref not built")
+def test_csi_on_a_target_longer_than_512_mbp(tmp_path):
+    """A 700 Mbp target needs CSI depth 6 (BAI cannot index it): our CSI against htslib-1.3's, through htslib's iterator,
+    with records on both sides of the 2^29 boundary; the separated files decode through our own CSI reader."""
+    L700 = 700_000_000
+    sam = ["@HD\tVN:1.0\tSO:coordinate", "@SQ\tSN:big\tLN:%d" % L700, "@SQ\tSN:small\tLN:5000"]
+    rng = random.Random(4)
+    pos = sorted(rng.randrange(1, L700 - 400) for _ in range(3000)) + []
+    pos += []
+    for k, p in enumerate(sorted(pos + [2 ** 29 - 60, 2 ** 29 - 1, 2 ** 29, 2 ** 29 + 5, 536_900_000])):
+        cigar = "50M" if k % 3 else "20M%dN30M" % (100 + k % 200)
+        sam.append("r%d\t0\tbig\t%d\t60\t%s\t*\t0\t0\t%s\t*" % (k, p + 1, cigar, "A" * 50))
+    for k in range(20):
+        sam.append("s%d\t0\tsmall\t%d\t60\t50M\t*\t0\t0\t%s\t*" % (k, 100 + 10 * k, "C" * 50))
+    d = tmp_path / "prep"; d.mkdir()
+    (tmp_path / "in.sam").write_text("\n".join(sam) + "\n")
+    bam = str(d / "portcullis.sorted.alignments.bam")
+    subprocess.check_call([ob.BAMTOOL, "sam2bam", str(tmp_path / "in.sam"), bam, "noindex"], stderr=subprocess.DEVNULL)
+    subprocess.check_call([ob.BAMTOOL, "index_csi", bam])
+    (d / "portcullis.genome.fa").write_text(">big\nA\n>small\nA\n"); (d / "portcullis.genome.fa.fai").write_text("big\t1\t5\t1\t2\nsmall\t1\t14\t1\t2\n")
+    pre = str(tmp_path / "o" / "p")
+    counts = jb.separate_bams(str(d), pre, use_csi=True, threads=2)
+    assert counts[0] > 900 and counts[1] > 1900
+    regions = ["0:%d-%d" % (b, b + w) for b, w in [(2 ** 29 - 100, 200), (2 ** 29, 1), (0, L700), (536_899_990, 100), (123_456_789, 5_000_000)]] + ["1:0-5000", "1:150-160"]
+    regions += ["0:%d-%d" % (b, b + rng.choice([1, 500, 100000, 50_000_000])) for b in (rng.randrange(L700) for _ in range(80))]
+    for kind in ("spliced", "unspliced"):
+        f = "%s.%s.bam" % (pre, kind)
+        ref_copy = str(tmp_path / (kind + ".bam"))
+        os.symlink(f, ref_copy)
+        subprocess.check_call([ob.BAMTOOL, "index_csi", ref_copy])
+        q = [subprocess.run([ob.BAMTOOL, "query", f, ix] + regions, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+             for ix in (f + ".csi", ref_copy + ".csi")]
+        assert q[0] == q[1] and sum(int(l.split(b"\t")[1]) for l in q[0].splitlines()) > 100
+    # our reader through our CSI: the unspliced file as a prep directory
+    d2 = tmp_path / "prep2"; d2.mkdir()
+    for src, dst in ((pre + ".unspliced.bam", "portcullis.sorted.alignments.bam"), (pre + ".unspliced.bam.csi", "portcullis.sorted.alignments.bam.csi"),
+                     (str(d / "portcullis.genome.fa"), "portcullis.genome.fa"), (str(d / "portcullis.genome.fa.fai"), "portcullis.genome.fa.fai")):
+        os.symlink(src, str(d2 / dst))
+    cols = jb.PrepDir(str(d2), use_csi=True).decode(-1, 2)
+    assert len(cols["pos"]) == counts[1] and int(cols["pos"].max()) > 2 ** 29
