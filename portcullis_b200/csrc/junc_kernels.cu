@@ -692,7 +692,10 @@ void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint
 // flag kernel + three scan kernels + consumer kernel.
 // ================================================================================================
 constexpr int FS_THREADS = 512;
-constexpr int FS_ITEMS = 4;
+#ifndef PJ_FS_ITEMS
+#define PJ_FS_ITEMS 4
+#endif
+constexpr int FS_ITEMS = PJ_FS_ITEMS;
 constexpr int FS_TILE = FS_THREADS * FS_ITEMS;
 
 template <typename F>

@@ -47,6 +47,9 @@ WANT = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram read"
         ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("inst_executed", "warp inst")]
 
 
+PEAK_GBS = 6540          # MEASURED_PEAKS.json hbm_gbs on this pool's B200s
+
+
 def to_bytes(v, unit):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
@@ -63,13 +66,21 @@ def kernels(src, dst, traffic_json=None):
     traffic = {}
     with open(dst, "w") as f:
         f.write("# ncu `--set full --clock-control none` summary\n\nSource: `%s` (kept out of git; regenerate with the command in DESIGN.md).\n\n" % src)
-        f.write("| kernel | " + " | ".join(n for _, n in WANT) + " |\n|---|" + "---:|" * len(WANT) + "\n")
+        f.write("Last column: DRAM bytes moved / kernel time, and its share of the measured HBM peak (MEASURED_PEAKS.json hbm_gbs).\n\n")
+        f.write("| kernel | " + " | ".join(n for _, n in WANT) + " | achieved DRAM |\n|---|" + "---:|" * (len(WANT) + 1) + "\n")
         for k, rs in seen.items():
             r = rs[-1]
             cells = []
             for m, _ in WANT:
                 cells.append(("%s %s" % (r[col[m]], units[col[m]])).strip() if m in col else "-")
-            f.write("| `%s` | " % k + " | ".join(cells) + " |\n")
+            gbs = ""
+            if "dram__bytes_read.sum" in col and "gpu__time_duration.sum" in col:
+                tot = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+                tu = units[col["gpu__time_duration.sum"]]
+                secs = float(r[col["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-9, "nsecond": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3}.get(tu, 1.0)
+                if secs > 0:
+                    gbs = "%.0f GB/s (%.0f%% of %d)" % (tot / secs / 1e9, 100 * tot / secs / 1e9 / PEAK_GBS, PEAK_GBS)
+            f.write("| `%s` | " % k + " | ".join(cells) + " | " + gbs + " |\n")
             if "dram__bytes_read.sum" in col:
                 t = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
                     to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
