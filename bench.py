@@ -318,15 +318,22 @@ def extra_leg(p, device, genomes, cores, steps):
 
 
 def e2e_bam(prep, cores, n_spliced):
-    """Whole front end from the BAM file: BGZF decode + genome load + GPU + finalize + writers (one run)."""
+    """Whole front end from the BAM file: BGZF decode + genome load + GPU + finalize + writers, each run with a fresh library
+    context.  One untimed run first (page cache, allocator pools), then three timed ones; the median is reported."""
     from portcullis_b200 import junction_builder as jb
     out = os.path.join(WORKDIR, "out_e2e", "p")
-    b = jb.JunctionBuilder(prep, out)
-    b.setThreads(cores)
-    t0 = time.perf_counter()
-    rep = b.process()
-    dt = time.perf_counter() - t0
-    return {"value": n_spliced / dt, "unit": UNIT, "seconds": round(dt, 3), "host_threads": cores,
+    runs = []
+    for it in range(4):
+        b = jb.JunctionBuilder(prep, out)
+        b.setThreads(cores)
+        t0 = time.perf_counter()
+        rep = b.process()
+        dt = time.perf_counter() - t0
+        if it:
+            runs.append((dt, rep))
+    runs.sort(key=lambda r: r[0])
+    dt, rep = runs[len(runs) // 2]
+    return {"value": n_spliced / dt, "unit": UNIT, "seconds": round(dt, 3), "seconds_all": [round(r[0], 3) for r in runs], "host_threads": cores,
             "breakdown_s": {k: round(rep[k], 4) for k in ("t_open_s", "t_genome_s", "t_decode_s", "t_finalize_s", "t_write_s")},
             "gpu_pipeline_ms": round(rep["t_gpu_ms"], 3)}
 
