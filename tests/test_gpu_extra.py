@@ -216,3 +216,26 @@ def test_extra_call_sequence_and_rejections():
         assert e.value.code == L.PJ_EDATA
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("fixture", ["extra_mm", "clipped3"])
+def test_cli_with_every_junc_flag(tmp_path, fixture):
+    """`portcullis junc --separate --extra --exon_gff --intron_gff -t 3 --gpus 1` as a process: tab == the reference's --extra tab,
+    gff / bed == the plain ones, the three BAMs == the reference's (md5), exit code 0 and the reference's closing line."""
+    import hashlib
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "portcullis_b200", "bin", "portcullis")
+    out = str(tmp_path / "o" / "p")
+    p = subprocess.run([exe, "junc", "--separate", "--extra", "--exon_gff", "--intron_gff", "-t", "3", "--gpus", "1", "-o", out, make_prep(tmp_path, fixture)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-500:]
+    assert "Portcullis junc completed." in p.stdout and "Splitting BAM:" in p.stdout and "Calculating extra junction metrics:" in p.stdout
+    g = os.path.join(GOLDEN, fixture)
+    assert_tab_equal(out + ".junctions.tab", os.path.join(g, "ref_extra.junctions.tab"))
+    for ext in ("bed", "intron.gff3"):
+        assert open(out + ".junctions." + ext, "rb").read() == open(os.path.join(g, "ref.junctions." + ext), "rb").read(), ext
+    want = {l.split("\t")[0]: l.split("\t")[1] for l in open(os.path.join(g, "ref_separate.md5"))}
+    for kind in ("spliced", "unspliced", "unmapped"):
+        assert hashlib.md5(open("%s.%s.bam" % (out, kind), "rb").read()).hexdigest() == want[kind], kind
+    assert os.path.exists(out + ".spliced.bam.bai") and os.path.exists(out + ".unspliced.bam.bai")
