@@ -24,6 +24,7 @@ namespace pjk {
 // ================================================================================================
 // generic exclusive scan (uint32), three phases; tile = 512 threads x 8 items
 // ================================================================================================
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -334,29 +335,31 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
         const unsigned long long slot0 = tile_base + off[r];
         if (slot0 + nN > (unsigned long long)pair_cap) { e |= ERR_KEY_OVERFLOW; continue; }
         uint32_t slot = (uint32_t)slot0;
-        const int32_t tid = R.tid[i], pos = R.pos[i], refLen = tlen[tid];
+        // every column of the record first: independent loads, one round trip instead of one per use
+        const int32_t tid = R.tid[i], pos = R.pos[i];
         const uint32_t flag = R.flag[i];
-        const uint32_t* cg = R.cigar + R.cigar_off[i];
-        const int32_t n = (int32_t)(R.cigar_off[i + 1] - R.cigar_off[i]);
-        const uint8_t xs = R.xs[i];
+        const uint32_t cig0 = R.cigar_off[i], cig1 = R.cigar_off[i + 1];
+        const uint8_t xs = R.xs[i], mq = R.mapq[i];
+        const int32_t mtid = R.mtid[i], mpos = R.mpos[i], lq = R.l_qseq[i];
+        const uint64_t so = R.seq_off[i], so1 = R.seq_off[i + 1];
+        const int32_t refLen = tlen[tid];
+        const uint64_t tbase = toff[tid];
+        const uint32_t* cg = R.cigar + cig0;
+        const int32_t n = (int32_t)(cig1 - cig0);
+        const uint32_t wf = __ldg(cg), wl = __ldg(cg + n - 1);
         uint32_t bits = 0;
         if (flag & 0x40u) bits |= PB_R1;
         if (flag & 0x10u) bits |= PB_REV;
         if (nN > 1) bits |= PB_MS;
-        if (R.mapq[i] >= PJ_MAP_QUALITY_THRESHOLD) bits |= PB_UM;
+        if (mq >= PJ_MAP_QUALITY_THRESHOLD) bits |= PB_UM;
         if (flag & 0x2u) bits |= PB_BPP;
-        if (portcullis_proper_pair(flag, tid, R.mtid[i], pos, R.mpos[i], orientation)) bits |= PB_PPP;
+        if (portcullis_proper_pair(flag, tid, mtid, pos, mpos, orientation)) bits |= PB_PPP;
         if (xs == '+') bits |= PB_XSP; else if (xs == '-') bits |= PB_XSN;
-        const uint64_t tbase = toff[tid];
         // getQuerySeqAfterClipping (bam_alignment.cc:256-264), quirk Q3: only a FIRST / LAST op of type S clips
-        const int32_t lq = R.l_qseq[i];
-        const uint32_t wf = __ldg(cg), wl = __ldg(cg + n - 1);
         int32_t ds = cig_op(wf) == OP_S ? cig_len(wf) : 0; const int32_t de = cig_op(wl) == OP_S ? cig_len(wl) : 0;
         if (ds > lq) ds = lq;
         int64_t qs = (int64_t)lq - ds - de + 1; if (qs > lq - ds) qs = lq - ds; if (qs < 0) qs = 0;
-        const uint64_t so = R.seq_off[i];
-        if (lq > 1 && (int64_t)(R.seq_off[i + 1] - so) < (int64_t)((lq + 1) >> 1)) e |= ERR_SEQ_MISSING;
-        const uint32_t cig0 = R.cigar_off[i];
+        if (lq > 1 && (int64_t)(so1 - so) < (int64_t)((lq + 1) >> 1)) e |= ERR_SEQ_MISSING;
         int32_t lStart = pos, lEndExc = pos;
         int32_t p = pos, qpos = 0;            // plain reference / query position at the start of op c (calcAlignmentStats / getPadded* walks)
         uint32_t kN = 0, a_eq = 0;            // N ops seen so far; how many of them end exactly at p
@@ -974,7 +977,6 @@ constexpr uint64_t NIB1 = 0x1111111111111111ull;
 
 // 16 consecutive nibbles of a BAM-ordered nibble stream (even index = high nibble of its byte), starting at nibble index
 // `nib` of `base`, returned MSB-first: nibble t sits at bits [60-4t, 64-4t).  Two aligned 64-bit loads cover any alignment.
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint64_t bswap64(uint64_t v) {
     const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
     return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
