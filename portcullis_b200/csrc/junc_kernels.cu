@@ -255,7 +255,18 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
             const uint32_t flag = R.flag[i];
             lq = R.l_qseq[i];
             int64_t rlen = 0;
-            for (uint32_t c = c0; c < c1; c++) {
+            // the first four ops with independent loads (one round trip covers most short-read CIGARs; a zero word is a
+            // neutral 0M), the rest one by one
+            uint32_t w4[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w4[k] = (c0 + k < c1) ? __ldg(R.cigar + c0 + k) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = w4[k], op = cig_op(w);
+                if (op_ref(op)) rlen += cig_len(w);
+                if (op == OP_N) { nN++; if (cig_len(w) == 0) zeron[r] = true; }
+            }
+            for (uint32_t c = c0 + 4; c < c1; c++) {
                 const uint32_t w = __ldg(R.cigar + c), op = cig_op(w);
                 if (op_ref(op)) rlen += cig_len(w);
                 if (op == OP_N) { nN++; if (cig_len(w) == 0) zeron[r] = true; }
