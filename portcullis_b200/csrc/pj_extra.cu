@@ -308,6 +308,110 @@ __global__ void __launch_bounds__(32) k_x_cap(int32_t T, const uint32_t* __restr
     }
 }
 
+// Region starts among the hot reads: a hot read opens a new region when no earlier hot read of its target can still be alive
+// at its position (the sequential walk of k_x_cap stops at `P > lastHot + span` for the same reason).
+__global__ void __launch_bounds__(256) k_x_region_flag(uint32_t nH, const uint32_t* __restrict__ H, const int32_t* __restrict__ u_tid, const int32_t* __restrict__ u_pos,
+                                                        const int32_t* __restrict__ maxspan_t, uint32_t* __restrict__ flag) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nH) return;
+    bool st = h == 0;
+    if (!st) {
+        const uint32_t a = H[h - 1], b = H[h];
+        st = u_tid[a] != u_tid[b] || (int64_t)u_pos[b] > (int64_t)u_pos[a] + maxspan_t[u_tid[b]];
+    }
+    flag[h] = st ? 1u : 0u;
+}
+
+// k_x_cap with the state in shared memory: one warp per REGION (regions are independent), end counts in a ring indexed by
+// position (valid while span + 2 <= XR_RING), the next XR_STAGE reads' positions and spans staged by coalesced loads.  Same
+// arithmetic as k_x_cap, which remains the path for targets whose reads span more than the ring.
+constexpr int XR_RING = 4096;
+constexpr int XR_STAGE = 1024;
+__global__ void __launch_bounds__(32) k_x_cap_ring(uint32_t nR, const uint32_t* __restrict__ RS, const uint32_t* __restrict__ H, uint32_t nH,
+                                                    const int32_t* __restrict__ u_tid, const uint32_t* __restrict__ u_toff, const int32_t* __restrict__ u_pos,
+                                                    const int32_t* __restrict__ u_alen, const int32_t* __restrict__ maxspan_t, uint8_t* __restrict__ accepted) {
+    __shared__ uint32_t ring[XR_RING];
+    __shared__ int32_t spos[XR_STAGE], salen[XR_STAGE];
+    const uint32_t r = blockIdx.x; const int lane = threadIdx.x;
+    if (r >= nR) return;
+    constexpr uint32_t M = XR_RING - 1;
+    uint32_t h = RS[r]; const uint32_t hEnd = r + 1 < nR ? RS[r + 1] : nH;
+    const uint32_t start = H[h];
+    const int32_t t = u_tid[start];
+    const uint32_t lo = u_toff[t], hi = u_toff[t + 1];
+    const int64_t span = maxspan_t[t];
+    const int64_t P0 = u_pos[start];
+    for (int k = lane; k < XR_RING; k += 32) ring[k] = 0;
+    __syncwarp();
+    int64_t live = 0;
+    {   // every earlier read still alive at P0 is accepted (no hot column within reach)
+        const uint32_t a0 = x_lower(u_pos, lo, start, P0 - span);
+        uint32_t c = 0;
+        for (uint32_t j = a0 + lane; j < start; j += 32) {
+            const int64_t E = (int64_t)u_pos[j] + u_alen[j];
+            if (E >= P0) { c++; atomicAdd(&ring[(uint32_t)E & M], 1u); }
+        }
+        live = __reduce_add_sync(0xffffffffu, c);
+    }
+    __syncwarp();
+    uint32_t sbase = start, sn = 0;
+    auto stage = [&](uint32_t from) {
+        sbase = from; sn = min((uint32_t)XR_STAGE, hi - from);
+        for (uint32_t k = lane; k < sn; k += 32) { spos[k] = u_pos[from + k]; salen[k] = u_alen[from + k]; }
+        __syncwarp();
+    };
+    auto pos_of = [&](uint32_t j) -> int32_t { const uint32_t k = j - sbase; return k < sn ? spos[k] : u_pos[j]; };
+    auto alen_of = [&](uint32_t j) -> int32_t { const uint32_t k = j - sbase; return k < sn ? salen[k] : u_alen[j]; };
+    stage(start);
+    uint32_t i = start; int64_t prevP = P0, lastHot = P0;
+    while (i < hi) {
+        if (i - sbase >= (uint32_t)(XR_STAGE / 2) && sbase + sn < hi) stage(i);
+        const int64_t P = pos_of(i);
+        if (P > lastHot + span) break;
+        if (P > prevP) {                                   // nodes whose end has been passed are freed (end <= P - 1); their slots recycle
+            uint32_t s2 = 0;
+            for (int64_t e = prevP + lane; e < P; e += 32) { s2 += ring[(uint32_t)e & M]; ring[(uint32_t)e & M] = 0; }
+            live -= __reduce_add_sync(0xffffffffu, s2);
+            __syncwarp();
+        }
+        uint32_t n = 0;                                    // reads on this column
+        for (;;) {
+            const uint32_t j = i + n + lane;
+            const unsigned same = __ballot_sync(0xffffffffu, j < hi && pos_of(j) == P);
+            if (same == 0xffffffffu) { n += 32; continue; }
+            n += __ffs(~same) - 1; break;
+        }
+        const bool is_hot = h < hEnd && H[h] == i;
+        uint32_t keep = n;
+        if (is_hot) { const int64_t room = (int64_t)(PLP_MAXCNT - 1) - live; keep = (uint32_t)(room < 1 ? 1 : room > (int64_t)n ? (int64_t)n : room); h += n; }
+        bool zero_len = false;
+        if (is_hot) { for (uint32_t k = lane; k < n; k += 32) zero_len |= alen_of(i + k) == 0; zero_len = __any_sync(0xffffffffu, zero_len); }
+        if (is_hot && zero_len) {                          // a read without reference span gets no node unless it opens the column: replay one by one
+            if (lane == 0) {
+                int64_t lv = live;
+                for (uint32_t k = 0; k < n; k++) {
+                    const int64_t E = P + alen_of(i + k);
+                    const bool ok = k == 0 || 2 + lv <= PLP_MAXCNT;
+                    accepted[i + k] = ok ? 1 : 0;
+                    if (ok && (k == 0 ? E >= P : E > P)) { ring[(uint32_t)E & M] += 1; lv++; }
+                }
+                live = lv;
+            }
+            live = __shfl_sync(0xffffffffu, live, 0);
+        } else {
+            uint32_t c = 0;
+            for (uint32_t k = lane; k < n; k += 32) {
+                if (k >= keep) { accepted[i + k] = 0; continue; }
+                const int64_t E = P + alen_of(i + k);
+                if (k == 0 ? E >= P : E > P) { c++; atomicAdd(&ring[(uint32_t)E & M], 1u); }
+            }
+            live += __reduce_add_sync(0xffffffffu, c);
+        }
+        __syncwarp();
+        i += n; prevP = P; if (is_hot) lastHot = P;
+    }
+}
+
 // out[t] = max of target t's slice of v; blockIdx.y walks the targets [t0, t0 + gridDim.y).  16-byte loads once the slice
 // is aligned (slices start at arbitrary word offsets), several of them in flight per thread.
 __global__ void __launch_bounds__(256) k_x_max(const uint32_t* __restrict__ v, const uint64_t* __restrict__ doff, int32_t t0, uint32_t* __restrict__ out) {
@@ -528,7 +632,26 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
     if (nH) {
         CU(c, cudaMallocAsync(&H, (size_t)nH * 4, st)); CU(c, cudaMallocAsync(&accepted, (size_t)U, st)); CU(c, cudaMemsetAsync(accepted, 1, (size_t)U, st));
         k_x_compact<<<blocks_for(U, 256), 256, 0, st>>>(U, hot, hoff, H);
-        k_x_cap<<<(uint32_t)T, 32, 0, st>>>(T, u_toff, u_pos, u_alen, maxspan, c->d_tlen, d_doff, H, nH, c->x_depth, accepted);
+        // regions are independent: one warp each with its state in shared memory when every capped target's longest read span fits
+        // the ring, else the general kernel (one warp per target, counters in the zeroed depth buffer)
+        std::vector<int32_t> h_span((size_t)T);
+        CU(c, cudaMemcpyAsync(h_span.data(), maxspan, (size_t)T * 4, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+        bool fits = true; for (int32_t t = 0; t < T; t++) if (c->x_maxlive[t] >= (uint32_t)PLP_MAXCNT && (int64_t)h_span[t] + 2 > XR_RING) fits = false;
+        if (getenv("PJ_CAP_GENERAL")) fits = false;            // tests: force the general kernel
+        if (fits) {
+            uint32_t *rflag = nullptr, *roff = nullptr, *RS = nullptr; uint32_t nR = 0;
+            CU(c, cudaMallocAsync(&rflag, (size_t)nH * 4, st)); CU(c, cudaMallocAsync(&roff, (size_t)nH * 4, st));
+            k_x_region_flag<<<blocks_for(nH, 256), 256, 0, st>>>(nH, H, u_tid, u_pos, maxspan, rflag);
+            launch_exclusive_scan(rflag, roff, nH, dscan_tmp, c->d_scalars + 11, st);
+            CU(c, cudaMemcpyAsync(&nR, c->d_scalars + 11, 4, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
+            CU(c, cudaMallocAsync(&RS, (size_t)std::max<uint32_t>(nR, 1) * 4, st));
+            k_x_compact<<<blocks_for(nH, 256), 256, 0, st>>>(nH, rflag, roff, RS);
+            if (nR) k_x_cap_ring<<<nR, 32, 0, st>>>(nR, RS, H, nH, u_tid, u_toff, u_pos, u_alen, maxspan, accepted);
+            CU(c, cudaFreeAsync(rflag, st)); CU(c, cudaFreeAsync(roff, st)); CU(c, cudaFreeAsync(RS, st));
+            launches += 6;
+        } else {
+            k_x_cap<<<(uint32_t)T, 32, 0, st>>>(T, u_toff, u_pos, u_alen, maxspan, c->d_tlen, d_doff, H, nH, c->x_depth, accepted);
+        }
     }
     if (nH) { launches += 6; marks.mark("x_cap"); }
     if (U) k_x_depth<<<blocks_for(U, 256), 256, 0, st>>>(U, u_tid, u_pos, u_rid, c->cigar_off.p, c->cigar.p, accepted, c->d_tlen, d_doff, c->x_depth);

@@ -152,10 +152,13 @@ def test_two_contexts_exchange_names_and_depth():
     assert (ex["mm_m"] > ex["mm_n"]).any()
 
 
-def test_pileup_cap_is_replayed():
+@pytest.mark.parametrize("general", [False, True])
+def test_pileup_cap_is_replayed(general, monkeypatch):
     """> 8000 reads on one column: htslib's pileup stops accepting reads there (sam.c:1906).  The oracle models it (and is
     pinned against the reference on the same data in test_oracle_extra); the library replays it on the GPU (k_x_cap), so
     even the coverage column stays bit-equal."""
+    if general:
+        monkeypatch.setenv("PJ_CAP_GENERAL", "1")      # the one-warp-per-target kernel with global counters (reads longer than the ring)
     ds = synth.deep_dataset()
     cols = synth.to_columns(ds)
     erows, _, ex, capped, maxq = oracle_extra(cols, ds["lengths"], ds["genomes"])
