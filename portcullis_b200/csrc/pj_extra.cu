@@ -174,9 +174,14 @@ __global__ void __launch_bounds__(256) k_x_live(uint32_t U, const int32_t* __res
     const int32_t t = u_tid[i]; const int64_t L = tlen[t]; const int64_t p = u_pos[i];
     if (p < 0 || p >= L) return;
     uint32_t* d = diff + doff[t];
-    atomicAdd(d + p, 1u);
     int64_t e = p + (int64_t)u_alen[i] + 1; if (e > L) e = L;
-    atomicAdd(d + e, 0xffffffffu);
+    // reads are in position order: the lanes of a warp mostly share their start (and, on a pile-up, their end) — one atomic per
+    // distinct address instead of one per read
+    const unsigned act = __activemask();
+    const unsigned ps = __match_any_sync(act, (unsigned long long)(uintptr_t)(d + p));
+    if ((int)(threadIdx.x & 31) == __ffs(ps) - 1) atomicAdd(d + p, (uint32_t)__popc(ps));
+    const unsigned es = __match_any_sync(act, (unsigned long long)(uintptr_t)(d + e));
+    if ((int)(threadIdx.x & 31) == __ffs(es) - 1) atomicAdd(d + e, 0u - (uint32_t)__popc(es));
 }
 
 // depth vector of DepthParser (depth_parser.cc:121-156): reads count on M/=/X columns only (is_del / is_refskip are
