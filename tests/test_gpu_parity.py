@@ -166,3 +166,29 @@ def test_both_sort_implementations_agree():
     b, _, _ = gpu_run(cols, ds["lengths"], ds["genomes"], legacy_sort=1)
     assert a.tobytes() == b.tobytes()
     check_against_oracle(cols, ds["lengths"], ds["genomes"], legacy_sort=1)
+
+
+@pytest.mark.skipif(not os.path.exists(ob.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("fixture,strandedness", [("kat", None), ("clipped3", "firststrand"), ("short_pe", "secondstrand"), ("long_se", None), ("indel_rich", "unstranded")])
+def test_strand_analysis_report_matches_reference(tmp_path, fixture, strandedness):
+    """A15: JunctionSystem::determineStrandedness(true) (junction_system.cc:455-560) is a stdout report — totals, the four
+    correlation ratios (printed `-nan` when a class is empty), the two 'Determined ...' lines — plus a warning on stderr when
+    --strandedness disagrees.  Our CLI prints the same block as the reference binary."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prep = make_prep(tmp_path, fixture)
+    extra = ["--strandedness", strandedness] if strandedness else []
+
+    def block(cmd):
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0, p.stderr[-400:]
+        lines = p.stdout.split("\n")
+        a = lines.index("Strand Analysis")
+        b = max(i for i, l in enumerate(lines) if l.startswith("Determined RNAseq strandedness"))
+        warn = [l for l in p.stderr.split("\n") if l.startswith("Warning!")]
+        return lines[a:b + 1], warn
+
+    ours = block([os.path.join(root, "portcullis_b200", "bin", "portcullis"), "junc", "-t", "2", "-o", str(tmp_path / "o" / "p")] + extra + [prep])
+    ref = block([ob.REF_BIN, "junc", "-t", "1", "-o", str(tmp_path / "r" / "p")] + extra + [prep])
+    assert ours[0] == ref[0]
+    assert ours[1] == ref[1]
