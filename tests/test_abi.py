@@ -116,3 +116,14 @@ int main(void) {
                            "-L", libdir, "-lportcullis_junc", "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()
     assert out[0] == "1" and out[1] == "256" and out[2] == "256"
+
+
+def test_corrupted_bam_and_index_never_crash_the_readers():
+    """80 + 80 random corruptions of a fixture's BAM / BAI (tools/fuzz_decoder.py, in a child process): open, plan, decode and
+    `--separate` either work or raise PjError; a crash would show as a non-zero exit without the summary line."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mode in ("bam", "bai"):
+        p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_decoder.py"), mode, "7000", "80"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert p.returncode == 0 and ("mode %s cases 80" % mode) in p.stdout, p.stderr[-600:]
