@@ -147,15 +147,20 @@ void BamFile::open(const std::string& bam_path) {
     if (s.read(b4, 4) != 4 || memcmp(b4, "BAM\1", 4) != 0) throw IoError("not a BAM file: " + bam_path);
     if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
     uint32_t l_text = rd32(b4);
+    // sizes in a corrupted header must not turn into giant allocations: DEFLATE cannot expand more than about 1032:1
+    const uint64_t max_unc = (uint64_t)file_.size() * 1100ull + 65536ull;
+    if (l_text > max_unc) throw IoError("corrupt BAM header (l_text) in " + bam_path);
     hdr_.text.resize(l_text);
     if (l_text && s.read(&hdr_.text[0], l_text) != l_text) throw IoError("truncated BAM header text");
     while (!hdr_.text.empty() && hdr_.text.back() == '\0') hdr_.text.pop_back();
     if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
     uint32_t n_ref = rd32(b4);
+    if ((uint64_t)n_ref * 9ull > max_unc) throw IoError("corrupt BAM header (n_ref) in " + bam_path);
     hdr_.names.resize(n_ref); hdr_.lens.resize(n_ref);
     for (uint32_t i = 0; i < n_ref; i++) {
         if (s.read(b4, 4) != 4) throw IoError("truncated BAM header");
         uint32_t l_name = rd32(b4);
+        if (l_name > max_unc) throw IoError("corrupt BAM header (l_name) in " + bam_path);
         std::string nm(l_name, '\0');
         if (l_name && s.read(&nm[0], l_name) != l_name) throw IoError("truncated BAM header");
         while (!nm.empty() && nm.back() == '\0') nm.pop_back();
@@ -173,6 +178,8 @@ bool BamFile::load_bai(const std::string& bai_path) {
     need(8);
     if (memcmp(p, "BAI\1", 4) != 0) throw IoError("not a BAI index: " + bai_path);
     uint32_t n_ref = rd32(p + 4); o = 8;
+    if ((uint64_t)n_ref * 8ull > n - o) throw IoError("corrupt BAI (n_ref): " + bai_path);          // every reference takes at least n_bin + n_intv
+    if (!hdr_.lens.empty() && n_ref != hdr_.lens.size()) throw IoError("the BAI index does not belong to this BAM (" + std::to_string(n_ref) + " references, header has " + std::to_string(hdr_.lens.size()) + "): " + bai_path);
     idx_.assign(n_ref, BamTargetIndex());
     for (uint32_t r = 0; r < n_ref; r++) {
         BamTargetIndex& t = idx_[r];
@@ -218,6 +225,8 @@ bool BamFile::load_csi(const std::string& csi_path) {
     if (min_shift < 1 || min_shift > 30 || depth < 0 || depth > 10) throw IoError("unsupported CSI geometry: " + csi_path);   // depth 0: htslib writes it for targets shorter than one window
     o = 16; need(l_aux + 4ull); o += l_aux;
     const uint32_t n_ref = rd32(p + o); o += 4;
+    if ((uint64_t)n_ref * 4ull > n - o) throw IoError("corrupt CSI (n_ref): " + csi_path);
+    if (!hdr_.lens.empty() && n_ref != hdr_.lens.size()) throw IoError("the CSI index does not belong to this BAM (" + std::to_string(n_ref) + " references, header has " + std::to_string(hdr_.lens.size()) + "): " + csi_path);
     auto first_bin = [](int lvl) { return (uint64_t)(((1ull << (3 * lvl)) - 1) / 7); };
     const uint64_t meta_bin = first_bin(depth + 1) + 1;
     idx_.assign(n_ref, BamTargetIndex());
@@ -324,7 +333,7 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
             if (g != 4) throw IoError("truncated BAM record in " + file_.path());
             bs = rd32(b4);
         }
-        if (bs < 32) throw IoError("corrupt BAM record (block_size < 32)");
+        if (bs < 32 || bs > (1u << 29)) throw IoError("corrupt BAM record (block_size " + std::to_string(bs) + ")");
         const uint8_t* p = s.take(bs);                      // most records lie inside one BGZF block: parse them in place
         if (!p) {
             rec.resize(bs);
