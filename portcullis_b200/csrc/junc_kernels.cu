@@ -128,6 +128,20 @@ void launch_coord_keys(int64_t n, const int32_t* tid, const int32_t* pos, const 
 
 void launch_fill_i32(int32_t* a, int64_t n, int32_t v, cudaStream_t st) { if (n > 0) k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, v); }
 void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st) { if (n > 0 && add) k_rebase_u32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, add); }
+// Offsets of a submitted batch (already rebased into the shard arena): both prefix columns must be non-decreasing and stay inside
+// what has been copied, or the CIGAR / SEQ walks of the pipeline would leave the arena.  Sets *bad on the first violation.
+__global__ void __launch_bounds__(256) k_check_offsets(int64_t first, int64_t n, const uint32_t* __restrict__ cigar_off, const uint64_t* __restrict__ seq_off,
+                                                        uint64_t cig_lo, uint64_t cig_hi, uint64_t seq_lo, uint64_t seq_hi, unsigned long long* __restrict__ bad) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    const uint64_t c0 = cigar_off[i], c1 = cigar_off[i + 1], s0 = seq_off[i], s1 = seq_off[i + 1];
+    if (c0 > c1 || c0 < cig_lo || c1 > cig_hi || s0 > s1 || s0 < seq_lo || s1 > seq_hi) *bad = 1ull;
+}
+void launch_check_offsets(int64_t first, int64_t n, const uint32_t* cigar_off, const uint64_t* seq_off, uint64_t cig_lo, uint64_t cig_hi,
+                          uint64_t seq_lo, uint64_t seq_hi, unsigned long long* bad, cudaStream_t st) {
+    if (n > 0) k_check_offsets<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(first, n, cigar_off, seq_off, cig_lo, cig_hi, seq_lo, seq_hi, bad);
+}
 void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { if (n > 0 && add) k_rebase_u64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, n, add); }
 
 // ================================================================================================

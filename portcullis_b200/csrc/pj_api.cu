@@ -134,7 +134,7 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
     c->max_slots = cfg->reserved[2] > 0 ? std::max(2, cfg->reserved[2]) : 4;
     c->extra = cfg->extra_metrics != 0;
     CU(c, cudaMalloc(&c->d_scalars, 16 * sizeof(uint32_t)));
-    CU(c, cudaMalloc(&c->d_shard_acc, 2 * sizeof(unsigned long long)));
+    CU(c, cudaMalloc(&c->d_shard_acc, 4 * sizeof(unsigned long long)));
     CU(c, cudaMallocHost((void**)&c->h_scalars, 16 * sizeof(uint32_t)));
     // keep stream-ordered allocations cached between shards
     cudaMemPool_t pool; CU(c, cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -283,7 +283,7 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
         (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 48, 0, st))) return rc;
     if (c->extra && (rc = ensure(c, c->name_code, r, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
-    CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 2 * sizeof(unsigned long long), st));
+    CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 4 * sizeof(unsigned long long), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
     CU(c, cudaMemsetAsync(c->seq4.p, 0, 16, st));                       // the lead pad is read (and masked out) by k_match: keep it defined
     // Pre-grow the stream-ordered pool that pj_shard_run allocates its temporaries from (about 12 B per record and 80 B
@@ -380,6 +380,8 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
     if (nseq) CU(c, cudaMemcpyAsync(c->seq4.p + c->n_seq, b->seq4 + sb, nseq, H2D, st));
     launch_rebase_u32(c->cigar_off.p + R + 1, n, (uint32_t)c->n_cig - cb, st);
     launch_rebase_u64(c->seq_off.p + R + 1, n, c->n_seq - sb, st);
+    // the prefix columns of the batch must stay inside what was copied (a malformed batch must not send the kernels out of the arena)
+    launch_check_offsets((int64_t)R, n, c->cigar_off.p, c->seq_off.p, c->n_cig, c->n_cig + ncig, c->n_seq, c->n_seq + nseq, c->d_shard_acc + 2, st);
     CU(c, cudaGetLastError());
     {
         std::lock_guard<std::mutex> lk(c->staging_mu);
@@ -429,9 +431,10 @@ int pj_shard_run(pj_ctx* c) {
     };
     {
         // front end: the longest N op and the number of N ops were accumulated while the batches were copied in
-        unsigned long long acc[2] = {0, 0};
+        unsigned long long acc[3] = {0, 0, 0};
         CU(c, cudaStreamSynchronize(c->copy_stream));
         CU(c, cudaMemcpy(acc, c->d_shard_acc, sizeof acc, cudaMemcpyDeviceToHost));
+        if (acc[2]) return fail(c, PJ_EINVAL, "pj_shard_run: a submitted batch has cigar_off / seq_off columns that are not non-decreasing prefix offsets within its cigar / seq4 arrays");
         const uint32_t maxN = (uint32_t)(acc[0] & 0xffffffffull);
         if (acc[1] >= 0xfffffff0ull) return fail(c, PJ_EINVAL, "pj_shard_run: more than 2^32 read-junction pairs in one shard");
         len_bits = std::max(1, bit_length(maxN)); key_bits = len_bits + gbits;

@@ -62,7 +62,7 @@ struct pj_ctx {
     // per-target accumulators + misc device scalars
     unsigned long long *d_spliced = nullptr, *d_unspliced = nullptr, *d_sumq = nullptr; int32_t *d_minq = nullptr, *d_maxq = nullptr;
     uint32_t* d_scalars = nullptr;    // [0]=err [1]=max_nlen [2]=P [3]=J [4]=E [5]=scratch total [6]=tile ticket
-    unsigned long long* d_shard_acc = nullptr;   // [0] (low 32 bits) longest N op, [1] number of N ops of the shard: filled while batches are copied in
+    unsigned long long* d_shard_acc = nullptr;   // [0] (low 32 bits) longest N op, [1] number of N ops of the shard, [2] != 0: a batch had malformed prefix offsets; filled while batches are copied in
     uint32_t* h_scalars = nullptr;    // pinned mirror
     // results
     pj_junction* d_rows = nullptr; size_t rows_cap = 0; int64_t n_junc = 0; uint64_t n_pairs = 0;

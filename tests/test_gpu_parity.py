@@ -147,6 +147,17 @@ def test_rejected_inputs_fail_loudly():
     # the oracle rejects the same input
     with pytest.raises(ob.OracleError):
         ob.run(cols, ds["lengths"], [b""])
+    # prefix columns that are not prefix offsets (a host bug): rejected before any kernel walks them, not a device fault
+    def swap_middle(a):
+        b = a.copy(); b[1], b[2] = a[2] + 7, a[1]; return b
+    for col, edit in (("cigar_off", lambda a: a[::-1].copy()), ("cigar_off", swap_middle), ("seq_off", lambda a: np.concatenate([a[:1], a[1:][::-1]])), ("seq_off", swap_middle)):
+        bad = dict(cols); bad[col] = edit(cols[col]).astype(cols[col].dtype)
+        if bad[col][-1] < bad[col][0]:
+            bad[col][0], bad[col][-1] = cols[col][0], cols[col][-1]        # keep the ends plausible: the host checks those itself
+        assert not np.all(np.diff(bad[col].astype(np.int64)) >= 0)
+        with pytest.raises(L.PjError) as ei:
+            gpu_run(bad, ds["lengths"], ds["genomes"])
+        assert ei.value.code in (L.PJ_EINVAL, L.PJ_EDATA), col
 
 
 @pytest.mark.parametrize("group", [1, 2, 4, 8, 16, 32])
