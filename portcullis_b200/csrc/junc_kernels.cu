@@ -558,7 +558,10 @@ int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint
 // ticket, which guarantees that every tile a block waits on has already started.
 // ================================================================================================
 constexpr int OS_THREADS = 512;
-constexpr int OS_ITEMS = 16;
+#ifndef PJ_OS_ITEMS
+#define PJ_OS_ITEMS 16
+#endif
+constexpr int OS_ITEMS = PJ_OS_ITEMS;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;       // 8192 keys per tile
 constexpr int OS_WARPS = OS_THREADS / 32;
 constexpr int OS_MAX_BITS = 10;
