@@ -2,6 +2,7 @@
 #include "bam_io.hpp"
 #include <zlib.h>
 #include "inflate_fast.hpp"
+#include "crc32_fast.hpp"
 #include <cstring>
 #include <climits>
 #include <algorithm>
@@ -67,6 +68,8 @@ bool BgzfStream::load_block(uint64_t coff) {
         int rc = inflate(z, Z_FINISH);
         if (rc != Z_STREAM_END || z->total_out != isize) throw IoError("BGZF inflate failed in " + f_.path());
     }
+    // CRC32 trailer, like htslib's bgzf_read_block: a corrupted block (or a decoder bug) must not reach the junction counts
+    if (isize && crc32_block(ubuf_.data(), isize) != rd32(p + bsize - 8)) throw IoError("BGZF block CRC32 mismatch in " + f_.path());
     ulen_ = isize; upos_ = 0; next_coff_ = coff + bsize; have_block_ = true;
     return true;
 }
@@ -413,6 +416,7 @@ int pjio::inflate_selftest(int n_cases) {
         deflate(&z, Z_FINISH); const size_t cn = z.total_out; deflateEnd(&z);
         std::vector<uint8_t> o(n + 64);
         if (!inf.run(c.data(), cn, o.data(), n) || memcmp(o.data(), d.data(), n) != 0) bad++;
+        if (crc32_block(d.data(), n) != (uint32_t)crc32(0L, d.data(), (uInt)n)) bad++;     // crc32_fast.hpp against zlib
         // corrupted and truncated input must never read or write out of bounds (the result itself is irrelevant: the caller
         // falls back to zlib whenever run() returns false, and BGZF carries its own size trailer)
         if (cn > 8) { c[cn / 2] ^= 0x55; std::vector<uint8_t> o2(n + 64); (void)inf.run(c.data(), cn, o2.data(), n); (void)inf.run(c.data(), cn / 2, o2.data(), n); }

@@ -12,6 +12,7 @@
 // specification (§5.2 BAI, CSIv1); they are equivalent to, not byte-equal with, `samtools index` output.
 #include "bam_out.hpp"
 #include "inflate_fast.hpp"
+#include "crc32_fast.hpp"
 
 namespace pjio {
 
@@ -69,10 +70,15 @@ void scan_records(const BamFile& bam, int threads, const std::function<void(cons
                 // the fast decoder may write up to 64 bytes past the block: decode into scratch, another thread owns what follows
                 uint8_t tmp[65536 + 64];
                 const bool ok = B.coff + B.bsize + 16 <= mf.size() && fast[t]->run(src, n, tmp, B.isize);
-                if (ok) { memcpy(dst, tmp, B.isize); continue; }
+                const uint32_t want_crc = rd32(mf.data() + B.coff + B.bsize - 8);
+                if (ok) {
+                    if (crc32_block(tmp, B.isize) != want_crc) throw IoError("BGZF block CRC32 mismatch in " + mf.path());
+                    memcpy(dst, tmp, B.isize); continue;
+                }
                 if (!z_open) { if (inflateInit2(&z, -15) != Z_OK) throw IoError("inflateInit2 failed"); z_open = true; } else inflateReset(&z);
                 z.next_in = (Bytef*)src; z.avail_in = (uInt)n; z.next_out = dst; z.avail_out = B.isize;
                 if (inflate(&z, Z_FINISH) != Z_STREAM_END || z.total_out != B.isize) { inflateEnd(&z); throw IoError("BGZF inflate failed in " + mf.path()); }
+                if (crc32_block(dst, B.isize) != want_crc) { inflateEnd(&z); throw IoError("BGZF block CRC32 mismatch in " + mf.path()); }
             }
             if (z_open) inflateEnd(&z);
         });

@@ -118,12 +118,19 @@ namespace {
 
 class Out {
 public:
-    explicit Out(const std::string& path) : f_(fopen(path.c_str(), "wb")) {
+    explicit Out(const std::string& path) : f_(fopen(path.c_str(), "wb")), path_(path) {
         if (!f_) throw std::runtime_error("cannot open " + path + " for writing");
         buf_.reserve(1 << 22);
     }
     Out() : f_(nullptr) {}                                   // in-memory: rows formatted by a worker thread
-    ~Out() { if (f_) { flush(); fclose(f_); } }
+    ~Out() { if (f_) { if (!buf_.empty()) (void)fwrite(buf_.data(), 1, buf_.size(), f_); fclose(f_); } }   // best effort only: writers call close()
+    // Flushes and closes the file; a short write or a failing close (ENOSPC, EIO, quota) is an error, never a silently truncated table.
+    void close() {
+        if (!f_) return;
+        flush();
+        FILE* f = f_; f_ = nullptr;
+        if (fclose(f) != 0) throw std::runtime_error("error closing " + path_ + " (disk full?)");
+    }
     const std::string& str() const { return buf_; }
     void s(const char* p, size_t n) { buf_.append(p, n); if (f_ && buf_.size() > (1u << 22) - 4096) flush(); }
     void s(const char* p) { s(p, strlen(p)); }
@@ -133,9 +140,15 @@ public:
     void i(int64_t v) { if (v < 0) { c('-'); u((uint64_t)(-(v + 1)) + 1); } else u((uint64_t)v); }
     void g(double v, int prec = 6) { char t[48]; int k = snprintf(t, sizeof t, "%.*g", prec, v); s(t, (size_t)k); }
     void f3(double v) { char t[48]; int k = snprintf(t, sizeof t, "%.3f", v); s(t, (size_t)k); }
-    void flush() { if (f_ && !buf_.empty()) { fwrite(buf_.data(), 1, buf_.size(), f_); buf_.clear(); } }
+    void flush() {
+        if (f_ && !buf_.empty()) {
+            const size_t n = fwrite(buf_.data(), 1, buf_.size(), f_);
+            if (n != buf_.size()) { buf_.clear(); throw std::runtime_error("short write to " + path_ + " (disk full?)"); }
+            buf_.clear();
+        }
+    }
 private:
-    FILE* f_; std::string buf_;
+    FILE* f_; std::string path_; std::string buf_;
 };
 
 // Formats rows [0, n) with `fmt(out, r)` on a few threads and appends the pieces to `o` in row order.
@@ -209,6 +222,7 @@ void write_tab(const std::string& path, const pj_junction* rows, int64_t n, cons
         o.c('\n');
     });
     o.c('\n');        // `strm << js << endl` leaves one blank line at EOF (junction_system.cc:356)
+    o.close();
 }
 
 void write_bed(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
@@ -228,6 +242,7 @@ void write_bed(const std::string& path, const pj_junction* rows, int64_t n, cons
         o.i(j.start - j.left); o.c(','); o.i(j.right - j.end); o.c('\t');
         o.s("0,"); o.i(j.end - j.left + 1); o.c('\n');
     });
+    o.close();
 }
 
 void write_exon_gff(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
@@ -260,6 +275,7 @@ void write_exon_gff(const std::string& path, const pj_junction* rows, int64_t n,
         lead("match_part", (int64_t)j.end + 2, (int64_t)j.right + 1);
         o.s("ID=junc_"); o.u(j.index); o.s("_right;Parent=junc_"); o.u(j.index); o.c('\n');
     });
+    o.close();
 }
 
 void write_intron_gff(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
@@ -273,6 +289,7 @@ void write_intron_gff(const std::string& path, const pj_junction* rows, int64_t 
         o.u(j.nb_raw_aln); o.c('\t'); o.c(strand_char(j.consensus_strand)); o.s("\t.\tmult="); o.u(j.nb_raw_aln);
         o.s(";grp=junc_"); o.u(j.index); o.s(";src=E\n");
     });
+    o.close();
 }
 
 } // namespace pjhost

@@ -958,8 +958,10 @@ __global__ void __launch_bounds__(256) k_entropy_compact(uint32_t n, const uint3
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && eflag[i]) epos[eoff[i]] = i;
 }
-// One warp per junction: lane l evaluates emission points l, l+32, ... and the warp adds the terms with a fixed shuffle
-// tree (deterministic; the order differs from the reference's loop only by fp64 rounding, far inside the 1e-6 bound).
+// One warp per junction: lane l evaluates the terms of emission points k0 + 32c + l in parallel, and the warp then adds the 32
+// terms of the round ONE BY ONE in loop order (every lane runs the same chain of fp64 additions on shuffled values), so the
+// sum is formed exactly as Junction::calcEntropy forms it: sum = (...((0 + t0) + t1) + ...).  A junction has at most one
+// emission point per distinct read start, so the sequential part is short (entropy text must not depend on a tree order).
 __global__ void __launch_bounds__(256) k_entropy_sum(uint32_t n_junc, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ eoff,
                                                       const uint32_t* __restrict__ epos, double* __restrict__ entropy) {
     const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -969,15 +971,19 @@ __global__ void __launch_bounds__(256) k_entropy_sum(uint32_t n_junc, const uint
     double sum = 0.0;
     if (n > 1) {
         const uint32_t k0 = eoff[s], k1 = eoff[e - 1];       // the last element of a segment always emits
-        for (uint32_t k = k0 + lane; k <= k1; k += 32) {
-            const uint32_t i = epos[k];
-            const uint32_t term = (k == k0) ? (i - s + 1) : (i - epos[k - 1]);   // elements since the previous emission (quirk Q1)
-            const double p = (double)term / (double)n;          // a true division: term == n must give exactly 1.0 (entropy 0)
-            sum += p * log2(p);
+        for (uint32_t kb = k0; kb <= k1; kb += 32) {
+            const uint32_t k = kb + lane;
+            double t = 0.0;
+            if (k <= k1) {
+                const uint32_t i = epos[k];
+                const uint32_t term = (k == k0) ? (i - s + 1) : (i - epos[k - 1]);   // elements since the previous emission (quirk Q1)
+                const double p = (double)term / (double)n;      // a true division: term == n must give exactly 1.0 (entropy 0)
+                t = p * log2(p);
+            }
+            const int cnt = (int)min(32u, k1 - kb + 1u);
+            for (int l = 0; l < cnt; l++) sum += __shfl_sync(FULL, t, l);
         }
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     if (lane == 0) entropy[j] = fabs(sum);
 }
 void launch_entropy_compact(uint32_t n, const uint32_t* eflag, const uint32_t* eoff, uint32_t* epos, cudaStream_t st) {

@@ -272,7 +272,8 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->compute_stream));
     extra_reset(c);
-    c->n_rec = 0; c->n_cig = 0; c->n_seq = 16; c->have_result = false;   // SEQ stream: 16-byte lead pad (k_match may look back up to 15 nibbles) c->n_junc = 0; c->n_pairs = 0;
+    c->n_rec = 0; c->n_cig = 0; c->n_seq = 16; c->have_result = false;   // SEQ stream: 16-byte lead pad (k_match may look back up to 15 nibbles)
+    c->n_junc = 0; c->n_pairs = 0;
     cudaStream_t st = c->copy_stream;
     const size_t r = (size_t)std::max<int64_t>(n_records_hint, 1024);
     int rc;

@@ -127,3 +127,40 @@ def test_corrupted_bam_and_index_never_crash_the_readers():
     for mode in ("bam", "bai"):
         p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_decoder.py"), mode, "7000", "80"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         assert p.returncode == 0 and ("mode %s cases 80" % mode) in p.stdout, p.stderr[-600:]
+
+
+def _bgzf_blocks(buf):
+    off = 0
+    while off + 18 <= len(buf):
+        xlen = int.from_bytes(buf[off + 10:off + 12], "little")
+        bsize = int.from_bytes(buf[off + 16:off + 18], "little") + 1
+        yield off, xlen, bsize
+        off += bsize
+
+
+def test_bgzf_crc_mismatch_is_detected(tmp_path):
+    """a block whose payload inflates cleanly to ISIZE bytes but does not match its CRC32 trailer (bit-rot, or a
+    decoder bug) must be rejected by both readers, as htslib's bgzf_read does — not flow into the junction counts."""
+    import zlib
+    from portcullis_b200 import junction_builder as jb, _lib as L
+    src = os.path.join(os.path.dirname(__file__), "golden", "short_pe")
+    bam = bytearray(open(src + "/reads.bam", "rb").read())
+    blocks = [b for b in _bgzf_blocks(bam) if b[2] > 200]
+    off, xlen, bsize = blocks[len(blocks) // 2]
+    raw = bytearray(zlib.decompress(bytes(bam[off + 12 + xlen:off + bsize - 8]), -15))
+    raw[len(raw) // 2] ^= 0x01                                    # one flipped bit in the uncompressed records
+    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+    payload = comp.compress(bytes(raw)) + comp.flush()
+    new_block = bytearray(bam[off:off + 12 + xlen]) + payload + bam[off + bsize - 8:off + bsize]     # stale CRC, same ISIZE
+    new_block[16:18] = (len(new_block) - 1).to_bytes(2, "little")
+    out = bam[:off] + new_block + bam[off + bsize:]
+    d = str(tmp_path / "p")
+    os.makedirs(d)
+    open(d + "/portcullis.sorted.alignments.bam", "wb").write(bytes(out))
+    for a, b in (("reads.bam.bai", "portcullis.sorted.alignments.bam.bai"), ("genome.fa", "portcullis.genome.fa"), ("genome.fa.fai", "portcullis.genome.fa.fai")):
+        os.symlink(os.path.join(src, a), os.path.join(d, b))
+    p = jb.PrepDir(d)                                             # the index still points at valid block starts up to the patched block
+    with pytest.raises(L.PjError, match="CRC32"):
+        p.decode(-1, 2)
+    with pytest.raises(L.PjError, match="CRC32"):
+        jb.separate_bams(d, str(tmp_path / "s" / "p"), threads=2)
