@@ -57,12 +57,33 @@ typedef struct pjh_report {
     double  t_teardown_s;        /* pj_destroy                                                    */
     double  t_extra_s;           /* --extra: name exchange + pj_extra_run + coverage (0 otherwise) */
     double  t_separate_s;        /* --separate: splitting + indexing the BAM on the host (0 otherwise) */
+    int32_t n_segments;          /* shards run (pj_shard_begin ... pj_shard_fetch), summed over GPUs    */
+    int32_t n_gap_cuts;          /* segment boundaries placed inside a target (at a position no spliced read spans) */
 } pjh_report;
 
 void pjh_options_default(pjh_options* o);
 /* Runs the whole `junc` stage. Returns 0 or a PJ_E* code; message in pjh_last_error(). */
 int pjh_junc_run(const pjh_options* opt, pjh_report* report);
 const char* pjh_last_error(void);
+
+/* ---- one process per GPU (torchrun / MPI style launch; the reference's counterpart is one task per target on its thread
+ * pool, src/junction_builder.cc:109-112, 459-542) ----
+ * Every process computes the same work plan: the BAM-ordered decode tasks, weighted by the index's record counts, are cut
+ * into n_parts contiguous ranges; a cut inside a target is moved to the next record no spliced read spans, so no junction
+ * (key: refid, start, end — lib/include/portcullis/intron.hpp:69-73) has reads in two parts.  pjh_junc_run_part decodes and
+ * runs part `part` on device opt->gpu_ids[0] (default 0) with opt->threads decode threads and keeps the rows (already in
+ * (tid, start, end) order; parts concatenate in part order) and the per-target scalars.  No collective is involved: the
+ * caller moves the rows to one process (shared memory, a file, MPI_Gatherv ...) and calls pjh_junc_finish there, which
+ * merges, runs A12/A13 (pj_junctions_finalize) and writes the output files exactly like pjh_junc_run. */
+typedef struct pjh_partial pjh_partial;
+int     pjh_junc_run_part(const pjh_options* opt, int32_t part, int32_t n_parts, pjh_partial** out, pjh_report* report);
+int64_t pjh_partial_rows(const pjh_partial* p, const pj_junction** rows);          /* returns the row count               */
+int32_t pjh_partial_stats(const pjh_partial* p, const pj_target_stats** stats);    /* returns n_targets; one entry each   */
+void    pjh_partial_free(pjh_partial* p);
+/* rows[n_rows]: the parts' rows concatenated in part order (finalized in place); stats[n_targets]: per-target scalars summed
+ * over the parts (counts and sums added, min/max combined; a part that saw no record of a target reports min = INT32_MAX). */
+int     pjh_junc_finish(const pjh_options* opt, pj_junction* rows, int64_t n_rows, const pj_target_stats* stats, int32_t n_targets,
+                        pjh_report* report);
 
 /* `portcullis junc ...` command line (argv[0] is the mode word).  Returns the process exit code. */
 int pjh_junc_main(int argc, char** argv);
@@ -88,6 +109,15 @@ int         pjh_prep_genome(pjh_prep* p, int32_t tid, const char** bases, int64_
  * counts (compressed bytes when the index has no counts).  Deterministic, so every rank of a multi-process launch
  * computes the same plan. */
 int         pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_target);
+
+/* The range plan pjh_junc_run / pjh_junc_run_part execute (see pjh_junc_run_part): n_parts contiguous record-balanced ranges,
+ * each cut into segments of at most seg_records records (<= 0: the default, 32 Mi); whole_targets != 0 gives the `--extra`
+ * plan instead (LPT of whole targets, one segment per part).  segments_per_part[n_parts] receives the number of segments of
+ * every part; n_gap_cuts the number of boundaries that fell inside a target.  pjh_plan_decode decodes one segment into
+ * columnar arrays owned by `p` (valid until the next decode).  Used by the tests: the segments partition the records of the
+ * BAM in file order, and no spliced record of an earlier segment reaches the first position of a later one. */
+int         pjh_plan_describe(const pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t* segments_per_part, int32_t* n_gap_cuts);
+int         pjh_plan_decode(pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t part, int32_t segment, int32_t threads, pj_batch* out);
 
 /* Checks the built-in fast DEFLATE decoder (BGZF blocks) against zlib on n_cases synthetic streams; returns the number of
  * mismatches (0 = pass).  BGZF blocks the fast decoder rejects are decoded by zlib, so it can only be an accelerator. */

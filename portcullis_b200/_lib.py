@@ -85,7 +85,7 @@ class PjhReport(C.Structure):
                 ("t_finalize_s", C.c_double), ("t_write_s", C.c_double), ("t_total_s", C.c_double),
                 ("n_gpus_used", C.c_int32), ("n_kernel_launches", C.c_int32),
                 ("t_init_s", C.c_double), ("t_run_s", C.c_double), ("t_teardown_s", C.c_double),
-                ("t_extra_s", C.c_double), ("t_separate_s", C.c_double)]
+                ("t_extra_s", C.c_double), ("t_separate_s", C.c_double), ("n_segments", C.c_int32), ("n_gap_cuts", C.c_int32)]
 
 
 class PjhPrepOptions(C.Structure):
@@ -157,6 +157,11 @@ SYMBOLS = {
     "pj_extra_finalize": (None, [_P, C.c_int64]),
     "pjh_options_default": (None, [C.POINTER(PjhOptions)]),
     "pjh_junc_run": (C.c_int, [C.POINTER(PjhOptions), C.POINTER(PjhReport)]),
+    "pjh_junc_run_part": (C.c_int, [C.POINTER(PjhOptions), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(PjhReport)]),
+    "pjh_partial_rows": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pjh_partial_stats": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pjh_partial_free": (None, [C.c_void_p]),
+    "pjh_junc_finish": (C.c_int, [C.POINTER(PjhOptions), C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(PjhReport)]),
     "pjh_last_error": (C.c_char_p, []),
     "pjh_junc_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "pjh_prep_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
@@ -170,6 +175,8 @@ SYMBOLS = {
     "pjh_prep_genome": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
     "pjh_inflate_selftest": (C.c_int, [C.c_int32]),
     "pjh_plan_shards": (C.c_int, [_P, C.c_int32, _P]),
+    "pjh_plan_describe": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, C.POINTER(C.c_int32)]),
+    "pjh_plan_decode": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PjBatch)]),
     "pjh_separate_bams": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _P]),
     "pjh_write_outputs_extra": (C.c_int, [C.c_char_p, _P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,
                                           C.c_int32, C.c_int32]),

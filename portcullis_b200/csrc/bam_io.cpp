@@ -327,6 +327,7 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
     std::vector<uint8_t> rec;
     const int32_t n_ref = (int32_t)hdr_.lens.size();
     for (;;) {
+        if (task.end_voff && s.tell() >= task.end_voff) break;   // the records from the gap cut on belong to the next slice
         uint32_t bs;
         if (const uint8_t* h = s.take(4)) bs = rd32(h);
         else {
@@ -386,6 +387,46 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
             out.seq4.resize(s0 + nb); memcpy(&out.seq4[s0], sq, nb);
         }
         out.seq_off.push_back((uint64_t)out.seq4.size());
+    }
+}
+
+bool BamFile::find_gap_cut(int32_t want_tid, int32_t pos_lo, uint64_t start_voff, uint64_t* cut_voff, int32_t* cut_pos) const {
+    BgzfStream s(file_);
+    s.seek(start_voff);
+    std::vector<uint8_t> rec;
+    int64_t max_end = -1;                                    // last reference base covered by a spliced record seen so far
+    for (;;) {
+        const uint64_t here = s.tell();
+        uint32_t bs;
+        if (const uint8_t* h = s.take(4)) bs = rd32(h);
+        else {
+            uint8_t b4[4];
+            size_t g = s.read(b4, 4);
+            if (g == 0) return false;
+            if (g != 4) throw IoError("truncated BAM record in " + file_.path());
+            bs = rd32(b4);
+        }
+        if (bs < 32 || bs > (1u << 29)) throw IoError("corrupt BAM record (block_size " + std::to_string(bs) + ")");
+        const uint8_t* p = s.take(bs);
+        if (!p) {
+            rec.resize(bs);
+            if (s.read(rec.data(), bs) != bs) throw IoError("truncated BAM record in " + file_.path());
+            p = rec.data();
+        }
+        const int32_t tid = (int32_t)rd32(p), pos = (int32_t)rd32(p + 4);
+        if (tid != want_tid) { if (tid > want_tid || tid < 0) return false; else continue; }
+        if (pos >= hdr_.lens[(size_t)tid]) return false;     // decode() stops the target here too (Q13)
+        if (pos >= pos_lo && (int64_t)pos > max_end) { *cut_voff = here; *cut_pos = pos; return true; }
+        const uint32_t l_name = p[8], n_cig = rd16(p + 12);
+        if (32ull + l_name + 4ull * n_cig > bs) throw IoError("corrupt BAM record (fields exceed block_size)");
+        const uint8_t* cg = p + 32 + l_name;
+        int64_t rlen = 0; bool spliced = false;
+        for (uint32_t k = 0; k < n_cig; k++) {
+            const uint32_t c = rd32(cg + 4 * k), op = c & 0xf;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += c >> 4;
+            if (op == 3) spliced = true;
+        }
+        if (spliced) max_end = std::max<int64_t>(max_end, (int64_t)pos + rlen - 1);
     }
 }
 

@@ -73,6 +73,7 @@ struct BamHeader {
 struct DecodeTask {
     int32_t tid; int32_t pos_lo; int32_t pos_hi; uint64_t voff;
     uint64_t approx_bytes;                 // compressed-size estimate, for scheduling
+    uint64_t end_voff = 0;                 // != 0: stop at the first record whose virtual offset is >= end_voff (a gap cut, find_gap_cut)
 };
 
 // Columnar records (same columns as pj_batch), owned vectors.
@@ -107,6 +108,12 @@ public:
     // Decode one task into `out` (appended).  Applies the reference's record visibility rule (Q13):
     // tid == target, pos < target_len, endpos > 0; iteration of a target stops at the first pos >= target_len.
     void decode(const DecodeTask& t, ColumnarChunk& out) const;
+    // Sub-target cut: junctions are keyed by (refid, start, end) (lib/include/portcullis/intron.hpp:69-73), so
+    // a target can be cut at any record R with  pos(R) >= pos_lo  and  pos(R) > end of every SPLICED record before it  — no read
+    // with an N op spans the cut, hence no junction has reads on both sides.  Scans the records of `tid` in file order from
+    // `start_voff` (the linear-index offset of the window holding pos_lo, so every record overlapping it is seen) and returns the
+    // first such record: its virtual offset and position.  false: the target ends before a cut is found.
+    bool find_gap_cut(int32_t tid, int32_t pos_lo, uint64_t start_voff, uint64_t* cut_voff, int32_t* cut_pos) const;
     const MappedFile& file() const { return file_; }
 private:
     MappedFile file_;

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -263,151 +264,237 @@ int pj_genome_load_fasta(pj_ctx* ctx, const char* fasta_path, const char* fai_pa
 }
 
 // ------------------------------------------------------------------------------------------------
-// JunctionBuilder::process equivalent
+// Work plan.  A *segment* is a list of decode tasks that one GPU context runs as one shard (pj_shard_begin ... pj_shard_fetch); a
+// *part* is the list of segments one GPU owns.  Two plans:
+//   * ranges (default): the BAM-ordered list of decode tasks, weighted by the index's record counts, is cut into n_parts contiguous
+//     ranges of equal weight, and every range into segments of at most `seg_budget` records.  A cut that falls inside a target is
+//     moved to the next record no spliced read spans (BamFile::find_gap_cut), so no junction has reads on both sides: segments are
+//     independent, their rows concatenate in (tid, start, end) order, and device memory is bounded by the segment size instead of
+//     the whole shard (the reference bounds memory the same way, by flushing junctions the scan has passed, junction_builder.cc:324-331).
+//     An oversized target (or a genome with fewer targets than GPUs) no longer pins the balance to whole targets.
+//   * whole targets (`--extra`, or PJ_WHOLE_TARGETS=1): LPT of whole targets on record counts, one segment per part; the extra
+//     metrics need every unspliced record of a target on one device.
 // ------------------------------------------------------------------------------------------------
-int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
-    if (!o || !o->prep_dir) return fail(PJ_EINVAL, "pjh_junc_run: no prep directory given");
-    pjh_report R; memset(&R, 0, sizeof R);
-    const double t0 = now_s();
-    const bool say = !o->quiet;
-    const bool extra = o->extra != 0;      // junction_builder.cc:113-117 turns --separate on for --extra; here the metrics come from the records in HBM instead
-    const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
-    {   // output directory (junction_builder.cc:65-66, 86-91)
-        fs::path parent = fs::path(prefix).parent_path();
-        std::error_code ec;
-        if (!parent.empty() && !fs::exists(parent, ec) && !fs::create_directories(parent, ec))
-            return fail(PJ_EIO, "Could not create output directory at: " + parent.string());
+namespace {
+
+struct Segment { std::vector<DecodeTask> tasks; std::vector<int32_t> targets; uint64_t weight = 0; };
+typedef std::vector<Segment> Part;
+
+struct PlanItem { int32_t tid; size_t k; uint64_t w; };        // task k of target tid, estimated records
+
+uint64_t env_u64(const char* name, uint64_t dflt) { const char* e = getenv(name); return (e && *e) ? strtoull(e, nullptr, 10) : dflt; }
+
+void seg_add_task(Segment& sg, const DecodeTask& t, uint64_t w) {
+    sg.tasks.push_back(t); sg.weight += w;
+    if (sg.targets.empty() || sg.targets.back() != t.tid) sg.targets.push_back(t.tid);
+}
+
+// returns PJ_OK; parts.size() == n_parts (parts may be empty when there is less work than parts)
+int plan_parts(const pjh_prep* prep, int n_parts, bool whole_targets, uint64_t seg_budget, std::vector<Part>& parts, int* n_gap_cuts) {
+    const int32_t T = (int32_t)prep->bam.header().names.size();
+    parts.assign((size_t)n_parts, Part());
+    if (n_gap_cuts) *n_gap_cuts = 0;
+    if (!prep->indexed) {                                     // no index: one whole-file task on part 0
+        Segment sg; sg.tasks.push_back(prep->bam.whole_file_task()); for (int32_t t = 0; t < T; t++) sg.targets.push_back(t);
+        parts[0].push_back(std::move(sg));
+        return PJ_OK;
     }
-    pjh_prep* prep = nullptr;
-    int rc = pjh_prep_open(o->prep_dir, o->use_csi, &prep);
-    if (rc) return rc;
-    std::unique_ptr<pjh_prep> prep_guard(prep);
-    const pjio::BamHeader& H = prep->bam.header();
-    const int32_t T = (int32_t)H.names.size();
-    if (T == 0) return fail(PJ_EDATA, "BAM header declares no target sequences");
-    int n_gpus = std::max(1, o->n_gpus);
-    if (n_gpus > T) n_gpus = T;
-    int threads = std::max(1, o->threads);
-    static const char* ORI[] = {"SE", "FR", "RF", "FF", "UNKNOWN"};
-    static const char* STR[] = {"UNSTRANDED", "FIRSTSTRAND", "SECONDSTRAND", "UNKNOWN"};
-    if (say) {
-        std::cout << "Settings:\n - BAM Strandedness: " << STR[std::min(std::max(o->strandedness, 0), 3)]
-                  << "\n - BAM Read Orientation: " << ORI[std::min(std::max(o->orientation, 0), 4)]
-                  << "\n - BAM Indexing mode: " << (o->use_csi ? "CSI" : "BAI")
-                  << "\n - Host decode threads: " << threads << "\n - GPUs: " << n_gpus << "\n - Separate BAMs: " << (o->separate ? "true" : "false") << "\n\n";
-    }
-    if (o->separate) {
-        // JunctionBuilder::separateBams (junction_builder.cc:152-226): host I/O only, before the junction pass like the reference
-        const double ts = now_s();
-        pjio::SeparateCounts sc;
-        const std::string un = prefix + ".unspliced.bam", sp = prefix + ".spliced.bam", um = prefix + ".unmapped.bam";
-        if (say) std::cout << "Splitting BAM:\n - Saving unspliced alignments to: \"" << un << "\"\n - Saving spliced alignments to: \"" << sp
-                           << "\"\n - Saving unmapped reads to: \"" << um << "\"\n - Processing BAM ..." << std::flush;
-        try { pjio::separate_bams(prep->bam, sp, un, um, o->use_csi != 0, threads, sc); }
-        catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
-        R.t_separate_s = now_s() - ts;
-        if (say) std::cout << " done.\n - Found " << sc.spliced << " spliced alignments.\n - Found " << sc.unspliced << " unspliced alignments.\n - Found "
-                           << sc.unmapped << " unmapped reads.\n - Indexed the unspliced and spliced alignments (" << (o->use_csi ? "CSI" : "BAI") << ").\n = Wall time taken: "
-                           << std::fixed << std::setprecision(1) << R.t_separate_s << "s\n" << std::defaultfloat << std::setprecision(6) << std::endl;
-    }
-    // ---- shard targets over GPUs: LPT on index record counts (fallback: compressed bytes) ----
     std::vector<std::vector<DecodeTask>> ttasks((size_t)T);
     std::vector<uint64_t> weight((size_t)T, 0);
-    if (prep->indexed) for (int32_t t = 0; t < T; t++) { prep->bam.plan_target(t, 4u << 20, ttasks[t]); weight[t] = target_weight(prep, t); }
-    else n_gpus = 1;
-    std::vector<std::vector<int32_t>> shard((size_t)n_gpus);
-    {
+    // decode tasks of about 4 MB of BGZF data; smaller for small files so that every part still gets tasks to balance with
+    const uint64_t task_bytes = std::min<uint64_t>(4u << 20, std::max<uint64_t>(64u << 10, prep->bam.file().size() / ((uint64_t)n_parts * 64)));
+    for (int32_t t = 0; t < T; t++) { prep->bam.plan_target(t, task_bytes, ttasks[t]); weight[t] = ttasks[t].empty() ? 0 : target_weight(prep, t); }
+    if (whole_targets) {
         std::vector<int32_t> owner((size_t)T, 0);
-        if ((rc = pjh_plan_shards(prep, n_gpus, owner.data()))) return rc;
-        for (int32_t t = 0; t < T; t++) shard[(size_t)owner[t]].push_back(t);     // ascending tid = BAM order inside a shard
+        int rc = pjh_plan_shards(prep, n_parts, owner.data());
+        if (rc) return rc;
+        for (int g = 0; g < n_parts; g++) {
+            Segment sg;
+            for (int32_t t = 0; t < T; t++) if (owner[t] == g) {                 // ascending tid = BAM order inside a shard
+                if (ttasks[t].empty()) { sg.targets.push_back(t); continue; }
+                uint64_t bytes = 0; for (auto& k : ttasks[t]) bytes += k.approx_bytes;
+                for (auto& k : ttasks[t]) seg_add_task(sg, k, bytes ? weight[t] * k.approx_bytes / bytes : 0);
+            }
+            if (!sg.tasks.empty() || !sg.targets.empty()) parts[(size_t)g].push_back(std::move(sg));
+        }
+        return PJ_OK;
     }
-    R.t_open_s = now_s() - t0;
-    R.n_gpus_used = n_gpus;
+    // ---- flatten, weigh, place the boundaries ----
+    std::vector<PlanItem> items;
+    uint64_t W = 0;
+    for (int32_t t = 0; t < T; t++) {
+        uint64_t bytes = 0; for (auto& k : ttasks[t]) bytes += std::max<uint64_t>(k.approx_bytes, 1);
+        for (size_t k = 0; k < ttasks[t].size(); k++) {
+            const uint64_t w = std::max<uint64_t>(1, (uint64_t)((double)weight[t] * (double)std::max<uint64_t>(ttasks[t][k].approx_bytes, 1) / (double)bytes));
+            items.push_back(PlanItem{t, k, w}); W += w;
+        }
+    }
+    const size_t n = items.size();
+    if (n == 0) return PJ_OK;
+    std::vector<uint64_t> cum(n + 1, 0);
+    for (size_t i = 0; i < n; i++) cum[i + 1] = cum[i] + items[i].w;
+    // boundary = (item index where the next segment starts, part that segment belongs to)
+    struct Boundary { size_t at; int part; };
+    std::vector<Boundary> bounds;
+    auto first_at_or_after = [&](double target) { return (size_t)(std::lower_bound(cum.begin(), cum.end(), (uint64_t)std::ceil(target)) - cum.begin()); };
+    size_t prev = 0;
+    for (int g = 0; g < n_parts; g++) {
+        size_t end = g + 1 == n_parts ? n : std::min(n, std::max(prev, first_at_or_after((double)W * (g + 1) / n_parts)));
+        // index `end` in cum[] means items [prev, end) are in the part; choose the nearer of the two candidate cuts
+        if (end > prev && end < n && g + 1 < n_parts) { const double tgt = (double)W * (g + 1) / n_parts; if (tgt - (double)cum[end - 1] < (double)cum[end] - tgt && end - 1 > prev) end--; }
+        const uint64_t wp = cum[end] - cum[prev];
+        const int nseg = (int)std::max<uint64_t>(1, (wp + seg_budget - 1) / std::max<uint64_t>(seg_budget, 1));
+        size_t sp = prev;
+        for (int q = 0; q < nseg; q++) {
+            bounds.push_back(Boundary{sp, g});
+            size_t se = q + 1 == nseg ? end : std::min(end, std::max(sp, first_at_or_after((double)cum[prev] + (double)wp * (q + 1) / nseg)));
+            sp = se;
+        }
+        prev = end;
+    }
+    // ---- build the segments; intra-target boundaries become gap cuts ----
+    size_t cur = 0;                                            // next item not yet handed out
+    bool have_head = false; DecodeTask head{}; uint64_t head_w = 0;
+    for (size_t b = 0; b < bounds.size(); b++) {
+        const size_t stop = b + 1 < bounds.size() ? std::max(bounds[b + 1].at, cur) : n;   // items [cur, stop) belong to this segment
+        Segment sg;
+        if (have_head) { seg_add_task(sg, head, head_w); have_head = false; }
+        for (; cur < stop; cur++) seg_add_task(sg, ttasks[items[cur].tid][items[cur].k], items[cur].w);
+        if (cur < n && !sg.tasks.empty() && sg.tasks.back().tid == items[cur].tid) {
+            // the next segment would start inside target t: look for the gap cut from task (t, k) on
+            const int32_t t = items[cur].tid; const size_t k = items[cur].k;
+            const DecodeTask& at = ttasks[t][k];
+            uint64_t cut_voff = 0; int32_t cut_pos = 0;
+            if (prep->bam.find_gap_cut(t, at.pos_lo, at.voff, &cut_voff, &cut_pos)) {
+                if (n_gap_cuts) (*n_gap_cuts)++;
+                DecodeTask tail = at; tail.pos_hi = INT32_MAX; tail.end_voff = cut_voff; tail.approx_bytes = 1;
+                seg_add_task(sg, tail, 0);
+                size_t k2 = k; while (k2 + 1 < ttasks[t].size() && ttasks[t][k2].pos_hi <= cut_pos) k2++;
+                head = ttasks[t][k2]; head.voff = cut_voff; head.pos_lo = cut_pos; head.end_voff = 0; have_head = true;
+                head_w = 0;
+                for (; cur < n && items[cur].tid == t && items[cur].k <= k2; cur++) head_w += items[cur].w;   // these items are covered by tail + head
+            } else {
+                for (; cur < n && items[cur].tid == t; cur++) seg_add_task(sg, ttasks[t][items[cur].k], items[cur].w);   // no gap before the target ends
+            }
+        }
+        if (!sg.tasks.empty()) parts[(size_t)bounds[b].part].push_back(std::move(sg));
+    }
+    if (have_head) {                                           // a cut after the last boundary cannot happen, but never drop work
+        Segment sg; seg_add_task(sg, head, head_w);
+        for (; cur < n; cur++) seg_add_task(sg, ttasks[items[cur].tid][items[cur].k], items[cur].w);
+        parts.back().push_back(std::move(sg));
+    }
+    return PJ_OK;
+}
 
-    struct GpuOut { pj_ctx* ctx = nullptr; std::vector<pj_junction_extra> extra; std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int rc = PJ_OK; std::string err; };
-    std::vector<GpuOut> outs((size_t)n_gpus);
-    const int threads_per_gpu = std::max(1, threads / n_gpus);
+} // namespace
+
+// rows + per-target scalars of one part (one GPU), before A12/A13
+struct pjh_partial {
+    std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; pjh_report rep;
+};
+
+// ------------------------------------------------------------------------------------------------
+// JunctionBuilder::process equivalent
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct GpuOut {
+    pj_ctx* ctx = nullptr; std::vector<pj_junction_extra> extra; std::vector<pj_junction> rows; std::vector<pj_target_stats> stats;
+    float gpu_ms = 0; int launches = 0; double genome_s = 0, decode_s = 0, init_s = 0, run_s = 0, teardown_s = 0; int n_segments = 0;
+    int rc = PJ_OK; std::string err;
+};
+
+// One GPU: CUDA context + library context + genome of the part's targets, then the part's segments one after the other
+// (decode workers -> pinned staging -> H2D -> pj_shard_run -> rows appended).  `device` is the CUDA ordinal.
+void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device, int threads, bool extra, GpuOut& out) {
+    const pjio::BamHeader& H = prep->bam.header();
+    const int32_t T = (int32_t)H.names.size();
+    auto bail = [&](int code, const std::string& m) { out.rc = code; out.err = m; };
+    out.stats.assign((size_t)T, pj_target_stats{0, 0, 0, INT32_MAX, 0});
+    if (part.empty()) return;                                          // less work than GPUs
+    uint64_t hint = 0; for (auto& sg : part) hint = std::max(hint, sg.weight);
+    std::vector<int32_t> my_targets;
+    for (auto& sg : part) for (int32_t t : sg.targets) if (my_targets.empty() || my_targets.back() != t) my_targets.push_back(t);
+    // ---- GPU side on its own host thread: CUDA start-up takes about a second on a B200, so BGZF decode starts right away and
+    // only the staging copies wait for the context. ----
+    pj_ctx* ctx = nullptr;
+    std::mutex gm; std::condition_variable gcv; bool ready = false; int gpu_rc = PJ_OK; std::string gpu_err;
+    int genome_rc = PJ_OK; std::string genome_err;
+    const double ti = now_s();
+    std::thread gpu_thread([&]() {
+        pj_config cfg; memset(&cfg, 0, sizeof cfg);
+        cfg.device = device; cfg.orientation = o->orientation;
+        cfg.reserved[2] = 4;                                           // pinned staging buffers (filled by one thread, drained by the copy engine)
+        cfg.extra_metrics = extra ? 1 : 0;
+        int r = pj_create(&cfg, &ctx);
+        std::string em;
+        if (r) em = pj_global_last_error();
+        if (!r && (r = pj_targets_set(ctx, T, H.lens.data()))) em = pj_last_error(ctx);
+        if (!r && (r = pj_shard_begin(ctx, (int64_t)hint + 1024, (int64_t)hint * 4 + 1024, (int64_t)hint * 56 + 1024))) em = pj_last_error(ctx);
+        out.init_s = now_s() - ti;
+        { std::lock_guard<std::mutex> lk(gm); ready = true; gpu_rc = r; gpu_err = em; }
+        gcv.notify_all();
+        if (r) return;
+        // genome: only this part's targets become resident on this GPU (own CUDA stream; overlaps the batch submission)
+        const double tg = now_s();
+        std::string seq;
+        for (int32_t t : my_targets) {
+            if (prep->indexed && prep->bam.index()[(size_t)t].first_voff == 0) continue;   // no records -> no junctions -> no genome needed
+            const pjio::FaiEntry* e = prep->fasta.find(H.names[t]);
+            if (!e) continue;
+            try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { genome_rc = PJ_EIO; genome_err = ex.what(); return; }
+            int q = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size());
+            if (q) { genome_rc = q; genome_err = pj_last_error(ctx); return; }
+        }
+        out.genome_s = now_s() - tg;
+    });
+    struct Cleanup {
+        std::thread& t; pj_ctx*& c; double* td;
+        ~Cleanup() { if (t.joinable()) t.join(); if (c) { const double a = now_s(); pj_destroy(c); *td = now_s() - a; } }
+    } cleanup{gpu_thread, ctx, &out.teardown_s};
+    auto wait_ready = [&]() -> int { std::unique_lock<std::mutex> lk(gm); gcv.wait(lk, [&] { return ready; }); return gpu_rc; };
+    // copy one decoded chunk into a pinned staging buffer of the context
+    auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
+        int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
+        if (q) return fail(q, pj_last_error(ctx));
+        const size_t n = (size_t)ch.n();
+        memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
+        memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
+        memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
+        memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
+        memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
+        if (extra) memcpy((void*)st.name_code, ch.name_code.data(), n * 8);
+        st.n_records = ch.n();
+        return PJ_OK;
+    };
+    // alignments: workers inflate + parse a task into a pooled pageable chunk (recycled, so its vectors keep their capacity and
+    // their faulted-in pages); this thread takes the chunks in BAM order, copies each into one of a few pinned staging buffers
+    // and enqueues the host-to-device copies.  Growing a large pinned pool costs far more (cudaMallocHost, about 0.6 ms per MB,
+    // serialised) than this one extra memcpy, and the decode can run ahead of a context that is still starting.
+    struct ChunkPool {
+        std::mutex mu; std::vector<std::unique_ptr<ColumnarChunk>> free_list;
+        std::unique_ptr<ColumnarChunk> get() {
+            { std::lock_guard<std::mutex> lk(mu); if (!free_list.empty()) { auto c = std::move(free_list.back()); free_list.pop_back(); return c; } }
+            return std::make_unique<ColumnarChunk>();
+        }
+        void put(std::unique_ptr<ColumnarChunk> c) { c->clear(); std::lock_guard<std::mutex> lk(mu); free_list.push_back(std::move(c)); }
+    } pool;
+    struct Payload { std::unique_ptr<ColumnarChunk> chunk; };
     // decoded-but-unsubmitted chunks (pageable): enough for the decode to keep going while a CUDA context is still starting
-    const size_t window_per_gpu = std::max<size_t>((size_t)threads_per_gpu * 4 + 2, 192);
-    auto run_gpu = [&](int g) {
-        GpuOut& out = outs[(size_t)g];
-        auto bail = [&](int code, const std::string& m) { out.rc = code; out.err = m; };
-        // ---- decode plan for this shard ----
-        std::vector<DecodeTask> tasks;
-        uint64_t nrec_hint = 0;
-        if (prep->indexed) for (int32_t t : shard[(size_t)g]) { tasks.insert(tasks.end(), ttasks[t].begin(), ttasks[t].end()); nrec_hint += weight[t]; }
-        else tasks.push_back(prep->bam.whole_file_task());
-        // ---- GPU side on its own host thread: CUDA context + library context + genome upload.  CUDA start-up takes about a
-        // second on a B200, so BGZF decode starts right away and only the staging copies wait for the context. ----
-        pj_ctx* ctx = nullptr;
-        std::mutex gm; std::condition_variable gcv; bool ready = false; int gpu_rc = PJ_OK; std::string gpu_err;
-        int genome_rc = PJ_OK; std::string genome_err;
-        const double ti = now_s();
-        std::thread gpu_thread([&]() {
-            pj_config cfg; memset(&cfg, 0, sizeof cfg);
-            cfg.device = o->gpu_ids ? o->gpu_ids[g] : g; cfg.orientation = o->orientation;
-            cfg.reserved[2] = 4;                                           // pinned staging buffers (filled by one thread, drained by the copy engine)
-            cfg.extra_metrics = extra ? 1 : 0;
-            int r = pj_create(&cfg, &ctx);
-            std::string em;
-            if (r) em = pj_global_last_error();
-            if (!r && (r = pj_targets_set(ctx, T, H.lens.data()))) em = pj_last_error(ctx);
-            if (!r && (r = pj_shard_begin(ctx, (int64_t)nrec_hint + 1024, (int64_t)nrec_hint * 4 + 1024, (int64_t)nrec_hint * 56 + 1024))) em = pj_last_error(ctx);
-            out.init_s = now_s() - ti;
-            { std::lock_guard<std::mutex> lk(gm); ready = true; gpu_rc = r; gpu_err = em; }
-            gcv.notify_all();
-            if (r) return;
-            // genome: only this shard's targets become resident on this GPU (own CUDA stream; overlaps the batch submission)
-            const double tg = now_s();
-            std::string seq;
-            for (int32_t t : shard[(size_t)g]) {
-                if (ttasks[t].empty() && prep->indexed) continue;          // no records -> no junctions -> no genome needed
-                const pjio::FaiEntry* e = prep->fasta.find(H.names[t]);
-                if (!e) continue;
-                try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { genome_rc = PJ_EIO; genome_err = ex.what(); return; }
-                int q = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size());
-                if (q) { genome_rc = q; genome_err = pj_last_error(ctx); return; }
-            }
-            out.genome_s = now_s() - tg;
-        });
-        struct Cleanup {
-            std::thread& t; pj_ctx*& c; double* td;
-            ~Cleanup() { if (t.joinable()) t.join(); if (c) { const double a = now_s(); pj_destroy(c); *td = now_s() - a; } }
-        } cleanup{gpu_thread, ctx, &out.teardown_s};
-        auto wait_ready = [&]() -> int { std::unique_lock<std::mutex> lk(gm); gcv.wait(lk, [&] { return ready; }); return gpu_rc; };
-        // copy one decoded chunk into a pinned staging buffer of the context
-        auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
-            int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
-            if (q) return fail(q, pj_last_error(ctx));
-            const size_t n = (size_t)ch.n();
-            memcpy((void*)st.tid, ch.tid.data(), n * 4); memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2);
-            memcpy((void*)st.mapq, ch.mapq.data(), n); memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4);
-            memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4);
-            memcpy((void*)st.cigar_off, ch.cigar_off.data(), (n + 1) * 4); memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4);
-            memcpy((void*)st.seq_off, ch.seq_off.data(), (n + 1) * 8); memcpy((void*)st.seq4, ch.seq4.data(), ch.seq4.size());
-            if (extra) memcpy((void*)st.name_code, ch.name_code.data(), n * 8);
-            st.n_records = ch.n();
-            return PJ_OK;
-        };
-        // alignments: workers inflate + parse a task into a pooled pageable chunk (recycled, so its vectors keep their capacity and
-        // their faulted-in pages); this thread takes the chunks in BAM order, copies each into one of a few pinned staging buffers
-        // and enqueues the host-to-device copies.  Growing a large pinned pool costs far more (cudaMallocHost, about 0.6 ms per MB,
-        // serialised) than this one extra memcpy, and the decode can run ahead of a context that is still starting.
-        struct ChunkPool {
-            std::mutex mu; std::vector<std::unique_ptr<ColumnarChunk>> free_list;
-            std::unique_ptr<ColumnarChunk> get() {
-                { std::lock_guard<std::mutex> lk(mu); if (!free_list.empty()) { auto c = std::move(free_list.back()); free_list.pop_back(); return c; } }
-                return std::make_unique<ColumnarChunk>();
-            }
-            void put(std::unique_ptr<ColumnarChunk> c) { c->clear(); std::lock_guard<std::mutex> lk(mu); free_list.push_back(std::move(c)); }
-        } pool;
-        struct Payload { std::unique_ptr<ColumnarChunk> chunk; };
+    const size_t window = std::max<size_t>((size_t)threads * 4 + 2, 192);
+    bool first = true;
+    for (const Segment& sg : part) {
+        int r;
+        if (!first) {                                                  // the first shard was opened by the GPU thread
+            if ((r = pj_shard_begin(ctx, (int64_t)sg.weight + 1024, (int64_t)sg.weight * 4 + 1024, (int64_t)sg.weight * 56 + 1024))) return bail(r, pj_last_error(ctx));
+        }
         const double td = now_s();
-        int r = ordered_pipeline<Payload>(tasks.size(), threads_per_gpu, window_per_gpu,
+        r = ordered_pipeline<Payload>(sg.tasks.size(), threads, window,
             [&](size_t k, Payload& p) -> int {
                 p.chunk = pool.get();
                 p.chunk->with_names = extra;
-                prep->bam.decode(tasks[k], *p.chunk);
+                prep->bam.decode(sg.tasks[k], *p.chunk);
                 return PJ_OK;
             },
             [&](size_t, Payload& p) -> int {
@@ -422,96 +509,46 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
                 return q;
             });
         if (r) { wait_ready(); return bail(r, g_err); }
-        out.decode_s = now_s() - td;
-        if ((r = wait_ready())) return bail(r, gpu_err);
-        gpu_thread.join();
-        if (genome_rc) return bail(genome_rc, genome_err);
+        out.decode_s += now_s() - td;
+        if (first) {
+            if ((r = wait_ready())) return bail(r, gpu_err);
+            gpu_thread.join();
+            if (genome_rc) return bail(genome_rc, genome_err);
+            first = false;
+        }
         const double tr = now_s();
         if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));
         const int64_t J = pj_shard_num_junctions(ctx);
-        out.rows.resize((size_t)J); out.stats.resize((size_t)T);
-        if ((r = pj_shard_fetch(ctx, out.rows.data(), J, out.stats.data(), T))) return bail(r, pj_last_error(ctx));
-        out.run_s = now_s() - tr;
-        int32_t nl = 0; pj_shard_timing(ctx, &out.gpu_ms, &nl); out.launches = nl;
-        if (extra) { out.ctx = ctx; ctx = nullptr; }                       // the extra metrics need every shard's context: destroyed after that phase
-    };
-    if (say) std::cout << "Finding junctions and calculating basic metrics:\n - Sharding " << T << " target sequences over " << n_gpus << " GPU(s)" << std::endl;
-    {
-        std::vector<std::thread> th;
-        for (int g = 1; g < n_gpus; g++) th.emplace_back(run_gpu, g);
-        run_gpu(0);
-        for (auto& t : th) t.join();
+        const size_t base = out.rows.size();
+        out.rows.resize(base + (size_t)J);
+        std::vector<pj_target_stats> st((size_t)T);
+        if ((r = pj_shard_fetch(ctx, out.rows.data() + base, J, st.data(), T))) return bail(r, pj_last_error(ctx));
+        for (int32_t t = 0; t < T; t++) {                              // a target may be spread over several segments
+            pj_target_stats& a = out.stats[(size_t)t]; const pj_target_stats& b = st[(size_t)t];
+            a.spliced_count += b.spliced_count; a.unspliced_count += b.unspliced_count; a.sum_query_lengths += b.sum_query_lengths;
+            a.min_query_length = std::min(a.min_query_length, b.min_query_length); a.max_query_length = std::max(a.max_query_length, b.max_query_length);
+        }
+        out.run_s += now_s() - tr;
+        float ms = 0; int32_t nl = 0; pj_shard_timing(ctx, &ms, &nl); out.gpu_ms += ms; out.launches += nl; out.n_segments++;
     }
-    struct CtxGuard { std::vector<GpuOut>& o; ~CtxGuard() { for (auto& x : o) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; } } } ctx_guard{outs};
-    for (auto& out : outs) if (out.rc) return fail(out.rc, out.err);
-    if (extra) {
-        // ---- calcExtraMetrics (junction_builder.cc:293-312) over the records resident on the GPUs ----
-        const double tx = now_s();
-        if (say) std::cout << "Calculating extra junction metrics:" << std::endl;
-        int32_t maxq_all = 0;
-        for (int g = 0; g < n_gpus; g++) for (int32_t t : shard[(size_t)g]) maxq_all = std::max(maxq_all, outs[g].stats[t].max_query_length);
-        if (!prep->indexed) for (auto& st : outs[0].stats) maxq_all = std::max(maxq_all, st.max_query_length);
-        // spliced read names of the whole file on every GPU (the reference's map spans the BAM, junction_builder.cc:179-186)
-        if (n_gpus > 1) {
-            std::vector<std::vector<uint64_t>> names((size_t)n_gpus);
-            for (int g = 0; g < n_gpus; g++) {
-                names[g].resize((size_t)std::max<int64_t>(pj_extra_num_spliced_names(outs[g].ctx), 0));
-                if ((rc = pj_extra_export_names(outs[g].ctx, names[g].data(), (int64_t)names[g].size()))) return fail(rc, pj_last_error(outs[g].ctx));
-            }
-            for (int g = 0; g < n_gpus; g++) for (int h = 0; h < n_gpus; h++)
-                if (h != g && (rc = pj_extra_import_names(outs[g].ctx, names[h].data(), (int64_t)names[h].size()))) return fail(rc, pj_last_error(outs[g].ctx));
-        }
-        {
-            std::vector<std::thread> th; std::vector<int> xr((size_t)n_gpus, PJ_OK);
-            auto one = [&](int g) { outs[g].extra.resize(outs[g].rows.size()); xr[g] = pj_extra_run(outs[g].ctx, maxq_all, outs[g].extra.data(), (int64_t)outs[g].extra.size()); };
-            for (int g = 1; g < n_gpus; g++) th.emplace_back(one, g);
-            one(0);
-            for (auto& t : th) t.join();
-            for (int g = 0; g < n_gpus; g++) if (xr[g]) return fail(xr[g], pj_last_error(outs[g].ctx));
-        }
-        // coverage: depth vector of the previous covered target (Q14), wherever that target lives
-        std::vector<int32_t> owner((size_t)T, 0);
-        for (int g = 0; g < n_gpus; g++) for (int32_t t : shard[(size_t)g]) owner[t] = g;
-        std::vector<uint8_t> covered((size_t)T, 0); std::vector<int32_t> src((size_t)T, -1);
-        for (int32_t t = 0; t < T; t++) {
-            int32_t cv = 0; uint32_t live = 0;
-            if ((rc = pj_extra_target_pileup(outs[owner[t]].ctx, t, &cv, &live))) return fail(rc, pj_last_error(outs[owner[t]].ctx));
-            covered[t] = (uint8_t)cv;
-            if (live >= 8000 && o->verbose) std::cerr << " - " << H.names[t] << ": up to " << live << " unspliced alignments on one position; htslib's 8000-read pileup cap is replayed there\n";
-        }
-        pj_extra_coverage_source(T, covered.data(), src.data());
-        for (int g = 0; g < n_gpus; g++) {
-            auto& rws = outs[g].rows;
-            for (size_t a = 0; a < rws.size();) {
-                size_t b = a; while (b < rws.size() && rws[b].tid == rws[a].tid) b++;
-                const int32_t t = rws[a].tid, d = src[t];
-                if (d >= 0) {
-                    std::vector<int32_t> st(b - a), en(b - a); std::vector<uint32_t> sums((b - a) * 4);
-                    for (size_t k = a; k < b; k++) { st[k - a] = rws[k].start; en[k - a] = rws[k].end; }
-                    pj_ctx* dc = outs[owner[d]].ctx;
-                    if ((rc = pj_extra_coverage(dc, d, (int64_t)(b - a), st.data(), en.data(), sums.data()))) return fail(rc, pj_last_error(dc));
-                    for (size_t k = a; k < b; k++) memcpy(outs[g].extra[k].cov_sum, &sums[(k - a) * 4], 16);
-                }
-                a = b;
-            }
-        }
-        for (auto& x : outs) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; }
-        R.t_extra_s = now_s() - tx;
+    if (extra) { out.ctx = ctx; ctx = nullptr; }                       // the extra metrics need every shard's context: destroyed after that phase
+}
+
+void merge_stats(std::vector<pj_target_stats>& into, const pj_target_stats* from, int32_t T) {
+    for (int32_t t = 0; t < T; t++) {
+        pj_target_stats& a = into[(size_t)t]; const pj_target_stats& b = from[t];
+        a.spliced_count += b.spliced_count; a.unspliced_count += b.unspliced_count; a.sum_query_lengths += b.sum_query_lengths;
+        a.min_query_length = std::min(a.min_query_length, b.min_query_length); a.max_query_length = std::max(a.max_query_length, b.max_query_length);
     }
-    // ---- gather (junction_builder.cc:249-283) ----
+}
+
+// A12/A13 + writers + strand report over the gathered rows (junction_builder.cc:249-290, junction_system.cc:250-383, 455-560)
+int finish_rows(const pjh_options* o, const pjio::BamHeader& H, std::vector<pj_junction>& rows, std::vector<pj_junction_extra>& xrows,
+                const std::vector<pj_target_stats>& stats, pjh_report& R) {
+    const bool say = !o->quiet; const bool extra = o->extra != 0 && xrows.size() == rows.size() && !rows.empty();
+    const int32_t T = (int32_t)H.names.size();
+    const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
     const double tf = now_s();
-    std::vector<pj_junction> rows; std::vector<pj_junction_extra> xrows;
-    std::vector<pj_target_stats> stats((size_t)T);
-    for (int32_t t = 0; t < T; t++) { stats[t] = pj_target_stats{0, 0, 0, INT32_MAX, 0}; }
-    for (int g = 0; g < n_gpus; g++) {
-        rows.insert(rows.end(), outs[g].rows.begin(), outs[g].rows.end());
-        xrows.insert(xrows.end(), outs[g].extra.begin(), outs[g].extra.end());
-        for (int32_t t : shard[(size_t)g]) stats[t] = outs[g].stats[t];
-        if (!prep->indexed) stats = outs[g].stats;
-        R.t_gpu_ms = std::max<double>(R.t_gpu_ms, outs[g].gpu_ms); R.n_kernel_launches += outs[g].launches;
-        R.t_genome_s = std::max(R.t_genome_s, outs[g].genome_s); R.t_decode_s = std::max(R.t_decode_s, outs[g].decode_s);
-        R.t_init_s = std::max(R.t_init_s, outs[g].init_s); R.t_run_s = std::max(R.t_run_s, outs[g].run_s); R.t_teardown_s = std::max(R.t_teardown_s, outs[g].teardown_s);
-    }
     uint64_t spliced = 0, unspliced = 0, sumq = 0; int32_t minq = INT32_MAX, maxq = 0;
     if (say) std::cout << " - All shards completed.\n - Combining results.\n\n" << std::left << std::setw(12) << "Sequence" << "\t" << std::right << std::setw(12) << "unspliced"
                        << "\t" << std::setw(12) << "spliced" << "\t" << std::setw(12) << "total" << std::endl;
@@ -523,16 +560,21 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
     }
     const uint64_t total = spliced + unspliced;
     const double mean_q = (double)sumq / (double)total;
-    if (extra) {     // bring rows and their extra columns into the final (tid, start, end) order together
+    bool sorted = true;
+    for (size_t i = 1; i < rows.size() && sorted; i++) {
+        const pj_junction &x = rows[i - 1], &y = rows[i];
+        sorted = x.tid != y.tid ? x.tid < y.tid : x.start != y.start ? x.start < y.start : x.end <= y.end;
+    }
+    if (!sorted || extra) {     // bring rows (and their extra columns) into the final (tid, start, end) order together
         std::vector<size_t> ord(rows.size()); for (size_t i = 0; i < ord.size(); i++) ord[i] = i;
-        std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+        if (!sorted) std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
             const pj_junction &x = rows[a], &y = rows[b];
             return x.tid != y.tid ? x.tid < y.tid : x.start != y.start ? x.start < y.start : x.end < y.end; });
-        std::vector<pj_junction> r2(rows.size()); std::vector<pj_junction_extra> x2(rows.size());
-        for (size_t i = 0; i < ord.size(); i++) { r2[i] = rows[ord[i]]; x2[i] = xrows[ord[i]]; }
-        rows.swap(r2); xrows.swap(x2);
-        pj_extra_finalize(xrows.data(), (int64_t)xrows.size());
+        std::vector<pj_junction> r2(rows.size()); for (size_t i = 0; i < ord.size(); i++) r2[i] = rows[ord[i]];
+        rows.swap(r2);
+        if (extra) { std::vector<pj_junction_extra> x2(rows.size()); for (size_t i = 0; i < ord.size(); i++) x2[i] = xrows[ord[i]]; xrows.swap(x2); pj_extra_finalize(xrows.data(), (int64_t)xrows.size()); }
     }
+    int rc;
     if ((rc = pj_junctions_finalize(rows.data(), (int64_t)rows.size(), mean_q))) return fail(rc, "finalize failed");
     R.t_finalize_s = now_s() - tf;
     if (say) {
@@ -582,7 +624,234 @@ int pjh_junc_run(const pjh_options* o, pjh_report* rep) {
             std::cerr << "Warning!  User input and portcullis disagree about the strandedness of the dataset\n" << std::endl;
     }
     R.n_junctions = (int64_t)rows.size(); R.n_spliced = spliced; R.n_unspliced = unspliced; R.mean_query_length = mean_q;
-    R.min_query_length = minq; R.max_query_length = maxq; R.t_total_s = now_s() - t0;
+    R.min_query_length = minq; R.max_query_length = maxq;
+    return PJ_OK;
+}
+
+// part < 0: the whole stage in this process (o->n_gpus GPUs, one host thread each).  part >= 0: only part `part` of `n_parts`
+// (one process per GPU, e.g. under torchrun): rows and per-target scalars go to `partial`, nothing is finalized or written.
+int junc_core(const pjh_options* o, int part, int n_parts_in, pjh_partial* partial, pjh_report* rep) {
+    if (!o || !o->prep_dir) return fail(PJ_EINVAL, "pjh_junc_run: no prep directory given");
+    pjh_report R; memset(&R, 0, sizeof R);
+    const double t0 = now_s();
+    const bool rank_mode = part >= 0;
+    const bool say = !o->quiet && !rank_mode;
+    const bool extra = o->extra != 0;      // junction_builder.cc:113-117 turns --separate on for --extra; here the metrics come from the records in HBM instead
+    if (rank_mode && extra) return fail(PJ_EINVAL, "pjh_junc_run_part: the --extra metrics exchange read names between contexts; run them in one process (pjh_junc_run)");
+    const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
+    if (!rank_mode) {   // output directory (junction_builder.cc:65-66, 86-91)
+        fs::path parent = fs::path(prefix).parent_path();
+        std::error_code ec;
+        if (!parent.empty() && !fs::exists(parent, ec) && !fs::create_directories(parent, ec))
+            return fail(PJ_EIO, "Could not create output directory at: " + parent.string());
+    }
+    pjh_prep* prep = nullptr;
+    int rc = pjh_prep_open(o->prep_dir, o->use_csi, &prep);
+    if (rc) return rc;
+    std::unique_ptr<pjh_prep> prep_guard(prep);
+    const pjio::BamHeader& H = prep->bam.header();
+    const int32_t T = (int32_t)H.names.size();
+    if (T == 0) return fail(PJ_EDATA, "BAM header declares no target sequences");
+    int n_parts = rank_mode ? std::max(1, n_parts_in) : std::max(1, o->n_gpus);
+    if (rank_mode && part >= n_parts) return fail(PJ_EINVAL, "pjh_junc_run_part: part out of range");
+    int threads = std::max(1, o->threads);
+    static const char* ORI[] = {"SE", "FR", "RF", "FF", "UNKNOWN"};
+    static const char* STR[] = {"UNSTRANDED", "FIRSTSTRAND", "SECONDSTRAND", "UNKNOWN"};
+    if (say) {
+        std::cout << "Settings:\n - BAM Strandedness: " << STR[std::min(std::max(o->strandedness, 0), 3)]
+                  << "\n - BAM Read Orientation: " << ORI[std::min(std::max(o->orientation, 0), 4)]
+                  << "\n - BAM Indexing mode: " << (o->use_csi ? "CSI" : "BAI")
+                  << "\n - Host decode threads: " << threads << "\n - GPUs: " << n_parts << "\n - Separate BAMs: " << (o->separate ? "true" : "false") << "\n\n";
+    }
+    if (o->separate && !rank_mode) {
+        // JunctionBuilder::separateBams (junction_builder.cc:152-226): host I/O only, before the junction pass like the reference
+        const double ts = now_s();
+        pjio::SeparateCounts sc;
+        const std::string un = prefix + ".unspliced.bam", sp = prefix + ".spliced.bam", um = prefix + ".unmapped.bam";
+        if (say) std::cout << "Splitting BAM:\n - Saving unspliced alignments to: \"" << un << "\"\n - Saving spliced alignments to: \"" << sp
+                           << "\"\n - Saving unmapped reads to: \"" << um << "\"\n - Processing BAM ..." << std::flush;
+        try { pjio::separate_bams(prep->bam, sp, un, um, o->use_csi != 0, threads, sc); }
+        catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+        R.t_separate_s = now_s() - ts;
+        if (say) std::cout << " done.\n - Found " << sc.spliced << " spliced alignments.\n - Found " << sc.unspliced << " unspliced alignments.\n - Found "
+                           << sc.unmapped << " unmapped reads.\n - Indexed the unspliced and spliced alignments (" << (o->use_csi ? "CSI" : "BAI") << ").\n = Wall time taken: "
+                           << std::fixed << std::setprecision(1) << R.t_separate_s << "s\n" << std::defaultfloat << std::setprecision(6) << std::endl;
+    }
+    // ---- work plan: contiguous record-balanced ranges cut at gaps (whole targets by LPT for --extra) ----
+    if (!prep->indexed) n_parts = rank_mode ? n_parts : 1;
+    const bool whole_targets = extra || env_u64("PJ_WHOLE_TARGETS", 0) != 0;
+    if (whole_targets && !rank_mode && n_parts > T) n_parts = T;
+    std::vector<Part> parts; int n_cuts = 0;
+    try { if ((rc = plan_parts(prep, n_parts, whole_targets, env_u64("PJ_SEG_RECORDS", 32u << 20), parts, &n_cuts))) return rc; }
+    catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    R.t_open_s = now_s() - t0;
+    R.n_gpus_used = n_parts;
+    if (say) {
+        size_t nseg = 0; for (auto& p : parts) nseg += p.size();
+        std::cout << "Finding junctions and calculating basic metrics:\n - Sharding " << T << " target sequences over " << n_parts << " GPU(s)";
+        if (!whole_targets) std::cout << " in " << nseg << " segment(s), " << n_cuts << " cut(s) inside a target";
+        std::cout << std::endl;
+    }
+    if (rank_mode) {
+        GpuOut out;
+        run_part(o, prep, parts[(size_t)part], o->gpu_ids ? o->gpu_ids[0] : 0, threads, false, out);
+        if (out.rc) return fail(out.rc, out.err);
+        partial->rows.swap(out.rows); partial->stats.swap(out.stats);
+        R.t_gpu_ms = out.gpu_ms; R.n_kernel_launches = out.launches; R.t_genome_s = out.genome_s; R.t_decode_s = out.decode_s; R.t_init_s = out.init_s;
+        R.t_run_s = out.run_s; R.t_teardown_s = out.teardown_s; R.n_junctions = (int64_t)partial->rows.size(); R.n_segments = out.n_segments; R.n_gap_cuts = n_cuts;
+        for (auto& st : partial->stats) { R.n_spliced += st.spliced_count; R.n_unspliced += st.unspliced_count; }
+        R.t_total_s = now_s() - t0;
+        partial->rep = R;
+        if (rep) *rep = R;
+        return PJ_OK;
+    }
+    std::vector<GpuOut> outs((size_t)n_parts);
+    const int threads_per_gpu = std::max(1, threads / n_parts);
+    {
+        std::vector<std::thread> th;
+        auto one = [&](int g) { run_part(o, prep, parts[(size_t)g], o->gpu_ids ? o->gpu_ids[g] : g, threads_per_gpu, extra, outs[(size_t)g]); };
+        for (int g = 1; g < n_parts; g++) th.emplace_back(one, g);
+        one(0);
+        for (auto& t : th) t.join();
+    }
+    const int n_gpus = n_parts;
+    struct CtxGuard { std::vector<GpuOut>& o; ~CtxGuard() { for (auto& x : o) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; } } } ctx_guard{outs};
+    for (auto& out : outs) if (out.rc) return fail(out.rc, out.err);
+    if (extra) {
+        // ---- calcExtraMetrics (junction_builder.cc:293-312) over the records resident on the GPUs ----
+        const double tx = now_s();
+        if (say) std::cout << "Calculating extra junction metrics:" << std::endl;
+        std::vector<int32_t> owner((size_t)T, 0);
+        for (int g = 0; g < n_gpus; g++) for (auto& sg : parts[(size_t)g]) for (int32_t t : sg.targets) owner[t] = g;
+        int32_t maxq_all = 0;
+        for (int g = 0; g < n_gpus; g++) for (auto& st : outs[g].stats) maxq_all = std::max(maxq_all, st.max_query_length);
+        for (int g = 0; g < n_gpus; g++) if (!outs[g].ctx) return fail(PJ_ESTATE, "--extra: a GPU has no records to work on; use fewer GPUs");
+        // spliced read names of the whole file on every GPU (the reference's map spans the BAM, junction_builder.cc:179-186)
+        if (n_gpus > 1) {
+            std::vector<std::vector<uint64_t>> names((size_t)n_gpus);
+            for (int g = 0; g < n_gpus; g++) {
+                names[g].resize((size_t)std::max<int64_t>(pj_extra_num_spliced_names(outs[g].ctx), 0));
+                if ((rc = pj_extra_export_names(outs[g].ctx, names[g].data(), (int64_t)names[g].size()))) return fail(rc, pj_last_error(outs[g].ctx));
+            }
+            for (int g = 0; g < n_gpus; g++) for (int h = 0; h < n_gpus; h++)
+                if (h != g && (rc = pj_extra_import_names(outs[g].ctx, names[h].data(), (int64_t)names[h].size()))) return fail(rc, pj_last_error(outs[g].ctx));
+        }
+        {
+            std::vector<std::thread> th; std::vector<int> xr((size_t)n_gpus, PJ_OK);
+            auto one = [&](int g) { outs[g].extra.resize(outs[g].rows.size()); xr[g] = pj_extra_run(outs[g].ctx, maxq_all, outs[g].extra.data(), (int64_t)outs[g].extra.size()); };
+            for (int g = 1; g < n_gpus; g++) th.emplace_back(one, g);
+            one(0);
+            for (auto& t : th) t.join();
+            for (int g = 0; g < n_gpus; g++) if (xr[g]) return fail(xr[g], pj_last_error(outs[g].ctx));
+        }
+        // coverage: depth vector of the previous covered target (Q14), wherever that target lives
+        std::vector<uint8_t> covered((size_t)T, 0); std::vector<int32_t> src((size_t)T, -1);
+        for (int32_t t = 0; t < T; t++) {
+            int32_t cv = 0; uint32_t live = 0;
+            if ((rc = pj_extra_target_pileup(outs[owner[t]].ctx, t, &cv, &live))) return fail(rc, pj_last_error(outs[owner[t]].ctx));
+            covered[t] = (uint8_t)cv;
+            if (live >= 8000 && o->verbose) std::cerr << " - " << H.names[t] << ": up to " << live << " unspliced alignments on one position; htslib's 8000-read pileup cap is replayed there\n";
+        }
+        pj_extra_coverage_source(T, covered.data(), src.data());
+        for (int g = 0; g < n_gpus; g++) {
+            auto& rws = outs[g].rows;
+            for (size_t a = 0; a < rws.size();) {
+                size_t b = a; while (b < rws.size() && rws[b].tid == rws[a].tid) b++;
+                const int32_t t = rws[a].tid, d = src[t];
+                if (d >= 0) {
+                    std::vector<int32_t> st(b - a), en(b - a); std::vector<uint32_t> sums((b - a) * 4);
+                    for (size_t k = a; k < b; k++) { st[k - a] = rws[k].start; en[k - a] = rws[k].end; }
+                    pj_ctx* dc = outs[owner[d]].ctx;
+                    if ((rc = pj_extra_coverage(dc, d, (int64_t)(b - a), st.data(), en.data(), sums.data()))) return fail(rc, pj_last_error(dc));
+                    for (size_t k = a; k < b; k++) memcpy(outs[g].extra[k].cov_sum, &sums[(k - a) * 4], 16);
+                }
+                a = b;
+            }
+        }
+        for (auto& x : outs) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; }
+        R.t_extra_s = now_s() - tx;
+    }
+    // ---- gather (junction_builder.cc:249-283) ----
+    std::vector<pj_junction> rows; std::vector<pj_junction_extra> xrows;
+    std::vector<pj_target_stats> stats((size_t)T, pj_target_stats{0, 0, 0, INT32_MAX, 0});
+    for (int g = 0; g < n_gpus; g++) {
+        rows.insert(rows.end(), outs[g].rows.begin(), outs[g].rows.end());
+        xrows.insert(xrows.end(), outs[g].extra.begin(), outs[g].extra.end());
+        merge_stats(stats, outs[g].stats.data(), T);
+        R.t_gpu_ms = std::max<double>(R.t_gpu_ms, outs[g].gpu_ms); R.n_kernel_launches += outs[g].launches; R.n_segments += outs[g].n_segments;
+        R.t_genome_s = std::max(R.t_genome_s, outs[g].genome_s); R.t_decode_s = std::max(R.t_decode_s, outs[g].decode_s);
+        R.t_init_s = std::max(R.t_init_s, outs[g].init_s); R.t_run_s = std::max(R.t_run_s, outs[g].run_s); R.t_teardown_s = std::max(R.t_teardown_s, outs[g].teardown_s);
+    }
+    R.n_gap_cuts = n_cuts;
+    if ((rc = finish_rows(o, H, rows, xrows, stats, R))) return rc;
+    R.t_total_s = now_s() - t0;
+    if (rep) *rep = R;
+    return PJ_OK;
+}
+
+} // namespace
+
+int pjh_junc_run(const pjh_options* o, pjh_report* rep) { return junc_core(o, -1, 0, nullptr, rep); }
+
+int pjh_plan_describe(const pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t* segments_per_part, int32_t* n_gap_cuts) {
+    if (!p || n_parts < 1 || !segments_per_part) return fail(PJ_EINVAL, "pjh_plan_describe: bad argument");
+    std::vector<Part> parts; int cuts = 0;
+    try { int rc = plan_parts(p, n_parts, whole_targets != 0, seg_records > 0 ? (uint64_t)seg_records : (32u << 20), parts, &cuts); if (rc) return rc; }
+    catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    for (int32_t g = 0; g < n_parts; g++) segments_per_part[g] = (int32_t)parts[(size_t)g].size();
+    if (n_gap_cuts) *n_gap_cuts = cuts;
+    return PJ_OK;
+}
+
+int pjh_plan_decode(pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t part, int32_t segment, int32_t threads, pj_batch* out) {
+    if (!p || n_parts < 1 || part < 0 || part >= n_parts || !out) return fail(PJ_EINVAL, "pjh_plan_decode: bad argument");
+    std::vector<Part> parts;
+    try { int rc = plan_parts(p, n_parts, whole_targets != 0, seg_records > 0 ? (uint64_t)seg_records : (32u << 20), parts, nullptr); if (rc) return rc; }
+    catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    if (segment < 0 || (size_t)segment >= parts[(size_t)part].size()) return fail(PJ_EINVAL, "pjh_plan_decode: segment out of range");
+    const Segment& sg = parts[(size_t)part][(size_t)segment];
+    p->decoded.clear(); p->decoded.with_names = p->want_names;
+    int rc = ordered_pipeline<ColumnarChunk>(sg.tasks.size(), std::max(1, threads), (size_t)std::max(1, threads) * 3 + 2,
+        [&](size_t k, ColumnarChunk& c) { c.with_names = p->want_names; p->bam.decode(sg.tasks[k], c); return PJ_OK; },
+        [&](size_t, ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
+    if (rc) return rc;
+    chunk_view(p->decoded, out);
+    return PJ_OK;
+}
+
+int pjh_junc_run_part(const pjh_options* o, int32_t part, int32_t n_parts, pjh_partial** out, pjh_report* rep) {
+    if (!out || part < 0 || n_parts < 1) return fail(PJ_EINVAL, "pjh_junc_run_part: bad argument");
+    *out = nullptr;
+    auto p = std::make_unique<pjh_partial>();
+    int rc = junc_core(o, part, n_parts, p.get(), rep);
+    if (rc) return rc;
+    *out = p.release();
+    return PJ_OK;
+}
+int64_t pjh_partial_rows(const pjh_partial* p, const pj_junction** rows) { if (!p) return -1; if (rows) *rows = p->rows.data(); return (int64_t)p->rows.size(); }
+int32_t pjh_partial_stats(const pjh_partial* p, const pj_target_stats** stats) { if (!p) return -1; if (stats) *stats = p->stats.data(); return (int32_t)p->stats.size(); }
+void pjh_partial_free(pjh_partial* p) { delete p; }
+
+int pjh_junc_finish(const pjh_options* o, pj_junction* rows_in, int64_t n_rows, const pj_target_stats* stats_in, int32_t n_targets, pjh_report* rep) {
+    if (!o || !o->prep_dir || (n_rows && !rows_in) || !stats_in) return fail(PJ_EINVAL, "pjh_junc_finish: bad argument");
+    const double t0 = now_s();
+    pjh_prep* prep = nullptr;
+    int rc = pjh_prep_open(o->prep_dir, o->use_csi, &prep);
+    if (rc) return rc;
+    std::unique_ptr<pjh_prep> guard(prep);
+    const pjio::BamHeader& H = prep->bam.header();
+    if ((int32_t)H.names.size() != n_targets) return fail(PJ_EINVAL, "pjh_junc_finish: stats must have one entry per target of the BAM header");
+    {
+        const std::string prefix = (o->output_prefix && *o->output_prefix) ? o->output_prefix : "portcullis";
+        fs::path parent = fs::path(prefix).parent_path(); std::error_code ec;
+        if (!parent.empty() && !fs::exists(parent, ec) && !fs::create_directories(parent, ec)) return fail(PJ_EIO, "Could not create output directory at: " + parent.string());
+    }
+    std::vector<pj_junction> rows(rows_in, rows_in + n_rows); std::vector<pj_junction_extra> xrows;
+    std::vector<pj_target_stats> stats(stats_in, stats_in + n_targets);
+    pjh_report R; memset(&R, 0, sizeof R);
+    if ((rc = finish_rows(o, H, rows, xrows, stats, R))) return rc;
+    if (n_rows) memcpy(rows_in, rows.data(), (size_t)n_rows * sizeof(pj_junction));
+    R.t_total_s = now_s() - t0;
     if (rep) *rep = R;
     return PJ_OK;
 }

@@ -40,6 +40,19 @@ class PrepDir:
         _check(self._lib.pjh_plan_shards(self._p, n_gpus, owner.ctypes.data), self._lib.pjh_last_error)
         return owner
 
+    def plan(self, n_parts, seg_records=0, whole_targets=False):
+        """(segments per part, gap cuts) of the range plan the junc driver executes for n_parts GPUs."""
+        seg = np.zeros(n_parts, dtype=np.int32)
+        cuts = C.c_int32()
+        _check(self._lib.pjh_plan_describe(self._p, n_parts, int(whole_targets), int(seg_records), seg.ctypes.data, C.byref(cuts)), self._lib.pjh_last_error)
+        return seg, cuts.value
+
+    def decode_segment(self, n_parts, part, segment, seg_records=0, threads=1, whole_targets=False):
+        """Owned numpy columns of one segment of the plan."""
+        b = L.PjBatch()
+        _check(self._lib.pjh_plan_decode(self._p, n_parts, int(whole_targets), int(seg_records), part, segment, threads, C.byref(b)), self._lib.pjh_last_error)
+        return from_batch(b)
+
     def decode(self, tid=-1, threads=1, names=False):
         """Decode one target (or all with tid=-1) into owned numpy columns; names=True adds the name_code column."""
         b = L.PjBatch()
@@ -218,6 +231,19 @@ class JuncGpu:
             self.close()
         except Exception:
             pass
+
+
+# layout of pj_target_stats (include/portcullis_junc.h)
+TARGET_STATS_DTYPE = np.dtype([("spliced", "<u8"), ("unspliced", "<u8"), ("sumq", "<u8"), ("minq", "<i4"), ("maxq", "<i4")])
+
+
+def merge_target_stats(parts):
+    """Per-target scalars of several parts -> one array (counts and sums added, min / max combined)."""
+    out = parts[0].copy()
+    for p in parts[1:]:
+        out["spliced"] += p["spliced"]; out["unspliced"] += p["unspliced"]; out["sumq"] += p["sumq"]
+        out["minq"] = np.minimum(out["minq"], p["minq"]); out["maxq"] = np.maximum(out["maxq"], p["maxq"])
+    return out
 
 
 def finalize(rows, mean_query_length):
@@ -415,6 +441,55 @@ class JunctionBuilder:
     def setOutputExonGFF(self, b): self.output_exon_gff = bool(b)
     def setOutputIntronGFF(self, b): self.output_intron_gff = bool(b)
     def setVerbose(self, b): self.verbose = bool(b)
+
+    def _options(self):
+        lib = L.load()
+        o = L.PjhOptions()
+        lib.pjh_options_default(C.byref(o))
+        keep = [os.fsencode(self.prep_dir), os.fsencode(self.output), self.source.encode()]
+        o.prep_dir, o.output_prefix, o.source = keep
+        o.threads, o.n_gpus = self.threads, self.gpus
+        if self.gpu_ids is not None:
+            ids = (C.c_int32 * len(self.gpu_ids))(*self.gpu_ids)
+            keep.append(ids)
+            o.gpu_ids = ids
+        o.orientation = L.ORIENT[self.orientation]
+        o.strandedness = L.STRANDEDNESS[self.strand_specific]
+        o.use_csi, o.exon_gff, o.intron_gff = int(self.use_csi), int(self.output_exon_gff), int(self.output_intron_gff)
+        o.verbose, o.separate, o.extra, o.quiet = int(self.verbose), int(self.separate), int(self.extra), int(self.quiet)
+        return lib, o, keep
+
+    def process_part(self, part, n_parts, device=0):
+        """One process per GPU (torchrun): decode and run part `part` of the n_parts-way work plan on CUDA device `device`.
+        Returns (rows, stats, report): rows in (tid, start, end) order, not yet finalized; stats one entry per target."""
+        saved = self.gpu_ids
+        self.gpu_ids = [int(device)]
+        try:
+            lib, o, keep = self._options()
+        finally:
+            self.gpu_ids = saved
+        h = C.c_void_p()
+        rep = L.PjhReport()
+        _check(lib.pjh_junc_run_part(C.byref(o), int(part), int(n_parts), C.byref(h), C.byref(rep)), lib.pjh_last_error)
+        try:
+            pr, ps = C.c_void_p(), C.c_void_p()
+            n = lib.pjh_partial_rows(h, C.byref(pr))
+            t = lib.pjh_partial_stats(h, C.byref(ps))
+            rows = np.frombuffer(C.string_at(pr, n * L.JUNCTION_DTYPE.itemsize), dtype=L.JUNCTION_DTYPE).copy() if n else np.zeros(0, dtype=L.JUNCTION_DTYPE)
+            stats = np.frombuffer(C.string_at(ps, t * C.sizeof(L.PjTargetStats)), dtype=TARGET_STATS_DTYPE).copy()
+        finally:
+            lib.pjh_partial_free(h)
+        return rows, stats, {f: getattr(rep, f) for f, _ in L.PjhReport._fields_}
+
+    def finish(self, rows, stats):
+        """Rows of all parts concatenated in part order + merged per-target stats -> A12/A13, output files, report."""
+        lib, o, keep = self._options()
+        rows = np.ascontiguousarray(rows, dtype=L.JUNCTION_DTYPE)
+        stats = np.ascontiguousarray(stats, dtype=TARGET_STATS_DTYPE)
+        rep = L.PjhReport()
+        _check(lib.pjh_junc_finish(C.byref(o), rows.ctypes.data, len(rows), stats.ctypes.data, len(stats), C.byref(rep)), lib.pjh_last_error)
+        self.report = {f: getattr(rep, f) for f, _ in L.PjhReport._fields_}
+        return rows, self.report
 
     def process(self):
         lib = L.load()
