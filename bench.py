@@ -1,20 +1,25 @@
 #!/usr/bin/env python3
-"""Benchmark of the junc hot path (BASELINE.json metric: spliced alignments / second through junc).
+"""Benchmark of the junc hot path (BASELINE.json metric: spliced alignments / second through junc at 1/2/4/8 B200).
 
-    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (torchrun launches one rank per GPU for N > 1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation (oracle/_ref)
+    python bench.py --preset c2|c4|c5 [--scale F]            # the other named shapes (committed under profiles/)
 
-Workload: config "c2" of BASELINE.json (synthetic 100 Mb genome = 10 targets x 10 Mb, 10 M 2x150 alignments), made on
-the box by portcullis_b200/bin/pjsynth.  With N ranks every rank owns its own 10 targets / 10 M alignments (weak
-scaling: targets are independent shards, no data-path collective).  One "step" = one pass of the hot path over the
-rank's whole shard.
+Workload (default): BASELINE config 3, the one the metric is quoted on — synthetic human-scale genome (24 targets with the
+GRCh38 lengths, 3.1 Gb) and 200 M 2x150 alignments, made on the box by portcullis_b200/bin/pjsynth; it fits one B200.
+The WHOLE job is sharded over the N ranks by the product's own range plan (pjh_plan_*: contiguous record-balanced
+ranges of the BAM, cut inside a target only where no spliced read spans) — strong scaling, no data-path collective.
+One "step" = one pass of the hot path over every rank's part of the job.
 
- value : spliced alignments / s, whole job, alignment columns and packed genome already resident in HBM
- e2e   : same metric through the C ABI (pj_shard_begin / pj_batch_submit / pj_shard_run / pj_shard_fetch) with the
-         columns in PINNED HOST memory: H2D of every column and D2H of the junction rows inside the timed region
- e2e_bam (extra): the JunctionBuilder front end from the BAM file (BGZF decode, genome load, GPU, writers), once
+ value   : spliced alignments / s, whole job: every rank's alignment columns and packed genome already resident in HBM,
+           pj_shard_run per step (CUDA-event device time reported beside the wall time)
+ e2e     : same metric through the C ABI (pj_shard_begin / pj_batch_submit / pj_shard_run / pj_shard_fetch) with the
+           decoded columns in pinned HOST memory: H2D of every column and D2H of the junction rows inside the timed region
+ e2e_bam : same metric from the BAM FILE to the output files (BGZF decode, genome load, GPU, gather on rank 0, A12/A13,
+           writers) — the like-for-like counterpart of the reference arm, which also starts at the BAM file
 """
 import argparse
+import hashlib
 import json
 import os
 import shutil
@@ -33,12 +38,29 @@ WORKDIR = os.environ.get("PJ_BENCH_DIR", "/tmp/pj_bench")
 METRIC = "spliced_alignments_per_sec"
 UNIT = "spliced alignments/s"
 
+WORKLOADS = {
+    "c2": "c2: synthetic 100 Mb genome (10 x 10 Mb), 10M 2x150 spliced alignments",
+    "c3": "c3: synthetic human-scale 3.1 Gb genome (24 targets, GRCh38 lengths), 200M 2x150 alignments, sharded over the GPUs",
+    "c4": "c4: deep skewed coverage, 8 hot loci with 1-4M reads per junction, heavy multi-mapping (100 Mb genome)",
+    "c5": "c5: long-read-style alignments (1-10 kb, up to 20 introns per read, indels near splice sites; 100 Mb genome)",
+}
+# fraction of the workload the CPU reference is timed on (about 10-30 s of CPU work per pass)
+CPU_SAMPLE = {"c2": 1.0, "c3": 0.05, "c4": 0.25, "c5": 0.1}
+
 
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+def config_of(args):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": "%s (pjsynth preset %s scale %g)" % (WORKLOADS[args.preset], args.preset, args.scale),
+            "preset": args.preset, "scale": args.scale,
+            "sharding": "whole job over the ranks: contiguous record-balanced ranges of the BAM, cut inside a target only where no spliced read spans; no collective",
+            "l2": "inputs (GBs of columns per GPU) are larger than the 126 MB L2"}
 
 
 def make_workload(preset, scale, seed, threads):
@@ -88,38 +110,45 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def algorithmic_bytes(cols, n_pairs, n_junc):
-    """SURVEY §8(d) formula, evaluated on the actual workload (see DESIGN.md 'Algorithmic bytes')."""
-    import numpy as np
-    n_rec = len(cols["pos"])
-    n_cig = len(cols["cigar"])
-    seq_bytes = len(cols["seq4"])                    # 4-bit SEQ of spliced records only
-    # CIGAR words of spliced records (the only ones the per-pair kernels touch)
-    has_seq = np.diff(cols["seq_off"].astype(np.int64)) > 0
-    n_cig_spliced = int(np.diff(cols["cigar_off"].astype(np.int64))[has_seq].sum())
-    fixed = 32 * n_rec + 4 * n_cig + seq_bytes
-    pair = 48 * n_pairs                               # 8-B key + 16-B payload, written once and read once
-    genome = seq_bytes // 2                           # SURVEY: 2-bit genome window of the anchor bases
-    rows = 326 * n_junc
-    total = fixed + pair + genome + rows
+def algorithmic_bytes(n_rec, n_cig, seq_bytes, n_cig_spliced, n_pairs, n_junc):
+    """SURVEY §8(d), literally: per record 32 B of fixed columns + 4 B per CIGAR op + the 4-bit SEQ of spliced records +
+    48 B per read-junction pair (a 24-B pair record = 8-B key + 16-B payload, written once and read once) + ceil(a/4) bytes
+    of 2-bit genome under the anchor bases (a = read bases of spliced records = 2 * seq_bytes); per junction a 320-B row + 6 B of
+    motif reads.  Sort traffic is NOT algorithmic.  Per stage: the bytes of that formula the stage has to move (24-B pair
+    records; the sort and the segmentation are charged one read + one write of what they permute / label, which the
+    pipeline total does not contain — they are overhead by §8(d))."""
+    genome = seq_bytes // 2
+    total = 32 * n_rec + 4 * n_cig + seq_bytes + 48 * n_pairs + genome + 326 * n_junc
     per_stage = {
-        # what each kernel must at least move (inputs read once, outputs written once)
-        # fused front end: every record column once, every CIGAR word once, one (key, PairA, PairB) per pair written
-        "scan_emit": (4 + 4 + 2 + 1 + 1 + 4 + 4 + 4 + 4) * n_rec + 4 * n_cig + (8 + 32) * n_pairs,
-        "scan_reads": (4 + 4 + 2 + 4 + 4) * n_rec + 4 * n_cig + 8 * n_rec,
-        "pair_offsets": 8 * n_rec,
-        "emit_pairs": (4 + 4 + 2 + 1 + 1 + 4 + 4 + 4 + 4 + 4) * n_rec + 4 * n_cig + (8 + 32) * n_pairs,
-        "radix_sort": 2 * 12 * n_pairs,              # one read + one write of (key,val): any extra pass is overhead
-        "segments": (8 + 4 + 4) * n_pairs,
-        "reduce1": (4 + 4 + 32) * n_pairs + 4 * n_pairs,
-        "entropy": 12 * n_pairs + 8 * n_junc,
-        # k_match: vals + jid + PairA/B + result per pair; CIGAR and SEQ of the read; the same number of genome bases
-        # from the 4-bit plane (SEQ and genome windows have equal length)
-        "match": (4 + 4 + 32 + 16) * n_pairs + 4 * n_cig_spliced + seq_bytes + seq_bytes,
-        "reduce2": (4 + 16) * n_pairs,
-        "finalize": (256 + 100 + 84) * n_junc,
+        "scan_emit": 32 * n_rec + 4 * n_cig + 24 * n_pairs,            # every column + CIGAR once, pair records written
+        "radix_sort": 2 * 24 * n_pairs,                                 # one permutation of the pair records (overhead stage)
+        "segments": (8 + 4) * n_pairs,                                  # key read, junction id written (overhead stage)
+        "reduce1": 24 * n_pairs + 64 * n_junc,
+        "entropy": 8 * n_pairs + 8 * n_junc,
+        "match": (24 + 16) * n_pairs + 4 * n_cig_spliced + seq_bytes + genome,   # pair record, result, CIGAR + SEQ of the read, 2-bit genome window
+        "reduce2": 16 * n_pairs + 100 * n_junc,
+        "finalize": 326 * n_junc,
     }
     return total, per_stage
+
+
+def md5_file(path, chunk=1 << 24):
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        while True:
+            b = f.read(chunk)
+            if not b:
+                break
+            h.update(b)
+    return h.hexdigest()
+
+
+def golden_md5(preset, scale):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize.json")) as f:
+            return json.load(f).get("%s@%g" % (preset, scale))
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -137,51 +166,71 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cores = max(1, host_cores() // world)
+    all_cores = host_cores()
+    cores = max(1, all_cores // world)
 
-    prep, meta = make_workload(args.preset, args.scale, args.seed + rank, cores)
-    t0 = time.time()
-    p = jb.PrepDir(prep)
-    cols = p.decode(-1, cores)
-    t_decode = time.time() - t0
-    n_rec = len(cols["pos"])
-    genomes = [p.genome(t) for t in range(len(p.names))]
-
-    # pinned host copies of every column (the e2e arm copies from these inside the timed region)
-    pinned = {}
-    keep = []
-    for k, v in cols.items():
-        t = torch.from_numpy(np.ascontiguousarray(v).view(np.uint8)).pin_memory() if v.size else torch.zeros(0, dtype=torch.uint8)
-        keep.append(t)
-        pinned[k] = t.numpy().view(v.dtype) if v.size else v
-    h2d_bytes = int(sum(v.nbytes for v in cols.values()))
-
-    g = jb.JuncGpu(local, "UNKNOWN")
-    g.set_targets(p.lengths)
-    t0 = time.time()
-    for t, s in enumerate(genomes):
-        g.set_genome(t, s)
-    g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"]))
-    g.submit(pinned)
-    nj = g.run()                                     # also finishes the genome upload
-    t_setup = time.time() - t0
-    rows, st = g.fetch()
-    n_spliced = int(st["spliced"].sum())
-    n_pairs = int(rows["nb_raw_aln"].astype(np.int64).sum())
-    d2h_bytes = int(rows.nbytes + 32 * len(p.lengths))
-
-    def sync_all():
+    def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    # ---------------- workload: made once per box, by rank 0 ----------------
+    t0 = time.time()
+    if rank == 0:
+        make_workload(args.preset, args.scale, args.seed, all_cores)
+    barrier()
+    prep, meta = make_workload(args.preset, args.scale, args.seed, all_cores)
+    t_gen = time.time() - t0
+
+    # ---------------- this rank's part of the job, decoded once into host memory ----------------
+    t0 = time.time()
+    p = jb.PrepDir(prep)
+    T = len(p.names)
+    HUGE = 1 << 40                                     # one segment per part: the whole part is resident for the `value` arm
+    seg, cuts = p.plan(world, HUGE)
+    if int(seg[rank]) > 0:
+        cols = p.decode_segment(world, rank, 0, HUGE, threads=cores, copy=False)     # views of the handle's arrays
+    else:                                              # less work than ranks (tiny inputs only): an empty shard
+        from portcullis_b200.columnar import COLUMNS
+        cols = {k: np.zeros(1 if k in ("cigar_off", "seq_off") else 0, dtype=dt) for k, dt in COLUMNS}
+    t_decode = time.time() - t0
+    n_rec = len(cols["pos"])
+    cudart = torch.cuda.cudart()
+    registered = []
+    for k, v in cols.items():                          # page-lock the decoded columns in place (no second copy of the shard)
+        if v.nbytes:
+            rc = cudart.cudaHostRegister(v.ctypes.data, v.nbytes, 0)
+            try:
+                ok = int(rc) == 0
+            except Exception:
+                ok = str(rc).lower().endswith("success")
+            if ok:
+                registered.append(v.ctypes.data)
+    h2d_bytes = int(sum(v.nbytes for v in cols.values()))
+    my_targets = [int(t) for t in np.unique(cols["tid"])] if n_rec else []
+
+    g = jb.JuncGpu(local, "UNKNOWN")
+    g.set_targets(p.lengths)
+    t0 = time.time()
+    for t in my_targets:
+        g.set_genome(t, p.genome(t))
+    g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"]))
+    g.submit(cols)
+    nj = g.run()                                       # also finishes the genome upload
+    t_setup = time.time() - t0
+    rows, st = g.fetch()
+    n_spliced = int(st["spliced"].sum())
+    n_pairs = int(rows["nb_raw_aln"].astype(np.int64).sum())
+    d2h_bytes = int(rows.nbytes + 32 * T)
+    del rows
 
     # ---------------- resident arm ----------------
     for _ in range(args.warmup):
         g.run()
     sampler = ClockSampler(local)
     sampler.start()
-    sync_all()
+    barrier()
     t0 = time.perf_counter()
     dev_ms, launches, stage_acc = 0.0, 0, {}
     for _ in range(args.steps):
@@ -191,41 +240,60 @@ def run_ours(args):
         launches += nl
         for name, v in stages:
             stage_acc[name] = stage_acc.get(name, 0.0) + v
-    sync_all()
+    barrier()
     wall = time.perf_counter() - t0
     # ---------------- e2e arm (host buffers through the C ABI) ----------------
-    # results land in pinned host memory too (what a C++ host would allocate with cudaMallocHost): a pageable destination makes
-    # the D2H copy go through the driver's bounce buffers and page-faults 29 MB per step
-    rows_pin_t = torch.empty(int(nj + 16) * L.JUNCTION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-    rows_pin = rows_pin_t.numpy().view(L.JUNCTION_DTYPE)
-    for _ in range(max(3, args.warmup)):          # the link and the arena need a few passes of their own on a fresh box
-        g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"])); g.submit(pinned); g.run(); g.fetch(rows_pin)
-    sync_all()
-    t1 = time.perf_counter()
-    for _ in range(args.steps):
-        g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"]))
-        g.submit(pinned)
-        g.run()
-        rows2, _ = g.fetch(rows_pin)
-    sync_all()
-    wall_e2e = time.perf_counter() - t1
+    wall_e2e = 0.0
+    e2e_steps = args.steps if not args.resident_only else 0
+    if e2e_steps:
+        # results land in pinned host memory too (what a C++ host would allocate with cudaMallocHost)
+        rows_pin_t = torch.empty(int(nj + 16) * L.JUNCTION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        rows_pin = rows_pin_t.numpy().view(L.JUNCTION_DTYPE)
+        for _ in range(3):                             # the link and the arena need a few passes of their own on a fresh box
+            g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"])); g.submit(cols); g.run(); g.fetch(rows_pin)
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"]))
+            g.submit(cols)
+            g.run()
+            rows2, _ = g.fetch(rows_pin)
+        barrier()
+        wall_e2e = time.perf_counter() - t1
+        assert len(rows2) == nj
     sampler.stop.set()
     sampler.join()
-    assert len(rows2) == nj
+
+    # per-rank workload numbers for the roofline (before the columns are released)
+    has_seq = np.diff(cols["seq_off"].astype(np.int64)) > 0 if n_rec else np.zeros(0, bool)
+    n_cig_spliced = int(np.diff(cols["cigar_off"].astype(np.int64))[has_seq].sum()) if n_rec else 0
+    n_cig, seq_bytes = len(cols["cigar"]), len(cols["seq4"])
+    g.close()
+    for ptr in registered:
+        cudart.cudaHostUnregister(ptr)
+    del cols
+    p.close()
+
+    # ---------------- e2e_bam arm: BAM file -> output files, the product's own driver ----------------
+    e2e_bam = None
+    if not args.no_bam and not args.resident_only:
+        e2e_bam = e2e_bam_leg(args, prep, rank, world, local, cores, barrier, np, jb)
 
     # max over ranks, sums of units
     tv = torch.tensor([wall, wall_e2e, dev_ms], dtype=torch.float64, device="cuda")
-    uv = torch.tensor([n_spliced, n_rec, h2d_bytes, d2h_bytes, launches], dtype=torch.float64, device="cuda")
+    uv = torch.tensor([n_spliced, n_rec, h2d_bytes, d2h_bytes, launches, n_pairs, nj], dtype=torch.float64, device="cuda")
+    per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+    per_rank[rank] = dev_ms / max(args.steps, 1)
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
         dist.all_reduce(uv, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     wall_m, wall_e2e_m, dev_ms_m = [float(x) for x in tv.tolist()]
-    tot_spliced, tot_rec, tot_h2d, tot_d2h, tot_launches = [float(x) for x in uv.tolist()]
+    tot_spliced, tot_rec, tot_h2d, tot_d2h, tot_launches, tot_pairs, tot_junc = [float(x) for x in uv.tolist()]
 
     if rank == 0:
-        total_alg, per_stage = algorithmic_bytes(cols, n_pairs, nj)
+        total_alg, per_stage = algorithmic_bytes(n_rec, n_cig, seq_bytes, n_cig_spliced, n_pairs, nj)     # rank 0's part
         stage_ms = {k: v / args.steps for k, v in stage_acc.items()}
-        dom = max((k for k in stage_ms if k in per_stage), key=lambda k: stage_ms[k])
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -233,114 +301,116 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = max((k for k in stage_ms if k in per_stage), key=lambda k: stage_ms[k])
         achieved = per_stage[dom] / (stage_ms[dom] * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")) as f:
                 tj = json.load(f)
-                traffic = tj.get(dom)
+                traffic = tj.get(args.preset, {}).get(dom) if isinstance(tj.get(args.preset), dict) else None
         except Exception:
             pass
+        stage_table = {k: {"ms": round(stage_ms[k], 4), "alg_bytes": int(per_stage[k]), "gbs": round(per_stage[k] / (stage_ms[k] * 1e-3) / 1e9, 1),
+                           "frac": round(per_stage[k] / (stage_ms[k] * 1e-3) / 1e9 / peak, 4)} for k in stage_ms if k in per_stage and stage_ms[k] > 0}
+        pipe_ms = dev_ms / args.steps
+        cfg = config_of(args)
         line = {
             "metric": METRIC, "value": tot_spliced * args.steps / wall_m, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": wall_m / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "c2: synthetic 100 Mb genome (10 x 10 Mb), 10M 2x150 alignments per GPU (pjsynth preset %s scale %g)" % (args.preset, args.scale),
-                       "records_per_gpu": n_rec, "spliced_per_gpu": n_spliced, "read_junction_pairs_per_gpu": n_pairs,
-                       "junctions_per_gpu": int(nj), "l2": "inputs (%.2f GB of columns per GPU) are larger than the 126 MB L2" % (h2d_bytes / 1e9),
-                       "sharding": "targets -> ranks, independent shards, no collective"},
+            "warmup": args.warmup, "ms_per_step": wall_m / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
+            "workload_stats": {"records": int(tot_rec), "spliced": int(tot_spliced), "read_junction_pairs": int(tot_pairs), "junctions": int(tot_junc),
+                               "records_rank0": n_rec, "gap_cuts_in_plan": int(cuts), "host_cores": all_cores, "decode_threads_per_rank": cores},
             "device_ms_per_step": dev_ms_m / args.steps,
+            "device_ms_per_step_by_rank": [round(float(x), 4) for x in per_rank.tolist()],
             "all_alignments_per_sec": tot_rec * args.steps / wall_m,
             "gpu_launches": int(tot_launches),
             "clocks": sampler.summary(),
-            "e2e": {"value": tot_spliced * args.steps / wall_e2e_m, "unit": UNIT, "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
-                    "ms_per_step": wall_e2e_m / args.steps * 1e3},
+            "e2e": ({"value": tot_spliced * e2e_steps / wall_e2e_m, "unit": UNIT, "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
+                     "ms_per_step": wall_e2e_m / e2e_steps * 1e3,
+                     "what": "C ABI with the decoded columns in pinned host memory (pj_shard_begin/pj_batch_submit/pj_shard_run/pj_shard_fetch)"} if e2e_steps else None),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": per_stage[dom], "avg_launch_ms": stage_ms[dom],
-                         "pipeline_algorithmic_bytes": total_alg, "pipeline_achieved_gbs": total_alg / (dev_ms_m / args.steps * 1e-3) / 1e9,
-                         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()}},
-            "setup": {"decode_s": round(t_decode, 3), "genome_and_first_run_s": round(t_setup, 3), "host_threads": cores},
+                         "bytes_model": "SURVEY 8(d) literally: 32 B/record + 4 B/CIGAR op + 4-bit SEQ of spliced records + 48 B/pair (24-B record written once, read once) + ceil(a/4) B of 2-bit genome + 326 B/junction",
+                         "pipeline_algorithmic_bytes": total_alg, "pipeline_ms": pipe_ms, "pipeline_achieved_gbs": total_alg / (pipe_ms * 1e-3) / 1e9,
+                         "pipeline_frac": total_alg / (pipe_ms * 1e-3) / 1e9 / peak, "scope": "rank 0's part of the job",
+                         "stages": stage_table},
+            "setup": {"generate_s": round(t_gen, 1), "decode_s": round(t_decode, 3), "genome_and_first_run_s": round(t_setup, 3), "host_threads": cores},
         }
-        if world == 1 and not args.no_bam:          # before the CPU baseline: the reference's runs leave the host busy with write-back
-            line["e2e_bam"] = e2e_bam(prep, cores, n_spliced)
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, cores)
-        if world == 1 and args.extra:
-            g.close()
-            line["extra_metrics"] = extra_leg(p, local, genomes, cores, max(2, min(args.steps, 5)))
+        if e2e_bam is not None:
+            line["e2e_bam"] = e2e_bam
+        if world == 1 and not args.no_cpu_baseline and not args.resident_only:
+            line["cpu_baseline"] = cpu_baseline(args, all_cores)
+            if e2e_bam is not None and line["cpu_baseline"].get("value"):
+                e2e_bam["ratio_vs_cpu_baseline"] = round(e2e_bam["value"] / line["cpu_baseline"]["value"], 2)
+                e2e_bam["ratio_note"] = "both arms start at the BAM file and end with the output files written; the CPU arm runs on a bounded sample (see cpu_baseline.sample)"
         print(json.dumps(line))
-    g.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def extra_leg(p, device, genomes, cores, steps):
-    """The `--extra` metrics on the bench workload: device time of pj_extra_run (CUDA events inside the
-    library) and of the whole junc + extra step, inputs resident in pinned host memory."""
-    import numpy as np
-    from portcullis_b200 import junction_builder as jb
-    cols = p.decode(-1, cores, names=True)
-    n = len(cols["pos"])
-    g = jb.JuncGpu(device, "UNKNOWN", extra=True)
-    g.set_targets(p.lengths)
-    for t, s in enumerate(genomes):
-        g.set_genome(t, s)
-    acc, stage_acc, junc_ms, cov_s = 0.0, {}, 0.0, 0.0
-    for it in range(steps + 1):
-        g.shard_begin(n, len(cols["cigar"]), len(cols["seq4"]))
-        g.submit(cols)
-        g.run()
-        rows, st = g.fetch()
-        x = g.extra_run(int(st["maxq"].max()))
-        t0 = time.perf_counter()
-        covered = np.array([g.target_pileup(t)[0] for t in range(len(p.lengths))], dtype=np.uint8)
-        src = jb.coverage_source(covered)
-        for t in np.unique(rows["tid"]):
-            if src[t] >= 0:
-                sel = np.nonzero(rows["tid"] == t)[0]
-                x["cov_sum"][sel] = g.coverage(src[t], rows["start"][sel], rows["end"][sel])
-        dt = time.perf_counter() - t0
-        if it == 0:
-            continue                                   # warm-up
-        ms, nl, stages = g.extra_timing()
-        acc += ms
-        cov_s += dt
-        junc_ms += g.timing()[0]
-        for name, v in stages:
-            stage_acc[name] = stage_acc.get(name, 0.0) + v
-    g.close()
-    x = jb.extra_finalize(x)
-    return {"pj_extra_run_device_ms": round(acc / steps, 3), "launches": nl, "stage_ms": {k: round(v / steps, 4) for k, v in stage_acc.items()},
-            "coverage_queries_wall_ms": round(cov_s / steps * 1e3, 3), "junc_pipeline_device_ms_in_extra_mode": round(junc_ms / steps, 3),
-            "junctions": int(len(rows)), "unspliced_flank_total": int(x["up_aln"].astype(np.int64).sum() + x["down_aln"].astype(np.int64).sum()),
-            "steps": steps}
-
-
-def e2e_bam(prep, cores, n_spliced):
-    """Whole front end from the BAM file: BGZF decode + genome load + GPU + finalize + writers, each run with a fresh library
-    context.  One untimed run first (page cache, allocator pools), then three timed ones; the median is reported."""
-    from portcullis_b200 import junction_builder as jb
-    out = os.path.join(WORKDIR, "out_e2e", "p")
+def e2e_bam_leg(args, prep, rank, world, local, cores, barrier, np, jb):
+    """BAM file -> output files through the product's driver.  N = 1: JunctionBuilder.process() (the call a user makes).
+    N > 1: one process per GPU — every rank decodes and runs its part of the range plan (process_part), drops its rows into
+    /dev/shm, rank 0 concatenates them in part order and runs finish() (A12/A13 + writers).  The only synchronisation is
+    the barrier; no collective touches the data.  One untimed pass first, then three timed ones (median)."""
+    out = os.path.join(WORKDIR, "out_e2e_%s" % args.preset, "p")
+    shm = "/dev/shm/pj_bench_rows_%d" % os.getuid()
+    if rank == 0:
+        shutil.rmtree(shm, ignore_errors=True)
+        os.makedirs(shm, exist_ok=True)
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+    barrier()
     runs = []
-    for it in range(4):
+    reps = []
+    n_spliced = 0
+    for it in range(args.bam_passes + 1):
         b = jb.JunctionBuilder(prep, out)
         b.setThreads(cores)
+        barrier()
         t0 = time.perf_counter()
-        rep = b.process()
+        if world == 1:
+            rep = b.process()
+            n_spliced = rep["n_spliced"]
+        else:
+            rows, stats, rep = b.process_part(rank, world, device=local)
+            rows.tofile(os.path.join(shm, "rows_%d.bin" % rank))
+            stats.tofile(os.path.join(shm, "stats_%d.bin" % rank))
+            barrier()
+            if rank == 0:
+                from portcullis_b200 import _lib as L
+                allrows = np.concatenate([np.fromfile(os.path.join(shm, "rows_%d.bin" % r), dtype=L.JUNCTION_DTYPE) for r in range(world)])
+                allstats = jb.merge_target_stats([np.fromfile(os.path.join(shm, "stats_%d.bin" % r), dtype=jb.TARGET_STATS_DTYPE) for r in range(world)])
+                _, frep = b.finish(allrows, allstats)
+                n_spliced = frep["n_spliced"]
+                rep = dict(rep, t_finalize_s=frep["t_finalize_s"], t_write_s=frep["t_write_s"], n_junctions=frep["n_junctions"])
+        barrier()
         dt = time.perf_counter() - t0
         if it:
-            runs.append((dt, rep))
-    runs.sort(key=lambda r: r[0])
-    dt, rep = runs[len(runs) // 2]
-    return {"value": n_spliced / dt, "unit": UNIT, "seconds": round(dt, 3), "seconds_all": [round(r[0], 3) for r in runs], "host_threads": cores,
-            "breakdown_s": {k: round(rep[k], 4) for k in ("t_open_s", "t_genome_s", "t_decode_s", "t_finalize_s", "t_write_s")},
-            "gpu_pipeline_ms": round(rep["t_gpu_ms"], 3)}
+            runs.append(dt)
+            reps.append(rep)
+    if rank != 0:
+        return None
+    order = sorted(range(len(runs)), key=lambda i: runs[i])
+    mid = order[len(order) // 2]
+    dt, rep = runs[mid], reps[mid]
+    res = {"value": n_spliced / dt, "unit": UNIT, "seconds": round(dt, 3), "seconds_all": [round(r, 3) for r in runs], "host_threads_per_rank": cores,
+           "breakdown_s_rank0": {k: round(rep[k], 4) for k in ("t_open_s", "t_init_s", "t_genome_s", "t_decode_s", "t_run_s", "t_finalize_s", "t_write_s")},
+           "gpu_pipeline_ms_rank0": round(rep["t_gpu_ms"], 3), "segments_rank0": rep.get("n_segments"), "junctions": rep.get("n_junctions"),
+           "what": "BAM file -> junctions.tab/.bed written; BGZF decode on the host cores, %d GPU(s)" % world}
+    gold = golden_md5(args.preset, args.scale)
+    if gold and args.seed == 0:
+        got = md5_file(out + ".junctions.tab")
+        res["parity"] = {"junctions_tab_md5": got, "equals_reference_md5": got == gold["md5"]["junctions.tab"],
+                         "reference": "unmodified reference junc on the same prep directory (tests/golden/fullsize.json)"}
+    shutil.rmtree(shm, ignore_errors=True)
+    return res
 
 
-def run_reference_once(prep, threads):
+def run_reference_once(prep, threads, tag="r"):
     """The unmodified reference `junc` (oracle/_ref/portcullis_ref) on the box's host cores; returns (seconds, spliced)."""
-    out = os.path.join(WORKDIR, "out_ref", "r")
+    out = os.path.join(WORKDIR, "out_ref", tag)
     t0 = time.perf_counter()
     pr = subprocess.run([REF_BIN, "junc", "-t", str(threads), "-o", out, prep], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     dt = time.perf_counter() - t0
@@ -356,7 +426,8 @@ def run_reference_once(prep, threads):
 
 
 def cpu_sample(args, cores):
-    scale = args.scale * args.cpu_sample_frac
+    frac = args.cpu_sample_frac if args.cpu_sample_frac > 0 else CPU_SAMPLE.get(args.preset, 0.1)
+    scale = args.scale * frac
     prep, meta = make_workload(args.preset, scale, args.seed, cores)
     threads = min(cores, meta["n_targets"])                              # the reference caps threads at #targets
     return prep, meta, threads, scale
@@ -370,7 +441,7 @@ def cpu_baseline(args, cores):
     best = min((run_reference_once(prep, threads) for _ in range(2)), key=lambda r: r[0])
     dt, spliced, find_s = best
     return {"value": spliced / dt, "unit": UNIT, "cores": threads, "kind": "reference",
-            "sample": "pjsynth preset %s scale %g (%d alignments, %d spliced): unmodified reference `junc -t %d`, whole-run wall %.2fs (findJunctions %.1fs), best of 2 warm"
+            "sample": "pjsynth preset %s scale %g (%d alignments, %d spliced): unmodified reference `junc -t %d` from the BAM file, whole-run wall %.2fs (findJunctions %.1fs), best of 2 warm"
                       % (args.preset, scale, meta["n_records"], spliced, threads, dt, find_s or -1)}
 
 
@@ -393,14 +464,13 @@ def run_reference(args):
         spliced += sp
     wall = time.perf_counter() - t0
     v = spliced / wall
+    sample = ("bounded sample of the workload: pjsynth preset %s scale %g (%d alignments, %d spliced) per step through the unmodified reference `junc -t %d`, BAM file -> output files, on %d host cores"
+              % (args.preset, scale, meta["n_records"], meta["n_spliced"], threads, cores))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": "c2: synthetic 100 Mb genome (10 x 10 Mb), 10M 2x150 alignments per GPU (pjsynth preset %s scale %g)" % (args.preset, args.scale),
-                   "step": "bounded sample: preset %s scale %g (%d alignments) through the unmodified reference `junc -t %d` from the BAM file"
-                           % (args.preset, scale, meta["n_records"], threads)},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": "pjsynth preset %s scale %g, %d alignments per step" % (args.preset, scale, meta["n_records"])},
+        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": config_of(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -412,13 +482,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--preset", default="c2")
+    ap.add_argument("--preset", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-sample-frac", type=float, default=1.0, help="fraction of the workload the CPU reference is timed on (1.0 = the whole c2 workload, about 4.5 s per pass on 10 host threads)")
+    ap.add_argument("--cpu-sample-frac", type=float, default=0.0, help="fraction of the workload the CPU reference is timed on (0 = per-preset default: about 10-30 s of CPU work)")
+    ap.add_argument("--bam-passes", type=int, default=3, help="timed passes of the BAM-file arm (after one untimed pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bam", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also time the `--extra` metrics phase (pj_extra_run + coverage) on the same workload; adds an extra_metrics object")
+    ap.add_argument("--resident-only", action="store_true", help="only the resident arm (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

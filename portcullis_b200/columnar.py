@@ -34,15 +34,17 @@ def batch_struct(cols):
     return b, keep
 
 
-def from_batch(b):
-    """Copy a PjBatch (e.g. filled by pjh_prep_decode) into owned numpy columns."""
+def from_batch(b, copy=True):
+    """Copy a PjBatch (e.g. filled by pjh_prep_decode) into owned numpy columns.  copy=False returns views of the library's
+    own arrays instead (valid until the next decode / close of the prep handle): no second copy of a multi-GB shard."""
     n = b.n_records
     out = {}
 
     def arr(ptr, count, dt):
         if not ptr or count == 0:
             return np.zeros(count, dtype=dt)
-        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,)).copy()
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,))
+        return a.copy() if copy else a
 
     for name, dt in COLUMNS:
         if name in ("cigar", "seq4"):

@@ -47,11 +47,11 @@ class PrepDir:
         _check(self._lib.pjh_plan_describe(self._p, n_parts, int(whole_targets), int(seg_records), seg.ctypes.data, C.byref(cuts)), self._lib.pjh_last_error)
         return seg, cuts.value
 
-    def decode_segment(self, n_parts, part, segment, seg_records=0, threads=1, whole_targets=False):
-        """Owned numpy columns of one segment of the plan."""
+    def decode_segment(self, n_parts, part, segment, seg_records=0, threads=1, whole_targets=False, copy=True):
+        """Numpy columns of one segment of the plan (copy=False: views of the handle's arrays, valid until its next decode)."""
         b = L.PjBatch()
         _check(self._lib.pjh_plan_decode(self._p, n_parts, int(whole_targets), int(seg_records), part, segment, threads, C.byref(b)), self._lib.pjh_last_error)
-        return from_batch(b)
+        return from_batch(b, copy=copy)
 
     def decode(self, tid=-1, threads=1, names=False):
         """Decode one target (or all with tid=-1) into owned numpy columns; names=True adds the name_code column."""

@@ -36,10 +36,7 @@ def synth(tmpdir, preset, scale, seed=0):
                                                       ("c2", 0.05, None, 2), ("c3", 0.004, "RF", 4)])
 def test_presets_reproduce_reference_files(tmp_path, preset, scale, orient, gpus):
     import torch
-    if not os.path.exists(ob.REF_BIN):
-        pytest.skip("oracle/_ref/portcullis_ref not built")
-    if torch.cuda.device_count() < gpus:
-        pytest.skip("needs %d GPUs" % gpus)
+    assert os.path.exists(ob.REF_BIN), "oracle/_ref/portcullis_ref not built (run __graft_entry__.build() where /root/reference exists)"
     prep, meta = synth(tmp_path, preset, scale)
     ref_prefix = os.path.join(str(tmp_path), "ref", "r")
     refrun.run_reference(prep, ref_prefix, threads=min(8, meta["n_targets"]), orientation=orient)
@@ -47,6 +44,9 @@ def test_presets_reproduce_reference_files(tmp_path, preset, scale, orient, gpus
     b = jb.JunctionBuilder(prep, out)
     b.setThreads(8)
     b.setGpus(gpus)
+    # the multi-GPU driver (one host thread + one library context per part) runs on however many devices the box has:
+    # with fewer devices than parts several contexts share a device, so this case is never skipped
+    b.gpu_ids = [g % torch.cuda.device_count() for g in range(gpus)]
     b.setOutputExonGFF(True)
     b.setOutputIntronGFF(True)
     if orient:
@@ -91,3 +91,88 @@ def test_full_c2_properties(tmp_path):
     w = rows["nb_raw_aln"].astype(np.float64)
     canon = float((w * (rows["canonical_ss"] == ord("C"))).sum() / w.sum())
     assert canon > 0.9, canon                                                      # planted GT..AG / CT..AC carry most reads
+
+
+@pytest.mark.parametrize("preset,scale,world,seg_records", [("c2", 0.05, 2, 0), ("c3", 0.004, 8, 20000), ("c4", 0.05, 4, 0), ("c5", 0.03, 3, 2000)])
+def test_one_process_per_gpu_mode_reproduces_reference_files(tmp_path, preset, scale, world, seg_records, monkeypatch):
+    """pjh_junc_run_part per rank + pjh_junc_finish on rank 0 (the torchrun path of bench.py), here with the ranks run one
+    after the other on however many devices exist; small segments force several shards per rank and cuts inside targets."""
+    import torch
+    assert os.path.exists(ob.REF_BIN)
+    if seg_records:
+        monkeypatch.setenv("PJ_SEG_RECORDS", str(seg_records))
+    prep, meta = synth(tmp_path, preset, scale)
+    ref_prefix = os.path.join(str(tmp_path), "ref", "r")
+    refrun.run_reference(prep, ref_prefix, threads=min(8, meta["n_targets"]))
+    out = os.path.join(str(tmp_path), "ours", "o")
+    b = jb.JunctionBuilder(prep, out)
+    b.setThreads(4)
+    b.setOutputExonGFF(True)
+    b.setOutputIntronGFF(True)
+    parts, stats, nseg, cuts = [], [], 0, 0
+    for r in range(world):
+        rows, st, rep = b.process_part(r, world, device=r % torch.cuda.device_count())
+        parts.append(rows); stats.append(st); nseg += rep["n_segments"]; cuts = rep["n_gap_cuts"]
+    assert nseg >= world or meta["n_records"] < 1000
+    if seg_records:
+        assert cuts > 0
+    allrows = np.concatenate(parts)
+    order = np.lexsort((allrows["end"], allrows["start"], allrows["tid"]))
+    assert np.array_equal(order, np.arange(len(allrows))), "parts do not concatenate in (tid, start, end) order"
+    _, rep = b.finish(allrows, jb.merge_target_stats(stats))
+    assert rep["n_spliced"] == meta["n_spliced"] and rep["n_spliced"] + rep["n_unspliced"] == meta["n_records"]
+    assert_tab_equal(out + ".junctions.tab", ref_prefix + ".junctions.tab")
+    assert filecmp.cmp(out + ".junctions.bed", ref_prefix + ".junctions.bed", shallow=False)
+    assert filecmp.cmp(out + ".junctions.intron.gff3", ref_prefix + ".junctions.intron.gff3", shallow=False)
+    assert_exon_gff_equal(out + ".junctions.exon.gff3", ref_prefix + ".junctions.exon.gff3")
+
+
+def _md5(path):
+    import hashlib
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 24), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("preset,gpus", [("c2", 1), ("c4", 2), ("c5", 1), ("c3", 4)])
+def test_full_size_presets_match_reference_md5(tmp_path, preset, gpus):
+    """BASELINE configs 2-5 at their NAMED sizes (c3: 3.1 Gb / 200 M alignments) against the md5 sums of the files the unmodified
+    reference wrote for the same prep directory (tests/golden/fullsize.json, made once on CPU by tests/golden/make_fullsize.py).
+    The integer / string columns must match byte for byte; the whole file is expected to as well (entropy is the only device
+    fp64 sum and is formed in the reference's order)."""
+    import hashlib
+    import torch
+    from compare import FP_COLS
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize.json")))["%s@1" % preset]
+    d = os.path.join(str(tmp_path), preset)
+    subprocess.check_call([PJSYNTH, "--preset", preset, "--scale", "1", "--out", d], stderr=subprocess.DEVNULL)
+    assert json.load(open(os.path.join(d, "synth.json"))) == gold["synth"]
+    assert _md5(os.path.join(d, "portcullis.sorted.alignments.bam")) == gold["input_md5"]["portcullis.sorted.alignments.bam"], "pjsynth is not reproducible on this box"
+    out = os.path.join(str(tmp_path), "out", "o")
+    b = jb.JunctionBuilder(d, out)
+    b.setThreads(os.cpu_count() or 8)
+    b.setGpus(gpus)
+    b.gpu_ids = [g % torch.cuda.device_count() for g in range(gpus)]
+    b.setOutputExonGFF(True)
+    b.setOutputIntronGFF(True)
+    rep = b.process()
+    assert rep["n_junctions"] == gold["junctions"]
+    assert _md5(out + ".junctions.bed") == gold["md5"]["junctions.bed"]
+    assert _md5(out + ".junctions.intron.gff3") == gold["md5"]["junctions.intron.gff3"]
+    h = hashlib.md5()
+    ent_sum = 0.0
+    with open(out + ".junctions.tab") as f:
+        for ln, line in enumerate(f):
+            c = line.rstrip("\n").split("\t")
+            if ln >= 1 and len(c) > 40:
+                ent_sum += float(c[32])
+                for k in FP_COLS:
+                    if k < len(c):
+                        c[k] = "#"
+            h.update(("\t".join(c) + "\n").encode())
+    assert h.hexdigest() == gold["tab_nofp_md5"], "integer / string columns of junctions.tab differ from the reference"
+    assert abs(ent_sum - gold["entropy_sum"]) <= 1e-6 * gold["entropy_sum"]
+    assert _md5(out + ".junctions.tab") == gold["md5"]["junctions.tab"], "junctions.tab differs from the reference in a floating-point column"
+    assert _md5(out + ".junctions.exon.gff3") == gold["md5"]["junctions.exon.gff3"]
