@@ -216,6 +216,27 @@ void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint
 constexpr int SE_THREADS = 256;
 constexpr unsigned long long SE_PREFIX = 1ull << 63, SE_AGG = 1ull << 62, SE_MASK = (1ull << 62) - 1ull;
 
+// Decoupled look-back by a whole warp: lane l polls the status word of tile (first - l), 32 predecessors per probe, and the warp
+// adds the aggregates down to the nearest inclusive prefix.  (One polling thread pays a dependent global round trip per
+// predecessor; with a few hundred tiles in flight that chain was most of the time of the single-pass scans.)
+// Must be called by all 32 lanes of one warp; every lane returns the exclusive prefix of `tile`.
+__device__ __forceinline__ unsigned long long lookback_warp(const unsigned long long* status, int64_t tile, int lane) {
+    unsigned long long excl = 0;
+    for (int64_t first = tile - 1; first >= 0; first -= 32) {
+        const int64_t t = first - lane;
+        unsigned long long v = SE_PREFIX;                              // before tile 0: an inclusive prefix of 0
+        if (t >= 0) { const volatile unsigned long long* sp = status + t; do { v = *sp; } while ((v >> 62) == 0ull); }
+        const uint32_t pm = __ballot_sync(FULL, (v & SE_PREFIX) != 0ull);
+        const int stop = pm ? __ffs(pm) - 1 : 31;                      // nearest tile that already knows its inclusive prefix
+        unsigned long long add = lane <= stop ? (v & SE_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) add += __shfl_xor_sync(FULL, add, o);
+        excl += add;
+        if (pm) break;
+    }
+    return excl;
+}
+
 __global__ void __launch_bounds__(256) k_prescan_cigar(const uint32_t* __restrict__ cigar, uint64_t n, uint32_t* __restrict__ max_nlen,
                                                         unsigned long long* __restrict__ n_nops) {
     uint32_t m = 0, k = 0;
@@ -237,8 +258,7 @@ void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen,
 template <int SE_ITEMS>
 __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
                                                            const uint32_t* __restrict__ max_nlen, int32_t orientation, TargetAcc T,
-                                                           uint64_t* __restrict__ keys, PairA* __restrict__ pa, PairB* __restrict__ pb,
-                                                           PairC* __restrict__ pc, PairD* __restrict__ pd,
+                                                           uint64_t* __restrict__ keys, PairRec* __restrict__ pr,
                                                            unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket,
                                                            uint32_t* __restrict__ total_pairs, uint32_t pair_cap, uint32_t* __restrict__ err) {
     __shared__ uint32_t s_tile, s_tot;
@@ -322,24 +342,20 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
     uint32_t off[SE_ITEMS]; uint32_t carry = 0;
 #pragma unroll
     for (int r = 0; r < SE_ITEMS; r++) { const uint32_t ex = block_excl_scan(cnt[r], &s_tot); off[r] = carry + ex; carry += s_tot; }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {                                            // warp 0: publish the tile aggregate, look back, publish the prefix
         volatile unsigned long long* st = status + tile;
         unsigned long long excl = 0;
-        if (tile == 0) *st = (unsigned long long)carry | SE_PREFIX;
+        if (tile == 0) { if (lane == 0) *st = (unsigned long long)carry | SE_PREFIX; }
         else {
-            *st = (unsigned long long)carry | SE_AGG;
-            __threadfence();
-            for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
-                volatile const unsigned long long* sp = status + t;
-                unsigned long long v;
-                do { v = *sp; } while ((v >> 62) == 0ull);
-                excl += v & SE_MASK;
-                if (v & SE_PREFIX) break;
-            }
-            *st = ((excl + carry) & SE_MASK) | SE_PREFIX;
+            if (lane == 0) { *st = (unsigned long long)carry | SE_AGG; __threadfence(); }
+            __syncwarp();
+            excl = lookback_warp(status, (int64_t)tile, lane);
+            if (lane == 0) *st = ((excl + carry) & SE_MASK) | SE_PREFIX;
         }
-        s_base = excl;
-        if (base + SE_TILE >= R.n) *total_pairs = (uint32_t)min(excl + carry, 0xffffffffull);   // the last tile knows the total
+        if (lane == 0) {
+            s_base = excl;
+            if (base + SE_TILE >= R.n) *total_pairs = (uint32_t)min(excl + carry, 0xffffffffull);   // the last tile knows the total
+        }
     }
     if (threadIdx.x < 4) {   // flush the block's per-target partials
         const int32_t t = tid_first + (int32_t)threadIdx.x;
@@ -419,10 +435,11 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
                     }
                 } else { up = kN - a_eq; down = nN - 1u - kN; }
                 keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
-                pa[slot] = PairA{(uint32_t)i, lStart, rendj, pos};
-                pb[slot] = PairB{rend[r], bits, (up << 16) | (down & 0xffffu), start};
-                pc[slot] = PairC{so * 2 + (uint64_t)ds, cig0 + (uint32_t)c, qpos};
-                pd[slot] = PairD{(int32_t)qs, lq, (uint32_t)c | ((uint32_t)(n - 1 - c) << 16), 0u};
+                PairRec* const o = pr + slot;
+                o->a = PairA{(uint32_t)i, lStart, rendj, pos};
+                o->b = PairB{rend[r], bits, (up << 16) | (down & 0xffffu), start};
+                o->c = PairC{so * 2 + (uint64_t)ds, cig0 + (uint32_t)c, qpos};
+                o->d = PairD{(int32_t)qs, lq, (uint32_t)c | ((uint32_t)(n - 1 - c) << 16), 0u};
                 slot++;
                 kN++; p += L; a_eq = L > 0 ? 1u : a_eq + 1u;
                 if (j < n) { lStart = rStart; lEndExc = rStart; } else break;
@@ -438,16 +455,16 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
 static int se_items() { static int v = [] { const char* e = getenv("PJ_SE_ITEMS"); int k = e ? atoi(e) : 4; return (k == 1 || k == 2 || k == 4) ? k : 4; }(); return v; }
 uint32_t se_num_tiles(int64_t n) { const int64_t tile = (int64_t)SE_THREADS * se_items(); return (uint32_t)((n + tile - 1) / tile); }
 void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
-                      const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, PairC* pc, PairD* pd, unsigned long long* status, uint32_t* ticket,
+                      const TargetAcc& T, uint64_t* keys, PairRec* pr, unsigned long long* status, uint32_t* ticket,
                       uint32_t* total_pairs, uint32_t pair_cap, uint32_t* err, cudaStream_t st) {
     if (R.n <= 0) return;
     const uint32_t nt = se_num_tiles(R.n);
     cudaMemsetAsync(status, 0, (size_t)nt * sizeof(unsigned long long), st);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     switch (se_items()) {
-    case 1: k_scan_emit<1><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, pc, pd, status, ticket, total_pairs, pair_cap, err); break;
-    case 4: k_scan_emit<4><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, pc, pd, status, ticket, total_pairs, pair_cap, err); break;
-    default: k_scan_emit<2><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pa, pb, pc, pd, status, ticket, total_pairs, pair_cap, err); break;
+    case 1: k_scan_emit<1><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err); break;
+    case 4: k_scan_emit<4><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err); break;
+    default: k_scan_emit<2><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err); break;
     }
 }
 
@@ -741,25 +758,22 @@ __global__ void __launch_bounds__(FS_THREADS) k_flag_scan(uint32_t n, F f, unsig
 #pragma unroll
     for (int k = 0; k < FS_ITEMS; k++) { fl[k] = (i0 + k < n) ? f.flag(i0 + k) : 0u; sum += fl[k]; }
     uint32_t ex = block_excl_scan(sum, &s_tot);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {                                            // warp 0: publish the tile aggregate, look back, publish the prefix
+        const int lane = threadIdx.x;
         const uint32_t tot = s_tot;
         volatile unsigned long long* st = status + tile;
         unsigned long long excl = 0;
-        if (tile == 0) *st = (unsigned long long)tot | SE_PREFIX;
+        if (tile == 0) { if (lane == 0) *st = (unsigned long long)tot | SE_PREFIX; }
         else {
-            *st = (unsigned long long)tot | SE_AGG;
-            __threadfence();
-            for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
-                volatile const unsigned long long* sp = status + t;
-                unsigned long long v;
-                do { v = *sp; } while ((v >> 62) == 0ull);
-                excl += v & SE_MASK;
-                if (v & SE_PREFIX) break;
-            }
-            *st = ((excl + tot) & SE_MASK) | SE_PREFIX;
+            if (lane == 0) { *st = (unsigned long long)tot | SE_AGG; __threadfence(); }
+            __syncwarp();
+            excl = lookback_warp(status, (int64_t)tile, lane);
+            if (lane == 0) *st = ((excl + tot) & SE_MASK) | SE_PREFIX;
         }
-        s_base = (uint32_t)excl;
-        if ((uint64_t)(tile + 1) * FS_TILE >= n) { *total_out = (uint32_t)(excl + tot); f.finish(n, (uint32_t)(excl + tot)); }
+        if (lane == 0) {
+            s_base = (uint32_t)excl;
+            if ((uint64_t)(tile + 1) * FS_TILE >= n) { *total_out = (uint32_t)(excl + tot); f.finish(n, (uint32_t)(excl + tot)); }
+        }
     }
     __syncthreads();
     ex += s_base;
@@ -824,24 +838,29 @@ struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { r
 // k_reduce1: stage-1 reductions per junction (SURVEY §8 "reduction algebra" stage 1)
 // ================================================================================================
 __global__ void __launch_bounds__(512) k_reduce1(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
-                                                  const PairA* __restrict__ pa, const PairB* __restrict__ pb, int32_t ppcheck,
-                                                  JuncAcc A, uint32_t* __restrict__ eflag) {
+                                                  const PairRec* __restrict__ pr, int32_t ppcheck,
+                                                  JuncAcc A, uint32_t* __restrict__ eflag, uint32_t* __restrict__ inv) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool ok = i < n;
     uint32_t j = 0xffffffffu;
     uint32_t c0 = 0, c1 = 0, c2 = 0;                 // packed 6-bit counters
     int32_t lmin = INT32_MAX, rmax = INT32_MIN; uint32_t anc = 0, up = 0, down = 0;
+    PairA a = PairA{0u, 0, 0, 0}; PairB b = PairB{0, 0u, 0u, 0};
+    uint32_t idx = 0;
+    if (ok) { j = jid[i]; idx = vals[i]; a = pr[idx].a; b = pr[idx].b; inv[idx] = i; }   // inv: emit slot -> sorted position (k_match runs in emit order)
+    // (pos, read_end) of the previous pair in sorted order: from the neighbouring lane; only lane 0 has to gather it
+    const uint32_t jprev = __shfl_up_sync(FULL, j, 1);
+    int32_t ppos = __shfl_up_sync(FULL, a.pos, 1), pend = __shfl_up_sync(FULL, b.read_end, 1);
     if (ok) {
-        j = jid[i];
-        const uint32_t idx = vals[i];
-        const PairA a = pa[idx]; const PairB b = pb[idx];
-        const bool has_prev = i > 0 && jid[i - 1] == j;
+        bool has_prev;
+        if (lane == 0) {
+            has_prev = i > 0 && jid[i - 1] == j;
+            if (has_prev) { const uint32_t ip = vals[i - 1]; ppos = pr[ip].a.pos; pend = pr[ip].b.read_end; }
+        } else has_prev = jprev == j;
         const bool last = (i + 1 == n) || (jid[i + 1] != j);
         bool dist = true, newpos = false;
         if (has_prev) {
-            const uint32_t ip = vals[i - 1];
-            const int32_t ppos = pa[ip].pos, pend = pb[ip].read_end;
             dist = (a.pos != ppos) || (b.read_end != pend);
             newpos = a.pos != ppos;
         }
@@ -926,27 +945,27 @@ __global__ void __launch_bounds__(512) k_reduce1(uint32_t n, const uint32_t* __r
 
 // Decodes the junction coordinates from the key of each segment head and initialises the accumulators.
 __global__ void __launch_bounds__(256) k_junc_init(uint32_t n_junc, const uint32_t* __restrict__ seg_start, const uint64_t* __restrict__ keys,
-                                                    const uint32_t* __restrict__ vals, const PairA* __restrict__ pa, const PairB* __restrict__ pb,
+                                                    const uint32_t* __restrict__ vals, const PairRec* __restrict__ pr,
                                                     const int32_t* __restrict__ read_tid, int32_t len_bits, JuncAcc A) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_junc) return;
     const uint32_t s = seg_start[j];
     const uint64_t key = keys[s];
     const uint32_t idx = vals[s];
-    const int32_t start = pb[idx].start;
+    const int32_t start = pr[idx].b.start;
     const int32_t size = (int32_t)(key & ((1ull << len_bits) - 1ull));
-    A.tid[j] = read_tid[pa[idx].rid];
+    A.tid[j] = read_tid[pr[idx].a.rid];
     A.start[j] = start; A.end[j] = start + size - 1;
     A.left[j] = INT32_MAX; A.right[j] = INT32_MIN;
 }
 
-void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairA* pa, const PairB* pb,
+void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairRec* pr,
                       const int32_t* read_tid, int32_t len_bits, const JuncAcc& A, cudaStream_t st) {
-    if (n_junc) k_junc_init<<<(n_junc + 255) / 256, 256, 0, st>>>(n_junc, seg_start, keys, vals, pa, pb, read_tid, len_bits, A);
+    if (n_junc) k_junc_init<<<(n_junc + 255) / 256, 256, 0, st>>>(n_junc, seg_start, keys, vals, pr, read_tid, len_bits, A);
 }
-void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, int32_t ppcheck,
-                    const JuncAcc& A, uint32_t* eflag, cudaStream_t st) {
-    if (n) k_reduce1<<<(n + 511) / 512, 512, 0, st>>>(n, vals, jid, pa, pb, ppcheck, A, eflag);
+void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, int32_t ppcheck,
+                    const JuncAcc& A, uint32_t* eflag, uint32_t* inv, cudaStream_t st) {
+    if (n) k_reduce1<<<(n + 511) / 512, 512, 0, st>>>(n, vals, jid, pr, ppcheck, A, eflag, inv);
 }
 
 // ================================================================================================
@@ -1046,6 +1065,10 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, 
     uint32_t o = 0; int32_t tl = 0;
     uint64_t gi0 = 0; uint32_t Bh = 0, Bl = 0;                                        // big-endian halves of SEQ word k (G == 1: carried)
     const uint64_t* gw = nullptr; const uint2* qw = nullptr;
+    // Chunks of one side are visited in increasing column order, so the LAST mismatch of the left anchor lies in the last chunk with
+    // a mismatch and the FIRST mismatch of the right anchor in the first one: remember that chunk's mask and column base, resolve the
+    // position once after the loop.  No divergent branch per chunk (with 25 lanes and 0.5 % substitutions it was taken almost always).
+    uint64_t lm = 0, fm = 0; int32_t lc = 0, fc = 0;
     for (;;) {
         if (k >= nchunk) {                                                            // next block of this lane
             if (++bi >= nq) break;
@@ -1089,15 +1112,16 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, 
                 d = (d & ~(0xfull << (60 - 4 * t))) | ((mm ? 0xfull : 0ull) << (60 - 4 * t));
             }
         }
-        if (d) {
-            uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;
-            const uint32_t cnt = (uint32_t)__popcll(m);
-            // max / min, not assignment: insertions and deletions update the same fields during the walk, before this drain
-            if (side == 0) { r.mism_l += cnt; r.last_left = max(r.last_left, sbase + c0 + 15 - ((__ffsll((long long)d) - 1) >> 2)); }
-            else           { r.mism_r += cnt; r.first_right = min(r.first_right, sbase + c0 + (__clzll((long long)d) >> 2)); }
-        }
+        uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;                            // one bit per mismatching column
+        const uint32_t cnt = (uint32_t)__popcll(m);
+        const bool nz = m != 0ull;
+        if (side == 0) { r.mism_l += cnt; if (nz) { lm = m; lc = sbase + c0; } }
+        else           { r.mism_r += cnt; if (nz && fm == 0ull) { fm = m; fc = sbase + c0; } }
         k += G;
     }
+    // max / min, not assignment: insertions and deletions update the same fields during the walk, before this drain
+    if (lm) r.last_left = max(r.last_left, lc + 15 - ((__ffsll((long long)lm) - 1) >> 2));
+    if (fm) r.first_right = min(r.first_right, fc + (__clzll((long long)fm) >> 2));
 }
 
 // One pass over the CIGAR serves both anchor windows: the left walk of the reference stops at the first op it rejects,
@@ -1190,20 +1214,24 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
 }
 
 template <int G>
-__global__ void __launch_bounds__(256, PJ_MATCH_CTAS) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
-                                                const PairA* __restrict__ pa, const PairB* __restrict__ pb,
-                                                const PairC* __restrict__ pc, const PairD* __restrict__ pd,
+__global__ void __launch_bounds__(256, PJ_MATCH_CTAS) k_match(uint32_t n, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ jid,
+                                                const PairRec* __restrict__ pr,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
     __shared__ MatchQueue Q;
     __shared__ MatchMasks M;
     init_match_masks(M);
     __syncthreads();                                                 // the only block-wide barrier: before any thread leaves
-    const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+    // Pairs are visited in EMIT order (= BAM order), not in junction order: the pair records are read coalesced, the SEQ / CIGAR streams
+    // are walked almost sequentially (neighbouring threads hold neighbouring reads, and the N ops of one long read sit in one warp and
+    // share its lines in L1), and the genome windows of neighbouring reads overlap.  Only the junction id (one 4-byte gather into an
+    // L2-resident array) and the result (one 16-byte scatter to the sorted position) are random.  In junction order every pair paid a
+    // 64-byte record gather plus random SEQ and CIGAR lines behind it, three dependent round trips deep.
+    const uint32_t idx = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
     const int gl = threadIdx.x % G;
-    if (i >= n) return;                                              // whole groups leave together
+    if (idx >= n) return;                                            // whole groups leave together
+    const uint32_t i = inv[idx];                                     // sorted position of this pair
+    const PairA a = pr[idx].a; const PairB b = pr[idx].b; const PairC c = pr[idx].c; const PairD d = pr[idx].d;
     const uint32_t j = jid[i];
-    const uint32_t idx = vals[i];
-    const PairA a = pa[idx]; const PairB b = pb[idx]; const PairC c = pc[idx]; const PairD d = pd[idx];
     // The walk below is a chain of dependent loads (CIGAR ops -> SEQ words / genome words).  The lines it will need are
     // known already: ask for them now so that they arrive while the CIGAR is being walked.
     if (G == 1) {
@@ -1249,21 +1277,21 @@ __global__ void __launch_bounds__(256, PJ_MATCH_CTAS) k_match(uint32_t n, const 
 }
 
 template <int G>
-static void launch_match_g(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const PairC* pc, const PairD* pd, const Reads& R, const Genome& Gn,
+static void launch_match_g(uint32_t n, const uint32_t* inv, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
                            const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     const uint64_t threads = (uint64_t)n * G;
-    k_match<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err);
+    k_match<G><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, inv, jid, pr, R, Gn, A, pm, err);
 }
-void launch_match(uint32_t n, int group, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const PairC* pc, const PairD* pd, const Reads& R, const Genome& Gn,
+void launch_match(uint32_t n, int group, const uint32_t* inv, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     if (!n) return;
     switch (group) {
-    case 1: launch_match_g<1>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
-    case 2: launch_match_g<2>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
-    case 4: launch_match_g<4>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
-    case 8: launch_match_g<8>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
-    case 16: launch_match_g<16>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
-    default: launch_match_g<32>(n, vals, jid, pa, pb, pc, pd, R, Gn, A, pm, err, st); break;
+    case 1: launch_match_g<1>(n, inv, jid, pr, R, Gn, A, pm, err, st); break;
+    case 2: launch_match_g<2>(n, inv, jid, pr, R, Gn, A, pm, err, st); break;
+    case 4: launch_match_g<4>(n, inv, jid, pr, R, Gn, A, pm, err, st); break;
+    case 8: launch_match_g<8>(n, inv, jid, pr, R, Gn, A, pm, err, st); break;
+    case 16: launch_match_g<16>(n, inv, jid, pr, R, Gn, A, pm, err, st); break;
+    default: launch_match_g<32>(n, inv, jid, pr, R, Gn, A, pm, err, st); break;
     }
 }
 

@@ -120,6 +120,9 @@ struct __align__(16) PairB { int32_t read_end; uint32_t bits; uint32_t updown; i
 struct __align__(16) PairC { uint64_t seq_nib0; uint32_t cig_abs; int32_t qpos_n; };   // first nibble of the clipped query in the SEQ stream;
                                                                                        // index of this N op in the CIGAR stream; query offset at it
 struct __align__(16) PairD { int32_t qsize; int32_t lq; uint32_t nops; uint32_t pad; }; // clipped query length (Q3); l_qseq; ops before | ops after << 16
+// The four 16-byte parts of one pair live in ONE 64-byte, 64-byte-aligned record: a gather touches two full 32-byte sectors of
+// one line instead of four half-used sectors in four arrays; the stage-1 reduction needs only the first sector (a, b).
+struct __align__(64) PairRec { PairA a; PairB b; PairC c; PairD d; };
 enum : uint32_t { PB_R1 = 1u << 0, PB_REV = 1u << 1, PB_MS = 1u << 2, PB_UM = 1u << 3, PB_BPP = 1u << 4, PB_PPP = 1u << 5,
                   PB_XSP = 1u << 6, PB_XSN = 1u << 7 };
 

@@ -31,7 +31,7 @@ void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint
 void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen, unsigned long long* n_nops, int n_sm, cudaStream_t st);
 uint32_t se_num_tiles(int64_t n);
 void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, const uint64_t* toff, const uint32_t* max_nlen, int32_t orientation,
-                      const TargetAcc& T, uint64_t* keys, PairA* pa, PairB* pb, PairC* pc, PairD* pd, unsigned long long* status, uint32_t* ticket,
+                      const TargetAcc& T, uint64_t* keys, PairRec* pr, unsigned long long* status, uint32_t* ticket,
                       uint32_t* total_pairs, uint32_t pair_cap, uint32_t* err, cudaStream_t st);
 uint32_t rs_num_blocks(uint32_t n);
 int launch_radix_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
@@ -44,13 +44,13 @@ void launch_segment(const uint64_t* keys, uint32_t n, uint32_t* jid, uint32_t* s
 void launch_entropy_index(uint32_t n, const uint32_t* eflag, uint32_t* eoff, uint32_t* epos, uint32_t* total_dev, unsigned long long* scratch, cudaStream_t st);
 void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st);
 void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint32_t* jid, uint32_t* seg_start, uint32_t n_junc, cudaStream_t st);
-void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairA* pa, const PairB* pb,
+void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairRec* pr,
                       const int32_t* read_tid, int32_t len_bits, const JuncAcc& A, cudaStream_t st);
-void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, int32_t ppcheck,
-                    const JuncAcc& A, uint32_t* eflag, cudaStream_t st);
+void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, int32_t ppcheck,
+                    const JuncAcc& A, uint32_t* eflag, uint32_t* inv, cudaStream_t st);
 void launch_entropy_compact(uint32_t n, const uint32_t* eflag, const uint32_t* eoff, uint32_t* epos, cudaStream_t st);
 void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32_t* eoff, const uint32_t* epos, double* entropy, cudaStream_t st);
-void launch_match(uint32_t n, int group, const uint32_t* vals, const uint32_t* jid, const PairA* pa, const PairB* pb, const PairC* pc, const PairD* pd, const Reads& R, const Genome& G,
+void launch_match(uint32_t n, int group, const uint32_t* inv, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& G,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st);
 void launch_reduce2(uint32_t n, const uint32_t* jid, const uint4* pm, const JuncAcc& A, cudaStream_t st);
 void launch_finalize(uint32_t n_junc, const uint32_t* seg_start, const JuncAcc& A, const Genome& G, const double* entropy,

@@ -416,7 +416,7 @@ int pj_shard_run(pj_ctx* c) {
     uint32_t* d_J = c->d_scalars + 3; uint32_t* d_E = c->d_scalars + 4; uint32_t* d_tmp_total = c->d_scalars + 5;
 
     uint64_t *keys_a = nullptr, *keys_b = nullptr; uint32_t *vals_a = nullptr, *vals_b = nullptr, *counts = nullptr, *scan_tmp2 = nullptr;
-    PairA* pa = nullptr; PairB* pb = nullptr; PairC* pc = nullptr; PairD* pd = nullptr; unsigned long long* se_status = nullptr;
+    PairRec* pr = nullptr; unsigned long long* se_status = nullptr;
     uint32_t P = 0; int len_bits = 1, key_bits = 2;
     const int gbits = std::max(1, bit_length(c->h_toff[T]));
     auto alloc_pairs = [&](uint32_t cap) -> int {
@@ -426,8 +426,7 @@ int pj_shard_run(pj_ctx* c) {
         CU(c, cudaMallocAsync(&vals_a, n * 4, st)); CU(c, cudaMallocAsync(&vals_b, n * 4, st));
         CU(c, cudaMallocAsync(&counts, (size_t)256 * nb * 4, st));
         CU(c, cudaMallocAsync(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, n)) * 4, st));
-        CU(c, cudaMallocAsync(&pa, n * sizeof(PairA), st)); CU(c, cudaMallocAsync(&pb, n * sizeof(PairB), st));
-        CU(c, cudaMallocAsync(&pc, n * sizeof(PairC), st)); CU(c, cudaMallocAsync(&pd, n * sizeof(PairD), st));
+        CU(c, cudaMallocAsync(&pr, n * sizeof(PairRec), st));
         return PJ_OK;
     };
     {
@@ -442,7 +441,7 @@ int pj_shard_run(pj_ctx* c) {
         if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
         if ((rc = alloc_pairs((uint32_t)acc[1]))) return rc;
         CU(c, cudaMallocAsync(&se_status, (size_t)std::max<uint32_t>(se_num_tiles(R), 1) * sizeof(unsigned long long), st));
-        launch_scan_emit(Rd, c->d_tlen, T, c->d_toff, reinterpret_cast<const uint32_t*>(c->d_shard_acc), c->orientation, TA, keys_a, pa, pb, pc, pd,
+        launch_scan_emit(Rd, c->d_tlen, T, c->d_toff, reinterpret_cast<const uint32_t*>(c->d_shard_acc), c->orientation, TA, keys_a, pr,
                          se_status, c->d_scalars + 6, d_P, (uint32_t)acc[1], d_err, st); c->n_launches++;
         mark(c, "scan_emit");
         CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -495,9 +494,10 @@ int pj_shard_run(pj_ctx* c) {
                   col(5), col(6), col(7), col(8), col(9), col(10), col(11), col(12), col(13), col(14), col(15), col(16), col(17), col(18), col(19),
                   col(20), col(21), col(22), col(23), jadhist};
         CU(c, cudaMemsetAsync(A.firstmm, 0xff, (size_t)J * 4, st));
-        launch_junc_init(J, seg_start, keys, vals, pa, pb, c->tid.p, len_bits, A, st); c->n_launches++;
-        launch_reduce1(P, vals, jid, pa, pb, (c->orientation == PJ_ORIENT_FR || c->orientation == PJ_ORIENT_RF || c->orientation == PJ_ORIENT_FF) ? 1 : 0,
-                       A, spare_u32, st); c->n_launches++;
+        launch_junc_init(J, seg_start, keys, vals, pr, c->tid.p, len_bits, A, st); c->n_launches++;
+        uint32_t* inv = nullptr; CU(c, cudaMallocAsync(&inv, (size_t)P * 4, st));   // emit slot -> sorted position (written by k_reduce1, read by k_match)
+        launch_reduce1(P, vals, jid, pr, (c->orientation == PJ_ORIENT_FR || c->orientation == PJ_ORIENT_RF || c->orientation == PJ_ORIENT_FF) ? 1 : 0,
+                       A, spare_u32, inv, st); c->n_launches++;
         mark(c, "reduce1");
         uint64_t* free_keys = which ? keys_a : keys_b;          // the non-result key buffer: 8 bytes per pair, reused below
         uint32_t* eoff = reinterpret_cast<uint32_t*>(free_keys);
@@ -517,7 +517,7 @@ int pj_shard_run(pj_ctx* c) {
                 const double bases_per_pair = 2.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
                 group = bases_per_pair <= 400 ? 1 : bases_per_pair <= 1200 ? 4 : bases_per_pair <= 4000 ? 8 : 32;
             }
-            launch_match(P, group, vals, jid, pa, pb, pc, pd, Rd, G, A, pm, d_err, st); c->n_launches++;
+            launch_match(P, group, inv, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
         }
         mark(c, "match");
         launch_reduce2(P, jid, pm, A, st); c->n_launches++;
@@ -525,11 +525,11 @@ int pj_shard_run(pj_ctx* c) {
         if (c->rows_cap < J) { if (c->d_rows) { CU(c, cudaStreamSynchronize(st)); cudaFree(c->d_rows); } c->rows_cap = (size_t)J + J / 4 + 16; CU(c, cudaMalloc(&c->d_rows, c->rows_cap * sizeof(pj_junction))); }
         launch_finalize(J, seg_start, A, G, entropy, c->d_rows, d_err, st); c->n_launches++;
         mark(c, "finalize");
-        if (c->extra && (rc = extra_keep_pairs(c, P, vals, jid, pa, st))) return rc;
+        if (c->extra && (rc = extra_keep_pairs(c, P, vals, jid, pr, st))) return rc;
         CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(fs_scratch, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
-        CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st));
+        CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st)); CU(c, cudaFreeAsync(inv, st));
     }
-    for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pa, (void*)pb, (void*)pc, (void*)pd, (void*)se_status})
+    for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pr, (void*)se_status})
         if (p) CU(c, cudaFreeAsync(p, st));
     if (c->extra && (rc = extra_classify(c, st))) return rc;
     mark(c, "end");

@@ -456,9 +456,9 @@ __global__ void __launch_bounds__(256) k_x_coverage(int64_t n, const int32_t* __
     out[g] = sum;
 }
 
-__global__ void __launch_bounds__(256) k_x_keep(uint32_t P, const uint32_t* __restrict__ vals, const PairA* __restrict__ pa, uint32_t* __restrict__ rid) {
+__global__ void __launch_bounds__(256) k_x_keep(uint32_t P, const uint32_t* __restrict__ vals, const PairRec* __restrict__ pr, uint32_t* __restrict__ rid) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P) rid[i] = pa[vals[i]].rid;
+    if (i < P) rid[i] = pr[vals[i]].a.rid;
 }
 
 // CUDA-event stage marks of pj_extra_run (same idea as the marks of pj_shard_run)
@@ -491,10 +491,10 @@ void extra_reset(pj_ctx* c) {
 }
 
 // end of pj_shard_run: remember, for every (read, junction) pair in sorted order, its record and its junction
-int extra_keep_pairs(pj_ctx* c, uint32_t P, const uint32_t* vals, const uint32_t* jid, const PairA* pa, cudaStream_t st) {
+int extra_keep_pairs(pj_ctx* c, uint32_t P, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, cudaStream_t st) {
     CU(c, cudaMallocAsync(&c->x_pair_rid, (size_t)std::max<uint32_t>(P, 1) * 4, st)); CU(c, cudaMallocAsync(&c->x_pair_jid, (size_t)std::max<uint32_t>(P, 1) * 4, st));
     if (P) {
-        k_x_keep<<<blocks_for(P, 256), 256, 0, st>>>(P, vals, pa, c->x_pair_rid); c->n_launches++;
+        k_x_keep<<<blocks_for(P, 256), 256, 0, st>>>(P, vals, pr, c->x_pair_rid); c->n_launches++;
         CU(c, cudaMemcpyAsync(c->x_pair_jid, jid, (size_t)P * 4, cudaMemcpyDeviceToDevice, st));
     }
     return PJ_OK;
