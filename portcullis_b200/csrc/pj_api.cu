@@ -280,8 +280,8 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     if ((rc = ensure(c, c->tid, r, 0, st)) || (rc = ensure(c, c->pos, r, 0, st)) || (rc = ensure(c, c->l_qseq, r, 0, st)) ||
         (rc = ensure(c, c->mtid, r, 0, st)) || (rc = ensure(c, c->mpos, r, 0, st)) || (rc = ensure(c, c->flag, r, 0, st)) ||
         (rc = ensure(c, c->mapq, r, 0, st)) || (rc = ensure(c, c->xs, r, 0, st)) || (rc = ensure(c, c->cigar_off, r + 1, 0, st)) ||
-        (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024), 0, st)) ||
-        (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 48, 0, st))) return rc;
+        (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024) + 64, 0, st)) ||
+        (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 256, 0, st))) return rc;   // slack: k_match stages 16-byte chunks that may reach past the last record
     if (c->extra && (rc = ensure(c, c->name_code, r, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 4 * sizeof(unsigned long long), st));
@@ -363,8 +363,8 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
     if ((rc = ensure(c, c->tid, need, R, st)) || (rc = ensure(c, c->pos, need, R, st)) || (rc = ensure(c, c->l_qseq, need, R, st)) ||
         (rc = ensure(c, c->mtid, need, R, st)) || (rc = ensure(c, c->mpos, need, R, st)) || (rc = ensure(c, c->flag, need, R, st)) ||
         (rc = ensure(c, c->mapq, need, R, st)) || (rc = ensure(c, c->xs, need, R, st)) || (rc = ensure(c, c->cigar_off, need + 1, R + 1, st)) ||
-        (rc = ensure(c, c->seq_off, need + 1, R + 1, st)) || (rc = ensure(c, c->cigar, (size_t)(c->n_cig + ncig), (size_t)c->n_cig, st)) ||
-        (rc = ensure(c, c->seq4, (size_t)(c->n_seq + nseq) + 16, (size_t)c->n_seq, st))) return rc;
+        (rc = ensure(c, c->seq_off, need + 1, R + 1, st)) || (rc = ensure(c, c->cigar, (size_t)(c->n_cig + ncig) + 64, (size_t)c->n_cig, st)) ||
+        (rc = ensure(c, c->seq4, (size_t)(c->n_seq + nseq) + 256, (size_t)c->n_seq, st))) return rc;
     if (c->extra && (rc = ensure(c, c->name_code, need, R, st))) return rc;
     const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
     CU(c, cudaMemcpyAsync(c->tid.p + R, b->tid, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->pos.p + R, b->pos, n * 4, H2D, st));
@@ -495,7 +495,8 @@ int pj_shard_run(pj_ctx* c) {
                   col(20), col(21), col(22), col(23), jadhist};
         CU(c, cudaMemsetAsync(A.firstmm, 0xff, (size_t)J * 4, st));
         launch_junc_init(J, seg_start, keys, vals, pr, c->tid.p, len_bits, A, st); c->n_launches++;
-        uint32_t* inv = nullptr; CU(c, cudaMallocAsync(&inv, (size_t)P * 4, st));   // emit slot -> sorted position (written by k_reduce1, read by k_match)
+        static const bool emit_order = [] { const char* e = getenv("PJ_MATCH_ORDER"); return e && atoi(e) == 1; }();   // 1: k_match walks pairs in emit (BAM) order
+        uint32_t* inv = nullptr; if (emit_order) CU(c, cudaMallocAsync(&inv, (size_t)P * 4, st));   // emit slot -> sorted position (written by k_reduce1, read by k_match)
         launch_reduce1(P, vals, jid, pr, (c->orientation == PJ_ORIENT_FR || c->orientation == PJ_ORIENT_RF || c->orientation == PJ_ORIENT_FF) ? 1 : 0,
                        A, spare_u32, inv, st); c->n_launches++;
         mark(c, "reduce1");
@@ -517,7 +518,7 @@ int pj_shard_run(pj_ctx* c) {
                 const double bases_per_pair = 2.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
                 group = bases_per_pair <= 400 ? 1 : bases_per_pair <= 1200 ? 4 : bases_per_pair <= 4000 ? 8 : 32;
             }
-            launch_match(P, group, inv, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
+            launch_match(P, group, inv, vals, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
         }
         mark(c, "match");
         launch_reduce2(P, jid, pm, A, st); c->n_launches++;
@@ -527,7 +528,7 @@ int pj_shard_run(pj_ctx* c) {
         mark(c, "finalize");
         if (c->extra && (rc = extra_keep_pairs(c, P, vals, jid, pr, st))) return rc;
         CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(fs_scratch, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
-        CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st)); CU(c, cudaFreeAsync(inv, st));
+        CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st)); if (inv) CU(c, cudaFreeAsync(inv, st));
     }
     for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pr, (void*)se_status})
         if (p) CU(c, cudaFreeAsync(p, st));
