@@ -1024,10 +1024,7 @@ void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32
 // ================================================================================================
 
 #ifndef PJ_MATCH_CTAS
-#define PJ_MATCH_CTAS 5          // resident CTAs per SM the register budget of k_match is set for (measured: 4 and 6 are slower on B200)
-#endif
-#ifndef PJ_MATCH_CTAS_STAGED
-#define PJ_MATCH_CTAS_STAGED 3   // G == 1: 26 KB static + 40 KB of staging per CTA
+#define PJ_MATCH_CTAS 4          // resident CTAs per SM the register budget of k_match is set for (64 registers: no spill in the hot loop; measured on B200: 3 / 4 / 5 -> 0.70 / 0.64 / 0.74 ms on c2)
 #endif
 constexpr uint64_t NIB1 = 0x1111111111111111ull;
 
@@ -1051,34 +1048,6 @@ struct MatchQueue {
 
 struct PairStats { uint32_t mism_l, mism_r; int32_t last_left; int32_t first_right; };
 
-// ---- per-thread staging of a pair's SEQ bytes and CIGAR words through shared memory (G == 1) ----
-// The walk is a chain of dependent loads: CIGAR op -> SEQ word -> next op ...; every link used to be a global round trip into a
-// random line (ncu: 28 % of the stall samples on the first use of a SEQ word, 15 % on CIGAR words).  As soon as the pair record is
-// known, the thread now asks for its whole SEQ span (112 B: a 150-base read from any alignment) and the 12 CIGAR words around its
-// N op with 16-byte cp.async copies (LDGSTS: no registers, all in flight at once), loads the junction's window meanwhile, waits
-// once, and then walks out of shared memory.  Pairs that do not fit (long reads, many ops) keep the global path, block by block.
-constexpr int ST_SEQ_CH = 7;       // 16-byte chunks of SEQ per thread
-constexpr int ST_CIG_CH = 3;       // 16-byte chunks of CIGAR per thread
-struct MatchStage {
-    uint4 seq[ST_SEQ_CH][256];     // chunk-major: chunk c of the 256 threads is one contiguous row (conflict-free)
-    uint4 cig[ST_CIG_CH][256];
-};
-struct StageView {
-    int64_t seq_w0;                // index (8-byte words of the SEQ stream) of staged word 0; < 0: SEQ not staged
-    int64_t cig_w0;                // index (CIGAR words of the shard) of staged word 0; < 0: CIGAR not staged / does not cover the read's ops
-};
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ uint2 stage_seq_word(const MatchStage& S, int w) {          // w-th 8-byte word of this thread's SEQ span
-    return reinterpret_cast<const uint2*>(&S.seq[w >> 1][threadIdx.x])[w & 1];
-}
-__device__ __forceinline__ uint32_t stage_cig_word(const MatchStage& S, int w) {       // w-th CIGAR word of this thread's window
-    return reinterpret_cast<const uint32_t*>(&S.cig[w >> 2][threadIdx.x])[w & 3];
-}
-
 // Flat loop over the 16-base chunks of all queued blocks.  Chunks are aligned to the genome's 16-base words (one aligned
 // 64-bit load); SEQ is extracted unaligned.  The left anchor tracks its LAST mismatch, the right anchor its FIRST: that is
 // all getNbMatchesFromEnd / getNbMatchesFromStart need.  Equal characters <=> equal nibbles because g4 uses the BAM
@@ -1090,18 +1059,12 @@ __device__ __forceinline__ void init_match_masks(MatchMasks& M) {
 }
 
 template <int G>
-__device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, int nq, const Genome& Gn, const uint8_t* __restrict__ seq4, int gl, PairStats& r,
-                                      const MatchStage* __restrict__ S, const StageView& sv) {
+__device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, int nq, const Genome& Gn, const uint8_t* __restrict__ seq4, int gl, PairStats& r) {
     const int col = threadIdx.x;
-    int ws = -1;                                                                      // >= 0: staged word index of the block's SEQ word 0
     int bi = -1; int32_t k = 0, nchunk = 0, a0 = 0, sbase = 0, side = 0;
     uint32_t o = 0; int32_t tl = 0;
     uint64_t gi0 = 0; uint32_t Bh = 0, Bl = 0;                                        // big-endian halves of SEQ word k (G == 1: carried)
     const uint64_t* gw = nullptr; const uint2* qw = nullptr;
-    // Chunks of one side are visited in increasing column order, so the LAST mismatch of the left anchor lies in the last chunk with
-    // a mismatch and the FIRST mismatch of the right anchor in the first one: remember that chunk's mask and column base, resolve the
-    // position once after the loop.  No divergent branch per chunk (with 25 lanes and 0.5 % substitutions it was taken almost always).
-    uint64_t lm = 0, fm = 0; int32_t lc = 0, fc = 0;
     for (;;) {
         if (k >= nchunk) {                                                            // next block of this lane
             if (++bi >= nq) break;
@@ -1120,16 +1083,10 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, 
             tl = a0 + len;                                                            // end column of the block in chunk coordinates
             k = gl;
             if (k >= nchunk) continue;
-            if (G == 1) {
-                // words 0 .. nchunk of the block must lie inside the staged span, else this block reads global memory
-                const int64_t w = (int64_t)(qn0 >> 4) - sv.seq_w0;
-                ws = (S && sv.seq_w0 >= 0 && w >= 0 && w + nchunk < 2 * ST_SEQ_CH) ? (int)w : -1;
-                const uint2 v = ws >= 0 ? stage_seq_word(*S, ws) : __ldg(qw);
-                Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123);
-            }
+            if (G == 1) { const uint2 v = __ldg(qw); Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123); }
         }
         if (G != 1) { const uint2 v = __ldg(qw + k); Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123); }
-        const uint2 cv = (G == 1 && ws >= 0) ? stage_seq_word(*S, ws + k + 1) : __ldg(qw + k + 1);   // consecutive chunks share a SEQ word: one load per chunk when G == 1
+        const uint2 cv = __ldg(qw + k + 1);                                           // consecutive chunks share a SEQ word: one load per chunk when G == 1
         const uint32_t Ch = __byte_perm(cv.x, 0, 0x0123), Cl = __byte_perm(cv.y, 0, 0x0123);
         // 64 bits at bit offset o of Bh:Bl:Ch:Cl, as two 32-bit funnel shifts
         const bool up = (o & 32u) != 0; const uint32_t sh = o & 31u;
@@ -1151,16 +1108,18 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, 
                 d = (d & ~(0xfull << (60 - 4 * t))) | ((mm ? 0xfull : 0ull) << (60 - 4 * t));
             }
         }
-        uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;                            // one bit per mismatching column
+        // One bit per mismatching column; count and extreme positions are updated with predicated arithmetic, not a branch: with 25
+        // lanes and 0.5 % substitutions some lane of the warp had a mismatch in 86 % of the chunks, so the branch was taken anyway,
+        // at 2-6 active lanes.  max / min, not assignment: insertions and deletions update the same fields during the walk.
+        uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;
         const uint32_t cnt = (uint32_t)__popcll(m);
-        const bool nz = m != 0ull;
-        if (side == 0) { r.mism_l += cnt; if (nz) { lm = m; lc = sbase + c0; } }
-        else           { r.mism_r += cnt; if (nz && fm == 0ull) { fm = m; fc = sbase + c0; } }
+        const int32_t cb = sbase + c0;
+        const int32_t lastc = m ? cb + 15 - ((__ffsll((long long)m) - 1) >> 2) : -1;
+        const int32_t firstc = m ? cb + (__clzll((long long)m) >> 2) : INT32_MAX;
+        if (side == 0) { r.mism_l += cnt; r.last_left = max(r.last_left, lastc); }
+        else           { r.mism_r += cnt; r.first_right = min(r.first_right, firstc); }
         k += G;
     }
-    // max / min, not assignment: insertions and deletions update the same fields during the walk, before this drain
-    if (lm) r.last_left = max(r.last_left, lc + 15 - ((__ffsll((long long)lm) - 1) >> 2));
-    if (fm) r.first_right = min(r.first_right, fc + (__clzll((long long)fm) >> 2));
 }
 
 // One pass over the CIGAR serves both anchor windows: the left walk of the reference stops at the first op it rejects,
@@ -1171,9 +1130,8 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
                                                const uint32_t* __restrict__ cgn /* this junction's N op */, int32_t ops_before, int32_t ops_after,
                                                int32_t start, int32_t qpos_n, const uint8_t* __restrict__ seq4, uint64_t seq_nib0, int32_t qsize,
                                                int32_t left, int32_t leftEnd, int32_t rightStart, int32_t right, int gl, uint32_t& err,
-                                               uint32_t& cols_l, uint32_t& cols_r, const MatchStage* __restrict__ S, const StageView& sv, int cig_n /* staged index of the N op */) {
-    // CIGAR word at offset `rel` from this junction's N op: from the staged window when it covers every op of the read
-    auto cigw = [&](int32_t rel) -> uint32_t { return (G == 1 && S && sv.cig_w0 >= 0) ? stage_cig_word(*S, cig_n + rel) : __ldg(cgn + rel); };
+                                               uint32_t& cols_l, uint32_t& cols_r) {
+    auto cigw = [&](int32_t rel) -> uint32_t { return __ldg(cgn + rel); };              // CIGAR word at offset `rel` from this junction's N op
     PairStats r{0u, 0u, -1, INT32_MAX};
     const int col = threadIdx.x;
     // The reference walks the CIGAR from its first op and skips, op by op, everything that starts before the window
@@ -1214,7 +1172,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
                 if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
                 Q.qn[nq][col] = seq_nib0 + (uint64_t)qPos; Q.gi[nq][col] = gbase + (uint64_t)(uint32_t)rPos;
                 Q.len[nq][col] = len; Q.sb[nq][col] = (int32_t)(cols << 1) | side;
-                if (++nq == MQ) { drain<G>(Q, M, nq, Gn, seq4, gl, r, S, sv); nq = 0; }
+                if (++nq == MQ) { drain<G>(Q, M, nq, Gn, seq4, gl, r); nq = 0; }
             }
             cols += (uint32_t)len;
         } else if (cr) {                                                                   // D or N inside the window: 'X' vs genome
@@ -1238,7 +1196,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
         if (cr) rPos += L;
         if (cq) qPos += L;
     }
-    drain<G>(Q, M, nq, Gn, seq4, gl, r, S, sv);
+    drain<G>(Q, M, nq, Gn, seq4, gl, r);
     if (side == 0) cols_l = cols; else cols_r = cols;
     if (G > 1) {   // combine the lanes of the group
         const int lane = threadIdx.x & 31;
@@ -1253,14 +1211,12 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
     return r;
 }
 
-template <int G>
-__global__ void __launch_bounds__(256, G == 1 ? PJ_MATCH_CTAS_STAGED : PJ_MATCH_CTAS) k_match(uint32_t n, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+template <int G, int CT /* resident CTAs per SM the register budget is set for */>
+__global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairRec* __restrict__ pr,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
     __shared__ MatchQueue Q;
     __shared__ MatchMasks M;
-    extern __shared__ __align__(16) unsigned char stage_raw[];      // MatchStage when G == 1 (dynamic: 40 KB on top of the static 26 KB)
-    MatchStage* const S = G == 1 ? reinterpret_cast<MatchStage*>(stage_raw) : nullptr;
     init_match_masks(M);
     __syncthreads();                                                 // the only block-wide barrier: before any thread leaves
     // Pairs are visited in EMIT order (= BAM order), not in junction order: the pair records are read coalesced, the SEQ / CIGAR streams
@@ -1275,26 +1231,15 @@ __global__ void __launch_bounds__(256, G == 1 ? PJ_MATCH_CTAS_STAGED : PJ_MATCH_
     const uint32_t i = inv ? inv[th] : th;                           // sorted position of this pair
     const PairA a = pr[idx].a; const PairB b = pr[idx].b; const PairC c = pr[idx].c; const PairD d = pr[idx].d;
     const uint32_t j = jid[i];
-    // The walk below is a chain of dependent loads (CIGAR ops -> SEQ words / genome words).  What it will need is known already:
-    // copy the SEQ span and the CIGAR window of this pair into shared memory now (cp.async), so that they arrive while the
-    // junction's window is being loaded; reads too long for the staging area keep prefetch hints + the global path.
-    StageView sv{-1, -1}; int cig_n = 0;
+    // The walk below is a chain of dependent loads (CIGAR ops -> SEQ words / genome words).  The lines it will need are
+    // known already: ask for them now so that they arrive while the junction's window is being loaded.  (Copying the SEQ span and
+    // the CIGAR window into shared memory with cp.async instead was measured on B200 and is slower in every variant — the wait
+    // replaces the same first-touch latency and the extra shared memory costs resident warps; profiles/r2_history.md.)
     if (G == 1) {
-        const int32_t ops_before = (int32_t)(d.nops & 0xffffu), ops_after = (int32_t)(d.nops >> 16);
-        // SEQ: from 8 bytes before the first base (a block's word 0 may start up to 15 nibbles early), 16-byte aligned
-        const uint64_t sb = (((c.seq_nib0 >> 1) - 8u) & ~15ull);
-        const uint8_t* sp = R.seq4 + sb;
-#pragma unroll
-        for (int q = 0; q < ST_SEQ_CH; q++) cp_async16(&S->seq[q][threadIdx.x], sp + 16 * q);
-        sv.seq_w0 = (int64_t)(sb >> 3);
-        // CIGAR: 12 words from (first op of the read, but at most 8 before the N op), 16-byte aligned
-        const uint32_t lo = (c.cig_abs - (uint32_t)min(ops_before, 8)) & ~3u;
-        const uint32_t* cp = R.cigar + lo;
-#pragma unroll
-        for (int q = 0; q < ST_CIG_CH; q++) cp_async16(&S->cig[q][threadIdx.x], cp + 4 * q);
-        cig_n = (int)(c.cig_abs - lo);
-        if (c.cig_abs - (uint32_t)ops_before >= lo && cig_n + ops_after < 4 * ST_CIG_CH) sv.cig_w0 = (int64_t)lo;
-        if (d.qsize > 200) { prefetch_l1(R.seq4 + (c.seq_nib0 >> 1) + 100); }
+        const uint8_t* sp = R.seq4 + (c.seq_nib0 >> 1);
+        prefetch_l1(R.cigar + c.cig_abs);
+        prefetch_l1(sp);
+        if (d.qsize > 200) prefetch_l1(sp + 100);
     }
     const int32_t start = b.start, end = A.end[j], left = A.left[j], right = A.right[j];
     const int32_t tid = A.tid[j];
@@ -1302,7 +1247,6 @@ __global__ void __launch_bounds__(256, G == 1 ? PJ_MATCH_CTAS_STAGED : PJ_MATCH_
         const uint64_t gb = Gn.goff[tid];
         prefetch_l1(Gn.g4 + ((gb + (uint64_t)(uint32_t)max(left, a.pos)) >> 4));
         prefetch_l1(Gn.g4 + ((gb + (uint64_t)(uint32_t)(end + 1)) >> 4));
-        cp_async_wait_all();                                         // this thread's own copies: no barrier needed (and none may be pending at exit)
     }
     const int32_t lq = d.lq;
     uint32_t err = 0, mmes, minMatch, nbMism;
@@ -1317,7 +1261,7 @@ __global__ void __launch_bounds__(256, G == 1 ? PJ_MATCH_CTAS_STAGED : PJ_MATCH_
         PairStats St{0u, 0u, -1, INT32_MAX}; uint32_t cols_l = 0, cols_r = 0;
         if (!err) {
             St = walk_pair<G>(Q, M, Gn, Gn.goff[tid], glen, R.cigar + c.cig_abs, (int32_t)(d.nops & 0xffffu), (int32_t)(d.nops >> 16), start, c.qpos_n,
-                             R.seq4, c.seq_nib0, d.qsize, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r, S, sv, cig_n);
+                             R.seq4, c.seq_nib0, d.qsize, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
             if (cols_l == 0 || cols_r == 0) err |= ERR_EMPTY_ANCHOR;
         }
         const uint32_t upMatches = cols_l - St.mism_l, downMatches = cols_r - St.mism_r;
@@ -1333,24 +1277,28 @@ __global__ void __launch_bounds__(256, G == 1 ? PJ_MATCH_CTAS_STAGED : PJ_MATCH_
     }
 }
 
-template <int G>
-static void launch_match_g(uint32_t n, const uint32_t* inv, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
-                           const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
+template <int G, int CT>
+static void launch_match_gc(uint32_t n, const uint32_t* inv, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
+                            const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     const uint64_t threads = (uint64_t)n * G;
-    const size_t dyn = G == 1 ? sizeof(MatchStage) : 0;
-    if (dyn) { static bool once = false; if (!once) { cudaFuncSetAttribute(k_match<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); once = true; } }
-    k_match<G><<<(unsigned)((threads + 255) / 256), 256, dyn, st>>>(n, inv, vals, jid, pr, R, Gn, A, pm, err);
+    k_match<G, CT><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, inv, vals, jid, pr, R, Gn, A, pm, err);
 }
-void launch_match(uint32_t n, int group, const uint32_t* inv, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
+// ctas: register budget (resident CTAs per SM) of the G == 1 kernel, 0 = default; a tuning knob (PJ_MATCH_CTAS).
+void launch_match(uint32_t n, int group, int ctas, const uint32_t* inv, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     if (!n) return;
     switch (group) {
-    case 1: launch_match_g<1>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 2: launch_match_g<2>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 4: launch_match_g<4>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 8: launch_match_g<8>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 16: launch_match_g<16>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    default: launch_match_g<32>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 1:
+        if (ctas == 5) launch_match_gc<1, 5>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
+        else if (ctas == 3) launch_match_gc<1, 3>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
+        else if (ctas == 6) launch_match_gc<1, 6>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
+        else launch_match_gc<1, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
+        break;
+    case 2: launch_match_gc<2, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 4: launch_match_gc<4, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 8: launch_match_gc<8, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 16: launch_match_gc<16, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    default: launch_match_gc<32, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
     }
 }
 

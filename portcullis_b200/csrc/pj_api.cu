@@ -518,7 +518,8 @@ int pj_shard_run(pj_ctx* c) {
                 const double bases_per_pair = 2.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
                 group = bases_per_pair <= 400 ? 1 : bases_per_pair <= 1200 ? 4 : bases_per_pair <= 4000 ? 8 : 32;
             }
-            launch_match(P, group, inv, vals, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
+            static const int match_ctas = [] { const char* e = getenv("PJ_MATCH_CTAS"); return e ? atoi(e) : 0; }();
+            launch_match(P, group, match_ctas, inv, vals, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
         }
         mark(c, "match");
         launch_reduce2(P, jid, pm, A, st); c->n_launches++;
