@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PJ_ABI_VERSION 1
+#define PJ_ABI_VERSION 2
 
 /* status codes */
 #define PJ_OK            0
@@ -102,6 +102,27 @@ typedef struct pj_batch {
     const uint64_t* seq_off;
     const uint8_t*  seq4;
     const uint64_t* name_code;
+    /* ---- lean form (ABI 2): what the host decoder ships, about half the bytes of the classic form over PCIe ----
+     * A batch is lean when lean != 0.  Then tid / cigar_off / seq_off / seq4 are ignored and may be NULL:
+     *   const_tid     : every record of the batch lies on this target (a decode task never spans targets);
+     *   n_cigar       : ops per record (BAM's own n_cigar_op); cigar[] holds the n_cigar_total words back to back and the
+     *                   prefix offsets are formed on the device (scan);
+     *   seq2          : read bases at 2 bits each (A=0, C=1, G=2, T=3; base q of a record in bits 2(q&3)..2(q&3)+1 of its byte
+     *                   q>>2), (l_qseq+3)/4 bytes for every record that has an N op and l_qseq > 0, nothing for the others,
+     *                   back to back (n_seq2_bytes in total); the offsets are formed on the device from cigar + l_qseq;
+     *   seqx_pos/code : the read bases that are not A/C/G/T (stored as 0 in seq2): base index within this batch's seq2
+     *                   (byte offset * 4 + q), ascending, and the BAM nibble (index into "=ACMGRSVTWYHKDBN"); records that own
+     *                   one must have bit 15 (0x8000, unused by the SAM spec) set in flag;
+     *   mtid / mpos   : may be NULL when the context's orientation is SE or UNKNOWN (nothing reads them then). */
+    int32_t         lean;
+    int32_t         const_tid;
+    const uint16_t* n_cigar;
+    int64_t         n_cigar_total;
+    const uint8_t*  seq2;
+    int64_t         n_seq2_bytes;
+    const uint64_t* seqx_pos;
+    const uint8_t*  seqx_code;
+    int64_t         n_seqx;
 } pj_batch;
 
 /* Per-target scalars: RegionResult minus the junction system
@@ -215,6 +236,10 @@ int pj_shard_begin(pj_ctx* ctx, int64_t n_records_hint, int64_t n_cigar_hint, in
  * acquiring blocks only while every buffer of the pool is in flight.
  */
 int pj_staging_acquire(pj_ctx* ctx, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out);
+/* Same for a lean batch (out->lean = 1): pos, flag, mapq, xs, l_qseq, mtid, mpos, n_cigar, cigar, seq2, seqx_pos, seqx_code
+ * (and name_code) point into the pinned buffer; the caller fills them and sets n_records, const_tid, n_cigar_total,
+ * n_seq2_bytes and n_seqx before pj_batch_submit. */
+int pj_staging_acquire_lean(pj_ctx* ctx, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq2_bytes, int64_t cap_seqx, pj_batch* out);
 
 /* Enqueue host->device copies of a batch (cudaMemcpyAsync on the context's copy stream) and
  * append it to the shard.  `b` may be a staging view or any caller-owned host buffers (those are

@@ -33,7 +33,11 @@ class PjBatch(C.Structure):
     _fields_ = [("n_records", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p),
                 ("mapq", C.c_void_p), ("xs", C.c_void_p), ("l_qseq", C.c_void_p), ("mtid", C.c_void_p),
                 ("mpos", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("seq_off", C.c_void_p),
-                ("seq4", C.c_void_p), ("name_code", C.c_void_p)]
+                ("seq4", C.c_void_p), ("name_code", C.c_void_p),
+                # lean form (ABI 2)
+                ("lean", C.c_int32), ("const_tid", C.c_int32), ("n_cigar", C.c_void_p), ("n_cigar_total", C.c_int64),
+                ("seq2", C.c_void_p), ("n_seq2_bytes", C.c_int64), ("seqx_pos", C.c_void_p), ("seqx_code", C.c_void_p),
+                ("n_seqx", C.c_int64)]
 
 
 class PjTargetStats(C.Structure):
@@ -126,6 +130,7 @@ SYMBOLS = {
     "pj_genome_load_fasta": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_char_p)]),
     "pj_shard_begin": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
     "pj_staging_acquire": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(PjBatch)]),
+    "pj_staging_acquire_lean": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.POINTER(PjBatch)]),
     "pj_batch_submit": (C.c_int, [_P, C.POINTER(PjBatch)]),
     "pj_shard_run": (C.c_int, [_P]),
     "pj_shard_num_junctions": (C.c_int64, [_P]),

@@ -102,6 +102,7 @@ int ordered_pipeline(size_t n, int threads, size_t window, const std::function<i
 }
 
 void chunk_view(const ColumnarChunk& c, pj_batch* b) {
+    memset(b, 0, sizeof *b);
     b->n_records = c.n(); b->tid = c.tid.data(); b->pos = c.pos.data(); b->flag = c.flag.data(); b->mapq = c.mapq.data(); b->xs = c.xs.data();
     b->l_qseq = c.l_qseq.data(); b->mtid = c.mtid.data(); b->mpos = c.mpos.data(); b->cigar_off = c.cigar_off.data(); b->cigar = c.cigar.data();
     b->seq_off = c.seq_off.data(); b->seq4 = c.seq4.data();

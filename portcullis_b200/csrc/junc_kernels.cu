@@ -149,9 +149,9 @@ void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { 
 // one thread packs 64 bases: four 128-bit loads, two g2 words, one gx word
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ raw, int64_t n, uint64_t base_index /* multiple of 64 */,
-                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx, uint64_t* __restrict__ g4,
+                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx,
                                                       uint64_t* __restrict__ exc_pos, uint8_t* __restrict__ exc_byte,
-                                                      uint32_t* __restrict__ exc_count, uint32_t exc_cap) {
+                                                      uint32_t* __restrict__ exc_count /* [0] side-table entries, [1] != 0: some base is not A/C/G/T */, uint32_t exc_cap) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t b0 = t * 64;
     if (b0 >= n) return;
@@ -165,20 +165,10 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
         for (int k = 0; k < 64; k++) c[k] = (b0 + k < n) ? raw[b0 + k] : (uint8_t)'A';
     }
     uint64_t w0 = 0, w1 = 0, x = 0;
-    uint64_t n8[4] = {0, 0, 0, 0};                                    // 4 words of 16 bases, base 16w + k in bits 63-4k .. 60-4k
 #pragma unroll
     for (int k = 0; k < 64; k++) {
         uint8_t ch = c[k];
         if (ch >= 'a' && ch <= 'z') ch -= 32;                        // boost::to_upper
-        {
-            uint32_t q;                                                // index into "=ACMGRSVTWYHKDBN" (hts.c:82), 0 if absent
-            switch (ch) { case 'A': q = 1; break; case 'C': q = 2; break; case 'M': q = 3; break; case 'G': q = 4; break; case 'R': q = 5; break;
-                          case 'S': q = 6; break; case 'V': q = 7; break; case 'T': q = 8; break; case 'W': q = 9; break; case 'Y': q = 10; break;
-                          case 'H': q = 11; break; case 'K': q = 12; break; case 'D': q = 13; break; case 'B': q = 14; break; case 'N': q = 15; break;
-                          default: q = 0; }
-            if (b0 + k >= n) q = 0;
-            n8[k >> 4] |= (uint64_t)q << (60 - 4 * (k & 15));
-        }
         uint32_t code; bool exc = false;
         switch (ch) { case 'A': code = 0; break; case 'C': code = 1; break; case 'G': code = 2; break; case 'T': code = 3; break;
                       default: exc = true; code = (ch == 'N') ? 0u : 1u; }
@@ -194,15 +184,14 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
     }
     const uint64_t gi = base_index + (uint64_t)b0;
     g2[gi >> 5] = w0; g2[(gi >> 5) + 1] = w1; gx[gi >> 6] = x;
-    ulonglong2* o4 = reinterpret_cast<ulonglong2*>(g4 + (gi >> 4));   // gi is a multiple of 64 -> 32-byte aligned
-    o4[0] = make_ulonglong2(n8[0], n8[1]); o4[1] = make_ulonglong2(n8[2], n8[3]);
+    if (x) exc_count[1] = 1u;
 }
 
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint64_t* g4,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st) {
     if (n <= 0) return;
     const int64_t threads = (n + 63) / 64;
-    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, g4, exc_pos, exc_byte, exc_count, exc_cap);
+    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, exc_pos, exc_byte, exc_count, exc_cap);
 }
 
 // ================================================================================================
@@ -396,11 +385,12 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
         if (flag & 0x2u) bits |= PB_BPP;
         if (portcullis_proper_pair(flag, tid, mtid, pos, mpos, orientation)) bits |= PB_PPP;
         if (xs == '+') bits |= PB_XSP; else if (xs == '-') bits |= PB_XSN;
+        if (flag & FLAG_SEQX) bits |= PB_SEQX;
         // getQuerySeqAfterClipping (bam_alignment.cc:256-264), quirk Q3: only a FIRST / LAST op of type S clips
         int32_t ds = cig_op(wf) == OP_S ? cig_len(wf) : 0; const int32_t de = cig_op(wl) == OP_S ? cig_len(wl) : 0;
         if (ds > lq) ds = lq;
         int64_t qs = (int64_t)lq - ds - de + 1; if (qs > lq - ds) qs = lq - ds; if (qs < 0) qs = 0;
-        if (lq > 1 && (int64_t)(so1 - so) < (int64_t)((lq + 1) >> 1)) e |= ERR_SEQ_MISSING;
+        if (lq > 1 && (int64_t)(so1 - so) < (int64_t)((lq + 3) >> 2)) e |= ERR_SEQ_MISSING;
         int32_t lStart = pos, lEndExc = pos;
         int32_t p = pos, qpos = 0;            // plain reference / query position at the start of op c (calcAlignmentStats / getPadded* walks)
         uint32_t kN = 0, a_eq = 0;            // N ops seen so far; how many of them end exactly at p
@@ -438,7 +428,7 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
                 PairRec* const o = pr + slot;
                 o->a = PairA{(uint32_t)i, lStart, rendj, pos};
                 o->b = PairB{rend[r], bits, (up << 16) | (down & 0xffffu), start};
-                o->c = PairC{so * 2 + (uint64_t)ds, cig0 + (uint32_t)c, qpos};
+                o->c = PairC{so * 4 + (uint64_t)ds, cig0 + (uint32_t)c, qpos};
                 o->d = PairD{(int32_t)qs, lq, (uint32_t)c | ((uint32_t)(n - 1 - c) << 16), 0u};
                 slot++;
                 kN++; p += L; a_eq = L > 0 ? 1u : a_eq + 1u;
@@ -810,6 +800,92 @@ void launch_entropy_index(uint32_t n, const uint32_t* eflag, uint32_t* eoff, uin
     k_flag_scan<<<nt, FS_THREADS, 0, st>>>(n, EntropyIndexOp{eflag, eoff, epos}, scratch, reinterpret_cast<uint32_t*>(scratch + nt), total_dev);
 }
 
+// ---- batch expansion at submit: prefix columns derived on the device (lean batches), 4-bit SEQ repacked (classic batches) ----
+// cigar_off from the per-record op counts
+struct CigarOffOp {
+    const uint16_t* ncig; uint32_t* out /* cigar_off + R: out[0] is the base already */; uint32_t base; uint32_t expect; unsigned long long* bad;
+    __device__ uint32_t flag(uint32_t i) const { return ncig[i]; }
+    __device__ void emit(uint32_t i, uint32_t excl, uint32_t fl) const { out[i + 1] = base + excl + fl; }
+    __device__ void finish(uint32_t, uint32_t total) const { if (total != expect) *bad = 1ull; }
+};
+// seq_off of a lean batch: a record has SEQ bytes in the 2-bit stream iff it has an N op and l_qseq > 0 (what the host decoder keeps)
+struct SeqOffOp {
+    const uint32_t* cigar_off /* + R */; const uint32_t* cigar; const int32_t* lq /* + R */; uint64_t* out /* seq_off + R */; uint64_t base; uint64_t expect; unsigned long long* bad;
+    __device__ uint32_t flag(uint32_t i) const {
+        const int32_t l = lq[i]; if (l <= 0) return 0u;
+        bool spliced = false;
+        for (uint32_t c = cigar_off[i]; c < cigar_off[i + 1]; c++) if (cig_op(__ldg(cigar + c)) == OP_N) { spliced = true; break; }
+        return spliced ? (uint32_t)((l + 3) >> 2) : 0u;
+    }
+    __device__ void emit(uint32_t i, uint32_t excl, uint32_t fl) const { out[i + 1] = base + (uint64_t)excl + fl; }
+    __device__ void finish(uint32_t, uint32_t total) const { if ((uint64_t)total != expect) *bad = 1ull; }
+};
+void launch_cigar_off(uint32_t n, const uint16_t* ncig, uint32_t* cigar_off_at_R, uint32_t base, uint32_t expect, unsigned long long* bad, unsigned long long* scratch, cudaStream_t st) {
+    if (!n) return;
+    const uint32_t nt = fs_num_tiles(n);
+    cudaMemsetAsync(scratch, 0, ((size_t)nt + 2) * 8, st);
+    k_flag_scan<<<nt, FS_THREADS, 0, st>>>(n, CigarOffOp{ncig, cigar_off_at_R, base, expect, bad}, scratch, reinterpret_cast<uint32_t*>(scratch + nt), reinterpret_cast<uint32_t*>(scratch + nt) + 1);
+}
+void launch_seq_off(uint32_t n, const uint32_t* cigar_off_at_R, const uint32_t* cigar, const int32_t* lq_at_R, uint64_t* seq_off_at_R, uint64_t base, uint64_t expect,
+                    unsigned long long* bad, unsigned long long* scratch, cudaStream_t st) {
+    if (!n) return;
+    const uint32_t nt = fs_num_tiles(n);
+    cudaMemsetAsync(scratch, 0, ((size_t)nt + 2) * 8, st);
+    k_flag_scan<<<nt, FS_THREADS, 0, st>>>(n, SeqOffOp{cigar_off_at_R, cigar, lq_at_R, seq_off_at_R, base, expect, bad}, scratch, reinterpret_cast<uint32_t*>(scratch + nt), reinterpret_cast<uint32_t*>(scratch + nt) + 1);
+}
+size_t fs_scratch_bytes(uint32_t n) { return ((size_t)fs_num_tiles(n) + 2) * 8; }
+
+// Classic batches carry BAM's 4-bit SEQ: repack into the 2-bit stream, one thread per record.  Bases that are not A/C/G/T are
+// written as 0, counted per record (pass 1) and listed in record order at the scanned offsets (pass 2).
+__device__ __forceinline__ uint32_t nib_code2(uint32_t nib) { return nib == 2u ? 1u : nib == 4u ? 2u : nib == 8u ? 3u : 0u; }   // A(1)->0 C(2)->1 G(4)->2 T(8)->3
+__global__ void __launch_bounds__(256) k_seq4_to_2(int64_t n, const uint8_t* __restrict__ s4, const uint64_t* __restrict__ off4 /* n+1, relative to s4 + off4[0] */,
+                                                    const int32_t* __restrict__ lq, const uint64_t* __restrict__ seq_off /* arena, + R */, uint8_t* __restrict__ seq2,
+                                                    uint16_t* __restrict__ flag /* + R */, uint32_t* __restrict__ xcount) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t o2 = seq_off[i], nb2 = seq_off[i + 1] - o2;
+    uint32_t nx = 0;
+    if (nb2) {
+        const uint8_t* src = s4 + (off4[i] - off4[0]);
+        const int32_t l = lq[i];
+        for (uint64_t b = 0; b < nb2; b++) {                         // 4 bases = 2 source bytes -> 1 byte
+            uint32_t out = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int32_t base = (int32_t)(4 * b) + q;
+                if (base < l) {
+                    const uint32_t byte = src[base >> 1], nib = (base & 1) ? (byte & 15u) : (byte >> 4);
+                    if (nib != 1u && nib != 2u && nib != 4u && nib != 8u) nx++;
+                    out |= nib_code2(nib) << (2 * q);
+                }
+            }
+            seq2[o2 + b] = (uint8_t)out;
+        }
+    }
+    xcount[i] = nx;
+    if (nx) flag[i] = (uint16_t)(flag[i] | FLAG_SEQX);
+}
+__global__ void __launch_bounds__(256) k_seq4_exceptions(int64_t n, const uint8_t* __restrict__ s4, const uint64_t* __restrict__ off4, const int32_t* __restrict__ lq,
+                                                          const uint64_t* __restrict__ seq_off, const uint32_t* __restrict__ xcount, const uint32_t* __restrict__ xoff,
+                                                          uint64_t* __restrict__ xpos /* + first free slot */, uint8_t* __restrict__ xcode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || xcount[i] == 0u) return;
+    const uint8_t* src = s4 + (off4[i] - off4[0]);
+    const int32_t l = lq[i];
+    uint32_t w = xoff[i];
+    for (int32_t base = 0; base < l; base++) {
+        const uint32_t byte = src[base >> 1], nib = (base & 1) ? (byte & 15u) : (byte >> 4);
+        if (nib != 1u && nib != 2u && nib != 4u && nib != 8u) { xpos[w] = seq_off[i] * 4ull + (uint64_t)base; xcode[w] = (uint8_t)nib; w++; }
+    }
+}
+void launch_seq4_to_2(int64_t n, const uint8_t* s4, const uint64_t* off4, const int32_t* lq, const uint64_t* seq_off, uint8_t* seq2, uint16_t* flag, uint32_t* xcount, cudaStream_t st) {
+    if (n > 0) k_seq4_to_2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, s4, off4, lq, seq_off, seq2, flag, xcount);
+}
+void launch_seq4_exceptions(int64_t n, const uint8_t* s4, const uint64_t* off4, const int32_t* lq, const uint64_t* seq_off, const uint32_t* xcount, const uint32_t* xoff,
+                            uint64_t* xpos, uint8_t* xcode, cudaStream_t st) {
+    if (n > 0) k_seq4_exceptions<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, s4, off4, lq, seq_off, xcount, xoff, xpos, xcode);
+}
+
 // ================================================================================================
 // warp-shuffle segmented reduction helpers.  Lanes hold nondecreasing junction ids; after the inclusive
 // segmented scan the LAST lane of every run holds the reduction of the run.
@@ -1017,30 +1093,33 @@ void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32
 // (bam_alignment.cc:341-462) + hammingDistance + getNbMatchesFromEnd/Start, fused into one walk that never
 // materialises the strings.  Quirks Q3-Q6 are kept.
 //
-// A group of G lanes (G = 1, 2, 4, 8, 16 or 32, chosen from the mean read length of the shard) owns one
-// (read, junction) pair.  The CIGAR walk is uniform inside the group; the columns of every M/=/X block are
-// compared 16 bases per step: 16 BAM nibbles (one unaligned 64-bit window of SEQ) against 16 genome bases
-// expanded from the 2-bit plane to one-hot nibbles, so a mismatch is a non-zero nibble of an XOR.
+// A group of G lanes (G = 1, 2, 4, 8, 16 or 32; 1 on every preset measured) owns one (read, junction) pair.  The CIGAR
+// walk is uniform inside the group; the columns of every M/=/X block are compared 32 bases per step: 64 bits of the read's
+// 2-bit stream (one unaligned window) XOR the aligned word of the genome's 2-bit plane.
 // ================================================================================================
 
 #ifndef PJ_MATCH_CTAS
 #define PJ_MATCH_CTAS 4          // resident CTAs per SM the register budget of k_match is set for (64 registers: no spill in the hot loop; measured on B200: 3 / 4 / 5 -> 0.70 / 0.64 / 0.74 ms on c2)
 #endif
-constexpr uint64_t NIB1 = 0x1111111111111111ull;
+constexpr uint64_t EVEN2 = 0x5555555555555555ull;
 
-// 16 consecutive nibbles of a BAM-ordered nibble stream (even index = high nibble of its byte), starting at nibble index
-// `nib` of `base`, returned MSB-first: nibble t sits at bits [60-4t, 64-4t).  Two aligned 64-bit loads cover any alignment.
-__device__ __forceinline__ uint64_t bswap64(uint64_t v) {
-    const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
-    return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | (uint64_t)__byte_perm(hi, 0, 0x0123);
+// bit k of v -> bit 2k (positions of a 1-bit-per-base mask in the 2-bit-per-base layout)
+__device__ __forceinline__ uint64_t spread32(uint32_t v) {
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & EVEN2;
+    return x;
 }
 // ---- per-lane queue of compare blocks (shared memory, one column per thread: conflict-free) ----
 // Lanes of a warp reach their M/=/X blocks in different CIGAR iterations; comparing inside the walk would make the
-// warp pay the longest block in EVERY iteration.  Instead the walk only queues (SEQ nibble index, genome index, length,
-// string offset, side) and drain() then runs ONE flat loop over 16-base chunks in which every lane is busy.
+// warp pay the longest block in EVERY iteration.  Instead the walk only queues (read base index, genome index, length,
+// string offset, side) and drain() then runs ONE flat loop over 32-base chunks in which every lane is busy.
 constexpr int MQ = 4;              // queued blocks per lane before a drain
 struct MatchQueue {
-    uint64_t qn[MQ][256];          // index of the block's first read nibble in the shard's SEQ stream
+    uint64_t qn[MQ][256];          // index of the block's first read base in the shard's SEQ stream
     uint64_t gi[MQ][256];          // global genome base index of its first column
     int32_t  len[MQ][256];
     int32_t  sb[MQ][256];          // (string offset of column 0) << 1 | side
@@ -1048,74 +1127,94 @@ struct MatchQueue {
 
 struct PairStats { uint32_t mism_l, mism_r; int32_t last_left; int32_t first_right; };
 
-// Flat loop over the 16-base chunks of all queued blocks.  Chunks are aligned to the genome's 16-base words (one aligned
-// 64-bit load); SEQ is extracted unaligned.  The left anchor tracks its LAST mismatch, the right anchor its FIRST: that is
-// all getNbMatchesFromEnd / getNbMatchesFromStart need.  Equal characters <=> equal nibbles because g4 uses the BAM
-// alphabet; code 0 (bytes outside it) is resolved exactly through the side table.
-struct MatchMasks { uint64_t first[16]; uint64_t last[17]; };     // column masks of a block's first / last chunk (shared memory: conflict-free 8-byte lookups)
-__device__ __forceinline__ void init_match_masks(MatchMasks& M) {
-    if (threadIdx.x < 16) M.first[threadIdx.x] = ~0ull >> (4 * threadIdx.x);                                   // a0 columns before the block
-    else if (threadIdx.x < 33) { const int t = threadIdx.x - 16; M.last[t] = t >= 16 ? ~0ull : ~(~0ull >> (4 * t)); }   // t valid columns
+// Character of read base `rb` (base index in the SEQ stream) as the reference's padded query string holds it (bam_alignment.cc:
+// 341-462 prints SEQ through "=ACMGRSVTWYHKDBN"): from the exception list when the base is not A/C/G/T.  *ex is a cursor into the
+// sorted list that only moves forward (columns are visited in increasing order).
+__device__ __forceinline__ uint8_t read_char_exact(const Reads& R, uint64_t rb, int64_t* ex) {
+    int64_t e = *ex;
+    while (e < R.n_seqx && R.seqx_pos[e] < rb) e++;
+    *ex = e;
+    if (e < R.n_seqx && R.seqx_pos[e] == rb) return (uint8_t)("=ACMGRSVTWYHKDBN"[R.seqx_code[e] & 15]);
+    return (uint8_t)("ACGT"[(R.seq2[rb >> 2] >> (2 * (rb & 3))) & 3]);
 }
 
+// Flat loop over the 32-base chunks of all queued blocks.  Chunks are aligned to the genome's 32-base words (one aligned
+// 64-bit load); the read bits are extracted unaligned (the stream has a 16-byte lead pad and tail slack).  The left anchor
+// tracks its LAST mismatch, the right anchor its FIRST: that is all getNbMatchesFromEnd / getNbMatchesFromStart need.
+// A read base stored in the 2-bit stream is A/C/G/T, so it equals the genome character iff the 2-bit codes are equal and the
+// genome base is not an exception (gx); reads that do carry other codes (`exact`) are compared character by character.
 template <int G>
-__device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, int nq, const Genome& Gn, const uint8_t* __restrict__ seq4, int gl, PairStats& r) {
+__device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome& Gn, const Reads& R, bool exact, int gl, PairStats& r) {
     const int col = threadIdx.x;
+    if (exact) {                                                                      // rare: the read has N / IUPAC bases
+        for (int bi = 0; bi < nq; bi++) {
+            const uint64_t gi0 = Q.gi[bi][col], qn0 = Q.qn[bi][col];
+            const int32_t len = Q.len[bi][col], sbv = Q.sb[bi][col], sbase = sbv >> 1, side = sbv & 1;
+            int64_t ex = 0;
+            {   // first exception at or after the block's first base
+                int64_t lo = 0, hi = R.n_seqx;
+                while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (R.seqx_pos[mid] < qn0) lo = mid + 1; else hi = mid; }
+                ex = lo;
+            }
+            for (int32_t cc = gl; cc < len; cc += G) {
+                const uint8_t q = read_char_exact(R, qn0 + (uint64_t)cc, &ex), g = genome_char(Gn, gi0 + (uint64_t)cc);
+                if (q != g) {
+                    if (side == 0) { r.mism_l++; r.last_left = max(r.last_left, sbase + cc); }
+                    else           { r.mism_r++; r.first_right = min(r.first_right, sbase + cc); }
+                }
+            }
+        }
+        return;
+    }
     int bi = -1; int32_t k = 0, nchunk = 0, a0 = 0, sbase = 0, side = 0;
-    uint32_t o = 0; int32_t tl = 0;
-    uint64_t gi0 = 0; uint32_t Bh = 0, Bl = 0;                                        // big-endian halves of SEQ word k (G == 1: carried)
-    const uint64_t* gw = nullptr; const uint2* qw = nullptr;
+    uint32_t sh = 0; int32_t tl = 0;
+    uint32_t Bl = 0, Bh = 0;                                                          // read word k (G == 1: carried between chunks)
+    uint64_t gw0 = 0;                                                                 // index of the block's first genome word (32-base units)
+    const uint2* qw = nullptr;
     for (;;) {
         if (k >= nchunk) {                                                            // next block of this lane
             if (++bi >= nq) break;
-            gi0 = Q.gi[bi][col];
+            const uint64_t gi0 = Q.gi[bi][col];
             const int32_t len = Q.len[bi][col];
             const int32_t sbv = Q.sb[bi][col]; sbase = sbv >> 1; side = sbv & 1;
-            a0 = (int32_t)(gi0 & 15);                                                 // chunks are aligned to the genome words
-            nchunk = (a0 + len + 15) >> 4;
-            gw = Gn.g4 + ((gi0 - a0) >> 4);
-            // the SEQ nibbles of chunk k are the 64 bits at bit offset o of the big-endian words qw[k], qw[k + 1]: the offset
-            // is the same for every chunk of the block (the stream has a 16-byte lead pad and 16 bytes of tail slack)
-            const uint64_t qn0 = Q.qn[bi][col] - (uint64_t)a0;
-            const uintptr_t ad = reinterpret_cast<uintptr_t>(seq4) + (uintptr_t)(qn0 >> 1);
-            qw = reinterpret_cast<const uint2*>(ad & ~(uintptr_t)7);
-            o = (uint32_t)(ad & 7) * 8 + (uint32_t)(qn0 & 1) * 4;
+            a0 = (int32_t)(gi0 & 31);                                                 // chunks are aligned to the genome words
+            nchunk = (a0 + len + 31) >> 5;
+            gw0 = (gi0 - (uint64_t)a0) >> 5;
+            // the read bases of chunk k are the 64 bits at bit offset sh of the little-endian words qw[k], qw[k + 1]: the offset
+            // is the same for every chunk of the block
+            const uint64_t qb0 = Q.qn[bi][col] - (uint64_t)a0;
+            qw = reinterpret_cast<const uint2*>(R.seq2) + (qb0 >> 5);
+            sh = (uint32_t)(qb0 & 31) * 2;
             tl = a0 + len;                                                            // end column of the block in chunk coordinates
             k = gl;
             if (k >= nchunk) continue;
-            if (G == 1) { const uint2 v = __ldg(qw); Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123); }
+            if (G == 1) { const uint2 v = __ldg(qw); Bl = v.x; Bh = v.y; }
         }
-        if (G != 1) { const uint2 v = __ldg(qw + k); Bh = __byte_perm(v.x, 0, 0x0123); Bl = __byte_perm(v.y, 0, 0x0123); }
-        const uint2 cv = __ldg(qw + k + 1);                                           // consecutive chunks share a SEQ word: one load per chunk when G == 1
-        const uint32_t Ch = __byte_perm(cv.x, 0, 0x0123), Cl = __byte_perm(cv.y, 0, 0x0123);
-        // 64 bits at bit offset o of Bh:Bl:Ch:Cl, as two 32-bit funnel shifts
-        const bool up = (o & 32u) != 0; const uint32_t sh = o & 31u;
-        const uint32_t w0 = up ? Bl : Bh, w1 = up ? Ch : Bl, w2 = up ? Cl : Ch;
-        const uint64_t x = ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | (uint64_t)__funnelshift_l(w2, w1, sh);
-        if (G == 1) { Bh = Ch; Bl = Cl; }
-        const uint64_t g = __ldg(gw + k);
-        const int32_t tk = tl - 16 * k;                                               // valid columns from this chunk's start (>= 16: all)
-        const uint64_t V = M.first[k == 0 ? a0 : 0] & M.last[tk < 16 ? tk : 16];
-        uint64_t d = (x ^ g) & V;
-        const int32_t c0 = 16 * k - a0;                                               // column of nibble 0 of this chunk
-        if (Gn.n_zero_code) {                                                         // genome bytes outside the BAM alphabet (or '=')
-            uint64_t z = ~(g | (g >> 1) | (g >> 2) | (g >> 3)) & NIB1 & V;
-            while (z) {
-                const int t = (63 - (__ffsll((long long)z) - 1)) >> 2;
-                z &= z - 1;
-                const uint32_t nibq = (uint32_t)(x >> (60 - 4 * t)) & 0xfu;
-                const bool mm = (uint8_t)("=ACMGRSVTWYHKDBN"[nibq]) != genome_exc_lookup(Gn, gi0 + (uint64_t)(int64_t)(c0 + t));
-                d = (d & ~(0xfull << (60 - 4 * t))) | ((mm ? 0xfull : 0ull) << (60 - 4 * t));
-            }
+        if (G != 1) { const uint2 v = __ldg(qw + k); Bl = v.x; Bh = v.y; }
+        const uint2 cv = __ldg(qw + k + 1);                                           // consecutive chunks share a read word: one load per chunk when G == 1
+        // 64 bits at bit offset sh of Bl:Bh:Cl:Ch (little-endian), as two 32-bit funnel shifts
+        const bool up = (sh & 32u) != 0; const uint32_t s5 = sh & 31u;
+        const uint32_t w0 = up ? Bh : Bl, w1 = up ? cv.x : Bh, w2 = up ? cv.y : cv.x;
+        const uint64_t x = ((uint64_t)__funnelshift_r(w1, w2, s5) << 32) | (uint64_t)__funnelshift_r(w0, w1, s5);
+        if (G == 1) { Bl = cv.x; Bh = cv.y; }
+        const uint64_t g = __ldg(Gn.g2 + gw0 + k);
+        const int32_t tk = tl - 32 * k;                                               // valid columns from this chunk's start (>= 32: all)
+        uint64_t V = EVEN2;
+        if (k == 0) V &= ~0ull << (2 * a0);                                           // a0 columns before the block
+        if (tk < 32) V &= ~(~0ull << (2 * tk));
+        const uint64_t d = x ^ g;
+        uint64_t m = (d | (d >> 1)) & V;                                              // one bit (2c) per mismatching column c
+        if (Gn.any_gx) {                                                              // genome bases that are not A/C/G/T never equal a read base stored here
+            const uint64_t wi = gw0 + (uint64_t)k;
+            const uint32_t e32 = (uint32_t)(__ldg(Gn.gx + (wi >> 1)) >> ((wi & 1) * 32));
+            if (e32) m |= spread32(e32) & V;
         }
-        // One bit per mismatching column; count and extreme positions are updated with predicated arithmetic, not a branch: with 25
-        // lanes and 0.5 % substitutions some lane of the warp had a mismatch in 86 % of the chunks, so the branch was taken anyway,
-        // at 2-6 active lanes.  max / min, not assignment: insertions and deletions update the same fields during the walk.
-        uint64_t m = d | (d >> 1); m |= m >> 2; m &= NIB1;
+        // count and extreme positions with predicated arithmetic, not a branch: with 25 lanes and 0.5 % substitutions some lane of
+        // the warp has a mismatch in most chunks.  max / min, not assignment: insertions and deletions update the same fields in the walk.
         const uint32_t cnt = (uint32_t)__popcll(m);
-        const int32_t cb = sbase + c0;
-        const int32_t lastc = m ? cb + 15 - ((__ffsll((long long)m) - 1) >> 2) : -1;
-        const int32_t firstc = m ? cb + (__clzll((long long)m) >> 2) : INT32_MAX;
+        const int32_t cb = sbase + 32 * k - a0;                                       // string offset of this chunk's column 0
+        const int32_t lastc = m ? cb + ((63 - __clzll((long long)m)) >> 1) : -1;
+        const int32_t firstc = m ? cb + ((__ffsll((long long)m) - 1) >> 1) : INT32_MAX;
         if (side == 0) { r.mism_l += cnt; r.last_left = max(r.last_left, lastc); }
         else           { r.mism_r += cnt; r.first_right = min(r.first_right, firstc); }
         k += G;
@@ -1126,9 +1225,9 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, const MatchMasks& M, 
 // and every op the right walk accepts starts at or after rightStart > leftEnd, so the two walks touch disjoint ops while
 // rPos / qPos accumulate identically (bam_alignment.cc:349-399).
 template <int G>
-__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& M, const Genome& Gn, uint64_t gbase, int64_t glen,
+__device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, const Reads& R, bool exact, uint64_t gbase, int64_t glen,
                                                const uint32_t* __restrict__ cgn /* this junction's N op */, int32_t ops_before, int32_t ops_after,
-                                               int32_t start, int32_t qpos_n, const uint8_t* __restrict__ seq4, uint64_t seq_nib0, int32_t qsize,
+                                               int32_t start, int32_t qpos_n, uint64_t seq_b0, int32_t qsize,
                                                int32_t left, int32_t leftEnd, int32_t rightStart, int32_t right, int gl, uint32_t& err,
                                                uint32_t& cols_l, uint32_t& cols_r) {
     auto cigw = [&](int32_t rel) -> uint32_t { return __ldg(cgn + rel); };              // CIGAR word at offset `rel` from this junction's N op
@@ -1170,9 +1269,9 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
                 }
             } else {
                 if ((int64_t)rPos + len > glen) { err |= ERR_GENOME_RANGE; break; }
-                Q.qn[nq][col] = seq_nib0 + (uint64_t)qPos; Q.gi[nq][col] = gbase + (uint64_t)(uint32_t)rPos;
+                Q.qn[nq][col] = seq_b0 + (uint64_t)qPos; Q.gi[nq][col] = gbase + (uint64_t)(uint32_t)rPos;
                 Q.len[nq][col] = len; Q.sb[nq][col] = (int32_t)(cols << 1) | side;
-                if (++nq == MQ) { drain<G>(Q, M, nq, Gn, seq4, gl, r); nq = 0; }
+                if (++nq == MQ) { drain<G>(Q, nq, Gn, R, exact, gl, r); nq = 0; }
             }
             cols += (uint32_t)len;
         } else if (cr) {                                                                   // D or N inside the window: 'X' vs genome
@@ -1196,7 +1295,7 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const MatchMasks& 
         if (cr) rPos += L;
         if (cq) qPos += L;
     }
-    drain<G>(Q, M, nq, Gn, seq4, gl, r);
+    drain<G>(Q, nq, Gn, R, exact, gl, r);
     if (side == 0) cols_l = cols; else cols_r = cols;
     if (G > 1) {   // combine the lanes of the group
         const int lane = threadIdx.x & 31;
@@ -1216,9 +1315,6 @@ __global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* _
                                                 const PairRec* __restrict__ pr,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
     __shared__ MatchQueue Q;
-    __shared__ MatchMasks M;
-    init_match_masks(M);
-    __syncthreads();                                                 // the only block-wide barrier: before any thread leaves
     // Pairs are visited in EMIT order (= BAM order), not in junction order: the pair records are read coalesced, the SEQ / CIGAR streams
     // are walked almost sequentially (neighbouring threads hold neighbouring reads, and the N ops of one long read sit in one warp and
     // share its lines in L1), and the genome windows of neighbouring reads overlap.  Only the junction id (one 4-byte gather into an
@@ -1236,17 +1332,17 @@ __global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* _
     // the CIGAR window into shared memory with cp.async instead was measured on B200 and is slower in every variant — the wait
     // replaces the same first-touch latency and the extra shared memory costs resident warps; profiles/r2_history.md.)
     if (G == 1) {
-        const uint8_t* sp = R.seq4 + (c.seq_nib0 >> 1);
+        const uint8_t* sp = R.seq2 + (c.seq_b0 >> 2);
         prefetch_l1(R.cigar + c.cig_abs);
         prefetch_l1(sp);
-        if (d.qsize > 200) prefetch_l1(sp + 100);
+        if (d.qsize > 400) prefetch_l1(sp + 100);
     }
     const int32_t start = b.start, end = A.end[j], left = A.left[j], right = A.right[j];
     const int32_t tid = A.tid[j];
     if (G == 1) {   // genome words under the two anchors of this read (16 bases per 8-byte word)
         const uint64_t gb = Gn.goff[tid];
-        prefetch_l1(Gn.g4 + ((gb + (uint64_t)(uint32_t)max(left, a.pos)) >> 4));
-        prefetch_l1(Gn.g4 + ((gb + (uint64_t)(uint32_t)(end + 1)) >> 4));
+        prefetch_l1(Gn.g2 + ((gb + (uint64_t)(uint32_t)max(left, a.pos)) >> 5));
+        prefetch_l1(Gn.g2 + ((gb + (uint64_t)(uint32_t)(end + 1)) >> 5));
     }
     const int32_t lq = d.lq;
     uint32_t err = 0, mmes, minMatch, nbMism;
@@ -1260,8 +1356,8 @@ __global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* _
         if (glen < 0) err |= ERR_GENOME_RANGE;
         PairStats St{0u, 0u, -1, INT32_MAX}; uint32_t cols_l = 0, cols_r = 0;
         if (!err) {
-            St = walk_pair<G>(Q, M, Gn, Gn.goff[tid], glen, R.cigar + c.cig_abs, (int32_t)(d.nops & 0xffffu), (int32_t)(d.nops >> 16), start, c.qpos_n,
-                             R.seq4, c.seq_nib0, d.qsize, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
+            St = walk_pair<G>(Q, Gn, R, (b.bits & PB_SEQX) != 0u, Gn.goff[tid], glen, R.cigar + c.cig_abs, (int32_t)(d.nops & 0xffffu), (int32_t)(d.nops >> 16), start, c.qpos_n,
+                             c.seq_b0, d.qsize, left, leftEnd, rightStart, right, gl, err, cols_l, cols_r);
             if (cols_l == 0 || cols_r == 0) err |= ERR_EMPTY_ANCHOR;
         }
         const uint32_t upMatches = cols_l - St.mism_l, downMatches = cols_r - St.mism_r;

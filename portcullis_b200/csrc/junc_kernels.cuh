@@ -32,27 +32,23 @@ enum : uint32_t {
 };
 
 // ---- packed genome resident in HBM ----
-// Two views of the same upper-cased sequence are kept resident:
-//   * 2-bit plane + exception bitmask (g2/gx): splice-site motif and Hamming windows (k_finalize), 128-bit friendly;
-//   * 4-bit plane (g4) in the BAM SEQ alphabet: lets the per-read anchor comparison be a 64-bit XOR of 16 bases.
-// g2 : 2 bits per base (A=0,C=1,G=2,T=3), 32 bases per 64-bit word, little-endian within the word.
+// g2 : 2 bits per base (A=0,C=1,G=2,T=3), 32 bases per 64-bit word, little-endian within the word (base k at bits 2k, 2k+1).
 // gx : 1 bit per base, set when the upper-cased byte is not A/C/G/T; 64 bases per 64-bit word.
 //      For an exception base the 2-bit field holds a sub-code: 0 = 'N', 1 = any other byte, whose exact value lives
 //      in the sorted side table (exc_pos, exc_byte).  Soft-masking never reaches the device: the reference upper-cases
 //      every fetched window (junction.cc:586-587, 635-638).
+// The read side uses the same 2-bit code (Reads::seq2), so the anchor comparison of k_match is a 64-bit XOR of 32 bases; the
+// motif and Hamming windows of k_finalize read the same plane.  0.375 B per base: 1.2 GB for a 3.1 Gb genome.
 struct Genome {
     const uint64_t* g2;
     const uint64_t* gx;
-    const uint64_t* g4;         // 4 bits per base in the BAM SEQ alphabet, 16 bases per word, base 16w + k in bits 63-4k..60-4k (the order a
-                                // byte-swapped BAM SEQ word has, so only the read side needs the swap): the plane the
-                                // mismatch walk XORs against SEQ.  Code 0 = '=' or a byte outside "=ACMGRSVTWYHKDBN" (exact byte in the side table)
     const uint64_t* goff;       // [n_targets] first base index of each target (multiple of 64)
     const int64_t*  glen;       // [n_targets] sequence length from the FASTA (-1 when the target was not loaded)
     const uint64_t* exc_pos;    // sorted global base indices of "other" exception bytes
     const uint8_t*  exc_byte;
     int32_t n_exc;
     int32_t n_exc_x;            // how many of them are 'X'
-    int32_t n_zero_code;        // how many bases have g4 code 0 (needs the side table to compare exactly)
+    int32_t any_gx;             // != 0: some base of the genome is not A/C/G/T (the compare loop then also reads gx)
 };
 
 __device__ __forceinline__ uint8_t genome_exc_lookup(const Genome& g, uint64_t gi) {
@@ -68,19 +64,6 @@ __device__ __forceinline__ uint8_t genome_char(const Genome& g, uint64_t gi) {
     const uint32_t code = (uint32_t)(w2 >> ((gi & 31) * 2)) & 3u;
     if (!((wx >> (gi & 63)) & 1ull)) return (uint8_t)("ACGT"[code]);
     return code == 0 ? (uint8_t)'N' : genome_exc_lookup(g, gi);
-}
-
-// Does BAM nibble q (index into "=ACMGRSVTWYHKDBN", hts.c:82) print the same character as genome base gi?
-// This is the char compare of SeqUtils::hammingDistance / getNbMatchesFrom* (junction.cc:225-231, 263-280)
-// evaluated on the packed representation.
-__device__ __forceinline__ bool base_matches(const Genome& g, uint64_t gi, uint32_t q) {
-    const uint64_t w2 = __ldg(g.g2 + (gi >> 5));
-    const uint64_t wx = __ldg(g.gx + (gi >> 6));
-    const uint32_t code = (uint32_t)(w2 >> ((gi & 31) * 2)) & 3u;
-    if (!((wx >> (gi & 63)) & 1ull)) return q == (1u << code);
-    if (code == 0) return q == 15u;
-    const uint8_t b = genome_exc_lookup(g, gi);
-    return (uint8_t)("=ACMGRSVTWYHKDBN"[q]) == b;
 }
 
 // SeqUtils::reverseComplement lookup (seq_utils.hpp:33-40), index c-'A'; 0 for holes and out-of-range bytes.
@@ -107,9 +90,15 @@ struct Reads {
     const int32_t*  mpos;
     const uint32_t* cigar_off;
     const uint32_t* cigar;
-    const uint64_t* seq_off;
-    const uint8_t*  seq4;
+    const uint64_t* seq_off;    // n+1 byte offsets into seq2
+    const uint8_t*  seq2;       // read bases, 2 bits each (A=0,C=1,G=2,T=3; base q of a record at bits 2(q&3) of its byte q>>2), every record on a
+                                // byte boundary; the stream has a 16-byte lead pad and tail slack.  A base that is not A/C/G/T is stored as 0 and
+                                // listed in (seqx_pos, seqx_code); its record carries FLAG_SEQX in the flag column.
+    const uint64_t* seqx_pos;   // sorted base indices (byte offset * 4 + q) of the non-ACGT read bases
+    const uint8_t*  seqx_code;  // their BAM nibbles (index into "=ACMGRSVTWYHKDBN")
+    int64_t n_seqx;
 };
+constexpr uint32_t FLAG_SEQX = 0x8000u;   // flag column, bit 15 (unused by the SAM spec): the record has non-ACGT read bases
 
 // Per-(read, N-op) record, written once by the emit kernel in BAM order and gathered once per later stage.
 // Two 16-byte halves so that each is one 128-bit load.
@@ -117,14 +106,14 @@ struct __align__(16) PairA { uint32_t rid; int32_t lstart; int32_t rend; int32_t
 struct __align__(16) PairB { int32_t read_end; uint32_t bits; uint32_t updown; int32_t start; };
 // Junction-local view of the read for the anchor comparison (k_match): lets it start at the N op instead of re-walking the
 // whole CIGAR (long reads have dozens of ops and a pair per N op) and spares it the per-read column gathers.
-struct __align__(16) PairC { uint64_t seq_nib0; uint32_t cig_abs; int32_t qpos_n; };   // first nibble of the clipped query in the SEQ stream;
+struct __align__(16) PairC { uint64_t seq_b0; uint32_t cig_abs; int32_t qpos_n; };     // first base of the clipped query in the SEQ stream (base index);
                                                                                        // index of this N op in the CIGAR stream; query offset at it
 struct __align__(16) PairD { int32_t qsize; int32_t lq; uint32_t nops; uint32_t pad; }; // clipped query length (Q3); l_qseq; ops before | ops after << 16
 // The four 16-byte parts of one pair live in ONE 64-byte, 64-byte-aligned record: a gather touches two full 32-byte sectors of
 // one line instead of four half-used sectors in four arrays; the stage-1 reduction needs only the first sector (a, b).
 struct __align__(64) PairRec { PairA a; PairB b; PairC c; PairD d; };
 enum : uint32_t { PB_R1 = 1u << 0, PB_REV = 1u << 1, PB_MS = 1u << 2, PB_UM = 1u << 3, PB_BPP = 1u << 4, PB_PPP = 1u << 5,
-                  PB_XSP = 1u << 6, PB_XSN = 1u << 7 };
+                  PB_XSP = 1u << 6, PB_XSN = 1u << 7, PB_SEQX = 1u << 8 /* the read has non-ACGT bases: exact per-base compare */ };
 
 // BamAlignment::calcIfProperPair (bam_alignment.cc:271-292)
 __host__ __device__ __forceinline__ bool portcullis_proper_pair(uint32_t flag, int32_t tid, int32_t mtid, int32_t pos, int32_t mpos, int orientation) {

@@ -26,7 +26,7 @@ void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st);
 void launch_check_offsets(int64_t first, int64_t n, const uint32_t* cigar_off, const uint64_t* seq_off, uint64_t cig_lo, uint64_t cig_hi,
                           uint64_t seq_lo, uint64_t seq_hi, unsigned long long* bad, cudaStream_t st);
 void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st);
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint64_t* g4,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st);
 void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen, unsigned long long* n_nops, int n_sm, cudaStream_t st);
 uint32_t se_num_tiles(int64_t n);
@@ -40,6 +40,13 @@ size_t os_scratch_words(uint32_t n, int key_bits);
 int launch_onesweep_sort(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, uint32_t n, int key_bits,
                          uint32_t* scratch, int n_sm, cudaStream_t st, int* n_launches);
 uint32_t fs_num_tiles(uint32_t n);
+size_t fs_scratch_bytes(uint32_t n);
+void launch_cigar_off(uint32_t n, const uint16_t* ncig, uint32_t* cigar_off_at_R, uint32_t base, uint32_t expect, unsigned long long* bad, unsigned long long* scratch, cudaStream_t st);
+void launch_seq_off(uint32_t n, const uint32_t* cigar_off_at_R, const uint32_t* cigar, const int32_t* lq_at_R, uint64_t* seq_off_at_R, uint64_t base, uint64_t expect,
+                    unsigned long long* bad, unsigned long long* scratch, cudaStream_t st);
+void launch_seq4_to_2(int64_t n, const uint8_t* s4, const uint64_t* off4, const int32_t* lq, const uint64_t* seq_off, uint8_t* seq2, uint16_t* flag, uint32_t* xcount, cudaStream_t st);
+void launch_seq4_exceptions(int64_t n, const uint8_t* s4, const uint64_t* off4, const int32_t* lq, const uint64_t* seq_off, const uint32_t* xcount, const uint32_t* xoff,
+                            uint64_t* xpos, uint8_t* xcode, cudaStream_t st);
 void launch_segment(const uint64_t* keys, uint32_t n, uint32_t* jid, uint32_t* seg_start, uint32_t* n_junc_dev, unsigned long long* scratch, cudaStream_t st);
 void launch_entropy_index(uint32_t n, const uint32_t* eflag, uint32_t* eoff, uint32_t* epos, uint32_t* total_dev, unsigned long long* scratch, cudaStream_t st);
 void launch_seg_heads(const uint64_t* keys, uint32_t n, uint32_t* head, cudaStream_t st);

@@ -36,31 +36,50 @@ void free_slot(StagingSlot& s) {
     if (s.block) cudaFreeHost(s.block);
     s.block = nullptr; s.block_bytes = 0;
     s.tid = s.pos = s.l_qseq = s.mtid = s.mpos = nullptr; s.flag = nullptr; s.mapq = s.xs = s.seq4 = nullptr;
-    s.cigar_off = s.cigar = nullptr; s.seq_off = nullptr; s.name_code = nullptr; s.cap_rec = s.cap_cig = s.cap_seq = 0;
+    s.cigar_off = s.cigar = nullptr; s.seq_off = nullptr; s.name_code = nullptr; s.cap_rec = s.cap_cig = s.cap_seq = s.cap_seqx = 0;
+    s.n_cigar = nullptr; s.seq2 = nullptr; s.seqx_pos = nullptr; s.seqx_code = nullptr;
 }
 
-int alloc_slot(pj_ctx* c, StagingSlot& s, int64_t cr, int64_t cc, int64_t cs) {
-    if (cr <= s.cap_rec && cc <= s.cap_cig && cs <= s.cap_seq && s.block) return PJ_OK;
-    cr = std::max(cr + cr / 8, s.cap_rec); cc = std::max(cc + cc / 8, s.cap_cig); cs = std::max(cs + cs / 8, s.cap_seq);
+// One pinned block carved into the columns of a batch.  Classic slots hold the 13 columns of the original pj_batch; lean
+// slots hold what a lean batch ships (no tid / cigar_off / seq_off, n_cigar and seq2 + exceptions instead).
+int alloc_slot(pj_ctx* c, StagingSlot& s, bool lean, int64_t cr, int64_t cc, int64_t cs, int64_t cx) {
+    if (s.lean == lean && cr <= s.cap_rec && cc <= s.cap_cig && cs <= s.cap_seq && cx <= s.cap_seqx && s.block) return PJ_OK;
+    if (s.lean == lean) { cr = std::max(cr + cr / 8, s.cap_rec); cc = std::max(cc + cc / 8, s.cap_cig); cs = std::max(cs + cs / 8, s.cap_seq); cx = std::max(cx + cx / 8, s.cap_seqx); }
     free_slot(s);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t r = (size_t)cr;
-    const size_t sz[13] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r),
-                           up((r + 1) * 4), up((size_t)cc * 4), up((r + 1) * 8), up((size_t)cs + 16), c->extra ? up(r * 8) : 0};
-    size_t total = 0; for (size_t v : sz) total += v;
+    size_t sz[16]; int nsz = 0;
+    if (!lean) {
+        const size_t q[13] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r),
+                              up((r + 1) * 4), up((size_t)cc * 4), up((r + 1) * 8), up((size_t)cs + 16), c->extra ? up(r * 8) : 0};
+        for (size_t v : q) sz[nsz++] = v;
+    } else {
+        const size_t q[12] = {up(r * 4), up(r * 4), up(r * 4), up(r * 4), up(r * 2), up(r), up(r), up(r * 2),
+                              up((size_t)cc * 4), up((size_t)cs + 16), up((size_t)cx * 8 + 8) + up((size_t)cx + 8), c->extra ? up(r * 8) : 0};
+        for (size_t v : q) sz[nsz++] = v;
+    }
+    size_t total = 0; for (int k = 0; k < nsz; k++) total += sz[k];
     {
         const auto t0 = std::chrono::steady_clock::now();
         CU(c, cudaMallocHost((void**)&s.block, total));
         c->t_pinned_alloc_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); c->pinned_alloc_bytes += total; c->n_pinned_allocs++;
     }
-    s.block_bytes = total;
+    s.block_bytes = total; s.lean = lean;
     uint8_t* p = s.block; size_t k = 0;
-    s.tid = (int32_t*)p; p += sz[k++]; s.pos = (int32_t*)p; p += sz[k++]; s.l_qseq = (int32_t*)p; p += sz[k++]; s.mtid = (int32_t*)p; p += sz[k++];
-    s.mpos = (int32_t*)p; p += sz[k++]; s.flag = (uint16_t*)p; p += sz[k++]; s.mapq = p; p += sz[k++]; s.xs = p; p += sz[k++];
-    s.cigar_off = (uint32_t*)p; p += sz[k++]; s.cigar = (uint32_t*)p; p += sz[k++]; s.seq_off = (uint64_t*)p; p += sz[k++]; s.seq4 = p; p += sz[k++];
-    s.name_code = c->extra ? (uint64_t*)p : nullptr;
-    s.cap_rec = cr; s.cap_cig = cc; s.cap_seq = cs;
-    s.cigar_off[0] = 0; s.seq_off[0] = 0;
+    if (!lean) {
+        s.tid = (int32_t*)p; p += sz[k++]; s.pos = (int32_t*)p; p += sz[k++]; s.l_qseq = (int32_t*)p; p += sz[k++]; s.mtid = (int32_t*)p; p += sz[k++];
+        s.mpos = (int32_t*)p; p += sz[k++]; s.flag = (uint16_t*)p; p += sz[k++]; s.mapq = p; p += sz[k++]; s.xs = p; p += sz[k++];
+        s.cigar_off = (uint32_t*)p; p += sz[k++]; s.cigar = (uint32_t*)p; p += sz[k++]; s.seq_off = (uint64_t*)p; p += sz[k++]; s.seq4 = p; p += sz[k++];
+        s.name_code = c->extra ? (uint64_t*)p : nullptr;
+        s.cigar_off[0] = 0; s.seq_off[0] = 0;
+    } else {
+        s.pos = (int32_t*)p; p += sz[k++]; s.l_qseq = (int32_t*)p; p += sz[k++]; s.mtid = (int32_t*)p; p += sz[k++]; s.mpos = (int32_t*)p; p += sz[k++];
+        s.flag = (uint16_t*)p; p += sz[k++]; s.mapq = p; p += sz[k++]; s.xs = p; p += sz[k++]; s.n_cigar = (uint16_t*)p; p += sz[k++];
+        s.cigar = (uint32_t*)p; p += sz[k++]; s.seq2 = p; p += sz[k++];
+        s.seqx_pos = (uint64_t*)p; s.seqx_code = p + up((size_t)cx * 8 + 8); p += sz[k++];
+        s.name_code = c->extra ? (uint64_t*)p : nullptr;
+    }
+    s.cap_rec = cr; s.cap_cig = cc; s.cap_seq = cs; s.cap_seqx = cx;
     return PJ_OK;
 }
 
@@ -77,8 +96,10 @@ void mark(pj_ctx* c, const char* name) {
 int finish_genome(pj_ctx* c) {
     if (!c->genome_dirty) return PJ_OK;
     CU(c, cudaStreamSynchronize(c->genome_stream));
-    uint32_t cnt = 0;
-    CU(c, cudaMemcpy(&cnt, c->d_exc_count, sizeof cnt, cudaMemcpyDeviceToHost));
+    uint32_t cnt2[2] = {0, 0};
+    CU(c, cudaMemcpy(cnt2, c->d_exc_count, sizeof cnt2, cudaMemcpyDeviceToHost));
+    const uint32_t cnt = cnt2[0];
+    c->any_gx = cnt2[1] ? 1 : 0;
     if (cnt > c->exc_cap)
         return fail(c, PJ_EDATA, "genome holds %u bytes outside ACGTN after upper-casing (limit %u): not a nucleotide FASTA?", cnt, c->exc_cap);
     std::vector<uint64_t> pos(cnt); std::vector<uint8_t> byt(cnt);
@@ -92,8 +113,7 @@ int finish_genome(pj_ctx* c) {
         CU(c, cudaMemcpy(c->d_exc_pos, p2.data(), cnt * sizeof(uint64_t), cudaMemcpyHostToDevice));
         CU(c, cudaMemcpy(c->d_exc_byte, b2.data(), cnt, cudaMemcpyHostToDevice));
         c->n_exc_x = (int32_t)std::count(b2.begin(), b2.end(), (uint8_t)'X');
-        c->n_zero_code = (int32_t)std::count_if(b2.begin(), b2.end(), [](uint8_t b) { return b == '=' || !strchr("ACMGRSVTWYHKDBN", (int)b); });
-    } else { c->n_exc_x = 0; c->n_zero_code = 0; }
+    } else c->n_exc_x = 0;
     c->n_exc = (int32_t)cnt;
     c->genome_dirty = false;
     return PJ_OK;
@@ -155,7 +175,8 @@ void pj_destroy(pj_ctx* c) {
     cudaDeviceSynchronize();
     lap("sync");
     c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
-    c->seq4.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_(); c->name_code.free_();
+    c->seq2.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_(); c->name_code.free_();
+    c->seqx_pos.free_(); c->seqx_code.free_(); c->tmp_seq4.free_(); c->tmp_off4.free_(); c->tmp_xcount.free_(); c->tmp_xoff.free_(); c->tmp_scan.free_(); c->tmp_ncig.free_(); c->tmp_fs.free_();
     extra_reset(c);
     lap("arena");
     for (StagingSlot* sl : c->slots) { free_slot(*sl); if (sl->done) cudaEventDestroy(sl->done); delete sl; }
@@ -164,7 +185,7 @@ void pj_destroy(pj_ctx* c) {
     for (int s = 0; s < 2; s++) { if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
                                   if (c->h_graw[s]) cudaFreeHost(c->h_graw[s]); if (c->d_graw[s]) cudaFree(c->d_graw[s]); }
     lap("genome staging");
-    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx); cudaFree(c->d_g4);
+    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx);
     cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
     cudaFree(c->d_spliced); cudaFree(c->d_unspliced); cudaFree(c->d_sumq); cudaFree(c->d_minq); cudaFree(c->d_maxq);
     cudaFree(c->d_scalars); cudaFree(c->d_shard_acc); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
@@ -237,9 +258,8 @@ int pj_targets_set(pj_ctx* c, int32_t n_targets, const int32_t* target_len) {
     CU(c, cudaMemcpy(c->d_glen, c->h_glen.data(), n_targets * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(c, cudaMalloc(&c->d_g2, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMalloc(&c->d_gx, g / 64 * sizeof(uint64_t) + 64));
     CU(c, cudaMemset(c->d_g2, 0, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMemset(c->d_gx, 0, g / 64 * sizeof(uint64_t) + 64));
-    CU(c, cudaMalloc(&c->d_g4, g / 2 + 64)); CU(c, cudaMemset(c->d_g4, 0, g / 2 + 64));
     CU(c, cudaMalloc(&c->d_exc_pos, c->exc_cap * sizeof(uint64_t))); CU(c, cudaMalloc(&c->d_exc_byte, c->exc_cap));
-    CU(c, cudaMalloc(&c->d_exc_count, sizeof(uint32_t))); CU(c, cudaMemset(c->d_exc_count, 0, sizeof(uint32_t)));
+    CU(c, cudaMalloc(&c->d_exc_count, 2 * sizeof(uint32_t))); CU(c, cudaMemset(c->d_exc_count, 0, 2 * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->d_spliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_unspliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_sumq, n_targets * 8));
     CU(c, cudaMalloc(&c->d_minq, n_targets * 4)); CU(c, cudaMalloc(&c->d_maxq, n_targets * 4));
     return PJ_OK;
@@ -257,7 +277,7 @@ int pj_genome_set_target(pj_ctx* c, int32_t tid, const char* bases, int64_t n_ba
         CU(c, cudaEventSynchronize(c->graw_ev[s]));                  // slot free again?
         memcpy(c->h_graw[s], bases + o, (size_t)k);
         CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->genome_stream));
-        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_g4, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->genome_stream);
+        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->genome_stream);
         CU(c, cudaEventRecord(c->graw_ev[s], c->genome_stream));
     }
     c->h_glen[tid] = n_bases < c->h_tlen[tid] ? n_bases : (int64_t)c->h_tlen[tid];
@@ -272,8 +292,8 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->compute_stream));
     extra_reset(c);
-    c->n_rec = 0; c->n_cig = 0; c->n_seq = 16; c->have_result = false;   // SEQ stream: 16-byte lead pad (k_match may look back up to 15 nibbles)
-    c->n_junc = 0; c->n_pairs = 0;
+    c->n_rec = 0; c->n_cig = 0; c->n_seq = 16; c->have_result = false;   // SEQ stream: 16-byte lead pad (k_match may look back up to 31 bases)
+    c->n_junc = 0; c->n_pairs = 0; c->n_seqx = 0;
     cudaStream_t st = c->copy_stream;
     const size_t r = (size_t)std::max<int64_t>(n_records_hint, 1024);
     int rc;
@@ -281,12 +301,12 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
         (rc = ensure(c, c->mtid, r, 0, st)) || (rc = ensure(c, c->mpos, r, 0, st)) || (rc = ensure(c, c->flag, r, 0, st)) ||
         (rc = ensure(c, c->mapq, r, 0, st)) || (rc = ensure(c, c->xs, r, 0, st)) || (rc = ensure(c, c->cigar_off, r + 1, 0, st)) ||
         (rc = ensure(c, c->seq_off, r + 1, 0, st)) || (rc = ensure(c, c->cigar, (size_t)std::max<int64_t>(n_cigar_hint, 1024) + 64, 0, st)) ||
-        (rc = ensure(c, c->seq4, (size_t)std::max<int64_t>(n_seq_bytes_hint, 1024) + 256, 0, st))) return rc;   // slack: k_match stages 16-byte chunks that may reach past the last record
+        (rc = ensure(c, c->seq2, (size_t)std::max<int64_t>(n_seq_bytes_hint / 2, 1024) + 256, 0, st))) return rc;   // the hint counts 4-bit bytes; the stream holds 2 bits per base
     if (c->extra && (rc = ensure(c, c->name_code, r, 0, st))) return rc;
     CU(c, cudaMemsetAsync(c->cigar_off.p, 0, sizeof(uint32_t), st));
     CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 4 * sizeof(unsigned long long), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
-    CU(c, cudaMemsetAsync(c->seq4.p, 0, 16, st));                       // the lead pad is read (and masked out) by k_match: keep it defined
+    CU(c, cudaMemsetAsync(c->seq2.p, 0, 16, st));                       // the lead pad is read (and masked out) by k_match: keep it defined
     // Pre-grow the stream-ordered pool that pj_shard_run allocates its temporaries from (about 12 B per record and 80 B
     // per read-junction pair): a cold pool costs hundreds of milliseconds for a multi-GB shard, and this way the growth
     // overlaps the caller's decode instead of sitting in front of the first kernel.
@@ -307,8 +327,8 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     return PJ_OK;
 }
 
-int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out) {
-    if (!c || !out || cap_records < 0 || cap_cigar < 0 || cap_seq_bytes < 0) return fail(c, PJ_EINVAL, "pj_staging_acquire: bad arguments");
+static int staging_acquire(pj_ctx* c, bool lean, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, int64_t cap_seqx, pj_batch* out) {
+    if (!c || !out || cap_records < 0 || cap_cigar < 0 || cap_seq_bytes < 0 || cap_seqx < 0) return fail(c, PJ_EINVAL, "pj_staging_acquire: bad arguments");
     CU(c, cudaSetDevice(c->device));
     std::lock_guard<std::mutex> lk(c->staging_mu);
     StagingSlot* pick = nullptr;
@@ -316,7 +336,7 @@ int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_
         StagingSlot* oldest = nullptr;
         for (StagingSlot* sl : c->slots) {
             if (sl->state == 2 && cudaEventQuery(sl->done) == cudaSuccess) sl->state = 0;
-            if (sl->state == 0 && (!pick || sl->cap_seq > pick->cap_seq)) pick = sl;      // prefer the roomiest free slot
+            if (sl->state == 0 && (!pick || (sl->lean == lean && pick->lean != lean) || (sl->lean == pick->lean && sl->cap_seq > pick->cap_seq))) pick = sl;   // prefer a slot of the right kind, then the roomiest
             if (sl->state == 2 && (!oldest || sl->seq_no < oldest->seq_no)) oldest = sl;
         }
         if (pick) break;
@@ -331,14 +351,22 @@ int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_
         CU(c, cudaEventSynchronize(oldest->done));
         oldest->state = 0;
     }
-    int rc = alloc_slot(c, *pick, std::max<int64_t>(cap_records, 1), std::max<int64_t>(cap_cigar, 1), std::max<int64_t>(cap_seq_bytes, 1));
+    int rc = alloc_slot(c, *pick, lean, std::max<int64_t>(cap_records, 1), std::max<int64_t>(cap_cigar, 1), std::max<int64_t>(cap_seq_bytes, 1), std::max<int64_t>(cap_seqx, 1));
     if (rc) return rc;
     pick->state = 1;
     StagingSlot& s = *pick;
+    memset(out, 0, sizeof *out);
     out->n_records = 0; out->tid = s.tid; out->pos = s.pos; out->flag = s.flag; out->mapq = s.mapq; out->xs = s.xs; out->l_qseq = s.l_qseq;
     out->mtid = s.mtid; out->mpos = s.mpos; out->cigar_off = s.cigar_off; out->cigar = s.cigar; out->seq_off = s.seq_off; out->seq4 = s.seq4;
     out->name_code = s.name_code;
+    out->lean = lean ? 1 : 0; out->n_cigar = s.n_cigar; out->seq2 = s.seq2; out->seqx_pos = s.seqx_pos; out->seqx_code = s.seqx_code;
     return PJ_OK;
+}
+int pj_staging_acquire(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq_bytes, pj_batch* out) {
+    return staging_acquire(c, false, cap_records, cap_cigar, cap_seq_bytes, 0, out);
+}
+int pj_staging_acquire_lean(pj_ctx* c, int64_t cap_records, int64_t cap_cigar, int64_t cap_seq2_bytes, int64_t cap_seqx, pj_batch* out) {
+    return staging_acquire(c, true, cap_records, cap_cigar, cap_seq2_bytes, cap_seqx, out);
 }
 
 int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
@@ -347,15 +375,34 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
     const int64_t n = b->n_records;
     if (n < 0) return fail(c, PJ_EINVAL, "pj_batch_submit: negative record count");
     if (n == 0) return PJ_OK;
-    if (!b->tid || !b->pos || !b->flag || !b->mapq || !b->xs || !b->l_qseq || !b->mtid || !b->mpos || !b->cigar_off || !b->seq_off)
-        return fail(c, PJ_EINVAL, "pj_batch_submit: null column");
+    if (n >= (1ll << 31)) return fail(c, PJ_EINVAL, "pj_batch_submit: more than 2^31 records in one batch");
+    const bool lean = b->lean != 0;
+    const bool oriented = c->orientation == PJ_ORIENT_FR || c->orientation == PJ_ORIENT_RF || c->orientation == PJ_ORIENT_FF;
+    if (!b->pos || !b->flag || !b->mapq || !b->xs || !b->l_qseq) return fail(c, PJ_EINVAL, "pj_batch_submit: null column");
+    if ((!lean || oriented) && (!b->mtid || !b->mpos)) return fail(c, PJ_EINVAL, "pj_batch_submit: mtid / mpos are required (the orientation enables the proper-pair rule)");
+    if (!lean && (!b->tid || !b->cigar_off || !b->seq_off)) return fail(c, PJ_EINVAL, "pj_batch_submit: null column");
+    if (lean && (!b->n_cigar || b->n_cigar_total < 0 || b->n_seq2_bytes < 0 || b->n_seqx < 0 || (b->n_seqx && (!b->seqx_pos || !b->seqx_code)) ||
+                 b->const_tid < 0 || b->const_tid >= c->n_targets))
+        return fail(c, PJ_EINVAL, "pj_batch_submit: malformed lean batch");
     if (c->extra && !b->name_code) return fail(c, PJ_EINVAL, "pj_batch_submit: the context computes the extra metrics, so batches must carry name_code");
     CU(c, cudaSetDevice(c->device));
-    const uint32_t cb = b->cigar_off[0], ce = b->cigar_off[n];
-    const uint64_t sb = b->seq_off[0], se = b->seq_off[n];
-    if (ce < cb || se < sb) return fail(c, PJ_EINVAL, "pj_batch_submit: offsets not monotone");
-    const uint64_t ncig = ce - cb, nseq = se - sb;
-    if ((ncig && !b->cigar) || (nseq && !b->seq4)) return fail(c, PJ_EINVAL, "pj_batch_submit: null cigar/seq column");
+    uint64_t cb = 0, ncig, sb = 0, nseq4 = 0, nseq2;
+    std::vector<uint64_t> off2;                                   // classic batches: offsets of the records in the 2-bit stream, formed here
+    if (!lean) {
+        cb = b->cigar_off[0]; const uint64_t ce = b->cigar_off[n];
+        sb = b->seq_off[0]; const uint64_t se = b->seq_off[n];
+        if (ce < cb || se < sb) return fail(c, PJ_EINVAL, "pj_batch_submit: offsets not monotone");
+        ncig = ce - cb; nseq4 = se - sb;
+        // a record's SEQ enters the stream when it is complete ((l_qseq + 1) / 2 bytes); anything shorter counts as missing
+        off2.resize((size_t)n + 1); off2[0] = c->n_seq;
+        for (int64_t i = 0; i < n; i++) {
+            const uint64_t a = b->seq_off[i], e = b->seq_off[i + 1]; const int32_t l = b->l_qseq[i];
+            const uint64_t n4 = e >= a ? e - a : 0;
+            off2[(size_t)i + 1] = off2[(size_t)i] + ((n4 > 0 && l > 0 && n4 >= (uint64_t)((l + 1) >> 1)) ? (uint64_t)((l + 3) >> 2) : 0ull);
+        }
+        nseq2 = off2[(size_t)n] - c->n_seq;
+    } else { ncig = (uint64_t)b->n_cigar_total; nseq2 = (uint64_t)b->n_seq2_bytes; }
+    if ((ncig && !b->cigar) || (nseq4 && !b->seq4) || (lean && nseq2 && !b->seq2)) return fail(c, PJ_EINVAL, "pj_batch_submit: null cigar/seq column");
     if (c->n_cig + ncig > 0xfffffff0ull) return fail(c, PJ_EINVAL, "pj_batch_submit: more than 2^32 CIGAR operations in one shard");
     cudaStream_t st = c->copy_stream;
     const size_t R = (size_t)c->n_rec, need = R + (size_t)n;
@@ -364,31 +411,70 @@ int pj_batch_submit(pj_ctx* c, const pj_batch* b) {
         (rc = ensure(c, c->mtid, need, R, st)) || (rc = ensure(c, c->mpos, need, R, st)) || (rc = ensure(c, c->flag, need, R, st)) ||
         (rc = ensure(c, c->mapq, need, R, st)) || (rc = ensure(c, c->xs, need, R, st)) || (rc = ensure(c, c->cigar_off, need + 1, R + 1, st)) ||
         (rc = ensure(c, c->seq_off, need + 1, R + 1, st)) || (rc = ensure(c, c->cigar, (size_t)(c->n_cig + ncig) + 64, (size_t)c->n_cig, st)) ||
-        (rc = ensure(c, c->seq4, (size_t)(c->n_seq + nseq) + 256, (size_t)c->n_seq, st))) return rc;
+        (rc = ensure(c, c->seq2, (size_t)(c->n_seq + nseq2) + 256, (size_t)c->n_seq, st))) return rc;
     if (c->extra && (rc = ensure(c, c->name_code, need, R, st))) return rc;
     const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
-    CU(c, cudaMemcpyAsync(c->tid.p + R, b->tid, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->pos.p + R, b->pos, n * 4, H2D, st));
-    CU(c, cudaMemcpyAsync(c->l_qseq.p + R, b->l_qseq, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->mtid.p + R, b->mtid, n * 4, H2D, st));
-    CU(c, cudaMemcpyAsync(c->mpos.p + R, b->mpos, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->flag.p + R, b->flag, n * 2, H2D, st));
+    CU(c, cudaMemcpyAsync(c->pos.p + R, b->pos, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->l_qseq.p + R, b->l_qseq, n * 4, H2D, st));
+    CU(c, cudaMemcpyAsync(c->flag.p + R, b->flag, n * 2, H2D, st));
     CU(c, cudaMemcpyAsync(c->mapq.p + R, b->mapq, n, H2D, st)); CU(c, cudaMemcpyAsync(c->xs.p + R, b->xs, n, H2D, st));
+    if (b->mtid && b->mpos) { CU(c, cudaMemcpyAsync(c->mtid.p + R, b->mtid, n * 4, H2D, st)); CU(c, cudaMemcpyAsync(c->mpos.p + R, b->mpos, n * 4, H2D, st)); }
+    else { CU(c, cudaMemsetAsync(c->mtid.p + R, 0xff, n * 4, st)); CU(c, cudaMemsetAsync(c->mpos.p + R, 0xff, n * 4, st)); }   // never read without an orientation
     if (c->extra) CU(c, cudaMemcpyAsync(c->name_code.p + R, b->name_code, n * 8, H2D, st));
-    CU(c, cudaMemcpyAsync(c->cigar_off.p + R + 1, b->cigar_off + 1, n * 4, H2D, st));
-    CU(c, cudaMemcpyAsync(c->seq_off.p + R + 1, b->seq_off + 1, n * 8, H2D, st));
     if (ncig) {
         CU(c, cudaMemcpyAsync(c->cigar.p + c->n_cig, b->cigar + cb, ncig * 4, H2D, st));
         launch_prescan_cigar(c->cigar.p + c->n_cig, ncig, reinterpret_cast<uint32_t*>(c->d_shard_acc), c->d_shard_acc + 1, c->n_sm, st);
     }
-    if (nseq) CU(c, cudaMemcpyAsync(c->seq4.p + c->n_seq, b->seq4 + sb, nseq, H2D, st));
-    launch_rebase_u32(c->cigar_off.p + R + 1, n, (uint32_t)c->n_cig - cb, st);
-    launch_rebase_u64(c->seq_off.p + R + 1, n, c->n_seq - sb, st);
-    // the prefix columns of the batch must stay inside what was copied (a malformed batch must not send the kernels out of the arena)
-    launch_check_offsets((int64_t)R, n, c->cigar_off.p, c->seq_off.p, c->n_cig, c->n_cig + ncig, c->n_seq, c->n_seq + nseq, c->d_shard_acc + 2, st);
+    int64_t new_seqx = 0;
+    if (!lean) {
+        CU(c, cudaMemcpyAsync(c->tid.p + R, b->tid, n * 4, H2D, st));
+        CU(c, cudaMemcpyAsync(c->cigar_off.p + R + 1, b->cigar_off + 1, n * 4, H2D, st));
+        launch_rebase_u32(c->cigar_off.p + R + 1, n, (uint32_t)c->n_cig - (uint32_t)cb, st);
+        // 4-bit SEQ -> 2-bit stream on the device (the prefix offsets of both forms come from the host)
+        if ((rc = ensure(c, c->tmp_off4, (size_t)n + 1, 0, st)) || (rc = ensure(c, c->tmp_seq4, (size_t)nseq4 + 16, 0, st)) ||
+            (rc = ensure(c, c->tmp_xcount, (size_t)n, 0, st)) || (rc = ensure(c, c->tmp_xoff, (size_t)n, 0, st)) ||
+            (rc = ensure(c, c->tmp_scan, (size_t)scan_tmp_elems((uint64_t)n) + 4, 0, st))) return rc;
+        CU(c, cudaMemcpyAsync(c->seq_off.p + R + 1, off2.data() + 1, n * 8, H2D, st));
+        CU(c, cudaMemcpyAsync(c->tmp_off4.p, b->seq_off, (n + 1) * 8, H2D, st));
+        if (nseq4) CU(c, cudaMemcpyAsync(c->tmp_seq4.p, b->seq4 + sb, nseq4, H2D, st));
+        // the prefix columns of the batch must stay inside what was copied (a malformed batch must not send the kernels out of the arena)
+        launch_check_offsets(0, n, c->cigar_off.p + R, c->tmp_off4.p, c->n_cig, c->n_cig + ncig, sb, sb + nseq4, c->d_shard_acc + 2, st);
+        unsigned long long bad = 0;
+        CU(c, cudaMemcpyAsync(&bad, c->d_shard_acc + 2, sizeof bad, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        if (bad) return fail(c, PJ_EINVAL, "pj_batch_submit: cigar_off / seq_off are not non-decreasing prefix offsets within the batch's cigar / seq4 arrays");
+        launch_seq4_to_2(n, c->tmp_seq4.p, c->tmp_off4.p, c->l_qseq.p + R, c->seq_off.p + R, c->seq2.p, c->flag.p + R, c->tmp_xcount.p, st);
+        launch_exclusive_scan(c->tmp_xcount.p, c->tmp_xoff.p, (uint64_t)n, c->tmp_scan.p, c->tmp_scan.p + scan_tmp_elems((uint64_t)n), st);
+        uint32_t nx = 0;
+        CU(c, cudaMemcpyAsync(&nx, c->tmp_scan.p + scan_tmp_elems((uint64_t)n), sizeof nx, cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+        if (nx) {
+            if ((rc = ensure(c, c->seqx_pos, (size_t)c->n_seqx + nx, (size_t)c->n_seqx, st)) || (rc = ensure(c, c->seqx_code, (size_t)c->n_seqx + nx, (size_t)c->n_seqx, st))) return rc;
+            launch_seq4_exceptions(n, c->tmp_seq4.p, c->tmp_off4.p, c->l_qseq.p + R, c->seq_off.p + R, c->tmp_xcount.p, c->tmp_xoff.p,
+                                   c->seqx_pos.p + c->n_seqx, c->seqx_code.p + c->n_seqx, st);
+            new_seqx = nx;
+        }
+    } else {
+        launch_fill_i32(c->tid.p + R, n, b->const_tid, st);
+        if ((rc = ensure(c, c->tmp_ncig, (size_t)n, 0, st)) || (rc = ensure(c, c->tmp_fs, fs_scratch_bytes((uint32_t)n) / 8 + 2, 0, st))) return rc;
+        CU(c, cudaMemcpyAsync(c->tmp_ncig.p, b->n_cigar, n * 2, H2D, st));
+        launch_cigar_off((uint32_t)n, c->tmp_ncig.p, c->cigar_off.p + R, (uint32_t)c->n_cig, (uint32_t)ncig, c->d_shard_acc + 2, c->tmp_fs.p, st);
+        if (nseq2) CU(c, cudaMemcpyAsync(c->seq2.p + c->n_seq, b->seq2, nseq2, H2D, st));
+        launch_seq_off((uint32_t)n, c->cigar_off.p + R, c->cigar.p, c->l_qseq.p + R, c->seq_off.p + R, c->n_seq, nseq2, c->d_shard_acc + 2, c->tmp_fs.p, st);
+        if (b->n_seqx) {
+            const size_t nx = (size_t)b->n_seqx;
+            if ((rc = ensure(c, c->seqx_pos, (size_t)c->n_seqx + nx, (size_t)c->n_seqx, st)) || (rc = ensure(c, c->seqx_code, (size_t)c->n_seqx + nx, (size_t)c->n_seqx, st))) return rc;
+            CU(c, cudaMemcpyAsync(c->seqx_pos.p + c->n_seqx, b->seqx_pos, nx * 8, H2D, st));
+            CU(c, cudaMemcpyAsync(c->seqx_code.p + c->n_seqx, b->seqx_code, nx, H2D, st));
+            launch_rebase_u64(c->seqx_pos.p + c->n_seqx, (int64_t)nx, c->n_seq * 4ull, st);
+            new_seqx = (int64_t)nx;
+        }
+    }
     CU(c, cudaGetLastError());
     {
         std::lock_guard<std::mutex> lk(c->staging_mu);
-        for (StagingSlot* sl : c->slots) if (b->tid == sl->tid) { CU(c, cudaEventRecord(sl->done, st)); sl->state = 2; sl->seq_no = ++c->submit_seq; }
+        for (StagingSlot* sl : c->slots) if (b->pos == sl->pos) { CU(c, cudaEventRecord(sl->done, st)); sl->state = 2; sl->seq_no = ++c->submit_seq; }
     }
-    c->n_rec += n; c->n_cig += ncig; c->n_seq += nseq;
+    c->n_rec += n; c->n_cig += ncig; c->n_seq += nseq2; c->n_seqx += new_seqx;
     return PJ_OK;
 }
 
@@ -398,7 +484,7 @@ int pj_shard_run(pj_ctx* c) {
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     int rc = finish_genome(c); if (rc) return rc;
     cudaStream_t st = c->compute_stream;
-    CU(c, cudaMemsetAsync(c->seq4.p + c->n_seq, 0, 16, c->copy_stream));  // tail slack of the SEQ stream: read in 8-byte words, masked out
+    CU(c, cudaMemsetAsync(c->seq2.p + c->n_seq, 0, 16, c->copy_stream));  // tail slack of the SEQ stream: read in 8-byte words, masked out
     CU(c, cudaEventRecord(c->copies_done, c->copy_stream));
     CU(c, cudaStreamWaitEvent(st, c->copies_done, 0));
     c->n_stage = 0; c->n_launches = 0; c->have_result = false;
@@ -410,7 +496,8 @@ int pj_shard_run(pj_ctx* c) {
     CU(c, cudaMemsetAsync(c->d_maxq, 0, T * 4, st));
     launch_fill_i32(c->d_minq, T, INT32_MAX, st); c->n_launches++;
     CU(c, cudaMemsetAsync(c->d_scalars, 0, 16 * sizeof(uint32_t), st));
-    Reads Rd{R, c->tid.p, c->pos.p, c->flag.p, c->mapq.p, c->xs.p, c->l_qseq.p, c->mtid.p, c->mpos.p, c->cigar_off.p, c->cigar.p, c->seq_off.p, c->seq4.p};
+    Reads Rd{R, c->tid.p, c->pos.p, c->flag.p, c->mapq.p, c->xs.p, c->l_qseq.p, c->mtid.p, c->mpos.p, c->cigar_off.p, c->cigar.p, c->seq_off.p, c->seq2.p,
+             c->seqx_pos.p, c->seqx_code.p, c->n_seqx};
     TargetAcc TA{c->d_spliced, c->d_unspliced, c->d_sumq, c->d_minq, c->d_maxq};
     uint32_t* d_err = c->d_scalars + 0; uint32_t* d_P = c->d_scalars + 2;
     uint32_t* d_J = c->d_scalars + 3; uint32_t* d_E = c->d_scalars + 4; uint32_t* d_tmp_total = c->d_scalars + 5;
@@ -434,7 +521,7 @@ int pj_shard_run(pj_ctx* c) {
         unsigned long long acc[3] = {0, 0, 0};
         CU(c, cudaStreamSynchronize(c->copy_stream));
         CU(c, cudaMemcpy(acc, c->d_shard_acc, sizeof acc, cudaMemcpyDeviceToHost));
-        if (acc[2]) return fail(c, PJ_EINVAL, "pj_shard_run: a submitted batch has cigar_off / seq_off columns that are not non-decreasing prefix offsets within its cigar / seq4 arrays");
+        if (acc[2]) return fail(c, PJ_EINVAL, "pj_shard_run: a submitted batch is inconsistent (prefix offsets outside its arrays, or the n_cigar / seq2 totals of a lean batch do not match its records)");
         const uint32_t maxN = (uint32_t)(acc[0] & 0xffffffffull);
         if (acc[1] >= 0xfffffff0ull) return fail(c, PJ_EINVAL, "pj_shard_run: more than 2^32 read-junction pairs in one shard");
         len_bits = std::max(1, bit_length(maxN)); key_bits = len_bits + gbits;
@@ -510,13 +597,15 @@ int pj_shard_run(pj_ctx* c) {
         }
         launch_entropy_sum(J, seg_start, eoff, epos, entropy, st); c->n_launches++;
         mark(c, "entropy");
-        Genome G{c->d_g2, c->d_gx, c->d_g4, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->n_zero_code};
+        Genome G{c->d_g2, c->d_gx, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->any_gx};
         uint4* pm = nullptr; CU(c, cudaMallocAsync(&pm, (size_t)P * sizeof(uint4), st));
         {   // lanes per (read, junction) pair: one 16-base word per lane and step; long reads get wider groups
             int group = c->match_group;
             if (group <= 0) {
-                const double bases_per_pair = 2.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
-                group = bases_per_pair <= 400 ? 1 : bases_per_pair <= 1200 ? 4 : bases_per_pair <= 4000 ? 8 : 32;
+                // one lane per pair wins on every preset measured (c5, 1-10 kb reads: G = 1 / 2 / 4 / 8 -> 7.5 / 8.2 / 10.2 / 13.3 ms); wider groups
+                // only for extreme anchors
+                const double bases_per_pair = 4.0 * (double)c->n_seq / (double)P;      // read bases available per pair (lower bound on read length)
+                group = bases_per_pair <= 4000 ? 1 : 8;
             }
             static const int match_ctas = [] { const char* e = getenv("PJ_MATCH_CTAS"); return e ? atoi(e) : 0; }();
             launch_match(P, group, match_ctas, inv, vals, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;

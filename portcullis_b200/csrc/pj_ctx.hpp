@@ -25,7 +25,9 @@ struct StagingSlot {
     uint16_t* flag = nullptr; uint8_t *mapq = nullptr, *xs = nullptr;
     uint32_t *cigar_off = nullptr, *cigar = nullptr; uint64_t* seq_off = nullptr; uint8_t* seq4 = nullptr;
     uint64_t* name_code = nullptr;         // only when the context computes the `--extra` metrics
-    int64_t cap_rec = 0, cap_cig = 0, cap_seq = 0;
+    uint16_t* n_cigar = nullptr; uint8_t* seq2 = nullptr; uint64_t* seqx_pos = nullptr; uint8_t* seqx_code = nullptr;   // lean slots
+    bool lean = false;
+    int64_t cap_rec = 0, cap_cig = 0, cap_seq = 0, cap_seqx = 0;
     cudaEvent_t done = nullptr;
     int state = 0;                         // 0 free, 1 handed out (being filled / waiting for submit), 2 copy in flight
     uint64_t seq_no = 0;                   // submit order, to find the oldest in-flight slot
@@ -43,16 +45,20 @@ struct pj_ctx {
     int32_t n_targets = 0;
     std::vector<int32_t> h_tlen; std::vector<uint64_t> h_toff, h_goff; std::vector<int64_t> h_glen;
     int32_t* d_tlen = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_goff = nullptr; int64_t* d_glen = nullptr;
-    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint64_t* d_g4 = nullptr; uint64_t g_total_bases = 0;
+    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint64_t g_total_bases = 0;
     uint64_t* d_exc_pos = nullptr; uint8_t* d_exc_byte = nullptr; uint32_t* d_exc_count = nullptr; uint32_t exc_cap = 1u << 20;
-    int32_t n_exc = 0, n_exc_x = 0, n_zero_code = 0; bool genome_dirty = false;
+    int32_t n_exc = 0, n_exc_x = 0, any_gx = 0; bool genome_dirty = false;
     uint8_t* h_graw[2] = {nullptr, nullptr}; uint8_t* d_graw[2] = {nullptr, nullptr}; cudaEvent_t graw_ev[2] = {nullptr, nullptr};
     static constexpr size_t GRAW_CHUNK = 64u << 20;
     // shard arena
     bool shard_open = false;
     int64_t n_rec = 0; uint64_t n_cig = 0, n_seq = 0;
-    pjapi::DevBuf<int32_t> tid, pos, l_qseq, mtid, mpos; pjapi::DevBuf<uint16_t> flag; pjapi::DevBuf<uint8_t> mapq, xs, seq4;
+    pjapi::DevBuf<int32_t> tid, pos, l_qseq, mtid, mpos; pjapi::DevBuf<uint16_t> flag; pjapi::DevBuf<uint8_t> mapq, xs, seq2;
     pjapi::DevBuf<uint32_t> cigar_off, cigar; pjapi::DevBuf<uint64_t> seq_off;
+    // non-ACGT read bases of the shard (sorted by base index) + per-batch scratch of pj_batch_submit
+    pjapi::DevBuf<uint64_t> seqx_pos; pjapi::DevBuf<uint8_t> seqx_code; int64_t n_seqx = 0;
+    pjapi::DevBuf<uint8_t> tmp_seq4; pjapi::DevBuf<uint64_t> tmp_off4; pjapi::DevBuf<uint32_t> tmp_xcount, tmp_xoff, tmp_scan; pjapi::DevBuf<uint16_t> tmp_ncig;
+    pjapi::DevBuf<unsigned long long> tmp_fs;
     std::vector<pjapi::StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
     std::thread prewarm_thread;         // grows the stream-ordered memory pool while the caller is still decoding
     double t_pinned_alloc_s = 0; size_t pinned_alloc_bytes = 0; int n_pinned_allocs = 0;   // PJ_TRACE: cost of growing the staging pool
@@ -62,7 +68,7 @@ struct pj_ctx {
     // per-target accumulators + misc device scalars
     unsigned long long *d_spliced = nullptr, *d_unspliced = nullptr, *d_sumq = nullptr; int32_t *d_minq = nullptr, *d_maxq = nullptr;
     uint32_t* d_scalars = nullptr;    // [0]=err [1]=max_nlen [2]=P [3]=J [4]=E [5]=scratch total [6]=tile ticket
-    unsigned long long* d_shard_acc = nullptr;   // [0] (low 32 bits) longest N op, [1] number of N ops of the shard, [2] != 0: a batch had malformed prefix offsets; filled while batches are copied in
+    unsigned long long* d_shard_acc = nullptr;   // [0] (low 32 bits) longest N op, [1] number of N ops of the shard, [2] != 0: a batch had malformed prefix offsets / inconsistent lean totals; filled while batches are copied in
     uint32_t* h_scalars = nullptr;    // pinned mirror
     // results
     pj_junction* d_rows = nullptr; size_t rows_cap = 0; int64_t n_junc = 0; uint64_t n_pairs = 0;

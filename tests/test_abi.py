@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), "symbol %s declared in include/ but not exported" % name
     assert declared == set(L.SYMBOLS), "python binding table out of sync with the headers: %s" % (declared ^ set(L.SYMBOLS))
-    assert lib.pj_abi_version() == 1
+    assert lib.pj_abi_version() == 2
     assert lib.pj_junction_size() == L.JUNCTION_DTYPE.itemsize == 256
 
 
@@ -115,7 +115,7 @@ int main(void) {
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                            "-L", libdir, "-lportcullis_junc", "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()
-    assert out[0] == "1" and out[1] == "256" and out[2] == "256"
+    assert out[0] == "2" and out[1] == "256" and out[2] == "256"
 
 
 def test_corrupted_bam_and_index_never_crash_the_readers():
