@@ -119,6 +119,14 @@ int         pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_t
 int         pjh_plan_describe(const pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t* segments_per_part, int32_t* n_gap_cuts);
 int         pjh_plan_decode(pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t part, int32_t segment, int32_t threads, pj_batch* out);
 
+/* Same segment in the LEAN batch form (pj_batch.lean): what the junc driver ships over PCIe.  `out` describes the whole segment
+ * (const_tid = -1); a lean batch must lie on one target, so runs[n_runs] lists the stretches of the segment — submit
+ * records [rec0, next rec0) of each with const_tid = tid, the CIGAR words from cig0, the seq2 bytes from seq0 and the
+ * exceptions from seqx0 (their positions made relative to seq0 * 4).  keep_mate = 0 omits mtid / mpos. */
+typedef struct pjh_lean_run { int32_t tid; int32_t pad; int64_t rec0, cig0, seq0, seqx0; } pjh_lean_run;
+int         pjh_plan_decode_lean(pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t part, int32_t segment, int32_t threads,
+                                 int32_t keep_mate, pj_batch* out, const pjh_lean_run** runs, int32_t* n_runs);
+
 /* Checks the built-in fast DEFLATE decoder (BGZF blocks) against zlib on n_cases synthetic streams; returns the number of
  * mismatches (0 = pass).  BGZF blocks the fast decoder rejects are decoded by zlib, so it can only be an accelerator. */
 int         pjh_inflate_selftest(int32_t n_cases);

@@ -40,6 +40,10 @@ class PjBatch(C.Structure):
                 ("n_seqx", C.c_int64)]
 
 
+class PjhLeanRun(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("pad", C.c_int32), ("rec0", C.c_int64), ("cig0", C.c_int64), ("seq0", C.c_int64), ("seqx0", C.c_int64)]
+
+
 class PjTargetStats(C.Structure):
     _fields_ = [("spliced_count", C.c_uint64), ("unspliced_count", C.c_uint64), ("sum_query_lengths", C.c_uint64),
                 ("min_query_length", C.c_int32), ("max_query_length", C.c_int32)]
@@ -181,6 +185,8 @@ SYMBOLS = {
     "pjh_inflate_selftest": (C.c_int, [C.c_int32]),
     "pjh_plan_shards": (C.c_int, [_P, C.c_int32, _P]),
     "pjh_plan_describe": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, C.POINTER(C.c_int32)]),
+    "pjh_plan_decode_lean": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PjBatch),
+                                       C.POINTER(C.POINTER(PjhLeanRun)), C.POINTER(C.c_int32)]),
     "pjh_plan_decode": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PjBatch)]),
     "pjh_separate_bams": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _P]),
     "pjh_write_outputs_extra": (C.c_int, [C.c_char_p, _P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_char_p), _P, C.c_char_p, C.c_char_p,

@@ -127,3 +127,71 @@ def from_records(records):
             raise ValueError("either every record has a name or none has")
         out["name_code"] = np.array(names, dtype=np.uint64)
     return out
+
+
+LEAN_COLUMNS = [("pos", np.int32), ("flag", np.uint16), ("mapq", np.uint8), ("xs", np.uint8), ("l_qseq", np.int32),
+                ("n_cigar", np.uint16), ("cigar", np.uint32), ("seq2", np.uint8), ("seqx_pos", np.uint64), ("seqx_code", np.uint8)]
+
+
+def lean_runs_from_batch(b, runs, n_runs, copy=False):
+    """Split a lean PjBatch describing a whole segment (pjh_plan_decode_lean) into one lean batch per target stretch.
+    Returns a list of dicts: tid + the lean columns (views of the library's arrays unless copy=True; the exception
+    positions are made relative to the stretch, so that small array is always a copy)."""
+    n = b.n_records
+
+    def arr(ptr, count, dt):
+        if not ptr or count == 0:
+            return np.zeros(count, dtype=dt)
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,))
+        return a.copy() if copy else a
+
+    whole = {"pos": arr(b.pos, n, np.int32), "flag": arr(b.flag, n, np.uint16), "mapq": arr(b.mapq, n, np.uint8), "xs": arr(b.xs, n, np.uint8),
+             "l_qseq": arr(b.l_qseq, n, np.int32), "n_cigar": arr(b.n_cigar, n, np.uint16), "cigar": arr(b.cigar, b.n_cigar_total, np.uint32),
+             "seq2": arr(b.seq2, b.n_seq2_bytes, np.uint8), "seqx_pos": arr(b.seqx_pos, b.n_seqx, np.uint64), "seqx_code": arr(b.seqx_code, b.n_seqx, np.uint8)}
+    if b.mtid and b.mpos:
+        whole["mtid"] = arr(b.mtid, n, np.int32)
+        whole["mpos"] = arr(b.mpos, n, np.int32)
+    if b.name_code:
+        whole["name_code"] = arr(b.name_code, n, np.uint64)
+    out = []
+    ends = [(runs[k + 1].rec0, runs[k + 1].cig0, runs[k + 1].seq0, runs[k + 1].seqx0) for k in range(n_runs - 1)] + [(n, b.n_cigar_total, b.n_seq2_bytes, b.n_seqx)]
+    for k in range(n_runs):
+        r = runs[k]
+        r1, c1, s1, x1 = ends[k]
+        d = {"tid": int(r.tid)}
+        for name in ("pos", "flag", "mapq", "xs", "l_qseq", "n_cigar", "mtid", "mpos", "name_code"):
+            if name in whole:
+                d[name] = whole[name][r.rec0:r1]
+        d["cigar"] = whole["cigar"][r.cig0:c1]
+        d["seq2"] = whole["seq2"][r.seq0:s1]
+        d["seqx_pos"] = whole["seqx_pos"][r.seqx0:x1] - np.uint64(r.seq0 * 4)
+        d["seqx_code"] = whole["seqx_code"][r.seqx0:x1]
+        out.append(d)
+    return out
+
+
+def lean_batch_struct(d):
+    """PjBatch (lean form) pointing at the arrays of one stretch returned by lean_runs_from_batch. Returns (struct, keepalive)."""
+    keep = []
+    b = L.PjBatch()
+    n = len(d["pos"])
+    b.n_records = n
+    b.lean = 1
+    b.const_tid = int(d["tid"])
+    for name, dt in LEAN_COLUMNS:
+        a = np.ascontiguousarray(d[name], dtype=dt)
+        keep.append(a)
+        setattr(b, name, a.ctypes.data if a.size else None)
+    for name, dt in (("mtid", np.int32), ("mpos", np.int32), ("name_code", np.uint64)):
+        if d.get(name) is not None:
+            a = np.ascontiguousarray(d[name], dtype=dt)
+            keep.append(a)
+            setattr(b, name, a.ctypes.data if a.size else None)
+    b.n_cigar_total = len(d["cigar"])
+    b.n_seq2_bytes = len(d["seq2"])
+    b.n_seqx = len(d["seqx_pos"])
+    return b, keep
+
+
+def lean_nbytes(d):
+    return int(sum(np.asarray(v).nbytes for k, v in d.items() if k != "tid"))

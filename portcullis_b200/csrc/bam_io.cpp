@@ -117,6 +117,7 @@ bool BamHeader::coordinate_sorted() const {
 void ColumnarChunk::clear() {
     tid.clear(); pos.clear(); l_qseq.clear(); mtid.clear(); mpos.clear(); flag.clear(); mapq.clear(); xs.clear();
     cigar_off.assign(1, 0); cigar.clear(); seq_off.assign(1, 0); seq4.clear(); name_code.clear();
+    n_cigar.clear(); seq2.clear(); seqx_pos.clear(); seqx_code.clear(); runs.clear();
 }
 
 uint64_t name_code(const char* qname, size_t len, uint16_t flag) {
@@ -129,6 +130,22 @@ uint64_t name_code(const char* qname, size_t len, uint16_t flag) {
 }
 
 void ColumnarChunk::append(const ColumnarChunk& o) {
+    if (lean) {
+        const int64_t r0 = n(), c0 = (int64_t)cigar.size(), s0 = (int64_t)seq2.size(), x0 = (int64_t)seqx_pos.size();
+        for (const Run& r : o.runs) {
+            if (!runs.empty() && runs.back().tid == r.tid) continue;                  // the target continues: same stretch
+            runs.push_back(Run{r.tid, 0, r0 + r.rec0, c0 + r.cig0, s0 + r.seq0, x0 + r.seqx0});
+        }
+        pos.insert(pos.end(), o.pos.begin(), o.pos.end()); l_qseq.insert(l_qseq.end(), o.l_qseq.begin(), o.l_qseq.end());
+        mtid.insert(mtid.end(), o.mtid.begin(), o.mtid.end()); mpos.insert(mpos.end(), o.mpos.begin(), o.mpos.end());
+        flag.insert(flag.end(), o.flag.begin(), o.flag.end()); mapq.insert(mapq.end(), o.mapq.begin(), o.mapq.end()); xs.insert(xs.end(), o.xs.begin(), o.xs.end());
+        n_cigar.insert(n_cigar.end(), o.n_cigar.begin(), o.n_cigar.end()); cigar.insert(cigar.end(), o.cigar.begin(), o.cigar.end());
+        seq2.insert(seq2.end(), o.seq2.begin(), o.seq2.end());
+        for (uint64_t v : o.seqx_pos) seqx_pos.push_back(v + (uint64_t)s0 * 4ull);
+        seqx_code.insert(seqx_code.end(), o.seqx_code.begin(), o.seqx_code.end());
+        name_code.insert(name_code.end(), o.name_code.begin(), o.name_code.end());
+        return;
+    }
     uint32_t cb = (uint32_t)cigar.size(); uint64_t sb = seq4.size();
     tid.insert(tid.end(), o.tid.begin(), o.tid.end()); pos.insert(pos.end(), o.pos.begin(), o.pos.end());
     l_qseq.insert(l_qseq.end(), o.l_qseq.begin(), o.l_qseq.end());
@@ -371,6 +388,46 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
         if (endpos <= 0) continue;
         const uint8_t* sq = cg + 4ull * n_cig;
         const uint8_t* aux = sq + (l_seq + 1) / 2 + l_seq;
+        if (out.lean) {
+            if (out.runs.empty() || out.runs.back().tid != tid)
+                out.runs.push_back(ColumnarChunk::Run{tid, 0, out.n(), (int64_t)out.cigar.size(), (int64_t)out.seq2.size(), (int64_t)out.seqx_pos.size()});
+            uint16_t fl = flag;
+            if (spliced && l_seq > 0) {
+                // 4-bit BAM SEQ -> 2 bits per base; anything that is not A/C/G/T is stored as 0 and listed as an exception
+                static const struct Lut { uint8_t v[256]; Lut() { for (int b = 0; b < 256; b++) { auto c2 = [](int nib, bool& bad) { switch (nib) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; default: bad = true; return 0; } };
+                                                                                  bool bad = false; const int hi = c2(b >> 4, bad), lo = c2(b & 15, bad); v[b] = (uint8_t)(hi | (lo << 2) | (bad ? 0x80 : 0)); } } } LUT;
+                const size_t nb4 = (size_t)(l_seq + 1) / 2, nb2 = (size_t)(l_seq + 3) / 4, s0 = out.seq2.size();
+                out.seq2.resize(s0 + nb2);
+                uint8_t* o2 = &out.seq2[s0];
+                bool any_bad = false;
+                for (size_t j = 0; j < nb2; j++) {
+                    const uint8_t a = LUT.v[sq[2 * j]], b2 = (2 * j + 1 < nb4) ? LUT.v[sq[2 * j + 1]] : (uint8_t)0;
+                    o2[j] = (uint8_t)((a & 15) | ((b2 & 15) << 4));
+                    any_bad |= ((a | b2) & 0x80) != 0;
+                }
+                if (any_bad) {                                   // rare: list the exact nibbles (the padding nibble of an odd length is not a base)
+                    bool real = false;
+                    for (int32_t q = 0; q < l_seq; q++) {
+                        const uint32_t nib = (q & 1) ? (sq[q >> 1] & 15u) : (uint32_t)(sq[q >> 1] >> 4);
+                        if (nib != 1 && nib != 2 && nib != 4 && nib != 8) { out.seqx_pos.push_back((uint64_t)s0 * 4ull + (uint64_t)q); out.seqx_code.push_back((uint8_t)nib); real = true; }
+                    }
+                    if (real) fl = (uint16_t)(fl | 0x8000u);
+                }
+            }
+            out.pos.push_back(pos); out.flag.push_back(fl); out.mapq.push_back(mapq); out.l_qseq.push_back(l_seq);
+            if (out.keep_mate) { out.mtid.push_back(mtid); out.mpos.push_back(mpos); }
+            out.xs.push_back(find_xs(aux, p + bs));
+            if (out.with_names) {
+                size_t ln = l_name; const char* qn = (const char*)p + 32;
+                while (ln && qn[ln - 1] == 0) ln--;
+                out.name_code.push_back(name_code(qn, strnlen(qn, ln), flag));
+            }
+            if (n_cig > 0xffffu) throw IoError("BAM record with more than 65535 CIGAR operations");
+            out.n_cigar.push_back((uint16_t)n_cig);
+            const size_t c0 = out.cigar.size(); out.cigar.resize(c0 + n_cig);
+            if (n_cig) memcpy(&out.cigar[c0], cg, 4ull * n_cig);
+            continue;
+        }
         out.tid.push_back(tid); out.pos.push_back(pos); out.flag.push_back(flag); out.mapq.push_back(mapq);
         out.l_qseq.push_back(l_seq); out.mtid.push_back(mtid); out.mpos.push_back(mpos);
         out.xs.push_back(find_xs(aux, p + bs));

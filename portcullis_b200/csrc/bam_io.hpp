@@ -87,6 +87,17 @@ struct ColumnarChunk {
     std::vector<uint8_t> seq4;
     bool with_names = false;               // set before decode(): also fill name_code (the `--extra` metrics need it)
     std::vector<uint64_t> name_code;
+    // ---- lean form (pj_batch.lean, include/portcullis_junc.h): set `lean` before decode().  tid / cigar_off / seq_off / seq4 stay
+    // empty; n_cigar, seq2 (2 bits per base, spliced records only) and the non-ACGT exceptions are filled instead; mtid / mpos only
+    // with keep_mate.  Every record of a decode task lies on one target: `runs` lists the (target, first record / CIGAR word / seq2
+    // byte / exception) of each stretch, one entry after decode(), several after append(). ----
+    bool lean = false, keep_mate = true;
+    std::vector<uint16_t> n_cigar;
+    std::vector<uint8_t> seq2;
+    std::vector<uint64_t> seqx_pos;        // base index within seq2 (byte * 4 + q), ascending
+    std::vector<uint8_t> seqx_code;        // BAM nibble
+    struct Run { int32_t tid; int32_t pad; int64_t rec0, cig0, seq0, seqx0; };
+    std::vector<Run> runs;
     int64_t n() const { return (int64_t)pos.size(); }
     void clear();
     void append(const ColumnarChunk& o);

@@ -182,7 +182,7 @@ int pjh_prep_decode(pjh_prep* p, int32_t tid, int32_t threads, pj_batch* out) {
     const int32_t T = pjh_prep_n_targets(p);
     if (p->indexed) { for (int32_t t = (tid < 0 ? 0 : tid); t < (tid < 0 ? T : tid + 1); t++) p->bam.plan_target(t, 2u << 20, tasks); }
     else { DecodeTask w = p->bam.whole_file_task(); if (tid >= 0) { w.tid = tid; } tasks.push_back(w); }
-    p->decoded.clear(); p->decoded.with_names = p->want_names;
+    p->decoded.clear(); p->decoded.with_names = p->want_names; p->decoded.lean = false;
     int rc = ordered_pipeline<ColumnarChunk>(tasks.size(), threads, (size_t)threads * 3 + 2,
         [&](size_t k, ColumnarChunk& c) { c.with_names = p->want_names; p->bam.decode(tasks[k], c); return PJ_OK; },
         [&](size_t, ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
@@ -456,7 +456,26 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
     } cleanup{gpu_thread, ctx, &out.teardown_s};
     auto wait_ready = [&]() -> int { std::unique_lock<std::mutex> lk(gm); gcv.wait(lk, [&] { return ready; }); return gpu_rc; };
     // copy one decoded chunk into a pinned staging buffer of the context
+    const bool lean = prep->indexed;                                   // a decode task of an indexed BAM lies on one target: the lean batch form applies
+    const bool keep_mate = o->orientation == PJ_ORIENT_FR || o->orientation == PJ_ORIENT_RF || o->orientation == PJ_ORIENT_FF;
     auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
+        if (ch.lean) {
+            // about half the bytes of the classic form cross PCIe: no tid / cigar_off / seq_off columns (formed on the device), SEQ at
+            // 2 bits per base, mate columns only when the orientation needs them
+            if (ch.runs.size() != 1) return fail(PJ_EINVAL, "internal: a lean chunk must lie on one target");
+            int q = pj_staging_acquire_lean(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq2.size(), (int64_t)ch.seqx_pos.size(), &st);
+            if (q) return fail(q, pj_last_error(ctx));
+            const size_t n = (size_t)ch.n();
+            memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2); memcpy((void*)st.mapq, ch.mapq.data(), n);
+            memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4); memcpy((void*)st.n_cigar, ch.n_cigar.data(), n * 2);
+            if (keep_mate) { memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4); } else { st.mtid = nullptr; st.mpos = nullptr; }
+            memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4); memcpy((void*)st.seq2, ch.seq2.data(), ch.seq2.size());
+            if (!ch.seqx_pos.empty()) { memcpy((void*)st.seqx_pos, ch.seqx_pos.data(), ch.seqx_pos.size() * 8); memcpy((void*)st.seqx_code, ch.seqx_code.data(), ch.seqx_code.size()); }
+            if (extra) memcpy((void*)st.name_code, ch.name_code.data(), n * 8);
+            st.n_records = ch.n(); st.const_tid = ch.runs[0].tid; st.n_cigar_total = (int64_t)ch.cigar.size(); st.n_seq2_bytes = (int64_t)ch.seq2.size();
+            st.n_seqx = (int64_t)ch.seqx_pos.size();
+            return PJ_OK;
+        }
         int q = pj_staging_acquire(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq4.size(), &st);
         if (q) return fail(q, pj_last_error(ctx));
         const size_t n = (size_t)ch.n();
@@ -494,7 +513,7 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         r = ordered_pipeline<Payload>(sg.tasks.size(), threads, window,
             [&](size_t k, Payload& p) -> int {
                 p.chunk = pool.get();
-                p.chunk->with_names = extra;
+                p.chunk->with_names = extra; p.chunk->lean = lean; p.chunk->keep_mate = keep_mate;
                 prep->bam.decode(sg.tasks[k], *p.chunk);
                 return PJ_OK;
             },
@@ -817,6 +836,33 @@ int pjh_plan_decode(pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t
         [&](size_t, ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
     if (rc) return rc;
     chunk_view(p->decoded, out);
+    return PJ_OK;
+}
+
+int pjh_plan_decode_lean(pjh_prep* p, int32_t n_parts, int32_t whole_targets, int64_t seg_records, int32_t part, int32_t segment, int32_t threads,
+                         int32_t keep_mate, pj_batch* out, const pjh_lean_run** runs, int32_t* n_runs) {
+    if (!p || n_parts < 1 || part < 0 || part >= n_parts || !out || !runs || !n_runs) return fail(PJ_EINVAL, "pjh_plan_decode_lean: bad argument");
+    if (!p->indexed) return fail(PJ_EINVAL, "pjh_plan_decode_lean: the lean form needs an indexed BAM (one target per decode task)");
+    std::vector<Part> parts;
+    try { int rc = plan_parts(p, n_parts, whole_targets != 0, seg_records > 0 ? (uint64_t)seg_records : (32u << 20), parts, nullptr); if (rc) return rc; }
+    catch (const std::exception& e) { return fail(PJ_EIO, e.what()); }
+    if (segment < 0 || (size_t)segment >= parts[(size_t)part].size()) return fail(PJ_EINVAL, "pjh_plan_decode_lean: segment out of range");
+    const Segment& sg = parts[(size_t)part][(size_t)segment];
+    p->decoded.clear(); p->decoded.with_names = p->want_names; p->decoded.lean = true; p->decoded.keep_mate = keep_mate != 0;
+    int rc = ordered_pipeline<ColumnarChunk>(sg.tasks.size(), std::max(1, threads), (size_t)std::max(1, threads) * 3 + 2,
+        [&](size_t k, ColumnarChunk& c) { c.with_names = p->want_names; c.lean = true; c.keep_mate = keep_mate != 0; p->bam.decode(sg.tasks[k], c); return PJ_OK; },
+        [&](size_t, ColumnarChunk& c) { p->decoded.append(c); return PJ_OK; });
+    p->decoded.lean = false;                                        // later classic decodes reuse the object
+    if (rc) return rc;
+    const ColumnarChunk& c = p->decoded;
+    memset(out, 0, sizeof *out);
+    out->n_records = c.n(); out->pos = c.pos.data(); out->flag = c.flag.data(); out->mapq = c.mapq.data(); out->xs = c.xs.data(); out->l_qseq = c.l_qseq.data();
+    out->mtid = keep_mate ? c.mtid.data() : nullptr; out->mpos = keep_mate ? c.mpos.data() : nullptr;
+    out->cigar = c.cigar.data(); out->lean = 1; out->const_tid = -1; out->n_cigar = c.n_cigar.data(); out->n_cigar_total = (int64_t)c.cigar.size();
+    out->seq2 = c.seq2.data(); out->n_seq2_bytes = (int64_t)c.seq2.size(); out->seqx_pos = c.seqx_pos.data(); out->seqx_code = c.seqx_code.data(); out->n_seqx = (int64_t)c.seqx_pos.size();
+    out->name_code = (c.with_names && (int64_t)c.name_code.size() == c.n()) ? c.name_code.data() : nullptr;
+    static_assert(sizeof(pjh_lean_run) == sizeof(ColumnarChunk::Run), "pjh_lean_run mirrors ColumnarChunk::Run");
+    *runs = reinterpret_cast<const pjh_lean_run*>(c.runs.data()); *n_runs = (int32_t)c.runs.size();
     return PJ_OK;
 }
 

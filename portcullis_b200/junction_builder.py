@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 from . import _lib as L
-from .columnar import batch_struct, from_batch
+from .columnar import batch_struct, from_batch, lean_batch_struct, lean_runs_from_batch
 
 
 def _check(rc, msg_fn):
@@ -52,6 +52,16 @@ class PrepDir:
         b = L.PjBatch()
         _check(self._lib.pjh_plan_decode(self._p, n_parts, int(whole_targets), int(seg_records), part, segment, threads, C.byref(b)), self._lib.pjh_last_error)
         return from_batch(b, copy=copy)
+
+    def decode_segment_lean(self, n_parts, part, segment, seg_records=0, threads=1, whole_targets=False, keep_mate=True, copy=False):
+        """One segment of the plan in the LEAN batch form, as a list of per-target stretches (dicts for JuncGpu.submit_lean);
+        copy=False: views of the handle's arrays, valid until its next decode."""
+        b = L.PjBatch()
+        runs = C.POINTER(L.PjhLeanRun)()
+        n_runs = C.c_int32()
+        _check(self._lib.pjh_plan_decode_lean(self._p, n_parts, int(whole_targets), int(seg_records), part, segment, threads, int(keep_mate),
+                                              C.byref(b), C.byref(runs), C.byref(n_runs)), self._lib.pjh_last_error)
+        return lean_runs_from_batch(b, runs, n_runs.value, copy=copy)
 
     def decode(self, tid=-1, threads=1, names=False):
         """Decode one target (or all with tid=-1) into owned numpy columns; names=True adds the name_code column."""
@@ -110,6 +120,12 @@ class JuncGpu:
 
     def submit(self, cols):
         b, keep = batch_struct(cols)
+        _check(self._lib.pj_batch_submit(self._ctx, C.byref(b)), self._err)
+        del keep
+
+    def submit_lean(self, stretch):
+        """One lean batch (a stretch of PrepDir.decode_segment_lean): the form the junc driver ships over PCIe."""
+        b, keep = lean_batch_struct(stretch)
         _check(self._lib.pj_batch_submit(self._ctx, C.byref(b)), self._err)
         del keep
 
