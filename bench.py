@@ -189,16 +189,14 @@ def run_ours(args):
     T = len(p.names)
     HUGE = 1 << 40                                     # one segment per part: the whole part is resident for the `value` arm
     seg, cuts = p.plan(world, HUGE)
-    if int(seg[rank]) > 0:
-        cols = p.decode_segment(world, rank, 0, HUGE, threads=cores, copy=False)     # views of the handle's arrays
-    else:                                              # less work than ranks (tiny inputs only): an empty shard
-        from portcullis_b200.columnar import COLUMNS
-        cols = {k: np.zeros(1 if k in ("cigar_off", "seq_off") else 0, dtype=dt) for k, dt in COLUMNS}
+    # the LEAN batch form, exactly what the product's driver ships over PCIe (pj_batch.lean): one batch per target stretch
+    from portcullis_b200.columnar import lean_nbytes
+    runs, whole = (p.decode_segment_lean(world, rank, 0, HUGE, threads=cores, keep_mate=False, copy=False, with_whole=True) if int(seg[rank]) > 0 else ([], {}))
     t_decode = time.time() - t0
-    n_rec = len(cols["pos"])
+    n_rec = int(sum(len(r["pos"]) for r in runs))
     cudart = torch.cuda.cudart()
     registered = []
-    for k, v in cols.items():                          # page-lock the decoded columns in place (no second copy of the shard)
+    for k, v in whole.items():                         # page-lock the decoded columns in place (no second copy of the shard)
         if v.nbytes:
             rc = cudart.cudaHostRegister(v.ctypes.data, v.nbytes, 0)
             try:
@@ -207,16 +205,22 @@ def run_ours(args):
                 ok = str(rc).lower().endswith("success")
             if ok:
                 registered.append(v.ctypes.data)
-    h2d_bytes = int(sum(v.nbytes for v in cols.values()))
-    my_targets = [int(t) for t in np.unique(cols["tid"])] if n_rec else []
+    h2d_bytes = int(sum(lean_nbytes(r) for r in runs))
+    my_targets = [r["tid"] for r in runs]
+    n_cig_all = int(sum(len(r["cigar"]) for r in runs))
+    seq2_all = int(sum(len(r["seq2"]) for r in runs))
+
+    def submit_all():
+        g.shard_begin(n_rec, n_cig_all, 2 * seq2_all)
+        for r in runs:
+            g.submit_lean(r)
 
     g = jb.JuncGpu(local, "UNKNOWN")
     g.set_targets(p.lengths)
     t0 = time.time()
     for t in my_targets:
         g.set_genome(t, p.genome(t))
-    g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"]))
-    g.submit(cols)
+    submit_all()
     nj = g.run()                                       # also finishes the genome upload
     t_setup = time.time() - t0
     rows, st = g.fetch()
@@ -250,12 +254,11 @@ def run_ours(args):
         rows_pin_t = torch.empty(int(nj + 16) * L.JUNCTION_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
         rows_pin = rows_pin_t.numpy().view(L.JUNCTION_DTYPE)
         for _ in range(3):                             # the link and the arena need a few passes of their own on a fresh box
-            g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"])); g.submit(cols); g.run(); g.fetch(rows_pin)
+            submit_all(); g.run(); g.fetch(rows_pin)
         barrier()
         t1 = time.perf_counter()
         for _ in range(e2e_steps):
-            g.shard_begin(n_rec, len(cols["cigar"]), len(cols["seq4"]))
-            g.submit(cols)
+            submit_all()
             g.run()
             rows2, _ = g.fetch(rows_pin)
         barrier()
@@ -265,13 +268,18 @@ def run_ours(args):
     sampler.join()
 
     # per-rank workload numbers for the roofline (before the columns are released)
-    has_seq = np.diff(cols["seq_off"].astype(np.int64)) > 0 if n_rec else np.zeros(0, bool)
-    n_cig_spliced = int(np.diff(cols["cigar_off"].astype(np.int64))[has_seq].sum()) if n_rec else 0
-    n_cig, seq_bytes = len(cols["cigar"]), len(cols["seq4"])
+    n_cig, n_cig_spliced, seq_bytes = n_cig_all, 0, 0                # seq_bytes: the 4-bit SEQ bytes of SURVEY 8(d), (l + 1) / 2 per spliced record
+    for r in runs:
+        off = np.concatenate([[0], np.cumsum(r["n_cigar"].astype(np.int64))])
+        isn = np.concatenate([[0], np.cumsum((r["cigar"] & 15) == 3)])
+        spl = (isn[off[1:]] - isn[off[:-1]]) > 0
+        n_cig_spliced += int(r["n_cigar"].astype(np.int64)[spl].sum())
+        lq = r["l_qseq"].astype(np.int64)[spl]
+        seq_bytes += int(((lq[lq > 0] + 1) // 2).sum())
     g.close()
     for ptr in registered:
         cudart.cudaHostUnregister(ptr)
-    del cols
+    del runs, whole
     p.close()
 
     # ---------------- e2e_bam arm: BAM file -> output files, the product's own driver ----------------
@@ -327,7 +335,7 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "e2e": ({"value": tot_spliced * e2e_steps / wall_e2e_m, "unit": UNIT, "h2d_bytes_per_step": int(tot_h2d), "d2h_bytes_per_step": int(tot_d2h),
                      "ms_per_step": wall_e2e_m / e2e_steps * 1e3,
-                     "what": "C ABI with the decoded columns in pinned host memory (pj_shard_begin/pj_batch_submit/pj_shard_run/pj_shard_fetch)"} if e2e_steps else None),
+                     "what": "C ABI with the decoded columns (lean batch form: 2-bit SEQ, per-record op counts) in pinned host memory: pj_shard_begin / pj_batch_submit / pj_shard_run / pj_shard_fetch"} if e2e_steps else None),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": per_stage[dom], "avg_launch_ms": stage_ms[dom],

@@ -133,7 +133,7 @@ LEAN_COLUMNS = [("pos", np.int32), ("flag", np.uint16), ("mapq", np.uint8), ("xs
                 ("n_cigar", np.uint16), ("cigar", np.uint32), ("seq2", np.uint8), ("seqx_pos", np.uint64), ("seqx_code", np.uint8)]
 
 
-def lean_runs_from_batch(b, runs, n_runs, copy=False):
+def lean_runs_from_batch(b, runs, n_runs, copy=False, with_whole=False):
     """Split a lean PjBatch describing a whole segment (pjh_plan_decode_lean) into one lean batch per target stretch.
     Returns a list of dicts: tid + the lean columns (views of the library's arrays unless copy=True; the exception
     positions are made relative to the stretch, so that small array is always a copy)."""
@@ -167,7 +167,7 @@ def lean_runs_from_batch(b, runs, n_runs, copy=False):
         d["seqx_pos"] = whole["seqx_pos"][r.seqx0:x1] - np.uint64(r.seq0 * 4)
         d["seqx_code"] = whole["seqx_code"][r.seqx0:x1]
         out.append(d)
-    return out
+    return (out, whole) if with_whole else out
 
 
 def lean_batch_struct(d):

@@ -1099,7 +1099,7 @@ void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32
 // ================================================================================================
 
 #ifndef PJ_MATCH_CTAS
-#define PJ_MATCH_CTAS 4          // resident CTAs per SM the register budget of k_match is set for (64 registers: no spill in the hot loop; measured on B200: 3 / 4 / 5 -> 0.70 / 0.64 / 0.74 ms on c2)
+#define PJ_MATCH_CTAS 5          // resident CTAs per SM the register budget of k_match is set for (measured on B200 with the 2-bit compare: 4 / 5 -> 0.445 / 0.439 ms on c2, 4.96 / 4.74 ms on c5)
 #endif
 constexpr uint64_t EVEN2 = 0x5555555555555555ull;
 
@@ -1385,7 +1385,7 @@ void launch_match(uint32_t n, int group, int ctas, const uint32_t* inv, const ui
     if (!n) return;
     switch (group) {
     case 1:
-        if (ctas == 5) launch_match_gc<1, 5>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
+        if (ctas == 4) launch_match_gc<1, 4>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
         else if (ctas == 3) launch_match_gc<1, 3>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
         else if (ctas == 6) launch_match_gc<1, 6>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
         else launch_match_gc<1, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);

@@ -53,7 +53,7 @@ class PrepDir:
         _check(self._lib.pjh_plan_decode(self._p, n_parts, int(whole_targets), int(seg_records), part, segment, threads, C.byref(b)), self._lib.pjh_last_error)
         return from_batch(b, copy=copy)
 
-    def decode_segment_lean(self, n_parts, part, segment, seg_records=0, threads=1, whole_targets=False, keep_mate=True, copy=False):
+    def decode_segment_lean(self, n_parts, part, segment, seg_records=0, threads=1, whole_targets=False, keep_mate=True, copy=False, with_whole=False):
         """One segment of the plan in the LEAN batch form, as a list of per-target stretches (dicts for JuncGpu.submit_lean);
         copy=False: views of the handle's arrays, valid until its next decode."""
         b = L.PjBatch()
@@ -61,7 +61,7 @@ class PrepDir:
         n_runs = C.c_int32()
         _check(self._lib.pjh_plan_decode_lean(self._p, n_parts, int(whole_targets), int(seg_records), part, segment, threads, int(keep_mate),
                                               C.byref(b), C.byref(runs), C.byref(n_runs)), self._lib.pjh_last_error)
-        return lean_runs_from_batch(b, runs, n_runs.value, copy=copy)
+        return lean_runs_from_batch(b, runs, n_runs.value, copy=copy, with_whole=with_whole)   # with_whole: also the unsplit arrays (e.g. to page-lock them once)
 
     def decode(self, tid=-1, threads=1, names=False):
         """Decode one target (or all with tid=-1) into owned numpy columns; names=True adds the name_code column."""
