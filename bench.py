@@ -95,7 +95,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(float(os.environ.get("PJ_BENCH_SMI_INTERVAL", "0.2")))
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())

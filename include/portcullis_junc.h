@@ -356,6 +356,30 @@ int  pj_jset_filter(pj_jset* s, int64_t n_records, const int32_t* tid, const int
  */
 int pj_junctions_finalize(pj_junction* rows, int64_t n_rows, double mean_query_length);
 
+/* ---- `filt` feature extraction (portcullis::ml::ModelFeatures, lib/src/model_features.cc) ----
+ * The per-junction feature vector the reference's filter trains its random forest on, computed on the device from junction
+ * rows and the genome already resident in the context (pj_targets_set + pj_genome_set_target / pj_genome_load_fasta):
+ *   pj_features_train_coding   = ModelFeatures::trainCodingPotentialModel  (model_features.cc:70-110): exon / intron 5th-order
+ *                                k-mer Markov models from the junctions with subset[i] != 0 (NULL: all)
+ *   pj_features_train_splicing = ModelFeatures::trainSplicingModels        (:112-166): donor / acceptor k-mer and positional
+ *                                models from pass[i] != 0, the "false" k-mer models from fail[i] != 0
+ *   pj_features_intron_threshold = ModelFeatures::calcIntronThreshold      (:61-68), host only
+ *   pj_features_run            = ModelFeatures::juncs2FeatureVectors / setRow (:168-228): out[n_rows][PJ_NB_FEATURES] =
+ *       Genuine(0), rna_usrs, rna_dist, rna_rel, rna_entropy, rna_rel2raw, rna_maxminanc, rna_maxmmes, rna_missmatch,
+ *       rna_intron (Junction::calcIntronScore, junction.cc:953-956), dna_minhamm, dna_coding (calcCodingPotential :1328-1358),
+ *       dna_pws, dna_ss (calcSplicingScores :1360-1382), JAD01..JAD20 log deviations (calcJunctionAnchorDepthLogDeviation :1384-1391).
+ * Counts are integer atomics and every probability product is formed left to right like the reference, so the products are
+ * bit-identical; only the final log() may differ in the last ulp.  rows must carry the host-finalized fields (mean_readlen,
+ * rel2raw, mean_mismatches).  device_ms (may be NULL) receives the kernel time of pj_features_run. */
+#define PJ_NB_FEATURES 34
+typedef struct pj_feat_models pj_feat_models;
+int      pj_features_create(pj_ctx* ctx, pj_feat_models** out);
+void     pj_features_destroy(pj_feat_models* m);
+int      pj_features_train_coding(pj_feat_models* m, const pj_junction* rows, int64_t n_rows, const uint8_t* subset);
+int      pj_features_train_splicing(pj_feat_models* m, const pj_junction* rows, int64_t n_rows, const uint8_t* pass, const uint8_t* fail);
+uint32_t pj_features_intron_threshold(const pj_junction* rows, int64_t n_rows, const uint8_t* subset);
+int      pj_features_run(pj_feat_models* m, const pj_junction* rows, int64_t n_rows, uint32_t l95, double* out, float* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,6 +164,12 @@ SYMBOLS = {
     "pj_extra_coverage": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
     "pj_extra_coverage_source": (None, [C.c_int32, _P, _P]),
     "pj_extra_finalize": (None, [_P, C.c_int64]),
+    "pj_features_create": (C.c_int, [_P, C.POINTER(_P)]),
+    "pj_features_destroy": (None, [_P]),
+    "pj_features_train_coding": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "pj_features_train_splicing": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "pj_features_intron_threshold": (C.c_uint32, [_P, C.c_int64, _P]),
+    "pj_features_run": (C.c_int, [_P, _P, C.c_int64, C.c_uint32, _P, C.POINTER(C.c_float)]),
     "pjh_options_default": (None, [C.POINTER(PjhOptions)]),
     "pjh_junc_run": (C.c_int, [C.POINTER(PjhOptions), C.POINTER(PjhReport)]),
     "pjh_junc_run_part": (C.c_int, [C.POINTER(PjhOptions), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(PjhReport)]),

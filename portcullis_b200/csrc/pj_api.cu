@@ -92,8 +92,10 @@ void mark(pj_ctx* c, const char* name) {
     c->n_stage++;
 }
 
+} // namespace
+
 // sort + upload the "other exception byte" table after genome uploads
-int finish_genome(pj_ctx* c) {
+int pjapi::finish_genome(pj_ctx* c) {
     if (!c->genome_dirty) return PJ_OK;
     CU(c, cudaStreamSynchronize(c->genome_stream));
     uint32_t cnt2[2] = {0, 0};
@@ -118,8 +120,6 @@ int finish_genome(pj_ctx* c) {
     c->genome_dirty = false;
     return PJ_OK;
 }
-
-} // namespace
 
 extern "C" {
 

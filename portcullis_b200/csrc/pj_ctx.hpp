@@ -107,6 +107,8 @@ template <typename T> int ensure(pj_ctx* c, DevBuf<T>& b, size_t need, size_t ke
     return PJ_OK;
 }
 
+int finish_genome(pj_ctx* c);           // pj_api.cu: sorts + uploads the genome's exception table once the uploads are done
+
 // pj_extra.cu: called at the end of pj_shard_run / from pj_shard_begin / pj_destroy
 int extra_keep_pairs(pj_ctx* c, uint32_t n_pairs, const uint32_t* vals, const uint32_t* jid, const pjk::PairRec* pr, cudaStream_t st);
 int extra_classify(pj_ctx* c, cudaStream_t st);
