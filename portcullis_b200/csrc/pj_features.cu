@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(128) k_feat_score(int64_t n, const JuncKey* __
     const double ss = (kmer_score(G, donor, kmer + (size_t)M_DONOR_T * KTAB) - kmer_score(G, donor, kmer + (size_t)M_DONOR_F * KTAB))
                     + (kmer_score(G, acc, kmer + (size_t)M_ACC_T * KTAB) - kmer_score(G, acc, kmer + (size_t)M_ACC_F * KTAB));
     o[0] = 0.0;                                                      // Genuine: a label, not a measurement
-    o[1] = (double)(f.nb_raw - f.nb_ms); o[2] = (double)f.nb_dist; o[3] = (double)f.nb_rel; o[4] = f.entropy; o[5] = f.rel2raw;
+    o[1] = (double)(f.nb_raw - f.nb_ms); o[2] = (double)f.nb_dist; o[3] = (double)f.nb_rel; o[4] = f.entropy;
+    o[5] = (double)f.nb_rel / (double)f.nb_raw;                     // Junction::getReliable2RawAlignmentRatio (junction.hpp:551-553): formed from the counts
     o[6] = (double)f.max_min_anc; o[7] = (double)f.maxmmes; o[8] = f.mean_mismatches;
     {   // Junction::calcIntronScore (junction.cc:953-956)
         const uint32_t size = (uint32_t)(k.end - k.start + 1);
