@@ -149,7 +149,7 @@ void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st) { 
 // one thread packs 64 bases: four 128-bit loads, two g2 words, one gx word
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__ raw, int64_t n, uint64_t base_index /* multiple of 64 */,
-                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx,
+                                                      uint64_t* __restrict__ g2, uint64_t* __restrict__ gx, uint32_t* __restrict__ gsum,
                                                       uint64_t* __restrict__ exc_pos, uint8_t* __restrict__ exc_byte,
                                                       uint32_t* __restrict__ exc_count /* [0] side-table entries, [1] != 0: some base is not A/C/G/T */, uint32_t exc_cap) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,14 +184,14 @@ __global__ void __launch_bounds__(256) k_pack_genome(const uint8_t* __restrict__
     }
     const uint64_t gi = base_index + (uint64_t)b0;
     g2[gi >> 5] = w0; g2[(gi >> 5) + 1] = w1; gx[gi >> 6] = x;
-    if (x) exc_count[1] = 1u;
+    if (x) { exc_count[1] = 1u; atomicOr(gsum + (gi >> 15), 1u << ((gi >> 10) & 31)); }   // 64 | 1024: the thread's bases lie in one stretch
 }
 
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint32_t* gsum,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st) {
     if (n <= 0) return;
     const int64_t threads = (n + 63) / 64;
-    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, exc_pos, exc_byte, exc_count, exc_cap);
+    k_pack_genome<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(raw, n, base_index, g2, gx, gsum, exc_pos, exc_byte, exc_count, exc_cap);
 }
 
 // ================================================================================================
@@ -1170,6 +1170,7 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome&
     uint32_t sh = 0; int32_t tl = 0;
     uint32_t Bl = 0, Bh = 0;                                                          // read word k (G == 1: carried between chunks)
     uint64_t gw0 = 0;                                                                 // index of the block's first genome word (32-base units)
+    bool blk_gx = false;                                                              // the block's stretch of the genome has exception bases: consult gx
     const uint2* qw = nullptr;
     for (;;) {
         if (k >= nchunk) {                                                            // next block of this lane
@@ -1186,6 +1187,10 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome&
             qw = reinterpret_cast<const uint2*>(R.seq2) + (qb0 >> 5);
             sh = (uint32_t)(qb0 & 31) * 2;
             tl = a0 + len;                                                            // end column of the block in chunk coordinates
+            blk_gx = false;
+            if (Gn.any_gx) {                                                          // does any 1024-base stretch under the block hold a non-ACGT base?
+                for (uint64_t sidx = gi0 >> 10; sidx <= (gi0 + (uint64_t)len - 1) >> 10; sidx++) blk_gx |= ((__ldg(Gn.gsum + (sidx >> 5)) >> (sidx & 31)) & 1u) != 0u;
+            }
             k = gl;
             if (k >= nchunk) continue;
             if (G == 1) { const uint2 v = __ldg(qw); Bl = v.x; Bh = v.y; }
@@ -1204,7 +1209,7 @@ __device__ __forceinline__ void drain(const MatchQueue& Q, int nq, const Genome&
         if (tk < 32) V &= ~(~0ull << (2 * tk));
         const uint64_t d = x ^ g;
         uint64_t m = (d | (d >> 1)) & V;                                              // one bit (2c) per mismatching column c
-        if (Gn.any_gx) {                                                              // genome bases that are not A/C/G/T never equal a read base stored here
+        if (blk_gx) {                                                                 // genome bases that are not A/C/G/T never equal a read base stored here
             const uint64_t wi = gw0 + (uint64_t)k;
             const uint32_t e32 = (uint32_t)(__ldg(Gn.gx + (wi >> 1)) >> ((wi & 1) * 32));
             if (e32) m |= spread32(e32) & V;

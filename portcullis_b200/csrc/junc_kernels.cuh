@@ -42,6 +42,8 @@ enum : uint32_t {
 struct Genome {
     const uint64_t* g2;
     const uint64_t* gx;
+    const uint32_t* gsum;       // 1 bit per 1024 bases: set when the stretch holds a base that is not A/C/G/T.  378 KB for a human genome, so it
+                                // stays in L1/L2: the compare loop consults it once per block and reads the gx plane only where it says so
     const uint64_t* goff;       // [n_targets] first base index of each target (multiple of 64)
     const int64_t*  glen;       // [n_targets] sequence length from the FASTA (-1 when the target was not loaded)
     const uint64_t* exc_pos;    // sorted global base indices of "other" exception bytes

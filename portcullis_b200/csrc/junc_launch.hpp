@@ -26,7 +26,7 @@ void launch_rebase_u32(uint32_t* a, int64_t n, uint32_t add, cudaStream_t st);
 void launch_check_offsets(int64_t first, int64_t n, const uint32_t* cigar_off, const uint64_t* seq_off, uint64_t cig_lo, uint64_t cig_hi,
                           uint64_t seq_lo, uint64_t seq_hi, unsigned long long* bad, cudaStream_t st);
 void launch_rebase_u64(uint64_t* a, int64_t n, uint64_t add, cudaStream_t st);
-void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx,
+void launch_pack_genome(const uint8_t* raw, int64_t n, uint64_t base_index, uint64_t* g2, uint64_t* gx, uint32_t* gsum,
                         uint64_t* exc_pos, uint8_t* exc_byte, uint32_t* exc_count, uint32_t exc_cap, cudaStream_t st);
 void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen, unsigned long long* n_nops, int n_sm, cudaStream_t st);
 uint32_t se_num_tiles(int64_t n);

@@ -15,6 +15,11 @@
 
 using namespace pjk;
 
+namespace {
+std::mutex g_trim_mu; std::thread g_trim_thread;          // background release of the memory pool of a destroyed context
+struct TrimJoin { ~TrimJoin() { std::lock_guard<std::mutex> lk(g_trim_mu); if (g_trim_thread.joinable()) g_trim_thread.join(); } } g_trim_join;
+}
+
 namespace pjapi {
 
 thread_local std::string g_last_error;
@@ -138,6 +143,7 @@ int pj_create(const pj_config* cfg, pj_ctx** out) {
         return fail(nullptr, PJ_ECUDA, "pj_create: no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PJ_EINVAL, "pj_create: device %d out of range (0..%d)", cfg->device, ndev - 1);
     if (cfg->orientation < PJ_ORIENT_SE || cfg->orientation > PJ_ORIENT_UNKNOWN) return fail(nullptr, PJ_EINVAL, "pj_create: bad orientation %d", cfg->orientation);
+    { std::lock_guard<std::mutex> lk(g_trim_mu); if (g_trim_thread.joinable()) g_trim_thread.join(); }
     pj_ctx* c = new pj_ctx();
     c->device = cfg->device; c->orientation = cfg->orientation;
     c->match_group = cfg->reserved[0];                 // 0 = choose from the data; 1..32 forces the lanes-per-pair of k_match (tuning / tests)
@@ -185,7 +191,7 @@ void pj_destroy(pj_ctx* c) {
     for (int s = 0; s < 2; s++) { if (c->graw_ev[s]) cudaEventDestroy(c->graw_ev[s]);
                                   if (c->h_graw[s]) cudaFreeHost(c->h_graw[s]); if (c->d_graw[s]) cudaFree(c->d_graw[s]); }
     lap("genome staging");
-    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx);
+    cudaFree(c->d_tlen); cudaFree(c->d_toff); cudaFree(c->d_goff); cudaFree(c->d_glen); cudaFree(c->d_g2); cudaFree(c->d_gx); cudaFree(c->d_gsum);
     cudaFree(c->d_exc_pos); cudaFree(c->d_exc_byte); cudaFree(c->d_exc_count);
     cudaFree(c->d_spliced); cudaFree(c->d_unspliced); cudaFree(c->d_sumq); cudaFree(c->d_minq); cudaFree(c->d_maxq);
     cudaFree(c->d_scalars); cudaFree(c->d_shard_acc); cudaFreeHost(c->h_scalars); cudaFree(c->d_rows);
@@ -194,9 +200,13 @@ void pj_destroy(pj_ctx* c) {
     if (c->copies_done) cudaEventDestroy(c->copies_done);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
-    {   // give the stream-ordered pool back (it was told to keep everything while the context lived)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    {   // Give the stream-ordered pool back (it was told to keep everything while the context lived).  Unmapping tens of GB takes
+        // about a second, so it runs on its own thread, under the caller's finalize + writers; the next pj_create / pj_destroy (or
+        // the end of the process) waits for it.
+        const int dev = c->device;
+        std::lock_guard<std::mutex> lk(g_trim_mu);
+        if (g_trim_thread.joinable()) g_trim_thread.join();
+        g_trim_thread = std::thread([dev]() { cudaSetDevice(dev); cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); });
     }
     lap("streams + pool");
     delete c;
@@ -258,6 +268,7 @@ int pj_targets_set(pj_ctx* c, int32_t n_targets, const int32_t* target_len) {
     CU(c, cudaMemcpy(c->d_glen, c->h_glen.data(), n_targets * sizeof(int64_t), cudaMemcpyHostToDevice));
     CU(c, cudaMalloc(&c->d_g2, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMalloc(&c->d_gx, g / 64 * sizeof(uint64_t) + 64));
     CU(c, cudaMemset(c->d_g2, 0, g / 32 * sizeof(uint64_t) + 64)); CU(c, cudaMemset(c->d_gx, 0, g / 64 * sizeof(uint64_t) + 64));
+    CU(c, cudaMalloc(&c->d_gsum, (g / 32768 + 2) * sizeof(uint32_t))); CU(c, cudaMemset(c->d_gsum, 0, (g / 32768 + 2) * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->d_exc_pos, c->exc_cap * sizeof(uint64_t))); CU(c, cudaMalloc(&c->d_exc_byte, c->exc_cap));
     CU(c, cudaMalloc(&c->d_exc_count, 2 * sizeof(uint32_t))); CU(c, cudaMemset(c->d_exc_count, 0, 2 * sizeof(uint32_t)));
     CU(c, cudaMalloc(&c->d_spliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_unspliced, n_targets * 8)); CU(c, cudaMalloc(&c->d_sumq, n_targets * 8));
@@ -277,7 +288,7 @@ int pj_genome_set_target(pj_ctx* c, int32_t tid, const char* bases, int64_t n_ba
         CU(c, cudaEventSynchronize(c->graw_ev[s]));                  // slot free again?
         memcpy(c->h_graw[s], bases + o, (size_t)k);
         CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->genome_stream));
-        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->genome_stream);
+        launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_gsum, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->genome_stream);
         CU(c, cudaEventRecord(c->graw_ev[s], c->genome_stream));
     }
     c->h_glen[tid] = n_bases < c->h_tlen[tid] ? n_bases : (int64_t)c->h_tlen[tid];
@@ -597,7 +608,7 @@ int pj_shard_run(pj_ctx* c) {
         }
         launch_entropy_sum(J, seg_start, eoff, epos, entropy, st); c->n_launches++;
         mark(c, "entropy");
-        Genome G{c->d_g2, c->d_gx, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->any_gx};
+        Genome G{c->d_g2, c->d_gx, c->d_gsum, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->any_gx};
         uint4* pm = nullptr; CU(c, cudaMallocAsync(&pm, (size_t)P * sizeof(uint4), st));
         {   // lanes per (read, junction) pair: one 16-base word per lane and step; long reads get wider groups
             int group = c->match_group;

@@ -45,7 +45,7 @@ struct pj_ctx {
     int32_t n_targets = 0;
     std::vector<int32_t> h_tlen; std::vector<uint64_t> h_toff, h_goff; std::vector<int64_t> h_glen;
     int32_t* d_tlen = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_goff = nullptr; int64_t* d_glen = nullptr;
-    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint64_t g_total_bases = 0;
+    uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint32_t* d_gsum = nullptr; uint64_t g_total_bases = 0;
     uint64_t* d_exc_pos = nullptr; uint8_t* d_exc_byte = nullptr; uint32_t* d_exc_count = nullptr; uint32_t exc_cap = 1u << 20;
     int32_t n_exc = 0, n_exc_x = 0, any_gx = 0; bool genome_dirty = false;
     uint8_t* h_graw[2] = {nullptr, nullptr}; uint8_t* d_graw[2] = {nullptr, nullptr}; cudaEvent_t graw_ev[2] = {nullptr, nullptr};

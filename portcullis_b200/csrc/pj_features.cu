@@ -212,7 +212,7 @@ int check_rows(pj_ctx* c, const pj_junction* rows, int64_t n) {
     return PJ_OK;
 }
 
-Genome genome_of(pj_ctx* c) { return Genome{c->d_g2, c->d_gx, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->any_gx}; }
+Genome genome_of(pj_ctx* c) { return Genome{c->d_g2, c->d_gx, c->d_gsum, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->any_gx}; }
 
 // counts -> probabilities: model[ctx][next] = count / sum over next (markov_model.cc:45-54, 94-103), fp64
 void normalise(const unsigned long long* cnt, double* prob, int n_ctx) {
