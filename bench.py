@@ -404,7 +404,7 @@ def e2e_bam_leg(args, prep, rank, world, local, cores, barrier, np, jb):
     mid = order[len(order) // 2]
     dt, rep = runs[mid], reps[mid]
     res = {"value": n_spliced / dt, "unit": UNIT, "seconds": round(dt, 3), "seconds_all": [round(r, 3) for r in runs], "host_threads_per_rank": cores,
-           "breakdown_s_rank0": {k: round(rep[k], 4) for k in ("t_open_s", "t_init_s", "t_genome_s", "t_decode_s", "t_run_s", "t_teardown_s", "t_finalize_s", "t_write_s")},
+           "breakdown_s_rank0": {k: round(rep[k], 4) for k in ("t_open_s", "t_init_s", "t_genome_s", "t_decode_s", "t_run_s", "t_teardown_s", "t_finalize_s", "t_write_s", "t_total_s")},
            "gpu_pipeline_ms_rank0": round(rep["t_gpu_ms"], 3), "segments_rank0": rep.get("n_segments"), "junctions": rep.get("n_junctions"),
            "what": "BAM file -> junctions.tab/.bed written; BGZF decode on the host cores, %d GPU(s)" % world}
     gold = golden_md5(args.preset, args.scale)

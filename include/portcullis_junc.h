@@ -317,6 +317,10 @@ int pj_extra_target_pileup(pj_ctx* ctx, int32_t tid, int32_t* covered, uint32_t*
  */
 int pj_extra_coverage(pj_ctx* ctx, int32_t depth_tid, int64_t n, const int32_t* intron_start, const int32_t* intron_end,
                       uint32_t* cov_sum4);
+/* The same for junctions of any number of targets in ONE launch: depth_tid[j] = the target whose depth vector junction j is
+ * scored against (pj_extra_coverage_source of the junction's own target; -1: none, the sums are 0).  The depth vectors must
+ * live in this context. */
+int pj_extra_coverage_batch(pj_ctx* ctx, int64_t n, const int32_t* depth_tid, const int32_t* intron_start, const int32_t* intron_end, uint32_t* cov_sum4);
 
 /* Q14 as a function: covered[t] per target -> depth_src[t] = target whose depth vector the reference applies to the
  * junctions of t (-1: coverage stays 0). */

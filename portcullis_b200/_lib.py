@@ -162,6 +162,7 @@ SYMBOLS = {
     "pj_extra_kernel_times": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]),
     "pj_extra_target_pileup": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]),
     "pj_extra_coverage": (C.c_int, [_P, C.c_int32, C.c_int64, _P, _P, _P]),
+    "pj_extra_coverage_batch": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "pj_extra_coverage_source": (None, [C.c_int32, _P, _P]),
     "pj_extra_finalize": (None, [_P, C.c_int64]),
     "pj_features_create": (C.c_int, [_P, C.POINTER(_P)]),

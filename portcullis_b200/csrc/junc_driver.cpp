@@ -773,19 +773,24 @@ int junc_core(const pjh_options* o, int part, int n_parts_in, pjh_partial* parti
             if (live >= 8000 && o->verbose) std::cerr << " - " << H.names[t] << ": up to " << live << " unspliced alignments on one position; htslib's 8000-read pileup cap is replayed there\n";
         }
         pj_extra_coverage_source(T, covered.data(), src.data());
-        for (int g = 0; g < n_gpus; g++) {
-            auto& rws = outs[g].rows;
-            for (size_t a = 0; a < rws.size();) {
-                size_t b = a; while (b < rws.size() && rws[b].tid == rws[a].tid) b++;
-                const int32_t t = rws[a].tid, d = src[t];
-                if (d >= 0) {
-                    std::vector<int32_t> st(b - a), en(b - a); std::vector<uint32_t> sums((b - a) * 4);
-                    for (size_t k = a; k < b; k++) { st[k - a] = rws[k].start; en[k - a] = rws[k].end; }
-                    pj_ctx* dc = outs[owner[d]].ctx;
-                    if ((rc = pj_extra_coverage(dc, d, (int64_t)(b - a), st.data(), en.data(), sums.data()))) return fail(rc, pj_last_error(dc));
-                    for (size_t k = a; k < b; k++) memcpy(outs[g].extra[k].cov_sum, &sums[(k - a) * 4], 16);
+        {   // one batched query per GPU that owns depth vectors (not one launch + sync per target: a 3 000-target genome went through the host)
+            struct Q { std::vector<int32_t> dt, st, en; std::vector<std::pair<int, size_t>> where; };
+            std::vector<Q> q((size_t)n_gpus);
+            for (int g = 0; g < n_gpus; g++) {
+                auto& rws = outs[g].rows;
+                for (size_t k = 0; k < rws.size(); k++) {
+                    const int32_t d = src[rws[k].tid];
+                    if (d < 0) continue;
+                    Q& x = q[(size_t)owner[d]];
+                    x.dt.push_back(d); x.st.push_back(rws[k].start); x.en.push_back(rws[k].end); x.where.emplace_back(g, k);
                 }
-                a = b;
+            }
+            for (int g = 0; g < n_gpus; g++) {
+                Q& x = q[(size_t)g];
+                if (x.dt.empty()) continue;
+                std::vector<uint32_t> sums(x.dt.size() * 4);
+                if ((rc = pj_extra_coverage_batch(outs[g].ctx, (int64_t)x.dt.size(), x.dt.data(), x.st.data(), x.en.data(), sums.data()))) return fail(rc, pj_last_error(outs[g].ctx));
+                for (size_t k = 0; k < x.where.size(); k++) memcpy(outs[(size_t)x.where[k].first].extra[x.where[k].second].cov_sum, &sums[k * 4], 16);
             }
         }
         for (auto& x : outs) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; }

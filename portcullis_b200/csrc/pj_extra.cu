@@ -327,17 +327,31 @@ __global__ void __launch_bounds__(256) k_x_region_flag(uint32_t nH, const uint32
     flag[h] = st ? 1u : 0u;
 }
 
-// k_x_cap with the state in shared memory: one warp per REGION (regions are independent), end counts in a ring indexed by
-// position (valid while span + 2 <= XR_RING), the next XR_STAGE reads' positions and spans staged by coalesced loads.  Same
-// arithmetic as k_x_cap, which remains the path for targets whose reads span more than the ring.
+// k_x_cap with the state in shared memory: one CTA per REGION (regions are independent), end counts in a ring indexed by
+// position (valid while span + 2 <= XR_RING).  Same arithmetic as k_x_cap, which remains the path for targets whose reads span
+// more than the ring.  The columns of a region are walked one after the other (htslib's rule is sequential), but everything
+// inside a column — freeing the ends that were passed, counting the reads that start on it, inserting the accepted ones — is
+// spread over the 256 threads: a hot locus puts tens of thousands of reads on ONE column, and with one warp per region those
+// passed through 32 lanes (37 ms on the hot-locus preset c4).
 constexpr int XR_RING = 4096;
-constexpr int XR_STAGE = 1024;
-__global__ void __launch_bounds__(32) k_x_cap_ring(uint32_t nR, const uint32_t* __restrict__ RS, const uint32_t* __restrict__ H, uint32_t nH,
-                                                    const int32_t* __restrict__ u_tid, const uint32_t* __restrict__ u_toff, const int32_t* __restrict__ u_pos,
-                                                    const int32_t* __restrict__ u_alen, const int32_t* __restrict__ maxspan_t, uint8_t* __restrict__ accepted) {
+constexpr int XC_THREADS = 256;
+__device__ __forceinline__ uint32_t xc_block_sum(uint32_t v, uint32_t* s_red) {
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < XC_THREADS / 32; w++) t += s_red[w];
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(XC_THREADS) k_x_cap_ring(uint32_t nR, const uint32_t* __restrict__ RS, const uint32_t* __restrict__ H, uint32_t nH,
+                                                            const int32_t* __restrict__ u_tid, const uint32_t* __restrict__ u_toff, const int32_t* __restrict__ u_pos,
+                                                            const int32_t* __restrict__ u_alen, const int32_t* __restrict__ maxspan_t, uint8_t* __restrict__ accepted) {
     __shared__ uint32_t ring[XR_RING];
-    __shared__ int32_t spos[XR_STAGE], salen[XR_STAGE];
-    const uint32_t r = blockIdx.x; const int lane = threadIdx.x;
+    __shared__ uint32_t s_red[XC_THREADS / 32];
+    __shared__ long long s_live;
+    const uint32_t r = blockIdx.x; const int tid = threadIdx.x;
     if (r >= nR) return;
     constexpr uint32_t M = XR_RING - 1;
     uint32_t h = RS[r]; const uint32_t hEnd = r + 1 < nR ? RS[r + 1] : nH;
@@ -346,73 +360,56 @@ __global__ void __launch_bounds__(32) k_x_cap_ring(uint32_t nR, const uint32_t* 
     const uint32_t lo = u_toff[t], hi = u_toff[t + 1];
     const int64_t span = maxspan_t[t];
     const int64_t P0 = u_pos[start];
-    for (int k = lane; k < XR_RING; k += 32) ring[k] = 0;
-    __syncwarp();
+    for (int k = tid; k < XR_RING; k += XC_THREADS) ring[k] = 0;
+    __syncthreads();
     int64_t live = 0;
     {   // every earlier read still alive at P0 is accepted (no hot column within reach)
         const uint32_t a0 = x_lower(u_pos, lo, start, P0 - span);
         uint32_t c = 0;
-        for (uint32_t j = a0 + lane; j < start; j += 32) {
+        for (uint32_t j = a0 + tid; j < start; j += XC_THREADS) {
             const int64_t E = (int64_t)u_pos[j] + u_alen[j];
             if (E >= P0) { c++; atomicAdd(&ring[(uint32_t)E & M], 1u); }
         }
-        live = __reduce_add_sync(0xffffffffu, c);
+        live = xc_block_sum(c, s_red);
     }
-    __syncwarp();
-    uint32_t sbase = start, sn = 0;
-    auto stage = [&](uint32_t from) {
-        sbase = from; sn = min((uint32_t)XR_STAGE, hi - from);
-        for (uint32_t k = lane; k < sn; k += 32) { spos[k] = u_pos[from + k]; salen[k] = u_alen[from + k]; }
-        __syncwarp();
-    };
-    auto pos_of = [&](uint32_t j) -> int32_t { const uint32_t k = j - sbase; return k < sn ? spos[k] : u_pos[j]; };
-    auto alen_of = [&](uint32_t j) -> int32_t { const uint32_t k = j - sbase; return k < sn ? salen[k] : u_alen[j]; };
-    stage(start);
     uint32_t i = start; int64_t prevP = P0, lastHot = P0;
-    while (i < hi) {
-        if (i - sbase >= (uint32_t)(XR_STAGE / 2) && sbase + sn < hi) stage(i);
-        const int64_t P = pos_of(i);
+    while (i < hi) {                                       // uniform over the block: every quantity below is the same in all threads
+        const int64_t P = u_pos[i];
         if (P > lastHot + span) break;
         if (P > prevP) {                                   // nodes whose end has been passed are freed (end <= P - 1); their slots recycle
             uint32_t s2 = 0;
-            for (int64_t e = prevP + lane; e < P; e += 32) { s2 += ring[(uint32_t)e & M]; ring[(uint32_t)e & M] = 0; }
-            live -= __reduce_add_sync(0xffffffffu, s2);
-            __syncwarp();
+            for (int64_t e = prevP + tid; e < P; e += XC_THREADS) { s2 += ring[(uint32_t)e & M]; ring[(uint32_t)e & M] = 0; }
+            live -= xc_block_sum(s2, s_red);
         }
-        uint32_t n = 0;                                    // reads on this column
-        for (;;) {
-            const uint32_t j = i + n + lane;
-            const unsigned same = __ballot_sync(0xffffffffu, j < hi && pos_of(j) == P);
-            if (same == 0xffffffffu) { n += 32; continue; }
-            n += __ffs(~same) - 1; break;
-        }
+        const uint32_t n = x_lower(u_pos, i, hi, P + 1) - i;   // reads on this column (positions are sorted)
         const bool is_hot = h < hEnd && H[h] == i;
         uint32_t keep = n;
         if (is_hot) { const int64_t room = (int64_t)(PLP_MAXCNT - 1) - live; keep = (uint32_t)(room < 1 ? 1 : room > (int64_t)n ? (int64_t)n : room); h += n; }
         bool zero_len = false;
-        if (is_hot) { for (uint32_t k = lane; k < n; k += 32) zero_len |= alen_of(i + k) == 0; zero_len = __any_sync(0xffffffffu, zero_len); }
+        if (is_hot) { uint32_t z = 0; for (uint32_t k = tid; k < n; k += XC_THREADS) z |= u_alen[i + k] == 0 ? 1u : 0u; zero_len = xc_block_sum(z, s_red) != 0u; }
         if (is_hot && zero_len) {                          // a read without reference span gets no node unless it opens the column: replay one by one
-            if (lane == 0) {
+            if (tid == 0) {
                 int64_t lv = live;
                 for (uint32_t k = 0; k < n; k++) {
-                    const int64_t E = P + alen_of(i + k);
+                    const int64_t E = P + u_alen[i + k];
                     const bool ok = k == 0 || 2 + lv <= PLP_MAXCNT;
                     accepted[i + k] = ok ? 1 : 0;
                     if (ok && (k == 0 ? E >= P : E > P)) { ring[(uint32_t)E & M] += 1; lv++; }
                 }
-                live = lv;
+                s_live = lv;
             }
-            live = __shfl_sync(0xffffffffu, live, 0);
+            __syncthreads();
+            live = s_live;
+            __syncthreads();
         } else {
             uint32_t c = 0;
-            for (uint32_t k = lane; k < n; k += 32) {
+            for (uint32_t k = tid; k < n; k += XC_THREADS) {
                 if (k >= keep) { accepted[i + k] = 0; continue; }
-                const int64_t E = P + alen_of(i + k);
+                const int64_t E = P + u_alen[i + k];
                 if (k == 0 ? E >= P : E > P) { c++; atomicAdd(&ring[(uint32_t)E & M], 1u); }
             }
-            live += __reduce_add_sync(0xffffffffu, c);
+            live += xc_block_sum(c, s_red);
         }
-        __syncwarp();
         i += n; prevP = P; if (is_hot) lastHot = P;
     }
 }
@@ -453,6 +450,27 @@ __global__ void __launch_bounds__(256) k_x_coverage(int64_t n, const int32_t* __
     else if (w == 2) { a = e + R; b = e + 2 * R; } else { a = e; b = e + R - 1; }
     uint32_t sum = 0;
     for (int64_t i = a; i <= b; i++) if (i >= 0 && i < size) sum += depth[i];
+    out[g] = sum;
+}
+
+// The same for junctions of many targets at once: dtid[j] names the target whose depth vector junction j is scored against
+// (the Q14 mapping, -1: none -> zeros), doff / tlen locate that vector.
+__global__ void __launch_bounds__(256) k_x_coverage_batch(int64_t n, const int32_t* __restrict__ start, const int32_t* __restrict__ end, const int32_t* __restrict__ dtid,
+                                                           const uint32_t* __restrict__ depth, const uint64_t* __restrict__ doff, const int32_t* __restrict__ tlen,
+                                                           uint32_t* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n * 4) return;
+    const int64_t j = g >> 2; const int w = (int)(g & 3);
+    const int32_t dt = dtid[j];
+    if (dt < 0) { out[g] = 0; return; }
+    const uint32_t* d = depth + doff[dt]; const int64_t size = tlen[dt];
+    const int32_t R = 10;
+    const int32_t s = start[j], e = end[j];
+    int32_t a, b;
+    if (w == 0) { a = s - 2 * R; b = s - R - 1; } else if (w == 1) { a = s - R; b = s; }
+    else if (w == 2) { a = e + R; b = e + 2 * R; } else { a = e; b = e + R - 1; }
+    uint32_t sum = 0;
+    for (int64_t i = a; i <= b; i++) if (i >= 0 && i < size) sum += d[i];
     out[g] = sum;
 }
 
@@ -651,7 +669,7 @@ int pj_extra_run(pj_ctx* c, int32_t max_query_length, pj_junction_extra* out, in
             CU(c, cudaMemcpyAsync(&nR, c->d_scalars + 11, 4, cudaMemcpyDeviceToHost, st)); CU(c, cudaStreamSynchronize(st));
             CU(c, cudaMallocAsync(&RS, (size_t)std::max<uint32_t>(nR, 1) * 4, st));
             k_x_compact<<<blocks_for(nH, 256), 256, 0, st>>>(nH, rflag, roff, RS);
-            if (nR) k_x_cap_ring<<<nR, 32, 0, st>>>(nR, RS, H, nH, u_tid, u_toff, u_pos, u_alen, maxspan, accepted);
+            if (nR) k_x_cap_ring<<<nR, XC_THREADS, 0, st>>>(nR, RS, H, nH, u_tid, u_toff, u_pos, u_alen, maxspan, accepted);
             CU(c, cudaFreeAsync(rflag, st)); CU(c, cudaFreeAsync(roff, st)); CU(c, cudaFreeAsync(RS, st));
             launches += 6;
         } else {
@@ -709,6 +727,29 @@ int pj_extra_coverage(pj_ctx* c, int32_t depth_tid, int64_t n, const int32_t* in
     CU(c, cudaMemcpyAsync(cov_sum4, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
     CU(c, cudaFreeAsync(ds, st)); CU(c, cudaFreeAsync(de, st)); CU(c, cudaFreeAsync(dout, st));
+    return PJ_OK;
+}
+
+// One launch for the junctions of any number of targets: depth_tid[j] is the target whose depth vector junction j uses
+// (pj_extra_coverage_source of the junction's own target), or -1.  cov_sum4[j][4] as pj_extra_coverage.
+int pj_extra_coverage_batch(pj_ctx* c, int64_t n, const int32_t* depth_tid, const int32_t* intron_start, const int32_t* intron_end, uint32_t* cov_sum4) {
+    if (!c || !c->x_ready) return fail(c, PJ_ESTATE, "pj_extra_coverage_batch: call pj_extra_run first");
+    if (n < 0 || (n && (!depth_tid || !intron_start || !intron_end || !cov_sum4))) return fail(c, PJ_EINVAL, "pj_extra_coverage_batch: bad arguments");
+    if (n == 0) return PJ_OK;
+    for (int64_t j = 0; j < n; j++) if (depth_tid[j] >= c->n_targets) return fail(c, PJ_EINVAL, "pj_extra_coverage_batch: bad target");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->compute_stream;
+    int32_t *ds = nullptr, *de = nullptr, *dt = nullptr; uint32_t* dout = nullptr; uint64_t* ddoff = nullptr;
+    const size_t T = (size_t)c->n_targets;
+    CU(c, cudaMallocAsync(&ds, (size_t)n * 4, st)); CU(c, cudaMallocAsync(&de, (size_t)n * 4, st)); CU(c, cudaMallocAsync(&dt, (size_t)n * 4, st));
+    CU(c, cudaMallocAsync(&dout, (size_t)n * 16, st)); CU(c, cudaMallocAsync(&ddoff, (T + 1) * 8, st));
+    CU(c, cudaMemcpyAsync(ds, intron_start, (size_t)n * 4, cudaMemcpyHostToDevice, st)); CU(c, cudaMemcpyAsync(de, intron_end, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(dt, depth_tid, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(ddoff, c->x_doff.data(), std::min(c->x_doff.size(), T + 1) * 8, cudaMemcpyHostToDevice, st));
+    k_x_coverage_batch<<<blocks_for((uint64_t)n * 4, 256), 256, 0, st>>>(n, ds, de, dt, c->x_depth, ddoff, c->d_tlen, dout);
+    CU(c, cudaMemcpyAsync(cov_sum4, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st)); CU(c, cudaGetLastError());
+    for (void* p : {(void*)ds, (void*)de, (void*)dt, (void*)dout, (void*)ddoff}) CU(c, cudaFreeAsync(p, st));
     return PJ_OK;
 }
 

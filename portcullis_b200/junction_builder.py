@@ -207,6 +207,15 @@ class JuncGpu:
         _check(self._lib.pj_extra_coverage(self._ctx, int(depth_tid), len(s), s.ctypes.data, e.ctypes.data, out.ctypes.data), self._err)
         return out
 
+    def coverage_batch(self, depth_tid, starts, ends):
+        """cov_sum of junctions of many targets in one launch; depth_tid[j] = target whose depth vector junction j uses (-1: none)."""
+        d = np.ascontiguousarray(depth_tid, dtype=np.int32)
+        s = np.ascontiguousarray(starts, dtype=np.int32)
+        e = np.ascontiguousarray(ends, dtype=np.int32)
+        out = np.zeros((len(s), 4), dtype=np.uint32)
+        _check(self._lib.pj_extra_coverage_batch(self._ctx, len(s), d.ctypes.data, s.ctypes.data, e.ctypes.data, out.ctypes.data), self._err)
+        return out
+
     def extra(self, rows, max_query_length):
         """All four `--extra` columns for a single-context run: rows as returned by fetch().  Returns
         (EXTRA_DTYPE array in the order of rows, {tid: live-read maximum} of the targets where htslib's pileup read cap was replayed)."""
@@ -219,11 +228,8 @@ class JuncGpu:
             if mx >= 8000:
                 over[t] = mx
         src = coverage_source(covered)
-        for t in np.unique(rows["tid"]):
-            if src[t] < 0:
-                continue
-            sel = np.nonzero(rows["tid"] == t)[0]
-            x["cov_sum"][sel] = self.coverage(src[t], rows["start"][sel], rows["end"][sel])
+        if len(rows):
+            x["cov_sum"] = self.coverage_batch(src[rows["tid"]], rows["start"], rows["end"])
         return extra_finalize(x), over
 
     def timing(self):
