@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
         const uint32_t flag = R.flag[i];
         const uint32_t cig0 = R.cigar_off[i], cig1 = R.cigar_off[i + 1];
         const uint8_t xs = R.xs[i], mq = R.mapq[i];
-        const int32_t mtid = R.mtid[i], mpos = R.mpos[i], lq = R.l_qseq[i];
+        const bool oriented = orientation == PJ_ORIENT_FR || orientation == PJ_ORIENT_RF || orientation == PJ_ORIENT_FF;   // uniform: the mate columns are only read then
+        const int32_t mtid = oriented ? R.mtid[i] : -1, mpos = oriented ? R.mpos[i] : -1, lq = R.l_qseq[i];
         const uint64_t so = R.seq_off[i], so1 = R.seq_off[i + 1];
         const int32_t refLen = tlen[tid];
         const uint64_t tbase = toff[tid];
