@@ -211,7 +211,18 @@ inline bool Inflater::run(const uint8_t* in, size_t in_len, uint8_t* out, size_t
                 if (bc < 0) return false;
                 if (dist > (size_t)(out - out_begin) || len > (size_t)(out_end - out)) return false;
                 const uint8_t* src = out - dist;
-                if (dist == 1) memset(out, src[0], len);                // runs (e.g. absent base qualities, 0xff)
+                if (dist >= 16 && out < out_fast) {
+                    // the common case (BAM blocks: mean match length ~30): two unconditional 16-byte copies, then a loop only for long
+                    // matches — no data-dependent loop exit for most matches.  out_fast keeps 300 bytes of room, so 32 bytes never overrun.
+                    uint64_t a, b, c, d;
+                    memcpy(&a, src, 8); memcpy(&b, src + 8, 8); memcpy(out, &a, 8); memcpy(out + 8, &b, 8);
+                    memcpy(&c, src + 16, 8); memcpy(&d, src + 24, 8); memcpy(out + 16, &c, 8); memcpy(out + 24, &d, 8);
+                    if (len > 32) {
+                        uint8_t* o = out + 32; const uint8_t* s = src + 32; const uint8_t* const oe = out + len;
+                        do { memcpy(&a, s, 8); memcpy(&b, s + 8, 8); memcpy(o, &a, 8); memcpy(o + 8, &b, 8); s += 16; o += 16; } while (o < oe);
+                    }
+                }
+                else if (dist == 1) memset(out, src[0], len);                // runs (e.g. absent base qualities, 0xff)
                 else if (dist >= 8) {                                   // word copies may run up to 7 bytes past the match: capacity has 16 bytes of slack
                     uint8_t* o = out; const uint8_t* s = src; const uint8_t* const oe = out + len;
                     do { uint64_t w; memcpy(&w, s, 8); memcpy(o, &w, 8); s += 8; o += 8; } while (o < oe);

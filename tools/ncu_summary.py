@@ -2,7 +2,7 @@
 """Turn ncu outputs brought back in gpurun_out/ into the small, tracked summaries under profiles/.
 
     python tools/ncu_summary.py launches gpurun_out/launches_rN.csv  profiles/rN_launches.md
-    python tools/ncu_summary.py kernels  gpurun_out/prof_rN.ncu-rep  profiles/rN_kernels.md [profiles/dominant_kernel_traffic.json]
+    python tools/ncu_summary.py kernels  gpurun_out/prof_rN.ncu-rep  profiles/rN_kernels.md [profiles/dominant_kernel_traffic.json [preset]]
 """
 import collections
 import csv
@@ -13,7 +13,7 @@ import sys
 
 STAGE_OF = {"k_scan_emit": "scan_emit", "k_os_pass": "radix_sort_one_pass", "k_os_hist": "radix_sort_hist", "k_scan_reads": "scan_reads", "k_emit_pairs": "emit_pairs", "k_rs_hist": "radix_sort", "k_rs_scatter": "radix_sort",
             "k_reduce1": "reduce1", "k_match": "match", "k_reduce2": "reduce2", "k_finalize": "finalize", "k_entropy_sum": "entropy",
-            "k_entropy_compact": "entropy", "k_seg_heads": "segments", "k_seg_ids": "segments", "k_junc_init": "reduce1"}
+            "k_entropy_compact": "entropy", "k_seg_heads": "segments", "k_seg_ids": "segments", "k_junc_init": "reduce1", "k_flag_scan": "flag_scans"}
 
 
 def short(name):
@@ -55,7 +55,7 @@ def to_bytes(v, unit):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
 
 
-def kernels(src, dst, traffic_json=None):
+def kernels(src, dst, traffic_json=None, preset=None):
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -88,8 +88,18 @@ def kernels(src, dst, traffic_json=None):
                 if st:
                     traffic[st] = traffic.get(st, 0) + t
     if traffic_json:
+        # {preset: {stage: bytes per launch}}: bench.py copies the dominant stage's value of its preset into roofline.traffic
+        allp = {}
+        try:
+            with open(traffic_json) as f:
+                allp = json.load(f)
+            if allp and not all(isinstance(v, dict) for v in allp.values()):
+                allp = {}
+        except Exception:
+            pass
+        allp[preset or "c2"] = {k: int(v) for k, v in traffic.items()}
         with open(traffic_json, "w") as f:
-            json.dump({k: int(v) for k, v in traffic.items()}, f, indent=1)
+            json.dump(allp, f, indent=1, sort_keys=True)
             f.write("\n")
     print("wrote", dst)
 
@@ -98,4 +108,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        kernels(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        kernels(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else None)
