@@ -422,6 +422,7 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
     pj_ctx* ctx = nullptr;
     std::mutex gm; std::condition_variable gcv; bool ready = false; int gpu_rc = PJ_OK; std::string gpu_err;
     int genome_rc = PJ_OK; std::string genome_err;
+    std::vector<char> genome_done((size_t)T, 0); bool genome_finished = false;   // guarded by gm: a segment only waits for the genome of ITS targets
     const double ti = now_s();
     std::thread gpu_thread([&]() {
         pj_config cfg; memset(&cfg, 0, sizeof cfg);
@@ -440,15 +441,21 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         // genome: only this part's targets become resident on this GPU (own CUDA stream; overlaps the batch submission)
         const double tg = now_s();
         std::string seq;
-        for (int32_t t : my_targets) {
-            if (prep->indexed && prep->bam.index()[(size_t)t].first_voff == 0) continue;   // no records -> no junctions -> no genome needed
+        auto done = [&](int32_t t, int code, const std::string& msg) {
+            { std::lock_guard<std::mutex> lk(gm); if (t >= 0) genome_done[(size_t)t] = 1; if (code) { genome_rc = code; genome_err = msg; } if (t < 0 || code) genome_finished = true; }
+            gcv.notify_all();
+        };
+        for (int32_t t : my_targets) {                                 // ascending = the order the segments need them
+            if (prep->indexed && prep->bam.index()[(size_t)t].first_voff == 0) { done(t, PJ_OK, ""); continue; }   // no records -> no junctions -> no genome needed
             const pjio::FaiEntry* e = prep->fasta.find(H.names[t]);
-            if (!e) continue;
-            try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { genome_rc = PJ_EIO; genome_err = ex.what(); return; }
+            if (!e) { done(t, PJ_OK, ""); continue; }
+            try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { done(t, PJ_EIO, ex.what()); return; }
             int q = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size());
-            if (q) { genome_rc = q; genome_err = pj_last_error(ctx); return; }
+            if (q) { done(t, q, pj_last_error(ctx)); return; }
+            done(t, PJ_OK, "");
         }
         out.genome_s = now_s() - tg;
+        done(-1, PJ_OK, "");
     });
     struct Cleanup {
         std::thread& t; pj_ctx*& c; double* td;
@@ -530,11 +537,11 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
             });
         if (r) { wait_ready(); return bail(r, g_err); }
         out.decode_s += now_s() - td;
-        if (first) {
-            if ((r = wait_ready())) return bail(r, gpu_err);
-            gpu_thread.join();
+        if (first) { if ((r = wait_ready())) return bail(r, gpu_err); first = false; }
+        {   // the genome of this segment's targets must be resident; later targets keep uploading under the next segments' decode
+            std::unique_lock<std::mutex> lk(gm);
+            gcv.wait(lk, [&] { if (genome_rc || genome_finished) return true; for (int32_t t : sg.targets) if (!genome_done[(size_t)t]) return false; return true; });
             if (genome_rc) return bail(genome_rc, genome_err);
-            first = false;
         }
         const double tr = now_s();
         if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));

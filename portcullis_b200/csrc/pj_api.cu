@@ -101,6 +101,7 @@ void mark(pj_ctx* c, const char* name) {
 
 // sort + upload the "other exception byte" table after genome uploads
 int pjapi::finish_genome(pj_ctx* c) {
+    std::lock_guard<std::mutex> glk(c->genome_mu);
     if (!c->genome_dirty) return PJ_OK;
     CU(c, cudaStreamSynchronize(c->genome_stream));
     uint32_t cnt2[2] = {0, 0};
@@ -287,10 +288,12 @@ int pj_genome_set_target(pj_ctx* c, int32_t tid, const char* bases, int64_t n_ba
         const int64_t k = std::min<int64_t>((int64_t)pj_ctx::GRAW_CHUNK, n - o);
         CU(c, cudaEventSynchronize(c->graw_ev[s]));                  // slot free again?
         memcpy(c->h_graw[s], bases + o, (size_t)k);
+        std::lock_guard<std::mutex> glk(c->genome_mu);               // per chunk: finish_genome (another thread) must not sort the exception table under a pack kernel
         CU(c, cudaMemcpyAsync(c->d_graw[s], c->h_graw[s], (size_t)k, cudaMemcpyHostToDevice, c->genome_stream));
         launch_pack_genome(c->d_graw[s], k, c->h_goff[tid] + (uint64_t)o, c->d_g2, c->d_gx, c->d_gsum, c->d_exc_pos, c->d_exc_byte, c->d_exc_count, c->exc_cap, c->genome_stream);
         CU(c, cudaEventRecord(c->graw_ev[s], c->genome_stream));
     }
+    std::lock_guard<std::mutex> glk(c->genome_mu);
     c->h_glen[tid] = n_bases < c->h_tlen[tid] ? n_bases : (int64_t)c->h_tlen[tid];
     CU(c, cudaMemcpyAsync(c->d_glen + tid, &c->h_glen[tid], sizeof(int64_t), cudaMemcpyHostToDevice, c->genome_stream));
     CU(c, cudaGetLastError());

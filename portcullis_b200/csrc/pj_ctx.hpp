@@ -48,6 +48,8 @@ struct pj_ctx {
     uint64_t* d_g2 = nullptr; uint64_t* d_gx = nullptr; uint32_t* d_gsum = nullptr; uint64_t g_total_bases = 0;
     uint64_t* d_exc_pos = nullptr; uint8_t* d_exc_byte = nullptr; uint32_t* d_exc_count = nullptr; uint32_t exc_cap = 1u << 20;
     int32_t n_exc = 0, n_exc_x = 0, any_gx = 0; bool genome_dirty = false;
+    std::mutex genome_mu;               // pj_genome_set_target (its own host thread) against finish_genome (inside pj_shard_run / pj_features_*): a target may still be
+                                        // uploading while a shard that does not need it runs
     uint8_t* h_graw[2] = {nullptr, nullptr}; uint8_t* d_graw[2] = {nullptr, nullptr}; cudaEvent_t graw_ev[2] = {nullptr, nullptr};
     static constexpr size_t GRAW_CHUNK = 64u << 20;
     // shard arena

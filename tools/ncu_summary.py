@@ -56,7 +56,10 @@ def to_bytes(v, unit):
 
 
 def kernels(src, dst, traffic_json=None, preset=None):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    if src.endswith(".csv"):                       # already exported on the GPU box (`ncu -i rep --page raw --csv`): the .ncu-rep files are too big to bring back
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
