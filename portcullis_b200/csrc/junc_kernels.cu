@@ -244,7 +244,7 @@ void launch_prescan_cigar(const uint32_t* cigar, uint64_t n, uint32_t* max_nlen,
     k_prescan_cigar<<<blocks, 256, 0, st>>>(cigar, n, max_nlen, n_nops);
 }
 
-template <int SE_ITEMS, bool DENSE /* phase B over the tile's spliced records compacted through shared memory (all lanes busy) */>
+template <int SE_ITEMS>
 __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int32_t* __restrict__ tlen, int32_t n_targets, const uint64_t* __restrict__ toff,
                                                            const uint32_t* __restrict__ max_nlen, int32_t orientation, TargetAcc T,
                                                            uint64_t* __restrict__ keys, PairRec* __restrict__ pr,
@@ -331,28 +331,6 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
     uint32_t off[SE_ITEMS]; uint32_t carry = 0;
 #pragma unroll
     for (int r = 0; r < SE_ITEMS; r++) { const uint32_t ex = block_excl_scan(cnt[r], &s_tot); off[r] = carry + ex; carry += s_tot; }
-    // Dense phase B: a third of the records of a typical RNA-seq BAM carry no N op, so with one thread per record a third of the lanes
-    // idle through the emit walk.  The tile's spliced records are compacted into a list in shared memory (with what phase A learnt
-    // about them) and phase B strides over that list instead.
-    constexpr int SE_TILE_C = SE_THREADS * SE_ITEMS;
-    __shared__ uint16_t s_ids[DENSE ? SE_TILE_C : 1];
-    __shared__ uint32_t s_cntz[DENSE ? SE_TILE_C : 1];                 // N ops of the record | zero-length-N flag << 31
-    __shared__ uint32_t s_off[DENSE ? SE_TILE_C : 1];                  // first pair slot of the record inside the tile
-    __shared__ int32_t s_rend[DENSE ? SE_TILE_C : 1];
-    __shared__ uint32_t s_nspl;
-    if (DENSE) {
-        uint32_t mine = 0;
-#pragma unroll
-        for (int r = 0; r < SE_ITEMS; r++) mine += cnt[r] ? 1u : 0u;
-        uint32_t w = block_excl_scan(mine, &s_tot);
-        if (threadIdx.x == 0) s_nspl = s_tot;
-#pragma unroll
-        for (int r = 0; r < SE_ITEMS; r++) if (cnt[r]) {
-            s_ids[w] = (uint16_t)(r * SE_THREADS + threadIdx.x);
-            s_cntz[w] = cnt[r] | (zeron[r] ? 0x80000000u : 0u); s_off[w] = off[r]; s_rend[w] = rend[r];
-            w++;
-        }
-    }
     if (threadIdx.x < 32) {                                            // warp 0: publish the tile aggregate, look back, publish the prefix
         volatile unsigned long long* st = status + tile;
         unsigned long long excl = 0;
@@ -379,19 +357,12 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
     const unsigned long long tile_base = s_base;
     // ---- phase B: JunctionSystem::addJunctions (junction_system.cc:140-210, recursion unrolled) for the spliced records ----
     uint32_t e = 0;
-    const int n_iter = DENSE ? (int)((s_nspl + SE_THREADS - 1) / SE_THREADS) : SE_ITEMS;
-#pragma unroll (DENSE ? 1 : SE_ITEMS)
-    for (int r = 0; r < n_iter; r++) {
-        uint32_t nN; int64_t i; unsigned long long slot0; int32_t rend_r; bool zeron_r;
-        if (DENSE) {
-            const uint32_t q = (uint32_t)r * SE_THREADS + threadIdx.x;
-            if (q >= s_nspl) continue;
-            const uint32_t cz = s_cntz[q];
-            nN = cz & 0x7fffffffu; zeron_r = (cz >> 31) != 0u; i = base + s_ids[q]; slot0 = tile_base + s_off[q]; rend_r = s_rend[q];
-        } else {
-            nN = cnt[r]; if (nN == 0) continue;
-            i = base + r * SE_THREADS + threadIdx.x; slot0 = tile_base + off[r]; rend_r = rend[r]; zeron_r = zeron[r];
-        }
+#pragma unroll
+    for (int r = 0; r < SE_ITEMS; r++) {
+        const uint32_t nN = cnt[r];
+        if (nN == 0) continue;
+        const int64_t i = base + r * SE_THREADS + threadIdx.x;
+        const unsigned long long slot0 = tile_base + off[r];
         if (slot0 + nN > (unsigned long long)pair_cap) { e |= ERR_KEY_OVERFLOW; continue; }
         uint32_t slot = (uint32_t)slot0;
         // every column of the record first: independent loads, one round trip instead of one per use
@@ -446,7 +417,7 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
                 // before the intron start / beyond its end + 1.  Ends are non-decreasing along the read, so with positive-length
                 // N ops and no clamping the counts follow from the op's rank; degenerate CIGARs take the literal loop.
                 uint32_t up, down;
-                if (zeron_r || clamped || start != p) {
+                if (zeron[r] || clamped || start != p) {
                     up = 0; down = 0; int32_t pp = pos;
                     for (int32_t k = 0; k < n; k++) {
                         const uint32_t w3 = __ldg(cg + k), o3 = cig_op(w3);
@@ -457,7 +428,7 @@ __global__ void __launch_bounds__(SE_THREADS, 5) k_scan_emit(Reads R, const int3
                 keys[slot] = ((tbase + (uint64_t)(uint32_t)start) << len_bits) | sz;
                 PairRec* const o = pr + slot;
                 o->a = PairA{(uint32_t)i, lStart, rendj, pos};
-                o->b = PairB{rend_r, bits, (up << 16) | (down & 0xffffu), start};
+                o->b = PairB{rend[r], bits, (up << 16) | (down & 0xffffu), start};
                 o->c = PairC{so * 4 + (uint64_t)ds, cig0 + (uint32_t)c, qpos};
                 o->d = PairD{(int32_t)qs, lq, (uint32_t)c | ((uint32_t)(n - 1 - c) << 16), 0u};
                 slot++;
@@ -481,14 +452,11 @@ void launch_scan_emit(const Reads& R, const int32_t* tlen, int32_t n_targets, co
     const uint32_t nt = se_num_tiles(R.n);
     cudaMemsetAsync(status, 0, (size_t)nt * sizeof(unsigned long long), st);
     cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
-    static const bool dense = [] { const char* e = getenv("PJ_SE_DENSE"); return e ? atoi(e) != 0 : true; }();
-#define PJ_SE(IT, DN) k_scan_emit<IT, DN><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err)
     switch (se_items()) {
-    case 1: if (dense) PJ_SE(1, true); else PJ_SE(1, false); break;
-    case 4: if (dense) PJ_SE(4, true); else PJ_SE(4, false); break;
-    default: if (dense) PJ_SE(2, true); else PJ_SE(2, false); break;
+    case 1: k_scan_emit<1><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err); break;
+    case 4: k_scan_emit<4><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err); break;
+    default: k_scan_emit<2><<<nt, SE_THREADS, 0, st>>>(R, tlen, n_targets, toff, max_nlen, orientation, T, keys, pr, status, ticket, total_pairs, pair_cap, err); break;
     }
-#undef PJ_SE
 }
 
 // ================================================================================================
