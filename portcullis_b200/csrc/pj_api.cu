@@ -49,7 +49,10 @@ void free_slot(StagingSlot& s) {
 // slots hold what a lean batch ships (no tid / cigar_off / seq_off, n_cigar and seq2 + exceptions instead).
 int alloc_slot(pj_ctx* c, StagingSlot& s, bool lean, int64_t cr, int64_t cc, int64_t cs, int64_t cx) {
     if (s.lean == lean && cr <= s.cap_rec && cc <= s.cap_cig && cs <= s.cap_seq && cx <= s.cap_seqx && s.block) return PJ_OK;
-    if (s.lean == lean) { cr = std::max(cr + cr / 8, s.cap_rec); cc = std::max(cc + cc / 8, s.cap_cig); cs = std::max(cs + cs / 8, s.cap_seq); cx = std::max(cx + cx / 8, s.cap_seqx); }
+    // Growing a slot is a cudaMallocHost (tens of ms, on the submitting thread): start with room for a typical 4 MB decode task and grow
+    // by half.  (A full-size c3 run re-allocated its four slots 24 times = 0.7 s before this.)
+    if (s.lean == lean) { cr = std::max(cr + cr / 2, s.cap_rec); cc = std::max(cc + cc / 2, s.cap_cig); cs = std::max(cs + cs / 2, s.cap_seq); cx = std::max(cx + cx / 2, s.cap_seqx); }
+    cr = std::max<int64_t>(cr, 192 << 10); cc = std::max<int64_t>(cc, 1 << 20); cs = std::max<int64_t>(cs, lean ? (8 << 20) : (16 << 20));
     free_slot(s);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t r = (size_t)cr;
