@@ -45,7 +45,7 @@ WORKLOADS = {
     "c5": "c5: long-read-style alignments (1-10 kb, up to 20 introns per read, indels near splice sites; 100 Mb genome)",
 }
 # fraction of the workload the CPU reference is timed on (about 10-30 s of CPU work per pass)
-CPU_SAMPLE = {"c2": 1.0, "c3": 0.05, "c4": 0.25, "c5": 0.1}
+CPU_SAMPLE = {"c2": 1.0, "c3": 0.05, "c4": 0.1, "c5": 0.05}
 
 
 def host_cores():
@@ -388,7 +388,14 @@ def e2e_bam_leg(args, prep, rank, world, local, cores, barrier, np, jb):
             barrier()
             if rank == 0:
                 from portcullis_b200 import _lib as L
-                allrows = np.concatenate([np.fromfile(os.path.join(shm, "rows_%d.bin" % r), dtype=L.JUNCTION_DTYPE) for r in range(world)])
+                sizes = [os.path.getsize(os.path.join(shm, "rows_%d.bin" % r)) // L.JUNCTION_DTYPE.itemsize for r in range(world)]
+                allrows = np.empty(sum(sizes), dtype=L.JUNCTION_DTYPE)            # parts land in place, in part order: one copy
+                at = 0
+                for r, k in enumerate(sizes):
+                    if k:
+                        with open(os.path.join(shm, "rows_%d.bin" % r), "rb") as fh:
+                            fh.readinto(allrows[at:at + k].view(np.uint8).reshape(-1))
+                    at += k
                 allstats = jb.merge_target_stats([np.fromfile(os.path.join(shm, "stats_%d.bin" % r), dtype=jb.TARGET_STATS_DTYPE) for r in range(world)])
                 _, frep = b.finish(allrows, allstats)
                 n_spliced = frep["n_spliced"]

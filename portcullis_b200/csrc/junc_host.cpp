@@ -140,6 +140,11 @@ public:
     void i(int64_t v) { if (v < 0) { c('-'); u((uint64_t)(-(v + 1)) + 1); } else u((uint64_t)v); }
     void g(double v, int prec = 6) { char t[48]; int k = snprintf(t, sizeof t, "%.*g", prec, v); s(t, (size_t)k); }
     void f3(double v) { char t[48]; int k = snprintf(t, sizeof t, "%.3f", v); s(t, (size_t)k); }
+    void raw(const std::string& v) {                          // a finished piece: written directly (in-memory writers append)
+        if (!f_) { buf_.append(v); return; }
+        flush();
+        if (!v.empty() && fwrite(v.data(), 1, v.size(), f_) != v.size()) throw std::runtime_error("short write to " + path_ + " (disk full?)");
+    }
     void flush() {
         if (f_ && !buf_.empty()) {
             const size_t n = fwrite(buf_.data(), 1, buf_.size(), f_);
@@ -154,13 +159,15 @@ private:
 // Formats rows [0, n) with `fmt(out, r)` on a few threads and appends the pieces to `o` in row order.
 template <typename F>
 void format_rows_parallel(Out& o, int64_t n, F fmt) {
-    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, (int64_t)std::thread::hardware_concurrency()), n / 1024));
+    // up to half the host threads per file (the four files are written concurrently), at least 1024 rows per thread
+    const int64_t hw = std::max<int64_t>(2, (int64_t)std::thread::hardware_concurrency());
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, std::max<int64_t>(4, hw / 2)), n / 1024));
     if (nt <= 1) { for (int64_t r = 0; r < n; r++) fmt(o, r); return; }
     std::vector<Out> parts((size_t)nt);
     std::vector<std::thread> th;
     for (int t = 0; t < nt; t++) th.emplace_back([&, t]() { const int64_t a = n * t / nt, b = n * (t + 1) / nt; for (int64_t r = a; r < b; r++) fmt(parts[(size_t)t], r); });
     for (auto& x : th) x.join();
-    for (auto& p : parts) o.s(p.str());
+    for (auto& p : parts) o.raw(p.str());            // straight to the file: no second copy through the writer's own buffer
 }
 
 inline char strand_char(uint8_t s) { return s == PJ_STRAND_POS ? '+' : s == PJ_STRAND_NEG ? '-' : '?'; }

@@ -916,7 +916,7 @@ struct OpMax { template <typename T> __device__ T operator()(T a, T b) const { r
 // ================================================================================================
 __global__ void __launch_bounds__(512) k_reduce1(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                   const PairRec* __restrict__ pr, int32_t ppcheck,
-                                                  JuncAcc A, uint32_t* __restrict__ eflag, uint32_t* __restrict__ inv) {
+                                                  JuncAcc A, uint32_t* __restrict__ eflag) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool ok = i < n;
@@ -925,7 +925,7 @@ __global__ void __launch_bounds__(512) k_reduce1(uint32_t n, const uint32_t* __r
     int32_t lmin = INT32_MAX, rmax = INT32_MIN; uint32_t anc = 0, up = 0, down = 0;
     PairA a = PairA{0u, 0, 0, 0}; PairB b = PairB{0, 0u, 0u, 0};
     uint32_t idx = 0;
-    if (ok) { j = jid[i]; idx = vals[i]; a = pr[idx].a; b = pr[idx].b; if (inv) inv[idx] = i; }   // inv: emit slot -> sorted position (k_match runs in emit order)
+    if (ok) { j = jid[i]; idx = vals[i]; a = pr[idx].a; b = pr[idx].b; }
     // (pos, read_end) of the previous pair in sorted order: from the neighbouring lane; only lane 0 has to gather it
     const uint32_t jprev = __shfl_up_sync(FULL, j, 1);
     int32_t ppos = __shfl_up_sync(FULL, a.pos, 1), pend = __shfl_up_sync(FULL, b.read_end, 1);
@@ -1041,8 +1041,8 @@ void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t
     if (n_junc) k_junc_init<<<(n_junc + 255) / 256, 256, 0, st>>>(n_junc, seg_start, keys, vals, pr, read_tid, len_bits, A);
 }
 void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, int32_t ppcheck,
-                    const JuncAcc& A, uint32_t* eflag, uint32_t* inv, cudaStream_t st) {
-    if (n) k_reduce1<<<(n + 511) / 512, 512, 0, st>>>(n, vals, jid, pr, ppcheck, A, eflag, inv);
+                    const JuncAcc& A, uint32_t* eflag, cudaStream_t st) {
+    if (n) k_reduce1<<<(n + 511) / 512, 512, 0, st>>>(n, vals, jid, pr, ppcheck, A, eflag);
 }
 
 // ================================================================================================
@@ -1317,20 +1317,16 @@ __device__ __forceinline__ PairStats walk_pair(MatchQueue& Q, const Genome& Gn, 
 }
 
 template <int G, int CT /* resident CTAs per SM the register budget is set for */>
-__global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* __restrict__ inv, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
+__global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ jid,
                                                 const PairRec* __restrict__ pr,
                                                 Reads R, Genome Gn, JuncAcc A, uint4* __restrict__ pm, uint32_t* __restrict__ errw) {
     __shared__ MatchQueue Q;
-    // Pairs are visited in EMIT order (= BAM order), not in junction order: the pair records are read coalesced, the SEQ / CIGAR streams
-    // are walked almost sequentially (neighbouring threads hold neighbouring reads, and the N ops of one long read sit in one warp and
-    // share its lines in L1), and the genome windows of neighbouring reads overlap.  Only the junction id (one 4-byte gather into an
-    // L2-resident array) and the result (one 16-byte scatter to the sorted position) are random.  In junction order every pair paid a
-    // 64-byte record gather plus random SEQ and CIGAR lines behind it, three dependent round trips deep.
-    const uint32_t th = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
+    // Pairs are visited in junction (sorted) order: the lanes of a warp then share the junction-wide window, so their walks have the same
+    // shape.  (Emit order — coalesced records, sequential SEQ — was measured: +13 % on c2, +38 % on c5; profiles/r2_history.md.)
+    const uint32_t i = (uint32_t)(((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / G);
     const int gl = threadIdx.x % G;
-    if (th >= n) return;                                             // whole groups leave together
-    const uint32_t idx = inv ? th : vals[th];                        // emit slot of this pair
-    const uint32_t i = inv ? inv[th] : th;                           // sorted position of this pair
+    if (i >= n) return;                                              // whole groups leave together
+    const uint32_t idx = vals[i];                                    // emit slot of this pair
     const PairA a = pr[idx].a; const PairB b = pr[idx].b; const PairC c = pr[idx].c; const PairD d = pr[idx].d;
     const uint32_t j = jid[i];
     // The walk below is a chain of dependent loads (CIGAR ops -> SEQ words / genome words).  The lines it will need are
@@ -1380,27 +1376,27 @@ __global__ void __launch_bounds__(256, CT) k_match(uint32_t n, const uint32_t* _
 }
 
 template <int G, int CT>
-static void launch_match_gc(uint32_t n, const uint32_t* inv, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
+static void launch_match_gc(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
                             const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     const uint64_t threads = (uint64_t)n * G;
-    k_match<G, CT><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, inv, vals, jid, pr, R, Gn, A, pm, err);
+    k_match<G, CT><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, vals, jid, pr, R, Gn, A, pm, err);
 }
 // ctas: register budget (resident CTAs per SM) of the G == 1 kernel, 0 = default; a tuning knob (PJ_MATCH_CTAS).
-void launch_match(uint32_t n, int group, int ctas, const uint32_t* inv, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
+void launch_match(uint32_t n, int group, int ctas, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& Gn,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st) {
     if (!n) return;
     switch (group) {
     case 1:
-        if (ctas == 4) launch_match_gc<1, 4>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
-        else if (ctas == 3) launch_match_gc<1, 3>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
-        else if (ctas == 6) launch_match_gc<1, 6>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
-        else launch_match_gc<1, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st);
+        if (ctas == 4) launch_match_gc<1, 4>(n, vals, jid, pr, R, Gn, A, pm, err, st);
+        else if (ctas == 3) launch_match_gc<1, 3>(n, vals, jid, pr, R, Gn, A, pm, err, st);
+        else if (ctas == 6) launch_match_gc<1, 6>(n, vals, jid, pr, R, Gn, A, pm, err, st);
+        else launch_match_gc<1, PJ_MATCH_CTAS>(n, vals, jid, pr, R, Gn, A, pm, err, st);
         break;
-    case 2: launch_match_gc<2, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 4: launch_match_gc<4, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 8: launch_match_gc<8, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    case 16: launch_match_gc<16, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
-    default: launch_match_gc<32, PJ_MATCH_CTAS>(n, inv, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 2: launch_match_gc<2, PJ_MATCH_CTAS>(n, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 4: launch_match_gc<4, PJ_MATCH_CTAS>(n, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 8: launch_match_gc<8, PJ_MATCH_CTAS>(n, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    case 16: launch_match_gc<16, PJ_MATCH_CTAS>(n, vals, jid, pr, R, Gn, A, pm, err, st); break;
+    default: launch_match_gc<32, PJ_MATCH_CTAS>(n, vals, jid, pr, R, Gn, A, pm, err, st); break;
     }
 }
 

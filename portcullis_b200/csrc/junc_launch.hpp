@@ -54,10 +54,10 @@ void launch_seg_ids(const uint64_t* keys, uint32_t n, const uint32_t* excl, uint
 void launch_junc_init(uint32_t n_junc, const uint32_t* seg_start, const uint64_t* keys, const uint32_t* vals, const PairRec* pr,
                       const int32_t* read_tid, int32_t len_bits, const JuncAcc& A, cudaStream_t st);
 void launch_reduce1(uint32_t n, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, int32_t ppcheck,
-                    const JuncAcc& A, uint32_t* eflag, uint32_t* inv, cudaStream_t st);
+                    const JuncAcc& A, uint32_t* eflag, cudaStream_t st);
 void launch_entropy_compact(uint32_t n, const uint32_t* eflag, const uint32_t* eoff, uint32_t* epos, cudaStream_t st);
 void launch_entropy_sum(uint32_t n_junc, const uint32_t* seg_start, const uint32_t* eoff, const uint32_t* epos, double* entropy, cudaStream_t st);
-void launch_match(uint32_t n, int group, int ctas, const uint32_t* inv /* null: junction order */, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& G,
+void launch_match(uint32_t n, int group, int ctas, const uint32_t* vals, const uint32_t* jid, const PairRec* pr, const Reads& R, const Genome& G,
                   const JuncAcc& A, uint4* pm, uint32_t* err, cudaStream_t st);
 void launch_reduce2(uint32_t n, const uint32_t* jid, const uint4* pm, const JuncAcc& A, cudaStream_t st);
 void launch_finalize(uint32_t n_junc, const uint32_t* seg_start, const JuncAcc& A, const Genome& G, const double* entropy,

@@ -130,6 +130,18 @@ int pjapi::finish_genome(pj_ctx* c) {
     return PJ_OK;
 }
 
+namespace {
+// Stream-ordered temporaries of one pj_shard_run: freed (cudaFreeAsync on the same stream) on EVERY exit path, also the early error
+// returns — the pool's release threshold is "never", so a leaked temporary would stay allocated for the life of the process.
+struct StreamTemps {
+    cudaStream_t st; std::vector<void*> v;
+    explicit StreamTemps(cudaStream_t s) : st(s) {}
+    template <typename T> cudaError_t alloc(T** p, size_t bytes) { void* q = nullptr; const cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 1, st); if (e == cudaSuccess) { v.push_back(q); *p = (T*)q; } return e; }
+    void release(void* p) { for (size_t k = 0; k < v.size(); k++) if (v[k] == p) { cudaFreeAsync(p, st); v.erase(v.begin() + (long)k); return; } }
+    ~StreamTemps() { for (void* p : v) cudaFreeAsync(p, st); }
+};
+} // namespace
+
 extern "C" {
 
 static_assert(sizeof(pj_junction) == 256, "pj_junction layout changed: update the bindings");
@@ -501,6 +513,7 @@ int pj_shard_run(pj_ctx* c) {
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     int rc = finish_genome(c); if (rc) return rc;
     cudaStream_t st = c->compute_stream;
+    StreamTemps tmp(st);
     CU(c, cudaMemsetAsync(c->seq2.p + c->n_seq, 0, 16, c->copy_stream));  // tail slack of the SEQ stream: read in 8-byte words, masked out
     CU(c, cudaEventRecord(c->copies_done, c->copy_stream));
     CU(c, cudaStreamWaitEvent(st, c->copies_done, 0));
@@ -526,11 +539,11 @@ int pj_shard_run(pj_ctx* c) {
     auto alloc_pairs = [&](uint32_t cap) -> int {
         const size_t n = std::max<size_t>(cap, 1);
         const uint32_t nb = rs_num_blocks((uint32_t)n);
-        CU(c, cudaMallocAsync(&keys_a, n * 8, st)); CU(c, cudaMallocAsync(&keys_b, n * 8, st));
-        CU(c, cudaMallocAsync(&vals_a, n * 4, st)); CU(c, cudaMallocAsync(&vals_b, n * 4, st));
-        CU(c, cudaMallocAsync(&counts, (size_t)256 * nb * 4, st));
-        CU(c, cudaMallocAsync(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, n)) * 4, st));
-        CU(c, cudaMallocAsync(&pr, n * sizeof(PairRec), st));
+        CU(c, tmp.alloc(&keys_a, n * 8)); CU(c, tmp.alloc(&keys_b, n * 8));
+        CU(c, tmp.alloc(&vals_a, n * 4)); CU(c, tmp.alloc(&vals_b, n * 4));
+        CU(c, tmp.alloc(&counts, (size_t)256 * nb * 4));
+        CU(c, tmp.alloc(&scan_tmp2, scan_tmp_elems(std::max<uint64_t>((uint64_t)256 * nb, n)) * 4));
+        CU(c, tmp.alloc(&pr, n * sizeof(PairRec)));
         return PJ_OK;
     };
     {
@@ -544,7 +557,7 @@ int pj_shard_run(pj_ctx* c) {
         len_bits = std::max(1, bit_length(maxN)); key_bits = len_bits + gbits;
         if (key_bits > 64) return fail(c, PJ_EINVAL, "pj_shard_run: junction key needs %d bits; split the shard into fewer targets", key_bits);
         if ((rc = alloc_pairs((uint32_t)acc[1]))) return rc;
-        CU(c, cudaMallocAsync(&se_status, (size_t)std::max<uint32_t>(se_num_tiles(R), 1) * sizeof(unsigned long long), st));
+        CU(c, tmp.alloc(&se_status, (size_t)std::max<uint32_t>(se_num_tiles(R), 1) * sizeof(unsigned long long)));
         launch_scan_emit(Rd, c->d_tlen, T, c->d_toff, reinterpret_cast<const uint32_t*>(c->d_shard_acc), c->orientation, TA, keys_a, pr,
                          se_status, c->d_scalars + 6, d_P, (uint32_t)acc[1], d_err, st); c->n_launches++;
         mark(c, "scan_emit");
@@ -560,9 +573,9 @@ int pj_shard_run(pj_ctx* c) {
         int which;
         if (P < (1u << 30) && !c->legacy_sort) {
             uint32_t* os_scratch = nullptr;
-            CU(c, cudaMallocAsync(&os_scratch, os_scratch_words(P, key_bits) * sizeof(uint32_t), st));
+            CU(c, tmp.alloc(&os_scratch, os_scratch_words(P, key_bits) * sizeof(uint32_t)));
             which = launch_onesweep_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, os_scratch, c->n_sm, st, &c->n_launches);
-            CU(c, cudaFreeAsync(os_scratch, st));
+            tmp.release(os_scratch);
         } else {
             which = launch_radix_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, counts, scan_tmp2, d_tmp_total, st, &c->n_launches);
         }
@@ -570,10 +583,10 @@ int pj_shard_run(pj_ctx* c) {
         uint32_t* spare_u32 = which ? vals_a : vals_b;        // free again: reused for the head flags / entropy flags
         mark(c, "radix_sort");
         uint32_t *jid = nullptr, *seg_start = nullptr; unsigned long long* fs_scratch = nullptr;
-        CU(c, cudaMallocAsync(&jid, (size_t)P * 4, st));
-        CU(c, cudaMallocAsync(&fs_scratch, ((size_t)fs_num_tiles(P) + 1) * 8, st));
+        CU(c, tmp.alloc(&jid, (size_t)P * 4));
+        CU(c, tmp.alloc(&fs_scratch, ((size_t)fs_num_tiles(P) + 1) * 8));
         if (!c->legacy_sort) {
-            CU(c, cudaMallocAsync(&seg_start, ((size_t)P + 1) * 4, st));        // J <= P is only known after the pass
+            CU(c, tmp.alloc(&seg_start, ((size_t)P + 1) * 4));        // J <= P is only known after the pass
             launch_segment(keys, P, jid, seg_start, d_J, fs_scratch, st); c->n_launches++;
             CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(c, cudaStreamSynchronize(st));
@@ -584,25 +597,23 @@ int pj_shard_run(pj_ctx* c) {
             CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CU(c, cudaStreamSynchronize(st));
             J = c->h_scalars[3];
-            CU(c, cudaMallocAsync(&seg_start, ((size_t)J + 1) * 4, st));
+            CU(c, tmp.alloc(&seg_start, ((size_t)J + 1) * 4));
             launch_seg_ids(keys, P, spare_u32, jid, seg_start, J, st); c->n_launches++;
         }
         mark(c, "segments");
         // ---- per-junction accumulators: one zero-filled block of uint32 columns ----
         const size_t NCOL = 24; uint32_t* acc = nullptr; uint32_t* jadhist = nullptr; double* entropy = nullptr;
-        CU(c, cudaMallocAsync(&acc, NCOL * (size_t)J * 4, st)); CU(c, cudaMemsetAsync(acc, 0, NCOL * (size_t)J * 4, st));
-        CU(c, cudaMallocAsync(&jadhist, (size_t)J * (PJ_NB_JAD + 1) * 4, st)); CU(c, cudaMemsetAsync(jadhist, 0, (size_t)J * (PJ_NB_JAD + 1) * 4, st));
-        CU(c, cudaMallocAsync(&entropy, (size_t)J * 8, st));
+        CU(c, tmp.alloc(&acc, NCOL * (size_t)J * 4)); CU(c, cudaMemsetAsync(acc, 0, NCOL * (size_t)J * 4, st));
+        CU(c, tmp.alloc(&jadhist, (size_t)J * (PJ_NB_JAD + 1) * 4)); CU(c, cudaMemsetAsync(jadhist, 0, (size_t)J * (PJ_NB_JAD + 1) * 4, st));
+        CU(c, tmp.alloc(&entropy, (size_t)J * 8));
         auto col = [&](size_t k) { return acc + k * (size_t)J; };
         JuncAcc A{(int32_t*)col(0), (int32_t*)col(1), (int32_t*)col(2), (int32_t*)col(3), (int32_t*)col(4),
                   col(5), col(6), col(7), col(8), col(9), col(10), col(11), col(12), col(13), col(14), col(15), col(16), col(17), col(18), col(19),
                   col(20), col(21), col(22), col(23), jadhist};
         CU(c, cudaMemsetAsync(A.firstmm, 0xff, (size_t)J * 4, st));
         launch_junc_init(J, seg_start, keys, vals, pr, c->tid.p, len_bits, A, st); c->n_launches++;
-        static const bool emit_order = [] { const char* e = getenv("PJ_MATCH_ORDER"); return e && atoi(e) == 1; }();   // 1: k_match walks pairs in emit (BAM) order
-        uint32_t* inv = nullptr; if (emit_order) CU(c, cudaMallocAsync(&inv, (size_t)P * 4, st));   // emit slot -> sorted position (written by k_reduce1, read by k_match)
         launch_reduce1(P, vals, jid, pr, (c->orientation == PJ_ORIENT_FR || c->orientation == PJ_ORIENT_RF || c->orientation == PJ_ORIENT_FF) ? 1 : 0,
-                       A, spare_u32, inv, st); c->n_launches++;
+                       A, spare_u32, st); c->n_launches++;
         mark(c, "reduce1");
         uint64_t* free_keys = which ? keys_a : keys_b;          // the non-result key buffer: 8 bytes per pair, reused below
         uint32_t* eoff = reinterpret_cast<uint32_t*>(free_keys);
@@ -615,7 +626,7 @@ int pj_shard_run(pj_ctx* c) {
         launch_entropy_sum(J, seg_start, eoff, epos, entropy, st); c->n_launches++;
         mark(c, "entropy");
         Genome G{c->d_g2, c->d_gx, c->d_gsum, c->d_goff, c->d_glen, c->d_exc_pos, c->d_exc_byte, c->n_exc, c->n_exc_x, c->any_gx};
-        uint4* pm = nullptr; CU(c, cudaMallocAsync(&pm, (size_t)P * sizeof(uint4), st));
+        uint4* pm = nullptr; CU(c, tmp.alloc(&pm, (size_t)P * sizeof(uint4)));
         {   // lanes per (read, junction) pair: one 16-base word per lane and step; long reads get wider groups
             int group = c->match_group;
             if (group <= 0) {
@@ -625,7 +636,7 @@ int pj_shard_run(pj_ctx* c) {
                 group = bases_per_pair <= 4000 ? 1 : 8;
             }
             static const int match_ctas = [] { const char* e = getenv("PJ_MATCH_CTAS"); return e ? atoi(e) : 0; }();
-            launch_match(P, group, match_ctas, inv, vals, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
+            launch_match(P, group, match_ctas, vals, jid, pr, Rd, G, A, pm, d_err, st); c->n_launches++;
         }
         mark(c, "match");
         launch_reduce2(P, jid, pm, A, st); c->n_launches++;
@@ -634,11 +645,7 @@ int pj_shard_run(pj_ctx* c) {
         launch_finalize(J, seg_start, A, G, entropy, c->d_rows, d_err, st); c->n_launches++;
         mark(c, "finalize");
         if (c->extra && (rc = extra_keep_pairs(c, P, vals, jid, pr, st))) return rc;
-        CU(c, cudaFreeAsync(jid, st)); CU(c, cudaFreeAsync(seg_start, st)); CU(c, cudaFreeAsync(fs_scratch, st)); CU(c, cudaFreeAsync(acc, st)); CU(c, cudaFreeAsync(jadhist, st));
-        CU(c, cudaFreeAsync(entropy, st)); CU(c, cudaFreeAsync(pm, st)); if (inv) CU(c, cudaFreeAsync(inv, st));
     }
-    for (void* p : {(void*)keys_a, (void*)keys_b, (void*)vals_a, (void*)vals_b, (void*)counts, (void*)scan_tmp2, (void*)pr, (void*)se_status})
-        if (p) CU(c, cudaFreeAsync(p, st));
     if (c->extra && (rc = extra_classify(c, st))) return rc;
     mark(c, "end");
     CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
