@@ -55,6 +55,42 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa(gpu_index):
+    """One process per GPU: keep this rank's threads and memory (decoded columns, pinned staging) on the NUMA node its GPU hangs off,
+    like `numactl --cpunodebind --preferred` would (round 1's 8-GPU e2e was limited by cross-socket host traffic).  Reads the
+    CPU / NUMA affinity columns of `nvidia-smi topo -m`; does nothing when the box does not expose them."""
+    info = {"node": None, "cpus": None}
+    try:
+        import ctypes
+        import re
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+        out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+        lines = [l for l in out.split("\n") if l.strip()]
+        hdr = next(l for l in lines if "CPU Affinity" in l).split("\t")
+        row = next(l for l in lines if l.startswith("GPU%d\t" % gpu_index) or l.startswith("GPU%d " % gpu_index)).split("\t")
+        ci, ni = hdr.index("CPU Affinity"), hdr.index("NUMA Affinity")
+        cpus = set()
+        for part in row[ci].strip().split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part.strip().isdigit():
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["cpus"] = "%d of %d allowed" % (len(use), len(allowed))
+        node = row[ni].strip().split(",")[0].split("-")[0]
+        if node.isdigit():
+            mask = ctypes.c_ulong(1 << int(node))
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 64)      # set_mempolicy(MPOL_PREFERRED, {node})
+            if rc == 0:
+                info["node"] = int(node)
+    except Exception:
+        pass
+    return info
+
+
 def config_of(args):
     """Identical in both arms (the driver compares them)."""
     return {"workload": "%s (pjsynth preset %s scale %g)" % (WORKLOADS[args.preset], args.preset, args.scale),
@@ -95,7 +131,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(float(os.environ.get("PJ_BENCH_SMI_INTERVAL", "0.2")))
+            self.stop.wait(float(os.environ.get("PJ_BENCH_SMI_INTERVAL", "0.25")))
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
@@ -168,6 +204,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     all_cores = host_cores()
     cores = max(1, all_cores // world)
+    numa = bind_to_gpu_numa(local) if world > 1 else {"node": None, "cpus": None}
+    if numa.get("cpus"):
+        cores = max(1, min(cores, host_cores()))
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,10 +269,15 @@ def run_ours(args):
     del rows
 
     # ---------------- resident arm ----------------
-    for _ in range(args.warmup):
-        g.run()
+    # The clock sampler starts BEFORE the warm-up: the first nvidia-smi call on a fresh box initialises NVML and can hold the driver for
+    # a second or more (seen once as a 1.7 s stall inside one timed step); the later calls are cheap.
     sampler = ClockSampler(local)
     sampler.start()
+    for _ in range(args.warmup):
+        g.run()
+    t_wait = time.time()
+    while not sampler.rows and sampler.is_alive() and time.time() - t_wait < 30:      # the first sample has come back
+        time.sleep(0.05)
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, stage_acc = 0.0, 0, {}
@@ -327,7 +371,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": wall_m / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
             "workload_stats": {"records": int(tot_rec), "spliced": int(tot_spliced), "read_junction_pairs": int(tot_pairs), "junctions": int(tot_junc),
-                               "records_rank0": n_rec, "gap_cuts_in_plan": int(cuts), "host_cores": all_cores, "decode_threads_per_rank": cores},
+                               "records_rank0": n_rec, "gap_cuts_in_plan": int(cuts), "host_cores": all_cores, "decode_threads_per_rank": cores, "numa_rank0": numa},
             "device_ms_per_step": dev_ms_m / args.steps,
             "device_ms_per_step_by_rank": [round(float(x), 4) for x in per_rank.tolist()],
             "all_alignments_per_sec": tot_rec * args.steps / wall_m,
