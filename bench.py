@@ -125,10 +125,11 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                cmd = ["nvidia-smi"] + (["-i", str(self.gpu)] if self.gpu is not None else []) + ["--query-gpu=" + self.Q, "--format=csv,noheader,nounits"]
+                out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                for line in out.split("\n"):                      # one row per GPU (all GPUs of the box when gpu is None)
+                    if line.strip():
+                        self.rows.append([c.strip() for c in line.split(",")])
             except Exception:
                 pass
             self.stop.wait(float(os.environ.get("PJ_BENCH_SMI_INTERVAL", "0.25")))
@@ -271,12 +272,15 @@ def run_ours(args):
     # ---------------- resident arm ----------------
     # The clock sampler starts BEFORE the warm-up: the first nvidia-smi call on a fresh box initialises NVML and can hold the driver for
     # a second or more (seen once as a 1.7 s stall inside one timed step); the later calls are cheap.
-    sampler = ClockSampler(local)
-    sampler.start()
+    # Under torchrun ONE sampler (rank 0) watches every GPU of the box: eight ranks polling nvidia-smi four times a second each
+    # visibly stalled the 5 ms steps of the 8-GPU run (per-rank device time 5 -> 7-10 ms).
+    sampler = ClockSampler(local if world == 1 else None)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         g.run()
     t_wait = time.time()
-    while not sampler.rows and sampler.is_alive() and time.time() - t_wait < 30:      # the first sample has come back
+    while rank == 0 and not sampler.rows and sampler.is_alive() and time.time() - t_wait < 30:      # the first sample has come back
         time.sleep(0.05)
     barrier()
     t0 = time.perf_counter()
@@ -309,7 +313,8 @@ def run_ours(args):
         wall_e2e = time.perf_counter() - t1
         assert len(rows2) == nj
     sampler.stop.set()
-    sampler.join()
+    if rank == 0:
+        sampler.join()
 
     # per-rank workload numbers for the roofline (before the columns are released)
     n_cig, n_cig_spliced, seq_bytes = n_cig_all, 0, 0                # seq_bytes: the 4-bit SEQ bytes of SURVEY 8(d), (l + 1) / 2 per spliced record
