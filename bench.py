@@ -25,7 +25,6 @@ import os
 import shutil
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -111,28 +110,50 @@ def make_workload(preset, scale, seed, threads):
         return d, json.load(f)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  ONE long-running
+    `nvidia-smi -lms` process writes a row per GPU every 250 ms; nothing is forked from this process while steps are being timed
+    (a Python thread that spawned nvidia-smi per sample held the GIL through each spawn and showed up as 30-60 ms stalls of the
+    rank that ran it)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu = gpu_index
+        self.gpu = gpu_index                            # None: every GPU of the box
         self.rows = []
-        self.stop = threading.Event()
+        self.proc = None
+        self.path = os.path.join(WORKDIR, "clocks_%d.csv" % os.getpid())
 
-    def run(self):
-        while not self.stop.is_set():
+    def start(self):
+        try:
+            os.makedirs(WORKDIR, exist_ok=True)
+            self.out = open(self.path, "w")
+            cmd = ["nvidia-smi"] + (["-i", str(self.gpu)] if self.gpu is not None else []) + \
+                  ["--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", os.environ.get("PJ_BENCH_SMI_MS", "250")]
+            self.proc = subprocess.Popen(cmd, stdout=self.out, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def n_rows(self):
+        try:
+            return sum(1 for _ in open(self.path))
+        except Exception:
+            return 0
+
+    def stop_and_collect(self):
+        if self.proc is not None:
+            self.proc.terminate()                       # the exact PID we started
             try:
-                cmd = ["nvidia-smi"] + (["-i", str(self.gpu)] if self.gpu is not None else []) + ["--query-gpu=" + self.Q, "--format=csv,noheader,nounits"]
-                out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                for line in out.split("\n"):                      # one row per GPU (all GPUs of the box when gpu is None)
-                    if line.strip():
-                        self.rows.append([c.strip() for c in line.split(",")])
+                self.proc.wait(timeout=10)
             except Exception:
-                pass
-            self.stop.wait(float(os.environ.get("PJ_BENCH_SMI_INTERVAL", "0.25")))
+                self.proc.kill()
+            self.out.close()
+        try:
+            with open(self.path) as f:
+                self.rows = [[c.strip() for c in line.split(",")] for line in f if line.strip()]
+            os.remove(self.path)
+        except Exception:
+            pass
 
     def summary(self):
         sm = sorted(int(float(r[1])) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
@@ -280,7 +301,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         g.run()
     t_wait = time.time()
-    while rank == 0 and not sampler.rows and sampler.is_alive() and time.time() - t_wait < 30:      # the first sample has come back
+    while rank == 0 and sampler.proc is not None and sampler.n_rows() == 0 and time.time() - t_wait < 30:      # the first sample has come back
         time.sleep(0.05)
     barrier()
     t0 = time.perf_counter()
@@ -312,9 +333,8 @@ def run_ours(args):
         barrier()
         wall_e2e = time.perf_counter() - t1
         assert len(rows2) == nj
-    sampler.stop.set()
     if rank == 0:
-        sampler.join()
+        sampler.stop_and_collect()
 
     # per-rank workload numbers for the roofline (before the columns are released)
     n_cig, n_cig_spliced, seq_bytes = n_cig_all, 0, 0                # seq_bytes: the 4-bit SEQ bytes of SURVEY 8(d), (l + 1) / 2 per spliced record
