@@ -291,30 +291,35 @@ def run_ours(args):
     del rows
 
     # ---------------- resident arm ----------------
-    # The clock sampler starts BEFORE the warm-up: the first nvidia-smi call on a fresh box initialises NVML and can hold the driver for
-    # a second or more (seen once as a 1.7 s stall inside one timed step); the later calls are cheap.
-    # Under torchrun ONE sampler (rank 0) watches every GPU of the box: eight ranks polling nvidia-smi four times a second each
-    # visibly stalled the 5 ms steps of the 8-GPU run (per-rank device time 5 -> 7-10 ms).
+    # The clock sampler (one `nvidia-smi -lms` process, the recipe's line) starts BEFORE the warm-up, so that its NVML start-up is over
+    # when the timed region begins; steady sampling does not move the step time (tools/smi_probe.py: 1.818 ms with and without).
+    # The warm-up runs for at least W steps AND at least --warmup-seconds of continuous load: for the first ~100 ms of work after the
+    # host-side set-up (seconds of decode with an idle GPU) single stages stall by 2-30 ms whatever else is running (per-step trace in
+    # profiles/r2_history.md), which 5 steps of a 2-7 ms pipeline do not cover.  The count actually run is reported as `warmup_steps_run`.
     sampler = ClockSampler(local if world == 1 else None)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
+    warm_run, t_warm = 0, time.perf_counter()
+    while warm_run < args.warmup or time.perf_counter() - t_warm < args.warmup_seconds:
         g.run()
-    t_wait = time.time()
-    while rank == 0 and sampler.proc is not None and sampler.n_rows() == 0 and time.time() - t_wait < 30:      # the first sample has come back
-        time.sleep(0.05)
+        warm_run += 1
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, stage_acc = 0.0, 0, {}
+    trace = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         g.run()
         ms, nl, stages = g.timing()
+        trace.append((round((time.perf_counter() - ts) * 1e3, 3), round(ms, 3), max(stages, key=lambda kv: kv[1])[0]))
         dev_ms += ms
         launches += nl
         for name, v in stages:
             stage_acc[name] = stage_acc.get(name, 0.0) + v
     barrier()
     wall = time.perf_counter() - t0
+    if os.environ.get("PJ_BENCH_TRACE"):
+        print("rank %d steps (wall ms, device ms, longest stage): %s" % (rank, trace), file=sys.stderr)
     # ---------------- e2e arm (host buffers through the C ABI) ----------------
     wall_e2e = 0.0
     e2e_steps = args.steps if not args.resident_only else 0
@@ -393,7 +398,7 @@ def run_ours(args):
         cfg = config_of(args)
         line = {
             "metric": METRIC, "value": tot_spliced * args.steps / wall_m, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": wall_m / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "warmup_steps_run": warm_run, "ms_per_step": wall_m / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
             "workload_stats": {"records": int(tot_rec), "spliced": int(tot_spliced), "read_junction_pairs": int(tot_pairs), "junctions": int(tot_junc),
                                "records_rank0": n_rec, "gap_cuts_in_plan": int(cuts), "host_cores": all_cores, "decode_threads_per_rank": cores, "numa_rank0": numa},
@@ -565,6 +570,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup-seconds", type=float, default=1.0, help="the warm-up also lasts at least this long (continuous load before the timed region)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--preset", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0)

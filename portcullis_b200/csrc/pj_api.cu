@@ -133,12 +133,13 @@ int pjapi::finish_genome(pj_ctx* c) {
 namespace {
 // Stream-ordered temporaries of one pj_shard_run: freed (cudaFreeAsync on the same stream) on EVERY exit path, also the early error
 // returns — the pool's release threshold is "never", so a leaked temporary would stay allocated for the life of the process.
+// the temporaries of one pj_shard_run: handed out by the context's arena, all of them given back when the run ends (also on an error return)
 struct StreamTemps {
-    cudaStream_t st; std::vector<void*> v;
-    explicit StreamTemps(cudaStream_t s) : st(s) {}
-    template <typename T> cudaError_t alloc(T** p, size_t bytes) { void* q = nullptr; const cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 1, st); if (e == cudaSuccess) { v.push_back(q); *p = (T*)q; } return e; }
-    void release(void* p) { for (size_t k = 0; k < v.size(); k++) if (v[k] == p) { cudaFreeAsync(p, st); v.erase(v.begin() + (long)k); return; } }
-    ~StreamTemps() { for (void* p : v) cudaFreeAsync(p, st); }
+    pjapi::TempArena& A; size_t high = 0;
+    explicit StreamTemps(pjapi::TempArena& a) : A(a) { A.reset(); }
+    template <typename T> cudaError_t alloc(T** p, size_t bytes) { void* q = nullptr; const cudaError_t e = A.alloc(&q, bytes); if (e == cudaSuccess) *p = (T*)q; high = std::max(high, A.need); return e; }
+    void release(void* p, size_t bytes) { A.release(p, bytes); }
+    ~StreamTemps() { A.reset(); }
 };
 } // namespace
 
@@ -199,6 +200,7 @@ void pj_destroy(pj_ctx* c) {
     c->tid.free_(); c->pos.free_(); c->l_qseq.free_(); c->mtid.free_(); c->mpos.free_(); c->flag.free_(); c->mapq.free_(); c->xs.free_();
     c->seq2.free_(); c->cigar_off.free_(); c->cigar.free_(); c->seq_off.free_(); c->name_code.free_();
     c->seqx_pos.free_(); c->seqx_code.free_(); c->tmp_seq4.free_(); c->tmp_off4.free_(); c->tmp_xcount.free_(); c->tmp_xoff.free_(); c->tmp_scan.free_(); c->tmp_ncig.free_(); c->tmp_fs.free_();
+    c->arena.free_all();
     extra_reset(c);
     lap("arena");
     for (StagingSlot* sl : c->slots) { free_slot(*sl); if (sl->done) cudaEventDestroy(sl->done); delete sl; }
@@ -216,7 +218,7 @@ void pj_destroy(pj_ctx* c) {
     if (c->copies_done) cudaEventDestroy(c->copies_done);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
-    {   // Give the stream-ordered pool back (it was told to keep everything while the context lived).  Unmapping tens of GB takes
+    {   // Give the stream-ordered pool back (the `--extra` path allocates from it, and it was told to keep everything while the context lived).  Unmapping tens of GB takes
         // about a second, so it runs on its own thread, under the caller's finalize + writers; the next pj_create / pj_destroy (or
         // the end of the process) waits for it.
         const int dev = c->device;
@@ -336,20 +338,18 @@ int pj_shard_begin(pj_ctx* c, int64_t n_records_hint, int64_t n_cigar_hint, int6
     CU(c, cudaMemsetAsync(c->d_shard_acc, 0, 4 * sizeof(unsigned long long), st));
     { static const uint64_t lead = 16; CU(c, cudaMemcpyAsync(c->seq_off.p, &lead, sizeof(uint64_t), cudaMemcpyHostToDevice, st)); }
     CU(c, cudaMemsetAsync(c->seq2.p, 0, 16, st));                       // the lead pad is read (and masked out) by k_match: keep it defined
-    // Pre-grow the stream-ordered pool that pj_shard_run allocates its temporaries from (about 12 B per record and 80 B
-    // per read-junction pair): a cold pool costs hundreds of milliseconds for a multi-GB shard, and this way the growth
-    // overlaps the caller's decode instead of sitting in front of the first kernel.
+    // Size the arena pj_shard_run takes its temporaries from (about 12 B per record and 110 B per read-junction pair) on a helper
+    // thread: cudaMalloc of a multi-GB block takes tens of milliseconds, and this way it overlaps the caller's decode instead of
+    // sitting in front of the first kernel.  An estimate that turns out too small costs one extra chunk in the first run.
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     {
-        const size_t est = (size_t)std::max<int64_t>(n_records_hint, 0) * (12 + 80) + (64u << 20);
-        const int dev = c->device; cudaStream_t ps = c->genome_stream;
-        if (n_records_hint > (1 << 20)) c->prewarm_thread = std::thread([est, dev, ps]() {
+        const size_t est = (size_t)std::max<int64_t>(n_records_hint, 0) * (12 + 110) + (64u << 20);
+        const int dev = c->device;
+        if (n_records_hint > (1 << 20) && c->arena.capacity() < est) c->prewarm_thread = std::thread([c, est, dev]() {
             cudaSetDevice(dev);
             size_t free_b = 0, total_b = 0;
-            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || est > free_b / 2) return;
-            void* p = nullptr;
-            if (cudaMallocAsync(&p, est, ps) == cudaSuccess) { cudaFreeAsync(p, ps); cudaStreamSynchronize(ps); }
-            else cudaGetLastError();
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || est > (free_b + c->arena.capacity()) / 2) return;
+            c->arena.reserve(est);
         });
     }
     c->shard_open = true;
@@ -513,7 +513,8 @@ int pj_shard_run(pj_ctx* c) {
     if (c->prewarm_thread.joinable()) c->prewarm_thread.join();
     int rc = finish_genome(c); if (rc) return rc;
     cudaStream_t st = c->compute_stream;
-    StreamTemps tmp(st);
+    StreamTemps tmp(c->arena);
+    const auto t_run0 = std::chrono::steady_clock::now();
     CU(c, cudaMemsetAsync(c->seq2.p + c->n_seq, 0, 16, c->copy_stream));  // tail slack of the SEQ stream: read in 8-byte words, masked out
     CU(c, cudaEventRecord(c->copies_done, c->copy_stream));
     CU(c, cudaStreamWaitEvent(st, c->copies_done, 0));
@@ -573,9 +574,10 @@ int pj_shard_run(pj_ctx* c) {
         int which;
         if (P < (1u << 30) && !c->legacy_sort) {
             uint32_t* os_scratch = nullptr;
-            CU(c, tmp.alloc(&os_scratch, os_scratch_words(P, key_bits) * sizeof(uint32_t)));
+            const size_t os_bytes = os_scratch_words(P, key_bits) * sizeof(uint32_t);
+            CU(c, tmp.alloc(&os_scratch, os_bytes));
             which = launch_onesweep_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, os_scratch, c->n_sm, st, &c->n_launches);
-            tmp.release(os_scratch);
+            tmp.release(os_scratch, os_bytes);                         // stream order keeps the sort ahead of the next user of these bytes
         } else {
             which = launch_radix_sort(keys_a, vals_a, keys_b, vals_b, P, key_bits, counts, scan_tmp2, d_tmp_total, st, &c->n_launches);
         }
@@ -651,6 +653,7 @@ int pj_shard_run(pj_ctx* c) {
     CU(c, cudaMemcpyAsync(c->h_scalars, c->d_scalars, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
     CU(c, cudaGetLastError());
+    c->arena.reset(); c->arena.consolidate(tmp.high);      // everything that used the temporaries has completed
     // timings
     c->stage_ms.clear(); c->stage_names.clear();
     for (size_t k = 1; k < c->n_stage; k++) {
@@ -658,6 +661,16 @@ int pj_shard_run(pj_ctx* c) {
         c->stage_ms.push_back(ms); c->stage_names.push_back(c->stages[k].name);
     }
     cudaEventElapsedTime(&c->total_ms, c->stages[0].ev, c->stages[c->n_stage - 1].ev);
+    static const bool trace_host = getenv("PJ_TRACE_HOST") != nullptr;     // debugging aid: report runs that took 20 % longer than the best one
+    if (trace_host) {
+        static float best = 1e30f; best = std::min(best, c->total_ms);
+        if (c->total_ms > 1.2f * best) {
+            std::string m;
+            for (size_t k = 0; k < c->stage_ms.size(); k++) { char b[64]; snprintf(b, sizeof b, " %s=%.2f", c->stage_names[k], c->stage_ms[k]); m += b; }
+            fprintf(stderr, "[pj trace] slow run: host %.2f ms, device %.2f ms (best %.2f):%s\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count(), c->total_ms, best, m.c_str());
+        }
+    }
     const uint32_t err = c->h_scalars[0];
     if (err) {
         std::string m = "input rejected (the reference aborts or is undefined on it):";

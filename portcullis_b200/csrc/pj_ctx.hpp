@@ -35,6 +35,45 @@ struct StagingSlot {
 
 struct StageTime { const char* name; cudaEvent_t ev; };
 
+// The temporaries of one pj_shard_run (sort keys, pair records, per-junction accumulators ...) come out of this per-context arena: a
+// bump pointer over one cudaMalloc'ed block.  The stream-ordered allocator they used before (cudaMallocAsync on the default pool) took
+// 2-450 ms for single allocations during the first dozen runs of every context (profiles/r2_history.md, "allocator stalls").
+// A run that outgrows the block spills into extra chunks; consolidate() at the end of that run replaces them by one block of the total.
+struct TempArena {
+    struct Chunk { char* p; size_t cap, used; };
+    std::vector<Chunk> chunks; size_t need = 0;
+    static size_t align(size_t b) { return (b + 255) & ~(size_t)255; }
+    size_t capacity() const { size_t t = 0; for (const Chunk& k : chunks) t += k.cap; return t; }
+    cudaError_t alloc(void** out, size_t bytes) {
+        const size_t a = align(bytes ? bytes : 1); need += a;
+        for (Chunk& k : chunks) if (k.used + a <= k.cap) { *out = k.p + k.used; k.used += a; return cudaSuccess; }
+        Chunk k{nullptr, std::max(a, (size_t)64 << 20), a};
+        const cudaError_t e = cudaMalloc((void**)&k.p, k.cap);
+        if (e != cudaSuccess) return e;
+        chunks.push_back(k); *out = k.p;
+        return cudaSuccess;
+    }
+    void release(void* p, size_t bytes) {              // only the most recent allocation of a chunk can be handed back
+        const size_t a = align(bytes ? bytes : 1);
+        for (Chunk& k : chunks) if (k.used >= a && k.p + (k.used - a) == (char*)p) { k.used -= a; need -= a; return; }
+    }
+    void reset() { for (Chunk& k : chunks) k.used = 0; need = 0; }
+    void free_all() { for (Chunk& k : chunks) cudaFree(k.p); chunks.clear(); need = 0; }
+    // all work that used the arena has completed (the caller synchronised the stream)
+    void consolidate(size_t high_water) {
+        if (chunks.size() <= 1) return;
+        free_all();
+        Chunk k{nullptr, high_water + high_water / 16 + ((size_t)1 << 20), 0};
+        if (cudaMalloc((void**)&k.p, k.cap) == cudaSuccess) chunks.push_back(k); else cudaGetLastError();
+    }
+    void reserve(size_t bytes) {                       // nothing of the arena is in use
+        if (capacity() >= bytes && chunks.size() == 1) return;
+        free_all();
+        Chunk k{nullptr, bytes, 0};
+        if (cudaMalloc((void**)&k.p, k.cap) == cudaSuccess) chunks.push_back(k); else cudaGetLastError();
+    }
+};
+
 } // namespace pjapi
 
 struct pj_ctx {
@@ -62,7 +101,8 @@ struct pj_ctx {
     pjapi::DevBuf<uint8_t> tmp_seq4; pjapi::DevBuf<uint64_t> tmp_off4; pjapi::DevBuf<uint32_t> tmp_xcount, tmp_xoff, tmp_scan; pjapi::DevBuf<uint16_t> tmp_ncig;
     pjapi::DevBuf<unsigned long long> tmp_fs;
     std::vector<pjapi::StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
-    std::thread prewarm_thread;         // grows the stream-ordered memory pool while the caller is still decoding
+    pjapi::TempArena arena;             // temporaries of pj_shard_run
+    std::thread prewarm_thread;         // sizes the arena while the caller is still decoding
     double t_pinned_alloc_s = 0; size_t pinned_alloc_bytes = 0; int n_pinned_allocs = 0;   // PJ_TRACE: cost of growing the staging pool
     std::mutex staging_mu;              // pj_staging_acquire / pj_batch_submit may be called from several host threads
     cudaStream_t genome_stream = nullptr;
