@@ -5,10 +5,11 @@ mkdir -p gpurun_out
 TAG=${1:-r2t}
 timeout 1500 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_c3.json 2> gpurun_out/${TAG}_bench_c3.err; echo "bench c3 rc=$?"; tail -c 300 gpurun_out/${TAG}_bench_c3.err
 timeout 900 python bench.py --preset c5 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_c5.json 2> gpurun_out/${TAG}_bench_c5.err; echo "bench c5 rc=$?"
-timeout 600 python bench.py --preset c2 --steps 20 --warmup 5 --no-bam --no-cpu-baseline > gpurun_out/${TAG}_bench_c2.json 2> gpurun_out/${TAG}_bench_c2.err; echo "bench c2 rc=$?"
+timeout 600 python bench.py --preset c2 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_c2.json 2> gpurun_out/${TAG}_bench_c2.err; echo "bench c2 rc=$?"
+timeout 600 python bench.py --preset c4 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_c4.json 2> gpurun_out/${TAG}_bench_c4.err; echo "bench c4 rc=$?"
 python - <<PY
 import json
-for p in ("c3","c5","c2"):
+for p in ("c3","c5","c2","c4"):
     try:
         d=json.loads(open("gpurun_out/${TAG}_bench_%s.json"%p).read().strip().split("\n")[-1])
         r=d["roofline"]
