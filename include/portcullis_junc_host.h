@@ -130,6 +130,8 @@ int         pjh_plan_decode_lean(pjh_prep* p, int32_t n_parts, int32_t whole_tar
 /* Checks the built-in fast DEFLATE decoder (BGZF blocks) against zlib on n_cases synthetic streams; returns the number of
  * mismatches (0 = pass).  BGZF blocks the fast decoder rejects are decoded by zlib, so it can only be an accelerator. */
 int         pjh_inflate_selftest(int32_t n_cases);
+/* Self-test of the writers' number formatting (fast "%g" / integer paths) against printf; returns the number of differences. */
+int         pjh_format_selftest(int32_t n_cases);
 
 /* ---- `--separate` (JunctionBuilder::separateBams, src/junction_builder.cc:152-226) ----
  * Splits the prepared BAM into <output_prefix>.spliced.bam (any N op), .unspliced.bam (mapped, no N) and .unmapped.bam and

@@ -190,6 +190,7 @@ SYMBOLS = {
     "pjh_prep_want_names": (None, [_P, C.c_int32]),
     "pjh_prep_genome": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int64)]),
     "pjh_inflate_selftest": (C.c_int, [C.c_int32]),
+    "pjh_format_selftest": (C.c_int, [C.c_int32]),
     "pjh_plan_shards": (C.c_int, [_P, C.c_int32, _P]),
     "pjh_plan_describe": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, _P, C.POINTER(C.c_int32)]),
     "pjh_plan_decode_lean": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PjBatch),

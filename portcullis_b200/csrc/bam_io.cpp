@@ -2,6 +2,9 @@
 #include "bam_io.hpp"
 #include <zlib.h>
 #include "inflate_fast.hpp"
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "crc32_fast.hpp"
 #include <cstring>
 #include <climits>
@@ -338,11 +341,76 @@ static uint8_t find_xs(const uint8_t* a, const uint8_t* end) {
     return 0;
 }
 
+// ---- 4-bit BAM SEQ -> 2 bits per base (lean batches) ----
+// out[j] holds bases 4j .. 4j+3 (base q at bits 2(q & 3)); anything that is not A/C/G/T becomes 0 and makes the function return true
+// ("look closer": the padding nibble of an odd length also triggers it).
+namespace {
+struct Seq2Lut { uint8_t v[256]; Seq2Lut() { for (int b = 0; b < 256; b++) { auto c2 = [](int nib, bool& bad) { switch (nib) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; default: bad = true; return 0; } };
+                                                                          bool bad = false; const int hi = c2(b >> 4, bad), lo = c2(b & 15, bad); v[b] = (uint8_t)(hi | (lo << 2) | (bad ? 0x80 : 0)); } } };
+const Seq2Lut SEQ2_LUT;
+inline bool seq4_to_2_scalar(const uint8_t* sq, size_t j0, size_t nb4, size_t nb2, uint8_t* o2) {
+    bool any_bad = false;
+    for (size_t j = j0; j < nb2; j++) {
+        const uint8_t a = SEQ2_LUT.v[sq[2 * j]], b2 = (2 * j + 1 < nb4) ? SEQ2_LUT.v[sq[2 * j + 1]] : (uint8_t)0;
+        o2[j] = (uint8_t)((a & 15) | ((b2 & 15) << 4));
+        any_bad |= ((a | b2) & 0x80) != 0;
+    }
+    return any_bad;
+}
+#if defined(__GNUC__) && defined(__x86_64__)
+// 32 bases per step: two nibble look-ups (pshufb), the pairs of 4-bit results folded into bytes with one multiply-add
+__attribute__((target("ssse3"))) bool seq4_to_2_ssse3(const uint8_t* sq, size_t nb4, size_t nb2, uint8_t* o2) {
+    const __m128i lut_code = _mm_setr_epi8(0, 0, 1, 0, 2, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0);
+    const __m128i lut_bad = _mm_setr_epi8((char)0x80, 0, 0, (char)0x80, 0, (char)0x80, (char)0x80, (char)0x80, 0, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80, (char)0x80);
+    const __m128i m4 = _mm_set1_epi8(0x0f), fold = _mm_set1_epi16(0x1001);
+    __m128i bad = _mm_setzero_si128();
+    size_t j = 0;                                              // input byte index
+    for (; j + 16 <= nb4; j += 16) {
+        const __m128i in = _mm_loadu_si128((const __m128i*)(sq + j));
+        const __m128i hi = _mm_and_si128(_mm_srli_epi16(in, 4), m4), lo = _mm_and_si128(in, m4);
+        const __m128i v = _mm_or_si128(_mm_shuffle_epi8(lut_code, hi), _mm_slli_epi16(_mm_shuffle_epi8(lut_code, lo), 2));   // first base | second base << 2
+        bad = _mm_or_si128(bad, _mm_or_si128(_mm_shuffle_epi8(lut_bad, hi), _mm_shuffle_epi8(lut_bad, lo)));
+        const __m128i w = _mm_maddubs_epi16(v, fold);          // v[2k] + 16 * v[2k + 1] in 16-bit lanes
+        _mm_storel_epi64((__m128i*)(o2 + j / 2), _mm_packus_epi16(w, w));
+    }
+    bool any_bad = _mm_movemask_epi8(bad) != 0;
+    any_bad |= seq4_to_2_scalar(sq, j / 2, nb4, nb2, o2);
+    return any_bad;
+}
+const bool HAVE_SSSE3 = __builtin_cpu_supports("ssse3");
+#else
+const bool HAVE_SSSE3 = false;
+inline bool seq4_to_2_ssse3(const uint8_t* sq, size_t nb4, size_t nb2, uint8_t* o2) { return seq4_to_2_scalar(sq, 0, nb4, nb2, o2); }
+#endif
+inline bool seq4_to_2(const uint8_t* sq, size_t nb4, size_t nb2, uint8_t* o2) { return HAVE_SSSE3 ? seq4_to_2_ssse3(sq, nb4, nb2, o2) : seq4_to_2_scalar(sq, 0, nb4, nb2, o2); }
+} // namespace
+
 void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
     BgzfStream s(file_);
     s.seek(task.voff);
     std::vector<uint8_t> rec;
     const int32_t n_ref = (int32_t)hdr_.lens.size();
+    // Lean columns are written through raw pointers into vectors grown in big steps (one capacity check per record instead of one
+    // per push_back — eight per record); the vectors are cut back to the filled length when the task is done, also on an exception.
+    struct LeanCols {
+        ColumnarChunk& o; int64_t n, cap; size_t nc, ccap, ns, scap;
+        int32_t *pos = nullptr, *lq = nullptr, *mtid = nullptr, *mpos = nullptr; uint16_t *flag = nullptr, *ncig = nullptr; uint8_t *mapq = nullptr, *xs = nullptr;
+        uint64_t* name = nullptr; uint32_t* cig = nullptr; uint8_t* seq2 = nullptr;
+        explicit LeanCols(ColumnarChunk& c) : o(c), n(c.n()), cap(c.n()), nc(c.cigar.size()), ccap(nc), ns(c.seq2.size()), scap(ns) {}
+        void size_records(size_t k) {
+            o.pos.resize(k); o.flag.resize(k); o.mapq.resize(k); o.l_qseq.resize(k); o.xs.resize(k); o.n_cigar.resize(k);
+            if (o.keep_mate) { o.mtid.resize(k); o.mpos.resize(k); }
+            if (o.with_names) o.name_code.resize(k);
+        }
+        void grow_records() {
+            cap = std::max<int64_t>(cap * 2, 8192); size_records((size_t)cap);
+            pos = o.pos.data(); flag = o.flag.data(); mapq = o.mapq.data(); lq = o.l_qseq.data(); xs = o.xs.data(); ncig = o.n_cigar.data();
+            mtid = o.mtid.data(); mpos = o.mpos.data(); name = o.name_code.data();
+        }
+        void grow_cigar(size_t need) { ccap = std::max<size_t>(std::max<size_t>(ccap * 2, nc + need), 32768); o.cigar.resize(ccap); cig = o.cigar.data(); }
+        void grow_seq(size_t need) { scap = std::max<size_t>(std::max<size_t>(scap * 2, ns + need), (size_t)1 << 19); o.seq2.resize(scap); seq2 = o.seq2.data(); }
+        ~LeanCols() { if (o.lean) { size_records((size_t)n); o.cigar.resize(nc); o.seq2.resize(ns); } }
+    } L(out);
     for (;;) {
         if (task.end_voff && s.tell() >= task.end_voff) break;   // the records from the gap cut on belong to the next slice
         uint32_t bs;
@@ -390,22 +458,15 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
         const uint8_t* aux = sq + (l_seq + 1) / 2 + l_seq;
         if (out.lean) {
             if (out.runs.empty() || out.runs.back().tid != tid)
-                out.runs.push_back(ColumnarChunk::Run{tid, 0, out.n(), (int64_t)out.cigar.size(), (int64_t)out.seq2.size(), (int64_t)out.seqx_pos.size()});
+                out.runs.push_back(ColumnarChunk::Run{tid, 0, L.n, (int64_t)L.nc, (int64_t)L.ns, (int64_t)out.seqx_pos.size()});
+            if (n_cig > 0xffffu) throw IoError("BAM record with more than 65535 CIGAR operations");
+            if (L.n == L.cap) L.grow_records();
             uint16_t fl = flag;
             if (spliced && l_seq > 0) {
                 // 4-bit BAM SEQ -> 2 bits per base; anything that is not A/C/G/T is stored as 0 and listed as an exception
-                static const struct Lut { uint8_t v[256]; Lut() { for (int b = 0; b < 256; b++) { auto c2 = [](int nib, bool& bad) { switch (nib) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; default: bad = true; return 0; } };
-                                                                                  bool bad = false; const int hi = c2(b >> 4, bad), lo = c2(b & 15, bad); v[b] = (uint8_t)(hi | (lo << 2) | (bad ? 0x80 : 0)); } } } LUT;
-                const size_t nb4 = (size_t)(l_seq + 1) / 2, nb2 = (size_t)(l_seq + 3) / 4, s0 = out.seq2.size();
-                out.seq2.resize(s0 + nb2);
-                uint8_t* o2 = &out.seq2[s0];
-                bool any_bad = false;
-                for (size_t j = 0; j < nb2; j++) {
-                    const uint8_t a = LUT.v[sq[2 * j]], b2 = (2 * j + 1 < nb4) ? LUT.v[sq[2 * j + 1]] : (uint8_t)0;
-                    o2[j] = (uint8_t)((a & 15) | ((b2 & 15) << 4));
-                    any_bad |= ((a | b2) & 0x80) != 0;
-                }
-                if (any_bad) {                                   // rare: list the exact nibbles (the padding nibble of an odd length is not a base)
+                const size_t nb4 = (size_t)(l_seq + 1) / 2, nb2 = (size_t)(l_seq + 3) / 4, s0 = L.ns;
+                if (L.ns + nb2 + 16 > L.scap) L.grow_seq(nb2 + 16);            // the 32-base steps store 8 bytes at a time
+                if (seq4_to_2(sq, nb4, nb2, L.seq2 + s0)) {                    // rare: list the exact nibbles (the padding nibble of an odd length is not a base)
                     bool real = false;
                     for (int32_t q = 0; q < l_seq; q++) {
                         const uint32_t nib = (q & 1) ? (sq[q >> 1] & 15u) : (uint32_t)(sq[q >> 1] >> 4);
@@ -413,19 +474,21 @@ void BamFile::decode(const DecodeTask& task, ColumnarChunk& out) const {
                     }
                     if (real) fl = (uint16_t)(fl | 0x8000u);
                 }
+                L.ns += nb2;
             }
-            out.pos.push_back(pos); out.flag.push_back(fl); out.mapq.push_back(mapq); out.l_qseq.push_back(l_seq);
-            if (out.keep_mate) { out.mtid.push_back(mtid); out.mpos.push_back(mpos); }
-            out.xs.push_back(find_xs(aux, p + bs));
+            const int64_t k = L.n;
+            L.pos[k] = pos; L.flag[k] = fl; L.mapq[k] = mapq; L.lq[k] = l_seq; L.ncig[k] = (uint16_t)n_cig;
+            if (out.keep_mate) { L.mtid[k] = mtid; L.mpos[k] = mpos; }
+            L.xs[k] = find_xs(aux, p + bs);
             if (out.with_names) {
                 size_t ln = l_name; const char* qn = (const char*)p + 32;
                 while (ln && qn[ln - 1] == 0) ln--;
-                out.name_code.push_back(name_code(qn, strnlen(qn, ln), flag));
+                L.name[k] = name_code(qn, strnlen(qn, ln), flag);
             }
-            if (n_cig > 0xffffu) throw IoError("BAM record with more than 65535 CIGAR operations");
-            out.n_cigar.push_back((uint16_t)n_cig);
-            const size_t c0 = out.cigar.size(); out.cigar.resize(c0 + n_cig);
-            if (n_cig) memcpy(&out.cigar[c0], cg, 4ull * n_cig);
+            if (L.nc + n_cig > L.ccap) L.grow_cigar(n_cig);
+            if (n_cig) memcpy(L.cig + L.nc, cg, 4ull * n_cig);
+            L.nc += n_cig;
+            L.n = k + 1;
             continue;
         }
         out.tid.push_back(tid); out.pos.push_back(pos); out.flag.push_back(flag); out.mapq.push_back(mapq);

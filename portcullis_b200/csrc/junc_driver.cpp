@@ -163,6 +163,7 @@ static uint64_t target_weight(const pjh_prep* p, int32_t t) {
 }
 
 int pjh_inflate_selftest(int32_t n_cases) { return pjio::inflate_selftest(n_cases); }
+int pjh_format_selftest(int32_t n_cases) { return pjhost::format_selftest(n_cases); }
 
 int pjh_plan_shards(const pjh_prep* p, int32_t n_gpus, int32_t* gpu_of_target) {
     if (!p || n_gpus < 1 || !gpu_of_target) return fail(PJ_EINVAL, "pjh_plan_shards: bad argument");
@@ -393,6 +394,8 @@ int plan_parts(const pjh_prep* prep, int n_parts, bool whole_targets, uint64_t s
 // rows + per-target scalars of one part (one GPU), before A12/A13
 struct pjh_partial {
     std::vector<pj_junction> rows; std::vector<pj_target_stats> stats; pjh_report rep;
+    std::thread teardown;                  // pj_destroy of the part's context, running while the caller gathers the rows
+    ~pjh_partial() { if (teardown.joinable()) teardown.join(); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -511,6 +514,11 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
     // decoded-but-unsubmitted chunks (pageable): enough for the decode to keep going while a CUDA context is still starting
     const size_t window = std::max<size_t>((size_t)threads * 4 + 2, 192);
     bool first = true;
+    {   // address space for the rows of all segments up front (untouched pages cost nothing): growing the vector segment by segment
+        // copied hundreds of MB of 256-byte rows around on a human-scale run
+        uint64_t recs = 0; for (auto& sg : part) recs += sg.weight;
+        out.rows.reserve((size_t)std::min<uint64_t>(recs / 8 + (1u << 20), 16u << 20));
+    }
     for (const Segment& sg : part) {
         int r;
         if (!first) {                                                  // the first shard was opened by the GPU thread
@@ -558,7 +566,9 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         out.run_s += now_s() - tr;
         float ms = 0; int32_t nl = 0; pj_shard_timing(ctx, &ms, &nl); out.gpu_ms += ms; out.launches += nl; out.n_segments++;
     }
-    if (extra) { out.ctx = ctx; ctx = nullptr; }                       // the extra metrics need every shard's context: destroyed after that phase
+    // The context goes back to the caller: the extra metrics need every shard's context, and without them the caller destroys it on a
+    // helper thread while the rows are finalized and written (freeing ~20 GB of device and pinned memory takes 0.3 s on a human-scale run).
+    out.ctx = ctx; ctx = nullptr;
 }
 
 void merge_stats(std::vector<pj_target_stats>& into, const pj_target_stats* from, int32_t T) {
@@ -722,7 +732,8 @@ int junc_core(const pjh_options* o, int part, int n_parts_in, pjh_partial* parti
     if (rank_mode) {
         GpuOut out;
         run_part(o, prep, parts[(size_t)part], o->gpu_ids ? o->gpu_ids[0] : 0, threads, false, out);
-        if (out.rc) return fail(out.rc, out.err);
+        if (out.rc) { if (out.ctx) pj_destroy(out.ctx); return fail(out.rc, out.err); }
+        if (out.ctx) { pj_ctx* c = out.ctx; out.ctx = nullptr; partial->teardown = std::thread([c]() { pj_destroy(c); }); }
         partial->rows.swap(out.rows); partial->stats.swap(out.stats);
         R.t_gpu_ms = out.gpu_ms; R.n_kernel_launches = out.launches; R.t_genome_s = out.genome_s; R.t_decode_s = out.decode_s; R.t_init_s = out.init_s;
         R.t_run_s = out.run_s; R.t_teardown_s = out.teardown_s; R.n_junctions = (int64_t)partial->rows.size(); R.n_segments = out.n_segments; R.n_gap_cuts = n_cuts;
@@ -744,6 +755,8 @@ int junc_core(const pjh_options* o, int part, int n_parts_in, pjh_partial* parti
     const int n_gpus = n_parts;
     struct CtxGuard { std::vector<GpuOut>& o; ~CtxGuard() { for (auto& x : o) if (x.ctx) { pj_destroy(x.ctx); x.ctx = nullptr; } } } ctx_guard{outs};
     for (auto& out : outs) if (out.rc) return fail(out.rc, out.err);
+    struct Teardown { std::vector<std::thread> th; void join() { for (auto& t : th) if (t.joinable()) t.join(); th.clear(); } ~Teardown() { join(); } } teardown;
+    if (!extra) for (auto& x : outs) if (x.ctx) { pj_ctx* c = x.ctx; x.ctx = nullptr; teardown.th.emplace_back([c]() { pj_destroy(c); }); }
     if (extra) {
         // ---- calcExtraMetrics (junction_builder.cc:293-312) over the records resident on the GPUs ----
         const double tx = now_s();
@@ -807,8 +820,11 @@ int junc_core(const pjh_options* o, int part, int n_parts_in, pjh_partial* parti
     std::vector<pj_junction> rows; std::vector<pj_junction_extra> xrows;
     std::vector<pj_target_stats> stats((size_t)T, pj_target_stats{0, 0, 0, INT32_MAX, 0});
     for (int g = 0; g < n_gpus; g++) {
-        rows.insert(rows.end(), outs[g].rows.begin(), outs[g].rows.end());
-        xrows.insert(xrows.end(), outs[g].extra.begin(), outs[g].extra.end());
+        if (n_gpus == 1) { rows.swap(outs[g].rows); xrows.swap(outs[g].extra); }       // one part: its rows are the table, no second copy
+        else {
+            rows.insert(rows.end(), outs[g].rows.begin(), outs[g].rows.end());
+            xrows.insert(xrows.end(), outs[g].extra.begin(), outs[g].extra.end());
+        }
         merge_stats(stats, outs[g].stats.data(), T);
         R.t_gpu_ms = std::max<double>(R.t_gpu_ms, outs[g].gpu_ms); R.n_kernel_launches += outs[g].launches; R.n_segments += outs[g].n_segments;
         R.t_genome_s = std::max(R.t_genome_s, outs[g].genome_s); R.t_decode_s = std::max(R.t_decode_s, outs[g].decode_s);
@@ -816,6 +832,7 @@ int junc_core(const pjh_options* o, int part, int n_parts_in, pjh_partial* parti
     }
     R.n_gap_cuts = n_cuts;
     if ((rc = finish_rows(o, H, rows, xrows, stats, R))) return rc;
+    { const double tj = now_s(); teardown.join(); R.t_teardown_s += now_s() - tj; }     // what is left of the contexts' teardown after the writers
     R.t_total_s = now_s() - t0;
     if (rep) *rep = R;
     return PJ_OK;

@@ -21,5 +21,6 @@ void write_exon_gff(const std::string& path, const pj_junction* rows, int64_t n,
 void write_intron_gff(const std::string& path, const pj_junction* rows, int64_t n, const std::vector<TargetInfo>& targets,
                       const std::string& source);
 std::string tab_header();
+int format_selftest(int n_cases);      // writers' number formatting against printf; number of differences
 
 } // namespace pjhost

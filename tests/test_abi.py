@@ -92,6 +92,11 @@ def test_fast_inflate_matches_zlib():
     assert L.load().pjh_inflate_selftest(300) == 0
 
 
+def test_writer_number_formatting_equals_printf():
+    # the writers' fast "%g" / "%.3f" / integer paths must print exactly what printf prints (byte-identical tables)
+    assert L.load().pjh_format_selftest(20000) == 0
+
+
 def test_headers_are_plain_c_and_link(tmp_path):
     """include/*.h compile as C99 and a C program can link the library and call it (no C++ or torch types in the ABI)."""
     import subprocess
