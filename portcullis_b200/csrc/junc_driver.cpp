@@ -82,15 +82,20 @@ int ordered_pipeline(size_t n, int threads, size_t window, const std::function<i
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++) pool.emplace_back(worker);
     int rc = PJ_OK;
+    static const bool trace = getenv("PJ_TRACE") != nullptr;
+    double t_wait = 0, t_busy = 0;
     for (size_t k = 0; k < n; k++) {
         std::unique_ptr<Payload> p;
+        const double tw0 = trace ? now_s() : 0;
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return failed || done[k]; });
             if (failed) { rc = fail(fail_code, fail_msg); break; }
             p = std::move(done[k]);
         }
+        const double tw1 = trace ? now_s() : 0;
         rc = consume(k, *p);
+        if (trace) { t_wait += tw1 - tw0; t_busy += now_s() - tw1; }
         { std::lock_guard<std::mutex> lk(mu); consumed = k + 1; if (rc) failed = true; }
         cv.notify_all();
         if (rc) break;
@@ -98,6 +103,7 @@ int ordered_pipeline(size_t n, int threads, size_t window, const std::function<i
     { std::lock_guard<std::mutex> lk(mu); if (rc) failed = true; consumed = n; }
     cv.notify_all();
     for (auto& t : pool) t.join();
+    if (trace) fprintf(stderr, "[pj pipeline] %zu tasks on %d workers: the in-order consumer was busy %.3f s and waited %.3f s for the workers\n", n, threads, t_busy, t_wait);
     return rc;
 }
 
@@ -409,6 +415,14 @@ struct GpuOut {
     int rc = PJ_OK; std::string err;
 };
 
+void merge_stats(std::vector<pj_target_stats>& into, const pj_target_stats* from, int32_t T) {
+    for (int32_t t = 0; t < T; t++) {
+        pj_target_stats& a = into[(size_t)t]; const pj_target_stats& b = from[t];
+        a.spliced_count += b.spliced_count; a.unspliced_count += b.unspliced_count; a.sum_query_lengths += b.sum_query_lengths;
+        a.min_query_length = std::min(a.min_query_length, b.min_query_length); a.max_query_length = std::max(a.max_query_length, b.max_query_length);
+    }
+}
+
 // One GPU: CUDA context + library context + genome of the part's targets, then the part's segments one after the other
 // (decode workers -> pinned staging -> H2D -> pj_shard_run -> rows appended).  `device` is the CUDA ordinal.
 void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device, int threads, bool extra, GpuOut& out) {
@@ -441,20 +455,49 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         { std::lock_guard<std::mutex> lk(gm); ready = true; gpu_rc = r; gpu_err = em; }
         gcv.notify_all();
         if (r) return;
-        // genome: only this part's targets become resident on this GPU (own CUDA stream; overlaps the batch submission)
+        // genome: only this part's targets become resident on this GPU (own CUDA stream; overlaps the batch submission).  Reading a
+        // target out of the FASTA file (line by line, faidx semantics) is host work of about 1 s per Gb on one thread, slower than the
+        // decode workers cover the genome on a human-scale run: a few parser threads read ahead, this thread uploads in target order.
         const double tg = now_s();
-        std::string seq;
         auto done = [&](int32_t t, int code, const std::string& msg) {
             { std::lock_guard<std::mutex> lk(gm); if (t >= 0) genome_done[(size_t)t] = 1; if (code) { genome_rc = code; genome_err = msg; } if (t < 0 || code) genome_finished = true; }
             gcv.notify_all();
         };
-        for (int32_t t : my_targets) {                                 // ascending = the order the segments need them
-            if (prep->indexed && prep->bam.index()[(size_t)t].first_voff == 0) { done(t, PJ_OK, ""); continue; }   // no records -> no junctions -> no genome needed
-            const pjio::FaiEntry* e = prep->fasta.find(H.names[t]);
-            if (!e) { done(t, PJ_OK, ""); continue; }
-            try { prep->fasta.fetch_all(*e, seq); } catch (const std::exception& ex) { done(t, PJ_EIO, ex.what()); return; }
-            int q = pj_genome_set_target(ctx, t, seq.data(), (int64_t)seq.size());
-            if (q) { done(t, q, pj_last_error(ctx)); return; }
+        const size_t nt = my_targets.size();
+        std::vector<std::string> seqs(nt); std::vector<char> state(nt, 0);         // 0 not parsed, 1 parsed, 2 nothing to load, 3 failed
+        std::vector<std::string> perr(nt);
+        std::mutex pm; std::condition_variable pcv; std::atomic<size_t> pnext{0}; size_t uploaded = 0; bool pstop = false;
+        const int n_parsers = (int)std::min<size_t>(nt, (size_t)std::max(1, std::min(3, threads / 4)));
+        std::vector<std::thread> parsers;
+        for (int w = 0; w < n_parsers; w++) parsers.emplace_back([&]() {
+            for (;;) {
+                const size_t i = pnext.fetch_add(1);
+                if (i >= nt) return;
+                { std::unique_lock<std::mutex> lk(pm); pcv.wait(lk, [&] { return pstop || i < uploaded + 4; }); if (pstop) return; }   // at most four targets in host memory
+                const int32_t t = my_targets[i];
+                char st = 1; std::string msg;
+                const pjio::FaiEntry* e = nullptr;
+                if (prep->indexed && prep->bam.index()[(size_t)t].first_voff == 0) st = 2;       // no records -> no junctions -> no genome needed
+                else if (!(e = prep->fasta.find(H.names[t]))) st = 2;
+                else { try { prep->fasta.fetch_all(*e, seqs[i]); } catch (const std::exception& ex) { st = 3; msg = ex.what(); } }
+                { std::lock_guard<std::mutex> lk(pm); state[i] = st; perr[i] = msg; }
+                pcv.notify_all();
+            }
+        });
+        struct JoinParsers { std::vector<std::thread>& th; std::mutex& m; std::condition_variable& cv; bool& stop;
+                             ~JoinParsers() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); for (auto& t : th) if (t.joinable()) t.join(); } } join_parsers{parsers, pm, pcv, pstop};
+        for (size_t i = 0; i < nt; i++) {                                  // ascending = the order the segments need them
+            const int32_t t = my_targets[i];
+            char st;
+            { std::unique_lock<std::mutex> lk(pm); pcv.wait(lk, [&] { return state[i] != 0; }); st = state[i]; }
+            if (st == 3) { done(t, PJ_EIO, perr[i]); return; }
+            if (st == 1) {
+                int q = pj_genome_set_target(ctx, t, seqs[i].data(), (int64_t)seqs[i].size());
+                if (q) { done(t, q, pj_last_error(ctx)); return; }
+                std::string().swap(seqs[i]);
+            }
+            { std::lock_guard<std::mutex> lk(pm); uploaded = i + 1; }
+            pcv.notify_all();
             done(t, PJ_OK, "");
         }
         out.genome_s = now_s() - tg;
@@ -468,6 +511,23 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
     // copy one decoded chunk into a pinned staging buffer of the context
     const bool lean = prep->indexed;                                   // a decode task of an indexed BAM lies on one target: the lean batch form applies
     const bool keep_mate = o->orientation == PJ_ORIENT_FR || o->orientation == PJ_ORIENT_RF || o->orientation == PJ_ORIENT_FF;
+    // The copy of a decoded chunk into pinned staging is the one serial step of the pipeline (12 GB on a human-scale run): it is cut
+    // into 1 MB pieces that a few short-lived helper threads copy together with this thread.
+    const int copy_helpers = threads >= 8 ? 3 : threads >= 4 ? 1 : 0;
+    struct Piece { void* d; const void* s; size_t n; };
+    std::vector<Piece> pieces;
+    auto add_copy = [&](const void* dst, const void* src, size_t n) {
+        for (size_t off = 0; off < n; off += (size_t)1 << 20) pieces.push_back(Piece{(char*)const_cast<void*>(dst) + off, (const char*)src + off, std::min<size_t>((size_t)1 << 20, n - off)});
+    };
+    auto run_copies = [&]() {
+        std::atomic<size_t> next{0};
+        auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= pieces.size()) return; memcpy(pieces[k].d, pieces[k].s, pieces[k].n); } };
+        std::vector<std::thread> th;
+        if (pieces.size() > 2) for (int h = 0; h < copy_helpers; h++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        pieces.clear();
+    };
     auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
         if (ch.lean) {
             // about half the bytes of the classic form cross PCIe: no tid / cigar_off / seq_off columns (formed on the device), SEQ at
@@ -476,12 +536,13 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
             int q = pj_staging_acquire_lean(ctx, ch.n(), (int64_t)ch.cigar.size(), (int64_t)ch.seq2.size(), (int64_t)ch.seqx_pos.size(), &st);
             if (q) return fail(q, pj_last_error(ctx));
             const size_t n = (size_t)ch.n();
-            memcpy((void*)st.pos, ch.pos.data(), n * 4); memcpy((void*)st.flag, ch.flag.data(), n * 2); memcpy((void*)st.mapq, ch.mapq.data(), n);
-            memcpy((void*)st.xs, ch.xs.data(), n); memcpy((void*)st.l_qseq, ch.l_qseq.data(), n * 4); memcpy((void*)st.n_cigar, ch.n_cigar.data(), n * 2);
-            if (keep_mate) { memcpy((void*)st.mtid, ch.mtid.data(), n * 4); memcpy((void*)st.mpos, ch.mpos.data(), n * 4); } else { st.mtid = nullptr; st.mpos = nullptr; }
-            memcpy((void*)st.cigar, ch.cigar.data(), ch.cigar.size() * 4); memcpy((void*)st.seq2, ch.seq2.data(), ch.seq2.size());
-            if (!ch.seqx_pos.empty()) { memcpy((void*)st.seqx_pos, ch.seqx_pos.data(), ch.seqx_pos.size() * 8); memcpy((void*)st.seqx_code, ch.seqx_code.data(), ch.seqx_code.size()); }
-            if (extra) memcpy((void*)st.name_code, ch.name_code.data(), n * 8);
+            add_copy(st.pos, ch.pos.data(), n * 4); add_copy(st.flag, ch.flag.data(), n * 2); add_copy(st.mapq, ch.mapq.data(), n);
+            add_copy(st.xs, ch.xs.data(), n); add_copy(st.l_qseq, ch.l_qseq.data(), n * 4); add_copy(st.n_cigar, ch.n_cigar.data(), n * 2);
+            if (keep_mate) { add_copy(st.mtid, ch.mtid.data(), n * 4); add_copy(st.mpos, ch.mpos.data(), n * 4); } else { st.mtid = nullptr; st.mpos = nullptr; }
+            add_copy(st.cigar, ch.cigar.data(), ch.cigar.size() * 4); add_copy(st.seq2, ch.seq2.data(), ch.seq2.size());
+            if (!ch.seqx_pos.empty()) { add_copy(st.seqx_pos, ch.seqx_pos.data(), ch.seqx_pos.size() * 8); add_copy(st.seqx_code, ch.seqx_code.data(), ch.seqx_code.size()); }
+            if (extra) add_copy(st.name_code, ch.name_code.data(), n * 8);
+            run_copies();
             st.n_records = ch.n(); st.const_tid = ch.runs[0].tid; st.n_cigar_total = (int64_t)ch.cigar.size(); st.n_seq2_bytes = (int64_t)ch.seq2.size();
             st.n_seqx = (int64_t)ch.seqx_pos.size();
             return PJ_OK;
@@ -519,65 +580,88 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         uint64_t recs = 0; for (auto& sg : part) recs += sg.weight;
         out.rows.reserve((size_t)std::min<uint64_t>(recs / 8 + (1u << 20), 16u << 20));
     }
-    for (const Segment& sg : part) {
+    // ONE ordered pipeline over the decode tasks of all segments: when the last task of a segment has been submitted the consumer runs
+    // the shard (a few ms of GPU time + the row fetch) and opens the next one, while the workers keep decoding ahead into the window.
+    // (One pipeline per segment left the workers idle through every run + fetch and through the ramp-up and tail of every segment.)
+    std::vector<const DecodeTask*> all; std::vector<size_t> seg_end;
+    for (const Segment& sg : part) { for (const DecodeTask& t : sg.tasks) all.push_back(&t); seg_end.push_back(all.size()); }
+    size_t cur = 0;                                                    // segment being filled
+    auto finish_segment = [&](const Segment& sg) -> int {
         int r;
-        if (!first) {                                                  // the first shard was opened by the GPU thread
-            if ((r = pj_shard_begin(ctx, (int64_t)sg.weight + 1024, (int64_t)sg.weight * 4 + 1024, (int64_t)sg.weight * 56 + 1024))) return bail(r, pj_last_error(ctx));
-        }
-        const double td = now_s();
-        r = ordered_pipeline<Payload>(sg.tasks.size(), threads, window,
-            [&](size_t k, Payload& p) -> int {
-                p.chunk = pool.get();
-                p.chunk->with_names = extra; p.chunk->lean = lean; p.chunk->keep_mate = keep_mate;
-                prep->bam.decode(sg.tasks[k], *p.chunk);
-                return PJ_OK;
-            },
-            [&](size_t, Payload& p) -> int {
-                int q = PJ_OK;
-                if (p.chunk->n() > 0) {
-                    if ((q = wait_ready())) return fail(q, gpu_err);
-                    pj_batch st; memset(&st, 0, sizeof st);
-                    if ((q = stage(*p.chunk, st))) return q;
-                    if ((q = pj_batch_submit(ctx, &st))) q = fail(q, pj_last_error(ctx));
-                }
-                pool.put(std::move(p.chunk));
-                return q;
-            });
-        if (r) { wait_ready(); return bail(r, g_err); }
-        out.decode_s += now_s() - td;
-        if (first) { if ((r = wait_ready())) return bail(r, gpu_err); first = false; }
+        if (first) { if ((r = wait_ready())) return fail(r, gpu_err); first = false; }
         {   // the genome of this segment's targets must be resident; later targets keep uploading under the next segments' decode
             std::unique_lock<std::mutex> lk(gm);
             gcv.wait(lk, [&] { if (genome_rc || genome_finished) return true; for (int32_t t : sg.targets) if (!genome_done[(size_t)t]) return false; return true; });
-            if (genome_rc) return bail(genome_rc, genome_err);
+            if (genome_rc) return fail(genome_rc, genome_err);
         }
         const double tr = now_s();
-        if ((r = pj_shard_run(ctx))) return bail(r, pj_last_error(ctx));
+        if ((r = pj_shard_run(ctx))) return fail(r, pj_last_error(ctx));
         const int64_t J = pj_shard_num_junctions(ctx);
         const size_t base = out.rows.size();
         out.rows.resize(base + (size_t)J);
         std::vector<pj_target_stats> st((size_t)T);
-        if ((r = pj_shard_fetch(ctx, out.rows.data() + base, J, st.data(), T))) return bail(r, pj_last_error(ctx));
-        for (int32_t t = 0; t < T; t++) {                              // a target may be spread over several segments
-            pj_target_stats& a = out.stats[(size_t)t]; const pj_target_stats& b = st[(size_t)t];
-            a.spliced_count += b.spliced_count; a.unspliced_count += b.unspliced_count; a.sum_query_lengths += b.sum_query_lengths;
-            a.min_query_length = std::min(a.min_query_length, b.min_query_length); a.max_query_length = std::max(a.max_query_length, b.max_query_length);
-        }
+        if ((r = pj_shard_fetch(ctx, out.rows.data() + base, J, st.data(), T))) return fail(r, pj_last_error(ctx));
+        merge_stats(out.stats, st.data(), T);                          // a target may be spread over several segments
         out.run_s += now_s() - tr;
         float ms = 0; int32_t nl = 0; pj_shard_timing(ctx, &ms, &nl); out.gpu_ms += ms; out.launches += nl; out.n_segments++;
-    }
+        return PJ_OK;
+    };
+    auto open_segment = [&](const Segment& sg) -> int {                // the first shard was opened by the GPU thread
+        int r = pj_shard_begin(ctx, (int64_t)sg.weight + 1024, (int64_t)sg.weight * 4 + 1024, (int64_t)sg.weight * 56 + 1024);
+        return r ? fail(r, pj_last_error(ctx)) : PJ_OK;
+    };
+    // segments without a decode task at the front of the part
+    auto drain_empty = [&]() -> int {
+        while (cur < part.size() && seg_end[cur] == (cur ? seg_end[cur - 1] : 0)) {
+            int r;
+            if ((r = wait_ready())) return fail(r, gpu_err);
+            if (cur > 0 && (r = open_segment(part[cur]))) return r;
+            if ((r = finish_segment(part[cur]))) return r;
+            cur++;
+        }
+        return PJ_OK;
+    };
+    const double td = now_s();
+    int r = drain_empty();
+    if (r) { wait_ready(); return bail(r, g_err); }
+    bool opened = true;                                                // is the shard of segment `cur` open?  (segment 0: by the GPU thread)
+    if (cur > 0) opened = false;
+    r = ordered_pipeline<Payload>(all.size(), threads, window,
+        [&](size_t k, Payload& p) -> int {
+            p.chunk = pool.get();
+            p.chunk->with_names = extra; p.chunk->lean = lean; p.chunk->keep_mate = keep_mate;
+            prep->bam.decode(*all[k], *p.chunk);
+            return PJ_OK;
+        },
+        [&](size_t k, Payload& p) -> int {
+            int q = PJ_OK;
+            if ((q = wait_ready())) return fail(q, gpu_err);
+            if (!opened) { if ((q = open_segment(part[cur]))) return q; opened = true; }
+            if (p.chunk->n() > 0) {
+                pj_batch st; memset(&st, 0, sizeof st);
+                if ((q = stage(*p.chunk, st))) return q;
+                if ((q = pj_batch_submit(ctx, &st))) return fail(q, pj_last_error(ctx));
+            }
+            pool.put(std::move(p.chunk));
+            if (k + 1 == seg_end[cur]) {                               // the segment is complete
+                if ((q = finish_segment(part[cur]))) return q;
+                cur++; opened = false;
+                // the following segments that have no task at all
+                while (cur < part.size() && seg_end[cur] == seg_end[cur - 1]) {
+                    if ((q = open_segment(part[cur]))) return q;
+                    if ((q = finish_segment(part[cur]))) return q;
+                    cur++;
+                }
+            }
+            return q;
+        });
+    if (r) { wait_ready(); return bail(r, g_err); }
+    out.decode_s = now_s() - td - out.run_s;
     // The context goes back to the caller: the extra metrics need every shard's context, and without them the caller destroys it on a
     // helper thread while the rows are finalized and written (freeing ~20 GB of device and pinned memory takes 0.3 s on a human-scale run).
     out.ctx = ctx; ctx = nullptr;
 }
 
-void merge_stats(std::vector<pj_target_stats>& into, const pj_target_stats* from, int32_t T) {
-    for (int32_t t = 0; t < T; t++) {
-        pj_target_stats& a = into[(size_t)t]; const pj_target_stats& b = from[t];
-        a.spliced_count += b.spliced_count; a.unspliced_count += b.unspliced_count; a.sum_query_lengths += b.sum_query_lengths;
-        a.min_query_length = std::min(a.min_query_length, b.min_query_length); a.max_query_length = std::max(a.max_query_length, b.max_query_length);
-    }
-}
 
 // A12/A13 + writers + strand report over the gathered rows (junction_builder.cc:249-290, junction_system.cc:250-383, 455-560)
 int finish_rows(const pjh_options* o, const pjio::BamHeader& H, std::vector<pj_junction>& rows, std::vector<pj_junction_extra>& xrows,

@@ -101,6 +101,7 @@ struct pj_ctx {
     pjapi::DevBuf<uint8_t> tmp_seq4; pjapi::DevBuf<uint64_t> tmp_off4; pjapi::DevBuf<uint32_t> tmp_xcount, tmp_xoff, tmp_scan; pjapi::DevBuf<uint16_t> tmp_ncig;
     pjapi::DevBuf<unsigned long long> tmp_fs;
     std::vector<pjapi::StagingSlot*> slots; int max_slots = 4; uint64_t submit_seq = 0;
+    int64_t slot_floor[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};   // [classic | lean][records, CIGAR words, SEQ bytes, exceptions]: largest capacities any slot was given
     pjapi::TempArena arena;             // temporaries of pj_shard_run
     std::thread prewarm_thread;         // sizes the arena while the caller is still decoding
     double t_pinned_alloc_s = 0; size_t pinned_alloc_bytes = 0; int n_pinned_allocs = 0;   // PJ_TRACE: cost of growing the staging pool
