@@ -457,7 +457,7 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         if (r) return;
         // genome: only this part's targets become resident on this GPU (own CUDA stream; overlaps the batch submission).  Reading a
         // target out of the FASTA file (line by line, faidx semantics) is host work of about 1 s per Gb on one thread, slower than the
-        // decode workers cover the genome on a human-scale run: a few parser threads read ahead, this thread uploads in target order.
+        // decode workers cover the genome on a human-scale run: two parser threads read ahead, this thread uploads in target order.
         const double tg = now_s();
         auto done = [&](int32_t t, int code, const std::string& msg) {
             { std::lock_guard<std::mutex> lk(gm); if (t >= 0) genome_done[(size_t)t] = 1; if (code) { genome_rc = code; genome_err = msg; } if (t < 0 || code) genome_finished = true; }
@@ -467,7 +467,7 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
         std::vector<std::string> seqs(nt); std::vector<char> state(nt, 0);         // 0 not parsed, 1 parsed, 2 nothing to load, 3 failed
         std::vector<std::string> perr(nt);
         std::mutex pm; std::condition_variable pcv; std::atomic<size_t> pnext{0}; size_t uploaded = 0; bool pstop = false;
-        const int n_parsers = (int)std::min<size_t>(nt, (size_t)std::max(1, std::min(3, threads / 4)));
+        const int n_parsers = (int)std::min<size_t>(nt, (size_t)std::max(1, std::min(2, threads / 4)));
         std::vector<std::thread> parsers;
         for (int w = 0; w < n_parsers; w++) parsers.emplace_back([&]() {
             for (;;) {
@@ -511,23 +511,10 @@ void run_part(const pjh_options* o, pjh_prep* prep, const Part& part, int device
     // copy one decoded chunk into a pinned staging buffer of the context
     const bool lean = prep->indexed;                                   // a decode task of an indexed BAM lies on one target: the lean batch form applies
     const bool keep_mate = o->orientation == PJ_ORIENT_FR || o->orientation == PJ_ORIENT_RF || o->orientation == PJ_ORIENT_FF;
-    // The copy of a decoded chunk into pinned staging is the one serial step of the pipeline (12 GB on a human-scale run): it is cut
-    // into 1 MB pieces that a few short-lived helper threads copy together with this thread.
-    const int copy_helpers = threads >= 8 ? 3 : threads >= 4 ? 1 : 0;
-    struct Piece { void* d; const void* s; size_t n; };
-    std::vector<Piece> pieces;
-    auto add_copy = [&](const void* dst, const void* src, size_t n) {
-        for (size_t off = 0; off < n; off += (size_t)1 << 20) pieces.push_back(Piece{(char*)const_cast<void*>(dst) + off, (const char*)src + off, std::min<size_t>((size_t)1 << 20, n - off)});
-    };
-    auto run_copies = [&]() {
-        std::atomic<size_t> next{0};
-        auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= pieces.size()) return; memcpy(pieces[k].d, pieces[k].s, pieces[k].n); } };
-        std::vector<std::thread> th;
-        if (pieces.size() > 2) for (int h = 0; h < copy_helpers; h++) th.emplace_back(work);
-        work();
-        for (auto& t : th) t.join();
-        pieces.clear();
-    };
+    // The copy of a decoded chunk into pinned staging stays on this thread.  (Splitting it over short-lived helper threads was measured
+    // on the 16-core box: with every core busy decoding, waiting for the helpers to be scheduled cost more than the copy, +1 s on c3.)
+    auto add_copy = [&](const void* dst, const void* src, size_t n) { if (n) memcpy(const_cast<void*>(dst), src, n); };
+    auto run_copies = [&]() {};
     auto stage = [&](const ColumnarChunk& ch, pj_batch& st) -> int {
         if (ch.lean) {
             // about half the bytes of the classic form cross PCIe: no tid / cigar_off / seq_off columns (formed on the device), SEQ at

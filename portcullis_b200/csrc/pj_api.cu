@@ -55,7 +55,7 @@ int alloc_slot(pj_ctx* c, StagingSlot& s, bool lean, int64_t cr, int64_t cc, int
     // entries was re-allocated as a whole: 15 allocations = 0.85 s on a full-size c3 run).  What one slot had to grow to is the floor of the
     // context's other slots.
     if (s.lean == lean) { cr = std::max(cr + cr / 2, s.cap_rec); cc = std::max(cc + cc / 2, s.cap_cig); cs = std::max(cs + cs / 2, s.cap_seq); cx = std::max(cx * 2, s.cap_seqx); }
-    cr = std::max<int64_t>(cr, 384 << 10); cc = std::max<int64_t>(cc, 3 << 19); cs = std::max<int64_t>(cs, lean ? (12 << 20) : (24 << 20)); cx = std::max<int64_t>(cx, 64 << 10);   // ~29 MB per lean slot: room for the 2-3x larger-than-average decode tasks of a dense region
+    cr = std::max<int64_t>(cr, 384 << 10); cc = std::max<int64_t>(cc, 3 << 19); cs = std::max<int64_t>(cs, lean ? (12 << 20) : (24 << 20)); cx = std::max<int64_t>(cx, 512 << 10);   // ~34 MB per lean slot: room for the 2-3x larger-than-average decode tasks of a dense region
     int64_t* hw = c->slot_floor[lean ? 1 : 0];
     cr = hw[0] = std::max(cr, hw[0]); cc = hw[1] = std::max(cc, hw[1]); cs = hw[2] = std::max(cs, hw[2]); cx = hw[3] = std::max(cx, hw[3]);
     free_slot(s);
