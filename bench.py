@@ -223,7 +223,18 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device visible; the junc path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     all_cores = host_cores()
     cores = max(1, all_cores // world)
     numa = bind_to_gpu_numa(local) if world > 1 else {"node": None, "cpus": None}
