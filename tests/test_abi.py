@@ -86,6 +86,30 @@ def test_host_finalize_edge_cases():
     assert one["mean_readlen"][0] == 0 and one["uniq_junc"][0] == 0
 
 
+def test_host_finalize_parallel_sweep_equals_the_pairwise_walk():
+    """A12/A13 on the host is one parallel sweep with per-row closed forms of the reference's pair-by-pair walk (junction_system.cc:250-320);
+    the oracle restates the walk itself.  Large random tables (several host threads, groups that straddle thread ranges, many
+    single-junction targets, target changes next to the ends) must come out byte-identical, sorted or not on entry."""
+    from portcullis_b200 import junction_builder as jb
+    import oracle_binding as ob
+    rng = np.random.default_rng(7)
+    for n, n_targets, span in ((200_000, 7, 60_000), (150_001, 40_000, 500), (70_000, 3, 2_000_000), (5, 5, 100), (3, 1, 50)):
+        tid = rng.integers(0, n_targets, n)
+        start = rng.integers(10, span, n)
+        length = rng.integers(1, 40, n) * 10
+        key = (tid.astype(np.int64) << 44) | (start.astype(np.int64) << 20) | length
+        _, first = np.unique(key, return_index=True)                     # junction keys are unique
+        r = np.zeros(len(first), dtype=L.JUNCTION_DTYPE)
+        r["tid"], r["start"], r["end"] = tid[first], start[first], (start + length)[first]
+        r["nb_raw_aln"] = rng.integers(1, 50, len(r)); r["nb_rel_aln"] = rng.integers(0, 50, len(r)) % (r["nb_raw_aln"] + 1)
+        r["nb_mismatches"] = rng.integers(0, 200, len(r)); r["maxmmes"] = rng.integers(0, 60, len(r)); r["suspicious"] = rng.integers(0, 2, len(r))
+        order = np.lexsort((r["end"], r["start"], r["tid"]))
+        for rows in (r[order], r[rng.permutation(len(r))]):
+            a = jb.finalize(rows.copy(), 151.25)
+            b = ob.finalize(rows.copy(), 151.25)
+            assert a.tobytes() == b.tobytes()
+
+
 def test_fast_inflate_matches_zlib():
     """The built-in DEFLATE decoder used for BGZF blocks agrees with zlib on 300 synthetic streams (random, DNA-like,
     run-heavy, LZ-heavy, all-zero data; stored / fixed / dynamic blocks; several strategies)."""

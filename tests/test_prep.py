@@ -195,3 +195,25 @@ def test_force_resort_does_not_touch_the_input_index(tmp_path):
     a = jb.PrepDir(str(tmp_path / "o")).decode(-1, 2)
     b = synth.to_columns(ds)
     assert len(a["pos"]) == len(b["pos"]) and np.array_equal(np.sort(a["pos"]), np.sort(b["pos"]))
+
+
+def test_genome_fetch_block_path_equals_faidx_semantics(tmp_path):
+    """FastaFile::fetch_all copies whole blocks of regular lines (thousands of lines per block) and falls back to the line loop for
+    the tail: 60 / 70 / 61-column records, a CRLF record, a record that ends on a partial line, one shorter than a block."""
+    if not os.path.exists(ob.BAMTOOL):
+        pytest.skip("oracle/_ref not built")
+    ds = synth.make_dataset(53, n_targets=5, target_len=4000, genes_per_target=1)
+    _, bams = write_inputs(ds, str(tmp_path / "in"))
+    rng = random.Random(5)
+    seqs, text = [], []
+    for name, (width, n_bases, eol) in zip(ds["names"], ((60, 60 * 6000 + 17, "\n"), (70, 70 * 5000, "\r\n"), (61, 61 * 4100 + 60, "\n"), (60, 60 * 2048, "\n"), (80, 333, "\n"))):
+        sq = "".join(rng.choice("ACGTNacgtn") for _ in range(n_bases))
+        seqs.append(sq)
+        text.append(">" + name + eol + eol.join(sq[k:k + width] for k in range(0, n_bases, width)) + eol)
+    fa = tmp_path / "wide.fa"
+    fa.write_bytes("".join(text).encode())
+    jb.Prepare(str(tmp_path / "o")).prepare(bams, str(fa))
+    p = jb.PrepDir(str(tmp_path / "o"))
+    for t, sq in enumerate(seqs):
+        assert p.genome(t) == sq.encode(), "target %d" % t
+    p.close()
