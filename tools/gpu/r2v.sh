@@ -1,4 +1,5 @@
 #!/bin/bash
+# round 2, GPU call V: bisect of the stalled first steps (tools/stall_probe.py with PJ_TRACE_HOST=1), then bench traces and the GPU tests with the arena allocator
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export PJ_TRACE_HOST=1
