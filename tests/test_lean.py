@@ -174,3 +174,34 @@ def test_lean_batches_with_exceptions_match_oracle(tmp_path, seed):
     rows, st = _gpu_rows(lambda g: [g.submit_lean(r) for r in runs], p.lengths, genomes)
     assert_rows_equal(rows, exp, "lean vs oracle")
     assert np.array_equal(st["spliced"], exp_st["spliced"])
+
+
+def test_lean_seq_repack_at_block_boundaries(tmp_path):
+    """The 4-bit -> 2-bit SEQ repack works 32 bases at a time (SSSE3) with a scalar tail: read lengths on every side of the 32- and
+    4-base boundaries, odd lengths (padding nibble), N / IUPAC bases in the first, last and boundary positions, all-N reads."""
+    import random
+    import oracle_binding as ob
+    import refrun
+    if not os.path.exists(ob.BAMTOOL):
+        pytest.skip("oracle/_ref/bamtool not built")
+    rng = random.Random(3)
+    genome = "".join(rng.choice("ACGT") for _ in range(60000)).encode()
+    recs, pos = [], 100
+    for l in [2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 30, 31, 32, 33, 34, 35, 36, 47, 48, 49, 63, 64, 65, 66, 95, 96, 97, 127, 128, 129, 160, 161, 255, 256, 257, 1001]:
+        for variant in range(4):
+            seq = [rng.choice("ACGT") for _ in range(l)]
+            if variant == 1:
+                for q in (0, l - 1, 15, 16, 31, 32, 33, 63, 64):
+                    if q < l:
+                        seq[q] = rng.choice("NRYKMSWBDHV")
+            if variant == 2:
+                seq = ["N"] * l
+            if variant == 3 and l > 40:
+                seq[rng.randrange(32, l)] = "N"                   # only in the scalar tail or a later block
+            a = max(1, l // 2)
+            recs.append(dict(name="r%d_%d" % (l, variant), flag=0, tid=0, pos=pos, mapq=60, cigar="%dM200N%dM" % (a, l - a) if l - a > 0 else "%dM" % a,
+                             mtid=-1, mpos=-1, seq="".join(seq), xs="+"))
+            pos += 7
+    ds = dict(names=["chr1"], lengths=np.array([len(genome)], dtype=np.int32), genomes=[genome], records=recs)
+    n_exc = _check_lean_equals_classic(refrun.make_prep_dir(ds, str(tmp_path / "edges")), keep_mate=False)
+    assert n_exc > 100
