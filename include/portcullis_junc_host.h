@@ -54,7 +54,7 @@ typedef struct pjh_report {
     int32_t n_kernel_launches;
     double  t_init_s;            /* CUDA context + pj_create + pj_targets_set (max over GPUs)     */
     double  t_run_s;             /* wall time of pj_shard_run + pj_shard_fetch (max over GPUs)    */
-    double  t_teardown_s;        /* pj_destroy                                                    */
+    double  t_teardown_s;        /* pj_destroy: what is left of it after the writers (it runs on a helper thread under them) */
     double  t_extra_s;           /* --extra: name exchange + pj_extra_run + coverage (0 otherwise) */
     double  t_separate_s;        /* --separate: splitting + indexing the BAM on the host (0 otherwise) */
     int32_t n_segments;          /* shards run (pj_shard_begin ... pj_shard_fetch), summed over GPUs    */
@@ -79,7 +79,8 @@ typedef struct pjh_partial pjh_partial;
 int     pjh_junc_run_part(const pjh_options* opt, int32_t part, int32_t n_parts, pjh_partial** out, pjh_report* report);
 int64_t pjh_partial_rows(const pjh_partial* p, const pj_junction** rows);          /* returns the row count               */
 int32_t pjh_partial_stats(const pjh_partial* p, const pj_target_stats** stats);    /* returns n_targets; one entry each   */
-void    pjh_partial_free(pjh_partial* p);
+void    pjh_partial_free(pjh_partial* p);                                            /* must be called: it also waits for the part's GPU context, which
+                                                                                    * is torn down on a helper thread while the caller gathers the rows */
 /* rows[n_rows]: the parts' rows concatenated in part order (finalized in place); stats[n_targets]: per-target scalars summed
  * over the parts (counts and sums added, min/max combined; a part that saw no record of a target reports min = INT32_MAX). */
 int     pjh_junc_finish(const pjh_options* opt, pj_junction* rows, int64_t n_rows, const pj_target_stats* stats, int32_t n_targets,
